@@ -1,0 +1,164 @@
+"""ctypes binding of oracle/libbp_oracle.so (ORACLE — test infrastructure only).
+
+Mirrors the slice of the pymunk API the reference environments call
+(reference call sites: ship_ice_env.py:117-120,218-219,280-281; sim_utils.py:136-153; ship.py:77-98).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+DYNAMIC, KINEMATIC, STATIC = 0, 1, 2
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libbp_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("chipmunk_oracle.cpp", "spfa_oracle.cpp")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "libbp_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        dp = C.POINTER(C.c_double)
+        L.cpo_space_new.restype = C.c_void_p
+        L.cpo_space_free.argtypes = [C.c_void_p]
+        L.cpo_space_set.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.cpo_space_set_order.argtypes = [C.c_void_p, C.c_int]
+        L.cpo_body_new.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.cpo_poly_new.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, C.c_double]
+        L.cpo_shape_set_mass.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.cpo_shape_set_density.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.cpo_shape_set_material.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int]
+        L.cpo_poly_centroid.argtypes = [C.c_int, dp, dp]
+        L.cpo_shape_count.argtypes = [C.c_void_p, C.c_int]
+        L.cpo_shape_get_verts.argtypes = [C.c_void_p, C.c_int, dp]
+        L.cpo_shape_get_mass.argtypes = [C.c_void_p, C.c_int, dp]
+        L.cpo_body_set_velocity.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.cpo_body_set_angular_velocity.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.cpo_body_get.argtypes = [C.c_void_p, C.c_int, dp]
+        L.cpo_num_bodies.argtypes = [C.c_void_p]
+        L.cpo_get_state.argtypes = [C.c_void_p, dp]
+        L.cpo_step.argtypes = [C.c_void_p, C.c_double]
+        L.cpo_shipice_substeps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.cpo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.cpo_reset_stats.argtypes = [C.c_void_p]
+        L.cpo_get_arbiters.argtypes = [C.c_void_p, dp, C.c_int]
+        L.spfa_oracle.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Space:
+    """pymunk.Space restricted to what the 2D envs use."""
+
+    def __init__(self, iterations=10, damping=1.0, gravity=(0.0, 0.0)):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.cpo_space_new())
+        self.L.cpo_space_set(self.h, int(iterations), float(damping), float(gravity[0]), float(gravity[1]))
+
+    def __del__(self):
+        try:
+            self.L.cpo_space_free(self.h)
+        except Exception:
+            pass
+
+    def set_order(self, mode):
+        self.L.cpo_space_set_order(self.h, int(mode))
+
+    def add_body(self, body_type, x, y, angle):
+        return self.L.cpo_body_new(self.h, body_type, float(x), float(y), float(angle))
+
+    def add_poly(self, body, verts, radius):
+        v = np.ascontiguousarray(verts, dtype=np.float64)
+        return self.L.cpo_poly_new(self.h, body, v.shape[0], _dp(v), float(radius))
+
+    def set_density(self, shape, rho):
+        self.L.cpo_shape_set_density(self.h, shape, float(rho))
+
+    def set_mass(self, shape, m):
+        self.L.cpo_shape_set_mass(self.h, shape, float(m))
+
+    def set_material(self, shape, e, u, ctype=0):
+        self.L.cpo_shape_set_material(self.h, shape, float(e), float(u), int(ctype))
+
+    def get_vertices(self, shape):
+        n = self.L.cpo_shape_count(self.h, shape)
+        out = np.empty((n, 2), dtype=np.float64)
+        self.L.cpo_shape_get_verts(self.h, shape, _dp(out))
+        return out
+
+    def shape_mass(self, shape):
+        out = np.empty(4, dtype=np.float64)
+        self.L.cpo_shape_get_mass(self.h, shape, _dp(out))
+        return out
+
+    def set_velocity(self, body, vx, vy):
+        self.L.cpo_body_set_velocity(self.h, body, float(vx), float(vy))
+
+    def set_angular_velocity(self, body, w):
+        self.L.cpo_body_set_angular_velocity(self.h, body, float(w))
+
+    def body(self, b):
+        out = np.empty(8, dtype=np.float64)
+        self.L.cpo_body_get(self.h, b, _dp(out))
+        return out
+
+    def num_bodies(self):
+        return self.L.cpo_num_bodies(self.h)
+
+    def state(self):
+        out = np.empty((self.num_bodies(), 6), dtype=np.float64)
+        self.L.cpo_get_state(self.h, _dp(out))
+        return out
+
+    def step(self, dt):
+        self.L.cpo_step(self.h, float(dt))
+
+    def shipice_substeps(self, ship_body, steps, dt, yaw_lo, yaw_hi, map_width):
+        return self.L.cpo_shipice_substeps(self.h, ship_body, int(steps), float(dt), float(yaw_lo), float(yaw_hi), float(map_width))
+
+    def stats(self):
+        out = (C.c_longlong * 11)()
+        self.L.cpo_get_stats(self.h, out)
+        keys = ["steps", "pairs_bb", "pairs_touch", "arb_solved", "arb_nonzero", "gjk_iters", "epa_calls",
+                "max_arb", "max_nonzero", "moved_bodies", "max_moved"]
+        return dict(zip(keys, list(out)))
+
+    def reset_stats(self):
+        self.L.cpo_reset_stats(self.h)
+
+    def arbiters(self, max_rows=8192):
+        out = np.zeros((max_rows, 7), dtype=np.float64)
+        n = self.L.cpo_get_arbiters(self.h, _dp(out), max_rows)
+        return out[:min(n, max_rows)]
+
+
+def poly_centroid_hull(verts):
+    """pymunk.Poly(None, verts).center_of_gravity (sim_utils.py:140-141)."""
+    v = np.ascontiguousarray(verts, dtype=np.float64)
+    out = np.empty(2, dtype=np.float64)
+    lib().cpo_poly_centroid(v.shape[0], _dp(v), _dp(out))
+    return out
+
+
+def spfa(input_map, source):
+    """Port of spfa.spfa (deps/spfa/src/main.cpp:10): bool[H,W], (i,j) -> (f32[H,W], i32[H,W])."""
+    m = np.ascontiguousarray(np.asarray(input_map).astype(bool).astype(np.uint8))
+    H, W = m.shape
+    d = np.empty((H, W), dtype=np.float32)
+    p = np.empty((H, W), dtype=np.int32)
+    lib().spfa_oracle(m.ctypes.data_as(C.POINTER(C.c_uint8)), H, W, int(source[0]), int(source[1]),
+                      d.ctypes.data_as(C.POINTER(C.c_float)), p.ctypes.data_as(C.POINTER(C.c_int32)))
+    return d, p
