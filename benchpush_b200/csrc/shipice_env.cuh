@@ -1,0 +1,154 @@
+// ship-ice-v0 environment logic on top of the rigid-body core (one warp = one environment).
+// Follows ShipIceEnv.reset / step of the reference (ship_ice_env.py:186-220, 223-249, 261-355),
+// CostMap.get_obs_from_poly (cost_map.py:274-281), total_work_done (evaluation/metrics.py:96-126),
+// poly_area / poly_centroid (geometry/polygon.py:25-41).
+#pragma once
+#include "sim_step.cuh"
+
+namespace bp {
+
+// Per-env outputs of one env step (SoA over envs; device pointers owned by the caller).
+struct StepOut {
+    double* reward;             // [E]
+    unsigned char* terminated;  // [E]
+    unsigned char* truncated;   // [E] always 0 (the reference never truncates: ship_ice_env.py:355)
+    double* state;              // [E][3] ship (x, y, theta) rounded to 2 decimals (info['state'])
+    double* pose;               // [E][3] unrounded ship pose
+    double* total_work;         // [E]
+    double* collision_reward;   // [E]  (= -work)
+    double* scaled_collision_reward;   // [E]
+    double* dist_reward;        // [E]
+    unsigned char* trial_success;      // [E]
+    int* status;                // [E] StatusBits
+};
+
+// geometry/polygon.py:25-41 on the world-space hull vertices of body b (np.roll(y, 1)[i] = y[i-1]).
+BP_DEV void area_centroid_abs(const double* wv, int n, double* area, double* cx, double* cy) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < n; i++) {
+        int j = (i == 0) ? n - 1 : i - 1;
+        s1 += wv[2 * i] * wv[2 * j + 1];
+        s2 += wv[2 * i + 1] * wv[2 * j];
+    }
+    double A = 0.5 * fabs(s1 - s2);
+    double sx = 0.0, sy = 0.0;
+    for (int i = 0; i < n; i++) {
+        int j = (i == 0) ? n - 1 : i - 1;
+        double u = wv[2 * i] * wv[2 * j + 1] - wv[2 * j] * wv[2 * i + 1];
+        sx += (wv[2 * i] + wv[2 * j]) * u;
+        sy += (wv[2 * i + 1] + wv[2 * j + 1]) * u;
+    }
+    double k = 1.0 / (6.0 * A);
+    *area = A; *cx = fabs(k * sx); *cy = fabs(k * sy);
+}
+
+BP_DEV double round2(double x) { return rint(x * 100.0) / 100.0; }
+
+BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, int layout_id, int env, const StepOut& out) {
+    LayoutView L = layout_view(T, d, layout_id);
+    EnvScal* sc = ev.sc;
+    const int lane = bp_lane();
+    init_env(ev, L, P, d, layout_id);
+    // 1000 settle substeps with the ship at rest (ship_ice_env.py:218-219)
+    double prev_dt = 0.0;
+    for (int k = 0; k < P.settle_steps; k++) {
+        substep(ev, L, P, d, P.dt, prev_dt);
+        prev_dt = P.dt;
+        if (k == 0 || (k & 127) == 127) sleep_pass(ev, L, d);
+    }
+    sleep_pass(ev, L, d);
+    // prev_obs = get_obs_from_poly(polygons) (ship_ice_env.py:220): cache |centroid| and area per floe
+    int nb = sc->nbody;
+    for (int b = lane; b < nb - 1; b += BP_NL) {
+        area_centroid_abs(ev.wv + (size_t)b * VMAX * 2, L.nv[b], &ev.area[b], &ev.cenx[b], &ev.ceny[b]);
+        ev.moved_step[b] = 0;
+    }
+    if (lane == 0) {
+        int r = sc->robot;
+        V2 o = body_origin(ev, L, r);
+        out.pose[3 * env] = o.x; out.pose[3 * env + 1] = o.y; out.pose[3 * env + 2] = ev.pa[r];
+        out.state[3 * env] = round2(o.x); out.state[3 * env + 1] = round2(o.y); out.state[3 * env + 2] = round2(ev.pa[r]);
+        out.total_work[env] = 0.0; out.reward[env] = 0.0; out.terminated[env] = 0; out.truncated[env] = 0;
+        out.collision_reward[env] = 0.0; out.scaled_collision_reward[env] = 0.0; out.dist_reward[env] = 0.0;
+        out.trial_success[env] = 0; out.status[env] = sc->status;
+        sc->t = 0; sc->total_work = 0.0;
+    }
+    bp_wsync();
+}
+
+BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, double action, int env, const StepOut& out) {
+    EnvScal* sc = ev.sc;
+    LayoutView L = layout_view(T, d, sc->layout);
+    const int lane = bp_lane();
+    const int r = sc->robot;
+    // ship_ice_env.py:263-274: yaw rate from the action, constant surge along the heading at step start
+    if (lane == 0) {
+        sc->t++;
+        double a = ev.pa[r];
+        double s, c; bp_sincos(a, &s, &c);
+        ev.vw[r] = action * P.yaw_step;
+        ev.vx[r] = c * P.target_speed + (-s) * 0.0;
+        ev.vy[r] = s * P.target_speed + c * 0.0;
+    }
+    bp_wsync();
+    sleep_pass(ev, L, d);
+    bool yaw_violated = false, boundary_violated = false;
+    for (int k = 0; k < P.substeps; k++) {
+        substep(ev, L, P, d, P.dt, P.dt);
+        // ship_ice_env.py:284-290
+        double a = ev.pa[r];
+        if (a <= P.yaw_lo || a >= P.yaw_hi) { if (lane == 0) ev.vw[r] = 0.0; yaw_violated = true; }
+        V2 o = body_origin(ev, L, r);
+        if (o.x < 0 || o.x > P.map_w) boundary_violated = true;
+        bp_wsync();
+    }
+    V2 o = body_origin(ev, L, r);
+    bool boundary_terminal = false;
+    if (o.x < 0 && fabs(o.x - 0) >= P.boundary_limit) boundary_terminal = true;
+    if (o.x > P.map_w && fabs(o.x - P.map_w) >= P.boundary_limit) boundary_terminal = true;
+    // work = sum_i area(a_i) * || |c(a_i)| - |c(b_i)| ||  — only floes that moved this step contribute
+    int na = sc->n_awake;
+    for (int k = lane; k < na; k += BP_NL) {
+        int b = ev.awake[k];
+        double w = 0.0;
+        if (b != r && ev.moved_step[b]) {
+            double A, cx, cy;
+            area_centroid_abs(ev.wv + (size_t)b * VMAX * 2, L.nv[b], &A, &cx, &cy);
+            double dx = ev.cenx[b] - cx, dy = ev.ceny[b] - cy;
+            w = sqrt(dx * dx + dy * dy) * ev.area[b];
+            ev.cenx[b] = cx; ev.ceny[b] = cy; ev.area[b] = A;
+            ev.moved_step[b] = 0;
+        }
+        ev.tmp[b] = w;
+    }
+    bp_wsync();
+    if (lane == 0) {
+        // ascending body index, like zip(prev_obs, updated) in the reference
+        double work = 0.0;
+        for (int b = 0; b < sc->nbody - 1; b++) if (ev.is_awake[b]) work += ev.tmp[b];
+        sc->total_work += work;
+        double y = o.y;
+        bool terminated = (y >= P.goal_y) || boundary_terminal;
+        double dist_reward = 0.0;
+        if (y < P.goal_y) {
+            double a = ev.pa[r];
+            double s, c; bp_sincos(a, &s, &c);
+            dist_reward = 1.0 * (c * 0.0 + s * 1.0);
+        }
+        double collision_reward = -work;
+        double reward = P.beta * collision_reward + dist_reward;
+        if (yaw_violated) reward += P.yaw_penalty;
+        if (boundary_violated) reward += P.boundary_penalty;
+        bool success = false;
+        if (terminated && !boundary_terminal) { reward += P.terminal_reward; success = true; }
+        out.reward[env] = reward; out.terminated[env] = terminated ? 1 : 0; out.truncated[env] = 0;
+        out.pose[3 * env] = o.x; out.pose[3 * env + 1] = o.y; out.pose[3 * env + 2] = ev.pa[r];
+        out.state[3 * env] = round2(o.x); out.state[3 * env + 1] = round2(o.y); out.state[3 * env + 2] = round2(ev.pa[r]);
+        out.total_work[env] = sc->total_work; out.collision_reward[env] = collision_reward;
+        out.scaled_collision_reward[env] = collision_reward * P.beta; out.dist_reward[env] = dist_reward;
+        out.trial_success[env] = success ? 1 : 0; out.status[env] = sc->status;
+    }
+    bp_wsync();
+}
+
+}  // namespace bp

@@ -1,0 +1,194 @@
+"""Ice-field layouts for ship-ice-v0: packing of the reference's trial format and a seeded synthetic
+generator.
+
+The reference keeps 100 pre-generated trials per concentration in pickles
+(``ship_ice_env.py:75-80``: ``ddict['exp'][concentration][trial] = {goal, ship_state, obstacles}``)
+and picks ``trial = experiment[episode_idx % 100]`` at reset (``ship_ice_env.py:188-192``).  Layouts
+are INPUTS here too: :func:`pack_trials` turns that structure into flat arrays for the CUDA
+library; :func:`load_reference_pickle` reads a reference pickle when the user has one; and
+:func:`generate_ice_field` builds statistically similar fields (non-overlapping random circles,
+a random convex polygon in each circle's bounding square — the recipe of ``cost_map.py:219-260`` and
+``geometry/polygon.py:53-146``) from a seed, for machines without the reference data.
+"""
+from __future__ import annotations
+
+import pickle
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+
+VMAX = 20
+
+
+@dataclass
+class PackedLayouts:
+    n_floes: np.ndarray      # int32 [L]
+    n_verts: np.ndarray      # int32 [L, F]
+    verts: np.ndarray        # float64 [L, F, VMAX, 2] world coordinates (raw trial vertices)
+    centres: np.ndarray      # float64 [L, F, 2]
+    ship_state: np.ndarray   # float64 [L, 3]
+
+    @property
+    def n_layouts(self) -> int:
+        return int(self.n_floes.shape[0])
+
+    @property
+    def max_floes(self) -> int:
+        return int(self.n_verts.shape[1])
+
+
+def _poly_area(v: np.ndarray) -> float:
+    # geometry/polygon.py:25-29
+    x, y = v.T
+    return 0.5 * np.abs(np.dot(x, np.roll(y, 1)) - np.dot(y, np.roll(x, 1)))
+
+
+def pack_trials(trials: Sequence[dict], max_floes: int | None = None) -> PackedLayouts:
+    """Pack a list of reference-format trials.  Zero-area obstacles are dropped (ship_ice_env.py:206)."""
+    kept = []
+    for t in trials:
+        obs = [ob for ob in t["obstacles"] if _poly_area(np.asarray(ob["vertices"], dtype=np.float64)) != 0]
+        kept.append(obs)
+    F = max(len(o) for o in kept)
+    if max_floes is not None:
+        if F > max_floes:
+            raise ValueError(f"layout has {F} floes > max_floes={max_floes}")
+        F = max_floes
+    L = len(trials)
+    n_floes = np.zeros(L, dtype=np.int32)
+    n_verts = np.zeros((L, F), dtype=np.int32)
+    verts = np.zeros((L, F, VMAX, 2), dtype=np.float64)
+    centres = np.zeros((L, F, 2), dtype=np.float64)
+    ship_state = np.zeros((L, 3), dtype=np.float64)
+    for l, (t, obs) in enumerate(zip(trials, kept)):
+        n_floes[l] = len(obs)
+        ship_state[l] = np.asarray(t["ship_state"], dtype=np.float64)
+        for f, ob in enumerate(obs):
+            v = np.asarray(ob["vertices"], dtype=np.float64)
+            if v.shape[0] > VMAX:
+                raise ValueError(f"obstacle with {v.shape[0]} vertices > {VMAX}")
+            n_verts[l, f] = v.shape[0]
+            verts[l, f, : v.shape[0]] = v
+            centres[l, f] = np.asarray(ob["centre"], dtype=np.float64)
+    return PackedLayouts(n_floes, n_verts, verts, centres, ship_state)
+
+
+def unpack_trials(p: PackedLayouts) -> List[dict]:
+    """Inverse of :func:`pack_trials` (reference trial format), e.g. to feed a CPU checker."""
+    out = []
+    for l in range(p.n_layouts):
+        obs = []
+        for f in range(int(p.n_floes[l])):
+            n = int(p.n_verts[l, f])
+            obs.append({"vertices": p.verts[l, f, :n].copy(), "centre": (p.centres[l, f, 0], p.centres[l, f, 1])})
+        out.append({"goal": (2, 40), "ship_state": tuple(p.ship_state[l]), "obstacles": obs})
+    return out
+
+
+def load_reference_pickle(path: str, concentration: float) -> List[dict]:
+    """Read one of the reference's ``experiments_XX_100_r06_d40x12.pk`` files."""
+    with open(path, "rb") as f:
+        d = pickle.load(f)
+    exp = d["exp"][concentration]
+    return [exp[i] for i in range(len(exp))]
+
+
+def save_packed(path: str, p: PackedLayouts) -> None:
+    np.savez_compressed(path, n_floes=p.n_floes, n_verts=p.n_verts, verts=p.verts, centres=p.centres, ship_state=p.ship_state)
+
+
+def load_packed(path: str) -> PackedLayouts:
+    z = np.load(path)
+    return PackedLayouts(z["n_floes"], z["n_verts"], z["verts"], z["centres"], z["ship_state"])
+
+
+# ---------------------------------------------------------------------------------- synthetic generator
+def _random_convex_polygon(rng: np.random.Generator, diameter: float, n: int) -> np.ndarray:
+    """Valtr's random convex polygon in a ``diameter`` x ``diameter`` box (geometry/polygon.py:53-146)."""
+    xs = np.sort(rng.uniform(0, diameter, n))
+    ys = np.sort(rng.uniform(0, diameter, n))
+
+    def chains(vals):
+        lo, hi = vals[0], vals[-1]
+        top = bot = lo
+        vec = []
+        for v in vals[1:-1]:
+            if rng.integers(2):
+                vec.append(v - top)
+                top = v
+            else:
+                vec.append(bot - v)
+                bot = v
+        vec.append(hi - top)
+        vec.append(bot - hi)
+        return np.array(vec)
+
+    xv = chains(xs)
+    yv = chains(ys)
+    rng.shuffle(yv)
+    ang = np.arctan2(xv, yv)
+    order = np.argsort(ang, kind="stable")
+    xv, yv = xv[order], yv[order]
+    px = np.concatenate(([0.0], np.cumsum(xv)[:-1]))
+    py = np.concatenate(([0.0], np.cumsum(yv)[:-1]))
+    px += xs[0] - px.min()
+    py += ys[0] - py.min()
+    return np.stack([px, py], axis=1)
+
+
+def _centroid(v: np.ndarray) -> np.ndarray:
+    x, y = v.T
+    a = 0.5 * (np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+    u = x * np.roll(y, -1) - np.roll(x, -1) * y
+    return np.array([np.dot(x + np.roll(x, -1), u), np.dot(y + np.roll(y, -1), u)]) / (6 * a)
+
+
+def generate_ice_field(seed: int, concentration: float, map_width: float = 12.0, min_y: float = 2.0, max_y: float = 40.0,
+                       min_r: float = 0.2, max_r: float = 0.6, max_floes: int = 653) -> dict:
+    """One synthetic trial in the reference's format.  Circles of radius U(min_r, max_r) are dropped
+    without overlap until their area reaches ``concentration`` of the field; each carries a random
+    convex polygon with 10..20 vertices whose centroid sits at the circle centre."""
+    rng = np.random.default_rng(seed)
+    field_area = map_width * (max_y - min_y)
+    cell = 2 * max_r
+    gx, gy = int(np.ceil(map_width / cell)), int(np.ceil((max_y - min_y) / cell))
+    grid: List[List[List[int]]] = [[[] for _ in range(gx)] for _ in range(gy)]
+    cx, cy, cr = [], [], []
+    covered = 0.0
+    tries = 0
+    while covered < concentration * field_area and len(cx) < max_floes and tries < 200000:
+        tries += 1
+        r = rng.uniform(min_r, max_r)
+        x = rng.uniform(r, map_width - r)
+        y = rng.uniform(min_y + r, max_y - r)
+        ix, iy = int(x / cell), int((y - min_y) / cell)
+        ok = True
+        for jy in range(max(0, iy - 1), min(gy, iy + 2)):
+            for jx in range(max(0, ix - 1), min(gx, ix + 2)):
+                for k in grid[jy][jx]:
+                    if (cx[k] - x) ** 2 + (cy[k] - y) ** 2 < (cr[k] + r) ** 2:
+                        ok = False
+                        break
+                if not ok:
+                    break
+            if not ok:
+                break
+        if not ok:
+            continue
+        grid[iy][ix].append(len(cx))
+        cx.append(x); cy.append(y); cr.append(r)
+        covered += np.pi * r * r
+    obstacles = []
+    for x, y, r in zip(cx, cy, cr):
+        n = int(rng.integers(10, 21))
+        poly = _random_convex_polygon(rng, 2 * r, n)
+        poly = poly - _centroid(poly) + np.array([x, y])
+        poly = poly[::-1].copy()          # the reference's polygons are clockwise
+        obstacles.append({"vertices": poly, "centre": (x, y), "radius": r})
+    ship_x = rng.uniform(1.0, 10.0)
+    return {"goal": (2, 40), "ship_state": (float(ship_x), 1.0, float(np.pi / 2)), "obstacles": obstacles}
+
+
+def generate_experiment(n_trials: int, concentration: float, seed: int = 99, **kw) -> List[dict]:
+    return [generate_ice_field(seed * 100003 + i, concentration, **kw) for i in range(n_trials)]

@@ -1,0 +1,156 @@
+/* benchpush_b200 — C ABI of the B200-native batched simulator for BenchPush's 2D pushing envs.
+ *
+ * This is the drop-in boundary for the hot path.  The reference has one native FFI
+ * on this path (spfa, pybind11) and otherwise reaches native code through pymunk's cffi binding of
+ * Chipmunk2D; each entry point below names the reference interface it replaces (paths relative to
+ * the reference tree).  Plain pointers and sizes only; no torch types.  Unless a function says
+ * "host", pointers are DEVICE pointers owned by the caller (e.g. torch tensors) and the work is
+ * enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream) without
+ * synchronising the host.  Every function returns 0 on success or a negative bp_status code;
+ * bp_last_error() returns a message for the calling thread's last failure.
+ */
+#ifndef BENCHPUSH_B200_H
+#define BENCHPUSH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BP_VMAX 20            /* max vertices per convex obstacle */
+#define BP_OBS_C 4            /* ship-ice egocentric observation: 4 x 150 x 150 u8 */
+#define BP_OBS_H 150
+#define BP_OBS_W 150
+
+enum bp_status {
+    BP_OK = 0,
+    BP_ERR_INVALID = -1,      /* bad argument */
+    BP_ERR_CUDA = -2,         /* CUDA runtime error (no GPU, OOM, launch failure) */
+    BP_ERR_CAPACITY = -3,     /* a per-env capacity (pairs / live arbiters / colours) overflowed */
+    BP_ERR_STATE = -4         /* call order (e.g. step before load_layouts / reset) */
+};
+
+/* env status bits reported per env in bp_shipice_outputs.status */
+#define BP_ENV_PAIR_OVERFLOW 1
+#define BP_ENV_LIVE_OVERFLOW 2
+#define BP_ENV_COLOUR_OVERFLOW 4
+#define BP_ENV_GJK_ITER_CAP 8
+
+int bp_version(void);
+const char* bp_last_error(void);
+int bp_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * ship-ice-v0.  Replaces ShipIceEnv.__init__/reset/step/generate_observation
+ * (benchpush/environments/ship_ice_nav/ship_ice_env.py:37-106, 223-249, 261-355, 378-409), the
+ * pymunk.Space it drives (ship_ice_env.py:117-120, 218-219, 280-281) and the OccupancyGrid channel
+ * methods it calls (benchpush/common/occupancy_grid/occupancy_map.py:37-65, 112-140, 300-337,
+ * 379-433, 492-587) for a batch of independent environments.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bp_shipice bp_shipice_t;
+
+typedef struct bp_shipice_config {
+    int32_t n_envs;
+    int32_t max_floes;        /* capacity of obstacles per layout */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t pair_capacity;    /* neighbour-list capacity per env (0 = default 8 * (max_floes+1)) */
+    int32_t live_capacity;    /* touching-pair capacity per env (0 = default max(256, 2*(max_floes+1))) */
+    int32_t auto_reset;       /* 1: an env that terminated is reset by its NEXT step call (next trial) */
+    /* reference cfg keys that reach the hot path (ship_ice_nav/config.yaml) */
+    double dt;                /* cfg.dt = 0.8 */
+    int32_t steps;            /* cfg.sim.steps = 400 */
+    int32_t iterations;       /* cfg.sim.iterations = 10 */
+    double damping;           /* cfg.sim.damping = 0 */
+    double obstacle_density;  /* cfg.sim.obstacle_density = 0.001 */
+    double target_speed;      /* cfg.target_speed = 0.3 */
+    double goal_y;            /* cfg.goal_y = 9 */
+    double map_width;         /* cfg.occ.map_width = 12 */
+    double map_height;        /* cfg.occ.map_height = 40 */
+    int32_t m_to_pix_scale;   /* cfg.occ.m_to_pix_scale = 25 */
+    int32_t settle_steps;     /* 1000 (ship_ice_env.py:218) */
+    int32_t n_ship_verts;     /* cfg.ship.vertices */
+    double ship_verts[64];    /* x0,y0,x1,y1,... (<= 32 vertices) */
+    double ship_head[2];      /* cfg.ship.head */
+    double ship_tail[2];      /* cfg.ship.tail */
+} bp_shipice_config;
+
+/* Fill cfg with the reference defaults (ship_ice_nav/config.yaml). */
+void bp_shipice_default_config(bp_shipice_config* cfg);
+
+int bp_shipice_create(const bp_shipice_config* cfg, bp_shipice_t** out);
+int bp_shipice_destroy(bp_shipice_t* h);
+
+/* Ice-field layouts = the trials of the reference's experiment pickles
+ * (ship_ice_env.py:75-80, 186-216).  HOST pointers; the tables are built (hull, mass, normals —
+ * sim_utils.py:136-153, ship.py:77-98) and uploaded once.
+ *   n_floes[L], n_verts[L*max_floes], verts[L*max_floes*BP_VMAX*2] (world coordinates),
+ *   centres[L*max_floes*2], ship_state[L*3] (x, y, theta). */
+int bp_shipice_load_layouts(bp_shipice_t* h, int32_t n_layouts, const int32_t* n_floes, const int32_t* n_verts,
+                            const double* verts, const double* centres, const double* ship_state);
+
+typedef struct bp_shipice_outputs {   /* all DEVICE pointers, each may be NULL except obs/reward/terminated */
+    uint8_t* obs;                     /* [E][4][150][150]  footprint, goal-edt, orientation, occupancy */
+    double* reward;                   /* [E] */
+    uint8_t* terminated;              /* [E] */
+    uint8_t* truncated;               /* [E] (always 0: ship_ice_env.py:355) */
+    double* state;                    /* [E][3] info['state']: pose rounded to 2 decimals */
+    double* pose;                     /* [E][3] unrounded pose */
+    double* total_work;               /* [E] info['total_work'] */
+    double* collision_reward;         /* [E] */
+    double* scaled_collision_reward;  /* [E] */
+    double* dist_reward;              /* [E] */
+    uint8_t* trial_success;           /* [E] */
+    int32_t* status;                  /* [E] BP_ENV_* bits */
+} bp_shipice_outputs;
+
+/* ShipIceEnv.reset (ship_ice_env.py:223-249) for the envs with mask[e] != 0 (mask NULL = all):
+ * build the world from layout_ids[e], run the settle substeps, write the reset observation and info. */
+int bp_shipice_reset(bp_shipice_t* h, const int32_t* layout_ids, const uint8_t* mask,
+                     const bp_shipice_outputs* out, void* stream);
+
+/* ShipIceEnv.step (ship_ice_env.py:261-355) for every env: actions[E] in [-1, 1]. */
+int bp_shipice_step(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): copies actions to the device, steps, copies
+ * obs / reward / terminated / truncated (and the non-NULL info arrays) back, and synchronises. */
+int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out_host);
+
+/* CostMap.get_obs_from_poly (cost_map.py:274-281) = info['obs']: world-space hull vertices of every
+ * floe of env `env`.  HOST outputs: verts[max_floes*BP_VMAX*2], n_verts[max_floes]; returns n_floes. */
+int bp_shipice_get_obstacles(bp_shipice_t* h, int32_t env, double* verts, int32_t* n_verts);
+
+/* Body state of env `env` (parity fixtures / checkpoints), HOST: out[(n_floes+1)*6] =
+ * position x, y, angle, vx, vy, w per body; the ship is the last row.  Returns the body count. */
+int bp_shipice_get_bodies(bp_shipice_t* h, int32_t env, double* out);
+
+/* Counters of env `env`, HOST out[16]: stamp, n_awake, n_pairs, n_free, n_order, n_colours, status,
+ * n_apairs, n_cached, gjk_iters, pairs_evaluated, live_sum, awake_sum, recolours, rebuilds, substeps. */
+int bp_shipice_get_counters(bp_shipice_t* h, int32_t env, int64_t* out);
+
+/* Bytes of device memory held per env and in total. */
+size_t bp_shipice_env_bytes(bp_shipice_t* h);
+
+/* Number of kernel launches issued by this handle so far (for bench accounting). */
+int64_t bp_shipice_launch_count(bp_shipice_t* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grid shortest paths.  Replaces spfa.spfa(input_map, source) -> (dists, parents)
+ * (deps/spfa/src/main.cpp:10-116; call sites box_delivery_env.py:1121,1134,1226,
+ * area_clearing.py:1049,1061, position_controller.py:143) for a batch of maps:
+ *   maps[B][H][W] u8 (non-zero = free), sources[B][2] (row, col)
+ *   dists[B][H][W] f32 (unreachable -> 0), parents[B][H][W] i32 (raveled index or -1).
+ * Distances are bit-identical to the reference (same fp32 relaxation fixed point); parents are a
+ * valid shortest-path tree (ties may be broken differently from the reference's queue order).
+ * ---------------------------------------------------------------------------------------------- */
+int bp_spfa_batch(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t height, int32_t width,
+                  float* dists, int32_t* parents, void* stream);
+/* scratch-free host-buffer variant (copies in, runs, copies out, synchronises) */
+int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t height, int32_t width,
+                       float* dists, int32_t* parents);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BENCHPUSH_B200_H */

@@ -1,0 +1,92 @@
+"""ctypes loader for the TEST-ONLY host emulation of the env kernels (tests/emu/emu_harness.cpp)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "..", "..", "benchpush_b200", "csrc")
+
+
+def build():
+    so = os.path.join(_HERE, "libbp_emu.so")
+    srcs = [os.path.join(_HERE, "emu_harness.cpp")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-o", so,
+                               os.path.join(_HERE, "emu_harness.cpp")])
+    return so
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Emu:
+    def __init__(self, n_envs, packed, ship_verts, pmax=8192, lmax=1024, goal_y=9.0, settle_steps=1000,
+                 margin_body=0.3, margin_robot=0.6):
+        L = C.CDLL(build())
+        L.emu_create.restype = C.c_void_p
+        L.emu_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]
+        L.emu_env_bytes.restype = C.c_size_t
+        for f in ("emu_destroy", "emu_load_layouts", "emu_reset", "emu_step", "emu_set_robot_velocity", "emu_substeps",
+                  "emu_init_only", "emu_sleep_pass", "emu_get_bodies", "emu_get_out", "emu_get_scal", "emu_layout_verts", "emu_env_bytes"):
+            getattr(L, f).argtypes = None
+        self.L = L
+        self.p = packed
+        self.h = C.c_void_p(L.emu_create(n_envs, packed.max_floes, pmax, lmax, float(goal_y), settle_steps, float(margin_body), float(margin_robot)))
+        sv = np.ascontiguousarray(ship_verts, dtype=np.float64)
+        rc = L.emu_load_layouts(self.h, C.c_int(packed.n_layouts), _ip(packed.n_floes), _ip(np.ascontiguousarray(packed.n_verts)),
+                                _dp(np.ascontiguousarray(packed.verts)), _dp(np.ascontiguousarray(packed.centres)),
+                                _dp(np.ascontiguousarray(packed.ship_state)), _dp(sv), C.c_int(sv.shape[0]))
+        assert rc == 0
+
+    def reset(self, env, layout):
+        self.L.emu_reset(self.h, C.c_int(env), C.c_int(layout))
+
+    def init_only(self, env, layout):
+        self.L.emu_init_only(self.h, C.c_int(env), C.c_int(layout))
+
+    def step(self, env, action):
+        self.L.emu_step(self.h, C.c_int(env), C.c_double(action))
+
+    def set_robot_velocity(self, env, vx, vy, w):
+        self.L.emu_set_robot_velocity(self.h, C.c_int(env), C.c_double(vx), C.c_double(vy), C.c_double(w))
+
+    def substeps(self, env, n, first=False):
+        self.L.emu_substeps(self.h, C.c_int(env), C.c_int(n), C.c_int(1 if first else 0))
+
+    def sleep_pass(self, env):
+        self.L.emu_sleep_pass(self.h, C.c_int(env))
+
+    def bodies(self, env, layout):
+        nb = int(self.p.n_floes[layout]) + 1
+        out = np.zeros((nb, 6), dtype=np.float64)
+        self.L.emu_get_bodies(self.h, C.c_int(env), _dp(out))
+        return out
+
+    def out(self, env):
+        o = np.zeros(13, dtype=np.float64)
+        self.L.emu_get_out(self.h, C.c_int(env), _dp(o))
+        keys = ["reward", "terminated", "truncated", "sx", "sy", "sa", "total_work", "collision_reward",
+                "scaled_collision_reward", "dist_reward", "trial_success", "status", "angle"]
+        return dict(zip(keys, o))
+
+    def scal(self, env):
+        o = (C.c_longlong * 16)()
+        self.L.emu_get_scal(self.h, C.c_int(env), o)
+        keys = ["stamp", "n_awake", "n_pairs", "n_free", "n_order", "n_colours", "status", "n_apairs", "n_cached", "gjk",
+                "pairs_eval", "live_sum", "awake_sum", "recolour", "rebuild", "substeps"]
+        return dict(zip(keys, list(o)))
+
+    def layout_verts(self, l, b):
+        out = np.zeros((20, 2), dtype=np.float64)
+        mi = np.zeros(4, dtype=np.float64)
+        n = self.L.emu_layout_verts(self.h, C.c_int(l), C.c_int(b), _dp(out), _dp(mi))
+        return out[:n], mi
+
+    def env_bytes(self):
+        return self.L.emu_env_bytes(self.h)

@@ -1,0 +1,127 @@
+// TEST-ONLY host emulation of the env kernels.
+// Compiles benchpush_b200/csrc/*.cuh as plain C++ with a one-lane "warp" (BP_HOST_EMU) so kernel
+// logic can be debugged and checked against the oracle on machines without a GPU.  It is never
+// loaded by the benchpush_b200 package: the product path is the CUDA library only.
+#define BP_HOST_EMU 1
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include "../../benchpush_b200/csrc/host_tables.h"
+#include "../../benchpush_b200/csrc/shipice_env.cuh"
+
+using namespace bp;
+
+struct Emu {
+    Dims d; SimParams P; HostLayouts H; LayoutTab T;
+    std::vector<char> mem; size_t env_bytes;
+    std::vector<double> reward, state, pose, total_work, coll, scoll, distr;
+    std::vector<unsigned char> term, trunc, succ; std::vector<int> status;
+    StepOut out;
+};
+
+extern "C" {
+
+void* emu_create(int n_envs, int max_floes, int pmax, int lmax, double goal_y, int settle_steps, double margin_body, double margin_robot) {
+    Emu* e = new Emu();
+    e->d.NB = max_floes + 1; e->d.PMAX = pmax; e->d.LMAX = lmax; e->d.n_envs = n_envs; e->d.n_layouts = 0;
+    ShipIceConfig c; c.goal_y = goal_y; c.settle_steps = settle_steps; c.margin_body = margin_body; c.margin_robot = margin_robot;
+    e->P = make_params(c);
+    e->env_bytes = env_mem_size(e->d);
+    e->mem.assign(e->env_bytes * n_envs, 0);
+    e->reward.resize(n_envs); e->state.resize(3 * n_envs); e->pose.resize(3 * n_envs); e->total_work.resize(n_envs);
+    e->coll.resize(n_envs); e->scoll.resize(n_envs); e->distr.resize(n_envs);
+    e->term.resize(n_envs); e->trunc.resize(n_envs); e->succ.resize(n_envs); e->status.resize(n_envs);
+    e->out.reward = e->reward.data(); e->out.terminated = e->term.data(); e->out.truncated = e->trunc.data();
+    e->out.state = e->state.data(); e->out.pose = e->pose.data(); e->out.total_work = e->total_work.data();
+    e->out.collision_reward = e->coll.data(); e->out.scaled_collision_reward = e->scoll.data(); e->out.dist_reward = e->distr.data();
+    e->out.trial_success = e->succ.data(); e->out.status = e->status.data();
+    return e;
+}
+void emu_destroy(void* h) { delete (Emu*)h; }
+int emu_load_layouts(void* h, int n_layouts, const int32_t* n_floes, const int32_t* n_verts, const double* verts,
+                     const double* centres, const double* ship_state, const double* ship_verts, int n_ship_verts) {
+    Emu* e = (Emu*)h;
+    ShipIceMaterial mat;
+    std::string err = build_shipice_layouts(e->H, n_layouts, e->d.NB - 1, n_floes, n_verts, verts, centres, ship_state, ship_verts, n_ship_verts, mat);
+    if (!err.empty()) { fprintf(stderr, "emu_load_layouts: %s\n", err.c_str()); return 1; }
+    e->d.n_layouts = n_layouts;
+    HostLayouts& H = e->H;
+    e->T.lv = H.lv.data(); e->T.ln = H.ln.data(); e->T.nv = H.nv.data(); e->T.rad = H.rad.data();
+    e->T.minv = H.minv.data(); e->T.iinv = H.iinv.data(); e->T.cog = H.cog.data(); e->T.mat_e = H.mat_e.data();
+    e->T.mat_u = H.mat_u.data(); e->T.init = H.init.data(); e->T.nbody = H.nbody.data();
+    return 0;
+}
+void emu_reset(void* h, int env, int layout) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    shipice_reset_env(ev, e->T, e->P, e->d, layout, env, e->out);
+}
+void emu_step(void* h, int env, double action) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    shipice_step_env(ev, e->T, e->P, e->d, action, env, e->out);
+}
+// one raw physics substep (for per-substep parity); robot velocity set explicitly
+void emu_set_robot_velocity(void* h, int env, double vx, double vy, double w) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    int r = ev.sc->robot; ev.vx[r] = vx; ev.vy[r] = vy; ev.vw[r] = w;
+}
+void emu_substeps(void* h, int env, int n, int first) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    LayoutView L = layout_view(e->T, e->d, ev.sc->layout);
+    for (int k = 0; k < n; k++) substep(ev, L, e->P, e->d, e->P.dt, (first && k == 0) ? 0.0 : e->P.dt);
+}
+void emu_init_only(void* h, int env, int layout) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    LayoutView L = layout_view(e->T, e->d, layout);
+    init_env(ev, L, e->P, e->d, layout);
+}
+void emu_sleep_pass(void* h, int env) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    LayoutView L = layout_view(e->T, e->d, ev.sc->layout);
+    sleep_pass(ev, L, e->d);
+}
+// [nbody][6]: origin x, y, angle, vx, vy, w
+int emu_get_bodies(void* h, int env, double* out) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    LayoutView L = layout_view(e->T, e->d, ev.sc->layout);
+    int nb = ev.sc->nbody;
+    for (int b = 0; b < nb; b++) {
+        V2 o = body_origin(ev, L, b);
+        out[6 * b] = o.x; out[6 * b + 1] = o.y; out[6 * b + 2] = ev.pa[b]; out[6 * b + 3] = ev.vx[b]; out[6 * b + 4] = ev.vy[b]; out[6 * b + 5] = ev.vw[b];
+    }
+    return nb;
+}
+void emu_get_out(void* h, int env, double* o13) {
+    Emu* e = (Emu*)h;
+    o13[0] = e->reward[env]; o13[1] = e->term[env]; o13[2] = e->trunc[env];
+    o13[3] = e->state[3 * env]; o13[4] = e->state[3 * env + 1]; o13[5] = e->state[3 * env + 2];
+    o13[6] = e->total_work[env]; o13[7] = e->coll[env]; o13[8] = e->scoll[env]; o13[9] = e->distr[env];
+    o13[10] = e->succ[env]; o13[11] = e->status[env]; o13[12] = e->pose[3 * env + 2];
+}
+void emu_get_scal(void* h, int env, long long* o) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    EnvScal* s = ev.sc;
+    o[0] = s->stamp; o[1] = s->n_awake; o[2] = s->n_pairs; o[3] = s->n_free; o[4] = s->n_order; o[5] = s->n_colours;
+    o[6] = s->status; o[7] = s->n_apairs; o[8] = s->n_cached; o[9] = s->stat_gjk; o[10] = s->stat_pairs_eval;
+    o[11] = s->stat_live_sum; o[12] = s->stat_awake_sum; o[13] = s->stat_recolour; o[14] = s->stat_rebuild; o[15] = s->stat_substeps;
+}
+// hull vertices of body b of layout l (for the hull parity test)
+int emu_layout_verts(void* h, int l, int b, double* out, double* minv_iinv) {
+    Emu* e = (Emu*)h;
+    size_t idx = (size_t)l * e->d.NB + b;
+    int n = e->H.nv[idx];
+    for (int i = 0; i < 2 * n; i++) out[i] = e->H.lv[idx * VMAX * 2 + i];
+    minv_iinv[0] = e->H.minv[idx]; minv_iinv[1] = e->H.iinv[idx]; minv_iinv[2] = e->H.cog[2 * idx]; minv_iinv[3] = e->H.cog[2 * idx + 1];
+    return n;
+}
+size_t emu_env_bytes(void* h) { return ((Emu*)h)->env_bytes; }
+
+}  // extern "C"
