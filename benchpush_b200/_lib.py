@@ -1,0 +1,98 @@
+"""ctypes binding of ``benchpush_b200/csrc/libbenchpush_b200.so`` (C ABI: include/benchpush_b200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is usable, loading / creating
+a handle raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libbenchpush_b200.so")
+
+BP_VMAX = 20
+OBS_SHAPE = (4, 150, 150)
+
+
+class BenchPushError(RuntimeError):
+    pass
+
+
+class ShipIceConfig(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("max_floes", C.c_int32), ("device", C.c_int32), ("pair_capacity", C.c_int32),
+        ("live_capacity", C.c_int32), ("auto_reset", C.c_int32),
+        ("dt", C.c_double), ("steps", C.c_int32), ("iterations", C.c_int32), ("damping", C.c_double),
+        ("obstacle_density", C.c_double), ("target_speed", C.c_double), ("goal_y", C.c_double),
+        ("map_width", C.c_double), ("map_height", C.c_double), ("m_to_pix_scale", C.c_int32), ("settle_steps", C.c_int32),
+        ("n_ship_verts", C.c_int32), ("ship_verts", C.c_double * 64), ("ship_head", C.c_double * 2), ("ship_tail", C.c_double * 2),
+    ]
+
+
+class ShipIceOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "obs", "reward", "terminated", "truncated", "state", "pose", "total_work", "collision_reward",
+        "scaled_collision_reward", "dist_reward", "trial_success", "status")]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise BenchPushError("nvcc build failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise BenchPushError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.bp_version.restype = C.c_int
+        L.bp_last_error.restype = C.c_char_p
+        L.bp_device_count.restype = C.c_int
+        L.bp_shipice_default_config.argtypes = [C.POINTER(ShipIceConfig)]
+        L.bp_shipice_default_config.restype = None
+        L.bp_shipice_create.argtypes = [C.POINTER(ShipIceConfig), C.POINTER(C.c_void_p)]
+        L.bp_shipice_destroy.argtypes = [C.c_void_p]
+        L.bp_shipice_load_layouts.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
+        L.bp_shipice_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
+        L.bp_shipice_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
+        L.bp_shipice_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs)]
+        L.bp_shipice_get_obstacles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.bp_shipice_get_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.bp_shipice_get_counters.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.bp_shipice_env_bytes.argtypes = [C.c_void_p]
+        L.bp_shipice_env_bytes.restype = C.c_size_t
+        L.bp_shipice_launch_count.argtypes = [C.c_void_p]
+        L.bp_shipice_launch_count.restype = C.c_int64
+        L.bp_spfa_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bp_spfa_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+EXPORTS = [
+    "bp_version", "bp_last_error", "bp_device_count", "bp_shipice_default_config", "bp_shipice_create",
+    "bp_shipice_destroy", "bp_shipice_load_layouts", "bp_shipice_reset", "bp_shipice_step", "bp_shipice_step_host",
+    "bp_shipice_get_obstacles", "bp_shipice_get_bodies", "bp_shipice_get_counters", "bp_shipice_env_bytes",
+    "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host",
+]
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        msg = lib().bp_last_error().decode("utf-8", "replace")
+        raise BenchPushError(f"benchpush_b200 error {rc}: {msg}")
+    return rc

@@ -1,0 +1,455 @@
+// C ABI of libbenchpush_b200.so (declared in include/benchpush_b200.h): handle management, layout
+// upload, kernel launches.  No CPU fallback: every entry point fails with BP_ERR_CUDA when the
+// CUDA runtime cannot run the kernels.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/benchpush_b200.h"
+#include "host_tables.h"
+#include "raster.cuh"
+#include "shipice_env.cuh"
+#include "spfa.cuh"
+
+using namespace bp;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) return fail(BP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ kernels
+// Persistent warps: each warp pulls environment indices from a global counter and simulates one
+// environment at a time (envs differ widely in cost: contact-free water vs. an ice jam).
+struct StepArgs {
+    char* mem; size_t env_bytes; Dims d; SimParams P; LayoutTab T; StepOut out;
+    const float* actions; const int32_t* layout_ids; const uint8_t* mask; int* counter; int auto_reset;
+};
+
+__global__ void __launch_bounds__(128) k_shipice_reset(StepArgs a) {
+    for (;;) {
+        int env = 0;
+        if (bp_lane() == 0) env = atomicAdd(a.counter, 1);
+        env = bp_wbcast(env);
+        if (env >= a.d.n_envs) break;
+        if (a.mask && !a.mask[env]) continue;
+        EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
+        int layout = a.layout_ids[env] % a.d.n_layouts;
+        shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
+        if (bp_lane() == 0) { ev.sc->first_layout = layout; ev.sc->episode = 0; ev.sc->done = 0; ev.sc->obs_raw = 1; }
+        bp_wsync();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_shipice_step(StepArgs a) {
+    for (;;) {
+        int env = 0;
+        if (bp_lane() == 0) env = atomicAdd(a.counter, 1);
+        env = bp_wbcast(env);
+        if (env >= a.d.n_envs) break;
+        EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
+        if (a.auto_reset && ev.sc->done) {
+            // next-step auto reset: the env moves on to its next trial (episode_idx % n_trials,
+            // ship_ice_env.py:188); this call returns the reset observation with reward 0.
+            int ep = ev.sc->episode + 1, first = ev.sc->first_layout;
+            int layout = (first + ep) % a.d.n_layouts;
+            shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
+            if (bp_lane() == 0) { ev.sc->first_layout = first; ev.sc->episode = ep; ev.sc->done = 0; ev.sc->obs_raw = 1; }
+            bp_wsync();
+            continue;
+        }
+        shipice_step_env(ev, a.T, a.P, a.d, (double)a.actions[env], env, a.out);
+        if (bp_lane() == 0) { ev.sc->done = a.out.terminated[env]; ev.sc->obs_raw = 0; }
+        bp_wsync();
+    }
+}
+
+struct ObsArgs {
+    char* mem; size_t env_bytes; Dims d; LayoutTab T; ObsParams O;
+    const double* rawv; const int* rawn; const double* rawcen; const uint8_t* mask; uint8_t* obs;
+};
+
+__global__ void __launch_bounds__(256) k_shipice_obs(ObsArgs a) {
+    __shared__ ObsSmem S;
+    int env = blockIdx.x;
+    if (a.mask && !a.mask[env]) return;
+    EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
+    const EnvScal* sc = ev.sc;
+    LayoutView L = layout_view(a.T, a.d, sc->layout);
+    int r = sc->robot;
+    V2 o = body_origin(ev, L, r);
+    uint8_t* out = a.obs + (size_t)env * BP_OBS_C * OBS_PIX;
+    if (sc->obs_raw) {
+        size_t base = (size_t)sc->layout * a.d.NB;
+        render_obs(S, a.O, r, a.rawv + base * VMAX * 2, VMAX * 2, a.rawn + base, a.rawcen + base * 2, a.rawcen + base * 2 + 1, 2,
+                   o.x, o.y, ev.pa[r], out);
+    } else {
+        render_obs(S, a.O, r, ev.wv, VMAX * 2, L.nv, ev.cenx, ev.ceny, 1, o.x, o.y, ev.pa[r], out);
+    }
+}
+
+__global__ void __launch_bounds__(512) k_spfa(const uint8_t* maps, const int32_t* sources, int batch, int H, int W,
+                                               float* dists, int32_t* parents, int* scratch, int* counter) {
+    __shared__ SpfaShared S;
+    __shared__ int s_map;
+    const size_t nv = (size_t)H * W;
+    int* q0 = scratch + (size_t)blockIdx.x * 3 * nv;
+    for (;;) {
+        if (threadIdx.x == 0) s_map = atomicAdd(counter, 1);
+        __syncthreads();
+        int m = s_map;
+        __syncthreads();
+        if (m >= batch) break;
+        spfa_block(S, maps + m * nv, H, W, sources[2 * m], sources[2 * m + 1], dists + m * nv, parents + m * nv, q0, q0 + nv, q0 + 2 * nv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ handle
+struct bp_shipice {
+    bp_shipice_config cfg;
+    Dims d; SimParams P; ObsParams O;
+    HostLayouts H;
+    LayoutTab T;               // device pointers
+    std::vector<void*> dev_allocs;
+    double *d_rawv = nullptr, *d_rawcen = nullptr; int* d_rawn = nullptr;
+    char* mem = nullptr; size_t env_bytes = 0;
+    int* counter = nullptr;
+    StepOut out;               // internal device outputs
+    int32_t* d_layout_ids = nullptr;
+    float* d_actions = nullptr; uint8_t* d_obs = nullptr;   // only for the host-buffer entry point
+    float* h_actions = nullptr; void* h_stage = nullptr; size_t h_stage_bytes = 0;
+    bool layouts_loaded = false, was_reset = false;
+    int64_t launches = 0;
+    int sm_count = 148;
+};
+
+template <typename T>
+static int dev_upload(bp_shipice* h, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, v.size() * sizeof(T) + 16));
+    CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    h->dev_allocs.push_back(p);
+    *out = (const T*)p;
+    return 0;
+}
+
+extern "C" {
+
+int bp_version(void) { return 100; }
+const char* bp_last_error(void) { return g_err.c_str(); }
+int bp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void bp_shipice_default_config(bp_shipice_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->n_envs = 1; c->max_floes = 653; c->device = 0; c->pair_capacity = 0; c->live_capacity = 0; c->auto_reset = 0;
+    c->dt = 0.8; c->steps = 400; c->iterations = 10; c->damping = 0.0; c->obstacle_density = 0.001;
+    c->target_speed = 0.3; c->goal_y = 9.0; c->map_width = 12.0; c->map_height = 40.0; c->m_to_pix_scale = 25;
+    c->settle_steps = 1000;
+    static const double sv[] = {1., -0., 0.9, 0.10, 0.5, 0.25, 0.25, 0.25, 0, 0.25, -0.25, 0.25, -0.5, 0.25, -0.75, 0.25, -1., 0.25,
+                                -1., -0.25, -0.75, -0.25, -0.5, -0.25, -0.25, -0.25, 0, -0.25, 0.25, -0.25, 0.5, -0.25, 0.9, -0.10};
+    c->n_ship_verts = 17;
+    memcpy(c->ship_verts, sv, sizeof(sv));
+    c->ship_head[0] = 1.0; c->ship_head[1] = 0.0; c->ship_tail[0] = -1.0; c->ship_tail[1] = 0.0;
+}
+
+int bp_shipice_create(const bp_shipice_config* cfg, bp_shipice_t** out_h) {
+    if (!cfg || !out_h) return fail(BP_ERR_INVALID, "null argument");
+    if (cfg->n_envs <= 0 || cfg->max_floes <= 0 || cfg->max_floes > 60000) return fail(BP_ERR_INVALID, "n_envs / max_floes out of range");
+    if (cfg->n_ship_verts < 3 || cfg->n_ship_verts > 32) return fail(BP_ERR_INVALID, "n_ship_verts out of range");
+    if (cfg->steps <= 0 || cfg->iterations <= 0 || cfg->dt <= 0) return fail(BP_ERR_INVALID, "steps / iterations / dt must be positive");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(BP_ERR_CUDA, "CUDA device not available");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    bp_shipice* h = new bp_shipice();
+    h->cfg = *cfg;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    Dims& d = h->d;
+    d.NB = cfg->max_floes + 1;
+    d.PMAX = cfg->pair_capacity > 0 ? cfg->pair_capacity : 8 * d.NB;
+    d.LMAX = cfg->live_capacity > 0 ? cfg->live_capacity : (2 * d.NB > 256 ? 2 * d.NB : 256);
+    d.n_envs = cfg->n_envs; d.n_layouts = 0;
+    ShipIceConfig sc;
+    sc.dt = cfg->dt; sc.steps = cfg->steps; sc.iterations = cfg->iterations; sc.damping = cfg->damping;
+    sc.target_speed = cfg->target_speed; sc.goal_y = cfg->goal_y; sc.map_width = cfg->map_width; sc.map_height = cfg->map_height;
+    sc.m_to_pix_scale = cfg->m_to_pix_scale; sc.settle_steps = cfg->settle_steps;
+    h->P = make_params(sc);
+    ObsParams& O = h->O;
+    double grid = 1.0 / cfg->m_to_pix_scale;                       // ship_ice_env.py:92
+    O.grid_w = (int)(cfg->map_width / grid); O.grid_h = (int)(cfg->map_height / grid);   // occupancy_map.py:20-21
+    O.scale = (double)cfg->m_to_pix_scale; O.vshift = 2.0; O.goal_y = cfg->goal_y;
+    O.g2m = cfg->map_height / O.grid_h; O.range_x = 12.0; O.range_y = 12.0;
+    O.n_robot_raw = cfg->n_ship_verts;
+    memcpy(O.robot_raw, cfg->ship_verts, sizeof(double) * 2 * cfg->n_ship_verts);
+    O.head[0] = cfg->ship_head[0]; O.head[1] = cfg->ship_head[1]; O.tail[0] = cfg->ship_tail[0]; O.tail[1] = cfg->ship_tail[1];
+    h->env_bytes = env_mem_size(d);
+    size_t total = h->env_bytes * (size_t)d.n_envs;
+    cudaError_t e = cudaMalloc((void**)&h->mem, total);
+    if (e != cudaSuccess) { delete h; return fail(BP_ERR_CUDA, std::string("cudaMalloc of env state (") + std::to_string(total >> 20) + " MiB): " + cudaGetErrorString(e)); }
+    CUDA_TRY(cudaMemset(h->mem, 0, total));
+    CUDA_TRY(cudaMalloc((void**)&h->counter, 64));
+    size_t E = d.n_envs;
+    auto A = [&](void** p, size_t bytes) -> cudaError_t { cudaError_t r = cudaMalloc(p, bytes); if (r == cudaSuccess) { h->dev_allocs.push_back(*p); cudaMemset(*p, 0, bytes); } return r; };
+    CUDA_TRY(A((void**)&h->out.reward, E * 8)); CUDA_TRY(A((void**)&h->out.terminated, E)); CUDA_TRY(A((void**)&h->out.truncated, E));
+    CUDA_TRY(A((void**)&h->out.state, E * 24)); CUDA_TRY(A((void**)&h->out.pose, E * 24)); CUDA_TRY(A((void**)&h->out.total_work, E * 8));
+    CUDA_TRY(A((void**)&h->out.collision_reward, E * 8)); CUDA_TRY(A((void**)&h->out.scaled_collision_reward, E * 8));
+    CUDA_TRY(A((void**)&h->out.dist_reward, E * 8)); CUDA_TRY(A((void**)&h->out.trial_success, E)); CUDA_TRY(A((void**)&h->out.status, E * 4));
+    CUDA_TRY(A((void**)&h->d_layout_ids, E * 4));
+    *out_h = h;
+    return BP_OK;
+}
+
+int bp_shipice_destroy(bp_shipice_t* h) {
+    if (!h) return BP_OK;
+    cudaSetDevice(h->cfg.device);
+    for (void* p : h->dev_allocs) cudaFree(p);
+    if (h->mem) cudaFree(h->mem);
+    if (h->counter) cudaFree(h->counter);
+    if (h->d_actions) cudaFree(h->d_actions);
+    if (h->d_obs) cudaFree(h->d_obs);
+    if (h->h_actions) cudaFreeHost(h->h_actions);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    delete h;
+    return BP_OK;
+}
+
+int bp_shipice_load_layouts(bp_shipice_t* h, int32_t n_layouts, const int32_t* n_floes, const int32_t* n_verts,
+                            const double* verts, const double* centres, const double* ship_state) {
+    if (!h || n_layouts <= 0 || !n_floes || !n_verts || !verts || !centres || !ship_state) return fail(BP_ERR_INVALID, "null / empty layout arguments");
+    if (h->layouts_loaded) return fail(BP_ERR_STATE, "layouts already loaded for this handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    ShipIceMaterial mat;
+    mat.density = h->cfg.obstacle_density;
+    std::string err = build_shipice_layouts(h->H, n_layouts, h->cfg.max_floes, n_floes, n_verts, verts, centres, ship_state,
+                                            h->cfg.ship_verts, h->cfg.n_ship_verts, mat);
+    if (!err.empty()) return fail(BP_ERR_INVALID, err);
+    HostLayouts& H = h->H;
+    int rc;
+    if ((rc = dev_upload(h, H.lv, &h->T.lv))) return rc;
+    if ((rc = dev_upload(h, H.ln, &h->T.ln))) return rc;
+    if ((rc = dev_upload(h, H.nv, &h->T.nv))) return rc;
+    if ((rc = dev_upload(h, H.rad, &h->T.rad))) return rc;
+    if ((rc = dev_upload(h, H.minv, &h->T.minv))) return rc;
+    if ((rc = dev_upload(h, H.iinv, &h->T.iinv))) return rc;
+    if ((rc = dev_upload(h, H.cog, &h->T.cog))) return rc;
+    if ((rc = dev_upload(h, H.mat_e, &h->T.mat_e))) return rc;
+    if ((rc = dev_upload(h, H.mat_u, &h->T.mat_u))) return rc;
+    if ((rc = dev_upload(h, H.init, &h->T.init))) return rc;
+    if ((rc = dev_upload(h, H.nbody, &h->T.nbody))) return rc;
+    const double* p; const int* q;
+    if ((rc = dev_upload(h, H.rawv, &p))) return rc; h->d_rawv = (double*)p;
+    if ((rc = dev_upload(h, H.rawcen, &p))) return rc; h->d_rawcen = (double*)p;
+    if ((rc = dev_upload(h, H.rawn, &q))) return rc; h->d_rawn = (int*)q;
+    h->d.n_layouts = n_layouts;
+    h->layouts_loaded = true;
+    return BP_OK;
+}
+
+static int copy_outputs(bp_shipice* h, const bp_shipice_outputs* o, cudaStream_t st, cudaMemcpyKind kind) {
+    size_t E = h->d.n_envs;
+    if (!o) return BP_OK;
+#define CP(dst, src, bytes) if (dst) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, kind, st));
+    CP(o->reward, h->out.reward, E * 8) CP(o->terminated, h->out.terminated, E) CP(o->truncated, h->out.truncated, E)
+    CP(o->state, h->out.state, E * 24) CP(o->pose, h->out.pose, E * 24) CP(o->total_work, h->out.total_work, E * 8)
+    CP(o->collision_reward, h->out.collision_reward, E * 8) CP(o->scaled_collision_reward, h->out.scaled_collision_reward, E * 8)
+    CP(o->dist_reward, h->out.dist_reward, E * 8) CP(o->trial_success, h->out.trial_success, E) CP(o->status, h->out.status, E * 4)
+#undef CP
+    return BP_OK;
+}
+
+static int launch_obs(bp_shipice* h, uint8_t* obs, const uint8_t* mask, cudaStream_t st) {
+    if (!obs) return BP_OK;
+    ObsArgs oa;
+    oa.mem = h->mem; oa.env_bytes = h->env_bytes; oa.d = h->d; oa.T = h->T; oa.O = h->O;
+    oa.rawv = h->d_rawv; oa.rawn = h->d_rawn; oa.rawcen = h->d_rawcen; oa.mask = mask; oa.obs = obs;
+    k_shipice_obs<<<h->d.n_envs, 256, 0, st>>>(oa);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BP_OK;
+}
+
+static int sim_grid(bp_shipice* h) {
+    // 4 warps per block; enough resident blocks to fill the SMs, never more warps than envs
+    int blocks = h->sm_count * 4;
+    int need = (h->d.n_envs + 3) / 4;
+    return blocks < need ? blocks : need;
+}
+
+int bp_shipice_reset(bp_shipice_t* h, const int32_t* layout_ids, const uint8_t* mask, const bp_shipice_outputs* out, void* stream) {
+    if (!h || !layout_ids) return fail(BP_ERR_INVALID, "null argument");
+    if (!h->layouts_loaded) return fail(BP_ERR_STATE, "load layouts before reset");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(h->counter, 0, 4, st));
+    StepArgs a;
+    a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
+    a.actions = nullptr; a.layout_ids = layout_ids; a.mask = mask; a.counter = h->counter; a.auto_reset = 0;
+    k_shipice_reset<<<sim_grid(h), 128, 0, st>>>(a);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    int rc = launch_obs(h, out ? out->obs : nullptr, mask, st);
+    if (rc) return rc;
+    h->was_reset = true;
+    return copy_outputs(h, out, st, cudaMemcpyDeviceToDevice);
+}
+
+int bp_shipice_step(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out, void* stream) {
+    if (!h || !actions) return fail(BP_ERR_INVALID, "null argument");
+    if (!h->was_reset) return fail(BP_ERR_STATE, "reset before step");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(h->counter, 0, 4, st));
+    StepArgs a;
+    a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
+    a.actions = actions; a.layout_ids = nullptr; a.mask = nullptr; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset;
+    k_shipice_step<<<sim_grid(h), 128, 0, st>>>(a);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    int rc = launch_obs(h, out ? out->obs : nullptr, nullptr, st);
+    if (rc) return rc;
+    return copy_outputs(h, out, st, cudaMemcpyDeviceToDevice);
+}
+
+int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* oh) {
+    if (!h || !actions || !oh) return fail(BP_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    size_t E = h->d.n_envs;
+    if (!h->d_actions) CUDA_TRY(cudaMalloc((void**)&h->d_actions, E * 4));
+    if (oh->obs && !h->d_obs) CUDA_TRY(cudaMalloc((void**)&h->d_obs, E * BP_OBS_C * OBS_PIX));
+    CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions, E * 4, cudaMemcpyHostToDevice, 0));
+    bp_shipice_outputs dev;
+    memset(&dev, 0, sizeof(dev));
+    dev.obs = oh->obs ? h->d_obs : nullptr;
+    int rc = bp_shipice_step(h, h->d_actions, &dev, nullptr);
+    if (rc) return rc;
+    if (oh->obs) CUDA_TRY(cudaMemcpyAsync(oh->obs, h->d_obs, E * BP_OBS_C * OBS_PIX, cudaMemcpyDeviceToHost, 0));
+    rc = copy_outputs(h, oh, 0, cudaMemcpyDeviceToHost);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(0));
+    return BP_OK;
+}
+
+static int fetch_env(bp_shipice* h, int env, std::vector<char>& buf) {
+    if (env < 0 || env >= h->d.n_envs) return fail(BP_ERR_INVALID, "env index out of range");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    buf.resize(h->env_bytes);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(buf.data(), h->mem + h->env_bytes * (size_t)env, h->env_bytes, cudaMemcpyDeviceToHost));
+    return BP_OK;
+}
+static LayoutView host_layout_view(bp_shipice* h, int l) {
+    LayoutTab T;
+    HostLayouts& H = h->H;
+    T.lv = H.lv.data(); T.ln = H.ln.data(); T.nv = H.nv.data(); T.rad = H.rad.data(); T.minv = H.minv.data(); T.iinv = H.iinv.data();
+    T.cog = H.cog.data(); T.mat_e = H.mat_e.data(); T.mat_u = H.mat_u.data(); T.init = H.init.data(); T.nbody = H.nbody.data();
+    LayoutView L;
+    size_t o = (size_t)l * h->d.NB;
+    L.lv = T.lv + o * VMAX * 2; L.ln = T.ln + o * VMAX * 2; L.nv = T.nv + o; L.rad = T.rad + o; L.minv = T.minv + o; L.iinv = T.iinv + o;
+    L.cog = T.cog + o * 2; L.mat_e = T.mat_e + o; L.mat_u = T.mat_u + o; L.init = T.init + o * 3; L.nbody = T.nbody[l];
+    return L;
+}
+
+int bp_shipice_get_obstacles(bp_shipice_t* h, int32_t env, double* verts, int32_t* n_verts) {
+    if (!h || !verts || !n_verts) return fail(BP_ERR_INVALID, "null argument");
+    if (!h->was_reset) return fail(BP_ERR_STATE, "reset first");
+    std::vector<char> buf;
+    int rc = fetch_env(h, env, buf);
+    if (rc) return rc;
+    EnvView ev = make_view(buf.data(), h->d);
+    LayoutView L = host_layout_view(h, ev.sc->layout);
+    int nf = ev.sc->nbody - 1;
+    for (int b = 0; b < nf; b++) {
+        n_verts[b] = L.nv[b];
+        memcpy(verts + (size_t)b * VMAX * 2, ev.wv + (size_t)b * VMAX * 2, sizeof(double) * 2 * L.nv[b]);
+    }
+    return nf;
+}
+
+int bp_shipice_get_bodies(bp_shipice_t* h, int32_t env, double* out) {
+    if (!h || !out) return fail(BP_ERR_INVALID, "null argument");
+    if (!h->was_reset) return fail(BP_ERR_STATE, "reset first");
+    std::vector<char> buf;
+    int rc = fetch_env(h, env, buf);
+    if (rc) return rc;
+    EnvView ev = make_view(buf.data(), h->d);
+    LayoutView L = host_layout_view(h, ev.sc->layout);
+    int nb = ev.sc->nbody;
+    for (int b = 0; b < nb; b++) {
+        double c = ev.rc[b], s = ev.rs[b], cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
+        out[6 * b] = ev.px[b] - (cx * c - cy * s); out[6 * b + 1] = ev.py[b] - (cx * s + cy * c); out[6 * b + 2] = ev.pa[b];
+        out[6 * b + 3] = ev.vx[b]; out[6 * b + 4] = ev.vy[b]; out[6 * b + 5] = ev.vw[b];
+    }
+    return nb;
+}
+
+int bp_shipice_get_counters(bp_shipice_t* h, int32_t env, int64_t* o) {
+    if (!h || !o) return fail(BP_ERR_INVALID, "null argument");
+    std::vector<char> buf;
+    int rc = fetch_env(h, env, buf);
+    if (rc) return rc;
+    EnvView ev = make_view(buf.data(), h->d);
+    EnvScal* s = ev.sc;
+    o[0] = s->stamp; o[1] = s->n_awake; o[2] = s->n_pairs; o[3] = s->n_free; o[4] = s->n_order; o[5] = s->n_colours;
+    o[6] = s->status; o[7] = s->n_apairs; o[8] = s->n_cached; o[9] = s->stat_gjk; o[10] = s->stat_pairs_eval;
+    o[11] = s->stat_live_sum; o[12] = s->stat_awake_sum; o[13] = s->stat_recolour; o[14] = s->stat_rebuild; o[15] = s->stat_substeps;
+    return BP_OK;
+}
+
+size_t bp_shipice_env_bytes(bp_shipice_t* h) { return h ? h->env_bytes : 0; }
+int64_t bp_shipice_launch_count(bp_shipice_t* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ spfa
+static int* g_spfa_scratch = nullptr; static size_t g_spfa_scratch_bytes = 0; static int* g_spfa_counter = nullptr;
+
+int bp_spfa_batch(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t H, int32_t W, float* dists, int32_t* parents, void* stream) {
+    if (!maps || !sources || !dists || !parents) return fail(BP_ERR_INVALID, "null argument");
+    if (batch <= 0 || H <= 0 || W <= 0 || (long long)H * W > (1ll << 26)) return fail(BP_ERR_INVALID, "bad batch / grid size");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int blocks = sms * 4; if (blocks > batch) blocks = batch;
+    size_t need = (size_t)blocks * 3 * H * W * sizeof(int);
+    if (need > g_spfa_scratch_bytes) {
+        if (g_spfa_scratch) CUDA_TRY(cudaFree(g_spfa_scratch));
+        g_spfa_scratch = nullptr; g_spfa_scratch_bytes = 0;
+        CUDA_TRY(cudaMalloc((void**)&g_spfa_scratch, need));
+        g_spfa_scratch_bytes = need;
+    }
+    if (!g_spfa_counter) CUDA_TRY(cudaMalloc((void**)&g_spfa_counter, 64));
+    CUDA_TRY(cudaMemsetAsync(g_spfa_counter, 0, 4, st));
+    k_spfa<<<blocks, 512, 0, st>>>(maps, sources, batch, H, W, dists, parents, g_spfa_scratch, g_spfa_counter);
+    CUDA_TRY(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t H, int32_t W, float* dists, int32_t* parents) {
+    if (!maps || !sources || !dists || !parents) return fail(BP_ERR_INVALID, "null argument");
+    size_t nv = (size_t)H * W * batch;
+    uint8_t* dm = nullptr; int32_t* ds = nullptr; float* dd = nullptr; int32_t* dp = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dm, nv)); CUDA_TRY(cudaMalloc((void**)&ds, (size_t)batch * 8));
+    CUDA_TRY(cudaMalloc((void**)&dd, nv * 4)); CUDA_TRY(cudaMalloc((void**)&dp, nv * 4));
+    CUDA_TRY(cudaMemcpy(dm, maps, nv, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ds, sources, (size_t)batch * 8, cudaMemcpyHostToDevice));
+    int rc = bp_spfa_batch(dm, ds, batch, H, W, dd, dp, nullptr);
+    if (rc == BP_OK) {
+        cudaError_t e1 = cudaMemcpy(dists, dd, nv * 4, cudaMemcpyDeviceToHost);
+        cudaError_t e2 = cudaMemcpy(parents, dp, nv * 4, cudaMemcpyDeviceToHost);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(BP_ERR_CUDA, "spfa result copy failed");
+    }
+    cudaFree(dm); cudaFree(ds); cudaFree(dd); cudaFree(dp);
+    return rc;
+}
+
+}  // extern "C"

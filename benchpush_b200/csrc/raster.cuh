@@ -1,0 +1,265 @@
+// Egocentric observation rasteriser for ship-ice-v0: one thread block per environment, the four
+// 150x150 channels are composed in shared memory and written to HBM once, coalesced.
+//
+// Follows ShipIceEnv.generate_observation (ship_ice_env.py:378-409, egocentric branch) and the
+// OccupancyGrid methods it calls (occupancy_map.py:37-65 compute_occ_img, :112-140
+// ego_view_obstacle_map, :300-337 _compute_global_footprint, :379-410 ego_view_footprint, :413-433
+// global_goal_dist_transform, :492-521 ego_view_goal_dist_transform, :524-554 global_orientation_map,
+// :557-587 ego_view_orientation_map).  Third-party primitives restated bit-exactly:
+//   * skimage.draw.polygon -> point_in_polygon of skimage/_shared/geometry.pyx (crossing test in
+//     which vertices (|d| < 1e-12) and edges count as inside), evaluated in fp64 without FMA; the
+//     quotient test (x0*y1 - x1*y0)/(y1 - y0) > 0 is evaluated as a sign test of numerator and
+//     denominator, which is exact because an IEEE quotient of finite non-zero operands of this
+//     magnitude cannot underflow to zero;
+//   * cv2.line(thickness=1, LINE_8, shift=0) -> clipLine + the 8-connected LineIterator,
+//     including the reference's uint16 cast of the end points (occupancy_map.py:546-547).
+// Only the pixels of the 150x150 window are ever produced (the reference builds 1000x300 global
+// maps and crops); the result is identical because every global map is a pure function of the pixel.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "sim_core.cuh"
+
+#if defined(__CUDACC__) && !defined(BP_HOST_EMU)
+#define BP_TID ((int)threadIdx.x)
+#define BP_NT ((int)blockDim.x)
+#define BP_BSYNC() __syncthreads()
+#define BP_SMEM_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#else
+#define BP_TID 0
+#define BP_NT 1
+#define BP_BSYNC()
+static inline int bp_emu_atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
+#define BP_SMEM_ATOMIC_ADD(p, v) bp_emu_atomic_add((p), (v))
+#endif
+
+namespace bp {
+
+constexpr int OBS_WIN = 150;
+constexpr int OBS_PIX = OBS_WIN * OBS_WIN;
+constexpr int MAX_ROBOT_RAW = 32;
+constexpr int MAX_CAND = 512;
+
+struct ObsParams {
+    int grid_h, grid_w;          // 1000, 300  (int(map/grid))
+    double scale;                // m_to_pix_scale = occ_map_width / map_width = 25
+    double vshift;               // local_window_v_shift = 2
+    double goal_y;               // cfg.goal_y
+    double g2m;                  // map_height / occ_map_height = 0.04
+    double range_x, range_y;     // local_range = [12, 12]
+    int n_robot_raw;
+    double robot_raw[2 * MAX_ROBOT_RAW];
+    double head[2], tail[2];
+};
+
+// skimage point_in_polygon on vertices (px[i], py[i]) = (vx[2i]*sx, vx[2i+1]*sy); != 0 means inside.
+BP_DEV bool pip_inclusive(const double* v, int n, double scale, double x, double y) {
+    const double eps = 1e-12;
+    unsigned r_cross = 0, l_cross = 0;
+    double x1 = v[2 * (n - 1)] * scale - x;
+    double y1 = v[2 * (n - 1) + 1] * scale - y;
+    for (int i = 0; i < n; i++) {
+        double x0 = v[2 * i] * scale - x;
+        double y0 = v[2 * i + 1] * scale - y;
+        if ((-eps < x0 && x0 < eps) && (-eps < y0 && y0 < eps)) return true;
+        bool sr = (y0 > 0) != (y1 > 0);
+        bool sl = (y0 < 0) != (y1 < 0);
+        if (sr || sl) {
+            double num = x0 * y1 - x1 * y0;
+            double den = y1 - y0;
+            bool pos = (num > 0 && den > 0) || (num < 0 && den < 0);
+            bool ngt = (num > 0 && den < 0) || (num < 0 && den > 0);
+            if (sr && pos) r_cross++;
+            if (sl && ngt) l_cross++;
+        }
+        x1 = x0; y1 = y0;
+    }
+    if ((r_cross & 1) != (l_cross & 1)) return true;
+    return (r_cross & 1) != 0;
+}
+
+// cv::clipLine on 64-bit points
+BP_DEV bool clip_line(long long W, long long H, long long& x1, long long& y1, long long& x2, long long& y2) {
+    long long right = W - 1, bottom = H - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += (long long)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += (long long)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += (long long)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+                x1 = a; c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += (long long)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+                x2 = a; c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// numpy float64 -> uint16 cast as executed on x86-64 (truncate to integer, keep the low 16 bits)
+BP_DEV long long cast_u16(double x) { return (long long)((unsigned short)(long long)x); }
+
+// Draw the orientation line (value 127) and the head pixel (255) into the window-local map.
+BP_DEV void draw_orientation(unsigned char* loc, const ObsParams& O, double px, double py, double c, double s, int gi0, int gj0) {
+    double ms = -s;
+    double hx = O.head[0] * c + O.head[1] * ms + px, hy = O.head[0] * s + O.head[1] * c + py;
+    double tx = O.tail[0] * c + O.tail[1] * ms + px, ty = O.tail[0] * s + O.tail[1] * c + py;
+    long long x1 = cast_u16(hx * O.scale), y1 = cast_u16(hy * O.scale);
+    long long x2 = cast_u16(tx * O.scale), y2 = cast_u16(ty * O.scale);
+    long long hpx = x1, hpy = y1;
+    const long long W = O.grid_w, H = O.grid_h;
+    bool ok = true;
+    if (!(x1 >= 0 && x1 < W && x2 >= 0 && x2 < W && y1 >= 0 && y1 < H && y2 >= 0 && y2 < H)) ok = clip_line(W, H, x1, y1, x2, y2);
+    if (ok) {
+        long long dx = x2 - x1, dy = y2 - y1;
+        long long sx = 1, sy = 1;
+        if (dx < 0) { dx = -dx; dy = -dy; x1 = x2; y1 = y2; }
+        if (dy < 0) { dy = -dy; sy = -1; }
+        bool vert = dy > dx;
+        if (vert) { long long t = dx; dx = dy; dy = t; }
+        long long err = dx - 2 * dy, plusDelta = 2 * dx, minusDelta = -2 * dy;
+        long long x = x1, y = y1;
+        for (long long i = 0; i <= dx; i++) {
+            long long li = y - gi0, lj = x - gj0;
+            if (li >= 0 && li < OBS_WIN && lj >= 0 && lj < OBS_WIN) loc[li * OBS_WIN + lj] = 127;
+            bool m = err < 0;
+            err += minusDelta + (m ? plusDelta : 0);
+            if (vert) { y += sy; if (m) x += sx; } else { x += sx; if (m) y += sy; }
+        }
+    }
+    // np.clip(head_pix, [0,0], [W-1,H-1]); global_orientation[head_y, head_x] = 1.0
+    if (hpx > W - 1) hpx = W - 1;
+    if (hpy > H - 1) hpy = H - 1;
+    long long li = hpy - gi0, lj = hpx - gj0;
+    if (li >= 0 && li < OBS_WIN && lj >= 0 && lj < OBS_WIN) loc[li * OBS_WIN + lj] = 255;
+}
+
+// Shared-memory working set of one block.
+struct ObsSmem {
+    unsigned char occ[OBS_PIX];
+    unsigned char ori[OBS_PIX];
+    double fpv[2 * MAX_ROBOT_RAW];      // in-grid robot vertices in metres (scaled on use)
+    int cand[MAX_CAND];
+    int n_cand, n_fp, cand_overflow;
+};
+
+// Compose the observation of one env.  verts/nverts/cen describe the obstacles as world-space
+// polygons: after a step these are the hull vertices wv (get_obs_from_poly), at reset the raw trial
+// vertices.  poly_stride = doubles between consecutive polygons.
+BP_DEV void render_obs(ObsSmem& S, const ObsParams& O, int n_obst, const double* verts, int poly_stride, const int* nverts,
+                       const double* cenx, const double* ceny, int cen_stride, double rx, double ry, double ra,
+                       unsigned char* out /* [4][150][150] */) {
+    const int tid = BP_TID, nt = BP_NT;
+    double s, c; bp_sincos(ra, &s, &c);
+    // window origin (occupancy_map.py:121-129): int() truncates toward zero
+    const int window_x = (int)(rx * O.scale);
+    const int window_y = (int)((ry + O.vshift) * O.scale);
+    const int gi0 = window_y - OBS_WIN / 2, gj0 = window_x - OBS_WIN / 2;
+    for (int i = tid; i < OBS_PIX; i += nt) { S.occ[i] = 0; S.ori[i] = 0; }
+    if (tid == 0) {
+        S.n_cand = 0; S.cand_overflow = 0;
+        // footprint vertices: all configured vertices, those outside the grid are dropped (occupancy_map.py:320-330)
+        int k = 0; double ms = -s;
+        for (int i = 0; i < O.n_robot_raw; i++) {
+            double vx = O.robot_raw[2 * i], vy = O.robot_raw[2 * i + 1];
+            double wx = vx * c + vy * ms + rx, wy = vx * s + vy * c + ry;
+            double gx = wx * O.scale, gy = wy * O.scale;
+            if (gy < 0 || gy >= O.grid_h || gx < 0 || gx >= O.grid_w) continue;
+            S.fpv[2 * k] = wx; S.fpv[2 * k + 1] = wy; k++;
+        }
+        S.n_fp = k;
+    }
+    BP_BSYNC();
+    if (tid == 0) draw_orientation(S.ori, O, rx, ry, c, s, gi0, gj0);
+    // candidate obstacles: pass the local-range test and can touch the window
+    const double wl = (double)gj0 - 2.0, wr = (double)(gj0 + OBS_WIN) + 2.0, wb = (double)gi0 - 2.0, wt = (double)(gi0 + OBS_WIN) + 2.0;
+    for (int b = tid; b < n_obst; b += nt) {
+        double cx = cenx[(size_t)b * cen_stride], cy = ceny[(size_t)b * cen_stride];
+        if (fabs(rx - cx) > O.range_x || fabs(ry - cy) > O.range_y) continue;
+        const double* v = verts + (size_t)b * poly_stride;
+        int n = nverts[b];
+        double l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
+        for (int i = 0; i < n; i++) {
+            double x = v[2 * i] * O.scale, y = v[2 * i + 1] * O.scale;
+            l = fmin(l, x); r = fmax(r, x); bt = fmin(bt, y); tp = fmax(tp, y);
+        }
+        if (r < wl || l > wr || tp < wb || bt > wt) continue;
+        int k = BP_SMEM_ATOMIC_ADD(&S.n_cand, 1);
+        if (k < MAX_CAND) S.cand[k] = b; else S.cand_overflow = 1;
+    }
+    BP_BSYNC();
+    int nc = S.n_cand < MAX_CAND ? S.n_cand : MAX_CAND;
+    for (int k = 0; k < nc; k++) {
+        int b = S.cand[k];
+        const double* v = verts + (size_t)b * poly_stride;
+        int n = nverts[b];
+        double rmin = INFINITY, rmax = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
+        for (int i = 0; i < n; i++) {
+            double x = v[2 * i] * O.scale, y = v[2 * i + 1] * O.scale;
+            cmin = fmin(cmin, x); cmax = fmax(cmax, x); rmin = fmin(rmin, y); rmax = fmax(rmax, y);
+        }
+        // skimage _polygon bounding box, clipped to the global image, then to the window
+        long long minr = (long long)fmax(0.0, rmin), maxr = (long long)ceil(rmax);
+        long long minc = (long long)fmax(0.0, cmin), maxc = (long long)ceil(cmax);
+        if (maxr > O.grid_h - 1) maxr = O.grid_h - 1;
+        if (maxc > O.grid_w - 1) maxc = O.grid_w - 1;
+        if (minr < gi0) minr = gi0;
+        if (minc < gj0) minc = gj0;
+        if (maxr > gi0 + OBS_WIN - 1) maxr = gi0 + OBS_WIN - 1;
+        if (maxc > gj0 + OBS_WIN - 1) maxc = gj0 + OBS_WIN - 1;
+        if (maxr < minr || maxc < minc) continue;
+        int bw = (int)(maxc - minc + 1), bh = (int)(maxr - minr + 1);
+        for (int i = tid; i < bw * bh; i += nt) {
+            int rr = (int)minr + i / bw, cc = (int)minc + i % bw;
+            if (pip_inclusive(v, n, O.scale, (double)cc, (double)rr)) S.occ[(rr - gi0) * OBS_WIN + (cc - gj0)] = 255;
+        }
+    }
+    BP_BSYNC();
+    // footprint bounding box (draw.polygon without a shape argument)
+    long long fminr = 0, fmaxr = -1, fminc = 0, fmaxc = -1;
+    if (S.n_fp > 0) {
+        double rmin = INFINITY, rmax = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
+        for (int i = 0; i < S.n_fp; i++) {
+            double x = S.fpv[2 * i] * O.scale, y = S.fpv[2 * i + 1] * O.scale;
+            cmin = fmin(cmin, x); cmax = fmax(cmax, x); rmin = fmin(rmin, y); rmax = fmax(rmax, y);
+        }
+        fminr = (long long)fmax(0.0, rmin); fmaxr = (long long)ceil(rmax);
+        fminc = (long long)fmax(0.0, cmin); fmaxc = (long long)ceil(cmax);
+    }
+    for (int i = tid; i < OBS_PIX; i += nt) {
+        int li = i / OBS_WIN, lj = i % OBS_WIN;
+        int gi = gi0 + li, gj = gj0 + lj;
+        bool inb = !(gi < 0 || gi >= O.grid_h || gj < 0 || gj >= O.grid_w);
+        unsigned char fp = 0, edt = 255, ori = 0, occ = 0;
+        if (inb) {
+            fp = 127;
+            if (gi >= fminr && gi <= fmaxr && gj >= fminc && gj <= fmaxc && pip_inclusive(S.fpv, S.n_fp, O.scale, (double)gj, (double)gi)) fp = 255;
+            double dgoal = O.goal_y - gi * O.g2m;
+            if (dgoal < 0) dgoal = 0;
+            edt = (unsigned char)(int)((dgoal / O.goal_y) * 255.0);
+            ori = S.ori[i];
+            occ = S.occ[i];
+        }
+        out[i] = fp; out[OBS_PIX + i] = edt; out[2 * OBS_PIX + i] = ori; out[3 * OBS_PIX + i] = occ;
+    }
+    BP_BSYNC();
+}
+
+}  // namespace bp

@@ -81,7 +81,8 @@ struct LayoutTab {
 struct EnvScal {
     int stamp, n_awake, n_pairs, cur, n_free, n_order, n_colours, dirty;
     int status, layout, nbody, robot, t, rebuild, n_apairs, n_cached;
-    int any_wake, episode, pad1, pad2;
+    int any_wake, episode, done, first_layout;
+    int obs_raw, pad0, pad1, pad2;
     double total_work;
     long long stat_gjk, stat_pairs_eval, stat_live_sum, stat_awake_sum, stat_recolour, stat_rebuild, stat_substeps;
 };

@@ -1,0 +1,104 @@
+// Batched single-source shortest paths on 8-connected boolean grids: one thread block per map.
+//
+// Replaces spfa.spfa (reference deps/spfa/src/main.cpp:10-116).  The reference relaxes edges with a
+// sequential SPFA queue in fp32 (weights 1 and sqrtf(2), :14,:74).  Because fp32 addition is
+// monotone, every label-correcting schedule converges to the same least fixed point
+//     d[v] = min_u fl32(d[u] + w(u,v)),  d[source] = 0,
+// so a frontier-parallel relaxation with atomicMin on the (non-negative, hence order-preserving)
+// float bit patterns yields distances BIT-IDENTICAL to the reference.  Parents are chosen
+// deterministically afterwards (first neighbour, in the reference's direction order, that attains
+// the minimum); the reference's own tie-break depends on its queue order.
+// Quirks kept: moves between two free cells are allowed regardless of the orthogonal neighbours
+// (no corner-cutting check, :50-61); unreachable cells report 0 (:101); "infinity" = 2*H*W (:28);
+// a blocked source reaches nothing.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "raster.cuh"   // BP_TID / BP_NT / BP_BSYNC
+
+namespace bp {
+
+#if defined(__CUDACC__) && !defined(BP_HOST_EMU)
+BP_DEV int spfa_atomic_min(int* p, int v) { return atomicMin(p, v); }
+BP_DEV int spfa_atomic_exch(int* p, int v) { return atomicExch(p, v); }
+BP_DEV int spfa_atomic_add(int* p, int v) { return atomicAdd(p, v); }
+BP_DEV int f2i(float f) { return __float_as_int(f); }
+BP_DEV float i2f(int i) { return __int_as_float(i); }
+#else
+BP_DEV int spfa_atomic_min(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+BP_DEV int spfa_atomic_exch(int* p, int v) { int o = *p; *p = v; return o; }
+BP_DEV int spfa_atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
+BP_DEV int f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
+BP_DEV float i2f(int i) { float f; memcpy(&f, &i, 4); return f; }
+#endif
+
+struct SpfaShared { int n_next; };
+
+// scratch: q0[HW], q1[HW], mark[HW] (ints).  dist_out doubles as the working distance array.
+BP_DEV void spfa_block(SpfaShared& S, const uint8_t* map, int H, int W, int si, int sj, float* dist_out, int32_t* parents,
+                       int* q0, int* q1, int* mark) {
+    const int tid = BP_TID, nt = BP_NT;
+    const int nv = H * W;
+    const float inf = 2.0f * (float)nv;
+    const float s2 = sqrtf(2.0f);
+    const int di[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+    const int dj[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
+    int* dist = (int*)dist_out;
+    const int inf_i = f2i(inf);
+    for (int v = tid; v < nv; v += nt) { dist[v] = inf_i; mark[v] = 0; }
+    BP_BSYNC();
+    const int s = si * W + sj;
+    if (tid == 0) { dist[s] = f2i(0.0f); q0[0] = s; S.n_next = 0; }
+    BP_BSYNC();
+    int n_cur = 1, iter = 1;
+    while (n_cur > 0) {
+        for (int idx = tid; idx < n_cur; idx += nt) {
+            int u = q0[idx];
+            if (!map[u]) continue;
+            float du = i2f(*(volatile int*)&dist[u]);
+            int ui = u / W, uj = u - ui * W;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                int ip = ui + di[k], jp = uj + dj[k];
+                if (ip < 0 || jp < 0 || ip >= H || jp >= W) continue;
+                int v = ip * W + jp;
+                if (!map[v]) continue;
+                float nd = du + ((k & 1) ? 1.0f : s2);
+                int ndi = f2i(nd);
+                int old = spfa_atomic_min(&dist[v], ndi);
+                if (ndi < old) {
+                    if (spfa_atomic_exch(&mark[v], iter) != iter) { int pos = spfa_atomic_add(&S.n_next, 1); q1[pos] = v; }
+                }
+            }
+        }
+        BP_BSYNC();
+        n_cur = S.n_next;
+        BP_BSYNC();
+        if (tid == 0) S.n_next = 0;
+        int* t = q0; q0 = q1; q1 = t;
+        iter++;
+        BP_BSYNC();
+    }
+    // parents + output convention
+    for (int v = tid; v < nv; v += nt) {
+        float d = i2f(dist[v]);
+        int par = -1;
+        if (v != s && d < inf && map[v]) {
+            int vi = v / W, vj = v - vi * W;
+            for (int k = 0; k < 8 && par < 0; k++) {
+                int ip = vi - di[k], jp = vj - dj[k];       // u such that u + dir[k] = v
+                if (ip < 0 || jp < 0 || ip >= H || jp >= W) continue;
+                int u = ip * W + jp;
+                if (!map[u]) continue;
+                float du = i2f(dist[u]);
+                if (du < inf && du + ((k & 1) ? 1.0f : s2) == d) par = u;
+            }
+        }
+        parents[v] = par;
+    }
+    BP_BSYNC();
+    for (int v = tid; v < nv; v += nt) { float d = i2f(dist[v]); dist_out[v] = (d < inf) ? d : 0.0f; }
+    BP_BSYNC();
+}
+
+}  // namespace bp

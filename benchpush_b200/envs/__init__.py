@@ -1,0 +1,12 @@
+"""Batched environments.  Ids follow the reference registry (benchpush/environments/__init__.py:3-51)."""
+from .ship_ice import ShipIceVecEnv
+
+REGISTRY = {"ship-ice-v0": ShipIceVecEnv}
+MAX_EPISODE_STEPS = {"ship-ice-v0": 300, "box-delivery-v0": 30000, "area-clearing-v0": 400, "maze-NAMO-v0": 30000}
+
+
+def make(env_id: str, num_envs: int, cfg=None, **kw):
+    """Vector analogue of ``gym.make(id, cfg=cfg)``."""
+    if env_id not in REGISTRY:
+        raise KeyError(f"{env_id!r} is not available in benchpush_b200 (have: {sorted(REGISTRY)})")
+    return REGISTRY[env_id](num_envs=num_envs, cfg=cfg, **kw)

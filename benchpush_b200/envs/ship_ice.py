@@ -1,0 +1,239 @@
+"""``ship-ice-v0`` as a batched environment on one B200.
+
+Keeps the reference's gym-style API (``ShipIceEnv``, ship_ice_env.py:37-355): ``reset() -> (obs, info)``,
+``step(action) -> (obs, reward, terminated, truncated, info)``, the cfg dict with the same keys and
+the same one-level merge, and the same ``info`` keys — but every return value carries a leading
+batch dimension and lives on the GPU as a torch tensor.  All simulation work happens in
+``libbenchpush_b200.so`` (CUDA, sm_100a); torch only owns the buffers and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..layouts import PackedLayouts, generate_experiment, load_reference_pickle, pack_trials
+from ..utils import DotDict, merge_cfg
+
+_CFG_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "configs", "ship_ice.yaml")
+
+
+class _LazyObstacles:
+    """``info['obs']`` of the reference is the list of world-space vertex arrays of every floe
+    (cost_map.py:274-281).  Materialising it for a whole batch every step would move gigabytes, so
+    it is fetched per env on demand: ``info['obs'][e]`` -> list of (V_i, 2) float64 arrays."""
+
+    def __init__(self, env):
+        self._env = env
+
+    def __len__(self):
+        return self._env.num_envs
+
+    def __getitem__(self, e):
+        return self._env.get_obstacles(int(e))
+
+
+class ShipIceVecEnv:
+    metadata = {"render_modes": []}
+
+    def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[PackedLayouts] = None,
+                 trials: Optional[Sequence[dict]] = None, ice_file: Optional[str] = None, auto_reset: bool = False,
+                 first_trial: Optional[Sequence[int]] = None, synthetic_seed: int = 99, n_synthetic_trials: int = 100):
+        if not torch.cuda.is_available():
+            raise _lib.BenchPushError("ShipIceVecEnv needs a CUDA device (there is no CPU fallback)")
+        self.cfg = merge_cfg(DotDict.load_from_file(_CFG_PATH), cfg)
+        if self.cfg.low_dim_state or not self.cfg.egocentric_obs:
+            raise NotImplementedError("only the egocentric image observation is implemented (cfg.egocentric_obs=true, low_dim_state=false)")
+        if self.cfg.random_start:
+            raise NotImplementedError("cfg.random_start is not implemented: start poses come from the layouts")
+        assert self.cfg.concentration in [0.1, 0.2, 0.3, 0.4, 0.5], "concentration must be one of 0.1 .. 0.5 (ship_ice_env.py:75)"
+        self.num_envs = int(num_envs)
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.goal = (0, self.cfg.goal_y)
+        self.max_yaw_rate_step = (np.pi / 2) / 7
+        self.beta = 30
+        self.num_channels = 4
+        # ---- layouts (the reference loads experiments_XX_100_r06_d40x12.pk, ship_ice_env.py:76-80)
+        if layouts is None:
+            if trials is None:
+                if ice_file is not None:
+                    trials = load_reference_pickle(ice_file, self.cfg.concentration)
+                else:
+                    trials = generate_experiment(n_synthetic_trials, self.cfg.concentration, seed=synthetic_seed)
+            layouts = pack_trials(trials)
+        self.layouts = layouts
+        self.env_max_trial = layouts.n_layouts
+        # ---- native handle
+        L = _lib.lib()
+        c = _lib.ShipIceConfig()
+        L.bp_shipice_default_config(C.byref(c))
+        c.n_envs = self.num_envs
+        c.max_floes = layouts.max_floes
+        c.device = self.device_index
+        c.auto_reset = 1 if auto_reset else 0
+        c.dt = float(self.cfg.dt); c.steps = int(self.cfg.sim.steps); c.iterations = int(self.cfg.sim.iterations)
+        c.damping = float(self.cfg.sim.damping); c.obstacle_density = float(self.cfg.sim.obstacle_density)
+        c.target_speed = float(self.cfg.target_speed); c.goal_y = float(self.cfg.goal_y)
+        c.map_width = float(self.cfg.occ.map_width); c.map_height = float(self.cfg.occ.map_height)
+        c.m_to_pix_scale = int(self.cfg.occ.m_to_pix_scale)
+        if tuple(self.cfg.sim.gravity) != (0, 0):
+            raise NotImplementedError("non-zero gravity is not supported by the awake-set solver")
+        sv = np.asarray(self.cfg.ship.vertices, dtype=np.float64)
+        c.n_ship_verts = sv.shape[0]
+        for i, v in enumerate(sv.reshape(-1)):
+            c.ship_verts[i] = float(v)
+        c.ship_head[0], c.ship_head[1] = map(float, self.cfg.ship.head)
+        c.ship_tail[0], c.ship_tail[1] = map(float, self.cfg.ship.tail)
+        self._h = C.c_void_p()
+        _lib.check(L.bp_shipice_create(C.byref(c), C.byref(self._h)))
+        self._L = L
+        nf = np.ascontiguousarray(layouts.n_floes, dtype=np.int32)
+        nv = np.ascontiguousarray(layouts.n_verts, dtype=np.int32)
+        vs = np.ascontiguousarray(layouts.verts, dtype=np.float64)
+        ce = np.ascontiguousarray(layouts.centres, dtype=np.float64)
+        ss = np.ascontiguousarray(layouts.ship_state, dtype=np.float64)
+        _lib.check(L.bp_shipice_load_layouts(self._h, layouts.n_layouts, nf.ctypes.data, nv.ctypes.data, vs.ctypes.data,
+                                             ce.ctypes.data, ss.ctypes.data))
+        # ---- buffers
+        E, dev = self.num_envs, self.device
+        self.obs = torch.zeros((E,) + _lib.OBS_SHAPE, dtype=torch.uint8, device=dev)
+        self._reward = torch.zeros(E, dtype=torch.float64, device=dev)
+        self._terminated = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self._truncated = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self._state = torch.zeros((E, 3), dtype=torch.float64, device=dev)
+        self._pose = torch.zeros((E, 3), dtype=torch.float64, device=dev)
+        self._total_work = torch.zeros(E, dtype=torch.float64, device=dev)
+        self._coll = torch.zeros(E, dtype=torch.float64, device=dev)
+        self._scoll = torch.zeros(E, dtype=torch.float64, device=dev)
+        self._dist = torch.zeros(E, dtype=torch.float64, device=dev)
+        self._success = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self._status = torch.zeros(E, dtype=torch.int32, device=dev)
+        o = _lib.ShipIceOutputs()
+        o.obs = self.obs.data_ptr(); o.reward = self._reward.data_ptr(); o.terminated = self._terminated.data_ptr()
+        o.truncated = self._truncated.data_ptr(); o.state = self._state.data_ptr(); o.pose = self._pose.data_ptr()
+        o.total_work = self._total_work.data_ptr(); o.collision_reward = self._coll.data_ptr()
+        o.scaled_collision_reward = self._scoll.data_ptr(); o.dist_reward = self._dist.data_ptr()
+        o.trial_success = self._success.data_ptr(); o.status = self._status.data_ptr()
+        self._out = o
+        if first_trial is None:
+            first_trial = np.arange(E) % self.env_max_trial       # env e starts at trial e % n
+        self._next_trial = torch.as_tensor(np.asarray(first_trial, dtype=np.int32), device=dev)
+        self._actions = torch.zeros(E, dtype=torch.float32, device=dev)
+        self.observation_shape = _lib.OBS_SHAPE
+        self.action_low, self.action_high = -1.0, 1.0
+        self.check_status = True
+
+    # ------------------------------------------------------------------ gym-style API
+    @property
+    def unwrapped(self):
+        return self
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _info(self, reset: bool):
+        info = {"state": self._state, "total_work": self._total_work, "obs": _LazyObstacles(self), "pose": self._pose}
+        if not reset:
+            info.update({"collision reward": self._coll, "scaled collision reward": self._scoll, "dist reward": self._dist,
+                         "trial_success": self._success.bool()})
+        return info
+
+    def _raise_on_status(self):
+        if not self.check_status:
+            return
+        bad = int((self._status & 7).max().item())
+        if bad:
+            raise _lib.BenchPushError(f"per-env capacity overflow (status bits {bad}): raise pair_capacity / live_capacity")
+
+    def reset(self, seed=None, options=None, mask: Optional[torch.Tensor] = None):
+        """Reset all envs (or those with ``mask[e]`` set) to their next trial.  ``seed`` is accepted and
+        ignored, as in the reference (ship_ice_env.py:223): layouts are deterministic inputs."""
+        with torch.cuda.device(self.device):
+            mptr = None
+            if mask is not None:
+                mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+                mptr = C.c_void_p(mask.data_ptr())
+            _lib.check(self._L.bp_shipice_reset(self._h, C.c_void_p(self._next_trial.data_ptr()), mptr, C.byref(self._out), self._stream()))
+            if mask is None:
+                self._next_trial = (self._next_trial + 1) % self.env_max_trial
+            else:
+                self._next_trial = torch.where(mask.bool(), (self._next_trial + 1) % self.env_max_trial, self._next_trial)
+        self._raise_on_status()
+        return self.obs, self._info(reset=True)
+
+    def step(self, action):
+        with torch.cuda.device(self.device):
+            a = torch.as_tensor(action, dtype=torch.float32, device=self.device).reshape(self.num_envs)
+            self._actions.copy_(a)
+            _lib.check(self._L.bp_shipice_step(self._h, C.c_void_p(self._actions.data_ptr()), C.byref(self._out), self._stream()))
+        self._raise_on_status()
+        return self.obs, self._reward, self._terminated.bool(), self._truncated.bool(), self._info(reset=False)
+
+    def step_async_nocheck(self, action_dev: torch.Tensor):
+        """Enqueue one step without any host synchronisation (actions already on the device)."""
+        _lib.check(self._L.bp_shipice_step(self._h, C.c_void_p(action_dev.data_ptr()), C.byref(self._out), self._stream()))
+
+    def step_host(self, actions: np.ndarray, want_obs: bool = False):
+        """The same step through host buffers (numpy in, numpy out; copies inside)."""
+        E = self.num_envs
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(E)
+        if not hasattr(self, "_host"):
+            self._host = {"reward": np.zeros(E), "terminated": np.zeros(E, np.uint8), "truncated": np.zeros(E, np.uint8),
+                          "state": np.zeros((E, 3)), "total_work": np.zeros(E), "trial_success": np.zeros(E, np.uint8),
+                          "status": np.zeros(E, np.int32), "obs": None}
+        hb = self._host
+        if want_obs and hb["obs"] is None:
+            hb["obs"] = np.zeros((E,) + _lib.OBS_SHAPE, np.uint8)
+        o = _lib.ShipIceOutputs()
+        o.reward = hb["reward"].ctypes.data; o.terminated = hb["terminated"].ctypes.data; o.truncated = hb["truncated"].ctypes.data
+        o.state = hb["state"].ctypes.data; o.total_work = hb["total_work"].ctypes.data
+        o.trial_success = hb["trial_success"].ctypes.data; o.status = hb["status"].ctypes.data
+        if want_obs:
+            o.obs = hb["obs"].ctypes.data
+        _lib.check(self._L.bp_shipice_step_host(self._h, a.ctypes.data, C.byref(o)))
+        return hb
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.bp_shipice_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self):
+        raise NotImplementedError("rendering is out of scope for the batched simulator")
+
+    # ------------------------------------------------------------------ inspection helpers
+    def get_obstacles(self, e: int):
+        F = self.layouts.max_floes
+        verts = np.zeros((F, _lib.BP_VMAX, 2), dtype=np.float64)
+        nv = np.zeros(F, dtype=np.int32)
+        n = _lib.check(self._L.bp_shipice_get_obstacles(self._h, e, verts.ctypes.data, nv.ctypes.data))
+        return [verts[i, : nv[i]].copy() for i in range(n)]
+
+    def get_bodies(self, e: int) -> np.ndarray:
+        out = np.zeros((self.layouts.max_floes + 1, 6), dtype=np.float64)
+        n = _lib.check(self._L.bp_shipice_get_bodies(self._h, e, out.ctypes.data))
+        return out[:n]
+
+    def counters(self, e: int) -> dict:
+        o = np.zeros(16, dtype=np.int64)
+        _lib.check(self._L.bp_shipice_get_counters(self._h, e, o.ctypes.data))
+        keys = ["stamp", "n_awake", "n_pairs", "n_free", "n_order", "n_colours", "status", "n_apairs", "n_cached", "gjk",
+                "pairs_eval", "live_sum", "awake_sum", "recolour", "rebuild", "substeps"]
+        return dict(zip(keys, o.tolist()))
+
+    def env_bytes(self) -> int:
+        return int(self._L.bp_shipice_env_bytes(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._L.bp_shipice_launch_count(self._h))

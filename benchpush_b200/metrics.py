@@ -1,0 +1,106 @@
+"""Efficiency / effort scoring (reference benchpush/common/metrics/base_metric.py:7-105 and
+ship_ice_metric.py:5-72), batched over environments.
+
+The reference keeps one metric object per (single) env and appends one score per finished episode to
+``rewards``, ``efficiency_scores``, ``effort_scores``.  ``ShipIceMetric`` here keeps the same
+attribute names and formulas; ``update`` consumes the batched ``info`` of ``ShipIceVecEnv.step`` and
+appends one entry for every env whose episode ended in that step.  Plotting is out of scope.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+
+import torch
+
+
+class BaseMetric(ABC):
+    def __init__(self, alg_name) -> None:
+        self.rewards = []
+        self.efficiency_scores = []
+        self.effort_scores = []
+        self.success_rates = []
+        self.alg_name = alg_name
+
+    @abstractmethod
+    def update(self, info, reward, eps_complete=False):
+        ...
+
+    @abstractmethod
+    def reset(self, info, mask=None):
+        ...
+
+
+class ShipIceMetric(BaseMetric):
+    """efficiency = 1_success * L / l_0 with L = goal_y - y_start (ship_ice_metric.py:26-34, 72);
+    effort = m_0 l_0 / (m_0 l_0 + sum_i m_i l_i) with sum_i m_i l_i = info['total_work'] (:37-43).
+    The ship path length l_0 integrates the 2-decimal-rounded ``info['state']`` (:52-55)."""
+
+    def __init__(self, alg_name, ship_mass, goal, num_envs=None, device=None) -> None:
+        super().__init__(alg_name=alg_name)
+        self.ship_mass = float(ship_mass)
+        self.goal_line = float(goal[1])
+        self._n = num_envs
+        self._dev = device
+        self.successes = []
+        self._alloc_done = False
+
+    def _alloc(self, info):
+        st = info["state"]
+        self._n, self._dev = st.shape[0], st.device
+        z = lambda: torch.zeros(self._n, dtype=torch.float64, device=self._dev)
+        self.eps_reward, self.total_mass_dist, self.total_ship_dist, self.L = z(), z(), z(), z()
+        self.trial_success = torch.zeros(self._n, dtype=torch.bool, device=self._dev)
+        self.ship_state = torch.zeros((self._n, 3), dtype=torch.float64, device=self._dev)
+        self._alloc_done = True
+
+    def reset(self, info, mask=None):
+        if not self._alloc_done:
+            self._alloc(info)
+        m = torch.ones(self._n, dtype=torch.bool, device=self._dev) if mask is None else mask.bool()
+        zero = torch.zeros((), dtype=torch.float64, device=self._dev)
+        self.eps_reward = torch.where(m, zero, self.eps_reward)
+        self.total_mass_dist = torch.where(m, zero, self.total_mass_dist)
+        self.total_ship_dist = torch.where(m, zero, self.total_ship_dist)
+        self.trial_success = self.trial_success & ~m
+        self.ship_state = torch.where(m[:, None], info["state"], self.ship_state)
+        self.L = torch.where(m, self.goal_line - info["state"][:, 1], self.L)
+
+    def compute_efficiency_score(self):
+        eff = self.L / self.total_ship_dist
+        return torch.where(self.trial_success, eff, torch.zeros_like(eff))
+
+    def compute_effort_score(self):
+        ml = self.ship_mass * self.total_ship_dist
+        return ml / (ml + self.total_mass_dist)
+
+    def update(self, info, reward, eps_complete=False):
+        """eps_complete: bool tensor [E] (``terminated | truncated``) or a python bool applied to all."""
+        self.eps_reward = self.eps_reward + reward
+        self.total_mass_dist = info["total_work"].clone()
+        self.trial_success = info["trial_success"].clone()
+        st = info["state"]
+        self.total_ship_dist = self.total_ship_dist + torch.linalg.norm(self.ship_state[:, :2] - st[:, :2], dim=1)
+        self.ship_state = st.clone()
+        done = eps_complete if torch.is_tensor(eps_complete) else torch.full((self._n,), bool(eps_complete), device=self._dev)
+        if bool(done.any()):
+            idx = torch.nonzero(done).flatten()
+            self.rewards.extend(self.eps_reward[idx].tolist())
+            self.efficiency_scores.extend(self.compute_efficiency_score()[idx].tolist())
+            self.effort_scores.extend(self.compute_effort_score()[idx].tolist())
+            self.successes.extend(self.trial_success[idx].tolist())
+        return done
+
+    def reduce(self):
+        """Episode-metric sums, all-reduced over ranks when torch.distributed is initialised
+        (the only collective of the path: envs never exchange data)."""
+        import torch.distributed as dist
+        t = torch.tensor([len(self.rewards), float(sum(self.successes)), float(sum(self.efficiency_scores)),
+                          float(sum(self.effort_scores)), float(sum(self.rewards))], dtype=torch.float64,
+                         device=self._dev if self._dev is not None else "cpu")
+        if dist.is_available() and dist.is_initialized():
+            if dist.get_backend() == "gloo":
+                t = t.cpu()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n = max(float(t[0]), 1.0)
+        return {"episodes": int(t[0]), "success_rate": float(t[1]) / n, "efficiency_mean": float(t[2]) / n,
+                "effort_mean": float(t[3]) / n, "reward_mean": float(t[4]) / n}

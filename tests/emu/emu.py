@@ -88,5 +88,19 @@ class Emu:
         n = self.L.emu_layout_verts(self.h, C.c_int(l), C.c_int(b), _dp(out), _dp(mi))
         return out[:n], mi
 
+    def render_obs(self, env, raw):
+        out = np.zeros((4, 150, 150), dtype=np.uint8)
+        self.L.emu_render_obs(self.h, C.c_int(env), C.c_int(1 if raw else 0), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def spfa(self, m, source):
+        m = np.ascontiguousarray(np.asarray(m).astype(bool).astype(np.uint8))
+        H, W = m.shape
+        d = np.empty((H, W), dtype=np.float32)
+        p = np.empty((H, W), dtype=np.int32)
+        self.L.emu_spfa(m.ctypes.data_as(C.c_void_p), C.c_int(H), C.c_int(W), C.c_int(int(source[0])), C.c_int(int(source[1])),
+                        d.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p))
+        return d, p
+
     def env_bytes(self):
         return self.L.emu_env_bytes(self.h)

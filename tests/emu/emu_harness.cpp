@@ -9,6 +9,8 @@
 #include <vector>
 #include "../../benchpush_b200/csrc/host_tables.h"
 #include "../../benchpush_b200/csrc/shipice_env.cuh"
+#include "../../benchpush_b200/csrc/raster.cuh"
+#include "../../benchpush_b200/csrc/spfa.cuh"
 
 using namespace bp;
 
@@ -18,6 +20,7 @@ struct Emu {
     std::vector<double> reward, state, pose, total_work, coll, scoll, distr;
     std::vector<unsigned char> term, trunc, succ; std::vector<int> status;
     StepOut out;
+    ObsParams O; std::vector<unsigned char> raw_mode;
 };
 
 extern "C" {
@@ -36,6 +39,10 @@ void* emu_create(int n_envs, int max_floes, int pmax, int lmax, double goal_y, i
     e->out.state = e->state.data(); e->out.pose = e->pose.data(); e->out.total_work = e->total_work.data();
     e->out.collision_reward = e->coll.data(); e->out.scaled_collision_reward = e->scoll.data(); e->out.dist_reward = e->distr.data();
     e->out.trial_success = e->succ.data(); e->out.status = e->status.data();
+    ObsParams& O = e->O;
+    O.grid_w = 300; O.grid_h = 1000; O.scale = 25.0; O.vshift = 2.0; O.goal_y = goal_y; O.g2m = 40.0 / 1000; O.range_x = 12.0; O.range_y = 12.0;
+    O.head[0] = 1.0; O.head[1] = 0.0; O.tail[0] = -1.0; O.tail[1] = 0.0; O.n_robot_raw = 0;
+    e->raw_mode.assign(n_envs, 1);
     return e;
 }
 void emu_destroy(void* h) { delete (Emu*)h; }
@@ -50,6 +57,8 @@ int emu_load_layouts(void* h, int n_layouts, const int32_t* n_floes, const int32
     e->T.lv = H.lv.data(); e->T.ln = H.ln.data(); e->T.nv = H.nv.data(); e->T.rad = H.rad.data();
     e->T.minv = H.minv.data(); e->T.iinv = H.iinv.data(); e->T.cog = H.cog.data(); e->T.mat_e = H.mat_e.data();
     e->T.mat_u = H.mat_u.data(); e->T.init = H.init.data(); e->T.nbody = H.nbody.data();
+    e->O.n_robot_raw = n_ship_verts;
+    for (int i = 0; i < 2 * n_ship_verts; i++) e->O.robot_raw[i] = ship_verts[i];
     return 0;
 }
 void emu_reset(void* h, int env, int layout) {
@@ -121,6 +130,27 @@ int emu_layout_verts(void* h, int l, int b, double* out, double* minv_iinv) {
     for (int i = 0; i < 2 * n; i++) out[i] = e->H.lv[idx * VMAX * 2 + i];
     minv_iinv[0] = e->H.minv[idx]; minv_iinv[1] = e->H.iinv[idx]; minv_iinv[2] = e->H.cog[2 * idx]; minv_iinv[3] = e->H.cog[2 * idx + 1];
     return n;
+}
+// observation of env: raw != 0 rasterises the raw trial vertices (reset), else the hull world vertices
+void emu_render_obs(void* h, int env, int raw, unsigned char* out) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    LayoutView L = layout_view(e->T, e->d, ev.sc->layout);
+    static ObsSmem S;
+    int r = ev.sc->robot;
+    V2 o = body_origin(ev, L, r);
+    if (raw) {
+        size_t base = (size_t)ev.sc->layout * e->d.NB;
+        render_obs(S, e->O, r, e->H.rawv.data() + base * VMAX * 2, VMAX * 2, e->H.rawn.data() + base, e->H.rawcen.data() + base * 2,
+                   e->H.rawcen.data() + base * 2 + 1, 2, o.x, o.y, ev.pa[r], out);
+    } else {
+        render_obs(S, e->O, r, ev.wv, VMAX * 2, L.nv, ev.cenx, ev.ceny, 1, o.x, o.y, ev.pa[r], out);
+    }
+}
+void emu_spfa(const uint8_t* map, int H, int W, int si, int sj, float* dist, int32_t* parents) {
+    std::vector<int> scratch((size_t)3 * H * W);
+    SpfaShared S;
+    spfa_block(S, map, H, W, si, sj, dist, parents, scratch.data(), scratch.data() + (size_t)H * W, scratch.data() + (size_t)2 * H * W);
 }
 size_t emu_env_bytes(void* h) { return ((Emu*)h)->env_bytes; }
 

@@ -1,0 +1,70 @@
+"""Kernel LOGIC checked on the CPU: the .cuh sources compiled as host C++ with a one-lane warp
+(tests/emu, test-only) against the oracle.  The real CUDA build is checked by the -m gpu tests."""
+import numpy as np
+import pytest
+
+from tests.conftest import FIXTURES, SHIP_VERTS, fixture_conc
+from benchpush_b200.layouts import generate_experiment, pack_trials, unpack_trials
+from oracle import cpo
+from oracle.ship_ice_oracle import ShipIceOracleEnv
+from tests.emu.emu import Emu
+
+
+@pytest.mark.parametrize("name", ["c10_t7", "c30_t7", "c50_t0"])
+def test_emulated_kernels_match_oracle_bitwise(name, golden_layouts, pins):
+    p = golden_layouts[name]
+    emu = Emu(1, p, SHIP_VERTS)
+    env = ShipIceOracleEnv({"concentration": fixture_conc(name)}, experiment=unpack_trials(p), order_mode=1)
+    obs, info = env.reset()
+    emu.reset(0, 0)
+    assert np.array_equal(env.space.state(), emu.bodies(0, 0))
+    assert np.array_equal(obs, emu.render_obs(0, True))
+    for a in pins["%s_o1_actions" % name][:4]:
+        obs, r, term, _, info = env.step(float(a))
+        emu.step(0, float(a))
+        # same solver order, same fp64 rounding sequence: identical to the last bit
+        assert np.array_equal(env.space.state(), emu.bodies(0, 0))
+        out = emu.out(0)
+        assert out["status"] == 0
+        # work / reward go through numpy (BLAS dot, pow) in the oracle: summation order differs -> 1e-9 tolerance
+        np.testing.assert_allclose(out["reward"], r, rtol=1e-9, atol=1e-7)
+        np.testing.assert_allclose(out["total_work"], info["total_work"], rtol=1e-9, atol=1e-9)
+        assert (out["sx"], out["sy"], out["sa"]) == tuple(float(x) for x in info["state"])
+        assert np.array_equal(obs, emu.render_obs(0, False))
+
+
+def test_awake_set_is_small_and_exact(golden_layouts):
+    p = golden_layouts["c10_t0"]
+    emu = Emu(1, p, SHIP_VERTS)
+    emu.reset(0, 0)
+    sc = emu.scal(0)
+    assert sc["n_awake"] <= 3          # only the ship (and any deep-overlap pairs) stay awake in open water
+    assert sc["status"] == 0
+
+
+def test_emulated_spfa_matches_reference_golden(spfa_golden, golden_layouts):
+    emu = Emu(1, golden_layouts["c10_t0"], SHIP_VERTS)
+    for c in spfa_golden:
+        d, p = emu.spfa(c["map"], c["source"])
+        assert np.array_equal(d, c["dists"])                       # bit-identical distances
+        assert np.array_equal(p >= 0, c["parents"] >= 0)           # same reachable set
+        H, W = c["map"].shape
+        idx = np.argwhere(p >= 0)
+        pi, pj = np.divmod(p[p >= 0], W)
+        assert np.all(np.maximum(np.abs(idx[:, 0] - pi), np.abs(idx[:, 1] - pj)) == 1)
+        w = np.where((idx[:, 0] != pi) & (idx[:, 1] != pj), np.sqrt(np.float32(2.0)), np.float32(1.0)).astype(np.float32)
+        assert np.array_equal((d[pi, pj] + w).astype(np.float32), d[p >= 0])    # a valid shortest-path tree
+
+
+def test_product_hull_matches_oracle_hull_on_synthetic():
+    trials = generate_experiment(1, 0.4, seed=3)
+    p = pack_trials(trials)
+    emu = Emu(1, p, SHIP_VERTS)
+    env = ShipIceOracleEnv({"concentration": 0.4}, experiment=unpack_trials(p))
+    env.reset(settle=False)
+    for b, s in enumerate(env.poly_shapes):
+        ev, mi = emu.layout_verts(0, b)
+        assert np.array_equal(env.space.get_vertices(s), ev)
+        m = env.space.shape_mass(s)
+        np.testing.assert_allclose(1.0 / mi[0], m[0], rtol=1e-14)
+        np.testing.assert_allclose(1.0 / mi[1], m[3], rtol=1e-12)
