@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of ship-ice-v0 (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA, C ABI)
+    python bench.py --impl reference --gpus 1 --steps K ...  # the restated reference on the host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config 5 — ship-ice-v0, concentration 0.5 (~640 floes per env,
+synthetic seeded layouts), 65 536 envs in total split evenly over the ranks (strong scaling, as the
+metric is quoted "@65k envs on 1/2/4/8 B200"), random actions U(-1,1), next-step auto reset.
+One "step" = one `step()` of every env of the rank: 400 physics substeps + work/reward + 4x150x150 u8
+observation.  `value` = env steps actually simulated (reset calls are not counted as env steps, their
+cost stays in the timed region) / device time, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "env-steps/sec ship-ice-v0 @65k envs"
+UNIT = "env-steps/s"
+TOTAL_ENVS = 65536
+CONC = 0.5
+N_LAYOUTS = 100
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total envs over all ranks (default: the metric's 65536)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm (oracle)
+def _cpu_worker(args):
+    """One host process: one env of the workload stepped with the oracle for ~budget seconds."""
+    idx, seed, budget, nsteps = args
+    from benchpush_b200.layouts import generate_experiment
+    from oracle.ship_ice_oracle import ShipIceOracleEnv
+    trials = generate_experiment(1, CONC, seed=99 + idx)
+    env = ShipIceOracleEnv({"concentration": CONC}, experiment=trials, order_mode=1)
+    env.reset()
+    rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        o, r, term, _, info = env.step(float(rng.uniform(-1, 1)))
+        n += 1
+        if term:
+            env.reset()
+        if nsteps is not None:
+            if n >= nsteps:
+                break
+        elif time.perf_counter() - t0 > budget:
+            break
+    return n, time.perf_counter() - t0
+
+
+def cpu_sample(budget_s, nsteps=None, cores=None):
+    """Env-steps/s of the oracle with one env per host core, all cores busy at once."""
+    import multiprocessing as mp
+    cores = cores or (os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(i, 1000 + i, budget_s, nsteps) for i in range(cores)])
+    steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return steps / wall, cores, steps, wall
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # each bench "step" = every host core advances its env by one env step (a bounded sample of the workload)
+    total = a.warmup + a.steps
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    t_all = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(i, 1000 + i, 0.0, max(a.warmup, 1)) for i in range(cores)])          # warm-up (incl. reset)
+        res = pool.map(_cpu_worker, [(i, 2000 + i, 0.0, a.steps) for i in range(cores)])
+    steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    val = steps / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ship-ice-v0 concentration 0.5 (synthetic seeded layouts), one env per host core, random actions",
+                   "note": "the reference env cannot run here (pymunk/gymnasium absent): this is the restated reference (oracle/, fp64 C++ Chipmunk restatement + numpy rasters)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d env steps per core on %d cores (one env per core, incl. observation + reward)" % (a.steps, cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from benchpush_b200.envs import ShipIceVecEnv
+    from benchpush_b200.layouts import generate_experiment, pack_trials
+    from benchpush_b200.metrics import ShipIceMetric
+    from benchpush_b200.parallel import shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lo, hi = shard_range(a.envs, rank, world)
+    E = hi - lo
+
+    # layouts: every rank generates the same seeded set; trial selection is keyed by the GLOBAL env id
+    packed = pack_trials(generate_experiment(N_LAYOUTS, CONC, seed=99))
+    first = (np.arange(lo, hi) % N_LAYOUTS).astype(np.int32)
+    env = ShipIceVecEnv(num_envs=E, cfg={"concentration": CONC}, layouts=packed, device=local, auto_reset=True, first_trial=first)
+    env.check_status = False
+    n_floes = packed.n_floes[first].astype(np.float64)
+    sum_v = np.array([packed.n_verts[l, : packed.n_floes[l]].sum() for l in range(N_LAYOUTS)], dtype=np.float64)[first]
+    # algorithmic bytes per env step (SURVEY.md §8d / BASELINE.md §3): B = 56 N + 8 sum(V) + 90 036
+    alg_bytes_per_env = float(np.mean(56.0 * n_floes + 8.0 * sum_v + 90036.0))
+
+    obs, info = env.reset()
+    metric = ShipIceMetric("random", ship_mass=env.cfg.ship.mass, goal=env.goal)
+    metric.reset(info)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    total = a.warmup + a.steps
+    actions = [(torch.rand(E, generator=gen, device=dev) * 2 - 1).float() for _ in range(total)]
+    resets_in_step = torch.zeros(total + 1, dtype=torch.int64, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(k):
+        env.step_async_nocheck(actions[k])
+        # terminations of this step are reset by the next step call (auto reset): not env steps
+        resets_in_step[k + 1] = env._terminated.sum()
+
+    for k in range(a.warmup):
+        one_step(k)
+    barrier()
+    env.kernel_ms()
+    env.set_profiling(True)
+    launches0 = env.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(a.warmup, total):
+        one_step(k)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    km = env.kernel_ms()
+    env.set_profiling(False)
+    launches = env.launch_count() - launches0
+    n_resets = int(resets_in_step[a.warmup: total].sum().item())
+    env_steps = E * a.steps - n_resets
+    status_bits = int(env._status.max().item())
+
+    # ---- end to end through the public host-buffer API: actions H2D (pinned) + results D2H every step
+    h_actions = [torch.empty(E, dtype=torch.float32).pin_memory().copy_(actions[k].cpu()) for k in range(a.warmup, total)]
+    env.step_host(h_actions[0].numpy())                                       # allocate host staging outside the timed region
+    barrier()
+    t0 = time.perf_counter()
+    e2e_resets = 0
+    for k in range(a.steps):
+        hb = env.step_host(h_actions[k].numpy())
+        e2e_resets += int(hb["terminated"].sum())
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    # terminations of step k are resets of step k+1; the last step's are not inside the window, the priming step's are
+    e2e_steps = E * a.steps - e2e_resets
+    h2d = E * 4
+    d2h = E * (8 + 1 + 1 + 24 + 8 + 1 + 4)
+
+    t = torch.tensor([ms, t_e2e, float(env_steps), float(e2e_steps), km["step_ms"], km["obs_ms"], float(launches), float(status_bits)],
+                     dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    else:
+        tmax, tsum = t, t
+    ms_max, e2e_max = float(tmax[0]), float(tmax[1])
+    value = float(tsum[2]) / (ms_max * 1e-3)
+    e2e_value = float(tsum[3]) / e2e_max
+    red = metric.reduce()                                                   # NCCL all-reduce of episode-metric sums (only collective)
+
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        try:
+            v, cores, n, wall = cpu_sample(a.cpu_seconds)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "oracle (restated reference, fp64): one env per core on %d cores, %d env steps of the same workload in %.1f s" % (cores, n, wall)}
+        except Exception as ex:                                               # the GPU numbers stand on their own
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        step_ms_avg = km["step_ms"] / max(km["step_launches"], 1)
+        alg_bytes_launch = alg_bytes_per_env * E
+        achieved = alg_bytes_launch / (step_ms_avg * 1e-3) / 1e9 if step_ms_avg > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_env_step") * E
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ship-ice-v0 concentration 0.5 (BASELINE config 5), %d envs total (%d per GPU), 400 substeps/step, "
+                                   "4x150x150 u8 obs, U(-1,1) actions, next-step auto reset" % (a.envs, E),
+                       "layouts": "%d synthetic seeded ice fields (benchpush_b200.layouts.generate_ice_field, seed 99), mean %.0f floes" % (N_LAYOUTS, float(n_floes.mean())),
+                       "l2": "inputs_exceed_l2 (per-env state %.2f MB x %d envs per GPU)" % (env.env_bytes() / 1e6, E),
+                       "env_steps_timed": int(tsum[2]), "resets_timed": n_resets, "env_status_bits": int(tmax[7])},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "k_shipice_step", "kernel_ms": step_ms_avg, "obs_kernel_ms": km["obs_ms"] / max(km["obs_launches"], 1),
+                         "algorithmic_bytes_per_env_step": alg_bytes_per_env, "peak_source": peak_src,
+                         "note": "path is latency/issue bound by 400 sequential substeps (SURVEY.md §8d); HBM is the ceiling, not the limiter"},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "bp_shipice_step_host: actions from pinned host memory, reward/terminated/truncated/state/total_work/success/status read back every step; observations stay on the device for the policy"},
+            "gpu_launches": int(tsum[6]),
+            "episode_metrics": red,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

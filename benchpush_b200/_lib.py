@@ -73,6 +73,8 @@ def lib():
         L.bp_shipice_get_obstacles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.bp_shipice_get_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.bp_shipice_get_counters.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.bp_shipice_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        L.bp_shipice_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
         L.bp_shipice_env_bytes.argtypes = [C.c_void_p]
         L.bp_shipice_env_bytes.restype = C.c_size_t
         L.bp_shipice_launch_count.argtypes = [C.c_void_p]
@@ -87,6 +89,7 @@ EXPORTS = [
     "bp_version", "bp_last_error", "bp_device_count", "bp_shipice_default_config", "bp_shipice_create",
     "bp_shipice_destroy", "bp_shipice_load_layouts", "bp_shipice_reset", "bp_shipice_step", "bp_shipice_step_host",
     "bp_shipice_get_obstacles", "bp_shipice_get_bodies", "bp_shipice_get_counters", "bp_shipice_env_bytes",
+    "bp_shipice_set_profiling", "bp_shipice_get_kernel_ms",
     "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host",
 ]
 

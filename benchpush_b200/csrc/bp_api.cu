@@ -127,6 +127,11 @@ struct bp_shipice {
     bool layouts_loaded = false, was_reset = false;
     int64_t launches = 0;
     int sm_count = 148;
+    // optional per-kernel device timing (bench): events around the step and obs kernels
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+    std::vector<int> ev_kind;            // 0 = step/reset kernel, 1 = obs kernel (one entry per event pair)
+    double ms_acc[2] = {0, 0}; int64_t n_acc[2] = {0, 0};
 };
 
 template <typename T>
@@ -215,6 +220,7 @@ int bp_shipice_destroy(bp_shipice_t* h) {
     if (!h) return BP_OK;
     cudaSetDevice(h->cfg.device);
     for (void* p : h->dev_allocs) cudaFree(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->mem) cudaFree(h->mem);
     if (h->counter) cudaFree(h->counter);
     if (h->d_actions) cudaFree(h->d_actions);
@@ -269,12 +275,28 @@ static int copy_outputs(bp_shipice* h, const bp_shipice_outputs* o, cudaStream_t
     return BP_OK;
 }
 
+static void prof_begin(bp_shipice* h, int kind, cudaStream_t st) {
+    if (!h->profiling) return;
+    if (h->ev_used + 2 > h->ev_pool.size()) {
+        for (int i = 0; i < 2; i++) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+    }
+    cudaEventRecord(h->ev_pool[h->ev_used], st);
+    h->ev_kind.push_back(kind);
+}
+static void prof_end(bp_shipice* h, cudaStream_t st) {
+    if (!h->profiling) return;
+    cudaEventRecord(h->ev_pool[h->ev_used + 1], st);
+    h->ev_used += 2;
+}
+
 static int launch_obs(bp_shipice* h, uint8_t* obs, const uint8_t* mask, cudaStream_t st) {
     if (!obs) return BP_OK;
     ObsArgs oa;
     oa.mem = h->mem; oa.env_bytes = h->env_bytes; oa.d = h->d; oa.T = h->T; oa.O = h->O;
     oa.rawv = h->d_rawv; oa.rawn = h->d_rawn; oa.rawcen = h->d_rawcen; oa.mask = mask; oa.obs = obs;
+    prof_begin(h, 1, st);
     k_shipice_obs<<<h->d.n_envs, 256, 0, st>>>(oa);
+    prof_end(h, st);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return BP_OK;
@@ -314,7 +336,9 @@ int bp_shipice_step(bp_shipice_t* h, const float* actions, const bp_shipice_outp
     StepArgs a;
     a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
     a.actions = actions; a.layout_ids = nullptr; a.mask = nullptr; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset;
+    prof_begin(h, 0, st);
     k_shipice_step<<<sim_grid(h), 128, 0, st>>>(a);
+    prof_end(h, st);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     int rc = launch_obs(h, out ? out->obs : nullptr, nullptr, st);
@@ -404,6 +428,28 @@ int bp_shipice_get_counters(bp_shipice_t* h, int32_t env, int64_t* o) {
     o[0] = s->stamp; o[1] = s->n_awake; o[2] = s->n_pairs; o[3] = s->n_free; o[4] = s->n_order; o[5] = s->n_colours;
     o[6] = s->status; o[7] = s->n_apairs; o[8] = s->n_cached; o[9] = s->stat_gjk; o[10] = s->stat_pairs_eval;
     o[11] = s->stat_live_sum; o[12] = s->stat_awake_sum; o[13] = s->stat_recolour; o[14] = s->stat_rebuild; o[15] = s->stat_substeps;
+    return BP_OK;
+}
+
+int bp_shipice_set_profiling(bp_shipice_t* h, int32_t on) {
+    if (!h) return fail(BP_ERR_INVALID, "null handle");
+    h->profiling = on != 0;
+    return BP_OK;
+}
+
+int bp_shipice_get_kernel_ms(bp_shipice_t* h, double* out4) {
+    if (!h || !out4) return fail(BP_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (size_t i = 0; i * 2 < h->ev_used; i++) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+        int k = h->ev_kind[i];
+        h->ms_acc[k] += ms; h->n_acc[k]++;
+    }
+    h->ev_used = 0; h->ev_kind.clear();
+    out4[0] = h->ms_acc[0]; out4[1] = (double)h->n_acc[0]; out4[2] = h->ms_acc[1]; out4[3] = (double)h->n_acc[1];
+    h->ms_acc[0] = h->ms_acc[1] = 0; h->n_acc[0] = h->n_acc[1] = 0;
     return BP_OK;
 }
 

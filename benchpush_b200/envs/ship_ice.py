@@ -232,6 +232,14 @@ class ShipIceVecEnv:
                 "pairs_eval", "live_sum", "awake_sum", "recolour", "rebuild", "substeps"]
         return dict(zip(keys, o.tolist()))
 
+    def set_profiling(self, on: bool):
+        _lib.check(self._L.bp_shipice_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_ms(self) -> dict:
+        o = np.zeros(4, dtype=np.float64)
+        _lib.check(self._L.bp_shipice_get_kernel_ms(self._h, o.ctypes.data))
+        return {"step_ms": o[0], "step_launches": int(o[1]), "obs_ms": o[2], "obs_launches": int(o[3])}
+
     def env_bytes(self) -> int:
         return int(self._L.bp_shipice_env_bytes(self._h))
 

@@ -129,6 +129,13 @@ int bp_shipice_get_bodies(bp_shipice_t* h, int32_t env, double* out);
  * n_apairs, n_cached, gjk_iters, pairs_evaluated, live_sum, awake_sum, recolours, rebuilds, substeps. */
 int bp_shipice_get_counters(bp_shipice_t* h, int32_t env, int64_t* out);
 
+/* Device timing of the kernels this handle launches (bench.py's roofline): when enabled, CUDA
+ * events bracket every step/reset kernel and every observation kernel on their launch stream.
+ * get_kernel_ms synchronises and returns, since the last call, out[4] = {step-kernel ms total,
+ * step-kernel launches, obs-kernel ms total, obs-kernel launches}. */
+int bp_shipice_set_profiling(bp_shipice_t* h, int32_t on);
+int bp_shipice_get_kernel_ms(bp_shipice_t* h, double* out4);
+
 /* Bytes of device memory held per env and in total. */
 size_t bp_shipice_env_bytes(bp_shipice_t* h);
 

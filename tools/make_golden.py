@@ -63,7 +63,7 @@ def make_pins():
             obs, info = env.reset()
             rng = np.random.default_rng(42)
             nsteps = 6 if conc >= 0.5 else 10
-            actions = rng.uniform(-1, 1, nsteps)
+            actions = rng.uniform(-1, 1, nsteps).astype(np.float32).astype(np.float64)   # exactly representable in the f32 action space
             rows, obs_sums = [], [obs.astype(np.int64).reshape(4, -1).sum(1)]
             for a in actions:
                 obs, r, term, _, info = env.step(float(a))

@@ -1,0 +1,50 @@
+"""Join an ncu SASS source page (CSV) with nvdisasm line info to get per-function / per-line
+instruction counts and stall samples for one kernel.  Usage:
+  ncu -i rep.ncu-rep --page source --csv > src.csv
+  python tools/ncu_lines.py src.csv path/to/lib.so k_shipice_step [topN]"""
+import csv, re, subprocess, sys, os, tempfile, collections
+src_csv, so, kernel = sys.argv[1], sys.argv[2], sys.argv[3]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
+cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+in_sec = False; func = None; line = None; fmap = {}
+for ln in dis:
+    if ln.startswith("//--------------------- .text."):
+        in_sec = kernel in ln
+        continue
+    if not in_sec: continue
+    m = re.match(r"^(\$?[_A-Za-z0-9$]+):\s*$", ln)
+    if m and not ln.startswith(".L_x"):
+        name = m.group(1)
+        mm = re.search(r"_ZN2bp(\d+)([a-z_0-9]+)", name)
+        func = mm.group(2)[:int(mm.group(1))] if mm else name[:40]
+        continue
+    m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+    if m:
+        line = (os.path.basename(m.group(1)), int(m.group(2)))
+        continue
+    m = re.match(r"^\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
+    if m:
+        fmap[int(m.group(1), 16)] = (func, line, m.group(2).strip())
+rows = list(csv.reader(open(src_csv)))
+hdr = rows[1]
+ci = {h: i for i, h in enumerate(hdr)}
+data = rows[2:]
+base = int(data[0][0], 16)
+byf = collections.Counter(); byl = collections.Counter(); sf = collections.Counter(); sl = collections.Counter(); thr = collections.Counter()
+tot_i = tot_s = 0
+for r in data:
+    off = int(r[0], 16) - base
+    ie = int(r[ci["Instructions Executed"]] or 0); ss = int(r[ci["# Samples"]] or 0); te = int(r[ci["Thread Instructions Executed"]] or 0)
+    f, l, txt = fmap.get(off, ("?", None, ""))
+    byf[f] += ie; sf[f] += ss; thr[f] += te; byl[(f, l)] += ie; sl[(f, l)] += ss
+    tot_i += ie; tot_s += ss
+print("total warp-instructions %d, samples %d" % (tot_i, tot_s))
+print("%-22s %8s %8s %8s" % ("function", "inst%", "samples%", "avg thr"))
+for f, v in byf.most_common(20):
+    print("%-22s %7.2f%% %7.2f%% %8.1f" % (f, 100 * v / tot_i, 100 * sf[f] / max(tot_s, 1), thr[f] / max(v, 1)))
+print("\ntop lines by samples")
+for (f, l), v in sl.most_common(top):
+    print("%-18s %-22s %7.2f%% samples %7.2f%% inst" % (f, "%s:%s" % l if l else "?", 100 * v / max(tot_s, 1), 100 * byl[(f, l)] / tot_i))
