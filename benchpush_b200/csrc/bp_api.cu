@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(256) k_shipice_obs(ObsArgs a) {
     if (sc->obs_raw) {
         size_t base = (size_t)sc->layout * a.d.NB;
         render_obs(S, a.O, r, a.rawv + base * VMAX * 2, VMAX * 2, a.rawn + base, a.rawcen + base * 2, a.rawcen + base * 2 + 1, 2,
-                   o.x, o.y, ev.pa[r], out);
+                   o.x, o.y, ev.body[r].pa, out);
     } else {
-        render_obs(S, a.O, r, ev.wv, VMAX * 2, L.nv, ev.cenx, ev.ceny, 1, o.x, o.y, ev.pa[r], out);
+        render_obs(S, a.O, r, ev.wv, VMAX * 2, L.nv, ev.cenx, ev.ceny, 1, o.x, o.y, ev.body[r].pa, out);
     }
 }
 
@@ -247,6 +247,7 @@ int bp_shipice_load_layouts(bp_shipice_t* h, int32_t n_layouts, const int32_t* n
     if ((rc = dev_upload(h, H.ln, &h->T.ln))) return rc;
     if ((rc = dev_upload(h, H.nv, &h->T.nv))) return rc;
     if ((rc = dev_upload(h, H.rad, &h->T.rad))) return rc;
+    if ((rc = dev_upload(h, H.rbound, &h->T.rbound))) return rc;
     if ((rc = dev_upload(h, H.minv, &h->T.minv))) return rc;
     if ((rc = dev_upload(h, H.iinv, &h->T.iinv))) return rc;
     if ((rc = dev_upload(h, H.cog, &h->T.cog))) return rc;
@@ -376,11 +377,11 @@ static int fetch_env(bp_shipice* h, int env, std::vector<char>& buf) {
 static LayoutView host_layout_view(bp_shipice* h, int l) {
     LayoutTab T;
     HostLayouts& H = h->H;
-    T.lv = H.lv.data(); T.ln = H.ln.data(); T.nv = H.nv.data(); T.rad = H.rad.data(); T.minv = H.minv.data(); T.iinv = H.iinv.data();
+    T.lv = H.lv.data(); T.ln = H.ln.data(); T.nv = H.nv.data(); T.rad = H.rad.data(); T.rbound = H.rbound.data(); T.minv = H.minv.data(); T.iinv = H.iinv.data();
     T.cog = H.cog.data(); T.mat_e = H.mat_e.data(); T.mat_u = H.mat_u.data(); T.init = H.init.data(); T.nbody = H.nbody.data();
     LayoutView L;
     size_t o = (size_t)l * h->d.NB;
-    L.lv = T.lv + o * VMAX * 2; L.ln = T.ln + o * VMAX * 2; L.nv = T.nv + o; L.rad = T.rad + o; L.minv = T.minv + o; L.iinv = T.iinv + o;
+    L.lv = T.lv + o * VMAX * 2; L.ln = T.ln + o * VMAX * 2; L.nv = T.nv + o; L.rad = T.rad + o; L.rbound = T.rbound + o; L.minv = T.minv + o; L.iinv = T.iinv + o;
     L.cog = T.cog + o * 2; L.mat_e = T.mat_e + o; L.mat_u = T.mat_u + o; L.init = T.init + o * 3; L.nbody = T.nbody[l];
     return L;
 }
@@ -411,9 +412,9 @@ int bp_shipice_get_bodies(bp_shipice_t* h, int32_t env, double* out) {
     LayoutView L = host_layout_view(h, ev.sc->layout);
     int nb = ev.sc->nbody;
     for (int b = 0; b < nb; b++) {
-        double c = ev.rc[b], s = ev.rs[b], cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
-        out[6 * b] = ev.px[b] - (cx * c - cy * s); out[6 * b + 1] = ev.py[b] - (cx * s + cy * c); out[6 * b + 2] = ev.pa[b];
-        out[6 * b + 3] = ev.vx[b]; out[6 * b + 4] = ev.vy[b]; out[6 * b + 5] = ev.vw[b];
+        double c = ev.body[b].rc, s = ev.body[b].rs, cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
+        out[6 * b] = ev.body[b].px - (cx * c - cy * s); out[6 * b + 1] = ev.body[b].py - (cx * s + cy * c); out[6 * b + 2] = ev.body[b].pa;
+        out[6 * b + 3] = ev.body[b].vx; out[6 * b + 4] = ev.body[b].vy; out[6 * b + 5] = ev.body[b].vw;
     }
     return nb;
 }
@@ -428,6 +429,8 @@ int bp_shipice_get_counters(bp_shipice_t* h, int32_t env, int64_t* o) {
     o[0] = s->stamp; o[1] = s->n_awake; o[2] = s->n_pairs; o[3] = s->n_free; o[4] = s->n_order; o[5] = s->n_colours;
     o[6] = s->status; o[7] = s->n_apairs; o[8] = s->n_cached; o[9] = s->stat_gjk; o[10] = s->stat_pairs_eval;
     o[11] = s->stat_live_sum; o[12] = s->stat_awake_sum; o[13] = s->stat_recolour; o[14] = s->stat_rebuild; o[15] = s->stat_substeps;
+    o[16] = s->stat_epa; o[17] = s->stat_skipped;
+    for (int k = 0; k < 8; k++) o[18 + k] = s->t_phase[k];
     return BP_OK;
 }
 

@@ -13,7 +13,7 @@ namespace bp {
 
 struct HostLayouts {
     int NB = 0, L = 0;
-    std::vector<double> lv, ln, rad, minv, iinv, cog, mat_e, mat_u, init;
+    std::vector<double> lv, ln, rad, rbound, minv, iinv, cog, mat_e, mat_u, init;
     std::vector<int> nv, nbody;
     // raw (un-hulled) world-space trial vertices: the reset observation rasterises these
     // (ship_ice_env.py:207,248), plus |centroid| of each raw polygon for the local-range test
@@ -54,7 +54,7 @@ inline std::string build_shipice_layouts(HostLayouts& H, int n_layouts, int max_
     H.NB = NB; H.L = n_layouts;
     size_t LB = (size_t)n_layouts * NB;
     H.lv.assign(LB * VMAX * 2, 0.0); H.ln.assign(LB * VMAX * 2, 0.0); H.nv.assign(LB, 0);
-    H.rad.assign(LB, 0.0); H.minv.assign(LB, 0.0); H.iinv.assign(LB, 0.0); H.cog.assign(LB * 2, 0.0);
+    H.rad.assign(LB, 0.0); H.rbound.assign(LB, 0.0); H.minv.assign(LB, 0.0); H.iinv.assign(LB, 0.0); H.cog.assign(LB * 2, 0.0);
     H.mat_e.assign(LB, 0.0); H.mat_u.assign(LB, 0.0); H.init.assign(LB * 3, 0.0); H.nbody.assign(n_layouts, 0);
     H.rawv.assign(LB * VMAX * 2, 0.0); H.rawn.assign(LB, 0); H.rawcen.assign(LB * 2, 0.0);
     if (n_ship_verts > 32) return "too many ship vertices";
@@ -69,6 +69,9 @@ inline std::string build_shipice_layouts(HostLayouts& H, int n_layouts, int max_
             H.lv[(idx * VMAX + i) * 2] = b.verts[i].x; H.lv[(idx * VMAX + i) * 2 + 1] = b.verts[i].y;
             H.ln[(idx * VMAX + i) * 2] = b.normals[i].x; H.ln[(idx * VMAX + i) * 2 + 1] = b.normals[i].y;
         }
+        double rb = 0.0;
+        for (size_t i = 0; i < b.verts.size(); i++) rb = std::fmax(rb, std::hypot(b.verts[i].x - b.cog.x, b.verts[i].y - b.cog.y));
+        H.rbound[idx] = rb * 1.000001 + radius;
         H.rad[idx] = radius; H.minv[idx] = b.m_inv; H.iinv[idx] = b.i_inv;
         H.cog[idx * 2] = b.cog.x; H.cog[idx * 2 + 1] = b.cog.y;
         H.mat_e[idx] = e; H.mat_u[idx] = u;

@@ -66,8 +66,8 @@ BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const Sim
     if (lane == 0) {
         int r = sc->robot;
         V2 o = body_origin(ev, L, r);
-        out.pose[3 * env] = o.x; out.pose[3 * env + 1] = o.y; out.pose[3 * env + 2] = ev.pa[r];
-        out.state[3 * env] = round2(o.x); out.state[3 * env + 1] = round2(o.y); out.state[3 * env + 2] = round2(ev.pa[r]);
+        out.pose[3 * env] = o.x; out.pose[3 * env + 1] = o.y; out.pose[3 * env + 2] = ev.body[r].pa;
+        out.state[3 * env] = round2(o.x); out.state[3 * env + 1] = round2(o.y); out.state[3 * env + 2] = round2(ev.body[r].pa);
         out.total_work[env] = 0.0; out.reward[env] = 0.0; out.terminated[env] = 0; out.truncated[env] = 0;
         out.collision_reward[env] = 0.0; out.scaled_collision_reward[env] = 0.0; out.dist_reward[env] = 0.0;
         out.trial_success[env] = 0; out.status[env] = sc->status;
@@ -84,11 +84,11 @@ BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimP
     // ship_ice_env.py:263-274: yaw rate from the action, constant surge along the heading at step start
     if (lane == 0) {
         sc->t++;
-        double a = ev.pa[r];
+        double a = ev.body[r].pa;
         double s, c; bp_sincos(a, &s, &c);
-        ev.vw[r] = action * P.yaw_step;
-        ev.vx[r] = c * P.target_speed + (-s) * 0.0;
-        ev.vy[r] = s * P.target_speed + c * 0.0;
+        ev.body[r].vw = action * P.yaw_step;
+        ev.body[r].vx = c * P.target_speed + (-s) * 0.0;
+        ev.body[r].vy = s * P.target_speed + c * 0.0;
     }
     bp_wsync();
     sleep_pass(ev, L, d);
@@ -96,8 +96,8 @@ BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimP
     for (int k = 0; k < P.substeps; k++) {
         substep(ev, L, P, d, P.dt, P.dt);
         // ship_ice_env.py:284-290
-        double a = ev.pa[r];
-        if (a <= P.yaw_lo || a >= P.yaw_hi) { if (lane == 0) ev.vw[r] = 0.0; yaw_violated = true; }
+        double a = ev.body[r].pa;
+        if (a <= P.yaw_lo || a >= P.yaw_hi) { if (lane == 0) ev.body[r].vw = 0.0; yaw_violated = true; }
         V2 o = body_origin(ev, L, r);
         if (o.x < 0 || o.x > P.map_w) boundary_violated = true;
         bp_wsync();
@@ -131,7 +131,7 @@ BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimP
         bool terminated = (y >= P.goal_y) || boundary_terminal;
         double dist_reward = 0.0;
         if (y < P.goal_y) {
-            double a = ev.pa[r];
+            double a = ev.body[r].pa;
             double s, c; bp_sincos(a, &s, &c);
             dist_reward = 1.0 * (c * 0.0 + s * 1.0);
         }
@@ -142,8 +142,8 @@ BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimP
         bool success = false;
         if (terminated && !boundary_terminal) { reward += P.terminal_reward; success = true; }
         out.reward[env] = reward; out.terminated[env] = terminated ? 1 : 0; out.truncated[env] = 0;
-        out.pose[3 * env] = o.x; out.pose[3 * env + 1] = o.y; out.pose[3 * env + 2] = ev.pa[r];
-        out.state[3 * env] = round2(o.x); out.state[3 * env + 1] = round2(o.y); out.state[3 * env + 2] = round2(ev.pa[r]);
+        out.pose[3 * env] = o.x; out.pose[3 * env + 1] = o.y; out.pose[3 * env + 2] = ev.body[r].pa;
+        out.state[3 * env] = round2(o.x); out.state[3 * env + 1] = round2(o.y); out.state[3 * env + 2] = round2(ev.body[r].pa);
         out.total_work[env] = sc->total_work; out.collision_reward[env] = collision_reward;
         out.scaled_collision_reward[env] = collision_reward * P.beta; out.dist_reward[env] = dist_reward;
         out.trial_success[env] = success ? 1 : 0; out.status[env] = sc->status;

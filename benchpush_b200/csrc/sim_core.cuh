@@ -69,6 +69,7 @@ struct LayoutTab {
     const double* ln;             // [L][NB][VMAX][2] edge normals (edge ending at vertex i)
     const int* nv;                // [L][NB]
     const double* rad;            // [L][NB] shape radius
+    const double* rbound;         // [L][NB] max |vertex - cog|: bounds the motion caused by rotation
     const double* minv;           // [L][NB]
     const double* iinv;           // [L][NB]
     const double* cog;            // [L][NB][2]
@@ -85,59 +86,58 @@ struct EnvScal {
     int obs_raw, pad0, pad1, pad2;
     double total_work;
     long long stat_gjk, stat_pairs_eval, stat_live_sum, stat_awake_sum, stat_recolour, stat_rebuild, stat_substeps;
+    long long stat_epa, stat_skipped, t_phase[8];
 };
 
-// Per-env mutable state (global memory; offsets are identical for every env).
+// Per-env mutable state lives in one block of global memory per env (identical offsets for every
+// env).  Records are arrays-of-structs sized to cache lines: a lane that works on one body / one
+// arbiter touches 1-2 lines instead of one line per field.
+struct alignas(16) BodyRec {      // 128 B = one L1/L2 line
+    double px, py, pa;              // cog position (world), angle
+    double vx, vy, vw;              // velocity
+    double bx, by, bw;              // bias (pseudo) velocity
+    double rc, rs;                  // cos / sin of pa
+    double bbl, bbb, bbr, bbt;      // AABB incl. shape radius
+    double D;                       // monotone bound on the path length travelled by any point of the body
+};
+struct ContactRec {                 // 96 B
+    double r1x, r1y, r2x, r2y, jn, jt, jb, nm, tm, bias, bounce;
+    unsigned hash, pad;
+};
+struct alignas(16) SlotRec {      // 256 B = two lines: one (recently) touching shape pair = cpArbiter
+    int a, b, pair, cnt, stamp;
+    unsigned char touch, first, keep, pad;
+    double nx, ny, e, u;
+    ContactRec c[2];
+    double pad2;
+};
+struct PairRec {                    // 24 B: neighbour-list entry
+    unsigned key, gjk;              // (i << 16) | j ; GJK warm-start id
+    int live;                       // slot index or -1
+    unsigned flags;                 // bit0 = evaluated at the current poses, bit1 = in apairs
+    double skip;                    // not touching and D[a] + D[b] < skip  =>  provably still not touching
+};
+
 struct EnvView {
     EnvScal* sc;
-    double *px, *py, *pa, *vx, *vy, *vw, *bx, *by, *bw, *rc, *rs;           // [NB]
-    double *bbl, *bbb, *bbr, *bbt, *b0l, *b0b, *b0r, *b0t;                   // [NB] current / at-build AABB
-    double *wv;                                                              // [NB][VMAX][2]
+    BodyRec* body;                                                           // [NB]
+    double* b0;                                                              // [NB][4] AABB at neighbour-list build
+    double* wv;                                                              // [NB][VMAX][2] world vertices
     double *cenx, *ceny, *area, *tmp;                                        // [NB] |centroid|, area at last env step; scratch
-    int *awake;                                                              // [NB]
+    int* awake;                                                              // [NB]
     unsigned char *is_awake, *moved, *moved_step, *act;                      // [NB]
-    unsigned long long *colmask;                                             // [NB]
-    unsigned *pkey[2], *pgjk[2];                                             // [PMAX]
-    int *plive[2];                                                           // [PMAX]
-    unsigned char *pflag[2];                                                 // [PMAX] bit0 = evaluated at current poses, bit1 = in apairs
+    unsigned long long* colmask;                                             // [NB]
+    PairRec* pair[2];                                                        // [PMAX] double-buffered over rebuilds
     int *adj_start, *adj, *deg;                                              // [NB+1], [2*PMAX], [NB]
     int *queue, *apairs;                                                     // [PMAX] eval queue; pairs incident to awake bodies
-    unsigned *livemask;                                                      // [PMAX/32]
-    // live arbiter slots
-    int *ls_a, *ls_b, *ls_pair, *ls_cnt, *ls_stamp;                          // [LMAX]
-    unsigned char *ls_touch, *ls_first, *ls_keep;                            // [LMAX]
-    double *ls_nx, *ls_ny, *ls_e, *ls_u;                                     // [LMAX]
-    double *ls_r1x, *ls_r1y, *ls_r2x, *ls_r2y, *ls_jn, *ls_jt, *ls_jb, *ls_nm, *ls_tm, *ls_bias, *ls_bounce;  // [2][LMAX]
-    unsigned *ls_hash;                                                       // [2][LMAX]
+    int* queue2; unsigned* qhint;                                            // [LMAX] EPA stage queue + simplex hint
+    unsigned* livemask;                                                      // [PMAX/32]
+    SlotRec* slot;                                                           // [LMAX]
     int *free_stack, *order, *colour, *col_start;                            // [LMAX],[LMAX],[LMAX],[MAXCOL+1]
 };
 
 #define BP_ALIGN16(x) (((x) + 15) & ~(size_t)15)
-
-// Host + device: carve the per-env block.  Order must match make_view().
-static inline size_t env_mem_size(const Dims& d) {
-    size_t NB = d.NB, P = d.PMAX, Lm = d.LMAX, t = 0;
-    t += BP_ALIGN16(sizeof(EnvScal));
-    t += 19 * BP_ALIGN16(NB * 8);                 // px..rs (11) + bb (8)
-    t += BP_ALIGN16(NB * VMAX * 2 * 8);           // wv
-    t += 4 * BP_ALIGN16(NB * 8);                  // cenx, ceny, area, tmp
-    t += BP_ALIGN16(NB * 4);                      // awake
-    t += 4 * BP_ALIGN16(NB);                      // is_awake, moved, moved_step, act
-    t += BP_ALIGN16(NB * 8);                      // colmask
-    t += 4 * BP_ALIGN16(P * 4);                   // pkey[2], pgjk[2]
-    t += 2 * BP_ALIGN16(P * 4);                   // plive[2]
-    t += 2 * BP_ALIGN16(P);                       // pflag[2]
-    t += BP_ALIGN16((NB + 1) * 4) + BP_ALIGN16(2 * P * 4) + BP_ALIGN16(NB * 4);   // adj_start, adj, deg
-    t += 2 * BP_ALIGN16(P * 4);                   // queue, apairs
-    t += BP_ALIGN16((P / 32 + 1) * 4);            // livemask
-    t += 5 * BP_ALIGN16(Lm * 4);                  // ls ints
-    t += 3 * BP_ALIGN16(Lm);                      // ls bytes
-    t += 4 * BP_ALIGN16(Lm * 8);                  // nx ny e u
-    t += 11 * BP_ALIGN16(2 * Lm * 8);             // per-contact doubles
-    t += BP_ALIGN16(2 * Lm * 4);                  // hash
-    t += 3 * BP_ALIGN16(Lm * 4) + BP_ALIGN16((MAXCOL + 1) * 4);
-    return BP_ALIGN16(t + 256);
-}
+#define BP_ALIGN128(x) (((x) + 127) & ~(size_t)127)
 
 #if defined(__CUDACC__) && !defined(BP_HOST_EMU)
 #define BP_HD __host__ __device__ inline
@@ -145,57 +145,45 @@ static inline size_t env_mem_size(const Dims& d) {
 #define BP_HD static inline
 #endif
 
-BP_HD EnvView make_view(char* base, const Dims& d) {
+// Carve the per-env block.  base == nullptr: returns only the size (in the sc field as an offset).
+BP_HD EnvView carve_env(char* base, const Dims& d, size_t* total) {
     EnvView v;
     size_t NB = d.NB, P = d.PMAX, Lm = d.LMAX;
     char* p = base;
-#define TAKE(ptr, type, bytes) ptr = (type*)p; p += BP_ALIGN16(bytes);
-    TAKE(v.sc, EnvScal, sizeof(EnvScal));
-    TAKE(v.px, double, NB * 8) TAKE(v.py, double, NB * 8) TAKE(v.pa, double, NB * 8)
-    TAKE(v.vx, double, NB * 8) TAKE(v.vy, double, NB * 8) TAKE(v.vw, double, NB * 8)
-    TAKE(v.bx, double, NB * 8) TAKE(v.by, double, NB * 8) TAKE(v.bw, double, NB * 8)
-    TAKE(v.rc, double, NB * 8) TAKE(v.rs, double, NB * 8)
-    TAKE(v.bbl, double, NB * 8) TAKE(v.bbb, double, NB * 8) TAKE(v.bbr, double, NB * 8) TAKE(v.bbt, double, NB * 8)
-    TAKE(v.b0l, double, NB * 8) TAKE(v.b0b, double, NB * 8) TAKE(v.b0r, double, NB * 8) TAKE(v.b0t, double, NB * 8)
+#define TAKE(ptr, type, bytes) ptr = (type*)p; p += BP_ALIGN128(bytes);
+    TAKE(v.sc, EnvScal, sizeof(EnvScal))
+    TAKE(v.body, BodyRec, NB * sizeof(BodyRec))
+    TAKE(v.slot, SlotRec, Lm * sizeof(SlotRec))
+    TAKE(v.b0, double, NB * 32)
     TAKE(v.wv, double, NB * VMAX * 2 * 8)
     TAKE(v.cenx, double, NB * 8) TAKE(v.ceny, double, NB * 8) TAKE(v.area, double, NB * 8) TAKE(v.tmp, double, NB * 8)
     TAKE(v.awake, int, NB * 4)
     TAKE(v.is_awake, unsigned char, NB) TAKE(v.moved, unsigned char, NB)
     TAKE(v.moved_step, unsigned char, NB) TAKE(v.act, unsigned char, NB)
     TAKE(v.colmask, unsigned long long, NB * 8)
-    TAKE(v.pkey[0], unsigned, P * 4) TAKE(v.pkey[1], unsigned, P * 4)
-    TAKE(v.pgjk[0], unsigned, P * 4) TAKE(v.pgjk[1], unsigned, P * 4)
-    TAKE(v.plive[0], int, P * 4) TAKE(v.plive[1], int, P * 4)
-    TAKE(v.pflag[0], unsigned char, P) TAKE(v.pflag[1], unsigned char, P)
+    TAKE(v.pair[0], PairRec, P * sizeof(PairRec)) TAKE(v.pair[1], PairRec, P * sizeof(PairRec))
     TAKE(v.adj_start, int, (NB + 1) * 4) TAKE(v.adj, int, 2 * P * 4) TAKE(v.deg, int, NB * 4)
     TAKE(v.queue, int, P * 4) TAKE(v.apairs, int, P * 4)
+    TAKE(v.queue2, int, Lm * 4) TAKE(v.qhint, unsigned, Lm * 4)
     TAKE(v.livemask, unsigned, (P / 32 + 1) * 4)
-    TAKE(v.ls_a, int, Lm * 4) TAKE(v.ls_b, int, Lm * 4) TAKE(v.ls_pair, int, Lm * 4)
-    TAKE(v.ls_cnt, int, Lm * 4) TAKE(v.ls_stamp, int, Lm * 4)
-    TAKE(v.ls_touch, unsigned char, Lm) TAKE(v.ls_first, unsigned char, Lm)
-    TAKE(v.ls_keep, unsigned char, Lm)
-    TAKE(v.ls_nx, double, Lm * 8) TAKE(v.ls_ny, double, Lm * 8) TAKE(v.ls_e, double, Lm * 8) TAKE(v.ls_u, double, Lm * 8)
-    TAKE(v.ls_r1x, double, 2 * Lm * 8) TAKE(v.ls_r1y, double, 2 * Lm * 8)
-    TAKE(v.ls_r2x, double, 2 * Lm * 8) TAKE(v.ls_r2y, double, 2 * Lm * 8)
-    TAKE(v.ls_jn, double, 2 * Lm * 8) TAKE(v.ls_jt, double, 2 * Lm * 8) TAKE(v.ls_jb, double, 2 * Lm * 8)
-    TAKE(v.ls_nm, double, 2 * Lm * 8) TAKE(v.ls_tm, double, 2 * Lm * 8)
-    TAKE(v.ls_bias, double, 2 * Lm * 8) TAKE(v.ls_bounce, double, 2 * Lm * 8)
-    TAKE(v.ls_hash, unsigned, 2 * Lm * 4)
     TAKE(v.free_stack, int, Lm * 4) TAKE(v.order, int, Lm * 4) TAKE(v.colour, int, Lm * 4)
     TAKE(v.col_start, int, (MAXCOL + 1) * 4)
 #undef TAKE
+    if (total) *total = (size_t)(p - base);
     return v;
 }
+BP_HD EnvView make_view(char* base, const Dims& d) { return carve_env(base, d, nullptr); }
+static inline size_t env_mem_size(const Dims& d) { size_t t = 0; carve_env((char*)0, d, &t); return BP_ALIGN128(t); }
 
 struct LayoutView {
-    const double *lv, *ln, *rad, *minv, *iinv, *cog, *mat_e, *mat_u, *init;
+    const double *lv, *ln, *rad, *rbound, *minv, *iinv, *cog, *mat_e, *mat_u, *init;
     const int* nv;
     int nbody;
 };
 BP_DEV LayoutView layout_view(const LayoutTab& T, const Dims& d, int l) {
     LayoutView L;
     size_t o = (size_t)l * d.NB;
-    L.lv = T.lv + o * VMAX * 2; L.ln = T.ln + o * VMAX * 2; L.nv = T.nv + o; L.rad = T.rad + o;
+    L.lv = T.lv + o * VMAX * 2; L.ln = T.ln + o * VMAX * 2; L.nv = T.nv + o; L.rad = T.rad + o; L.rbound = T.rbound + o;
     L.minv = T.minv + o; L.iinv = T.iinv + o; L.cog = T.cog + o * 2; L.mat_e = T.mat_e + o; L.mat_u = T.mat_u + o;
     L.init = T.init + o * 3; L.nbody = T.nbody[l];
     return L;
@@ -220,11 +208,11 @@ BP_DEV V2 rotv(V2 a, V2 b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * 
 // ------------------------------------------------------------------ geometry refresh of one body
 BP_DEV void refresh_body(const EnvView& ev, const LayoutView& L, int b) {
     double s, c;
-    bp_sincos(ev.pa[b], &s, &c);
-    ev.rc[b] = c; ev.rs[b] = s;
+    bp_sincos(ev.body[b].pa, &s, &c);
+    ev.body[b].rc = c; ev.body[b].rs = s;
     double cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
-    double tx = ev.px[b] - (cx * c - cy * s);
-    double ty = ev.py[b] - (cx * s + cy * c);
+    double tx = ev.body[b].px - (cx * c - cy * s);
+    double ty = ev.body[b].py - (cx * s + cy * c);
     double ms = -s;
     const double* lv = L.lv + (size_t)b * VMAX * 2;
     double* wv = ev.wv + (size_t)b * VMAX * 2;
@@ -238,13 +226,13 @@ BP_DEV void refresh_body(const EnvView& ev, const LayoutView& L, int b) {
         l = fmin(l, wx); r = fmax(r, wx); bt = fmin(bt, wy); tp = fmax(tp, wy);
     }
     double rad = L.rad[b];
-    ev.bbl[b] = l - rad; ev.bbb[b] = bt - rad; ev.bbr[b] = r + rad; ev.bbt[b] = tp + rad;
+    ev.body[b].bbl = l - rad; ev.body[b].bbb = bt - rad; ev.body[b].bbr = r + rad; ev.body[b].bbt = tp + rad;
 }
 // body position (pymunk Body.position = local origin in world space)
 BP_DEV V2 body_origin(const EnvView& ev, const LayoutView& L, int b) {
-    double c = ev.rc[b], s = ev.rs[b];
+    double c = ev.body[b].rc, s = ev.body[b].rs;
     double cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
-    return mk(ev.px[b] - (cx * c - cy * s), ev.py[b] - (cx * s + cy * c));
+    return mk(ev.body[b].px - (cx * c - cy * s), ev.body[b].py - (cx * s + cy * c));
 }
 
 // ------------------------------------------------------------------ narrowphase: GJK / EPA on world vertices
@@ -327,36 +315,44 @@ BP_DEVNI Closest epa(const Poly& A, const Poly& B, MPoint h0, MPoint h1, MPoint 
     }
 }
 
-BP_DEVNI Closest gjk(const Poly& A, const Poly& B, V2 cenA, V2 cenB, unsigned* id, int* iters, int* capped) {
+// GJK without the EPA tail.  Returns true when the origin lies inside the simplex (v0, p, v1): the
+// caller must then run EPA on it; *hint packs (v0.id, v1.id) so that gjk_epa() can rebuild exactly
+// that simplex (p is a pure function of the ordered pair v0, v1).
+BP_DEVNI bool gjk_only(const Poly& A, const Poly& B, V2 cenA, V2 cenB, unsigned id, Closest* out, unsigned* hint, int* iters, int* capped) {
     MPoint v0, v1;
-    if (*id) {
-        unsigned g = *id;
-        v0 = mpoint(A, B, (g >> 24) & 0xFF, (g >> 16) & 0xFF);
-        v1 = mpoint(A, B, (g >> 8) & 0xFF, g & 0xFF);
+    if (id) {
+        v0 = mpoint(A, B, (id >> 24) & 0xFF, (id >> 16) & 0xFF);
+        v1 = mpoint(A, B, (id >> 8) & 0xFF, id & 0xFF);
     } else {
         V2 axis = perp(cenA - cenB);
         v0 = msupport(A, B, axis);
         v1 = msupport(A, B, neg(axis));
     }
-    Closest out;
     int iteration = 1;
     for (;;) {
         (*iters)++;
-        if (iteration > GJK_MAX_IT) { *capped = 1; out = closest_points(v0, v1); break; }
-        if (point_greater(v1.ab, v0.ab, mk(0, 0))) { MPoint t = v0; v0 = v1; v1 = t; (*iters)++; }
+        if (iteration > GJK_MAX_IT) { *capped = 1; *out = closest_points(v0, v1); return false; }
+        if (point_greater(v1.ab, v0.ab, mk(0, 0))) { MPoint t = v0; v0 = v1; v1 = t; }
         double t = closest_t(v0.ab, v1.ab);
         V2 n = (-1.0 < t && t < 1.0) ? perp(v1.ab - v0.ab) : neg(lerp_t(v0.ab, v1.ab, t));
         MPoint p = msupport(A, B, n);
         if (point_greater(p.ab, v0.ab, mk(0, 0)) && point_greater(v1.ab, p.ab, mk(0, 0))) {
-            out = epa(A, B, v0, p, v1, capped);
-            break;
+            *hint = (v0.id & 0xFFFF) << 16 | (v1.id & 0xFFFF);
+            return true;
         }
-        if (dot(p.ab, n) <= fmax(dot(v0.ab, n), dot(v1.ab, n))) { out = closest_points(v0, v1); break; }
+        if (dot(p.ab, n) <= fmax(dot(v0.ab, n), dot(v1.ab, n))) { *out = closest_points(v0, v1); return false; }
         if (closest_dist(v0.ab, p.ab) < closest_dist(p.ab, v1.ab)) v1 = p; else v0 = p;
         iteration++;
     }
-    *id = out.id;
-    return out;
+}
+// EPA stage for a pair whose GJK stage ended inside the simplex described by `hint`.
+BP_DEVNI Closest gjk_epa(const Poly& A, const Poly& B, unsigned hint, int* capped) {
+    MPoint v0 = mpoint(A, B, (hint >> 24) & 0xFF, (hint >> 16) & 0xFF);
+    MPoint v1 = mpoint(A, B, (hint >> 8) & 0xFF, hint & 0xFF);
+    double t = closest_t(v0.ab, v1.ab);
+    V2 n = (-1.0 < t && t < 1.0) ? perp(v1.ab - v0.ab) : neg(lerp_t(v0.ab, v1.ab, t));
+    MPoint p = msupport(A, B, n);
+    return epa(A, B, v0, p, v1, capped);
 }
 
 struct EdgeW { V2 a, b; int ia, ib; };
@@ -375,19 +371,17 @@ BP_DEV EdgeW support_edge(const Poly& P, const double* ln, double rc, double rs,
 
 struct Manifold { int count; V2 n; V2 p1[2], p2[2]; unsigned hash[2]; };
 
-// Collide body a (first shape) with body b.  Returns contacts in world space (<= 2).
-BP_DEV void collide(const EnvView& ev, const LayoutView& L, int a, int b, unsigned* gid, Manifold* m, int* iters, int* capped) {
-    Poly A, B;
-    A.v = ev.wv + (size_t)a * VMAX * 2; A.n = L.nv[a];
-    B.v = ev.wv + (size_t)b * VMAX * 2; B.n = L.nv[b];
-    V2 cenA = mk((ev.bbl[a] + ev.bbr[a]) * 0.5, (ev.bbb[a] + ev.bbt[a]) * 0.5);
-    V2 cenB = mk((ev.bbl[b] + ev.bbr[b]) * 0.5, (ev.bbb[b] + ev.bbt[b]) * 0.5);
-    Closest pts = gjk(A, B, cenA, cenB, gid, iters, capped);
+BP_DEV Poly body_poly(const EnvView& ev, const LayoutView& L, int b) { Poly P; P.v = ev.wv + (size_t)b * VMAX * 2; P.n = L.nv[b]; return P; }
+BP_DEV V2 bb_centre(const BodyRec& r) { return mk((r.bbl + r.bbr) * 0.5, (r.bbb + r.bbt) * 0.5); }
+
+// Contact manifold (<= 2 points, world space) of bodies a, b from the closest-feature result.
+BP_DEV void make_manifold(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {
+    Poly A = body_poly(ev, L, a), B = body_poly(ev, L, b);
     m->count = 0;
     double ra = L.rad[a], rb = L.rad[b];
     if (pts.d - ra - rb <= 0.0) {
-        EdgeW e1 = support_edge(A, L.ln + (size_t)a * VMAX * 2, ev.rc[a], ev.rs[a], pts.n);
-        EdgeW e2 = support_edge(B, L.ln + (size_t)b * VMAX * 2, ev.rc[b], ev.rs[b], neg(pts.n));
+        EdgeW e1 = support_edge(A, L.ln + (size_t)a * VMAX * 2, ev.body[a].rc, ev.body[a].rs, pts.n);
+        EdgeW e2 = support_edge(B, L.ln + (size_t)b * VMAX * 2, ev.body[b].rc, ev.body[b].rs, neg(pts.n));
         double mindist = ra + rb;
         if (pts.d <= mindist) {
             V2 n = pts.n; m->n = n;

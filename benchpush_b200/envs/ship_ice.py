@@ -226,11 +226,13 @@ class ShipIceVecEnv:
         return out[:n]
 
     def counters(self, e: int) -> dict:
-        o = np.zeros(16, dtype=np.int64)
+        o = np.zeros(32, dtype=np.int64)
         _lib.check(self._L.bp_shipice_get_counters(self._h, e, o.ctypes.data))
         keys = ["stamp", "n_awake", "n_pairs", "n_free", "n_order", "n_colours", "status", "n_apairs", "n_cached", "gjk",
-                "pairs_eval", "live_sum", "awake_sum", "recolour", "rebuild", "substeps"]
-        return dict(zip(keys, o.tolist()))
+                "pairs_eval", "live_sum", "awake_sum", "recolour", "rebuild", "substeps", "epa", "skipped"]
+        out = dict(zip(keys, o[:18].tolist()))
+        out["phase_clocks"] = o[18:26].tolist()
+        return out
 
     def set_profiling(self, on: bool):
         _lib.check(self._L.bp_shipice_set_profiling(self._h, 1 if on else 0))

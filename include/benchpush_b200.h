@@ -125,8 +125,9 @@ int bp_shipice_get_obstacles(bp_shipice_t* h, int32_t env, double* verts, int32_
  * position x, y, angle, vx, vy, w per body; the ship is the last row.  Returns the body count. */
 int bp_shipice_get_bodies(bp_shipice_t* h, int32_t env, double* out);
 
-/* Counters of env `env`, HOST out[16]: stamp, n_awake, n_pairs, n_free, n_order, n_colours, status,
- * n_apairs, n_cached, gjk_iters, pairs_evaluated, live_sum, awake_sum, recolours, rebuilds, substeps. */
+/* Counters of env `env`, HOST out[32]: stamp, n_awake, n_pairs, n_free, n_order, n_colours, status,
+ * n_apairs, n_cached, gjk_iters, pairs_evaluated, live_sum, awake_sum, recolours, rebuilds, substeps,
+ * epa_pairs, pairs_skipped_by_motion_bound, then 8 per-phase clock sums (only with BP_PHASE_TIMERS). */
 int bp_shipice_get_counters(bp_shipice_t* h, int32_t env, int64_t* out);
 
 /* Device timing of the kernels this handle launches (bench.py's roofline): when enabled, CUDA

@@ -76,10 +76,10 @@ class Emu:
         return dict(zip(keys, o))
 
     def scal(self, env):
-        o = (C.c_longlong * 16)()
+        o = (C.c_longlong * 18)()
         self.L.emu_get_scal(self.h, C.c_int(env), o)
         keys = ["stamp", "n_awake", "n_pairs", "n_free", "n_order", "n_colours", "status", "n_apairs", "n_cached", "gjk",
-                "pairs_eval", "live_sum", "awake_sum", "recolour", "rebuild", "substeps"]
+                "pairs_eval", "live_sum", "awake_sum", "recolour", "rebuild", "substeps", "epa", "skipped"]
         return dict(zip(keys, list(o)))
 
     def layout_verts(self, l, b):

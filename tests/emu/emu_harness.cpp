@@ -54,7 +54,7 @@ int emu_load_layouts(void* h, int n_layouts, const int32_t* n_floes, const int32
     if (!err.empty()) { fprintf(stderr, "emu_load_layouts: %s\n", err.c_str()); return 1; }
     e->d.n_layouts = n_layouts;
     HostLayouts& H = e->H;
-    e->T.lv = H.lv.data(); e->T.ln = H.ln.data(); e->T.nv = H.nv.data(); e->T.rad = H.rad.data();
+    e->T.lv = H.lv.data(); e->T.ln = H.ln.data(); e->T.nv = H.nv.data(); e->T.rad = H.rad.data(); e->T.rbound = H.rbound.data();
     e->T.minv = H.minv.data(); e->T.iinv = H.iinv.data(); e->T.cog = H.cog.data(); e->T.mat_e = H.mat_e.data();
     e->T.mat_u = H.mat_u.data(); e->T.init = H.init.data(); e->T.nbody = H.nbody.data();
     e->O.n_robot_raw = n_ship_verts;
@@ -75,7 +75,7 @@ void emu_step(void* h, int env, double action) {
 void emu_set_robot_velocity(void* h, int env, double vx, double vy, double w) {
     Emu* e = (Emu*)h;
     EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
-    int r = ev.sc->robot; ev.vx[r] = vx; ev.vy[r] = vy; ev.vw[r] = w;
+    int r = ev.sc->robot; ev.body[r].vx = vx; ev.body[r].vy = vy; ev.body[r].vw = w;
 }
 void emu_substeps(void* h, int env, int n, int first) {
     Emu* e = (Emu*)h;
@@ -103,7 +103,7 @@ int emu_get_bodies(void* h, int env, double* out) {
     int nb = ev.sc->nbody;
     for (int b = 0; b < nb; b++) {
         V2 o = body_origin(ev, L, b);
-        out[6 * b] = o.x; out[6 * b + 1] = o.y; out[6 * b + 2] = ev.pa[b]; out[6 * b + 3] = ev.vx[b]; out[6 * b + 4] = ev.vy[b]; out[6 * b + 5] = ev.vw[b];
+        out[6 * b] = o.x; out[6 * b + 1] = o.y; out[6 * b + 2] = ev.body[b].pa; out[6 * b + 3] = ev.body[b].vx; out[6 * b + 4] = ev.body[b].vy; out[6 * b + 5] = ev.body[b].vw;
     }
     return nb;
 }
@@ -121,6 +121,7 @@ void emu_get_scal(void* h, int env, long long* o) {
     o[0] = s->stamp; o[1] = s->n_awake; o[2] = s->n_pairs; o[3] = s->n_free; o[4] = s->n_order; o[5] = s->n_colours;
     o[6] = s->status; o[7] = s->n_apairs; o[8] = s->n_cached; o[9] = s->stat_gjk; o[10] = s->stat_pairs_eval;
     o[11] = s->stat_live_sum; o[12] = s->stat_awake_sum; o[13] = s->stat_recolour; o[14] = s->stat_rebuild; o[15] = s->stat_substeps;
+    o[16] = s->stat_epa; o[17] = s->stat_skipped;
 }
 // hull vertices of body b of layout l (for the hull parity test)
 int emu_layout_verts(void* h, int l, int b, double* out, double* minv_iinv) {
@@ -142,9 +143,9 @@ void emu_render_obs(void* h, int env, int raw, unsigned char* out) {
     if (raw) {
         size_t base = (size_t)ev.sc->layout * e->d.NB;
         render_obs(S, e->O, r, e->H.rawv.data() + base * VMAX * 2, VMAX * 2, e->H.rawn.data() + base, e->H.rawcen.data() + base * 2,
-                   e->H.rawcen.data() + base * 2 + 1, 2, o.x, o.y, ev.pa[r], out);
+                   e->H.rawcen.data() + base * 2 + 1, 2, o.x, o.y, ev.body[r].pa, out);
     } else {
-        render_obs(S, e->O, r, ev.wv, VMAX * 2, L.nv, ev.cenx, ev.ceny, 1, o.x, o.y, ev.pa[r], out);
+        render_obs(S, e->O, r, ev.wv, VMAX * 2, L.nv, ev.cenx, ev.ceny, 1, o.x, o.y, ev.body[r].pa, out);
     }
 }
 void emu_spfa(const uint8_t* map, int H, int W, int si, int sj, float* dist, int32_t* parents) {

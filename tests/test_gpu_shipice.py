@@ -83,7 +83,7 @@ def test_batch_of_heterogeneous_layouts_and_episode_metrics(golden_layouts):
     rng = np.random.default_rng(3)
     alive = np.ones(E, dtype=bool)
     for k in range(60):
-        a = rng.uniform(-1, 1, E).astype(np.float32)
+        a = (0.3 * rng.uniform(-1, 1, E)).astype(np.float32)    # gentle steering: every episode reaches the goal line
         a[0] = 0.0                                        # env 0 sails straight to the goal
         obs, rew, term, trunc, info = env.step(a)
         done = met.update(info, rew, term | trunc)

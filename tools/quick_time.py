@@ -19,6 +19,12 @@ for k in range(steps):
     ev0.record(); env.step_async_nocheck(a); ev1.record(); torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     print("step %d: %.2f ms  -> %.0f env-steps/s   status %d" % (k, ms, E / ms * 1e3, int(env._status.max())), flush=True)
-c = env.counters(0); print(c)
+tot = np.zeros(8); cs = []
+for e in range(0, E, max(1, E // 64)):
+    c = env.counters(e); cs.append(c); tot += np.array(c["phase_clocks"], dtype=np.float64)
+if tot.sum() > 0:
+    names = ["integrate", "rebuild", "eval_pairs", "wake+order", "prestep+damp", "solve", "-", "-"]
+    print("phase share:", {n: round(float(t / tot.sum()), 3) for n, t in zip(names, tot) if n != "-"}, "clocks/substep %.0f" % (tot.sum() / sum(c["substeps"] for c in cs)))
+c = cs[0]; print(c)
 sub = max(c["substeps"], 1)
 print("per substep: awake %.1f live %.1f pairs_eval %.1f gjk %.1f recolour %.3f" % (c["awake_sum"] / sub, c["live_sum"] / sub, c["pairs_eval"] / sub, c["gjk"] / sub, c["recolour"] / sub))
