@@ -27,12 +27,16 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // ------------------------------------------------------------------------------------------------ kernels
 // Persistent warps: each warp pulls environment indices from a global counter and simulates one
 // environment at a time (envs differ widely in cost: contact-free water vs. an ice jam).
+#ifndef BP_MIN_BLOCKS
+#define BP_MIN_BLOCKS 4          // resident 128-thread blocks per SM the sim kernels are compiled for
+#endif
+
 struct StepArgs {
     char* mem; size_t env_bytes; Dims d; SimParams P; LayoutTab T; StepOut out;
     const float* actions; const int32_t* layout_ids; const uint8_t* mask; int* counter; int auto_reset;
 };
 
-__global__ void __launch_bounds__(128) k_shipice_reset(StepArgs a) {
+__global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_reset(StepArgs a) {
     for (;;) {
         int env = 0;
         if (bp_lane() == 0) env = atomicAdd(a.counter, 1);
@@ -47,7 +51,7 @@ __global__ void __launch_bounds__(128) k_shipice_reset(StepArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(128) k_shipice_step(StepArgs a) {
+__global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step(StepArgs a) {
     for (;;) {
         int env = 0;
         if (bp_lane() == 0) env = atomicAdd(a.counter, 1);
@@ -305,7 +309,7 @@ static int launch_obs(bp_shipice* h, uint8_t* obs, const uint8_t* mask, cudaStre
 
 static int sim_grid(bp_shipice* h) {
     // 4 warps per block; enough resident blocks to fill the SMs, never more warps than envs
-    int blocks = h->sm_count * 4;
+    int blocks = h->sm_count * BP_MIN_BLOCKS;
     int need = (h->d.n_envs + 3) / 4;
     return blocks < need ? blocks : need;
 }

@@ -83,6 +83,7 @@ struct EnvScal {
     int stamp, n_awake, n_pairs, cur, n_free, n_order, n_colours, dirty;
     int status, layout, nbody, robot, t, rebuild, n_apairs, n_cached;
     int any_wake, episode, done, first_layout;
+    double G;                     // monotone accumulator: bounds the growth of D[a] + D[b] of ANY pair
     int obs_raw, pad0, pad1, pad2;
     double total_work;
     long long stat_gjk, stat_pairs_eval, stat_live_sum, stat_awake_sum, stat_recolour, stat_rebuild, stat_substeps;
@@ -92,14 +93,16 @@ struct EnvScal {
 // Per-env mutable state lives in one block of global memory per env (identical offsets for every
 // env).  Records are arrays-of-structs sized to cache lines: a lane that works on one body / one
 // arbiter touches 1-2 lines instead of one line per field.
-struct alignas(16) BodyRec {      // 128 B = one L1/L2 line
+struct alignas(16) BodyRec {      // 128 B = one L1/L2 line: everything the solver needs of a body
     double px, py, pa;              // cog position (world), angle
     double vx, vy, vw;              // velocity
     double bx, by, bw;              // bias (pseudo) velocity
+    double minv, iinv;              // inverse mass / moment (0 for the kinematic robot)
     double rc, rs;                  // cos / sin of pa
-    double bbl, bbb, bbr, bbt;      // AABB incl. shape radius
     double D;                       // monotone bound on the path length travelled by any point of the body
+    double pad0, pad1;
 };
+struct BBox { double l, b, r, t; }; // AABB incl. shape radius
 struct ContactRec {                 // 96 B
     double r1x, r1y, r2x, r2y, jn, jt, jb, nm, tm, bias, bounce;
     unsigned hash, pad;
@@ -121,7 +124,8 @@ struct PairRec {                    // 24 B: neighbour-list entry
 struct EnvView {
     EnvScal* sc;
     BodyRec* body;                                                           // [NB]
-    double* b0;                                                              // [NB][4] AABB at neighbour-list build
+    BBox* bb;                                                                // [NB] current AABB
+    BBox* b0;                                                                // [NB] AABB at neighbour-list build
     double* wv;                                                              // [NB][VMAX][2] world vertices
     double *cenx, *ceny, *area, *tmp;                                        // [NB] |centroid|, area at last env step; scratch
     int* awake;                                                              // [NB]
@@ -129,7 +133,8 @@ struct EnvView {
     unsigned long long* colmask;                                             // [NB]
     PairRec* pair[2];                                                        // [PMAX] double-buffered over rebuilds
     int *adj_start, *adj, *deg;                                              // [NB+1], [2*PMAX], [NB]
-    int *queue, *apairs;                                                     // [PMAX] eval queue; pairs incident to awake bodies
+    int *queue, *queue0, *apairs;                                            // [PMAX] eval queues; pairs incident to awake bodies
+    double* ap_gate;                                                         // [PMAX] per apairs entry: no check needed while G < gate
     int* queue2; unsigned* qhint;                                            // [LMAX] EPA stage queue + simplex hint
     unsigned* livemask;                                                      // [PMAX/32]
     SlotRec* slot;                                                           // [LMAX]
@@ -154,7 +159,7 @@ BP_HD EnvView carve_env(char* base, const Dims& d, size_t* total) {
     TAKE(v.sc, EnvScal, sizeof(EnvScal))
     TAKE(v.body, BodyRec, NB * sizeof(BodyRec))
     TAKE(v.slot, SlotRec, Lm * sizeof(SlotRec))
-    TAKE(v.b0, double, NB * 32)
+    TAKE(v.bb, BBox, NB * sizeof(BBox)) TAKE(v.b0, BBox, NB * sizeof(BBox))
     TAKE(v.wv, double, NB * VMAX * 2 * 8)
     TAKE(v.cenx, double, NB * 8) TAKE(v.ceny, double, NB * 8) TAKE(v.area, double, NB * 8) TAKE(v.tmp, double, NB * 8)
     TAKE(v.awake, int, NB * 4)
@@ -163,7 +168,7 @@ BP_HD EnvView carve_env(char* base, const Dims& d, size_t* total) {
     TAKE(v.colmask, unsigned long long, NB * 8)
     TAKE(v.pair[0], PairRec, P * sizeof(PairRec)) TAKE(v.pair[1], PairRec, P * sizeof(PairRec))
     TAKE(v.adj_start, int, (NB + 1) * 4) TAKE(v.adj, int, 2 * P * 4) TAKE(v.deg, int, NB * 4)
-    TAKE(v.queue, int, P * 4) TAKE(v.apairs, int, P * 4)
+    TAKE(v.queue, int, P * 4) TAKE(v.queue0, int, P * 4) TAKE(v.apairs, int, P * 4) TAKE(v.ap_gate, double, P * 8)
     TAKE(v.queue2, int, Lm * 4) TAKE(v.qhint, unsigned, Lm * 4)
     TAKE(v.livemask, unsigned, (P / 32 + 1) * 4)
     TAKE(v.free_stack, int, Lm * 4) TAKE(v.order, int, Lm * 4) TAKE(v.colour, int, Lm * 4)
@@ -226,7 +231,8 @@ BP_DEV void refresh_body(const EnvView& ev, const LayoutView& L, int b) {
         l = fmin(l, wx); r = fmax(r, wx); bt = fmin(bt, wy); tp = fmax(tp, wy);
     }
     double rad = L.rad[b];
-    ev.body[b].bbl = l - rad; ev.body[b].bbb = bt - rad; ev.body[b].bbr = r + rad; ev.body[b].bbt = tp + rad;
+    BBox bx; bx.l = l - rad; bx.b = bt - rad; bx.r = r + rad; bx.t = tp + rad;
+    ev.bb[b] = bx;
 }
 // body position (pymunk Body.position = local origin in world space)
 BP_DEV V2 body_origin(const EnvView& ev, const LayoutView& L, int b) {
@@ -372,7 +378,7 @@ BP_DEV EdgeW support_edge(const Poly& P, const double* ln, double rc, double rs,
 struct Manifold { int count; V2 n; V2 p1[2], p2[2]; unsigned hash[2]; };
 
 BP_DEV Poly body_poly(const EnvView& ev, const LayoutView& L, int b) { Poly P; P.v = ev.wv + (size_t)b * VMAX * 2; P.n = L.nv[b]; return P; }
-BP_DEV V2 bb_centre(const BodyRec& r) { return mk((r.bbl + r.bbr) * 0.5, (r.bbb + r.bbt) * 0.5); }
+BP_DEV V2 bb_centre(const BBox& r) { return mk((r.l + r.r) * 0.5, (r.b + r.t) * 0.5); }
 
 // Contact manifold (<= 2 points, world space) of bodies a, b from the closest-feature result.
 BP_DEV void make_manifold(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {

@@ -31,8 +31,7 @@ BP_DEVNI void rebuild_pairs(const EnvView& ev, const SimParams& P, const Dims& d
     const int old_n = carry ? sc->n_pairs : 0;
     PairRec* np_ = ev.pair[nxt];
     for (int b = lane; b < nb; b += BP_NL) {
-        const BodyRec& r = ev.body[b];
-        ev.b0[4 * b] = r.bbl; ev.b0[4 * b + 1] = r.bbb; ev.b0[4 * b + 2] = r.bbr; ev.b0[4 * b + 3] = r.bbt;
+        ev.b0[b] = ev.bb[b];
         ev.deg[b] = 0;
     }
     bp_wsync();
@@ -40,13 +39,15 @@ BP_DEVNI void rebuild_pairs(const EnvView& ev, const SimParams& P, const Dims& d
     bool overflow = false;
     for (int i = 0; i < nb - 1; i++) {
         double mi = body_margin(P, sc, i);
-        double il = ev.b0[4 * i] - mi, ib = ev.b0[4 * i + 1] - mi, ir = ev.b0[4 * i + 2] + mi, it = ev.b0[4 * i + 3] + mi;
+        BBox bi = ev.b0[i];
+        double il = bi.l - mi, ib = bi.b - mi, ir = bi.r + mi, it = bi.t + mi;
         for (int base = i + 1; base < nb; base += BP_NL) {
             int j = base + lane;
             bool hit = false;
             if (j < nb) {
                 double mj = body_margin(P, sc, j);
-                hit = (il <= ev.b0[4 * j + 2] + mj && ev.b0[4 * j] - mj <= ir && ib <= ev.b0[4 * j + 3] + mj && ev.b0[4 * j + 1] - mj <= it);
+                BBox bj = ev.b0[j];
+                hit = (il <= bj.r + mj && bj.l - mj <= ir && ib <= bj.t + mj && bj.b - mj <= it);
             }
             int tot; int rk = bp_wrank(hit, &tot);
             if (hit) {
@@ -131,7 +132,7 @@ BP_DEV void add_body_pairs(const EnvView& ev, int bdy) {
         bool take = false; int p = -1;
         if (e < s1) { p = ev.adj[e]; take = !(pr[p].flags & 2); }
         int tot; int rk = bp_wrank(take, &tot);
-        if (take) { ev.apairs[n + rk] = p; pr[p].flags |= 2; }
+        if (take) { ev.apairs[n + rk] = p; ev.ap_gate[n + rk] = -1.0; pr[p].flags |= 2; }
         n += tot;
     }
     bp_wsync();
@@ -161,9 +162,11 @@ BP_DEVNI void build_apairs(const EnvView& ev) {
 // Compaction between the stages keeps lanes on the same code path (GJK/EPA are long and divergent).
 
 // Not-touching outcome for pair p: slot bookkeeping + separation bound.
-BP_DEV void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int p, int a, int b, double gap) {
+BP_DEV void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, double gap) {
     pr[p].flags |= 1;
-    pr[p].skip = ev.body[a].D + ev.body[b].D + gap * 0.999999 - 1e-9;
+    double g = gap * 0.999999 - 1e-9;
+    pr[p].skip = ev.body[a].D + ev.body[b].D + g;
+    ev.ap_gate[i] = sc->G + g;
     int slot = pr[p].live;
     if (slot >= 0 && ev.slot[slot].touch) {
         // separated: the arbiter stays cached (contacts + impulses kept) for `persistence` steps
@@ -176,7 +179,7 @@ BP_DEV void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int p, int a
 }
 
 // Touching / not-touching outcome from a closest-feature result.  Warp-convergent (slot allocation).
-BP_DEV void pair_finish(const EnvView& ev, const LayoutView& L, const Dims& d, PairRec* pr, bool active, int p, int a, int b, const Closest& pts) {
+BP_DEV void pair_finish(const EnvView& ev, const LayoutView& L, const Dims& d, PairRec* pr, bool active, int i, int p, int a, int b, const Closest& pts) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     Manifold m; m.count = 0;
@@ -232,10 +235,11 @@ BP_DEV void pair_finish(const EnvView& ev, const LayoutView& L, const Dims& d, P
             S.stamp = sc->stamp;
             pr[p].flags |= 1;
             pr[p].skip = -1.0;
+            ev.ap_gate[i] = -1.0;
             // a touching pair with an awake endpoint wakes the other (dynamic) endpoint
             if ((!ev.is_awake[a] && body_dynamic(L, a)) || (!ev.is_awake[b] && body_dynamic(L, b))) sc->any_wake = 1;
         } else {
-            pair_apart(ev, sc, pr, p, a, b, pts.d - L.rad[a] - L.rad[b]);
+            pair_apart(ev, sc, pr, i, p, a, b, pts.d - L.rad[a] - L.rad[b]);
         }
     }
     bp_wsync();
@@ -248,31 +252,45 @@ BP_DEVNI int eval_pairs(const EnvView& ev, const LayoutView& L, const Dims& d, i
     const int lane = bp_lane();
     PairRec* pr = ev.pair[sc->cur];
     const int n = sc->n_apairs;
-    // ---- stage 1
-    int nq = 0, n_eval = 0, n_skip = 0;
+    // ---- stage 1a: coarse gate scan over contiguous per-entry gates (no pair can need work while G < gate)
+    const double G = sc->G;
+    int n0 = 0;
     for (int base = i0; base < n; base += BP_NL) {
         int i = base + lane;
-        bool take = false; int p = -1;
-        if (i < n) {
-            p = ev.apairs[i];
+        bool pass = (i < n) && (G >= ev.ap_gate[i]);
+        int tot; int rk = bp_wrank(pass, &tot);
+        if (pass) ev.queue0[n0 + rk] = i;
+        n0 += tot;
+    }
+    bp_wsync();
+    // ---- stage 1b: exact need test + AABB filter on the survivors
+    int nq = 0, n_eval = 0, n_skip = 0;
+    for (int base = 0; base < n0; base += BP_NL) {
+        int k = base + lane;
+        bool take = false; int i = -1;
+        if (k < n0) {
+            i = ev.queue0[k];
+            int p = ev.apairs[i];
             PairRec q = pr[p];
             int a = q.key >> 16, b = q.key & 0xFFFF;
             bool mv = ev.moved[a] || ev.moved[b];
-            bool need = !(q.flags & 1) || (mv && (q.skip < 0.0 || ev.body[a].D + ev.body[b].D >= q.skip));
-            if (mv && !need) n_skip++;
-            if (need) {
+            double dsum = ev.body[a].D + ev.body[b].D;
+            bool need = !(q.flags & 1) || (mv && (q.skip < 0.0 || dsum >= q.skip));
+            if (!need) {
+                if (q.skip >= 0.0) { ev.ap_gate[i] = G + (q.skip - dsum); if (mv) n_skip++; }
+            } else {
                 n_eval++;
-                const BodyRec& A = ev.body[a]; const BodyRec& B = ev.body[b];
-                bool bbhit = (A.bbl <= B.bbr && B.bbl <= A.bbr && A.bbb <= B.bbt && B.bbb <= A.bbt);
+                BBox A = ev.bb[a], B = ev.bb[b];
+                bool bbhit = (A.l <= B.r && B.l <= A.r && A.b <= B.t && B.b <= A.t);
                 if (bbhit && !(L.minv[a] == 0.0 && L.minv[b] == 0.0)) take = true;
                 else {
-                    double gap = fmax(fmax(A.bbl - B.bbr, B.bbl - A.bbr), fmax(A.bbb - B.bbt, B.bbb - A.bbt));
-                    pair_apart(ev, sc, pr, p, a, b, bbhit ? 0.0 : gap);
+                    double gap = fmax(fmax(A.l - B.r, B.l - A.r), fmax(A.b - B.t, B.b - A.t));
+                    pair_apart(ev, sc, pr, i, p, a, b, bbhit ? 0.0 : gap);
                 }
             }
         }
         int tot; int rk = bp_wrank(take, &tot);
-        if (take) ev.queue[nq + rk] = p;
+        if (take) ev.queue[nq + rk] = i;
         nq += tot;
     }
     bp_wsync();
@@ -284,21 +302,23 @@ BP_DEVNI int eval_pairs(const EnvView& ev, const LayoutView& L, const Dims& d, i
         int p = -1, a = 0, b = 0;
         Closest pts; pts.d = 0; pts.id = 0; pts.n = mk(0, 0);
         unsigned hint = 0;
+        int i = -1;
         if (active) {
-            p = ev.queue[q];
+            i = ev.queue[q];
+            p = ev.apairs[i];
             unsigned key = pr[p].key;
             a = key >> 16; b = key & 0xFFFF;
             int capped = 0;
-            to_epa = gjk_only(body_poly(ev, L, a), body_poly(ev, L, b), bb_centre(ev.body[a]), bb_centre(ev.body[b]), pr[p].gjk, &pts, &hint, &gjk_it, &capped);
+            to_epa = gjk_only(body_poly(ev, L, a), body_poly(ev, L, b), bb_centre(ev.bb[a]), bb_centre(ev.bb[b]), pr[p].gjk, &pts, &hint, &gjk_it, &capped);
             if (capped) bp_atomic_or((unsigned*)&sc->status, ST_GJK_ITER);
         }
         int tot; int rk = bp_wrank(to_epa, &tot);
         if (to_epa) {
-            if (ne + rk < d.LMAX) { ev.queue2[ne + rk] = p; ev.qhint[ne + rk] = hint; }
+            if (ne + rk < d.LMAX) { ev.queue2[ne + rk] = i; ev.qhint[ne + rk] = hint; }
             else { bp_atomic_or((unsigned*)&sc->status, ST_LIVE_OVERFLOW); }
         }
         ne += tot;
-        pair_finish(ev, L, d, pr, active && !to_epa, p, a, b, pts);
+        pair_finish(ev, L, d, pr, active && !to_epa, i, p, a, b, pts);
     }
     if (ne > d.LMAX) ne = d.LMAX;
     // ---- stage 3
@@ -307,15 +327,17 @@ BP_DEVNI int eval_pairs(const EnvView& ev, const LayoutView& L, const Dims& d, i
         bool active = q < ne;
         int p = -1, a = 0, b = 0;
         Closest pts; pts.d = 0; pts.id = 0; pts.n = mk(0, 0);
+        int i = -1;
         if (active) {
-            p = ev.queue2[q];
+            i = ev.queue2[q];
+            p = ev.apairs[i];
             unsigned key = pr[p].key;
             a = key >> 16; b = key & 0xFFFF;
             int capped = 0;
             pts = gjk_epa(body_poly(ev, L, a), body_poly(ev, L, b), ev.qhint[q], &capped);
             if (capped) bp_atomic_or((unsigned*)&sc->status, ST_GJK_ITER);
         }
-        pair_finish(ev, L, d, pr, active, p, a, b, pts);
+        pair_finish(ev, L, d, pr, active, i, p, a, b, pts);
     }
     // statistics only
     int t1, t2, t3;
@@ -340,7 +362,7 @@ BP_DEVNI void wake_closure(const EnvView& ev, const LayoutView& L, const Dims& d
             int na = sc->n_awake;
             const PairRec* pr = ev.pair[sc->cur];
             for (int q = 0; q < nq; q++) {
-                int p = ev.queue[q];
+                int p = ev.apairs[ev.queue[q]];
                 int slot = pr[p].live;
                 if (slot < 0 || !ev.slot[slot].touch) continue;
                 unsigned key = pr[p].key;
@@ -436,8 +458,8 @@ BP_DEV void arb_prestep(const EnvView& ev, const LayoutView& L, const SimParams&
     int a = S.a, b = S.b;
     V2 n = mk(S.nx, S.ny);
     V2 tn = perp(n);
-    double ma = L.minv[a], ia = L.iinv[a], mb = L.minv[b], ib = L.iinv[b];
     const BodyRec& A = ev.body[a]; const BodyRec& B = ev.body[b];
+    double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     V2 delta = mk(B.px - A.px, B.py - A.py);
     V2 va = mk(A.vx, A.vy), vb = mk(B.vx, B.vy);
     double wa = A.vw, wb = B.vw;
@@ -462,8 +484,8 @@ BP_DEV void arb_warm(const EnvView& ev, const LayoutView& L, int s, double dt_co
     if (S.first) return;
     int a = S.a, b = S.b;
     V2 n = mk(S.nx, S.ny);
-    double ma = L.minv[a], ia = L.iinv[a], mb = L.minv[b], ib = L.iinv[b];
     BodyRec& A = ev.body[a]; BodyRec& B = ev.body[b];
+    double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     int cnt = S.cnt;
     for (int i = 0; i < cnt; i++) {
         const ContactRec& c = S.c[i];
@@ -480,8 +502,8 @@ BP_DEV void arb_solve(const EnvView& ev, const LayoutView& L, int s) {
     V2 n = mk(S.nx, S.ny);
     V2 tn = perp(n);
     double fr = S.u;
-    double ma = L.minv[a], ia = L.iinv[a], mb = L.minv[b], ib = L.iinv[b];
     BodyRec& A = ev.body[a]; BodyRec& B = ev.body[b];
+    double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     V2 va = mk(A.vx, A.vy), vb = mk(B.vx, B.vy);
     double wa = A.vw, wb = B.vw;
     V2 ba = mk(A.bx, A.by), bb = mk(B.bx, B.by);
@@ -529,6 +551,7 @@ BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P
     bp_wsync();
     // 1. integrate positions of the awake bodies (everything else has v = v_bias = 0 exactly)
     int na = sc->n_awake;
+    double dmax = 0.0;
     for (int k = lane; k < na; k += BP_NL) {
         int b = ev.awake[k];
         BodyRec& R = ev.body[b];
@@ -538,15 +561,20 @@ BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P
             double dx = (vx + bx) * dt, dy = (vy + by) * dt, da = (vw + bw) * dt;
             R.px = R.px + dx; R.py = R.py + dy; R.pa = R.pa + da;
             // motion bound of any point of the body (rotation about the cog), rounded up
-            R.D += (fabs(dx) + fabs(dy) + L.rbound[b] * fabs(da)) * 1.000001;
+            double dD = (fabs(dx) + fabs(dy) + L.rbound[b] * fabs(da)) * 1.000001;
+            R.D += dD;
+            dmax = fmax(dmax, dD);
             refresh_body(ev, L, b);
             double mg = body_margin(P, sc, b);
-            if (R.bbl < ev.b0[4 * b] - mg || R.bbr > ev.b0[4 * b + 2] + mg || R.bbb < ev.b0[4 * b + 1] - mg || R.bbt > ev.b0[4 * b + 3] + mg) sc->rebuild = 1;
+            BBox c = ev.bb[b], o = ev.b0[b];
+            if (c.l < o.l - mg || c.r > o.r + mg || c.b < o.b - mg || c.t > o.t + mg) sc->rebuild = 1;
             ev.moved_step[b] = 1;
             R.bx = 0.0; R.by = 0.0; R.bw = 0.0;
         }
         ev.moved[b] = mv ? 1 : 0;
     }
+    dmax = bp_wmax(dmax);
+    if (lane == 0) sc->G += 2.0 * dmax * 1.000001;
     bp_wsync();
     BP_TOCK(sc, 0, tk);
     if (sc->rebuild) { rebuild_pairs(ev, P, d, true); build_apairs(ev); }
@@ -686,7 +714,7 @@ BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& 
     if (lane == 0) {
         sc->stamp = 0; sc->n_awake = nb; sc->n_pairs = 0; sc->cur = 0; sc->n_free = d.LMAX; sc->n_order = 0; sc->n_colours = 0;
         sc->dirty = 1; sc->status = 0; sc->layout = layout_id; sc->nbody = nb; sc->robot = nb - 1; sc->t = 0; sc->rebuild = 0;
-        sc->n_apairs = 0; sc->n_cached = 0; sc->any_wake = 0; sc->total_work = 0.0;
+        sc->n_apairs = 0; sc->n_cached = 0; sc->any_wake = 0; sc->total_work = 0.0; sc->G = 0.0;
     }
     for (int b = lane; b < nb; b += BP_NL) {
         BodyRec& R = ev.body[b];
@@ -698,6 +726,7 @@ BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& 
         R.py = (s * cx + c * cy) + L.init[3 * b + 1];
         R.pa = a;
         R.vx = R.vy = R.vw = 0.0; R.bx = R.by = R.bw = 0.0; R.D = 0.0;
+        R.minv = L.minv[b]; R.iinv = L.iinv[b]; R.pad0 = R.pad1 = 0.0;
         refresh_body(ev, L, b);
         ev.awake[b] = b; ev.is_awake[b] = 1; ev.moved[b] = 0; ev.moved_step[b] = 0; ev.act[b] = 1;
     }

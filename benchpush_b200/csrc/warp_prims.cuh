@@ -32,6 +32,11 @@ BP_DEV int bp_wscan_excl(int v, int* total) {
     *total = __shfl_sync(0xffffffffu, x, 31);
     return x - v;
 }
+BP_DEV double bp_wmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 BP_DEV void bp_sincos(double a, double* s, double* c) { sincos(a, s, c); }
 #else
 #include <math.h>
@@ -44,6 +49,7 @@ BP_DEV bool bp_wany(bool p) { return p; }
 BP_DEV int bp_wbcast(int v) { return v; }
 BP_DEV int bp_wrank(bool pred, int* total) { *total = pred ? 1 : 0; return 0; }
 BP_DEV int bp_wscan_excl(int v, int* total) { *total = v; return 0; }
+BP_DEV double bp_wmax(double v) { return v; }
 BP_DEV void bp_sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
 #ifndef __CUDACC__
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
