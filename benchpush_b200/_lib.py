@@ -11,7 +11,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libbenchpush_b200.so")
+# BENCHPUSH_B200_LIB: development aid to load a differently-tuned build of the same CUDA library
+LIB_PATH = os.environ.get("BENCHPUSH_B200_LIB") or os.path.join(CSRC, "libbenchpush_b200.so")
 
 BP_VMAX = 20
 OBS_SHAPE = (4, 150, 150)

@@ -25,8 +25,9 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ kernels
-// Persistent warps: each warp pulls environment indices from a global counter and simulates one
-// environment at a time (envs differ widely in cost: contact-free water vs. an ice jam).
+// Persistent warps: each warp pulls batches of 32 / BP_NL environment indices from a global counter
+// and simulates them side by side, one per lane group (envs differ widely in cost: contact-free
+// water vs. an ice jam, so the batches are claimed dynamically).
 #ifndef BP_MIN_BLOCKS
 #define BP_MIN_BLOCKS 4          // resident 128-thread blocks per SM the sim kernels are compiled for
 #endif
@@ -36,41 +37,50 @@ struct StepArgs {
     const float* actions; const int32_t* layout_ids; const uint8_t* mask; int* counter; int auto_reset;
 };
 
+// Claim the next batch of environments for this warp: one per lane group.  Returns false when the
+// queue is empty.  Full-warp operation: every lane of the warp must call it (the groups of a warp
+// reconverge here after each batch, which keeps them in lockstep inside the substep loops).
+__device__ __forceinline__ bool claim_envs(int* counter, int n_envs, int* env) {
+    int base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, BP_GROUPS_PER_WARP);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    *env = base + bp_group_in_warp();
+    return base < n_envs;
+}
+
 __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_reset(StepArgs a) {
-    for (;;) {
-        int env = 0;
-        if (bp_lane() == 0) env = atomicAdd(a.counter, 1);
-        env = bp_wbcast(env);
-        if (env >= a.d.n_envs) break;
-        if (a.mask && !a.mask[env]) continue;
-        EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
-        int layout = a.layout_ids[env] % a.d.n_layouts;
-        shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
-        if (bp_lane() == 0) { ev.sc->first_layout = layout; ev.sc->episode = 0; ev.sc->done = 0; ev.sc->obs_raw = 1; }
-        bp_wsync();
+    int env;
+    while (claim_envs(a.counter, a.d.n_envs, &env)) {
+        if (env < a.d.n_envs && !(a.mask && !a.mask[env])) {
+            EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
+            int layout = a.layout_ids[env] % a.d.n_layouts;
+            shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
+            if (bp_lane() == 0) { ev.sc->first_layout = layout; ev.sc->episode = 0; ev.sc->done = 0; ev.sc->obs_raw = 1; }
+            bp_wsync();
+        }
+        __syncwarp();
     }
 }
 
 __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step(StepArgs a) {
-    for (;;) {
-        int env = 0;
-        if (bp_lane() == 0) env = atomicAdd(a.counter, 1);
-        env = bp_wbcast(env);
-        if (env >= a.d.n_envs) break;
-        EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
-        if (a.auto_reset && ev.sc->done) {
-            // next-step auto reset: the env moves on to its next trial (episode_idx % n_trials,
-            // ship_ice_env.py:188); this call returns the reset observation with reward 0.
-            int ep = ev.sc->episode + 1, first = ev.sc->first_layout;
-            int layout = (first + ep) % a.d.n_layouts;
-            shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
-            if (bp_lane() == 0) { ev.sc->first_layout = first; ev.sc->episode = ep; ev.sc->done = 0; ev.sc->obs_raw = 1; }
+    int env;
+    while (claim_envs(a.counter, a.d.n_envs, &env)) {
+        if (env < a.d.n_envs) {
+            EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
+            if (a.auto_reset && ev.sc->done) {
+                // next-step auto reset: the env moves on to its next trial (episode_idx % n_trials,
+                // ship_ice_env.py:188); this call returns the reset observation with reward 0.
+                int ep = ev.sc->episode + 1, first = ev.sc->first_layout;
+                int layout = (first + ep) % a.d.n_layouts;
+                shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
+                if (bp_lane() == 0) { ev.sc->first_layout = first; ev.sc->episode = ep; ev.sc->done = 0; ev.sc->obs_raw = 1; }
+            } else {
+                shipice_step_env(ev, a.T, a.P, a.d, (double)a.actions[env], env, a.out);
+                if (bp_lane() == 0) { ev.sc->done = a.out.terminated[env]; ev.sc->obs_raw = 0; }
+            }
             bp_wsync();
-            continue;
         }
-        shipice_step_env(ev, a.T, a.P, a.d, (double)a.actions[env], env, a.out);
-        if (bp_lane() == 0) { ev.sc->done = a.out.terminated[env]; ev.sc->obs_raw = 0; }
-        bp_wsync();
+        __syncwarp();
     }
 }
 
@@ -308,9 +318,11 @@ static int launch_obs(bp_shipice* h, uint8_t* obs, const uint8_t* mask, cudaStre
 }
 
 static int sim_grid(bp_shipice* h) {
-    // 4 warps per block; enough resident blocks to fill the SMs, never more warps than envs
+    // 4 warps per block, 32 / BP_NL envs per warp; enough resident blocks to fill the SMs, never more groups than envs
     int blocks = h->sm_count * BP_MIN_BLOCKS;
-    int need = (h->d.n_envs + 3) / 4;
+    if (const char* e = getenv("BP_BLOCKS_PER_SM")) { int b = atoi(e); if (b > 0 && b < BP_MIN_BLOCKS) blocks = h->sm_count * b; }   // tuning experiments only
+    int per_block = 4 * BP_GROUPS_PER_WARP;
+    int need = (h->d.n_envs + per_block - 1) / per_block;
     return blocks < need ? blocks : need;
 }
 

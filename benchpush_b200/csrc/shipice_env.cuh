@@ -23,7 +23,7 @@ struct StepOut {
 };
 
 // geometry/polygon.py:25-41 on the world-space hull vertices of body b (np.roll(y, 1)[i] = y[i-1]).
-BP_DEV void area_centroid_abs(const double* wv, int n, double* area, double* cx, double* cy) {
+BP_DEVNI void area_centroid_abs(const double* wv, int n, double* area, double* cx, double* cy) {
     double s1 = 0.0, s2 = 0.0;
     for (int i = 0; i < n; i++) {
         int j = (i == 0) ? n - 1 : i - 1;

@@ -211,7 +211,7 @@ BP_DEV V2 lerp(V2 a, V2 b, double t) { return a * (1.0 - t) + b * t; }
 BP_DEV V2 rotv(V2 a, V2 b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 // ------------------------------------------------------------------ geometry refresh of one body
-BP_DEV void refresh_body(const EnvView& ev, const LayoutView& L, int b) {
+BP_DEVNI void refresh_body(const EnvView& ev, const LayoutView& L, int b) {
     double s, c;
     bp_sincos(ev.body[b].pa, &s, &c);
     ev.body[b].rc = c; ev.body[b].rs = s;
@@ -223,6 +223,7 @@ BP_DEV void refresh_body(const EnvView& ev, const LayoutView& L, int b) {
     double* wv = ev.wv + (size_t)b * VMAX * 2;
     int n = L.nv[b];
     double l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
+#pragma unroll 2
     for (int i = 0; i < n; i++) {
         double x = lv[2 * i], y = lv[2 * i + 1];
         double wx = c * x + ms * y + tx;
@@ -245,8 +246,11 @@ BP_DEV V2 body_origin(const EnvView& ev, const LayoutView& L, int b) {
 struct MPoint { V2 ab; unsigned id; };       // Minkowski difference vertex; id = (index_a << 8) | index_b
 struct Poly { const double* v; int n; };
 
-BP_DEV int support_index(const Poly& P, V2 n) {
+// The one copy of the support scan (GJK, EPA and the manifold builder all call it): the hot path is
+// instruction-fetch bound (profiles/), so shared out-of-line leaves beat inlined copies.
+BP_DEVNI int support_index(const Poly& P, V2 n) {
     double mx = -INFINITY; int idx = 0;
+#pragma unroll 4
     for (int i = 0; i < P.n; i++) {
         double d = P.v[2 * i] * n.x + P.v[2 * i + 1] * n.y;
         if (d > mx) { mx = d; idx = i; }
@@ -273,7 +277,7 @@ BP_DEV bool point_greater(V2 a, V2 b, V2 c) {
     return (b.y - a.y) * (a.x + b.x - 2 * c.x) > (b.x - a.x) * (a.y + b.y - 2 * c.y);
 }
 struct Closest { V2 n; double d; unsigned id; };
-BP_DEV Closest closest_points(const MPoint& v0, const MPoint& v1) {
+BP_DEVNI Closest closest_points(const MPoint& v0, const MPoint& v1) {
     double t = closest_t(v0.ab, v1.ab);
     V2 p = lerp_t(v0.ab, v1.ab, t);
     V2 delta = v1.ab - v0.ab;
@@ -295,6 +299,7 @@ BP_DEVNI Closest epa(const Poly& A, const Poly& B, MPoint h0, MPoint h1, MPoint 
     int count = 3, iteration = 1;
     for (;;) {
         int mini = 0; double minDist = INFINITY;
+#pragma unroll 1
         for (int j = 0, i = count - 1; j < count; i = j, j++) {
             double d = closest_dist(hull[i].ab, hull[j].ab);
             if (d < minDist) { minDist = d; mini = i; }
@@ -305,6 +310,7 @@ BP_DEVNI Closest epa(const Poly& A, const Poly& B, MPoint h0, MPoint h1, MPoint 
         if (!dup && point_greater(v0.ab, v1.ab, p.ab) && iteration < EPA_MAX_IT) {
             int count2 = 1;
             hull2[0] = p;
+#pragma unroll 1
             for (int i = 0; i < count; i++) {
                 int index = (mini + 1 + i) % count;
                 V2 q0 = hull2[count2 - 1].ab;
@@ -381,7 +387,7 @@ BP_DEV Poly body_poly(const EnvView& ev, const LayoutView& L, int b) { Poly P; P
 BP_DEV V2 bb_centre(const BBox& r) { return mk((r.l + r.r) * 0.5, (r.b + r.t) * 0.5); }
 
 // Contact manifold (<= 2 points, world space) of bodies a, b from the closest-feature result.
-BP_DEV void make_manifold(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {
+BP_DEVNI void make_manifold(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {
     Poly A = body_poly(ev, L, a), B = body_poly(ev, L, b);
     m->count = 0;
     double ra = L.rad[a], rb = L.rad[b];

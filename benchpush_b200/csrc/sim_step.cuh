@@ -162,7 +162,7 @@ BP_DEVNI void build_apairs(const EnvView& ev) {
 // Compaction between the stages keeps lanes on the same code path (GJK/EPA are long and divergent).
 
 // Not-touching outcome for pair p: slot bookkeeping + separation bound.
-BP_DEV void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, double gap) {
+BP_DEVNI void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, double gap) {
     pr[p].flags |= 1;
     double g = gap * 0.999999 - 1e-9;
     pr[p].skip = ev.body[a].D + ev.body[b].D + g;
@@ -179,7 +179,7 @@ BP_DEV void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p
 }
 
 // Touching / not-touching outcome from a closest-feature result.  Warp-convergent (slot allocation).
-BP_DEV void pair_finish(const EnvView& ev, const LayoutView& L, const Dims& d, PairRec* pr, bool active, int i, int p, int a, int b, const Closest& pts) {
+BP_DEVNI void pair_finish(const EnvView& ev, const LayoutView& L, const Dims& d, PairRec* pr, bool active, int i, int p, int a, int b, const Closest& pts) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     Manifold m; m.count = 0;
@@ -382,9 +382,8 @@ BP_DEVNI void wake_closure(const EnvView& ev, const LayoutView& L, const Dims& d
 }
 
 // Free cached (separated) arbiters older than `persistence` steps (cpSpaceArbiterSetFilter).
-BP_DEV void expire_cached(const EnvView& ev, const SimParams& P, const Dims& d) {
+BP_DEVNI void expire_cached(const EnvView& ev, const SimParams& P, const Dims& d) {
     EnvScal* sc = ev.sc;
-    if (sc->n_cached <= 0) return;
     const int lane = bp_lane();
     PairRec* pr = ev.pair[sc->cur];
     for (int base = 0; base < d.LMAX; base += BP_NL) {
@@ -464,6 +463,7 @@ BP_DEV void arb_prestep(const EnvView& ev, const LayoutView& L, const SimParams&
     V2 va = mk(A.vx, A.vy), vb = mk(B.vx, B.vy);
     double wa = A.vw, wb = B.vw;
     int cnt = S.cnt;
+#pragma unroll 1
     for (int i = 0; i < cnt; i++) {
         ContactRec& c = S.c[i];
         V2 r1 = mk(c.r1x, c.r1y), r2 = mk(c.r2x, c.r2y);
@@ -487,6 +487,7 @@ BP_DEV void arb_warm(const EnvView& ev, const LayoutView& L, int s, double dt_co
     BodyRec& A = ev.body[a]; BodyRec& B = ev.body[b];
     double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     int cnt = S.cnt;
+#pragma unroll 1
     for (int i = 0; i < cnt; i++) {
         const ContactRec& c = S.c[i];
         V2 r1 = mk(c.r1x, c.r1y), r2 = mk(c.r2x, c.r2y);
@@ -509,6 +510,7 @@ BP_DEV void arb_solve(const EnvView& ev, const LayoutView& L, int s) {
     V2 ba = mk(A.bx, A.by), bb = mk(B.bx, B.by);
     double bwa = A.bw, bwb = B.bw;
     int cnt = S.cnt;
+#pragma unroll 1
     for (int i = 0; i < cnt; i++) {
         ContactRec& c = S.c[i];
         V2 r1 = mk(c.r1x, c.r1y), r2 = mk(c.r2x, c.r2y);
@@ -583,7 +585,7 @@ BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P
     int nq = eval_pairs(ev, L, d, 0);
     BP_TOCK(sc, 2, tk);
     wake_closure(ev, L, d, nq);
-    expire_cached(ev, P, d);
+    if (sc->n_cached > 0) expire_cached(ev, P, d);
     if (sc->dirty) build_order(ev, L, d);
     BP_TOCK(sc, 3, tk);
     // 3. prestep (uses the pre-damping velocities for the bounce term)

@@ -1,8 +1,8 @@
-// Warp-level primitives used by the env kernels (one warp simulates one environment).
+// Lane-group primitives used by the env kernels (a group of BP_NL lanes simulates one environment).
 //
 // All cross-lane communication in the kernels goes through memory + bp_wsync() or through the few
 // primitives below, so the same source also compiles as plain host C++ with a "warp" of ONE lane
-// (BP_HOST_EMU, used only by tests/ to debug kernel logic on machines without a GPU — the shipped
+// (BP_HOST_EMU: a "group" of ONE lane, used only by tests/ to debug kernel logic on machines without a GPU — the shipped
 // library never contains or calls that build).
 #pragma once
 #include <stdint.h>
@@ -10,31 +10,50 @@
 #if defined(__CUDACC__) && !defined(BP_HOST_EMU)
 #define BP_DEV __device__ __forceinline__
 #define BP_DEVNI __device__ __noinline__
-#define BP_NL 32
-BP_DEV int bp_lane() { return threadIdx.x & 31; }
-BP_DEV void bp_wsync() { __syncwarp(); }
-BP_DEV bool bp_wany(bool p) { return __any_sync(0xffffffffu, p); }
-BP_DEV int bp_wbcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
-// rank of this lane among the lanes with pred set (ascending lane order) and the total
+// One environment is simulated by a GROUP of BP_NL consecutive lanes of a warp (BP_NL = 32, 16, 8 or
+// 4; 32 / BP_NL environments share a warp).  Groups of one warp start every substep together and run
+// the same instruction stream, so SIMT divergence/reconvergence keeps them in lockstep through the
+// phases of a substep; all cross-lane primitives below are scoped to the calling lane's group
+// (sub-warp masks, like cooperative_groups::thread_block_tile).
+#ifndef BP_GROUP
+#define BP_GROUP 32
+#endif
+#define BP_NL BP_GROUP
+#define BP_GROUPS_PER_WARP (32 / BP_NL)
+BP_DEV int bp_lane() { return threadIdx.x & (BP_NL - 1); }
+BP_DEV int bp_group_in_warp() { return (threadIdx.x & 31) / BP_NL; }
+#if BP_GROUP == 32
+BP_DEV unsigned bp_gshift() { return 0u; }
+BP_DEV unsigned bp_gmask() { return 0xffffffffu; }
+#else
+BP_DEV unsigned bp_gshift() { return threadIdx.x & 31u & ~(unsigned)(BP_NL - 1); }
+BP_DEV unsigned bp_gmask() { return ((1u << BP_NL) - 1u) << bp_gshift(); }
+#endif
+BP_DEV void bp_wsync() { __syncwarp(bp_gmask()); }
+BP_DEV bool bp_wany(bool p) { return __any_sync(bp_gmask(), p); }
+BP_DEV int bp_wbcast(int v) { return __shfl_sync(bp_gmask(), v, 0, BP_NL); }
+// rank of this lane among the lanes of its group with pred set (ascending lane order) and the total
 BP_DEV int bp_wrank(bool pred, int* total) {
-    unsigned m = __ballot_sync(0xffffffffu, pred);
+    unsigned m = __ballot_sync(bp_gmask(), pred) >> bp_gshift();
     *total = __popc(m);
     return __popc(m & ((1u << bp_lane()) - 1u));
 }
-// exclusive prefix sum over lanes (ascending lane order) and the total
+// exclusive prefix sum over the lanes of the group (ascending lane order) and the total
 BP_DEV int bp_wscan_excl(int v, int* total) {
     int x = v;
+    const unsigned gm = bp_gmask();
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, x, o);
+    for (int o = 1; o < BP_NL; o <<= 1) {
+        int y = __shfl_up_sync(gm, x, o, BP_NL);
         if (bp_lane() >= o) x += y;
     }
-    *total = __shfl_sync(0xffffffffu, x, 31);
+    *total = __shfl_sync(gm, x, BP_NL - 1, BP_NL);
     return x - v;
 }
 BP_DEV double bp_wmax(double v) {
+    const unsigned gm = bp_gmask();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = BP_NL / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(gm, v, o, BP_NL));
     return v;
 }
 BP_DEV void bp_sincos(double a, double* s, double* c) { sincos(a, s, c); }

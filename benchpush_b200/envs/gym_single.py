@@ -1,0 +1,62 @@
+"""Single-environment view with the reference's exact return types, for callers written against
+``ShipIceEnv`` (ship_ice_env.py:37-355): ``reset() -> (np.uint8[4,150,150], info)``,
+``step(a) -> (obs, float, bool, bool, info)`` with ``info`` holding python / numpy values
+(ship_ice_env.py:241-247, 337-345).  It owns a ``ShipIceVecEnv`` with one env; nothing is simulated
+on the host.  gymnasium is not imported (absent from this image); the class is duck-typed and can be
+registered by a gymnasium user."""
+from __future__ import annotations
+
+import numpy as np
+
+from .ship_ice import ShipIceVecEnv
+
+
+class ShipIceEnvB200:
+    metadata = {"render_modes": []}
+
+    def __init__(self, cfg=None, **kw):
+        self._v = ShipIceVecEnv(num_envs=1, cfg=cfg, **kw)
+        self.cfg = self._v.cfg
+        self.goal = self._v.goal
+        self.max_yaw_rate_step = self._v.max_yaw_rate_step
+        self.beta = self._v.beta
+        self.num_channels = self._v.num_channels
+        self.episode_idx = None
+        self.t = 0
+        self.total_work = [0, []]
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def _info(self, info, reset):
+        out = {"state": tuple(float(x) for x in info["state"][0].tolist()),
+               "total_work": float(info["total_work"][0]) if not reset else 0,
+               "obs": info["obs"][0]}
+        if not reset:
+            out.update({"collision reward": float(info["collision reward"][0]),
+                        "scaled collision reward": float(info["scaled collision reward"][0]),
+                        "dist reward": float(info["dist reward"][0]),
+                        "trial_success": bool(info["trial_success"][0])})
+        return out
+
+    def reset(self, seed=None, options=None):
+        self.episode_idx = 0 if self.episode_idx is None else self.episode_idx + 1
+        obs, info = self._v.reset()
+        self.t = 0
+        self.total_work = [0, []]
+        return obs[0].cpu().numpy(), self._info(info, True)
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float32).reshape(1)
+        obs, r, term, trunc, info = self._v.step(a)
+        self.t += 1
+        out = self._info(info, False)
+        self.total_work[0] = out["total_work"]
+        return obs[0].cpu().numpy(), float(r[0]), bool(term[0]), bool(trunc[0]), out
+
+    def render(self):
+        raise NotImplementedError("rendering is out of scope for the batched simulator")
+
+    def close(self):
+        self._v.close()
