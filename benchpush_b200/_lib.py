@@ -70,6 +70,7 @@ def lib():
         L.bp_shipice_load_layouts.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
         L.bp_shipice_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
         L.bp_shipice_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
+        L.bp_shipice_step_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
         L.bp_shipice_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs)]
         L.bp_shipice_get_obstacles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.bp_shipice_get_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -88,7 +89,7 @@ def lib():
 
 EXPORTS = [
     "bp_version", "bp_last_error", "bp_device_count", "bp_shipice_default_config", "bp_shipice_create",
-    "bp_shipice_destroy", "bp_shipice_load_layouts", "bp_shipice_reset", "bp_shipice_step", "bp_shipice_step_host",
+    "bp_shipice_destroy", "bp_shipice_load_layouts", "bp_shipice_reset", "bp_shipice_step", "bp_shipice_step_masked", "bp_shipice_step_host",
     "bp_shipice_get_obstacles", "bp_shipice_get_bodies", "bp_shipice_get_counters", "bp_shipice_env_bytes",
     "bp_shipice_set_profiling", "bp_shipice_get_kernel_ms",
     "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host",

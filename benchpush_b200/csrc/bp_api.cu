@@ -12,6 +12,7 @@
 #include "host_tables.h"
 #include "raster.cuh"
 #include "shipice_env.cuh"
+#include "sim_batch.cuh"
 #include "spfa.cuh"
 
 using namespace bp;
@@ -35,6 +36,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 struct StepArgs {
     char* mem; size_t env_bytes; Dims d; SimParams P; LayoutTab T; StepOut out;
     const float* actions; const int32_t* layout_ids; const uint8_t* mask; int* counter; int auto_reset;
+    const DevConst* C;
 };
 
 // Claim the next batch of environments for this warp: one per lane group.  Returns false when the
@@ -62,10 +64,11 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_reset(StepArgs a
     }
 }
 
-__global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step(StepArgs a) {
+// One env per warp (the first design; kept for A/B measurements: BP_STEP_IMPL=warp).
+__global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepArgs a) {
     int env;
     while (claim_envs(a.counter, a.d.n_envs, &env)) {
-        if (env < a.d.n_envs) {
+        if (env < a.d.n_envs && !(a.mask && !a.mask[env])) {
             EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
             if (a.auto_reset && ev.sc->done) {
                 // next-step auto reset: the env moves on to its next trial (episode_idx % n_trials,
@@ -80,6 +83,20 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step(StepArgs a)
             }
             bp_wsync();
         }
+        __syncwarp();
+    }
+}
+
+// Batched step: each warp claims BK consecutive envs and advances them together (sim_batch.cuh).
+__global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step(StepArgs a) {
+    __shared__ BatchShared SH[4];
+    BatchShared& S = SH[threadIdx.x >> 5];
+    for (;;) {
+        int env0 = 0;
+        if ((threadIdx.x & 31) == 0) env0 = atomicAdd(a.counter, BK);
+        env0 = __shfl_sync(0xffffffffu, env0, 0);
+        if (env0 >= a.d.n_envs) break;
+        shipice_step_batch(a.C, S, a.mem, a.env_bytes, env0, a.actions, a.mask, a.out, a.auto_reset);
         __syncwarp();
     }
 }
@@ -134,6 +151,8 @@ struct bp_shipice {
     double *d_rawv = nullptr, *d_rawcen = nullptr; int* d_rawn = nullptr;
     char* mem = nullptr; size_t env_bytes = 0;
     int* counter = nullptr;
+    DevConst* d_const = nullptr;   // Dims, SimParams, array offsets, layout tables (device copy)
+    bool warp_impl = false;        // BP_STEP_IMPL=warp: one env per warp (A/B measurements)
     StepOut out;               // internal device outputs
     int32_t* d_layout_ids = nullptr;
     float* d_actions = nullptr; uint8_t* d_obs = nullptr;   // only for the host-buffer entry point
@@ -274,6 +293,12 @@ int bp_shipice_load_layouts(bp_shipice_t* h, int32_t n_layouts, const int32_t* n
     if ((rc = dev_upload(h, H.rawcen, &p))) return rc; h->d_rawcen = (double*)p;
     if ((rc = dev_upload(h, H.rawn, &q))) return rc; h->d_rawn = (int*)q;
     h->d.n_layouts = n_layouts;
+    DevConst hc;
+    hc.d = h->d; hc.P = h->P; hc.off = env_offsets(h->d); hc.T = h->T;
+    CUDA_TRY(cudaMalloc((void**)&h->d_const, sizeof(DevConst)));
+    h->dev_allocs.push_back(h->d_const);
+    CUDA_TRY(cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice));
+    if (const char* e = getenv("BP_STEP_IMPL")) h->warp_impl = (strcmp(e, "warp") == 0);
     h->layouts_loaded = true;
     return BP_OK;
 }
@@ -326,6 +351,15 @@ static int sim_grid(bp_shipice* h) {
     return blocks < need ? blocks : need;
 }
 
+static int batch_grid(bp_shipice* h) {
+    // 4 warps per block, BK envs per warp batch; never more warps than batches
+    int blocks = h->sm_count * BP_MIN_BLOCKS;
+    if (const char* e = getenv("BP_BLOCKS_PER_SM")) { int b = atoi(e); if (b > 0 && b < BP_MIN_BLOCKS) blocks = h->sm_count * b; }   // tuning experiments only
+    int per_block = 4 * BK;
+    int need = (h->d.n_envs + per_block - 1) / per_block;
+    return blocks < need ? blocks : need;
+}
+
 int bp_shipice_reset(bp_shipice_t* h, const int32_t* layout_ids, const uint8_t* mask, const bp_shipice_outputs* out, void* stream) {
     if (!h || !layout_ids) return fail(BP_ERR_INVALID, "null argument");
     if (!h->layouts_loaded) return fail(BP_ERR_STATE, "load layouts before reset");
@@ -334,7 +368,7 @@ int bp_shipice_reset(bp_shipice_t* h, const int32_t* layout_ids, const uint8_t* 
     CUDA_TRY(cudaMemsetAsync(h->counter, 0, 4, st));
     StepArgs a;
     a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
-    a.actions = nullptr; a.layout_ids = layout_ids; a.mask = mask; a.counter = h->counter; a.auto_reset = 0;
+    a.actions = nullptr; a.layout_ids = layout_ids; a.mask = mask; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const;
     k_shipice_reset<<<sim_grid(h), 128, 0, st>>>(a);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -344,7 +378,7 @@ int bp_shipice_reset(bp_shipice_t* h, const int32_t* layout_ids, const uint8_t* 
     return copy_outputs(h, out, st, cudaMemcpyDeviceToDevice);
 }
 
-int bp_shipice_step(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out, void* stream) {
+int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t* mask, const bp_shipice_outputs* out, void* stream) {
     if (!h || !actions) return fail(BP_ERR_INVALID, "null argument");
     if (!h->was_reset) return fail(BP_ERR_STATE, "reset before step");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -352,15 +386,20 @@ int bp_shipice_step(bp_shipice_t* h, const float* actions, const bp_shipice_outp
     CUDA_TRY(cudaMemsetAsync(h->counter, 0, 4, st));
     StepArgs a;
     a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
-    a.actions = actions; a.layout_ids = nullptr; a.mask = nullptr; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset;
+    a.actions = actions; a.layout_ids = nullptr; a.mask = mask; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset; a.C = h->d_const;
     prof_begin(h, 0, st);
-    k_shipice_step<<<sim_grid(h), 128, 0, st>>>(a);
+    if (h->warp_impl) k_shipice_step_warp<<<sim_grid(h), 128, 0, st>>>(a);
+    else k_shipice_step<<<batch_grid(h), 128, 0, st>>>(a);
     prof_end(h, st);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
-    int rc = launch_obs(h, out ? out->obs : nullptr, nullptr, st);
+    int rc = launch_obs(h, out ? out->obs : nullptr, mask, st);
     if (rc) return rc;
     return copy_outputs(h, out, st, cudaMemcpyDeviceToDevice);
+}
+
+int bp_shipice_step(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out, void* stream) {
+    return bp_shipice_step_masked(h, actions, nullptr, out, stream);
 }
 
 int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* oh) {

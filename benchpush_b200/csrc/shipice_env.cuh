@@ -76,13 +76,11 @@ BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const Sim
     bp_wsync();
 }
 
-BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, double action, int env, const StepOut& out) {
+// ship_ice_env.py:263-274: yaw rate from the action, constant surge along the heading at step start
+BP_DEVNI void shipice_step_begin(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, double action) {
     EnvScal* sc = ev.sc;
-    LayoutView L = layout_view(T, d, sc->layout);
-    const int lane = bp_lane();
     const int r = sc->robot;
-    // ship_ice_env.py:263-274: yaw rate from the action, constant surge along the heading at step start
-    if (lane == 0) {
+    if (bp_lane() == 0) {
         sc->t++;
         double a = ev.body[r].pa;
         double s, c; bp_sincos(a, &s, &c);
@@ -92,16 +90,25 @@ BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimP
     }
     bp_wsync();
     sleep_pass(ev, L, d);
-    bool yaw_violated = false, boundary_violated = false;
-    for (int k = 0; k < P.substeps; k++) {
-        substep(ev, L, P, d, P.dt, P.dt);
-        // ship_ice_env.py:284-290
-        double a = ev.body[r].pa;
-        if (a <= P.yaw_lo || a >= P.yaw_hi) { if (lane == 0) ev.body[r].vw = 0.0; yaw_violated = true; }
-        V2 o = body_origin(ev, L, r);
-        if (o.x < 0 || o.x > P.map_w) boundary_violated = true;
-        bp_wsync();
-    }
+}
+
+// ship_ice_env.py:284-290, after every substep: yaw limit (zero the yaw rate, never clamp the angle) and
+// boundary flag.  Executed by ONE lane for its env; returns bit0 = yaw violated, bit1 = boundary violated.
+BP_DEV int shipice_substep_checks(const EnvView& ev, const LayoutView& L, const SimParams& P, int r) {
+    int f = 0;
+    double a = ev.body[r].pa;
+    if (a <= P.yaw_lo || a >= P.yaw_hi) { ev.body[r].vw = 0.0; f |= 1; }
+    V2 o = body_origin(ev, L, r);
+    if (o.x < 0 || o.x > P.map_w) f |= 2;
+    return f;
+}
+
+// ship_ice_env.py:291-345: terminal tests, work, reward, info.
+BP_DEVNI void shipice_step_finish(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, int env, const StepOut& out,
+                                  bool yaw_violated, bool boundary_violated) {
+    EnvScal* sc = ev.sc;
+    const int lane = bp_lane();
+    const int r = sc->robot;
     V2 o = body_origin(ev, L, r);
     bool boundary_terminal = false;
     if (o.x < 0 && fabs(o.x - 0) >= P.boundary_limit) boundary_terminal = true;
@@ -149,6 +156,23 @@ BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimP
         out.trial_success[env] = success ? 1 : 0; out.status[env] = sc->status;
     }
     bp_wsync();
+}
+
+// One env, one warp: ShipIceEnv.step.
+BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, double action, int env, const StepOut& out) {
+    EnvScal* sc = ev.sc;
+    LayoutView L = layout_view(T, d, sc->layout);
+    const int r = sc->robot;
+    shipice_step_begin(ev, L, P, d, action);
+    int flags = 0;
+    for (int k = 0; k < P.substeps; k++) {
+        substep(ev, L, P, d, P.dt, P.dt);
+        int f = 0;
+        if (bp_lane() == 0) f = shipice_substep_checks(ev, L, P, r);
+        flags |= bp_wbcast(f);
+        bp_wsync();
+    }
+    shipice_step_finish(ev, L, P, d, env, out, (flags & 1) != 0, (flags & 2) != 0);
 }
 
 }  // namespace bp

@@ -180,11 +180,42 @@ BP_HD EnvView carve_env(char* base, const Dims& d, size_t* total) {
 BP_HD EnvView make_view(char* base, const Dims& d) { return carve_env(base, d, nullptr); }
 static inline size_t env_mem_size(const Dims& d) { size_t t = 0; carve_env((char*)0, d, &t); return BP_ALIGN128(t); }
 
+// The offsets of the per-env arrays are the same for every env of a handle: they are computed once
+// on the host (env_offsets) so that device code can form `base + constant` for just the arrays it
+// touches (view_at is inlined and dead fields disappear), instead of re-deriving the whole carve.
+#define BP_ENV_FIELD_LIST(X)                                                                         \
+    X(0, sc, EnvScal) X(1, body, BodyRec) X(2, slot, SlotRec) X(3, bb, BBox) X(4, b0, BBox) X(5, wv, double)      \
+    X(6, cenx, double) X(7, ceny, double) X(8, area, double) X(9, tmp, double) X(10, awake, int)                 \
+    X(11, is_awake, unsigned char) X(12, moved, unsigned char) X(13, moved_step, unsigned char)                  \
+    X(14, act, unsigned char) X(15, colmask, unsigned long long) X(16, pair[0], PairRec) X(17, pair[1], PairRec) \
+    X(18, adj_start, int) X(19, adj, int) X(20, deg, int) X(21, queue, int) X(22, queue0, int) X(23, apairs, int) \
+    X(24, ap_gate, double) X(25, queue2, int) X(26, qhint, unsigned) X(27, livemask, unsigned)                   \
+    X(28, free_stack, int) X(29, order, int) X(30, colour, int) X(31, col_start, int)
+struct EnvOff { unsigned o[32]; };
+static inline EnvOff env_offsets(const Dims& d) {
+    EnvOff O;
+    EnvView v = carve_env((char*)0, d, nullptr);
+#define X(i, member, type) O.o[i] = (unsigned)(size_t)v.member;
+    BP_ENV_FIELD_LIST(X)
+#undef X
+    return O;
+}
+BP_DEV EnvView view_at(char* base, const EnvOff& O) {
+    EnvView v;
+#define X(i, member, type) v.member = (type*)(base + O.o[i]);
+    BP_ENV_FIELD_LIST(X)
+#undef X
+    return v;
+}
+
 struct LayoutView {
     const double *lv, *ln, *rad, *rbound, *minv, *iinv, *cog, *mat_e, *mat_u, *init;
     const int* nv;
     int nbody;
 };
+// Everything a kernel needs that is constant for a handle; lives in device memory (one copy per
+// handle) so that out-of-line device functions can take it as ONE pointer.
+struct DevConst { Dims d; SimParams P; EnvOff off; LayoutTab T; };
 BP_DEV LayoutView layout_view(const LayoutTab& T, const Dims& d, int l) {
     LayoutView L;
     size_t o = (size_t)l * d.NB;
@@ -211,7 +242,7 @@ BP_DEV V2 lerp(V2 a, V2 b, double t) { return a * (1.0 - t) + b * t; }
 BP_DEV V2 rotv(V2 a, V2 b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 // ------------------------------------------------------------------ geometry refresh of one body
-BP_DEVNI void refresh_body(const EnvView& ev, const LayoutView& L, int b) {
+BP_DEV void refresh_body_impl(const EnvView& ev, const LayoutView& L, int b) {
     double s, c;
     bp_sincos(ev.body[b].pa, &s, &c);
     ev.body[b].rc = c; ev.body[b].rs = s;
@@ -235,6 +266,9 @@ BP_DEVNI void refresh_body(const EnvView& ev, const LayoutView& L, int b) {
     BBox bx; bx.l = l - rad; bx.b = bt - rad; bx.r = r + rad; bx.t = tp + rad;
     ev.bb[b] = bx;
 }
+BP_DEVNI void refresh_body(const EnvView& ev, const LayoutView& L, int b) { refresh_body_impl(ev, L, b); }
+// same, for callers that hold only the env block (batched hot path: only the touched arrays are addressed)
+BP_DEVNI void refresh_body_b(const DevConst* C, char* base, const LayoutView& L, int b) { refresh_body_impl(view_at(base, C->off), L, b); }
 // body position (pymunk Body.position = local origin in world space)
 BP_DEV V2 body_origin(const EnvView& ev, const LayoutView& L, int b) {
     double c = ev.body[b].rc, s = ev.body[b].rs;
@@ -387,7 +421,7 @@ BP_DEV Poly body_poly(const EnvView& ev, const LayoutView& L, int b) { Poly P; P
 BP_DEV V2 bb_centre(const BBox& r) { return mk((r.l + r.r) * 0.5, (r.b + r.t) * 0.5); }
 
 // Contact manifold (<= 2 points, world space) of bodies a, b from the closest-feature result.
-BP_DEVNI void make_manifold(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {
+BP_DEV void make_manifold_impl(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {
     Poly A = body_poly(ev, L, a), B = body_poly(ev, L, b);
     m->count = 0;
     double ra = L.rad[a], rb = L.rad[b];
@@ -419,6 +453,11 @@ BP_DEVNI void make_manifold(const EnvView& ev, const LayoutView& L, int a, int b
             }
         }
     }
+}
+
+BP_DEVNI void make_manifold(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) { make_manifold_impl(ev, L, a, b, pts, m); }
+BP_DEVNI void make_manifold_b(const DevConst* C, char* base, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {
+    make_manifold_impl(view_at(base, C->off), L, a, b, pts, m);
 }
 
 }  // namespace bp

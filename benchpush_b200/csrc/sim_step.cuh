@@ -162,7 +162,7 @@ BP_DEVNI void build_apairs(const EnvView& ev) {
 // Compaction between the stages keeps lanes on the same code path (GJK/EPA are long and divergent).
 
 // Not-touching outcome for pair p: slot bookkeeping + separation bound.
-BP_DEVNI void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, double gap) {
+BP_DEV void pair_apart_impl(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, double gap) {
     pr[p].flags |= 1;
     double g = gap * 0.999999 - 1e-9;
     pr[p].skip = ev.body[a].D + ev.body[b].D + g;
@@ -176,6 +176,12 @@ BP_DEVNI void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int
         bp_atomic_add(&sc->n_cached, 1);
         sc->dirty = 1;
     }
+}
+
+BP_DEVNI void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, double gap) { pair_apart_impl(ev, sc, pr, i, p, a, b, gap); }
+BP_DEVNI void pair_apart_b(const DevConst* C, char* base, int i, int p, int a, int b, double gap) {
+    EnvView ev = view_at(base, C->off);
+    pair_apart_impl(ev, ev.sc, ev.pair[ev.sc->cur], i, p, a, b, gap);
 }
 
 // Touching / not-touching outcome from a closest-feature result.  Warp-convergent (slot allocation).
@@ -544,6 +550,45 @@ BP_DEV void arb_solve(const EnvView& ev, const LayoutView& L, int s) {
     if (mb != 0.0 || ib != 0.0) { B.vx = vb.x; B.vy = vb.y; B.vw = wb; B.bx = bb.x; B.by = bb.y; B.bw = bwb; }
 }
 
+// Steps 3-6 of a substep for ONE env: prestep, velocity update, warm start, iterations.
+BP_DEVNI void solve_env(const EnvView& ev, const LayoutView& L, const SimParams& P, double dt, double prev_dt) {
+    EnvScal* sc = ev.sc;
+    const int lane = bp_lane();
+    // 3. prestep (uses the pre-damping velocities for the bounce term)
+    int no = sc->n_order;
+    for (int i = lane; i < no; i += BP_NL) arb_prestep(ev, L, P, ev.order[i]);
+    bp_wsync();
+    // 4. velocity update: v = v * damping^dt (gravity = 0, no forces); dynamic bodies only
+    int na = sc->n_awake;
+    for (int k = lane; k < na; k += BP_NL) {
+        int b = ev.awake[k];
+        if (body_dynamic(L, b)) {
+            BodyRec& R = ev.body[b];
+            R.vx = R.vx * P.damp + 0.0; R.vy = R.vy * P.damp + 0.0; R.vw = R.vw * P.damp + 0.0;
+        }
+    }
+    bp_wsync();
+    // 5. warm start + iterations, colour by colour (same-colour arbiters touch disjoint dynamic bodies)
+    double dt_coef = (prev_dt == 0.0) ? 0.0 : dt / prev_dt;
+    int nc = sc->n_colours;
+    for (int c = 0; c < nc; c++) {
+        int c0 = ev.col_start[c], c1 = ev.col_start[c + 1];
+        for (int i = c0 + lane; i < c1; i += BP_NL) arb_warm(ev, L, ev.order[i], dt_coef);
+        bp_wsync();
+    }
+    for (int it = 0; it < P.iterations; it++) {
+        for (int c = 0; c < nc; c++) {
+            int c0 = ev.col_start[c], c1 = ev.col_start[c + 1];
+            for (int i = c0 + lane; i < c1; i += BP_NL) arb_solve(ev, L, ev.order[i]);
+            bp_wsync();
+        }
+    }
+    // 6. arbiters solved this step are NORMAL next step
+    for (int i = lane; i < no; i += BP_NL) ev.slot[ev.order[i]].first = 0;
+    if (lane == 0) { sc->stat_substeps++; sc->stat_live_sum += no; sc->stat_awake_sum += na; }
+    bp_wsync();
+}
+
 // ------------------------------------------------------------------ one substep (cpSpaceStep)
 BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, double dt, double prev_dt) {
     EnvScal* sc = ev.sc;
@@ -588,40 +633,8 @@ BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P
     if (sc->n_cached > 0) expire_cached(ev, P, d);
     if (sc->dirty) build_order(ev, L, d);
     BP_TOCK(sc, 3, tk);
-    // 3. prestep (uses the pre-damping velocities for the bounce term)
-    int no = sc->n_order;
-    for (int i = lane; i < no; i += BP_NL) arb_prestep(ev, L, P, ev.order[i]);
-    bp_wsync();
-    // 4. velocity update: v = v * damping^dt (gravity = 0, no forces); dynamic bodies only
-    na = sc->n_awake;
-    for (int k = lane; k < na; k += BP_NL) {
-        int b = ev.awake[k];
-        if (body_dynamic(L, b)) {
-            BodyRec& R = ev.body[b];
-            R.vx = R.vx * P.damp + 0.0; R.vy = R.vy * P.damp + 0.0; R.vw = R.vw * P.damp + 0.0;
-        }
-    }
-    bp_wsync();
-    BP_TOCK(sc, 4, tk);
-    // 5. warm start + iterations, colour by colour (same-colour arbiters touch disjoint dynamic bodies)
-    double dt_coef = (prev_dt == 0.0) ? 0.0 : dt / prev_dt;
-    int nc = sc->n_colours;
-    for (int c = 0; c < nc; c++) {
-        int c0 = ev.col_start[c], c1 = ev.col_start[c + 1];
-        for (int i = c0 + lane; i < c1; i += BP_NL) arb_warm(ev, L, ev.order[i], dt_coef);
-        bp_wsync();
-    }
-    for (int it = 0; it < P.iterations; it++) {
-        for (int c = 0; c < nc; c++) {
-            int c0 = ev.col_start[c], c1 = ev.col_start[c + 1];
-            for (int i = c0 + lane; i < c1; i += BP_NL) arb_solve(ev, L, ev.order[i]);
-            bp_wsync();
-        }
-    }
-    // 6. arbiters solved this step are NORMAL next step
-    for (int i = lane; i < no; i += BP_NL) ev.slot[ev.order[i]].first = 0;
-    if (lane == 0) { sc->stat_substeps++; sc->stat_live_sum += no; sc->stat_awake_sum += na; }
-    bp_wsync();
+    // 3.-6. prestep, velocity update, warm start, iterations
+    solve_env(ev, L, P, dt, prev_dt);
     BP_TOCK(sc, 5, tk);
 }
 

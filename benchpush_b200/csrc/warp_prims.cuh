@@ -50,13 +50,19 @@ BP_DEV int bp_wscan_excl(int v, int* total) {
     *total = __shfl_sync(gm, x, BP_NL - 1, BP_NL);
     return x - v;
 }
+// group-relative ballot and indexed shuffle
+BP_DEV unsigned bp_wballot(bool pred) { return __ballot_sync(bp_gmask(), pred) >> bp_gshift(); }
+BP_DEV int bp_wshfl(int v, int src) { return __shfl_sync(bp_gmask(), v, src, BP_NL); }
 BP_DEV double bp_wmax(double v) {
     const unsigned gm = bp_gmask();
 #pragma unroll
     for (int o = BP_NL / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(gm, v, o, BP_NL));
     return v;
 }
-BP_DEV void bp_sincos(double a, double* s, double* c) { sincos(a, s, c); }
+// non-blocking hint: start moving the 128-byte line at p (and the following n_lines - 1) towards L1
+BP_DEV void bp_prefetch(const void* p, int n_lines) {
+    for (int i = 0; i < n_lines; i++) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p + 128 * i));
+}
 #else
 #include <math.h>
 #define BP_DEV static inline
@@ -68,21 +74,70 @@ BP_DEV bool bp_wany(bool p) { return p; }
 BP_DEV int bp_wbcast(int v) { return v; }
 BP_DEV int bp_wrank(bool pred, int* total) { *total = pred ? 1 : 0; return 0; }
 BP_DEV int bp_wscan_excl(int v, int* total) { *total = v; return 0; }
+BP_DEV unsigned bp_wballot(bool pred) { return pred ? 1u : 0u; }
+BP_DEV int bp_wshfl(int v, int src) { (void)src; return v; }
 BP_DEV double bp_wmax(double v) { return v; }
-BP_DEV void bp_sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
+BP_DEV void bp_prefetch(const void* p, int n_lines) { (void)p; (void)n_lines; }
 #ifndef __CUDACC__
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 #endif
 #endif
 
+#if defined(__CUDACC__) && !defined(BP_HOST_EMU)
+BP_DEV unsigned long long bp_d2bits(double x) { return (unsigned long long)__double_as_longlong(x); }
+BP_DEV double bp_bits2d(unsigned long long b) { return __longlong_as_double((long long)b); }
+#else
+BP_DEV unsigned long long bp_d2bits(double x) { unsigned long long b; __builtin_memcpy(&b, &x, 8); return b; }
+BP_DEV double bp_bits2d(unsigned long long b) { double x; __builtin_memcpy(&x, &b, 8); return x; }
+#endif
+// sin / cos of a body angle.  CUDA's sincos() and the host libm differ in the last bit now and then,
+// and the contact dynamics amplify one ulp into millimetres over an episode, so the kernels use their
+// own routine: argument reduction by pi/2 in three parts (Cody-Waite, constants of fdlibm's
+// e_rem_pio2.c, second iteration always taken) followed by fdlibm's k_sin.c / k_cos.c polynomials,
+// written with plain * + - only (the library is compiled with -fmad=false), hence bit-reproducible
+// on any IEEE-754 machine.  Error < 1 ulp for |a| < 2^20 * pi/2.
+BP_DEV void bp_sincos(double x, double* sn, double* cs) {
+    const double invpio2 = 6.36619772367581382433e-01;
+    const double pio2_1 = 1.57079632673412561417e+00, pio2_2 = 6.07710050630396597660e-11, pio2_2t = 2.02226624879595063154e-21;
+    double fn = rint(x * invpio2);
+    double t = x - fn * pio2_1;
+    double w = fn * pio2_2;
+    double r = t - w;
+    w = fn * pio2_2t - ((t - r) - w);
+    double y0 = r - w;
+    double y1 = (r - y0) - w;
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    double z = y0 * y0;
+    double v = z * y0;
+    double rs = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    double ks = y0 - ((z * (0.5 * y1 - v * rs) - y1) - v * S1);
+    double rc = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    double ax = fabs(y0), kc;
+    if (ax < 0.3) kc = 1.0 - (0.5 * z - (z * rc - y0 * y1));
+    else {
+        double qx = (ax > 0.78125) ? 0.28125 : bp_bits2d((bp_d2bits(ax) - 0x0020000000000000ull) & 0xFFFFFFFF00000000ull);
+        double hz = 0.5 * z - qx;
+        double a = 1.0 - qx;
+        kc = a - (hz - (z * rc - y0 * y1));
+    }
+    int n = (int)fn & 3;
+    *sn = (n == 0) ? ks : (n == 1) ? kc : (n == 2) ? -ks : -kc;
+    *cs = (n == 0) ? kc : (n == 1) ? -ks : (n == 2) ? -kc : ks;
+}
+
 // atomics (device) / plain ops (single-lane host emulation)
 #if defined(__CUDACC__) && !defined(BP_HOST_EMU)
 BP_DEV void bp_atomic_or(unsigned* p, unsigned v) { atomicOr(p, v); }
 BP_DEV void bp_atomic_and(unsigned* p, unsigned v) { atomicAnd(p, v); }
 BP_DEV int bp_atomic_add(int* p, int v) { return atomicAdd(p, v); }
+BP_DEV void bp_atomic_max_u64(unsigned long long* p, unsigned long long v) { atomicMax(p, v); }
 #else
 BP_DEV void bp_atomic_or(unsigned* p, unsigned v) { *p |= v; }
 BP_DEV void bp_atomic_and(unsigned* p, unsigned v) { *p &= v; }
 BP_DEV int bp_atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
+BP_DEV void bp_atomic_max_u64(unsigned long long* p, unsigned long long v) { if (v > *p) *p = v; }
 #endif

@@ -113,6 +113,11 @@ int bp_shipice_reset(bp_shipice_t* h, const int32_t* layout_ids, const uint8_t* 
 /* ShipIceEnv.step (ship_ice_env.py:261-355) for every env: actions[E] in [-1, 1]. */
 int bp_shipice_step(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out, void* stream);
 
+/* Same, for the envs with mask[e] != 0 only (mask NULL = all): the others keep their state and their
+ * previous outputs.  The reference has no counterpart (one env per process); batched callers use it
+ * to hold finished envs, or to de-synchronise episode phases. */
+int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t* mask, const bp_shipice_outputs* out, void* stream);
+
 /* Same call with HOST buffers (pageable or pinned): copies actions to the device, steps, copies
  * obs / reward / terminated / truncated (and the non-NULL info arrays) back, and synchronises. */
 int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out_host);

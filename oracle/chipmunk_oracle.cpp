@@ -215,8 +215,54 @@ struct Space {
     std::vector<int> order_y;
 };
 
+// Trigonometry.  Chipmunk calls libm (cpvforangle = cos/sin), and that is the default here.  libm
+// implementations differ in the last bit (glibc vs CUDA vs others) and the contact dynamics amplify
+// that over an episode, so for WHOLE-EPISODE comparisons the tests can switch the oracle to a
+// portable routine (cpo_set_portable_trig): Cody-Waite reduction by pi/2 + the fdlibm k_sin / k_cos
+// polynomials (published algorithm: FreeBSD msun e_rem_pio2.c medium path, k_sin.c, k_cos.c),
+// evaluated without fused multiply-add, which every IEEE-754 machine reproduces bit for bit.
+static int g_portable_trig = 0;
+static void portable_sincos(double x, double* sn, double* cs) {
+    static const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00,
+                        pio2_2 = 6.07710050630396597660e-11, pio2_2t = 2.02226624879595063154e-21;
+    static const double S[7] = {0, -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+    static const double Cc[7] = {0, 4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                 -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+    double fn = std::rint(x * invpio2);
+    double r0 = x - fn * pio2_1;
+    double w = fn * pio2_2;
+    double r = r0 - w;
+    w = fn * pio2_2t - ((r0 - r) - w);
+    double y = r - w, ytail = (r - y) - w;
+    double z = y * y, v = z * y;
+    double ps = S[2] + z * (S[3] + z * (S[4] + z * (S[5] + z * S[6])));
+    double ksin = y - ((z * (0.5 * ytail - v * ps) - ytail) - v * S[1]);
+    double pc = z * (Cc[1] + z * (Cc[2] + z * (Cc[3] + z * (Cc[4] + z * (Cc[5] + z * Cc[6])))));
+    double kcos, ay = std::fabs(y);
+    if (ay < 0.3) kcos = 1.0 - (0.5 * z - (z * pc - y * ytail));
+    else {
+        double qx;
+        if (ay > 0.78125) qx = 0.28125;
+        else { uint64_t bits; memcpy(&bits, &ay, 8); bits = (bits - 0x0020000000000000ull) & 0xFFFFFFFF00000000ull; memcpy(&qx, &bits, 8); }
+        double hz = 0.5 * z - qx, a = 1.0 - qx;
+        kcos = a - (hz - (z * pc - y * ytail));
+    }
+    switch ((int)fn & 3) {
+        case 0: *sn = ksin; *cs = kcos; break;
+        case 1: *sn = kcos; *cs = -ksin; break;
+        case 2: *sn = -ksin; *cs = -kcos; break;
+        default: *sn = -kcos; *cs = ksin; break;
+    }
+}
+static void trig(double a, double* sn, double* cs) {
+    if (g_portable_trig) portable_sincos(a, sn, cs);
+    else { *cs = std::cos(a); *sn = std::sin(a); }
+}
+
 static void set_transform(Body& b) {
-    cpFloat cs = std::cos(b.a), sn = std::sin(b.a);      // cpvforangle
+    cpFloat cs, sn;
+    trig(b.a, &sn, &cs);      // cpvforangle
     V c = b.cog;
     b.tr.a = cs; b.tr.b = sn; b.tr.c = -sn; b.tr.d = cs;
     b.tr.tx = b.p.x - (c.x * cs - c.y * sn);
@@ -702,6 +748,10 @@ static void space_step(Space* sp, cpFloat dt) {
 
 // ---------------------------------------------------------------- C API (ctypes)
 extern "C" {
+
+void cpo_set_portable_trig(int on) { g_portable_trig = on ? 1 : 0; }
+int cpo_get_portable_trig(void) { return g_portable_trig; }
+void cpo_sincos(double a, double* sn, double* cs) { trig(a, sn, cs); }
 
 void* cpo_space_new(void) {
     Space* sp = new Space();

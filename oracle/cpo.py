@@ -14,6 +14,23 @@ _LIB = None
 DYNAMIC, KINEMATIC, STATIC = 0, 1, 2
 
 
+def set_portable_trig(on):
+    """Process-wide switch: libm cos/sin (default, what Chipmunk calls) or the portable routine
+    (bit-reproducible everywhere; used for whole-episode comparisons).  See chipmunk_oracle.cpp."""
+    lib().cpo_set_portable_trig(1 if on else 0)
+
+
+def portable_trig():
+    return bool(lib().cpo_get_portable_trig())
+
+
+def sincos(a):
+    """(sin a, cos a) under the current trig mode."""
+    s, c = C.c_double(), C.c_double()
+    lib().cpo_sincos(C.c_double(float(a)), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
 def build(force=False):
     so = os.path.join(_HERE, "libbp_oracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("chipmunk_oracle.cpp", "spfa_oracle.cpp")]

@@ -165,7 +165,11 @@ class ShipIceOracleEnv:
         self.t += 1
         action = action * self.max_yaw_rate_step
         px, py, pa = self.ship_pose()
-        gv = R(pa) @ [self.target_speed, 0]
+        if cpo.portable_trig():
+            sn, cs = cpo.sincos(pa)          # same R(pa) @ [speed, 0], with the portable cos / sin
+            gv = [cs * self.target_speed + (-sn) * 0.0, sn * self.target_speed + cs * 0.0]
+        else:
+            gv = R(pa) @ [self.target_speed, 0]
         self.space.set_angular_velocity(self.ship_body, action)
         self.space.set_velocity(self.ship_body, gv[0], gv[1])
         flags = self.space.shipice_substeps(self.ship_body, self.steps, self.dt / self.steps,

@@ -28,6 +28,18 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
+@pytest.fixture
+def portable_trig():
+    """Switch the oracle to the portable cos / sin (the routine the kernels use) for one test: GPU, host
+    emulation and oracle are then bit-identical over whole episodes."""
+    from oracle import cpo
+    cpo.set_portable_trig(True)
+    try:
+        yield
+    finally:
+        cpo.set_portable_trig(False)
+
+
 FIXTURES = ["c10_t0", "c10_t7", "c30_t7", "c50_t0"]
 
 

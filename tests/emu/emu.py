@@ -53,6 +53,13 @@ class Emu:
     def step(self, env, action):
         self.L.emu_step(self.h, C.c_int(env), C.c_double(action))
 
+    def step_batch(self, env0, actions, auto_reset=False):
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        self.L.emu_step_batch(self.h, C.c_int(env0), a.ctypes.data_as(C.c_void_p), C.c_int(1 if auto_reset else 0))
+
+    def batch_size(self):
+        return int(self.L.emu_batch_size())
+
     def set_robot_velocity(self, env, vx, vy, w):
         self.L.emu_set_robot_velocity(self.h, C.c_int(env), C.c_double(vx), C.c_double(vy), C.c_double(w))
 

@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../benchpush_b200/csrc/host_tables.h"
 #include "../../benchpush_b200/csrc/shipice_env.cuh"
+#include "../../benchpush_b200/csrc/sim_batch.cuh"
 #include "../../benchpush_b200/csrc/raster.cuh"
 #include "../../benchpush_b200/csrc/spfa.cuh"
 
@@ -71,6 +72,15 @@ void emu_step(void* h, int env, double action) {
     EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
     shipice_step_env(ev, e->T, e->P, e->d, action, env, e->out);
 }
+// the batched path (sim_batch.cuh): envs [env0, env0 + BK) advance together; actions[n_envs]
+void emu_step_batch(void* h, int env0, const float* actions, int auto_reset) {
+    Emu* e = (Emu*)h;
+    static DevConst C;
+    C.d = e->d; C.P = e->P; C.off = env_offsets(e->d); C.T = e->T;
+    static BatchShared S;
+    shipice_step_batch(&C, S, e->mem.data(), e->env_bytes, env0, actions, nullptr, e->out, auto_reset);
+}
+int emu_batch_size() { return BK; }
 // one raw physics substep (for per-substep parity); robot velocity set explicitly
 void emu_set_robot_velocity(void* h, int env, double vx, double vy, double w) {
     Emu* e = (Emu*)h;

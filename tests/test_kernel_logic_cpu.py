@@ -11,7 +11,7 @@ from tests.emu.emu import Emu
 
 
 @pytest.mark.parametrize("name", ["c10_t7", "c30_t7", "c50_t0"])
-def test_emulated_kernels_match_oracle_bitwise(name, golden_layouts, pins):
+def test_emulated_kernels_match_oracle_bitwise(name, golden_layouts, pins, portable_trig):
     p = golden_layouts[name]
     emu = Emu(1, p, SHIP_VERTS)
     env = ShipIceOracleEnv({"concentration": fixture_conc(name)}, experiment=unpack_trials(p), order_mode=1)
@@ -31,6 +31,56 @@ def test_emulated_kernels_match_oracle_bitwise(name, golden_layouts, pins):
         np.testing.assert_allclose(out["total_work"], info["total_work"], rtol=1e-9, atol=1e-9)
         assert (out["sx"], out["sy"], out["sa"]) == tuple(float(x) for x in info["state"])
         assert np.array_equal(obs, emu.render_obs(0, False))
+
+
+def test_emulated_kernels_vs_libm_oracle(golden_layouts, pins):
+    """Against the oracle in its default mode (libm cos/sin, what Chipmunk calls) the only difference
+    is the last bit of cos/sin: 1e-9 over a few env steps."""
+    name = "c30_t7"
+    p = golden_layouts[name]
+    emu = Emu(1, p, SHIP_VERTS)
+    env = ShipIceOracleEnv({"concentration": fixture_conc(name)}, experiment=unpack_trials(p), order_mode=1)
+    env.reset(); emu.reset(0, 0)
+    for a in pins["%s_o1_actions" % name][:4]:
+        env.step(float(a)); emu.step(0, float(a))
+        np.testing.assert_allclose(env.space.state(), emu.bodies(0, 0), rtol=0, atol=1e-9)
+
+
+def test_portable_trig_accuracy():
+    """The kernels' cos/sin (restated in the oracle) against libm: <= 1 ulp on the angles a ship or floe can reach."""
+    import math
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-40, 40, 20000), rng.uniform(-1e-3, 1e-3, 1000), np.array([0.0, math.pi / 2, math.pi, -math.pi / 2, 1e-300, 0.78125, 0.3])])
+    cpo.set_portable_trig(True)
+    try:
+        got = np.array([cpo.sincos(x) for x in xs])
+    finally:
+        cpo.set_portable_trig(False)
+    ref = np.stack([np.sin(xs), np.cos(xs)], axis=1)
+    ulp = np.abs(got - ref) / np.spacing(np.abs(ref))
+    assert ulp.max() <= 1.0, ulp.max()
+    assert cpo.sincos(0.5) == (math.sin(0.5), math.cos(0.5))      # default mode is libm
+
+
+def test_batched_path_equals_one_env_per_warp_path():
+    """sim_batch.cuh (a warp advances 8 envs together) against sim_step.cuh (one env per warp): bit-identical."""
+    nl = 3
+    packed = pack_trials(generate_experiment(nl, 0.5, seed=11))
+    E = 10
+    kw = dict(pmax=8 * (packed.max_floes + 1), lmax=2 * (packed.max_floes + 1))
+    A, B = Emu(E, packed, SHIP_VERTS, **kw), Emu(E, packed, SHIP_VERTS, **kw)
+    for e in range(E):
+        A.reset(e, e % nl); B.reset(e, e % nl)
+    rng = np.random.default_rng(0)
+    for k in range(8):
+        acts = rng.uniform(-1, 1, E).astype(np.float32)
+        for e in range(E):
+            A.step(e, float(acts[e]))
+        for e0 in range(0, E, B.batch_size()):
+            B.step_batch(e0, acts)
+        for e in range(E):
+            assert np.array_equal(A.bodies(e, e % nl), B.bodies(e, e % nl))
+            assert A.out(e) == B.out(e)
 
 
 def test_awake_set_is_small_and_exact(golden_layouts):
