@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total envs over all ranks (default: the metric's 65536)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--desync", type=int, default=34,
+                    help="spread the episode phases before the warm-up: env e is advanced (global id mod DESYNC) steps (1 = all envs start at reset)")
     return ap.parse_args()
 
 
@@ -201,10 +203,16 @@ def run_ours(a):
     alg_bytes_per_env = float(np.mean(56.0 * n_floes + 8.0 * sum_v + 90036.0))
 
     obs, info = env.reset()
-    metric = ShipIceMetric("random", ship_mass=env.cfg.ship.mass, goal=env.goal)
-    metric.reset(info)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
+    # steady state: an episode lasts >= 34 steps and its cost grows as the ship enters the ice, so the envs are
+    # first spread over the episode phases (untimed): env with global id g takes (g mod DESYNC) steps
+    if a.desync > 1:
+        phase = torch.arange(lo, hi, device=dev) % a.desync
+        for r in range(a.desync - 1):
+            act = (torch.rand(E, generator=gen, device=dev) * 2 - 1).float()
+            env.step_async_nocheck(act, mask=(phase > r))
+        torch.cuda.synchronize()
     total = a.warmup + a.steps
     actions = [(torch.rand(E, generator=gen, device=dev) * 2 - 1).float() for _ in range(total)]
     resets_in_step = torch.zeros(total + 1, dtype=torch.int64, device=dev)
@@ -246,12 +254,20 @@ def run_ours(a):
 
     # ---- end to end through the public host-buffer API: actions H2D (pinned) + results D2H every step
     h_actions = [torch.empty(E, dtype=torch.float32).pin_memory().copy_(actions[k].cpu()) for k in range(a.warmup, total)]
-    env.step_host(h_actions[0].numpy())                                       # allocate host staging outside the timed region
+    hb = env.step_host(h_actions[0].numpy())                                  # allocate host staging outside the timed region
+    # episode scoring (ShipIceMetric) runs on the host results, inside the end-to-end region, as evaluate() does
+    def host_info(hb):
+        return {"state": torch.from_numpy(hb["state"]), "total_work": torch.from_numpy(hb["total_work"]),
+                "trial_success": torch.from_numpy(hb["trial_success"]).bool()}
+    metric = ShipIceMetric("random", ship_mass=env.cfg.ship.mass, goal=env.goal)
+    metric.reset(host_info(hb))
     barrier()
     t0 = time.perf_counter()
     e2e_resets = 0
     for k in range(a.steps):
         hb = env.step_host(h_actions[k].numpy())
+        term = torch.from_numpy(hb["terminated"]).bool()
+        metric.update(host_info(hb), torch.from_numpy(hb["reward"]), term)
         e2e_resets += int(hb["terminated"].sum())
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
@@ -301,6 +317,7 @@ def run_ours(a):
                                    "4x150x150 u8 obs, U(-1,1) actions, next-step auto reset" % (a.envs, E),
                        "layouts": "%d synthetic seeded ice fields (benchpush_b200.layouts.generate_ice_field, seed 99), mean %.0f floes" % (N_LAYOUTS, float(n_floes.mean())),
                        "l2": "inputs_exceed_l2 (per-env state %.2f MB x %d envs per GPU)" % (env.env_bytes() / 1e6, E),
+                       "episode_phase": "steady state: env g advanced (g mod %d) steps before the warm-up, auto reset inside the timed region" % a.desync if a.desync > 1 else "all envs start at reset",
                        "env_steps_timed": int(tsum[2]), "resets_timed": n_resets, "env_status_bits": int(tmax[7])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_shipice_step", "kernel_ms": step_ms_avg, "obs_kernel_ms": km["obs_ms"] / max(km["obs_launches"], 1),

@@ -44,6 +44,15 @@ BP_DEVNI void area_centroid_abs(const double* wv, int n, double* area, double* c
 
 BP_DEV double round2(double x) { return rint(x * 100.0) / 100.0; }
 
+// True when a substep can change nothing: the ship is the only awake body and does not move, and
+// no arbiter is touching or cached (so no stamp-based expiry is pending either).
+BP_DEV bool settle_is_idle(const EnvView& ev, const EnvScal* sc) {
+    if (sc->n_awake != 1 || sc->n_order != 0 || sc->n_cached != 0 || sc->dirty || sc->rebuild) return false;
+    if (ev.awake[0] != sc->robot) return false;
+    const BodyRec& R = ev.body[sc->robot];
+    return R.vx == 0.0 && R.vy == 0.0 && R.vw == 0.0 && R.bx == 0.0 && R.by == 0.0 && R.bw == 0.0;
+}
+
 BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, int layout_id, int env, const StepOut& out) {
     LayoutView L = layout_view(T, d, layout_id);
     EnvScal* sc = ev.sc;
@@ -55,6 +64,14 @@ BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const Sim
         substep(ev, L, P, d, P.dt, prev_dt);
         prev_dt = P.dt;
         if (k == 0 || (k & 127) == 127) sleep_pass(ev, L, d);
+        // Everything asleep, the ship at rest, no arbiter alive or cached: every remaining settle
+        // substep is exactly a no-op (nothing integrates, nothing is evaluated or solved), only the
+        // step counter advances — skip them.
+        if (settle_is_idle(ev, sc)) {
+            if (lane == 0) sc->stamp += P.settle_steps - 1 - k;
+            bp_wsync();
+            break;
+        }
     }
     sleep_pass(ev, L, d);
     // prev_obs = get_obs_from_poly(polygons) (ship_ice_env.py:220): cache |centroid| and area per floe

@@ -166,17 +166,23 @@ class ShipIceVecEnv:
         self._raise_on_status()
         return self.obs, self._info(reset=True)
 
-    def step(self, action):
+    def step(self, action, mask: Optional[torch.Tensor] = None):
+        """``mask`` (bool/uint8 [E], optional): step only the envs with mask set; the others keep their
+        state and their previous outputs (no counterpart in the single-env reference)."""
         with torch.cuda.device(self.device):
             a = torch.as_tensor(action, dtype=torch.float32, device=self.device).reshape(self.num_envs)
             self._actions.copy_(a)
-            _lib.check(self._L.bp_shipice_step(self._h, C.c_void_p(self._actions.data_ptr()), C.byref(self._out), self._stream()))
+            self.step_async_nocheck(self._actions, mask)
         self._raise_on_status()
         return self.obs, self._reward, self._terminated.bool(), self._truncated.bool(), self._info(reset=False)
 
-    def step_async_nocheck(self, action_dev: torch.Tensor):
+    def step_async_nocheck(self, action_dev: torch.Tensor, mask: Optional[torch.Tensor] = None):
         """Enqueue one step without any host synchronisation (actions already on the device)."""
-        _lib.check(self._L.bp_shipice_step(self._h, C.c_void_p(action_dev.data_ptr()), C.byref(self._out), self._stream()))
+        mptr = None
+        if mask is not None:
+            self._mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()      # kept alive until the next call
+            mptr = C.c_void_p(self._mask.data_ptr())
+        _lib.check(self._L.bp_shipice_step_masked(self._h, C.c_void_p(action_dev.data_ptr()), mptr, C.byref(self._out), self._stream()))
 
     def step_host(self, actions: np.ndarray, want_obs: bool = False):
         """The same step through host buffers (numpy in, numpy out; copies inside)."""

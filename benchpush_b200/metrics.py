@@ -100,6 +100,8 @@ class ShipIceMetric(BaseMetric):
         if dist.is_available() and dist.is_initialized():
             if dist.get_backend() == "gloo":
                 t = t.cpu()
+            elif not t.is_cuda:
+                t = t.cuda()                      # NCCL reduces device tensors (scores kept on the host)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         n = max(float(t[0]), 1.0)
         return {"episodes": int(t[0]), "success_rate": float(t[1]) / n, "efficiency_mean": float(t[2]) / n,
