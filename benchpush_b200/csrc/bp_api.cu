@@ -36,7 +36,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 struct StepArgs {
     char* mem; size_t env_bytes; Dims d; SimParams P; LayoutTab T; StepOut out;
     const float* actions; const int32_t* layout_ids; const uint8_t* mask; int* counter; int auto_reset;
-    const DevConst* C;
+    const DevConst* C; int use_snap;
 };
 
 // Claim the next batch of environments for this warp: one per lane group.  Returns false when the
@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_reset(StepArgs a
         if (env < a.d.n_envs && !(a.mask && !a.mask[env])) {
             EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
             int layout = a.layout_ids[env] % a.d.n_layouts;
-            shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
+            if (a.use_snap) shipice_reset_from_snapshot(a.C, a.mem + a.env_bytes * (size_t)env, layout, env, a.out);
+            else shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
             if (bp_lane() == 0) { ev.sc->first_layout = layout; ev.sc->episode = 0; ev.sc->done = 0; ev.sc->obs_raw = 1; }
             bp_wsync();
         }
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepAr
                 // ship_ice_env.py:188); this call returns the reset observation with reward 0.
                 int ep = ev.sc->episode + 1, first = ev.sc->first_layout;
                 int layout = (first + ep) % a.d.n_layouts;
-                shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
+                if (a.use_snap) shipice_reset_from_snapshot(a.C, a.mem + a.env_bytes * (size_t)env, layout, env, a.out);
+                else shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
                 if (bp_lane() == 0) { ev.sc->first_layout = first; ev.sc->episode = ep; ev.sc->done = 0; ev.sc->obs_raw = 1; }
             } else {
                 shipice_step_env(ev, a.T, a.P, a.d, (double)a.actions[env], env, a.out);
@@ -152,6 +154,7 @@ struct bp_shipice {
     char* mem = nullptr; size_t env_bytes = 0;
     int* counter = nullptr;
     DevConst* d_const = nullptr;   // Dims, SimParams, array offsets, layout tables (device copy)
+    char* snap = nullptr;          // post-reset env block of every layout (reset = copy)
     bool warp_impl = false;        // BP_STEP_IMPL=warp: one env per warp (A/B measurements)
     StepOut out;               // internal device outputs
     int32_t* d_layout_ids = nullptr;
@@ -295,9 +298,40 @@ int bp_shipice_load_layouts(bp_shipice_t* h, int32_t n_layouts, const int32_t* n
     h->d.n_layouts = n_layouts;
     DevConst hc;
     hc.d = h->d; hc.P = h->P; hc.off = env_offsets(h->d); hc.T = h->T;
+    hc.snap = nullptr; hc.env_bytes = h->env_bytes; hc.snap_pose = nullptr; hc.snap_status = nullptr;
     CUDA_TRY(cudaMalloc((void**)&h->d_const, sizeof(DevConst)));
     h->dev_allocs.push_back(h->d_const);
     CUDA_TRY(cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice));
+    // reset snapshots: simulate the reset of every layout once (init + settle), keep the env blocks
+    if (!getenv("BP_NO_SNAPSHOT")) {
+        size_t Ls = (size_t)n_layouts;
+        CUDA_TRY(cudaMalloc((void**)&h->snap, h->env_bytes * Ls));
+        h->dev_allocs.push_back(h->snap);
+        CUDA_TRY(cudaMemset(h->snap, 0, h->env_bytes * Ls));
+        StepOut so; void* p = nullptr;
+        auto T = [&](size_t bytes) -> void* { p = nullptr; if (cudaMalloc(&p, bytes) == cudaSuccess) { cudaMemset(p, 0, bytes); h->dev_allocs.push_back(p); } return p; };
+        so.reward = (double*)T(Ls * 8); so.terminated = (unsigned char*)T(Ls); so.truncated = (unsigned char*)T(Ls);
+        so.state = (double*)T(Ls * 24); so.pose = (double*)T(Ls * 24); so.total_work = (double*)T(Ls * 8);
+        so.collision_reward = (double*)T(Ls * 8); so.scaled_collision_reward = (double*)T(Ls * 8); so.dist_reward = (double*)T(Ls * 8);
+        so.trial_success = (unsigned char*)T(Ls); so.status = (int*)T(Ls * 4);
+        int32_t* ids = (int32_t*)T(Ls * 4);
+        if (!so.reward || !so.terminated || !so.truncated || !so.state || !so.pose || !so.total_work || !so.collision_reward ||
+            !so.scaled_collision_reward || !so.dist_reward || !so.trial_success || !so.status || !ids)
+            return fail(BP_ERR_CUDA, "cudaMalloc of the reset snapshots failed");
+        std::vector<int32_t> hid(Ls);
+        for (size_t i = 0; i < Ls; i++) hid[i] = (int32_t)i;
+        CUDA_TRY(cudaMemcpy(ids, hid.data(), Ls * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemset(h->counter, 0, 4));
+        StepArgs a;
+        a.mem = h->snap; a.env_bytes = h->env_bytes; a.d = h->d; a.d.n_envs = n_layouts; a.P = h->P; a.T = h->T; a.out = so;
+        a.actions = nullptr; a.layout_ids = ids; a.mask = nullptr; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const; a.use_snap = 0;
+        int blocks = (n_layouts + 3) / 4; if (blocks > h->sm_count * BP_MIN_BLOCKS) blocks = h->sm_count * BP_MIN_BLOCKS;
+        k_shipice_reset<<<blocks, 128>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        hc.snap = h->snap; hc.snap_pose = so.pose; hc.snap_status = so.status;
+        CUDA_TRY(cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice));
+    }
     if (const char* e = getenv("BP_STEP_IMPL")) h->warp_impl = (strcmp(e, "warp") == 0);
     h->layouts_loaded = true;
     return BP_OK;
@@ -368,7 +402,7 @@ int bp_shipice_reset(bp_shipice_t* h, const int32_t* layout_ids, const uint8_t* 
     CUDA_TRY(cudaMemsetAsync(h->counter, 0, 4, st));
     StepArgs a;
     a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
-    a.actions = nullptr; a.layout_ids = layout_ids; a.mask = mask; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const;
+    a.actions = nullptr; a.layout_ids = layout_ids; a.mask = mask; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const; a.use_snap = h->snap ? 1 : 0;
     k_shipice_reset<<<sim_grid(h), 128, 0, st>>>(a);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -386,7 +420,7 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
     CUDA_TRY(cudaMemsetAsync(h->counter, 0, 4, st));
     StepArgs a;
     a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
-    a.actions = actions; a.layout_ids = nullptr; a.mask = mask; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset; a.C = h->d_const;
+    a.actions = actions; a.layout_ids = nullptr; a.mask = mask; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset; a.C = h->d_const; a.use_snap = h->snap ? 1 : 0;
     prof_begin(h, 0, st);
     if (h->warp_impl) k_shipice_step_warp<<<sim_grid(h), 128, 0, st>>>(a);
     else k_shipice_step<<<batch_grid(h), 128, 0, st>>>(a);

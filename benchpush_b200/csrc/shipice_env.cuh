@@ -93,6 +93,27 @@ BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const Sim
     bp_wsync();
 }
 
+// ShipIceEnv.reset through the per-layout snapshot (DevConst::snap): identical to shipice_reset_env
+// because the post-reset state is a pure function of the layout.
+BP_DEVNI void shipice_reset_from_snapshot(const DevConst* C, char* base, int layout_id, int env, const StepOut& out) {
+    const int lane = bp_lane();
+    struct alignas(16) V16 { unsigned long long a, b; };      // 128-bit loads / stores
+    const V16* src = (const V16*)(C->snap + C->env_bytes * (size_t)layout_id);
+    V16* dst = (V16*)base;
+    const size_t n = C->env_bytes / sizeof(V16);
+#pragma unroll 4
+    for (size_t i = lane; i < n; i += BP_NL) dst[i] = src[i];
+    if (lane == 0) {
+        const double* p = C->snap_pose + 3 * layout_id;
+        out.pose[3 * env] = p[0]; out.pose[3 * env + 1] = p[1]; out.pose[3 * env + 2] = p[2];
+        out.state[3 * env] = round2(p[0]); out.state[3 * env + 1] = round2(p[1]); out.state[3 * env + 2] = round2(p[2]);
+        out.total_work[env] = 0.0; out.reward[env] = 0.0; out.terminated[env] = 0; out.truncated[env] = 0;
+        out.collision_reward[env] = 0.0; out.scaled_collision_reward[env] = 0.0; out.dist_reward[env] = 0.0;
+        out.trial_success[env] = 0; out.status[env] = C->snap_status[layout_id];
+    }
+    bp_wsync();
+}
+
 // ship_ice_env.py:263-274: yaw rate from the action, constant surge along the heading at step start
 BP_DEVNI void shipice_step_begin(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, double action) {
     EnvScal* sc = ev.sc;

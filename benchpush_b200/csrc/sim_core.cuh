@@ -215,7 +215,14 @@ struct LayoutView {
 };
 // Everything a kernel needs that is constant for a handle; lives in device memory (one copy per
 // handle) so that out-of-line device functions can take it as ONE pointer.
-struct DevConst { Dims d; SimParams P; EnvOff off; LayoutTab T; };
+struct DevConst {
+    Dims d; SimParams P; EnvOff off; LayoutTab T;
+    // reset snapshots: the env block right after reset depends on the layout only, so it is simulated
+    // once per layout (init + settle substeps) and a reset is a copy of that block.  nullptr = none.
+    const char* snap; size_t env_bytes;
+    const double* snap_pose;      // [L][3] ship pose after reset
+    const int* snap_status;       // [L]
+};
 BP_DEV LayoutView layout_view(const LayoutTab& T, const Dims& d, int l) {
     LayoutView L;
     size_t o = (size_t)l * d.NB;

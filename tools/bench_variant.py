@@ -7,11 +7,17 @@ import numpy as np, torch
 from benchpush_b200.envs import ShipIceVecEnv
 from benchpush_b200.layouts import generate_experiment, pack_trials
 E = int(sys.argv[1]); conc = float(sys.argv[2]); warm = int(sys.argv[3]); steps = int(sys.argv[4])
+desync = int(sys.argv[5]) if len(sys.argv) > 5 else 1      # > 1: spread the episode phases first (steady state, like bench.py)
 packed = pack_trials(generate_experiment(32, conc, seed=99))
 env = ShipIceVecEnv(num_envs=E, cfg={"concentration": conc}, layouts=packed, device=0, auto_reset=True)
 env.check_status = False
 env.reset()
 g = torch.Generator(device="cuda"); g.manual_seed(0)
+if desync > 1:
+    phase = torch.arange(E, device="cuda") % desync
+    for r in range(desync - 1):
+        env.step_async_nocheck(torch.rand(E, generator=g, device="cuda") * 2 - 1, mask=(phase > r))
+    torch.cuda.synchronize()
 acts = [(torch.rand(E, generator=g, device="cuda") * 2 - 1) for _ in range(warm + steps)]
 for k in range(warm):
     env.step_async_nocheck(acts[k])
