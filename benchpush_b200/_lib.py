@@ -39,6 +39,22 @@ class ShipIceOutputs(C.Structure):
         "scaled_collision_reward", "dist_reward", "trial_success", "status")]
 
 
+class MazeConfig(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("max_boxes", C.c_int32), ("device", C.c_int32), ("auto_reset", C.c_int32),
+        ("dt", C.c_double), ("steps", C.c_int32), ("iterations", C.c_int32), ("damping", C.c_double),
+        ("obstacle_density", C.c_double), ("obstacle_size", C.c_double), ("target_speed", C.c_double),
+        ("width", C.c_double), ("length", C.c_double), ("goal_x", C.c_double), ("goal_y", C.c_double),
+        ("goal_radius", C.c_double), ("min_r", C.c_double), ("m_to_pix_scale", C.c_int32), ("settle_steps", C.c_int32),
+        ("start", C.c_double * 3), ("n_walls", C.c_int32), ("walls", C.c_double * 64),
+        ("n_robot_verts", C.c_int32), ("robot_verts", C.c_double * 64),
+        ("n_wheels", C.c_int32), ("wheel_nv", C.c_int32 * 8), ("wheel_verts", C.c_double * 128),
+    ]
+
+
+MAZE_OBS_SHAPE = (4, 192, 192)
+
+
 def build(verbose: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     res = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
@@ -81,6 +97,18 @@ def lib():
         L.bp_shipice_env_bytes.restype = C.c_size_t
         L.bp_shipice_launch_count.argtypes = [C.c_void_p]
         L.bp_shipice_launch_count.restype = C.c_int64
+        L.bp_maze_default_config.argtypes = [C.POINTER(MazeConfig), C.c_int32]
+        L.bp_maze_default_config.restype = None
+        L.bp_maze_create.argtypes = [C.POINTER(MazeConfig), C.POINTER(C.c_void_p)]
+        L.bp_maze_destroy.argtypes = [C.c_void_p]
+        L.bp_maze_load_layouts.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.bp_maze_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
+        L.bp_maze_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
+        L.bp_maze_step_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
+        L.bp_maze_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs)]
+        L.bp_maze_get_obstacles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.bp_maze_get_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.bp_maze_get_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bp_spfa_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bp_spfa_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         _LIB = L
@@ -93,6 +121,8 @@ EXPORTS = [
     "bp_shipice_get_obstacles", "bp_shipice_get_bodies", "bp_shipice_get_counters", "bp_shipice_env_bytes",
     "bp_shipice_set_profiling", "bp_shipice_get_kernel_ms",
     "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host",
+    "bp_maze_default_config", "bp_maze_create", "bp_maze_destroy", "bp_maze_load_layouts", "bp_maze_reset", "bp_maze_step",
+    "bp_maze_step_masked", "bp_maze_step_host", "bp_maze_get_obstacles", "bp_maze_get_bodies", "bp_maze_get_maps",
 ]
 
 

@@ -11,7 +11,7 @@
 #include "../../include/benchpush_b200.h"
 #include "host_tables.h"
 #include "raster.cuh"
-#include "shipice_env.cuh"
+#include "maze_raster.cuh"
 #include "sim_batch.cuh"
 #include "spfa.cuh"
 
@@ -127,6 +127,34 @@ __global__ void __launch_bounds__(256) k_shipice_obs(ObsArgs a) {
     }
 }
 
+struct MazeObsArgs {
+    char* mem; size_t env_bytes; Dims d; LayoutTab T; MazeObsParams O;
+    const double* rawv; const int* rawn; const uint8_t* mask; uint8_t* obs;
+};
+
+// maze-NAMO observation: one block per env, the 288x288 crop lives in (dynamic) shared memory
+__global__ void __launch_bounds__(256) k_maze_obs(MazeObsArgs a) {
+    extern __shared__ __align__(16) unsigned char mz_smem_raw[];
+    MazeObsSmem& S = *reinterpret_cast<MazeObsSmem*>(mz_smem_raw);
+    int env = blockIdx.x;
+    if (a.mask && !a.mask[env]) return;
+    EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
+    const EnvScal* sc = ev.sc;
+    LayoutView L = layout_view(a.T, a.d, sc->layout);
+    int r = sc->robot;
+    V2 o = body_origin(ev, L, r);
+    uint8_t* out = a.obs + (size_t)env * MZ_OBS_C * MZ_PIX;
+    int first = 0;                                                   // bodies [n_walls, robot0) are the movable obstacles
+    while (first < L.robot0 && L.nv[first] == 2) first++;            // skip the wall segments
+    int n_obst = L.robot0 - first;
+    if (sc->obs_raw) {
+        size_t base = (size_t)sc->layout * a.d.NB + first;
+        render_maze_obs(S, a.O, n_obst, a.rawv + base * VMAX * 2, VMAX * 2, a.rawn + base, o.x, o.y, ev.body[r].pa, out);
+    } else {
+        render_maze_obs(S, a.O, n_obst, ev.wv + (size_t)first * VMAX * 2, VMAX * 2, L.nv + first, o.x, o.y, ev.body[r].pa, out);
+    }
+}
+
 __global__ void __launch_bounds__(512) k_spfa(const uint8_t* maps, const int32_t* sources, int batch, int H, int W,
                                                float* dists, int32_t* parents, int* scratch, int* counter) {
     __shared__ SpfaShared S;
@@ -147,6 +175,10 @@ __global__ void __launch_bounds__(512) k_spfa(const uint8_t* maps, const int32_t
 struct bp_shipice {
     bp_shipice_config cfg;
     Dims d; SimParams P; ObsParams O;
+    int kind = KIND_SHIPICE;       // KIND_MAZE: created by bp_maze_create
+    bp_maze_config mcfg; MazeConfig mz; MazeObsParams MO;
+    std::vector<uint8_t> wall_map; std::vector<double> dist_norm, dist_raw;   // maze: host copies of the constant maps
+    int max_boxes = 0;
     HostLayouts H;
     LayoutTab T;               // device pointers
     std::vector<void*> dev_allocs;
@@ -267,16 +299,7 @@ int bp_shipice_destroy(bp_shipice_t* h) {
     return BP_OK;
 }
 
-int bp_shipice_load_layouts(bp_shipice_t* h, int32_t n_layouts, const int32_t* n_floes, const int32_t* n_verts,
-                            const double* verts, const double* centres, const double* ship_state) {
-    if (!h || n_layouts <= 0 || !n_floes || !n_verts || !verts || !centres || !ship_state) return fail(BP_ERR_INVALID, "null / empty layout arguments");
-    if (h->layouts_loaded) return fail(BP_ERR_STATE, "layouts already loaded for this handle");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    ShipIceMaterial mat;
-    mat.density = h->cfg.obstacle_density;
-    std::string err = build_shipice_layouts(h->H, n_layouts, h->cfg.max_floes, n_floes, n_verts, verts, centres, ship_state,
-                                            h->cfg.ship_verts, h->cfg.n_ship_verts, mat);
-    if (!err.empty()) return fail(BP_ERR_INVALID, err);
+static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
     HostLayouts& H = h->H;
     int rc;
     if ((rc = dev_upload(h, H.lv, &h->T.lv))) return rc;
@@ -291,6 +314,7 @@ int bp_shipice_load_layouts(bp_shipice_t* h, int32_t n_layouts, const int32_t* n
     if ((rc = dev_upload(h, H.mat_u, &h->T.mat_u))) return rc;
     if ((rc = dev_upload(h, H.init, &h->T.init))) return rc;
     if ((rc = dev_upload(h, H.nbody, &h->T.nbody))) return rc;
+    if ((rc = dev_upload(h, H.robot0, &h->T.robot0))) return rc;
     const double* p; const int* q;
     if ((rc = dev_upload(h, H.rawv, &p))) return rc; h->d_rawv = (double*)p;
     if ((rc = dev_upload(h, H.rawcen, &p))) return rc; h->d_rawcen = (double*)p;
@@ -337,6 +361,19 @@ int bp_shipice_load_layouts(bp_shipice_t* h, int32_t n_layouts, const int32_t* n
     return BP_OK;
 }
 
+int bp_shipice_load_layouts(bp_shipice_t* h, int32_t n_layouts, const int32_t* n_floes, const int32_t* n_verts,
+                            const double* verts, const double* centres, const double* ship_state) {
+    if (!h || n_layouts <= 0 || !n_floes || !n_verts || !verts || !centres || !ship_state) return fail(BP_ERR_INVALID, "null / empty layout arguments");
+    if (h->layouts_loaded) return fail(BP_ERR_STATE, "layouts already loaded for this handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    ShipIceMaterial mat;
+    mat.density = h->cfg.obstacle_density;
+    std::string err = build_shipice_layouts(h->H, n_layouts, h->cfg.max_floes, n_floes, n_verts, verts, centres, ship_state,
+                                            h->cfg.ship_verts, h->cfg.n_ship_verts, mat);
+    if (!err.empty()) return fail(BP_ERR_INVALID, err);
+    return finish_load_layouts(h, n_layouts);
+}
+
 static int copy_outputs(bp_shipice* h, const bp_shipice_outputs* o, cudaStream_t st, cudaMemcpyKind kind) {
     size_t E = h->d.n_envs;
     if (!o) return BP_OK;
@@ -365,6 +402,17 @@ static void prof_end(bp_shipice* h, cudaStream_t st) {
 
 static int launch_obs(bp_shipice* h, uint8_t* obs, const uint8_t* mask, cudaStream_t st) {
     if (!obs) return BP_OK;
+    if (h->kind == KIND_MAZE) {
+        MazeObsArgs ma;
+        ma.mem = h->mem; ma.env_bytes = h->env_bytes; ma.d = h->d; ma.T = h->T; ma.O = h->MO;
+        ma.rawv = h->d_rawv; ma.rawn = h->d_rawn; ma.mask = mask; ma.obs = obs;
+        prof_begin(h, 1, st);
+        k_maze_obs<<<h->d.n_envs, 256, sizeof(MazeObsSmem), st>>>(ma);
+        prof_end(h, st);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return BP_OK;
+    }
     ObsArgs oa;
     oa.mem = h->mem; oa.env_bytes = h->env_bytes; oa.d = h->d; oa.T = h->T; oa.O = h->O;
     oa.rawv = h->d_rawv; oa.rawn = h->d_rawn; oa.rawcen = h->d_rawcen; oa.mask = mask; oa.obs = obs;
@@ -441,14 +489,15 @@ int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     size_t E = h->d.n_envs;
     if (!h->d_actions) CUDA_TRY(cudaMalloc((void**)&h->d_actions, E * 4));
-    if (oh->obs && !h->d_obs) CUDA_TRY(cudaMalloc((void**)&h->d_obs, E * BP_OBS_C * OBS_PIX));
+    const size_t obs_bytes = h->kind == KIND_MAZE ? (size_t)MZ_OBS_C * MZ_PIX : (size_t)BP_OBS_C * OBS_PIX;
+    if (oh->obs && !h->d_obs) CUDA_TRY(cudaMalloc((void**)&h->d_obs, E * obs_bytes));
     CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions, E * 4, cudaMemcpyHostToDevice, 0));
     bp_shipice_outputs dev;
     memset(&dev, 0, sizeof(dev));
     dev.obs = oh->obs ? h->d_obs : nullptr;
     int rc = bp_shipice_step(h, h->d_actions, &dev, nullptr);
     if (rc) return rc;
-    if (oh->obs) CUDA_TRY(cudaMemcpyAsync(oh->obs, h->d_obs, E * BP_OBS_C * OBS_PIX, cudaMemcpyDeviceToHost, 0));
+    if (oh->obs) CUDA_TRY(cudaMemcpyAsync(oh->obs, h->d_obs, E * obs_bytes, cudaMemcpyDeviceToHost, 0));
     rc = copy_outputs(h, oh, 0, cudaMemcpyDeviceToHost);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(0));
@@ -471,7 +520,7 @@ static LayoutView host_layout_view(bp_shipice* h, int l) {
     LayoutView L;
     size_t o = (size_t)l * h->d.NB;
     L.lv = T.lv + o * VMAX * 2; L.ln = T.ln + o * VMAX * 2; L.nv = T.nv + o; L.rad = T.rad + o; L.rbound = T.rbound + o; L.minv = T.minv + o; L.iinv = T.iinv + o;
-    L.cog = T.cog + o * 2; L.mat_e = T.mat_e + o; L.mat_u = T.mat_u + o; L.init = T.init + o * 3; L.nbody = T.nbody[l];
+    L.cog = T.cog + o * 2; L.mat_e = T.mat_e + o; L.mat_u = T.mat_u + o; L.init = T.init + o * 3; L.nbody = T.nbody[l]; L.robot0 = H.robot0[l];
     return L;
 }
 
@@ -483,10 +532,12 @@ int bp_shipice_get_obstacles(bp_shipice_t* h, int32_t env, double* verts, int32_
     if (rc) return rc;
     EnvView ev = make_view(buf.data(), h->d);
     LayoutView L = host_layout_view(h, ev.sc->layout);
-    int nf = ev.sc->nbody - 1;
-    for (int b = 0; b < nf; b++) {
-        n_verts[b] = L.nv[b];
-        memcpy(verts + (size_t)b * VMAX * 2, ev.wv + (size_t)b * VMAX * 2, sizeof(double) * 2 * L.nv[b]);
+    int nf = 0;
+    for (int b = 0; b < ev.sc->robot; b++) {
+        if (L.minv[b] == 0.0) continue;              // static walls
+        n_verts[nf] = L.nv[b];
+        memcpy(verts + (size_t)nf * VMAX * 2, ev.wv + (size_t)b * VMAX * 2, sizeof(double) * 2 * L.nv[b]);
+        nf++;
     }
     return nf;
 }
@@ -547,6 +598,133 @@ int bp_shipice_get_kernel_ms(bp_shipice_t* h, double* out4) {
 
 size_t bp_shipice_env_bytes(bp_shipice_t* h) { return h ? h->env_bytes : 0; }
 int64_t bp_shipice_launch_count(bp_shipice_t* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ maze-NAMO
+void bp_maze_default_config(bp_maze_config* c, int32_t maze_version) {
+    memset(c, 0, sizeof(*c));
+    c->n_envs = 1; c->max_boxes = 5; c->device = 0; c->auto_reset = 0;
+    c->dt = 0.8; c->steps = 400; c->iterations = 10; c->damping = 0.0; c->obstacle_density = 0.001; c->obstacle_size = 0.5;
+    c->target_speed = 0.15; c->goal_radius = 1.0; c->min_r = 0.86; c->m_to_pix_scale = 16; c->settle_steps = 1000;
+    double W, Lg;
+    if (maze_version == 2) {
+        W = Lg = 20.0; c->goal_x = 3.33; c->goal_y = 3.33;
+        c->start[0] = 16.66; c->start[1] = 16.66; c->start[2] = 3 * M_PI / 2;
+        const double w[6][4] = {{0, 0, W, 0}, {0, 0, 0, Lg}, {W, 0, W, Lg}, {0, Lg, W, Lg}, {W / 3, 0, W / 3, 2 * Lg / 3}, {2 * W / 3, Lg, 2 * W / 3, Lg / 3}};
+        memcpy(c->walls, w, sizeof(w));
+    } else {
+        W = Lg = 15.0; c->goal_x = 3.75; c->goal_y = 3.75;
+        c->start[0] = 11.25; c->start[1] = 3.75; c->start[2] = M_PI / 2;
+        const double w[6][4] = {{0, 0, W, 0}, {0, 0, 0, Lg}, {W, 0, W, Lg}, {0, Lg, W, Lg}, {2 * W / 2, Lg, 2 * W / 2, 5}, {W / 2, 0, W / 2, Lg - Lg / 3}};
+        memcpy(c->walls, w, sizeof(w));
+    }
+    c->width = W; c->length = Lg; c->n_walls = 6;
+    static const double rv[] = {0.7, -0.5, 0.55, -0.6, -0.55, -0.6, -0.7, -0.5, -0.7, 0.5, -0.55, 0.6, 0.55, 0.6, 0.7, 0.5};
+    c->n_robot_verts = 8; memcpy(c->robot_verts, rv, sizeof(rv));
+    static const double wv[4][8] = {{0.2, 0.6, 0.2, 0.7, 0.5, 0.7, 0.55, 0.6}, {0.2, -0.7, 0.2, -0.6, 0.55, -0.6, 0.55, -0.7},
+                                    {-0.2, 0.6, -0.2, 0.7, -0.55, 0.7, -0.55, 0.6}, {-0.2, -0.6, -0.2, -0.7, -0.55, -0.7, -0.55, -0.6}};
+    c->n_wheels = 4;
+    for (int w = 0; w < 4; w++) { c->wheel_nv[w] = 4; memcpy(c->wheel_verts + 16 * w, wv[w], sizeof(wv[w])); }
+}
+
+int bp_maze_create(const bp_maze_config* cfg, bp_maze_t** out_h) {
+    if (!cfg || !out_h) return fail(BP_ERR_INVALID, "null argument");
+    if (cfg->n_envs <= 0 || cfg->max_boxes < 0 || cfg->max_boxes > 4096) return fail(BP_ERR_INVALID, "n_envs / max_boxes out of range");
+    if (cfg->n_walls < 0 || cfg->n_walls > BP_MAZE_MAX_WALLS) return fail(BP_ERR_INVALID, "n_walls out of range");
+    if (cfg->n_robot_verts < 3 || cfg->n_robot_verts > 32 || cfg->n_wheels < 0 || cfg->n_wheels > BP_MAZE_MAX_WHEELS) return fail(BP_ERR_INVALID, "robot shape out of range");
+    for (int w = 0; w < cfg->n_wheels; w++) if (cfg->wheel_nv[w] < 3 || cfg->wheel_nv[w] > 8) return fail(BP_ERR_INVALID, "wheel vertex count out of range");
+    if (cfg->steps <= 0 || cfg->iterations <= 0 || cfg->dt <= 0 || cfg->m_to_pix_scale <= 0) return fail(BP_ERR_INVALID, "steps / iterations / dt / scale must be positive");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(BP_ERR_CUDA, "CUDA device not available");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    bp_shipice* h = new bp_shipice();
+    h->kind = KIND_MAZE; h->mcfg = *cfg; h->max_boxes = cfg->max_boxes;
+    memset(&h->cfg, 0, sizeof(h->cfg));
+    h->cfg.n_envs = cfg->n_envs; h->cfg.device = cfg->device; h->cfg.auto_reset = cfg->auto_reset;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    MazeConfig& m = h->mz;
+    m.dt = cfg->dt; m.steps = cfg->steps; m.iterations = cfg->iterations; m.damping = cfg->damping; m.target_speed = cfg->target_speed;
+    m.obstacle_density = cfg->obstacle_density; m.obstacle_size = cfg->obstacle_size; m.width = cfg->width; m.length = cfg->length;
+    m.goal_x = cfg->goal_x; m.goal_y = cfg->goal_y; m.goal_radius = cfg->goal_radius; m.min_r = cfg->min_r;
+    m.m_to_pix_scale = cfg->m_to_pix_scale; m.settle_steps = cfg->settle_steps;
+    memcpy(m.start, cfg->start, sizeof(m.start));
+    m.n_walls = cfg->n_walls; memcpy(m.walls, cfg->walls, sizeof(double) * 4 * cfg->n_walls);
+    m.n_robot_verts = cfg->n_robot_verts; memcpy(m.robot_verts, cfg->robot_verts, sizeof(double) * 2 * cfg->n_robot_verts);
+    m.n_wheels = cfg->n_wheels;
+    for (int w = 0; w < cfg->n_wheels; w++) { m.wheel_nv[w] = cfg->wheel_nv[w]; memcpy(m.wheel_verts + 16 * w, cfg->wheel_verts + 16 * w, sizeof(double) * 16); }
+    Dims& d = h->d;
+    d.NB = cfg->n_walls + cfg->max_boxes + 1 + cfg->n_wheels;
+    d.PMAX = d.NB * (d.NB - 1) / 2 + 8;
+    d.LMAX = d.PMAX < 256 ? d.PMAX : 256; if (d.LMAX < 64) d.LMAX = 64;
+    d.n_envs = cfg->n_envs; d.n_layouts = 0;
+    h->P = make_maze_params(m);
+    // the two state-independent maps
+    int H = 0, W = 0;
+    build_maze_maps(m, &H, &W, h->wall_map, h->dist_norm, h->dist_raw);
+    if (H <= 0 || W <= 0) { delete h; return fail(BP_ERR_INVALID, "empty maze grid"); }
+    auto A = [&](void** p, size_t bytes) -> cudaError_t { cudaError_t r = cudaMalloc(p, bytes); if (r == cudaSuccess) { h->dev_allocs.push_back(*p); cudaMemset(*p, 0, bytes); } return r; };
+    uint8_t* d_wall = nullptr; double* d_dist = nullptr;
+    CUDA_TRY(A((void**)&d_wall, (size_t)H * W)); CUDA_TRY(A((void**)&d_dist, (size_t)H * W * 8));
+    CUDA_TRY(cudaMemcpy(d_wall, h->wall_map.data(), (size_t)H * W, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_dist, h->dist_norm.data(), (size_t)H * W * 8, cudaMemcpyHostToDevice));
+    h->P.dist_map = d_dist; h->P.dist_h = H; h->P.dist_w = W;
+    MazeObsParams& O = h->MO;
+    O.grid_h = H; O.grid_w = W; O.scale = (double)cfg->m_to_pix_scale; O.n_robot_raw = cfg->n_robot_verts;
+    memcpy(O.robot_raw, cfg->robot_verts, sizeof(double) * 2 * cfg->n_robot_verts);
+    O.wall_map = d_wall; O.dist_map = d_dist;
+    CUDA_TRY(cudaFuncSetAttribute(k_maze_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MazeObsSmem)));
+    h->env_bytes = env_mem_size(d);
+    size_t total = h->env_bytes * (size_t)d.n_envs;
+    cudaError_t e = cudaMalloc((void**)&h->mem, total);
+    if (e != cudaSuccess) { delete h; return fail(BP_ERR_CUDA, std::string("cudaMalloc of env state (") + std::to_string(total >> 20) + " MiB): " + cudaGetErrorString(e)); }
+    CUDA_TRY(cudaMemset(h->mem, 0, total));
+    CUDA_TRY(cudaMalloc((void**)&h->counter, 64));
+    size_t E = d.n_envs;
+    CUDA_TRY(A((void**)&h->out.reward, E * 8)); CUDA_TRY(A((void**)&h->out.terminated, E)); CUDA_TRY(A((void**)&h->out.truncated, E));
+    CUDA_TRY(A((void**)&h->out.state, E * 24)); CUDA_TRY(A((void**)&h->out.pose, E * 24)); CUDA_TRY(A((void**)&h->out.total_work, E * 8));
+    CUDA_TRY(A((void**)&h->out.collision_reward, E * 8)); CUDA_TRY(A((void**)&h->out.scaled_collision_reward, E * 8));
+    CUDA_TRY(A((void**)&h->out.dist_reward, E * 8)); CUDA_TRY(A((void**)&h->out.trial_success, E)); CUDA_TRY(A((void**)&h->out.status, E * 4));
+    CUDA_TRY(A((void**)&h->d_layout_ids, E * 4));
+    *out_h = h;
+    return BP_OK;
+}
+
+int bp_maze_destroy(bp_maze_t* h) { return bp_shipice_destroy(h); }
+
+int bp_maze_load_layouts(bp_maze_t* h, int32_t n_layouts, const int32_t* n_boxes, const double* centres) {
+    if (!h || n_layouts <= 0 || !n_boxes || !centres) return fail(BP_ERR_INVALID, "null / empty layout arguments");
+    if (h->kind != KIND_MAZE) return fail(BP_ERR_INVALID, "not a maze handle");
+    if (h->layouts_loaded) return fail(BP_ERR_STATE, "layouts already loaded for this handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    std::string err = build_maze_layouts(h->H, n_layouts, h->max_boxes, n_boxes, centres, h->mz);
+    if (!err.empty()) return fail(BP_ERR_INVALID, err);
+    return finish_load_layouts(h, n_layouts);
+}
+
+int bp_maze_reset(bp_maze_t* h, const int32_t* layout_ids, const uint8_t* mask, const bp_maze_outputs* out, void* stream) {
+    return bp_shipice_reset(h, layout_ids, mask, out, stream);
+}
+int bp_maze_step(bp_maze_t* h, const float* actions, const bp_maze_outputs* out, void* stream) {
+    return bp_shipice_step_masked(h, actions, nullptr, out, stream);
+}
+int bp_maze_step_masked(bp_maze_t* h, const float* actions, const uint8_t* mask, const bp_maze_outputs* out, void* stream) {
+    return bp_shipice_step_masked(h, actions, mask, out, stream);
+}
+int bp_maze_step_host(bp_maze_t* h, const float* actions, const bp_maze_outputs* out_host) { return bp_shipice_step_host(h, actions, out_host); }
+int bp_maze_get_obstacles(bp_maze_t* h, int32_t env, double* verts, int32_t* n_verts) { return bp_shipice_get_obstacles(h, env, verts, n_verts); }
+int bp_maze_get_bodies(bp_maze_t* h, int32_t env, double* out) { return bp_shipice_get_bodies(h, env, out); }
+int bp_maze_get_maps(bp_maze_t* h, uint8_t* wall, double* dist_norm, double* dist_raw, int32_t* hw) {
+    if (!h || h->kind != KIND_MAZE) return fail(BP_ERR_INVALID, "not a maze handle");
+    size_t n = h->wall_map.size();
+    if (wall) memcpy(wall, h->wall_map.data(), n);
+    if (dist_norm) memcpy(dist_norm, h->dist_norm.data(), n * 8);
+    if (dist_raw) memcpy(dist_raw, h->dist_raw.data(), n * 8);
+    if (hw) { hw[0] = h->P.dist_h; hw[1] = h->P.dist_w; }
+    return BP_OK;
+}
+
 
 // ------------------------------------------------------------------------------------------------ spfa
 static int* g_spfa_scratch = nullptr; static size_t g_spfa_scratch_bytes = 0; static int* g_spfa_counter = nullptr;

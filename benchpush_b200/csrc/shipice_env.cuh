@@ -47,8 +47,8 @@ BP_DEV double round2(double x) { return rint(x * 100.0) / 100.0; }
 // True when a substep can change nothing: the ship is the only awake body and does not move, and
 // no arbiter is touching or cached (so no stamp-based expiry is pending either).
 BP_DEV bool settle_is_idle(const EnvView& ev, const EnvScal* sc) {
-    if (sc->n_awake != 1 || sc->n_order != 0 || sc->n_cached != 0 || sc->dirty || sc->rebuild) return false;
-    if (ev.awake[0] != sc->robot) return false;
+    // bodies that are not dynamic never leave the awake list, so "only they are awake" is a count
+    if (sc->n_awake != sc->n_fixed || sc->n_order != 0 || sc->n_cached != 0 || sc->dirty || sc->rebuild) return false;
     const BodyRec& R = ev.body[sc->robot];
     return R.vx == 0.0 && R.vy == 0.0 && R.vw == 0.0 && R.bx == 0.0 && R.by == 0.0 && R.bw == 0.0;
 }
@@ -76,8 +76,8 @@ BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const Sim
     sleep_pass(ev, L, d);
     // prev_obs = get_obs_from_poly(polygons) (ship_ice_env.py:220): cache |centroid| and area per floe
     int nb = sc->nbody;
-    for (int b = lane; b < nb - 1; b += BP_NL) {
-        area_centroid_abs(ev.wv + (size_t)b * VMAX * 2, L.nv[b], &ev.area[b], &ev.cenx[b], &ev.ceny[b]);
+    for (int b = lane; b < nb; b += BP_NL) {
+        if (body_dynamic(L, b)) area_centroid_abs(ev.wv + (size_t)b * VMAX * 2, L.nv[b], &ev.area[b], &ev.cenx[b], &ev.ceny[b]);
         ev.moved_step[b] = 0;
     }
     if (lane == 0) {
@@ -89,6 +89,8 @@ BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const Sim
         out.collision_reward[env] = 0.0; out.scaled_collision_reward[env] = 0.0; out.dist_reward[env] = 0.0;
         out.trial_success[env] = 0; out.status[env] = sc->status;
         sc->t = 0; sc->total_work = 0.0;
+        // maze: wall_collision and prev_dist_value are cleared after the settle steps (maze_NAMO_env.py:337-341)
+        sc->wall_hit = 0; sc->has_prev_dist = 0; sc->prev_dist = 0.0;
     }
     bp_wsync();
 }
@@ -122,9 +124,11 @@ BP_DEVNI void shipice_step_begin(const EnvView& ev, const LayoutView& L, const S
         sc->t++;
         double a = ev.body[r].pa;
         double s, c; bp_sincos(a, &s, &c);
-        ev.body[r].vw = action * P.yaw_step;
-        ev.body[r].vx = c * P.target_speed + (-s) * 0.0;
-        ev.body[r].vy = s * P.target_speed + c * 0.0;
+        double vw = action * P.yaw_step;
+        double vx = c * P.target_speed + (-s) * 0.0;
+        double vy = s * P.target_speed + c * 0.0;
+        // every shape of the kinematic robot is one body record with the same pose and velocity
+        for (int q = r; q < sc->nbody; q++) { ev.body[q].vw = vw; ev.body[q].vx = vx; ev.body[q].vy = vy; }
     }
     bp_wsync();
     sleep_pass(ev, L, d);
@@ -141,22 +145,17 @@ BP_DEV int shipice_substep_checks(const EnvView& ev, const LayoutView& L, const 
     return f;
 }
 
-// ship_ice_env.py:291-345: terminal tests, work, reward, info.
-BP_DEVNI void shipice_step_finish(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, int env, const StepOut& out,
-                                  bool yaw_violated, bool boundary_violated) {
+// total_work_done(prev_obs, updated) (evaluation/metrics.py:96-126):
+// work = sum_i area(a_i) * || |c(a_i)| - |c(b_i)| || over the movable polygons in creation order; only
+// bodies that moved this step can contribute.  Warp-cooperative; the sum is returned on lane 0.
+BP_DEVNI double step_work(const EnvView& ev, const LayoutView& L) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
-    const int r = sc->robot;
-    V2 o = body_origin(ev, L, r);
-    bool boundary_terminal = false;
-    if (o.x < 0 && fabs(o.x - 0) >= P.boundary_limit) boundary_terminal = true;
-    if (o.x > P.map_w && fabs(o.x - P.map_w) >= P.boundary_limit) boundary_terminal = true;
-    // work = sum_i area(a_i) * || |c(a_i)| - |c(b_i)| ||  — only floes that moved this step contribute
     int na = sc->n_awake;
     for (int k = lane; k < na; k += BP_NL) {
         int b = ev.awake[k];
         double w = 0.0;
-        if (b != r && ev.moved_step[b]) {
+        if (body_dynamic(L, b) && ev.moved_step[b]) {
             double A, cx, cy;
             area_centroid_abs(ev.wv + (size_t)b * VMAX * 2, L.nv[b], &A, &cx, &cy);
             double dx = ev.cenx[b] - cx, dy = ev.ceny[b] - cy;
@@ -167,10 +166,27 @@ BP_DEVNI void shipice_step_finish(const EnvView& ev, const LayoutView& L, const 
         ev.tmp[b] = w;
     }
     bp_wsync();
+    double work = 0.0;
     if (lane == 0) {
         // ascending body index, like zip(prev_obs, updated) in the reference
-        double work = 0.0;
-        for (int b = 0; b < sc->nbody - 1; b++) if (ev.is_awake[b]) work += ev.tmp[b];
+        const int r = sc->robot;
+        for (int b = 0; b < r; b++) if (ev.is_awake[b] && body_dynamic(L, b)) work += ev.tmp[b];
+    }
+    return work;
+}
+
+// ship_ice_env.py:291-345: terminal tests, work, reward, info.
+BP_DEVNI void shipice_step_finish(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, int env, const StepOut& out,
+                                  bool yaw_violated, bool boundary_violated) {
+    EnvScal* sc = ev.sc;
+    const int lane = bp_lane();
+    const int r = sc->robot;
+    V2 o = body_origin(ev, L, r);
+    bool boundary_terminal = false;
+    if (o.x < 0 && fabs(o.x - 0) >= P.boundary_limit) boundary_terminal = true;
+    if (o.x > P.map_w && fabs(o.x - P.map_w) >= P.boundary_limit) boundary_terminal = true;
+    double work = step_work(ev, L);
+    if (lane == 0) {
         sc->total_work += work;
         double y = o.y;
         bool terminated = (y >= P.goal_y) || boundary_terminal;
@@ -194,23 +210,6 @@ BP_DEVNI void shipice_step_finish(const EnvView& ev, const LayoutView& L, const 
         out.trial_success[env] = success ? 1 : 0; out.status[env] = sc->status;
     }
     bp_wsync();
-}
-
-// One env, one warp: ShipIceEnv.step.
-BP_DEVNI void shipice_step_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, double action, int env, const StepOut& out) {
-    EnvScal* sc = ev.sc;
-    LayoutView L = layout_view(T, d, sc->layout);
-    const int r = sc->robot;
-    shipice_step_begin(ev, L, P, d, action);
-    int flags = 0;
-    for (int k = 0; k < P.substeps; k++) {
-        substep(ev, L, P, d, P.dt, P.dt);
-        int f = 0;
-        if (bp_lane() == 0) f = shipice_substep_checks(ev, L, P, r);
-        flags |= bp_wbcast(f);
-        bp_wsync();
-    }
-    shipice_step_finish(ev, L, P, d, env, out, (flags & 1) != 0, (flags & 2) != 0);
 }
 
 }  // namespace bp

@@ -12,7 +12,7 @@
 // cache expiry, recolouring, sleep) reuse the warp-cooperative routines of sim_step.cuh, one env at
 // a time.
 #pragma once
-#include "shipice_env.cuh"
+#include "maze_env.cuh"
 
 namespace bp {
 
@@ -511,7 +511,7 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
             for (int e = lane; e < BK; e += BP_NL)
                 if (S.base[e]) {
                     EnvView ev = view_at(S.base[e], C->off);
-                    S.flags[e] |= (unsigned char)shipice_substep_checks(ev, S.L[e], P, ev.sc->robot);
+                    S.flags[e] |= (unsigned char)env_substep_checks(ev, S.L[e], P, ev.sc->robot);
                 }
             bp_wsync();
         }
@@ -521,7 +521,7 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
         if (!base) continue;
         EnvView ev = view_at(base, C->off);
         int env = S.env_id[e];
-        shipice_step_finish(ev, S.L[e], P, d, env, out, (S.flags[e] & 1) != 0, (S.flags[e] & 2) != 0);
+        env_step_finish(ev, S.L[e], P, d, env, out, (int)S.flags[e]);
         if (lane == 0) { ev.sc->done = out.terminated[env]; ev.sc->obs_raw = 0; }
         bp_wsync();
     }

@@ -53,7 +53,17 @@ struct SimParams {
     double boundary_limit;        // 0.0
     double boundary_penalty, terminal_reward, yaw_penalty;   // -50, 200, 0
     double margin_body, margin_robot;                        // neighbour-list margins (m)
+    // ---- env kind and the maze-NAMO constants (maze_NAMO_env.py:80-82, 406-410, 528-536)
+    int kind;                     // 0 = ship-ice-v0, 1 = maze-NAMO-v0
+    int n_walls;                  // static wall segments: bodies [0, n_walls) of a maze layout
+    double goal_x, goal_gy;       // cfg.env.goal_x / goal_y
+    double goal_reach;            // cfg.goal_radius + cfg.robot.min_r
+    double k_increment;           // 150
+    double pix_scale;             // cfg.occ.m_to_pix_scale (16)
+    const double* dist_map;       // [dist_h][dist_w] normalised goal-point distance map (occupancy_map.py:435-485)
+    int dist_h, dist_w;
 };
+enum EnvKind { KIND_SHIPICE = 0, KIND_MAZE = 1 };
 
 struct Dims {
     int NB;                       // bodies per env incl. robot (capacity)
@@ -76,7 +86,9 @@ struct LayoutTab {
     const double* mat_e;          // [L][NB]
     const double* mat_u;          // [L][NB]
     const double* init;           // [L][NB][3] body position x, y, angle
-    const int* nbody;             // [L] bodies incl. robot; robot index = nbody-1
+    const int* nbody;             // [L] bodies incl. robot
+    const int* robot0;            // [L] first body of the kinematic robot: its shapes are bodies [robot0, nbody), all
+                                  //     carrying the same pose and velocity (a compound pymunk body, one record per shape)
 };
 
 struct EnvScal {
@@ -84,7 +96,8 @@ struct EnvScal {
     int status, layout, nbody, robot, t, rebuild, n_apairs, n_cached;
     int any_wake, episode, done, first_layout;
     double G;                     // monotone accumulator: bounds the growth of D[a] + D[b] of ANY pair
-    int obs_raw, pad0, pad1, pad2;
+    int obs_raw, n_fixed, wall_hit, has_prev_dist;   // n_fixed: bodies that are not dynamic (robot shapes + walls)
+    double prev_dist;                                 // maze: distance-map value at the previous step (prev_dist_value)
     double total_work;
     long long stat_gjk, stat_pairs_eval, stat_live_sum, stat_awake_sum, stat_recolour, stat_rebuild, stat_substeps;
     long long stat_epa, stat_skipped, t_phase[8];
@@ -211,7 +224,7 @@ BP_DEV EnvView view_at(char* base, const EnvOff& O) {
 struct LayoutView {
     const double *lv, *ln, *rad, *rbound, *minv, *iinv, *cog, *mat_e, *mat_u, *init;
     const int* nv;
-    int nbody;
+    int nbody, robot0;
 };
 // Everything a kernel needs that is constant for a handle; lives in device memory (one copy per
 // handle) so that out-of-line device functions can take it as ONE pointer.
@@ -228,7 +241,7 @@ BP_DEV LayoutView layout_view(const LayoutTab& T, const Dims& d, int l) {
     size_t o = (size_t)l * d.NB;
     L.lv = T.lv + o * VMAX * 2; L.ln = T.ln + o * VMAX * 2; L.nv = T.nv + o; L.rad = T.rad + o; L.rbound = T.rbound + o;
     L.minv = T.minv + o; L.iinv = T.iinv + o; L.cog = T.cog + o * 2; L.mat_e = T.mat_e + o; L.mat_u = T.mat_u + o;
-    L.init = T.init + o * 3; L.nbody = T.nbody[l];
+    L.init = T.init + o * 3; L.nbody = T.nbody[l]; L.robot0 = T.robot0[l];
     return L;
 }
 
@@ -290,6 +303,8 @@ struct Poly { const double* v; int n; };
 // The one copy of the support scan (GJK, EPA and the manifold builder all call it): the hot path is
 // instruction-fetch bound (profiles/), so shared out-of-line leaves beat inlined copies.
 BP_DEVNI int support_index(const Poly& P, V2 n) {
+    // a 2-vertex shape is a cpSegmentShape (walls): SegmentSupportPoint returns ta only when strictly greater
+    if (P.n == 2) return (P.v[0] * n.x + P.v[1] * n.y > P.v[2] * n.x + P.v[3] * n.y) ? 0 : 1;
     double mx = -INFINITY; int idx = 0;
 #pragma unroll 4
     for (int i = 0; i < P.n; i++) {
@@ -411,9 +426,17 @@ BP_DEVNI Closest gjk_epa(const Poly& A, const Poly& B, unsigned hint, int* cappe
 struct EdgeW { V2 a, b; int ia, ib; };
 BP_DEV EdgeW support_edge(const Poly& P, const double* ln, double rc, double rs, V2 n) {
     int count = P.n;
+    double ms = -rs;
+    if (count == 2) {
+        // SupportEdgeForSegment (cpCollision.c): ln[0] is the segment normal rperp(normalize(b - a))
+        V2 tn = mk(rc * ln[0] + ms * ln[1], rs * ln[0] + rc * ln[1]);
+        EdgeW e;
+        if (dot(tn, n) > 0.0) { e.a = pvert(P, 0); e.b = pvert(P, 1); e.ia = 0; e.ib = 1; }
+        else { e.a = pvert(P, 1); e.b = pvert(P, 0); e.ia = 1; e.ib = 0; }
+        return e;
+    }
     int i1 = support_index(P, n);
     int i0 = (i1 - 1 + count) % count, i2 = (i1 + 1) % count;
-    double ms = -rs;
     V2 n1 = mk(rc * ln[2 * i1] + ms * ln[2 * i1 + 1], rs * ln[2 * i1] + rc * ln[2 * i1 + 1]);
     V2 n2 = mk(rc * ln[2 * i2] + ms * ln[2 * i2 + 1], rs * ln[2 * i2] + rc * ln[2 * i2 + 1]);
     EdgeW e;

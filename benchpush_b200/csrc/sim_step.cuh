@@ -8,7 +8,7 @@
 namespace bp {
 
 BP_DEV unsigned pair_key(int i, int j) { return ((unsigned)i << 16) | (unsigned)j; }
-BP_DEV double body_margin(const SimParams& P, const EnvScal* sc, int b) { return b == sc->robot ? P.margin_robot : P.margin_body; }
+BP_DEV double body_margin(const SimParams& P, const EnvScal* sc, int b) { return b >= sc->robot ? P.margin_robot : P.margin_body; }
 BP_DEV bool body_dynamic(const LayoutView& L, int b) { return L.minv[b] != 0.0; }
 
 #if defined(BP_PHASE_TIMERS) && defined(__CUDACC__) && !defined(BP_HOST_EMU)
@@ -728,8 +728,12 @@ BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& 
     const int nb = L.nbody;
     if (lane == 0) {
         sc->stamp = 0; sc->n_awake = nb; sc->n_pairs = 0; sc->cur = 0; sc->n_free = d.LMAX; sc->n_order = 0; sc->n_colours = 0;
-        sc->dirty = 1; sc->status = 0; sc->layout = layout_id; sc->nbody = nb; sc->robot = nb - 1; sc->t = 0; sc->rebuild = 0;
+        sc->dirty = 1; sc->status = 0; sc->layout = layout_id; sc->nbody = nb; sc->robot = L.robot0; sc->t = 0; sc->rebuild = 0;
         sc->n_apairs = 0; sc->n_cached = 0; sc->any_wake = 0; sc->total_work = 0.0; sc->G = 0.0;
+        sc->wall_hit = 0; sc->has_prev_dist = 0; sc->prev_dist = 0.0;
+        int nf = 0;
+        for (int b = 0; b < nb; b++) nf += body_dynamic(L, b) ? 0 : 1;
+        sc->n_fixed = nf;
     }
     for (int b = lane; b < nb; b += BP_NL) {
         BodyRec& R = ev.body[b];

@@ -1,7 +1,8 @@
 """Batched environments.  Ids follow the reference registry (benchpush/environments/__init__.py:3-51)."""
+from .maze_namo import MazeNamoVecEnv
 from .ship_ice import ShipIceVecEnv
 
-REGISTRY = {"ship-ice-v0": ShipIceVecEnv}
+REGISTRY = {"ship-ice-v0": ShipIceVecEnv, "maze-NAMO-v0": MazeNamoVecEnv}
 MAX_EPISODE_STEPS = {"ship-ice-v0": 300, "box-delivery-v0": 30000, "area-clearing-v0": 400, "maze-NAMO-v0": 30000}
 
 

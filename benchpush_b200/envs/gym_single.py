@@ -60,3 +60,58 @@ class ShipIceEnvB200:
 
     def close(self):
         self._v.close()
+
+
+class MazeNamoEnvB200:
+    """Single-environment view of :class:`MazeNamoVecEnv` with the reference's return types
+    (``MazeNAMO``, maze_NAMO_env.py:325-359, 402-485): obs ``np.uint8[4,192,192]``, python scalars in ``info``."""
+    metadata = {"render_modes": []}
+
+    def __init__(self, cfg=None, **kw):
+        from .maze_namo import MazeNamoVecEnv
+        self._v = MazeNamoVecEnv(num_envs=1, cfg=cfg, **kw)
+        self.cfg = self._v.cfg
+        self.goal = self._v.goal
+        self.max_yaw_rate_step = self._v.max_yaw_rate_step
+        self.beta = self._v.beta
+        self.maze_walls = self._v.maze_walls
+        self.episode_idx = None
+        self.t = 0
+        self.total_work = [0, []]
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def _info(self, info, reset):
+        out = {"state": tuple(float(x) for x in info["state"][0].tolist()),
+               "total_work": float(info["total_work"][0]) if not reset else 0, "obs": info["obs"][0]}
+        if reset:
+            out.update({"box_count": 0, "goal_dt": info["goal_dt"], "m_to_pix_scale": info["m_to_pix_scale"]})
+        else:
+            out.update({"collision reward": float(info["collision reward"][0]),
+                        "scaled collision reward": float(info["scaled collision reward"][0]),
+                        "dist increment reward": float(info["dist increment reward"][0]),
+                        "trial_success": bool(info["trial_success"][0])})
+        return out
+
+    def reset(self, seed=None, options=None):
+        self.episode_idx = 0 if self.episode_idx is None else self.episode_idx + 1
+        obs, info = self._v.reset()
+        self.t = 0
+        self.total_work = [0, []]
+        return obs[0].cpu().numpy(), self._info(info, True)
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float32).reshape(1)
+        obs, r, term, trunc, info = self._v.step(a)
+        self.t += 1
+        out = self._info(info, False)
+        self.total_work[0] = out["total_work"]
+        return obs[0].cpu().numpy(), float(r[0]), bool(term[0]), bool(trunc[0]), out
+
+    def render(self):
+        raise NotImplementedError("rendering is out of scope for the batched simulator")
+
+    def close(self):
+        self._v.close()

@@ -39,6 +39,11 @@ class _LazyObstacles:
 
 class ShipIceVecEnv:
     metadata = {"render_modes": []}
+    _prefix = "shipice"          # C ABI family of this env: bp_<prefix>_reset / step / ... (include/benchpush_b200.h)
+    _obs_shape = _lib.OBS_SHAPE
+
+    def _fn(self, name):
+        return getattr(self._L, "bp_%s_%s" % (self._prefix, name))
 
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[PackedLayouts] = None,
                  trials: Optional[Sequence[dict]] = None, ice_file: Optional[str] = None, auto_reset: bool = False,
@@ -158,7 +163,7 @@ class ShipIceVecEnv:
             if mask is not None:
                 mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
                 mptr = C.c_void_p(mask.data_ptr())
-            _lib.check(self._L.bp_shipice_reset(self._h, C.c_void_p(self._next_trial.data_ptr()), mptr, C.byref(self._out), self._stream()))
+            _lib.check(self._fn("reset")(self._h, C.c_void_p(self._next_trial.data_ptr()), mptr, C.byref(self._out), self._stream()))
             if mask is None:
                 self._next_trial = (self._next_trial + 1) % self.env_max_trial
             else:
@@ -182,7 +187,7 @@ class ShipIceVecEnv:
         if mask is not None:
             self._mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()      # kept alive until the next call
             mptr = C.c_void_p(self._mask.data_ptr())
-        _lib.check(self._L.bp_shipice_step_masked(self._h, C.c_void_p(action_dev.data_ptr()), mptr, C.byref(self._out), self._stream()))
+        _lib.check(self._fn("step_masked")(self._h, C.c_void_p(action_dev.data_ptr()), mptr, C.byref(self._out), self._stream()))
 
     def step_host(self, actions: np.ndarray, want_obs: bool = False):
         """The same step through host buffers (numpy in, numpy out; copies inside)."""
@@ -194,19 +199,19 @@ class ShipIceVecEnv:
                           "status": np.zeros(E, np.int32), "obs": None}
         hb = self._host
         if want_obs and hb["obs"] is None:
-            hb["obs"] = np.zeros((E,) + _lib.OBS_SHAPE, np.uint8)
+            hb["obs"] = np.zeros((E,) + self._obs_shape, np.uint8)
         o = _lib.ShipIceOutputs()
         o.reward = hb["reward"].ctypes.data; o.terminated = hb["terminated"].ctypes.data; o.truncated = hb["truncated"].ctypes.data
         o.state = hb["state"].ctypes.data; o.total_work = hb["total_work"].ctypes.data
         o.trial_success = hb["trial_success"].ctypes.data; o.status = hb["status"].ctypes.data
         if want_obs:
             o.obs = hb["obs"].ctypes.data
-        _lib.check(self._L.bp_shipice_step_host(self._h, a.ctypes.data, C.byref(o)))
+        _lib.check(self._fn("step_host")(self._h, a.ctypes.data, C.byref(o)))
         return hb
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            self._L.bp_shipice_destroy(self._h)
+            self._fn("destroy")(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -223,12 +228,12 @@ class ShipIceVecEnv:
         F = self.layouts.max_floes
         verts = np.zeros((F, _lib.BP_VMAX, 2), dtype=np.float64)
         nv = np.zeros(F, dtype=np.int32)
-        n = _lib.check(self._L.bp_shipice_get_obstacles(self._h, e, verts.ctypes.data, nv.ctypes.data))
+        n = _lib.check(self._fn("get_obstacles")(self._h, e, verts.ctypes.data, nv.ctypes.data))
         return [verts[i, : nv[i]].copy() for i in range(n)]
 
     def get_bodies(self, e: int) -> np.ndarray:
         out = np.zeros((self.layouts.max_floes + 1, 6), dtype=np.float64)
-        n = _lib.check(self._L.bp_shipice_get_bodies(self._h, e, out.ctypes.data))
+        n = _lib.check(self._fn("get_bodies")(self._h, e, out.ctypes.data))
         return out[:n]
 
     def counters(self, e: int) -> dict:

@@ -192,3 +192,76 @@ def generate_ice_field(seed: int, concentration: float, map_width: float = 12.0,
 
 def generate_experiment(n_trials: int, concentration: float, seed: int = 99, **kw) -> List[dict]:
     return [generate_ice_field(seed * 100003 + i, concentration, **kw) for i in range(n_trials)]
+
+
+# ------------------------------------------------------------------------------------------------ maze-NAMO
+def maze_walls(maze_version: int, width: float, length: float):
+    """construct_maze_walls (maze_NAMO_env.py:361-379): six wall centre lines [(x0, y0), (x1, y1)]."""
+    W, L = width, length
+    if maze_version == 1:
+        return [[(0, 0), (W, 0)], [(0, 0), (0, L)], [(W, 0), (W, L)], [(0, L), (W, L)],
+                [(2 * W / 2, L), (2 * W / 2, 5)], [(W / 2, 0), (W / 2, L - L / 3)]]
+    if maze_version == 2:
+        return [[(0, 0), (W, 0)], [(0, 0), (0, L)], [(W, 0), (W, L)], [(0, L), (W, L)],
+                [(W / 3, 0), (W / 3, 2 * L / 3)], [(2 * W / 3, L), (2 * W / 3, L / 3)]]
+    raise Exception("Invalid Maze Version!")
+
+
+def _segment_query(p, a, b, radius, max_dist) -> bool:
+    """pymunk ``space.point_query(p, max_dist, ShapeFilter())`` restricted to one Segment shape: True when the
+    signed distance from p to the rounded segment is strictly below max_dist (Chipmunk NearestPointQuery), with
+    the spatial-index prefilter (AABB of the segment against the box p +- max(max_dist, 0))."""
+    md = max(max_dist, 0.0)
+    l, r = min(a[0], b[0]) - radius, max(a[0], b[0]) + radius
+    bt, tp = min(a[1], b[1]) - radius, max(a[1], b[1]) + radius
+    if not (p[0] - md <= r and l <= p[0] + md and p[1] - md <= tp and bt <= p[1] + md):
+        return False
+    dx, dy = a[0] - b[0], a[1] - b[1]
+    t = (dx * (p[0] - b[0]) + dy * (p[1] - b[1])) / (dx * dx + dy * dy)
+    t = max(0.0, min(t, 1.0))
+    cx, cy = b[0] + dx * t, b[1] + dy * t
+    ex, ey = p[0] - cx, p[1] - cy
+    return (ex * ex + ey * ey) ** 0.5 - radius < max_dist
+
+
+def generate_maze_layout(rng, walls, num_obstacles: int, length: float, min_dist: float, wall_radius: float = 0.5):
+    """MazeNAMO.generate_obstacles, randomised branch (maze_NAMO_env.py:275-301), with ``rng`` (a
+    ``random.Random``) in place of the reference's unseeded global ``random`` module.  The space holds only the
+    wall segments at that point (:224-226 vs :253).  Quirk kept: the wall test sits inside the loop over the
+    previously placed obstacles, so the first obstacle is never tested against the walls."""
+    obstacles = []
+    while len(obstacles) < num_obstacles:
+        cx = rng.random() * (length - 0) + 0
+        cy = rng.random() * (length - 0) + 0
+        overlapped = False
+        for px, py in obstacles:
+            if ((cx - px) ** 2 + (cy - py) ** 2) ** 0.5 <= min_dist:
+                overlapped = True
+                break
+            if any(_segment_query((cx, cy), a, b, wall_radius, min_dist) for a, b in walls):
+                overlapped = True
+                break
+        if not overlapped:
+            obstacles.append([cx, cy])
+    return obstacles
+
+
+def generate_maze_layouts(n: int, seed: int = 0, maze_version: int = 1, num_obstacles: int = 5, width: float = 15.0,
+                          length: float = 15.0, min_dist: float = 0.62):
+    """``n`` seeded obstacle layouts (lists of [x, y] centres); layout k depends on (seed, k) only."""
+    import random
+    walls = maze_walls(maze_version, width, length)
+    return [generate_maze_layout(random.Random(seed * 1000003 + k), walls, num_obstacles, length, min_dist) for k in range(n)]
+
+
+def pack_maze_layouts(layouts, max_boxes: int | None = None):
+    """-> (n_boxes int32 [L], centres float64 [L, max_boxes, 2])"""
+    B = max(len(l) for l in layouts) if max_boxes is None else max_boxes
+    nb = np.array([len(l) for l in layouts], dtype=np.int32)
+    if int(nb.max()) > B:
+        raise ValueError("layout has more obstacles than max_boxes")
+    cen = np.zeros((len(layouts), max(B, 1), 2), dtype=np.float64)
+    for i, l in enumerate(layouts):
+        if len(l):
+            cen[i, :len(l)] = np.asarray(l, dtype=np.float64).reshape(-1, 2)
+    return nb, cen

@@ -106,3 +106,34 @@ class ShipIceMetric(BaseMetric):
         n = max(float(t[0]), 1.0)
         return {"episodes": int(t[0]), "success_rate": float(t[1]) / n, "efficiency_mean": float(t[2]) / n,
                 "effort_mean": float(t[3]) / n, "reward_mean": float(t[4]) / n}
+
+
+class MazeNamoMetric(ShipIceMetric):
+    """maze_namo_metric.py:5-75, batched.  Same scores as :class:`ShipIceMetric` with the robot in place of the
+    ship, except the reference path length: ``L = goal_dt[int(y0 * s), int(x0 * s)] / s`` read from
+    ``info['goal_dt']`` (the un-normalised wavefront hop-count map) at the 2-decimal-rounded start position
+    (:69-75)."""
+
+    def __init__(self, alg_name, robot_mass, num_envs=None, device=None) -> None:
+        super().__init__(alg_name=alg_name, ship_mass=robot_mass, goal=(0.0, 0.0), num_envs=num_envs, device=device)
+        self.robot_mass = float(robot_mass)
+        self._goal_dt = None
+
+    def reset(self, info, mask=None):
+        super().reset(info, mask)
+        if self._goal_dt is None or self._goal_dt_src is not info["goal_dt"]:
+            self._goal_dt_src = info["goal_dt"]
+            self._goal_dt = torch.as_tensor(info["goal_dt"], dtype=torch.float64, device=self._dev)
+        s = float(info["m_to_pix_scale"])
+        m = torch.ones(self._n, dtype=torch.bool, device=self._dev) if mask is None else mask.bool()
+        st = info["state"]
+        px = (st[:, 0] * s).to(torch.int64)       # int() truncates toward zero, like tensor.to(int64)
+        py = (st[:, 1] * s).to(torch.int64)
+        H, W = self._goal_dt.shape
+        px = torch.where(px < 0, px + W, px).clamp(0, W - 1)
+        py = torch.where(py < 0, py + H, py).clamp(0, H - 1)
+        self.L = torch.where(m, self._goal_dt[py, px] / s, self.L)
+
+    @property
+    def total_robot_dist(self):
+        return self.total_ship_dist

@@ -149,6 +149,82 @@ size_t bp_shipice_env_bytes(bp_shipice_t* h);
 int64_t bp_shipice_launch_count(bp_shipice_t* h);
 
 /* ------------------------------------------------------------------------------------------------
+ * maze-NAMO-v0.  Replaces MazeNAMO.__init__/reset/step/generate_observation
+ * (benchpush/environments/maze_NAMO/maze_NAMO_env.py:42-132, 325-359, 402-485, 514-525), the
+ * pymunk.Space it drives (maze_NAMO_env.py:145-216, 268, 415: static Segment walls of
+ * common/utils/sim_utils.py:174-181, the compound kinematic robot of common/robot.py:77-118, the
+ * (1,3) robot-wall pre_solve handler) and OccupancyGrid.ego_view_map_maze with the maps it needs
+ * (common/occupancy_grid/occupancy_map.py:67-94, 142-202, 338-376, 435-485) for a batch of envs.
+ * Same handle life cycle, output struct and call semantics as the ship-ice functions above; the
+ * observation is [E][4][192][192] u8 (footprint, movable obstacles, walls, goal-distance map) and
+ * `dist_reward` carries info['dist increment reward'].
+ * ---------------------------------------------------------------------------------------------- */
+#define BP_MAZE_OBS_C 4
+#define BP_MAZE_OBS_H 192
+#define BP_MAZE_OBS_W 192
+#define BP_MAZE_MAX_WALLS 16
+#define BP_MAZE_MAX_WHEELS 8
+
+typedef struct bp_shipice bp_maze_t;           /* same opaque handle type */
+typedef bp_shipice_outputs bp_maze_outputs;
+
+typedef struct bp_maze_config {
+    int32_t n_envs;
+    int32_t max_boxes;        /* capacity of movable obstacles per layout (cfg.num_obstacles = 5) */
+    int32_t device;
+    int32_t auto_reset;       /* 1: an env that terminated is reset by its NEXT step call (next layout) */
+    /* reference cfg keys that reach the hot path (maze_NAMO/config.yaml) */
+    double dt;                /* cfg.dt = 0.8 */
+    int32_t steps;            /* cfg.sim.steps = 400 */
+    int32_t iterations;       /* cfg.sim.iterations = 10 */
+    double damping;           /* cfg.sim.damping = 0 */
+    double obstacle_density;  /* cfg.sim.obstacle_density = 0.001 */
+    double obstacle_size;     /* cfg.obstacle_size = 0.5 (half side of the square obstacles) */
+    double target_speed;      /* cfg.target_speed = 0.15 */
+    double width, length;     /* cfg.env.width / length (15 x 15 for maze_version 1) */
+    double goal_x, goal_y;    /* cfg.env.goal_x / goal_y */
+    double goal_radius;       /* cfg.goal_radius = 1 */
+    double min_r;             /* cfg.robot.min_r = 0.86 */
+    int32_t m_to_pix_scale;   /* cfg.occ.m_to_pix_scale = 16 (local window 12 m = 192 cells is fixed) */
+    int32_t settle_steps;     /* 1000 (maze_NAMO_env.py:268) */
+    double start[3];          /* robot start pose x, y, theta (maze_NAMO_env.py:247-250) */
+    int32_t n_walls;          /* construct_maze_walls (maze_NAMO_env.py:361-379) */
+    double walls[4 * BP_MAZE_MAX_WALLS];            /* x0, y0, x1, y1 per wall */
+    int32_t n_robot_verts;    /* cfg.robot.vertices */
+    double robot_verts[64];
+    int32_t n_wheels;         /* cfg.robot.wheel_vertices */
+    int32_t wheel_nv[BP_MAZE_MAX_WHEELS];
+    double wheel_verts[BP_MAZE_MAX_WHEELS * 16];    /* up to 8 vertices per wheel, 16 doubles per wheel slot */
+} bp_maze_config;
+
+/* Fill cfg with the reference defaults for maze_version 1 or 2 (maze_NAMO/config.yaml, construct_maze_walls). */
+void bp_maze_default_config(bp_maze_config* cfg, int32_t maze_version);
+
+/* Builds the two state-independent global maps on the host (wall occupancy: compute_occ_img_walls,
+ * occupancy_map.py:67-94; goal-point wavefront distance map: global_goal_point_dist_transform, :435-485). */
+int bp_maze_create(const bp_maze_config* cfg, bp_maze_t** out);
+int bp_maze_destroy(bp_maze_t* h);
+
+/* Obstacle layouts (the reference samples them with the unseeded global `random`, maze_NAMO_env.py:275-301;
+ * here they are inputs).  HOST pointers: n_boxes[L], centres[L*max_boxes*2]. */
+int bp_maze_load_layouts(bp_maze_t* h, int32_t n_layouts, const int32_t* n_boxes, const double* centres);
+
+int bp_maze_reset(bp_maze_t* h, const int32_t* layout_ids, const uint8_t* mask, const bp_maze_outputs* out, void* stream);
+int bp_maze_step(bp_maze_t* h, const float* actions, const bp_maze_outputs* out, void* stream);
+int bp_maze_step_masked(bp_maze_t* h, const float* actions, const uint8_t* mask, const bp_maze_outputs* out, void* stream);
+int bp_maze_step_host(bp_maze_t* h, const float* actions, const bp_maze_outputs* out_host);
+
+/* info['obs']: world-space hull vertices of every movable obstacle of env `env`.  HOST outputs:
+ * verts[max_boxes*BP_VMAX*2], n_verts[max_boxes]; returns the obstacle count. */
+int bp_maze_get_obstacles(bp_maze_t* h, int32_t env, double* verts, int32_t* n_verts);
+/* Body state of env `env`, HOST out[n*6] (x, y, angle, vx, vy, w) in shape creation order: walls, obstacles,
+ * robot chassis, wheels.  Returns the body count. */
+int bp_maze_get_bodies(bp_maze_t* h, int32_t env, double* out);
+/* The constant maps, HOST outputs (each may be NULL): wall[H*W] u8, dist_norm[H*W] (global_distance_map),
+ * dist_raw[H*W] (info['goal_dt'], the un-normalised hop counts); hw[2] = {H, W}. */
+int bp_maze_get_maps(bp_maze_t* h, uint8_t* wall, double* dist_norm, double* dist_raw, int32_t* hw);
+
+/* ------------------------------------------------------------------------------------------------
  * Grid shortest paths.  Replaces spfa.spfa(input_map, source) -> (dists, parents)
  * (deps/spfa/src/main.cpp:10-116; call sites box_delivery_env.py:1121,1134,1226,
  * area_clearing.py:1049,1061, position_controller.py:143) for a batch of maps:

@@ -78,6 +78,7 @@ struct Plane { V v0, n; };
 
 struct Shape {
     int body;
+    int kind;    // 0 = cpPolyShape, 1 = cpSegmentShape (world[0].v0 = ta, world[1].v0 = tb, world[0].n = tn)
     int count;
     cpFloat r;
     std::vector<Plane> local;   // hull verts (CCW) + edge normals, body-local
@@ -211,6 +212,9 @@ struct Space {
     std::unordered_map<uint64_t, Arbiter> cache;   // keyed by (a<<32)|b
     std::vector<Arbiter*> arbiters;                // this step's solve list
     Stats st;
+    // collision-handler bookkeeping: number of pre_solve calls this far for shape pairs whose
+    // collision types are {1, 3} (robot chassis vs maze wall: maze_NAMO_env.py:203-216)
+    long long hits_13;
     // sweep scratch
     std::vector<int> order_y;
 };
@@ -326,8 +330,14 @@ static inline MinkowskiPoint mk_new(SupportPoint a, SupportPoint b) {
     MinkowskiPoint m = {a.p, b.p, vsub(b.p, a.p), (uint32_t)((a.index & 0xFF) << 8 | (b.index & 0xFF))};
     return m;
 }
+// cpCollision.c SegmentSupportPoint: ta (index 0) only when strictly greater, else tb (index 1)
+static inline SupportPoint segment_support(const Shape* s, V n) {
+    if (vdot(s->world[0].v0, n) > vdot(s->world[1].v0, n)) { SupportPoint sp = {s->world[0].v0, 0}; return sp; }
+    SupportPoint sp = {s->world[1].v0, 1}; return sp;
+}
+static inline SupportPoint shape_support(const Shape* s, V n) { return s->kind == 1 ? segment_support(s, n) : poly_support(s, n); }
 static inline MinkowskiPoint support(const Ctx* c, V n) {
-    return mk_new(poly_support(c->s1, vneg(n)), poly_support(c->s2, n));
+    return mk_new(shape_support(c->s1, vneg(n)), shape_support(c->s2, n));
 }
 static inline cpFloat closest_t(V a, V b) {
     V delta = vsub(b, a);
@@ -452,6 +462,18 @@ static Edge support_edge_for_poly(const Shape* s, int sid, V n) {
     }
 }
 
+// cpCollision.c SupportEdgeForSegment
+static Edge support_edge_for_segment(const Shape* s, int sid, V n) {
+    V ta = s->world[0].v0, tb = s->world[1].v0, tn = s->world[0].n;
+    if (vdot(tn, n) > 0.0) {
+        Edge e = {{ta, feature_id(sid, 0)}, {tb, feature_id(sid, 1)}, s->r, tn};
+        return e;
+    } else {
+        Edge e = {{tb, feature_id(sid, 1)}, {ta, feature_id(sid, 0)}, s->r, vneg(tn)};
+        return e;
+    }
+}
+
 struct CollisionInfo { V n; int count; V p1[2], p2[2]; uint64_t hash[2]; };
 
 // Chipmunk hashes the two vertex hashes with the symmetric CP_HASH_PAIR; here the pair of
@@ -494,6 +516,25 @@ static void poly_to_poly(Space* sp, int ia, int ib, uint32_t* id, CollisionInfo*
     if (pts.d - s1->r - s2->r <= 0.0) {
         contact_points(support_edge_for_poly(s1, ia, pts.n), support_edge_for_poly(s2, ib, vneg(pts.n)), pts, info);
     }
+}
+
+// cpCollision.c SegmentToPoly (the segment is always shape `a`: cpCollide requires type order
+// circle < segment < poly).  Neighbour tangents are zero for every segment the envs create
+// (sim_utils.py:174-181 never calls set_neighbors), so the end-cap rejection never fires.
+static void segment_to_poly(Space* sp, int ia, int ib, uint32_t* id, CollisionInfo* info) {
+    const Shape* seg = &sp->shapes[ia]; const Shape* poly = &sp->shapes[ib];
+    Ctx ctx = {seg, poly, sp};
+    ClosestPoints pts = gjk(&ctx, id);
+    if (pts.d - seg->r - poly->r <= 0.0) {
+        contact_points(support_edge_for_segment(seg, ia, pts.n), support_edge_for_poly(poly, ib, vneg(pts.n)), pts, info);
+    }
+}
+static void collide_shapes(Space* sp, int ia, int ib, uint32_t* id, CollisionInfo* info) {
+    int ka = sp->shapes[ia].kind, kb = sp->shapes[ib].kind;
+    if (ka == 0 && kb == 0) poly_to_poly(sp, ia, ib, id, info);
+    else if (ka == 1 && kb == 0) segment_to_poly(sp, ia, ib, id, info);
+    else if (ka == 1 && kb == 1) { /* cpCollide: segment-segment is only reached for non-static pairs; none exist here */ }
+    else { fprintf(stderr, "oracle: create segment shapes before poly shapes (pair %d,%d)\n", ia, ib); abort(); }
 }
 
 // ---------------------------------------------------------------- arbiter (cpArbiter.c)
@@ -681,7 +722,7 @@ static void space_step(Space* sp, cpFloat dt) {
         auto it = sp->cache.find(key);
         uint32_t gid = (it != sp->cache.end()) ? it->second.gjk_id : 0;
         CollisionInfo info; info.count = 0;
-        poly_to_poly(sp, ia, ib, &gid, &info);
+        collide_shapes(sp, ia, ib, &gid, &info);
         if (info.count == 0) { if (it != sp->cache.end()) it->second.gjk_id = gid; continue; }
         Arbiter* arb;
         if (it == sp->cache.end()) {
@@ -692,6 +733,10 @@ static void space_step(Space* sp, cpFloat dt) {
         arb->gjk_id = gid;
         arb->body_a = sp->shapes[ia].body; arb->body_b = sp->shapes[ib].body;
         arbiter_update(sp, arb, info);
+        {   // pre_solve of handler (1, 3) — called for every touching pair, solved or not
+            int ta = sp->shapes[ia].ctype, tb = sp->shapes[ib].ctype;
+            if ((ta == 1 && tb == 3) || (ta == 3 && tb == 1)) sp->hits_13++;
+        }
         // handlers used by ship-ice only do bookkeeping (ship_ice_env.py:150-180): begin/pre_solve return True
         const Body& ba = sp->bodies[arb->body_a]; const Body& bb = sp->bodies[arb->body_b];
         if (arb->state != ARB_IGNORE && !(ba.m == INFINITY && bb.m == INFINITY)) {
@@ -757,7 +802,7 @@ void* cpo_space_new(void) {
     Space* sp = new Space();
     sp->iterations = 10; sp->damping = 1.0; sp->gravity = v(0, 0);
     sp->slop = 0.1; sp->collision_bias = std::pow(1.0 - 0.1, 60.0); sp->persistence = 3;
-    sp->stamp = 0; sp->curr_dt = 0.0; sp->order_mode = 0;
+    sp->stamp = 0; sp->curr_dt = 0.0; sp->order_mode = 0; sp->hits_13 = 0;
     memset(&sp->st, 0, sizeof(sp->st));
     return sp;
 }
@@ -787,7 +832,7 @@ int cpo_poly_new(void* h, int body, int n, const double* xy, double radius) {
     for (int i = 0; i < n; i++) hull[i] = v(xy[2 * i], xy[2 * i + 1]);
     int hc = convex_hull(n, hull.data(), 0.0);
     Shape s;
-    s.body = body; s.count = hc; s.r = radius;
+    s.body = body; s.kind = 0; s.count = hc; s.r = radius;
     s.local.resize(hc); s.world.resize(hc);
     for (int i = 0; i < hc; i++) {
         V a = hull[(i - 1 + hc) % hc], b = hull[i];
@@ -804,6 +849,25 @@ int cpo_poly_new(void* h, int body, int n, const double* xy, double radius) {
         sp->bodies[body].shapes.push_back(sid);
         shape_cache_data(sp, sp->shapes[sid]);
     }
+    return sid;
+}
+// pymunk.Segment(body, a, b, radius): cpSegmentShapeInit — n = rperp(normalize(b - a))
+int cpo_segment_new(void* h, int body, double ax, double ay, double bx, double by, double radius) {
+    Space* sp = (Space*)h;
+    Shape s;
+    s.body = body; s.kind = 1; s.count = 2; s.r = radius;
+    s.local.resize(2); s.world.resize(2);
+    V a = v(ax, ay), b = v(bx, by);
+    V n = vrperp(vnormalize(vsub(b, a)));
+    s.local[0].v0 = a; s.local[0].n = n;
+    s.local[1].v0 = b; s.local[1].n = vneg(n);
+    s.e = 0; s.u = 0; s.ctype = 0;
+    s.mi_m = 0; s.mi_i = moment_for_segment(1.0, a, b, radius); s.mi_cog = vlerp(a, b, 0.5);
+    s.mi_area = radius * (M_PI * radius + 2.0 * vdist(a, b));
+    sp->shapes.push_back(s);
+    int sid = (int)sp->shapes.size() - 1;
+    sp->bodies[body].shapes.push_back(sid);
+    shape_cache_data(sp, sp->shapes[sid]);
     return sid;
 }
 void cpo_shape_set_mass(void* h, int sid, double m) {
@@ -869,6 +933,54 @@ int cpo_shipice_substeps(void* h, int ship_body, int steps, double dt, double ya
         if (pos.x < 0 || pos.x > map_width) flags |= 2;
     }
     return flags;
+}
+// maze_NAMO_env.py:414-419 — the substep loop of one env step.  flags bit1 = boundary constraint
+// violated (robot x outside [0, width]); the wall flag is read with cpo_hits_13.
+int cpo_maze_substeps(void* h, int robot_body, int steps, double dt, double width) {
+    Space* sp = (Space*)h; int flags = 0;
+    for (int k = 0; k < steps; k++) {
+        space_step(sp, dt);
+        V pos = body_get_position(sp->bodies[robot_body]);
+        if (pos.x < 0 || pos.x > width) flags |= 2;
+    }
+    return flags;
+}
+long long cpo_hits_13(void* h) { return ((Space*)h)->hits_13; }
+// pymunk Space.point_query(p, max_dist, ShapeFilter()) != []  — cpSpacePointQuery: a shape is reported
+// when its signed surface distance (rounded radius included) is strictly below max_dist
+// (NearestPointQuery: `if(info.distance < context->maxDistance)`); the candidate filter is the
+// shape's AABB against the box p +- max(max_dist, 0).
+int cpo_point_query_any(void* h, double px, double py, double max_dist) {
+    Space* sp = (Space*)h; V p = v(px, py);
+    cpFloat md = std::fmax(max_dist, 0.0);
+    for (const Shape& s : sp->shapes) {
+        if (!(p.x - md <= s.bb_r && s.bb_l <= p.x + md && p.y - md <= s.bb_t && s.bb_b <= p.y + md)) continue;
+        cpFloat dist;
+        if (s.kind == 1) {          // cpSegmentShapePointQuery
+            V a = s.world[0].v0, b = s.world[1].v0;
+            V delta = vsub(a, b);
+            cpFloat t = fclamp01(vdot(delta, vsub(p, b)) / vlengthsq(delta));
+            V closest = vadd(b, vmult(delta, t));
+            dist = vdist(p, closest) - s.r;
+        } else {                    // cpPolyShapePointQuery
+            int count = s.count; cpFloat r = s.r;
+            V v0 = s.world[count - 1].v0; cpFloat minDist = INFINITY; V closestPoint = v(0, 0); bool outside = false;
+            for (int i = 0; i < count; i++) {
+                V v1 = s.world[i].v0;
+                if (vdot(s.world[i].n, vsub(p, v1)) > 0.0) outside = true;
+                V d2 = vsub(v0, v1);
+                cpFloat t = fclamp01(vdot(d2, vsub(p, v1)) / vlengthsq(d2));
+                V closest = vadd(v1, vmult(d2, t));
+                cpFloat dd = vdist(p, closest);
+                if (dd < minDist) { minDist = dd; closestPoint = closest; }
+                v0 = v1;
+            }
+            (void)closestPoint;
+            dist = (outside ? minDist : -minDist) - r;
+        }
+        if (dist < max_dist) return 1;
+    }
+    return 0;
 }
 void cpo_get_stats(void* h, long long* out11) { memcpy(out11, &((Space*)h)->st, sizeof(Stats)); }
 void cpo_reset_stats(void* h) { memset(&((Space*)h)->st, 0, sizeof(Stats)); }

@@ -64,6 +64,11 @@ def lib():
         L.cpo_get_state.argtypes = [C.c_void_p, dp]
         L.cpo_step.argtypes = [C.c_void_p, C.c_double]
         L.cpo_shipice_substeps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.cpo_segment_new.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.cpo_maze_substeps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.cpo_hits_13.argtypes = [C.c_void_p]
+        L.cpo_hits_13.restype = C.c_longlong
+        L.cpo_point_query_any.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         L.cpo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.cpo_reset_stats.argtypes = [C.c_void_p]
         L.cpo_get_arbiters.argtypes = [C.c_void_p, dp, C.c_int]
@@ -100,6 +105,20 @@ class Space:
     def add_poly(self, body, verts, radius):
         v = np.ascontiguousarray(verts, dtype=np.float64)
         return self.L.cpo_poly_new(self.h, body, v.shape[0], _dp(v), float(radius))
+
+    def add_segment(self, body, a, b, radius):
+        return self.L.cpo_segment_new(self.h, body, float(a[0]), float(a[1]), float(b[0]), float(b[1]), float(radius))
+
+    def maze_substeps(self, robot_body, steps, dt, width):
+        return self.L.cpo_maze_substeps(self.h, robot_body, int(steps), float(dt), float(width))
+
+    def hits_13(self):
+        """pre_solve calls of the (1, 3) handler so far (robot chassis vs wall)."""
+        return int(self.L.cpo_hits_13(self.h))
+
+    def point_query_any(self, p, max_dist):
+        """bool(space.point_query(p, max_dist, ShapeFilter()))"""
+        return bool(self.L.cpo_point_query_any(self.h, float(p[0]), float(p[1]), float(max_dist)))
 
     def set_density(self, shape, rho):
         self.L.cpo_shape_set_density(self.h, shape, float(rho))

@@ -111,3 +111,47 @@ class Emu:
 
     def env_bytes(self):
         return self.L.emu_env_bytes(self.h)
+
+
+class MazeEmu(Emu):
+    """Host emulation of the maze-NAMO kernels (default cfg of maze_version 1 or 2); layouts = list of centre lists."""
+
+    def __init__(self, n_envs, layouts, max_boxes=5, maze_version=1, settle_steps=1000):
+        L = C.CDLL(build())
+        L.emu_maze_create.restype = C.c_void_p
+        L.emu_maze_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        L.emu_env_bytes.restype = C.c_size_t
+        self.L = L
+        self.max_boxes = max_boxes
+        self.layouts = layouts
+        self.h = C.c_void_p(L.emu_maze_create(n_envs, max_boxes, maze_version, settle_steps))
+        nb = np.array([len(l) for l in layouts], dtype=np.int32)
+        cen = np.zeros((len(layouts), max_boxes, 2), dtype=np.float64)
+        for i, l in enumerate(layouts):
+            cen[i, :len(l)] = np.asarray(l, dtype=np.float64).reshape(-1, 2)
+        rc = L.emu_maze_load_layouts(self.h, C.c_int(len(layouts)), C.c_int(max_boxes), _ip(nb), _dp(cen))
+        assert rc == 0
+        self.grid = int((20.0 if maze_version == 2 else 15.0) * 16)
+
+    def bodies(self, env, layout=None):
+        sc = (C.c_int * 8)()
+        self.L.emu_get_scal2(self.h, C.c_int(env), sc)
+        out = np.zeros((int(sc[1]), 6), dtype=np.float64)
+        self.L.emu_get_bodies(self.h, C.c_int(env), _dp(out))
+        return out
+
+    def scal2(self, env):
+        sc = (C.c_int * 8)()
+        self.L.emu_get_scal2(self.h, C.c_int(env), sc)
+        return dict(robot=int(sc[0]), nbody=int(sc[1]), n_fixed=int(sc[2]), wall_hit=int(sc[3]), has_prev_dist=int(sc[4]))
+
+    def maps(self):
+        n = self.grid
+        wall = np.zeros((n, n), dtype=np.uint8); dn = np.zeros((n, n)); dr = np.zeros((n, n))
+        self.L.emu_maze_get_maps(self.h, wall.ctypes.data_as(C.c_void_p), _dp(dn), _dp(dr))
+        return wall, dn, dr
+
+    def render_obs(self, env, raw):
+        out = np.zeros((4, 192, 192), dtype=np.uint8)
+        self.L.emu_maze_render_obs(self.h, C.c_int(env), C.c_int(1 if raw else 0), out.ctypes.data_as(C.c_void_p))
+        return out

@@ -8,9 +8,9 @@
 #include <string>
 #include <vector>
 #include "../../benchpush_b200/csrc/host_tables.h"
-#include "../../benchpush_b200/csrc/shipice_env.cuh"
 #include "../../benchpush_b200/csrc/sim_batch.cuh"
 #include "../../benchpush_b200/csrc/raster.cuh"
+#include "../../benchpush_b200/csrc/maze_raster.cuh"
 #include "../../benchpush_b200/csrc/spfa.cuh"
 
 using namespace bp;
@@ -22,6 +22,8 @@ struct Emu {
     std::vector<unsigned char> term, trunc, succ; std::vector<int> status;
     StepOut out;
     ObsParams O; std::vector<unsigned char> raw_mode;
+    // maze-NAMO
+    MazeConfig mz; MazeObsParams MO; std::vector<uint8_t> wall_map; std::vector<double> dist_norm, dist_raw;
 };
 
 extern "C" {
@@ -57,7 +59,7 @@ int emu_load_layouts(void* h, int n_layouts, const int32_t* n_floes, const int32
     HostLayouts& H = e->H;
     e->T.lv = H.lv.data(); e->T.ln = H.ln.data(); e->T.nv = H.nv.data(); e->T.rad = H.rad.data(); e->T.rbound = H.rbound.data();
     e->T.minv = H.minv.data(); e->T.iinv = H.iinv.data(); e->T.cog = H.cog.data(); e->T.mat_e = H.mat_e.data();
-    e->T.mat_u = H.mat_u.data(); e->T.init = H.init.data(); e->T.nbody = H.nbody.data();
+    e->T.mat_u = H.mat_u.data(); e->T.init = H.init.data(); e->T.nbody = H.nbody.data(); e->T.robot0 = H.robot0.data();
     e->O.n_robot_raw = n_ship_verts;
     for (int i = 0; i < 2 * n_ship_verts; i++) e->O.robot_raw[i] = ship_verts[i];
     return 0;
@@ -164,5 +166,89 @@ void emu_spfa(const uint8_t* map, int H, int W, int si, int sj, float* dist, int
     spfa_block(S, map, H, W, si, sj, dist, parents, scratch.data(), scratch.data() + (size_t)H * W, scratch.data() + (size_t)2 * H * W);
 }
 size_t emu_env_bytes(void* h) { return ((Emu*)h)->env_bytes; }
+
+// ---------------------------------------------------------------- maze-NAMO (default config of maze_version v)
+void* emu_maze_create(int n_envs, int max_boxes, int maze_version, int settle_steps) {
+    Emu* e = new Emu();
+    MazeConfig& m = e->mz;
+    double W = maze_version == 2 ? 20.0 : 15.0, Lg = W;
+    m.width = W; m.length = Lg; m.settle_steps = settle_steps;
+    if (maze_version == 2) {
+        m.goal_x = m.goal_y = 3.33; m.start[0] = m.start[1] = 16.66; m.start[2] = 3 * M_PI / 2;
+        const double w[6][4] = {{0, 0, W, 0}, {0, 0, 0, Lg}, {W, 0, W, Lg}, {0, Lg, W, Lg}, {W / 3, 0, W / 3, 2 * Lg / 3}, {2 * W / 3, Lg, 2 * W / 3, Lg / 3}};
+        memcpy(m.walls, w, sizeof(w));
+    } else {
+        m.goal_x = m.goal_y = 3.75; m.start[0] = 11.25; m.start[1] = 3.75; m.start[2] = M_PI / 2;
+        const double w[6][4] = {{0, 0, W, 0}, {0, 0, 0, Lg}, {W, 0, W, Lg}, {0, Lg, W, Lg}, {2 * W / 2, Lg, 2 * W / 2, 5}, {W / 2, 0, W / 2, Lg - Lg / 3}};
+        memcpy(m.walls, w, sizeof(w));
+    }
+    m.n_walls = 6;
+    static const double rv[] = {0.7, -0.5, 0.55, -0.6, -0.55, -0.6, -0.7, -0.5, -0.7, 0.5, -0.55, 0.6, 0.55, 0.6, 0.7, 0.5};
+    m.n_robot_verts = 8; memcpy(m.robot_verts, rv, sizeof(rv));
+    static const double wv[4][8] = {{0.2, 0.6, 0.2, 0.7, 0.5, 0.7, 0.55, 0.6}, {0.2, -0.7, 0.2, -0.6, 0.55, -0.6, 0.55, -0.7},
+                                    {-0.2, 0.6, -0.2, 0.7, -0.55, 0.7, -0.55, 0.6}, {-0.2, -0.6, -0.2, -0.7, -0.55, -0.7, -0.55, -0.6}};
+    m.n_wheels = 4;
+    for (int w = 0; w < 4; w++) { m.wheel_nv[w] = 4; memcpy(m.wheel_verts + 16 * w, wv[w], sizeof(wv[w])); }
+    e->d.NB = m.n_walls + max_boxes + 1 + m.n_wheels;
+    e->d.PMAX = e->d.NB * (e->d.NB - 1) / 2 + 8; e->d.LMAX = e->d.PMAX < 256 ? e->d.PMAX : 256; if (e->d.LMAX < 64) e->d.LMAX = 64;
+    e->d.n_envs = n_envs; e->d.n_layouts = 0;
+    e->P = make_maze_params(m);
+    int H = 0, Wd = 0;
+    build_maze_maps(m, &H, &Wd, e->wall_map, e->dist_norm, e->dist_raw);
+    e->P.dist_map = e->dist_norm.data(); e->P.dist_h = H; e->P.dist_w = Wd;
+    e->MO.grid_h = H; e->MO.grid_w = Wd; e->MO.scale = (double)m.m_to_pix_scale; e->MO.n_robot_raw = m.n_robot_verts;
+    memcpy(e->MO.robot_raw, m.robot_verts, sizeof(double) * 2 * m.n_robot_verts);
+    e->MO.wall_map = e->wall_map.data(); e->MO.dist_map = e->dist_norm.data();
+    e->env_bytes = env_mem_size(e->d);
+    e->mem.assign(e->env_bytes * n_envs, 0);
+    e->reward.resize(n_envs); e->state.resize(3 * n_envs); e->pose.resize(3 * n_envs); e->total_work.resize(n_envs);
+    e->coll.resize(n_envs); e->scoll.resize(n_envs); e->distr.resize(n_envs);
+    e->term.resize(n_envs); e->trunc.resize(n_envs); e->succ.resize(n_envs); e->status.resize(n_envs);
+    e->out.reward = e->reward.data(); e->out.terminated = e->term.data(); e->out.truncated = e->trunc.data();
+    e->out.state = e->state.data(); e->out.pose = e->pose.data(); e->out.total_work = e->total_work.data();
+    e->out.collision_reward = e->coll.data(); e->out.scaled_collision_reward = e->scoll.data(); e->out.dist_reward = e->distr.data();
+    e->out.trial_success = e->succ.data(); e->out.status = e->status.data();
+    return e;
+}
+int emu_maze_load_layouts(void* h, int n_layouts, int max_boxes, const int32_t* n_boxes, const double* centres) {
+    Emu* e = (Emu*)h;
+    std::string err = build_maze_layouts(e->H, n_layouts, max_boxes, n_boxes, centres, e->mz);
+    if (!err.empty()) { fprintf(stderr, "emu_maze_load_layouts: %s\n", err.c_str()); return 1; }
+    e->d.n_layouts = n_layouts;
+    HostLayouts& H = e->H;
+    e->T.lv = H.lv.data(); e->T.ln = H.ln.data(); e->T.nv = H.nv.data(); e->T.rad = H.rad.data(); e->T.rbound = H.rbound.data();
+    e->T.minv = H.minv.data(); e->T.iinv = H.iinv.data(); e->T.cog = H.cog.data(); e->T.mat_e = H.mat_e.data();
+    e->T.mat_u = H.mat_u.data(); e->T.init = H.init.data(); e->T.nbody = H.nbody.data(); e->T.robot0 = H.robot0.data();
+    return 0;
+}
+void emu_maze_get_maps(void* h, uint8_t* wall, double* dist_norm, double* dist_raw) {
+    Emu* e = (Emu*)h;
+    memcpy(wall, e->wall_map.data(), e->wall_map.size());
+    memcpy(dist_norm, e->dist_norm.data(), e->dist_norm.size() * 8);
+    memcpy(dist_raw, e->dist_raw.data(), e->dist_raw.size() * 8);
+}
+void emu_maze_render_obs(void* h, int env, int raw, unsigned char* out) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    LayoutView L = layout_view(e->T, e->d, ev.sc->layout);
+    static MazeObsSmem S;
+    int r = ev.sc->robot;
+    V2 o = body_origin(ev, L, r);
+    int first = 0;
+    while (first < L.robot0 && L.nv[first] == 2) first++;
+    int n_obst = L.robot0 - first;
+    if (raw) {
+        size_t base = (size_t)ev.sc->layout * e->d.NB + first;
+        render_maze_obs(S, e->MO, n_obst, e->H.rawv.data() + base * VMAX * 2, VMAX * 2, e->H.rawn.data() + base, o.x, o.y, ev.body[r].pa, out);
+    } else {
+        render_maze_obs(S, e->MO, n_obst, ev.wv + (size_t)first * VMAX * 2, VMAX * 2, L.nv + first, o.x, o.y, ev.body[r].pa, out);
+    }
+}
+int emu_get_scal2(void* h, int env, int* o) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    o[0] = ev.sc->robot; o[1] = ev.sc->nbody; o[2] = ev.sc->n_fixed; o[3] = ev.sc->wall_hit; o[4] = ev.sc->has_prev_dist;
+    return 0;
+}
 
 }  // extern "C"

@@ -79,9 +79,90 @@ def make_pins():
     np.savez_compressed(os.path.join(GOLD, "shipice_oracle_pins.npz"), **out)
 
 
+MAZE_LAYOUTS = [[[11.3, 6.0], [11.0, 9.5], [9.4, 12.4], [5.0, 12.6], [3.6, 8.0]],      # obstacles on the way to the goal
+                [[13.6, 5.0], [13.9, 8.0], [8.8, 11.2], [6.5, 11.5], [3.8, 6.0]]]      # obstacles next to the walls
+MAZE_WAYPOINTS = [(11.25, 12.2), (3.75, 12.4), (3.75, 3.75)]
+
+
+def maze_scripted_action(pose, wi, k, ep):
+    """Heading controller towards the waypoints (test driver only): returns (action, waypoint index)."""
+    import math
+    px, py, pa = pose
+    if ep == 1 and k < 40:
+        tx, ty = 14.0, 8.0                      # push an obstacle into the right wall, then hit the wall
+    else:
+        tx, ty = MAZE_WAYPOINTS[wi]
+        if math.hypot(tx - px, ty - py) < 1.0 and wi < len(MAZE_WAYPOINTS) - 1:
+            wi += 1
+            tx, ty = MAZE_WAYPOINTS[wi]
+    err = math.atan2(ty - py, tx - px) - pa
+    err = (err + math.pi) % (2 * math.pi) - math.pi
+    a = float(np.float32(np.clip(err / (0.8 * (math.pi / 2) / 15), -1, 1)))
+    return a, wi
+
+
+def make_maze():
+    """maze_golden.npz: (a) PINNED third-party outputs — scipy.ndimage.rotate(order=1) and scipy.special.sindg/cosdg
+    of the scipy in this image; (b) trajectory pins of the (unpinned) maze oracle with the portable cos/sin
+    (bit-reproducible on every machine): recorded actions, per-step rows, final states and observations."""
+    from scipy import special
+    from scipy.ndimage import rotate
+    from benchpush_b200.layouts import generate_maze_layouts
+    from oracle import cpo
+    from oracle.maze_oracle import MazeNamoOracleEnv
+    out = {}
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.uniform(-720, 720, 4000), np.arange(-360, 361, 15.0)])
+    out["dg_x"] = xs; out["dg_sin"] = special.sindg(xs); out["dg_cos"] = special.cosdg(xs)
+    for k, (n, binary, cval) in enumerate([(64, True, 0.0), (48, False, 1.0), (96, True, 0.0)]):
+        img = (rng.random((n, n)) < 0.35).astype(np.float64) if binary else rng.random((n, n))
+        ang = float(rng.uniform(-200, 200))
+        out["rot%d_in" % k] = img.astype(np.float32) if False else img
+        out["rot%d_angle" % k] = np.array([ang, cval])
+        out["rot%d_out" % k] = rotate(img, ang, reshape=False, cval=cval, order=1)
+    layouts = [list(l) for l in MAZE_LAYOUTS] + generate_maze_layouts(2, seed=5)
+    out["layouts"] = np.array(layouts, dtype=np.float64)
+    cpo.set_portable_trig(True)
+    try:
+        env = MazeNamoOracleEnv(layouts=layouts, order_mode=1)
+        for ep in range(len(layouts)):
+            obs, info = env.reset()
+            out["ep%d_reset_obs" % ep] = obs
+            out["ep%d_reset_state" % ep] = env.space.state()
+            wi = 0
+            arng = np.random.default_rng(100 + ep)
+            actions, rows = [], []
+            for k in range(260):
+                if ep < 2:
+                    a, wi = maze_scripted_action(env.robot_pose(), wi, k, ep)
+                else:
+                    a = float(np.float32(arng.uniform(-1, 1)))
+                obs, r, term, _, info = env.step(a)
+                st = env.space.state()
+                actions.append(a)
+                rows.append([st[11, 0], st[11, 1], st[11, 2], r, info["total_work"], float(term), float(info["trial_success"]),
+                             info["dist increment reward"], st[6:11, 0].sum(), st[6:11, 1].sum(), st[6:11, 2].sum()])
+                if k in (10, 60):
+                    out["ep%d_obs_k%d" % (ep, k)] = obs
+                if term:
+                    break
+            out["ep%d_actions" % ep] = np.array(actions)
+            out["ep%d_rows" % ep] = np.array(rows)
+            out["ep%d_final_state" % ep] = env.space.state()
+            out["ep%d_final_obs" % ep] = obs
+    finally:
+        cpo.set_portable_trig(False)
+    np.savez_compressed(os.path.join(GOLD, "maze_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "maze":
+        make_maze()
+        print("maze fixtures written to", GOLD)
+        sys.exit(0)
     make_layouts()
     make_spfa()
     make_pins()
+    make_maze()
     print("golden fixtures written to", GOLD)
