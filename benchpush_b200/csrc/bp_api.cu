@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepAr
 __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step(StepArgs a) {
     __shared__ BatchShared SH[4];
     BatchShared& S = SH[threadIdx.x >> 5];
+    load_shared_offsets(a.C->off);
     for (;;) {
         int env0 = 0;
         if ((threadIdx.x & 31) == 0) env0 = atomicAdd(a.counter, BK);

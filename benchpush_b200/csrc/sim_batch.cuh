@@ -52,7 +52,7 @@ BP_DEV int find_env(const int* off, int idx) {
 // Touching / not-touching outcome for ONE lane's pair (no warp-collective inside: lanes of one call
 // may belong to different envs).  Same state transitions as pair_finish (cpArbiterUpdate).
 BP_DEVNI void pair_finish_lane(const DevConst* C, char* base, const LayoutView& L, int i, int p, int a, int b, const Closest& pts) {
-    EnvView ev = view_at(base, C->off);
+    EnvView ev = view_s(base);
     EnvScal* sc = ev.sc;
     PairRec* pr = ev.pair[sc->cur];
     Manifold m; m.count = 0;
@@ -65,6 +65,7 @@ BP_DEVNI void pair_finish_lane(const DevConst* C, char* base, const LayoutView& 
         int k = bp_atomic_add(&sc->n_free, -1) - 1;
         if (k >= 0) {
             slot = ev.free_stack[k];
+            bp_atomic_max(&sc->slot_hw, slot + 1);
             pr[p].live = slot;
             SlotRec& S = ev.slot[slot];
             S.pair = p; S.a = a; S.b = b; S.cnt = 0; S.touch = 0; S.first = 1;
@@ -168,7 +169,7 @@ BP_DEV void batch_flush_epa(const DevConst* C, BatchShared& S, int n2) {
             unsigned ent = S.q2[q];
             int e = (int)(ent >> 24), i = (int)(ent & 0xFFFFFF);
             char* base = S.base[e];
-            EnvView ev = view_at(base, C->off);
+            EnvView ev = view_s(base);
             EnvScal* sc = ev.sc;
             const LayoutView& L = S.L[e];
             PairRec* pr = ev.pair[sc->cur];
@@ -190,7 +191,7 @@ BP_DEVNI void batch_build_worklist(const DevConst* C, BatchShared& S) {
     for (int t = lane; t < BK * BCOL; t += BP_NL) {
         int e = t / BCOL, c = t % BCOL, v = 0;
         if (S.base[e]) {
-            EnvView ev = view_at(S.base[e], C->off);
+            EnvView ev = view_s(S.base[e]);
             if (c < ev.sc->n_colours) v = ev.col_start[c + 1] - ev.col_start[c];
         }
         S.ccnt[e][c] = v;
@@ -225,7 +226,7 @@ BP_DEVNI void batch_build_worklist(const DevConst* C, BatchShared& S) {
     const int tot = S.off_ord[BK];
     for (int j = lane; j < tot; j += BP_NL) {
         int e = find_env(S.off_ord, j), pos = j - S.off_ord[e];
-        EnvView ev = view_at(S.base[e], C->off);
+        EnvView ev = view_s(S.base[e]);
         int nc = ev.sc->n_colours, c = 0;
         while (c + 1 < nc && ev.col_start[c + 1] <= pos) c++;
         S.wl[S.cpre[e][c] + (pos - ev.col_start[c])] = ((unsigned)e << 16) | (unsigned)ev.order[pos];
@@ -253,7 +254,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
         for (int i = lane; i < tot; i += BP_NL) {
             int e = find_env(S.off_awake, i), k = i - S.off_awake[e];
             char* base = S.base[e];
-            EnvView ev = view_at(base, C->off);
+            EnvView ev = view_s(base);
             EnvScal* sc = ev.sc;
             const LayoutView& L = S.L[e];
             int b = ev.awake[k];
@@ -271,7 +272,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
                 double mg = body_margin(P, sc, b);
                 BBox c = ev.bb[b], o = ev.b0[b];
                 if (c.l < o.l - mg || c.r > o.r + mg || c.b < o.b - mg || c.t > o.t + mg) sc->rebuild = 1;
-                ev.moved_step[b] = 1;
+                ev.moved_step[b] = 1; ev.mvrb[b] = 1;
                 R.bx = 0.0; R.by = 0.0; R.bw = 0.0;
             }
             ev.moved[b] = mv ? 1 : 0;
@@ -285,8 +286,8 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
     for (int e = 0; e < BK; e++) {
         char* base = S.base[e];
         if (base && ((const EnvScal*)base)->rebuild) {
-            EnvView ev = view_at(base, C->off);
-            rebuild_pairs(ev, P, d, true);
+            EnvView ev = view_s(base);
+            rebuild_pairs_inc(ev, P, d);
             build_apairs(ev);
         }
     }
@@ -308,7 +309,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
                 bool pass = false; unsigned ent = 0;
                 if (i < total) {
                     int e = find_env(S.off_ap, i), k = i - S.off_ap[e];
-                    EnvView ev = view_at(S.base[e], C->off);
+                    EnvView ev = view_s(S.base[e]);
                     pass = ev.sc->G >= ev.ap_gate[k];
                     ent = ((unsigned)e << 24) | (unsigned)k;
                 }
@@ -326,7 +327,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
                     ent = S.q0[q];
                     int e = (int)(ent >> 24), i = (int)(ent & 0xFFFFFF);
                     char* base = S.base[e];
-                    EnvView ev = view_at(base, C->off);
+                    EnvView ev = view_s(base);
                     EnvScal* sc = ev.sc;
                     const LayoutView& L = S.L[e];
                     PairRec* pr = ev.pair[sc->cur];
@@ -367,7 +368,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
                     ent = S.q1[q];
                     int e = (int)(ent >> 24), i = (int)(ent & 0xFFFFFF);
                     char* base = S.base[e];
-                    EnvView ev = view_at(base, C->off);
+                    EnvView ev = view_s(base);
                     EnvScal* sc = ev.sc;
                     const LayoutView& L = S.L[e];
                     PairRec* pr = ev.pair[sc->cur];
@@ -396,7 +397,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
         if (!base) continue;
         const EnvScal* sc = (const EnvScal*)base;
         if (sc->any_wake || sc->n_cached > 0 || sc->dirty) {
-            EnvView ev = view_at(base, C->off);
+            EnvView ev = view_s(base);
             if (sc->any_wake) wake_closure_scan(ev, S.L[e], d);
             if (sc->n_cached > 0) expire_cached(ev, P, d);
             if (sc->dirty) { build_order(ev, S.L[e], d); if (lane == 0) S.wl_valid = 0; }
@@ -408,7 +409,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
     if (S.n_items < 0) {
         // the merged list does not fit: solve env by env (same arithmetic, same order)
         for (int e = 0; e < BK; e++)
-            if (S.base[e]) { EnvView ev = view_at(S.base[e], C->off); solve_env(ev, S.L[e], P, dt, prev_dt); }
+            if (S.base[e]) { EnvView ev = view_s(S.base[e]); solve_env(ev, S.L[e], P, dt, prev_dt); }
         return;
     }
     // ---- 3. prestep over all arbiters of the batch
@@ -416,7 +417,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
     for (int j = lane; j < n_items; j += BP_NL) {
         unsigned ent = S.wl[j];
         int e = (int)(ent >> 16);
-        arb_prestep(view_at(S.base[e], C->off), S.L[e], P, (int)(ent & 0xFFFF));
+        arb_prestep(view_s(S.base[e]), S.L[e], P, (int)(ent & 0xFFFF));
     }
     // ---- 4. velocity update of the awake dynamic bodies (the awake lists may have grown)
     if (lane == 0) {
@@ -429,7 +430,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
         const int tot = S.off_awake[BK];
         for (int i = lane; i < tot; i += BP_NL) {
             int e = find_env(S.off_awake, i), k = i - S.off_awake[e];
-            EnvView ev = view_at(S.base[e], C->off);
+            EnvView ev = view_s(S.base[e]);
             int b = ev.awake[k];
             if (body_dynamic(S.L[e], b)) {
                 BodyRec& R = ev.body[b];
@@ -445,7 +446,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
         for (int j = c0 + lane; j < c1; j += BP_NL) {
             unsigned ent = S.wl[j];
             int e = (int)(ent >> 16);
-            arb_warm(view_at(S.base[e], C->off), S.L[e], (int)(ent & 0xFFFF), dt_coef);
+            arb_warm(view_s(S.base[e]), S.L[e], (int)(ent & 0xFFFF), dt_coef);
         }
         bp_wsync();
     }
@@ -455,7 +456,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
             for (int j = c0 + lane; j < c1; j += BP_NL) {
                 unsigned ent = S.wl[j];
                 int e = (int)(ent >> 16);
-                arb_solve(view_at(S.base[e], C->off), S.L[e], (int)(ent & 0xFFFF));
+                arb_solve(view_s(S.base[e]), S.L[e], (int)(ent & 0xFFFF));
             }
             bp_wsync();
         }
@@ -463,7 +464,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
     // ---- 6. arbiters solved this step are NORMAL next step
     for (int j = lane; j < n_items; j += BP_NL) {
         unsigned ent = S.wl[j];
-        view_at(S.base[ent >> 16], C->off).slot[ent & 0xFFFF].first = 0;
+        view_s(S.base[ent >> 16]).slot[ent & 0xFFFF].first = 0;
     }
     for (int e = lane; e < BK; e += BP_NL)
         if (S.base[e]) { EnvScal* sc = (EnvScal*)S.base[e]; sc->stat_substeps++; sc->stat_live_sum += sc->n_order; sc->stat_awake_sum += sc->n_awake; }
@@ -483,7 +484,7 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
         char* base = nullptr;
         if (env < d.n_envs && !(mask && !mask[env])) {
             base = mem + env_bytes * (size_t)env;
-            EnvView ev = view_at(base, C->off);
+            EnvView ev = view_s(base);
             EnvScal* sc = ev.sc;
             if (auto_reset && sc->done) {
                 int ep = sc->episode + 1, first = sc->first_layout;
@@ -510,7 +511,7 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
             batch_substep(C, S, P.dt, P.dt);
             for (int e = lane; e < BK; e += BP_NL)
                 if (S.base[e]) {
-                    EnvView ev = view_at(S.base[e], C->off);
+                    EnvView ev = view_s(S.base[e]);
                     S.flags[e] |= (unsigned char)env_substep_checks(ev, S.L[e], P, ev.sc->robot);
                 }
             bp_wsync();
@@ -519,7 +520,7 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
     for (int e = 0; e < BK; e++) {
         char* base = S.base[e];
         if (!base) continue;
-        EnvView ev = view_at(base, C->off);
+        EnvView ev = view_s(base);
         int env = S.env_id[e];
         env_step_finish(ev, S.L[e], P, d, env, out, (int)S.flags[e]);
         if (lane == 0) { ev.sc->done = out.terminated[env]; ev.sc->obs_raw = 0; }

@@ -98,6 +98,7 @@ struct EnvScal {
     double G;                     // monotone accumulator: bounds the growth of D[a] + D[b] of ANY pair
     int obs_raw, n_fixed, wall_hit, has_prev_dist;   // n_fixed: bodies that are not dynamic (robot shapes + walls)
     double prev_dist;                                 // maze: distance-map value at the previous step (prev_dist_value)
+    int slot_hw, pad_hw;          // every arbiter slot >= slot_hw is free: scans over the slots stop there
     double total_work;
     long long stat_gjk, stat_pairs_eval, stat_live_sum, stat_awake_sum, stat_recolour, stat_rebuild, stat_substeps;
     long long stat_epa, stat_skipped, t_phase[8];
@@ -143,6 +144,7 @@ struct EnvView {
     double *cenx, *ceny, *area, *tmp;                                        // [NB] |centroid|, area at last env step; scratch
     int* awake;                                                              // [NB]
     unsigned char *is_awake, *moved, *moved_step, *act;                      // [NB]
+    unsigned char* mvrb;                                                     // [NB] AABB changed since the last neighbour-list build
     unsigned long long* colmask;                                             // [NB]
     PairRec* pair[2];                                                        // [PMAX] double-buffered over rebuilds
     int *adj_start, *adj, *deg;                                              // [NB+1], [2*PMAX], [NB]
@@ -186,6 +188,7 @@ BP_HD EnvView carve_env(char* base, const Dims& d, size_t* total) {
     TAKE(v.livemask, unsigned, (P / 32 + 1) * 4)
     TAKE(v.free_stack, int, Lm * 4) TAKE(v.order, int, Lm * 4) TAKE(v.colour, int, Lm * 4)
     TAKE(v.col_start, int, (MAXCOL + 1) * 4)
+    TAKE(v.mvrb, unsigned char, NB)
 #undef TAKE
     if (total) *total = (size_t)(p - base);
     return v;
@@ -203,8 +206,8 @@ static inline size_t env_mem_size(const Dims& d) { size_t t = 0; carve_env((char
     X(14, act, unsigned char) X(15, colmask, unsigned long long) X(16, pair[0], PairRec) X(17, pair[1], PairRec) \
     X(18, adj_start, int) X(19, adj, int) X(20, deg, int) X(21, queue, int) X(22, queue0, int) X(23, apairs, int) \
     X(24, ap_gate, double) X(25, queue2, int) X(26, qhint, unsigned) X(27, livemask, unsigned)                   \
-    X(28, free_stack, int) X(29, order, int) X(30, colour, int) X(31, col_start, int)
-struct EnvOff { unsigned o[32]; };
+    X(28, free_stack, int) X(29, order, int) X(30, colour, int) X(31, col_start, int) X(32, mvrb, unsigned char)
+struct EnvOff { unsigned o[33]; };
 static inline EnvOff env_offsets(const Dims& d) {
     EnvOff O;
     EnvView v = carve_env((char*)0, d, nullptr);
@@ -220,6 +223,21 @@ BP_DEV EnvView view_at(char* base, const EnvOff& O) {
 #undef X
     return v;
 }
+
+// The offsets again, in shared memory (one copy per thread block, filled at kernel entry by
+// load_shared_offsets): device code of the batched hot path forms `base + bp_soff.o[i]` with an LDS at
+// a fixed address instead of a global load through the DevConst pointer.
+#if defined(__CUDACC__) && !defined(BP_HOST_EMU)
+__shared__ EnvOff bp_soff;
+BP_DEV void load_shared_offsets(const EnvOff& O) {
+    for (int i = threadIdx.x; i < (int)(sizeof(EnvOff) / sizeof(unsigned)); i += blockDim.x) bp_soff.o[i] = O.o[i];
+    __syncthreads();
+}
+#else
+static EnvOff bp_soff;
+static inline void load_shared_offsets(const EnvOff& O) { bp_soff = O; }
+#endif
+BP_DEV EnvView view_s(char* base) { return view_at(base, bp_soff); }
 
 struct LayoutView {
     const double *lv, *ln, *rad, *rbound, *minv, *iinv, *cog, *mat_e, *mat_u, *init;
@@ -247,6 +265,7 @@ BP_DEV LayoutView layout_view(const LayoutTab& T, const Dims& d, int l) {
 
 // ------------------------------------------------------------------ small vector helpers
 struct V2 { double x, y; };
+struct alignas(16) D2 { double x, y; };      // one vertex in memory: moved with a single 128-bit load / store
 BP_DEV V2 mk(double x, double y) { V2 r; r.x = x; r.y = y; return r; }
 BP_DEV V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
 BP_DEV V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
@@ -274,12 +293,15 @@ BP_DEV void refresh_body_impl(const EnvView& ev, const LayoutView& L, int b) {
     double* wv = ev.wv + (size_t)b * VMAX * 2;
     int n = L.nv[b];
     double l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
+    const D2* lv2 = (const D2*)lv;
+    D2* wv2 = (D2*)wv;
 #pragma unroll 2
     for (int i = 0; i < n; i++) {
-        double x = lv[2 * i], y = lv[2 * i + 1];
-        double wx = c * x + ms * y + tx;
-        double wy = s * x + c * y + ty;
-        wv[2 * i] = wx; wv[2 * i + 1] = wy;
+        D2 q = lv2[i];
+        double wx = c * q.x + ms * q.y + tx;
+        double wy = s * q.x + c * q.y + ty;
+        D2 w; w.x = wx; w.y = wy;
+        wv2[i] = w;
         l = fmin(l, wx); r = fmax(r, wx); bt = fmin(bt, wy); tp = fmax(tp, wy);
     }
     double rad = L.rad[b];
@@ -288,7 +310,7 @@ BP_DEV void refresh_body_impl(const EnvView& ev, const LayoutView& L, int b) {
 }
 BP_DEVNI void refresh_body(const EnvView& ev, const LayoutView& L, int b) { refresh_body_impl(ev, L, b); }
 // same, for callers that hold only the env block (batched hot path: only the touched arrays are addressed)
-BP_DEVNI void refresh_body_b(const DevConst* C, char* base, const LayoutView& L, int b) { refresh_body_impl(view_at(base, C->off), L, b); }
+BP_DEVNI void refresh_body_b(const DevConst* C, char* base, const LayoutView& L, int b) { refresh_body_impl(view_s(base), L, b); }
 // body position (pymunk Body.position = local origin in world space)
 BP_DEV V2 body_origin(const EnvView& ev, const LayoutView& L, int b) {
     double c = ev.body[b].rc, s = ev.body[b].rs;
@@ -305,15 +327,17 @@ struct Poly { const double* v; int n; };
 BP_DEVNI int support_index(const Poly& P, V2 n) {
     // a 2-vertex shape is a cpSegmentShape (walls): SegmentSupportPoint returns ta only when strictly greater
     if (P.n == 2) return (P.v[0] * n.x + P.v[1] * n.y > P.v[2] * n.x + P.v[3] * n.y) ? 0 : 1;
+    const D2* v = (const D2*)P.v;
     double mx = -INFINITY; int idx = 0;
 #pragma unroll 4
     for (int i = 0; i < P.n; i++) {
-        double d = P.v[2 * i] * n.x + P.v[2 * i + 1] * n.y;
+        D2 q = v[i];
+        double d = q.x * n.x + q.y * n.y;
         if (d > mx) { mx = d; idx = i; }
     }
     return idx;
 }
-BP_DEV V2 pvert(const Poly& P, int i) { return mk(P.v[2 * i], P.v[2 * i + 1]); }
+BP_DEV V2 pvert(const Poly& P, int i) { D2 q = ((const D2*)P.v)[i]; return mk(q.x, q.y); }
 BP_DEV MPoint mpoint(const Poly& A, const Poly& B, int ia, int ib) {
     MPoint m; m.ab = pvert(B, ib) - pvert(A, ia); m.id = (unsigned)((ia & 0xFF) << 8 | (ib & 0xFF)); return m;
 }
@@ -487,7 +511,7 @@ BP_DEV void make_manifold_impl(const EnvView& ev, const LayoutView& L, int a, in
 
 BP_DEVNI void make_manifold(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) { make_manifold_impl(ev, L, a, b, pts, m); }
 BP_DEVNI void make_manifold_b(const DevConst* C, char* base, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {
-    make_manifold_impl(view_at(base, C->off), L, a, b, pts, m);
+    make_manifold_impl(view_s(base), L, a, b, pts, m);
 }
 
 }  // namespace bp

@@ -20,60 +20,21 @@ BP_DEV bool body_dynamic(const LayoutView& L, int b) { return L.minv[b] != 0.0; 
 #endif
 
 // ------------------------------------------------------------------ neighbour list
-// Rebuild the candidate pair list from the current AABBs (sorted by (i,j), i<j; ballot compaction
-// keeps the order), carry per-pair state (GJK hint, flags, skip bound, live slot) over from the
-// previous list, rebuild the adjacency and the live bitmask.
-BP_DEVNI void rebuild_pairs(const EnvView& ev, const SimParams& P, const Dims& d, bool carry) {
+// Tail of a neighbour-list build: np_ = ev.pair[nxt][0..np) holds the new list (sorted by key, per-pair
+// state already carried over).  Re-links the live arbiter slots, frees the slots whose pair fell out
+// of the list, rebuilds the adjacency and the live bitmask, clears the moved-since-build flags.
+BP_DEV void rebuild_finish(const EnvView& ev, const Dims& d, int np, int nxt, bool carry) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     const int nb = sc->nbody;
-    const int cur = sc->cur, nxt = carry ? 1 - cur : cur;
-    const int old_n = carry ? sc->n_pairs : 0;
     PairRec* np_ = ev.pair[nxt];
-    for (int b = lane; b < nb; b += BP_NL) {
-        ev.b0[b] = ev.bb[b];
-        ev.deg[b] = 0;
-    }
+    const int hw = sc->slot_hw;
+    for (int s = lane; s < hw; s += BP_NL) ev.slot[s].keep = 0;
+    for (int b = lane; b < nb; b += BP_NL) { ev.deg[b] = 0; ev.mvrb[b] = 0; }
     bp_wsync();
-    int np = 0;
-    bool overflow = false;
-    for (int i = 0; i < nb - 1; i++) {
-        double mi = body_margin(P, sc, i);
-        BBox bi = ev.b0[i];
-        double il = bi.l - mi, ib = bi.b - mi, ir = bi.r + mi, it = bi.t + mi;
-        for (int base = i + 1; base < nb; base += BP_NL) {
-            int j = base + lane;
-            bool hit = false;
-            if (j < nb) {
-                double mj = body_margin(P, sc, j);
-                BBox bj = ev.b0[j];
-                hit = (il <= bj.r + mj && bj.l - mj <= ir && ib <= bj.t + mj && bj.b - mj <= it);
-            }
-            int tot; int rk = bp_wrank(hit, &tot);
-            if (hit) {
-                if (np + rk < d.PMAX) np_[np + rk].key = pair_key(i, j); else overflow = true;
-            }
-            np += tot;
-        }
-    }
-    if (bp_wany(overflow)) { if (lane == 0) bp_atomic_or((unsigned*)&sc->status, ST_PAIR_OVERFLOW); }
-    if (np > d.PMAX) np = d.PMAX;
-    for (int s = lane; s < d.LMAX; s += BP_NL) ev.slot[s].keep = 0;
-    bp_wsync();
-    const PairRec* op = ev.pair[cur];
     for (int p = lane; p < np; p += BP_NL) {
         unsigned key = np_[p].key;
-        unsigned gj = 0; int lv = -1; unsigned fl = 0; double sk = 0.0;
-        if (carry) {
-            int lo = 0, hi = old_n - 1;
-            while (lo <= hi) {
-                int mid = (lo + hi) >> 1;
-                unsigned k = op[mid].key;
-                if (k == key) { gj = op[mid].gjk; lv = op[mid].live; fl = op[mid].flags & 1; sk = op[mid].skip; break; }
-                if (k < key) lo = mid + 1; else hi = mid - 1;
-            }
-        }
-        np_[p].gjk = gj; np_[p].live = lv; np_[p].flags = fl; np_[p].skip = sk;
+        int lv = np_[p].live;
         if (lv >= 0) { ev.slot[lv].pair = p; ev.slot[lv].keep = 1; }
         bp_atomic_add(&ev.deg[key >> 16], 1);
         bp_atomic_add(&ev.deg[key & 0xFFFF], 1);
@@ -81,9 +42,9 @@ BP_DEVNI void rebuild_pairs(const EnvView& ev, const SimParams& P, const Dims& d
     bp_wsync();
     if (carry) {
         // live slots whose pair fell out of the list (bodies now farther apart than the margins)
-        for (int base = 0; base < d.LMAX; base += BP_NL) {
+        for (int base = 0; base < hw; base += BP_NL) {
             int s = base + lane;
-            bool drop = (s < d.LMAX) && ev.slot[s].pair >= 0 && !ev.slot[s].keep;
+            bool drop = (s < hw) && ev.slot[s].pair >= 0 && !ev.slot[s].keep;
             int tot; int rk = bp_wrank(drop, &tot);
             int nf = sc->n_free;
             if (drop) {
@@ -111,13 +72,165 @@ BP_DEVNI void rebuild_pairs(const EnvView& ev, const SimParams& P, const Dims& d
         ev.adj[ev.adj_start[i] + bp_atomic_add(&ev.deg[i], 1)] = p;
         ev.adj[ev.adj_start[j] + bp_atomic_add(&ev.deg[j], 1)] = p;
     }
-    int words = d.PMAX / 32 + 1;
+    int words = carry ? (np > sc->n_pairs ? np : sc->n_pairs) / 32 + 1 : d.PMAX / 32 + 1;
     for (int w = lane; w < words; w += BP_NL) ev.livemask[w] = 0;
     bp_wsync();
-    for (int s = lane; s < d.LMAX; s += BP_NL)
+    for (int s = lane; s < hw; s += BP_NL)
         if (ev.slot[s].pair >= 0 && ev.slot[s].touch) bp_atomic_or(&ev.livemask[ev.slot[s].pair >> 5], 1u << (ev.slot[s].pair & 31));
     if (lane == 0) { sc->n_pairs = np; sc->cur = nxt; sc->rebuild = 0; sc->dirty = 1; sc->n_apairs = 0; sc->stat_rebuild++; }
     bp_wsync();
+}
+
+// Rebuild the candidate pair list from the current AABBs (sorted by (i,j), i<j; ballot compaction
+// keeps the order), carry per-pair state (GJK hint, flags, skip bound, live slot) over from the
+// previous list, rebuild the adjacency and the live bitmask.
+BP_DEVNI void rebuild_pairs(const EnvView& ev, const SimParams& P, const Dims& d, bool carry) {
+    EnvScal* sc = ev.sc;
+    const int lane = bp_lane();
+    const int nb = sc->nbody;
+    const int cur = sc->cur, nxt = carry ? 1 - cur : cur;
+    const int old_n = carry ? sc->n_pairs : 0;
+    PairRec* np_ = ev.pair[nxt];
+    for (int b = lane; b < nb; b += BP_NL) ev.b0[b] = ev.bb[b];
+    bp_wsync();
+    int np = 0;
+    bool overflow = false;
+    for (int i = 0; i < nb - 1; i++) {
+        double mi = body_margin(P, sc, i);
+        BBox bi = ev.b0[i];
+        double il = bi.l - mi, ib = bi.b - mi, ir = bi.r + mi, it = bi.t + mi;
+        for (int base = i + 1; base < nb; base += BP_NL) {
+            int j = base + lane;
+            bool hit = false;
+            if (j < nb) {
+                double mj = body_margin(P, sc, j);
+                BBox bj = ev.b0[j];
+                hit = (il <= bj.r + mj && bj.l - mj <= ir && ib <= bj.t + mj && bj.b - mj <= it);
+            }
+            int tot; int rk = bp_wrank(hit, &tot);
+            if (hit) {
+                if (np + rk < d.PMAX) np_[np + rk].key = pair_key(i, j); else overflow = true;
+            }
+            np += tot;
+        }
+    }
+    if (bp_wany(overflow)) { if (lane == 0) bp_atomic_or((unsigned*)&sc->status, ST_PAIR_OVERFLOW); }
+    if (np > d.PMAX) np = d.PMAX;
+    bp_wsync();
+    const PairRec* op = ev.pair[cur];
+    for (int p = lane; p < np; p += BP_NL) {
+        unsigned key = np_[p].key;
+        unsigned gj = 0; int lv = -1; unsigned fl = 0; double sk = 0.0;
+        if (carry) {
+            int lo = 0, hi = old_n - 1;
+            while (lo <= hi) {
+                int mid = (lo + hi) >> 1;
+                unsigned k = op[mid].key;
+                if (k == key) { gj = op[mid].gjk; lv = op[mid].live; fl = op[mid].flags & 1; sk = op[mid].skip; break; }
+                if (k < key) lo = mid + 1; else hi = mid - 1;
+            }
+        }
+        np_[p].gjk = gj; np_[p].live = lv; np_[p].flags = fl; np_[p].skip = sk;
+    }
+    bp_wsync();
+    rebuild_finish(ev, d, np, nxt, carry);
+}
+
+// The same list, built incrementally.  A pair of two bodies whose AABBs did not change since the last
+// build passes the margin test now iff it passed then, so only pairs with a moved endpoint (ev.mvrb,
+// set wherever a body integrates) are re-tested: |moved| x nbody box tests instead of nbody^2 / 2.
+// The surviving old pairs and the fresh ones are merged by key, so the result is the list
+// rebuild_pairs() would produce, entry for entry.  Falls back to the full build when many bodies moved.
+constexpr int INC_MAX_MOVED = 64, INC_MAX_FRESH = 512;
+BP_DEVNI void rebuild_pairs_inc(const EnvView& ev, const SimParams& P, const Dims& d) {
+    EnvScal* sc = ev.sc;
+    const int lane = bp_lane();
+    const int nb = sc->nbody;
+    const int cur = sc->cur, nxt = 1 - cur;
+    const int old_n = sc->n_pairs;
+    const PairRec* op = ev.pair[cur];
+    PairRec* np_ = ev.pair[nxt];
+    int* mlist = ev.queue;                       // moved bodies, ascending
+    unsigned* fresh = (unsigned*)ev.queue0;      // fresh keys in discovery order
+    unsigned* fsort = (unsigned*)ev.adj;         // fresh keys, ascending (the adjacency is rebuilt below)
+    int* srank = ev.adj + d.PMAX;                // [old_n + 1] survivors before old entry p
+    const int max_m = INC_MAX_MOVED < d.PMAX ? INC_MAX_MOVED : d.PMAX;
+    const int max_f = INC_MAX_FRESH < d.PMAX ? INC_MAX_FRESH : d.PMAX;
+    int nm = 0;
+    for (int base = 0; base < nb; base += BP_NL) {
+        int b = base + lane;
+        bool f = (b < nb) && ev.mvrb[b];
+        int tot; int rk = bp_wrank(f, &tot);
+        if (f && nm + rk < max_m) mlist[nm + rk] = b;
+        nm += tot;
+    }
+    bp_wsync();
+    if (nm > max_m || old_n + 1 > d.PMAX) { rebuild_pairs(ev, P, d, true); return; }
+    for (int k = lane; k < nm; k += BP_NL) { int b = mlist[k]; ev.b0[b] = ev.bb[b]; }
+    bp_wsync();
+    // fresh pairs: every pair with a moved endpoint that passes the margin test now
+    int nf = 0;
+    for (int k = 0; k < nm; k++) {
+        const int m = mlist[k];
+        double mm = body_margin(P, sc, m);
+        BBox bm = ev.b0[m];
+        double il = bm.l - mm, ib = bm.b - mm, ir = bm.r + mm, it = bm.t + mm;
+        for (int base = 0; base < nb; base += BP_NL) {
+            int x = base + lane;
+            bool hit = false;
+            if (x < nb && x != m && !(x < m && ev.mvrb[x])) {      // a pair of two moved bodies is emitted by the smaller id
+                double mx = body_margin(P, sc, x);
+                BBox bx = ev.b0[x];
+                hit = (il <= bx.r + mx && bx.l - mx <= ir && ib <= bx.t + mx && bx.b - mx <= it);
+            }
+            int tot; int rk = bp_wrank(hit, &tot);
+            if (hit && nf + rk < max_f) fresh[nf + rk] = (x < m) ? pair_key(x, m) : pair_key(m, x);
+            nf += tot;
+        }
+    }
+    bp_wsync();
+    if (nf > max_f) { rebuild_pairs(ev, P, d, true); return; }
+    // sort the fresh keys (all distinct): rank = number of smaller keys
+    for (int e = lane; e < nf; e += BP_NL) {
+        unsigned key = fresh[e];
+        int r = 0;
+        for (int q = 0; q < nf; q++) r += (fresh[q] < key) ? 1 : 0;
+        fsort[r] = key;
+    }
+    // survivors of the old list: neither endpoint moved
+    int ns = 0;
+    for (int base = 0; base < old_n; base += BP_NL) {
+        int p = base + lane;
+        int sv = 0;
+        if (p < old_n) { unsigned key = op[p].key; sv = (!ev.mvrb[key >> 16] && !ev.mvrb[key & 0xFFFF]) ? 1 : 0; }
+        int tot; int ex = bp_wscan_excl(sv, &tot);
+        if (p < old_n) srank[p] = sv ? (ns + ex) : -(ns + ex) - 1;
+        ns += tot;
+    }
+    if (lane == 0) srank[old_n] = -ns - 1;
+    bp_wsync();
+    const int np = ns + nf;
+    if (np > d.PMAX) { rebuild_pairs(ev, P, d, true); return; }
+    for (int p = lane; p < old_n; p += BP_NL) {
+        int sr = srank[p];
+        if (sr < 0) continue;
+        PairRec q = op[p];
+        int lo = 0, hi = nf;                       // fresh keys below q.key
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (fsort[mid] < q.key) lo = mid + 1; else hi = mid; }
+        q.flags &= 1u;
+        np_[sr + lo] = q;
+    }
+    for (int i = lane; i < nf; i += BP_NL) {
+        unsigned key = fsort[i];
+        int lo = 0, hi = old_n;                    // first old entry with key >= this key
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (op[mid].key < key) lo = mid + 1; else hi = mid; }
+        int sr = srank[lo]; if (sr < 0) sr = -sr - 1;
+        PairRec q; q.key = key; q.gjk = 0; q.live = -1; q.flags = 0; q.skip = 0.0;
+        if (lo < old_n && op[lo].key == key) { q.gjk = op[lo].gjk; q.live = op[lo].live; q.flags = op[lo].flags & 1; q.skip = op[lo].skip; }
+        np_[sr + i] = q;
+    }
+    bp_wsync();
+    rebuild_finish(ev, d, np, nxt, true);
 }
 
 // Append the pairs incident to body `bdy` that are not yet in the awake-pair list.
@@ -180,7 +293,7 @@ BP_DEV void pair_apart_impl(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, 
 
 BP_DEVNI void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, double gap) { pair_apart_impl(ev, sc, pr, i, p, a, b, gap); }
 BP_DEVNI void pair_apart_b(const DevConst* C, char* base, int i, int p, int a, int b, double gap) {
-    EnvView ev = view_at(base, C->off);
+    EnvView ev = view_s(base);
     pair_apart_impl(ev, ev.sc, ev.pair[ev.sc->cur], i, p, a, b, gap);
 }
 
@@ -203,6 +316,7 @@ BP_DEVNI void pair_finish(const EnvView& ev, const LayoutView& L, const Dims& d,
     if (need) {
         if (rk < nfree) {
             slot = ev.free_stack[nfree - 1 - rk];
+            bp_atomic_max(&sc->slot_hw, slot + 1);
             pr[p].live = slot;
             SlotRec& S = ev.slot[slot];
             S.pair = p; S.a = a; S.b = b; S.cnt = 0; S.touch = 0; S.first = 1;
@@ -392,9 +506,10 @@ BP_DEVNI void expire_cached(const EnvView& ev, const SimParams& P, const Dims& d
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     PairRec* pr = ev.pair[sc->cur];
-    for (int base = 0; base < d.LMAX; base += BP_NL) {
+    const int hw = sc->slot_hw;
+    for (int base = 0; base < hw; base += BP_NL) {
         int s = base + lane;
-        bool drop = (s < d.LMAX) && ev.slot[s].pair >= 0 && !ev.slot[s].touch && (sc->stamp - ev.slot[s].stamp >= P.persistence);
+        bool drop = (s < hw) && ev.slot[s].pair >= 0 && !ev.slot[s].touch && (sc->stamp - ev.slot[s].stamp >= P.persistence);
         int tot; int rk = bp_wrank(drop, &tot);
         int nf = sc->n_free;
         if (drop) { pr[ev.slot[s].pair].live = -1; ev.slot[s].pair = -1; ev.free_stack[nf + rk] = s; }
@@ -615,7 +730,7 @@ BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P
             double mg = body_margin(P, sc, b);
             BBox c = ev.bb[b], o = ev.b0[b];
             if (c.l < o.l - mg || c.r > o.r + mg || c.b < o.b - mg || c.t > o.t + mg) sc->rebuild = 1;
-            ev.moved_step[b] = 1;
+            ev.moved_step[b] = 1; ev.mvrb[b] = 1;
             R.bx = 0.0; R.by = 0.0; R.bw = 0.0;
         }
         ev.moved[b] = mv ? 1 : 0;
@@ -624,7 +739,7 @@ BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P
     if (lane == 0) sc->G += 2.0 * dmax * 1.000001;
     bp_wsync();
     BP_TOCK(sc, 0, tk);
-    if (sc->rebuild) { rebuild_pairs(ev, P, d, true); build_apairs(ev); }
+    if (sc->rebuild) { rebuild_pairs_inc(ev, P, d); build_apairs(ev); }
     BP_TOCK(sc, 1, tk);
     // 2. collide, then close the awake set over newly touching bodies
     int nq = eval_pairs(ev, L, d, 0);
@@ -654,7 +769,8 @@ BP_DEVNI void sleep_pass(const EnvView& ev, const LayoutView& L, const Dims& d) 
         ev.act[b] = (nz || !body_dynamic(L, b)) ? 1 : 0;
     }
     bp_wsync();
-    for (int s = lane; s < d.LMAX; s += BP_NL) {
+    const int hw = sc->slot_hw;
+    for (int s = lane; s < hw; s += BP_NL) {
         const SlotRec& S = ev.slot[s];
         if (S.pair < 0) continue;
         bool seed = false;
@@ -666,7 +782,7 @@ BP_DEVNI void sleep_pass(const EnvView& ev, const LayoutView& L, const Dims& d) 
     bp_wsync();
     for (;;) {
         bool changed = false;
-        for (int s = lane; s < d.LMAX; s += BP_NL) {
+        for (int s = lane; s < hw; s += BP_NL) {
             const SlotRec& S = ev.slot[s];
             if (S.pair < 0 || !S.touch) continue;
             if (!body_dynamic(L, S.a) || !body_dynamic(L, S.b)) continue;
@@ -677,10 +793,10 @@ BP_DEVNI void sleep_pass(const EnvView& ev, const LayoutView& L, const Dims& d) 
     }
     // free the arbiters of sleeping bodies, clear the evaluated flags of their pairs
     bool any_sleep = false;
-    for (int base = 0; base < d.LMAX; base += BP_NL) {
+    for (int base = 0; base < hw; base += BP_NL) {
         int s = base + lane;
         bool drop = false;
-        if (s < d.LMAX && ev.slot[s].pair >= 0) {
+        if (s < hw && ev.slot[s].pair >= 0) {
             int a = ev.slot[s].a, b = ev.slot[s].b;
             drop = (body_dynamic(L, a) && !ev.act[a]) || (body_dynamic(L, b) && !ev.act[b]);
         }
@@ -730,7 +846,7 @@ BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& 
         sc->stamp = 0; sc->n_awake = nb; sc->n_pairs = 0; sc->cur = 0; sc->n_free = d.LMAX; sc->n_order = 0; sc->n_colours = 0;
         sc->dirty = 1; sc->status = 0; sc->layout = layout_id; sc->nbody = nb; sc->robot = L.robot0; sc->t = 0; sc->rebuild = 0;
         sc->n_apairs = 0; sc->n_cached = 0; sc->any_wake = 0; sc->total_work = 0.0; sc->G = 0.0;
-        sc->wall_hit = 0; sc->has_prev_dist = 0; sc->prev_dist = 0.0;
+        sc->wall_hit = 0; sc->has_prev_dist = 0; sc->prev_dist = 0.0; sc->slot_hw = 0; sc->pad_hw = 0;
         int nf = 0;
         for (int b = 0; b < nb; b++) nf += body_dynamic(L, b) ? 0 : 1;
         sc->n_fixed = nf;

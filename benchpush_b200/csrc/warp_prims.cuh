@@ -134,10 +134,12 @@ BP_DEV void bp_sincos(double x, double* sn, double* cs) {
 BP_DEV void bp_atomic_or(unsigned* p, unsigned v) { atomicOr(p, v); }
 BP_DEV void bp_atomic_and(unsigned* p, unsigned v) { atomicAnd(p, v); }
 BP_DEV int bp_atomic_add(int* p, int v) { return atomicAdd(p, v); }
+BP_DEV void bp_atomic_max(int* p, int v) { atomicMax(p, v); }
 BP_DEV void bp_atomic_max_u64(unsigned long long* p, unsigned long long v) { atomicMax(p, v); }
 #else
 BP_DEV void bp_atomic_or(unsigned* p, unsigned v) { *p |= v; }
 BP_DEV void bp_atomic_and(unsigned* p, unsigned v) { *p &= v; }
 BP_DEV int bp_atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
+BP_DEV void bp_atomic_max(int* p, int v) { if (v > *p) *p = v; }
 BP_DEV void bp_atomic_max_u64(unsigned long long* p, unsigned long long v) { if (v > *p) *p = v; }
 #endif

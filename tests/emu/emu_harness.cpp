@@ -80,6 +80,7 @@ void emu_step_batch(void* h, int env0, const float* actions, int auto_reset) {
     static DevConst C;
     C.d = e->d; C.P = e->P; C.off = env_offsets(e->d); C.T = e->T; C.snap = nullptr; C.env_bytes = e->env_bytes; C.snap_pose = nullptr; C.snap_status = nullptr;
     static BatchShared S;
+    load_shared_offsets(C.off);
     shipice_step_batch(&C, S, e->mem.data(), e->env_bytes, env0, actions, nullptr, e->out, auto_reset);
 }
 int emu_batch_size() { return BK; }
