@@ -1,0 +1,339 @@
+// box-delivery-v0: kernels and C ABI (bp_boxdel_*, declared in include/benchpush_b200.h).
+// Included at the end of bp_api.cu (one translation unit, one shared library).
+#pragma once
+#include "boxdel_obs.cuh"
+#include "boxdel_host.h"
+
+using namespace bp::bd;
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void k_bd_init_statics(BdConst* C) {
+    int k = threadIdx.x;
+    if (k < C->P.n_static) bd_init_static(C->S, k);
+}
+
+// warp per env
+__global__ void __launch_bounds__(128) k_bd_reset(const BdConst* C, const int32_t* layout_ids, const uint8_t* mask, BdOut out) {
+    int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= C->n_envs || (mask && !mask[env])) return;
+    BdEnv* E = bd_env(*C, env);
+    int layout = (layout_ids ? layout_ids[env] : env) % C->n_layouts;
+    int episode = 0;
+    bd_reset_env(*C, E, layout, episode);
+    if ((threadIdx.x & 31) == 0) bd_reset_out(*C, E, env, out);
+}
+
+// thread per env: action decode, target, straight-line test
+__global__ void k_bd_begin(const BdConst* C, const float* actions, const uint8_t* mask) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= C->n_envs || (mask && !mask[env])) return;
+    bd_begin_step(*C, bd_env(*C, env), (double)actions[env]);
+}
+
+// block per (env, item) pulled from a counter; item k < NB: box distance, k == NB: robot path (phase 0)
+__global__ void __launch_bounds__(256) k_bd_dist(const BdConst* C, const uint8_t* mask, int phase, int* scratch, int* counter) {
+    __shared__ SpfaShared S;
+    __shared__ int s_item;
+    const int per_env = C->P.NB + 1;
+    const int total = C->n_envs * per_env;
+    int* my = scratch + (size_t)blockIdx.x * bd_scratch_ints(C->P);
+    for (;;) {
+        if (threadIdx.x == 0) {
+            // skip items that need no work without a block-wide round trip
+            int it;
+            for (;;) {
+                it = atomicAdd(counter, 1);
+                if (it >= total) break;
+                int env = it / per_env, k = it - env * per_env;
+                if (mask && !mask[env]) continue;
+                const BdEnv* E = bd_env(*C, env);
+                if (k < C->P.NB ? (E->body[1 + k].alive == 1) : (phase == 0 && E->need_spfa)) break;
+            }
+            s_item = it;
+        }
+        __syncthreads();
+        int it = s_item;
+        __syncthreads();
+        if (it >= total) break;
+        int env = it / per_env, k = it - env * per_env;
+        bd_dist_item(S, *C, bd_env(*C, env), k, phase, my);
+    }
+}
+
+// warp per env: waypoint headings, controller loop, until-still loop
+__global__ void __launch_bounds__(128) k_bd_move(const BdConst* C, const uint8_t* mask) {
+    __shared__ BdLoop LS[4];
+    int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= C->n_envs || (mask && !mask[env])) return;
+    BdEnv* E = bd_env(*C, env);
+    if ((threadIdx.x & 31) == 0) bd_finalize_path(*C, E);
+    __syncwarp();
+    bd_move(*C, E, LS[threadIdx.x >> 5]);
+}
+
+// thread per env
+__global__ void k_bd_finish(const BdConst* C, const uint8_t* mask, BdOut out) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= C->n_envs || (mask && !mask[env])) return;
+    bd_finish_step(*C, bd_env(*C, env), env, out);
+}
+
+// block per env pulled from a counter
+__global__ void __launch_bounds__(256) k_bd_obs(const BdConst* C, const uint8_t* mask, uint8_t* obs, int* scratch, int* counter) {
+    __shared__ BdObsShared S;
+    __shared__ int s_env;
+    int* my = scratch + (size_t)blockIdx.x * bd_scratch_ints(C->P);
+    const size_t obs_bytes = (size_t)C->P.LW * C->P.LW * 4;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int e;
+            for (;;) { e = atomicAdd(counter, 1); if (e >= C->n_envs || !(mask && !mask[e])) break; }
+            s_env = e;
+        }
+        __syncthreads();
+        int env = s_env;
+        __syncthreads();
+        if (env >= C->n_envs) break;
+        bd_obs_item(S, *C, bd_env(*C, env), my, obs + obs_bytes * env);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ handle
+struct bp_boxdel {
+    bp_boxdel_config cfg;
+    BdConst hC;                      // host copy (device pointers inside)
+    BdConst* dC = nullptr;
+    BdLayout* d_layouts = nullptr; short* d_pa = nullptr; short* d_pb = nullptr;
+    uint8_t *d_cspace = nullptr, *d_thin = nullptr, *d_small = nullptr, *d_rchan = nullptr; int32_t* d_closest = nullptr; float* d_recept = nullptr;
+    char* d_envs = nullptr; int* d_scratch = nullptr; int* d_counter = nullptr; int n_blocks = 0;
+    bool loaded = false;
+    int64_t launches = 0;
+};
+
+
+extern "C" {
+
+void bp_boxdel_default_config(bp_boxdel_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->n_envs = 1; c->num_boxes = 10; c->device = 0; c->action_type = 1;
+    c->steps = 100; c->iterations = 10; c->settle_steps = 1000; c->inactivity_cutoff = 200;
+    c->ctrl_dt = 0.2; c->target_speed = 0.3; c->damping = 0.0;
+    c->box_size = 0.44; c->box_density = 0.001;
+    c->room_length = 10; c->room_width = 5; c->receptacle_width = 1.5;
+    c->local_map_width = 10; c->local_map_pixel_width = 224; c->step_size = 1.75;
+    c->robot_length = 0.6; c->robot_width = 0.92;
+    c->partial_rewards_scale = 0.2; c->goal_reward = 10.0; c->collision_penalty = 0.25; c->non_movement_penalty = 0.0;
+    c->correct_direction_reward_scale = 3.0; c->use_correct_direction_reward = 0; c->ministep_size = 2.5;
+    c->shortest_path_channel_scale = 0.25;
+    const double chassis[8] = {0.26, -0.35, -0.31, -0.35, -0.31, 0.35, 0.26, 0.35};
+    const double bumper[8] = {0.31, -0.53, 0.20, -0.39, 0.20, 0.39, 0.31, 0.53};
+    const double wheels[32] = {0.09, 0.35, 0.09, 0.39, 0.24, 0.39, 0.24, 0.35,   0.09, -0.39, 0.09, -0.35, 0.24, -0.35, 0.24, -0.39,
+                               -0.09, 0.35, -0.09, 0.39, -0.24, 0.39, -0.24, 0.35,   -0.09, -0.35, -0.09, -0.39, -0.24, -0.39, -0.24, -0.35};
+    memcpy(c->chassis_verts, chassis, sizeof(chassis)); memcpy(c->bumper_verts, bumper, sizeof(bumper)); memcpy(c->wheel_verts, wheels, sizeof(wheels));
+}
+
+int bp_boxdel_create(const bp_boxdel_config* cfg, bp_boxdel_t** out) {
+    if (!cfg || !out) return fail(BP_ERR_INVALID, "null argument");
+    if (cfg->n_envs <= 0 || cfg->num_boxes <= 0 || cfg->num_boxes > MAXBOX) return fail(BP_ERR_INVALID, "n_envs / num_boxes out of range");
+    if (cfg->action_type != 0 && cfg->action_type != 1) return fail(BP_ERR_INVALID, "action_type must be 0 (position) or 1 (heading)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(BP_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    bp_boxdel* h = new bp_boxdel();
+    h->cfg = *cfg;
+    memset(&h->hC, 0, sizeof(h->hC));
+    *out = h;
+    return BP_OK;
+}
+
+int bp_boxdel_destroy(bp_boxdel_t* h) {
+    if (!h) return BP_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->dC); cudaFree(h->d_layouts); cudaFree(h->d_pa); cudaFree(h->d_pb); cudaFree(h->d_cspace); cudaFree(h->d_thin); cudaFree(h->d_small);
+    cudaFree(h->d_rchan); cudaFree(h->d_closest); cudaFree(h->d_recept); cudaFree(h->d_envs); cudaFree(h->d_scratch); cudaFree(h->d_counter);
+    delete h;
+    return BP_OK;
+}
+
+// All pointers are HOST pointers.  starts[L][3]; n_boxes[L]; boxes[L][num_boxes][3] (x, y, heading);
+// statics: st_nv[ns], st_verts[ns][4][2] (body-local, as passed to pymunk.Poly), st_pose[ns][3], st_rad[ns], st_ctype[ns]
+// in shape creation order (receptacle, walls, corners: box_delivery_env.py:256-263, sim_utils.py:96-131);
+// maps of the room (box_delivery_env.py:1140-1175): cspace / cspace_thin u8[H][W] (1 = free), closest i32[2][H][W],
+// small_free u8[S][S] (S = local_map_pixel_width + 20), robot_chan u8[LW][LW] (0 / 255).
+int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                   int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                   int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
+                   const uint8_t* small_free, const uint8_t* robot_chan) {
+    if (!h || !starts || !n_boxes || !boxes || !st_nv || !st_verts || !st_pose || !st_rad || !st_ctype || !cspace || !cspace_thin || !closest || !small_free || !robot_chan)
+        return fail(BP_ERR_INVALID, "null argument");
+    if (h->loaded) return fail(BP_ERR_STATE, "already loaded");
+    if (n_layouts <= 0 || n_static <= 0 || n_static > MAXSTAT) return fail(BP_ERR_INVALID, "n_layouts / n_static out of range");
+    const bp_boxdel_config& c = h->cfg;
+    CUDA_TRY(cudaSetDevice(c.device));
+    BdHost HB;
+    {
+        std::string err = bd_host_build(HB, c, n_layouts, starts, n_boxes, boxes, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype, H, W);
+        if (!err.empty()) return fail(BP_ERR_INVALID, err);
+    }
+    h->hC = HB.K;
+    BdConst& K = h->hC;
+    BdParams& P = K.P;
+    std::vector<BdLayout>& LY = HB.LY;
+    // ---- upload
+    const size_t nv = (size_t)H * W;
+    std::vector<short>& pa = HB.pa; std::vector<short>& pb = HB.pb;
+    CUDA_TRY(cudaMalloc((void**)&h->d_layouts, sizeof(BdLayout) * n_layouts));
+    CUDA_TRY(cudaMemcpy(h->d_layouts, LY.data(), sizeof(BdLayout) * n_layouts, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_pa, 2 * P.n_slots)); CUDA_TRY(cudaMalloc((void**)&h->d_pb, 2 * P.n_slots));
+    CUDA_TRY(cudaMemcpy(h->d_pa, pa.data(), 2 * P.n_slots, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_pb, pb.data(), 2 * P.n_slots, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_cspace, nv)); CUDA_TRY(cudaMemcpy(h->d_cspace, cspace, nv, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_thin, nv)); CUDA_TRY(cudaMemcpy(h->d_thin, cspace_thin, nv, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_closest, nv * 8)); CUDA_TRY(cudaMemcpy(h->d_closest, closest, nv * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_small, (size_t)P.SMALL * P.SMALL)); CUDA_TRY(cudaMemcpy(h->d_small, small_free, (size_t)P.SMALL * P.SMALL, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_rchan, (size_t)P.LW * P.LW)); CUDA_TRY(cudaMemcpy(h->d_rchan, robot_chan, (size_t)P.LW * P.LW, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_recept, nv * 4));
+    K.layouts = h->d_layouts; K.n_layouts = n_layouts; K.n_envs = c.n_envs; K.pair_a = h->d_pa; K.pair_b = h->d_pb;
+    K.cspace = h->d_cspace; K.cspace_thin = h->d_thin; K.closest = h->d_closest; K.small_free = h->d_small; K.robot_chan = h->d_rchan; K.recept_dist = h->d_recept;
+    K.env_bytes = bd_env_bytes(P.n_slots);
+    CUDA_TRY(cudaMalloc((void**)&h->d_envs, K.env_bytes * c.n_envs));
+    CUDA_TRY(cudaMemset(h->d_envs, 0, K.env_bytes * c.n_envs));
+    K.envs = h->d_envs;
+    int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+    h->n_blocks = sms * 4;
+    CUDA_TRY(cudaMalloc((void**)&h->d_scratch, (size_t)h->n_blocks * bd_scratch_ints(P) * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&h->d_counter, 64));
+    CUDA_TRY(cudaMalloc((void**)&h->dC, sizeof(BdConst)));
+    CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdConst), cudaMemcpyHostToDevice));
+    k_bd_init_statics<<<1, 32>>>(h->dC);
+    CUDA_TRY(cudaGetLastError());
+    // receptacle-source distance field: static for the handle (the reference recomputes it every step, :1115-1129)
+    {
+        int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
+        pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
+        int32_t src[2] = {closest[(size_t)pi * W + pj], closest[nv + (size_t)pi * W + pj]};
+        int32_t* d_src = nullptr; int32_t* d_par = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&d_src, 8)); CUDA_TRY(cudaMalloc((void**)&d_par, nv * 4));
+        CUDA_TRY(cudaMemcpy(d_src, src, 8, cudaMemcpyHostToDevice));
+        int rc = bp_spfa_batch(h->d_cspace, d_src, 1, H, W, h->d_recept, d_par, nullptr);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaFree(d_src); cudaFree(d_par);
+        if (rc != BP_OK) return rc;
+        if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("receptacle spfa: ") + cudaGetErrorString(e));
+    }
+    CUDA_TRY(cudaMemcpy(&K, h->dC, sizeof(BdConst), cudaMemcpyDeviceToHost));     // statics now in world space
+    h->loaded = true;
+    return BP_OK;
+}
+
+static BdOut bd_out(const bp_boxdel_outputs* o) {
+    BdOut r; memset(&r, 0, sizeof(r));
+    if (o) { r.reward = o->reward; r.terminated = o->terminated; r.truncated = o->truncated; r.info = o->info; r.info_i = o->info_i; r.completed = o->completed; r.box_verts = o->box_verts; }
+    return r;
+}
+
+static int bd_launch_obs(bp_boxdel* h, const uint8_t* mask, uint8_t* obs, cudaStream_t st) {
+    if (!obs) return BP_OK;
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
+    int blocks = h->n_blocks < h->cfg.n_envs ? h->n_blocks : h->cfg.n_envs;
+    k_bd_obs<<<blocks, 256, 0, st>>>(h->dC, mask, obs, h->d_scratch, h->d_counter);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_boxdel_reset(bp_boxdel_t* h, const int32_t* layout_ids, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream) {
+    if (!h || !h->loaded) return fail(BP_ERR_STATE, "bp_boxdel_load first");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int E = h->cfg.n_envs;
+    k_bd_reset<<<(E * 32 + 127) / 128, 128, 0, st>>>(h->dC, layout_ids, mask, bd_out(out));
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return bd_launch_obs(h, mask, out ? out->obs : nullptr, st);
+}
+
+int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream) {
+    if (!h || !h->loaded) return fail(BP_ERR_STATE, "bp_boxdel_load first");
+    if (!actions) return fail(BP_ERR_INVALID, "null actions");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int E = h->cfg.n_envs;
+    int items = E * (h->cfg.num_boxes + 1);
+    int blocks = h->n_blocks < items ? h->n_blocks : items;
+    k_bd_begin<<<(E + 127) / 128, 128, 0, st>>>(h->dC, actions, mask);
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
+    k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 0, h->d_scratch, h->d_counter);
+    k_bd_move<<<(E * 32 + 127) / 128, 128, 0, st>>>(h->dC, mask);
+    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
+    k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 1, h->d_scratch, h->d_counter);
+    k_bd_finish<<<(E + 127) / 128, 128, 0, st>>>(h->dC, mask, bd_out(out));
+    h->launches += 5;
+    CUDA_TRY(cudaGetLastError());
+    return bd_launch_obs(h, mask, out ? out->obs : nullptr, st);
+}
+
+// host-buffer variant: actions and every non-null output are HOST pointers; copies in, steps, copies out, synchronises
+int bp_boxdel_step_host(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host) {
+    if (!h || !h->loaded) return fail(BP_ERR_STATE, "bp_boxdel_load first");
+    if (!actions || !out_host) return fail(BP_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int E = h->cfg.n_envs, NB = h->cfg.num_boxes;
+    const size_t obs_b = (size_t)E * h->hC.P.LW * h->hC.P.LW * 4;
+    float* d_act = nullptr; CUDA_TRY(cudaMalloc((void**)&d_act, 4 * (size_t)E));
+    CUDA_TRY(cudaMemcpy(d_act, actions, 4 * (size_t)E, cudaMemcpyHostToDevice));
+    bp_boxdel_outputs d; memset(&d, 0, sizeof(d));
+    struct Item { void** dev; void* host; size_t bytes; };
+    Item items[8] = {{(void**)&d.obs, out_host->obs, obs_b}, {(void**)&d.reward, out_host->reward, 8 * (size_t)E},
+                     {(void**)&d.terminated, out_host->terminated, (size_t)E}, {(void**)&d.truncated, out_host->truncated, (size_t)E},
+                     {(void**)&d.info, out_host->info, 64 * (size_t)E}, {(void**)&d.info_i, out_host->info_i, 16 * (size_t)E},
+                     {(void**)&d.completed, out_host->completed, (size_t)E * NB}, {(void**)&d.box_verts, out_host->box_verts, (size_t)E * NB * SV * 16}};
+    int rc = BP_OK;
+    for (auto& it : items) if (it.host && cudaMalloc(it.dev, it.bytes) != cudaSuccess) rc = fail(BP_ERR_CUDA, "cudaMalloc (step_host)");
+    if (rc == BP_OK) rc = bp_boxdel_step(h, d_act, nullptr, &d, nullptr);
+    if (rc == BP_OK) for (auto& it : items) if (it.host && cudaMemcpy(it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(BP_ERR_CUDA, "copy out (step_host)");
+    for (auto& it : items) if (*it.dev) cudaFree(*it.dev);
+    cudaFree(d_act);
+    return rc;
+}
+
+// HOST out[(1 + num_boxes)][7]: body origin x, y, angle, vx, vy, w, alive — row 0 = robot.  Synchronises.
+int bp_boxdel_get_bodies(bp_boxdel_t* h, int32_t env, double* out) {
+    if (!h || !h->loaded || env < 0 || env >= h->cfg.n_envs || !out) return fail(BP_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<char> buf(sizeof(BdEnv));
+    CUDA_TRY(cudaMemcpy(buf.data(), h->d_envs + h->hC.env_bytes * env, sizeof(BdEnv), cudaMemcpyDeviceToHost));
+    const BdEnv* E = (const BdEnv*)buf.data();
+    for (int b = 0; b <= h->cfg.num_boxes; b++) {
+        const BdBody& B = E->body[b];
+        double ox = B.px - (B.cgx * B.rc - B.cgy * B.rs), oy = B.py - (B.cgx * B.rs + B.cgy * B.rc);
+        double* o = out + 7 * b;
+        o[0] = ox; o[1] = oy; o[2] = B.pa; o[3] = B.vx; o[4] = B.vy; o[5] = B.vw; o[6] = B.alive;
+    }
+    return BP_OK;
+}
+
+// HOST out[16]: n_path, move_sign, need_spfa, status, robot_hit, substeps so far, candidate pairs so far, arbiters so far,
+// robot_distance, then init_dist / final_dist are returned through dists[2][num_boxes]; path[24][3].  Debug / parity aid.
+int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double* dists, double* path) {
+    if (!h || !h->loaded || env < 0 || env >= h->cfg.n_envs) return fail(BP_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<char> buf(sizeof(BdEnv));
+    CUDA_TRY(cudaMemcpy(buf.data(), h->d_envs + h->hC.env_bytes * env, sizeof(BdEnv), cudaMemcpyDeviceToHost));
+    const BdEnv* E = (const BdEnv*)buf.data();
+    if (out16) {
+        out16[0] = E->n_path; out16[1] = E->move_sign; out16[2] = E->need_spfa; out16[3] = E->status; out16[4] = E->robot_hit;
+        out16[5] = (double)E->stat_substeps; out16[6] = (double)E->stat_cand; out16[7] = (double)E->stat_arb; out16[8] = E->robot_distance;
+        for (int i = 9; i < 16; i++) out16[i] = 0.0;
+    }
+    if (dists) for (int i = 0; i < h->cfg.num_boxes; i++) { dists[i] = E->init_dist[i]; dists[h->cfg.num_boxes + i] = E->final_dist[i]; }
+    if (path) memcpy(path, E->path, sizeof(E->path));
+    return BP_OK;
+}
+
+int64_t bp_boxdel_launch_count(bp_boxdel_t* h) { return h ? h->launches : 0; }
+size_t bp_boxdel_env_bytes(bp_boxdel_t* h) { return h ? h->hC.env_bytes : 0; }
+
+}  // extern "C"

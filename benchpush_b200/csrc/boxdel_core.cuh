@@ -1,0 +1,580 @@
+// Small-world rigid-body core for box-delivery-v0 (and the other room-sized envs): one warp steps one
+// environment whose whole world is ~30 convex shapes (compound kinematic robot, <= 20 dynamic boxes,
+// static walls / corners / receptacle).
+//
+// Replaces the per-env `pymunk.Space.step` calls of BoxDeliveryEnv (reference call sites
+// box_delivery_env.py:278-279 settle, :945 controller loop, :1019 until-still loop) together with the
+// collision handlers the env installs (:196-229, prevent_boundary_intersection :294-311) and
+// `space.remove` (:765-767).  Semantics = Chipmunk2D cpSpaceStep as restated in SURVEY.md Appendix A
+// and oracle/chipmunk_oracle.cpp (handler_mode 1): same pair order (ascending shape pair), same
+// arbiter cache life cycle, same greedy-colour solver order, fp64 without FMA contraction.
+//
+// Why not the ship-ice core (sim_step.cuh): that one is built around awake sets and exact motion bounds
+// for ~650 bodies; here the handlers teleport bodies inside a step and the env removes bodies, and the
+// world is small enough that ALL candidate pairs (a dense, precomputed list of the <= 600 shape pairs
+// that can have an effect) are AABB-tested by the 32 lanes every substep.  The arbiter cache is a dense
+// table indexed by that pair id: no allocation, no hashing.  Narrowphase leaves (GJK / EPA / support
+// edges) are shared with sim_core.cuh.
+//
+// Pairs that cannot have any effect are not in the list: robot shape vs receptacle ((1,4) begin -> False,
+// both bodies of infinite mass), box vs receptacle ((2,4) pre_solve -> False: never solved), wheels /
+// bumper vs walls (default handler, both bodies of infinite mass).
+#pragma once
+#include "sim_core.cuh"
+
+namespace bp {
+namespace bd {
+
+constexpr int MAXBOX = 20;        // cfg.boxes.num_boxes_large
+constexpr int NROBOT = 6;         // chassis, 4 wheels, front bumper (sim_utils.py:20-76)
+constexpr int MAXSTAT = 16;       // receptacle + 4 walls + 3 corners x 3 triangles = 14 in an empty room
+constexpr int SV = 4;             // vertices per shape (rectangles, the bumper trapezoid, corner triangles)
+constexpr int NMOV = NROBOT + MAXBOX;
+constexpr int MAXCAND = 128;      // AABB-overlapping pairs per substep
+constexpr int MAXWP = 24;         // waypoints of one robot path
+constexpr int MAXCOLOUR = 32;
+
+enum BdStatus { BD_OK = 0, BD_CAND_OVERFLOW = 1, BD_COLOUR_OVERFLOW = 2, BD_GJK_ITER = 4, BD_PATH_OVERFLOW = 8, BD_STEP_LIMIT = 16 };
+enum SlotState { SL_NONE = 0, SL_FIRST = 1, SL_NORMAL = 2, SL_CACHED = 3 };
+
+struct BdParams {
+    int NB;                       // boxes per env (capacity = cfg num_boxes)
+    int n_static, n_s3;           // static shapes; those with collision_type 3 (walls, corners)
+    int s3[MAXSTAT];              // static index of the k-th type-3 shape, ascending
+    int recept;                   // static index of the receptacle (collision_type 4)
+    int n_slots;                  // dense pair table size
+    int iterations, persistence, settle_steps;
+    double dt;                    // cfg.controller.dt / cfg.sim.steps (the physics substep)
+    double damp, bias_coef, slop;
+    double ctrl_dt, target_speed; // cfg.controller.dt, cfg.controller.target_speed
+    // maps
+    int H, W, LW, SMALL, CROP;    // padded room (430 x 542), local map (224), small map (244), crop (318)
+    int small_i0, small_j0, px_off;
+    double ppm;                   // local_map_pixels_per_meter
+    double local_map_width, step_size, room_length, room_width, robot_radius;
+    double recept_x, recept_y;
+    // rewards / episode (box_delivery/config.yaml:135-147, :120-124)
+    double partial_scale, goal_reward, collision_penalty, nonmove_penalty, correct_scale, ministep;
+    int use_correct, inactivity_cutoff, num_boxes, action_type;   // action_type 0 = position (pixel index), 1 = heading
+    double sp_div, sp_scale;      // (sqrt(2) * LW) / ppm ; cfg.env.shortest_path_channel_scale
+};
+
+struct BdBody {                   // 144 B
+    double px, py, pa;            // cog position (world), angle
+    double vx, vy, vw, bx, by, bw;
+    double minv, iinv, rc, rs, cgx, cgy;
+    int alive, idx;
+};
+
+struct alignas(16) BdSlot {       // one shape pair of the dense table = cpArbiter while state != SL_NONE
+    int stamp; unsigned gjk;
+    unsigned char state, cnt, live, pad;
+    int pad2;
+    double nx, ny, e, u;
+    ContactRec c[2];
+};
+
+struct BdLayout {                 // immutable per layout
+    double start[3];
+    int n_boxes, pad;
+    double box_init[MAXBOX][3];
+    double box_lv[MAXBOX][SV][2], box_ln[MAXBOX][SV][2];
+    double box_cog[MAXBOX][2], box_minv[MAXBOX], box_iinv[MAXBOX];
+};
+
+struct BdShapes {                 // immutable per handle: robot shapes (body-local) and static shapes (world)
+    double rb_lv[NROBOT][SV][2], rb_ln[NROBOT][SV][2], rb_rad[NROBOT], rb_e[NROBOT], rb_u[NROBOT];
+    int rb_nv[NROBOT];
+    double st_lv[MAXSTAT][SV][2], st_ln[MAXSTAT][SV][2], st_pose[MAXSTAT][3];   // as created (body-local + body pose)
+    alignas(16) double st_v[MAXSTAT][SV][2];                                       // world (filled by bd_init_statics); 128-bit vertex loads
+    double st_n[MAXSTAT][SV][2], st_p[MAXSTAT][2];
+    BBox st_bb[MAXSTAT];
+    double st_rad[MAXSTAT], st_e[MAXSTAT], st_u[MAXSTAT];
+    int st_nv[MAXSTAT], st_ctype[MAXSTAT];
+    double box_rad, box_e, box_u;
+};
+
+struct BdEnv {                    // mutable per env (header; the slot table follows it in the env block)
+    int layout, episode, t, status, stamp, n_order, robot_hit, inactivity, cum_boxes, done, truncated, n_prev;
+    int n_path, move_sign, need_spfa, src_i, src_j, tgt_i, tgt_j, pad0;
+    long long stat_substeps, stat_cand, stat_arb;
+    double prev_dt, cum_distance, cum_reward, total_work, last_work, reward, ministeps;
+    double init_pos[2], init_heading, robot_distance;
+    double path[MAXWP][3];
+    double tgt[2];
+    double init_dist[MAXBOX], final_dist[MAXBOX];
+    BdBody body[1 + MAXBOX];      // [0] robot (all six shapes), [1 + i] box i
+    alignas(16) double wv[NMOV][SV][2];   // world vertices of the moving shapes: [0, 6) robot, [6 + i] box i (128-bit vertex loads)
+    BBox bb[NMOV];
+    double prev_boxes[MAXBOX][SV][2];   // CostMap.get_obs_from_poly at the previous env step (work accounting)
+    unsigned char completed[MAXBOX];
+    short order[MAXCAND];         // this step's solve list (slot ids), colour-sorted
+    short cand[MAXCAND];
+    Closest cpts[MAXCAND];
+    unsigned char ccnt[MAXCAND];
+    Manifold cman[MAXCAND];
+};
+
+BP_HD size_t bd_env_bytes(int n_slots) { return BP_ALIGN128(sizeof(BdEnv)) + BP_ALIGN128((size_t)n_slots * sizeof(BdSlot)); }
+BP_DEV BdSlot* bd_slots(BdEnv* e) { return (BdSlot*)((char*)e + BP_ALIGN128(sizeof(BdEnv))); }
+
+struct BdConst {
+    BdParams P; BdShapes S;
+    const BdLayout* layouts; int n_layouts, n_envs;
+    const short* pair_a; const short* pair_b;      // [n_slots] shape ids of the dense pair table (a < b)
+    // static maps of the room (box_delivery_env.py:1140-1175), identical for every env of the handle
+    const uint8_t* cspace; const uint8_t* cspace_thin;      // [H][W] 1 = free
+    const int32_t* closest;                                 // [2][H][W] distance_transform_edt indices
+    const uint8_t* small_free;                              // [SMALL][SMALL] 1 = free floor (small_obstacle_map)
+    const uint8_t* robot_chan;                              // [LW][LW] robot_state_channel * 255
+    const float* recept_dist;                               // [H][W] spfa from the receptacle cell, unscaled
+    char* envs; size_t env_bytes;
+};
+BP_DEV BdEnv* bd_env(const BdConst& C, int e) { return (BdEnv*)(C.envs + (size_t)e * C.env_bytes); }
+
+// dense pair table (ascending (shape a, shape b) with a < b):  shape ids: [0,6) robot, [6, 6+NB) boxes, then statics
+static inline int bd_build_pairs(const BdParams& P, short* pa, short* pb) {
+    int n = 0, NB = P.NB;
+    auto put = [&](int a, int b) { if (pa) { pa[n] = (short)a; pb[n] = (short)b; } n++; };
+    for (int j = 0; j < NB; j++) put(0, NROBOT + j);
+    for (int k = 0; k < P.n_s3; k++) put(0, NROBOT + NB + P.s3[k]);
+    for (int r = 1; r < NROBOT; r++) for (int j = 0; j < NB; j++) put(r, NROBOT + j);
+    for (int i = 0; i < NB; i++) {
+        for (int j = i + 1; j < NB; j++) put(NROBOT + i, NROBOT + j);
+        for (int k = 0; k < P.n_s3; k++) put(NROBOT + i, NROBOT + NB + P.s3[k]);
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------ shape access
+struct ShapeRef { const double* v; const double* ln; int n; double rad, e, u; double rc, rs; int body; BBox bb; };   // body: -1 = static
+BP_DEV ShapeRef shape_ref(const BdConst& C, const BdEnv* E, int s) {
+    ShapeRef r; const int NB = C.P.NB;
+    if (s < NROBOT) {
+        r.v = &E->wv[s][0][0]; r.ln = &C.S.rb_ln[s][0][0]; r.n = C.S.rb_nv[s]; r.rad = C.S.rb_rad[s]; r.e = C.S.rb_e[s]; r.u = C.S.rb_u[s];
+        r.rc = E->body[0].rc; r.rs = E->body[0].rs; r.body = 0; r.bb = E->bb[s];
+    } else if (s < NROBOT + NB) {
+        int i = s - NROBOT; const BdLayout& L = C.layouts[E->layout];
+        r.v = &E->wv[s][0][0]; r.ln = &L.box_ln[i][0][0]; r.n = SV; r.rad = C.S.box_rad; r.e = C.S.box_e; r.u = C.S.box_u;
+        r.rc = E->body[1 + i].rc; r.rs = E->body[1 + i].rs; r.body = 1 + i; r.bb = E->bb[s];
+    } else {
+        int k = s - NROBOT - NB;
+        r.v = &C.S.st_v[k][0][0]; r.ln = &C.S.st_n[k][0][0]; r.n = C.S.st_nv[k]; r.rad = C.S.st_rad[k]; r.e = C.S.st_e[k]; r.u = C.S.st_u[k];
+        r.rc = 1.0; r.rs = 0.0; r.body = -1; r.bb = C.S.st_bb[k];
+    }
+    return r;
+}
+
+// world vertices + AABB of one shape from its body pose (cpPolyShapeCacheData)
+BP_DEV void cache_shape(const double* lv, int n, double rad, double c, double s, double px, double py, double cgx, double cgy,
+                        double* wv, BBox* bb) {
+    double tx = px - (cgx * c - cgy * s);
+    double ty = py - (cgx * s + cgy * c);
+    double ms = -s;
+    double l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
+    for (int i = 0; i < n; i++) {
+        double qx = lv[2 * i], qy = lv[2 * i + 1];
+        double wx = c * qx + ms * qy + tx;
+        double wy = s * qx + c * qy + ty;
+        wv[2 * i] = wx; wv[2 * i + 1] = wy;
+        l = fmin(l, wx); r = fmax(r, wx); bt = fmin(bt, wy); tp = fmax(tp, wy);
+    }
+    bb->l = l - rad; bb->b = bt - rad; bb->r = r + rad; bb->t = tp + rad;
+}
+// pymunk Body.position (local origin in world space) and its setter (cpBodySetPosition)
+BP_DEV V2 bd_origin(const BdBody& b) { return mk(b.px - (b.cgx * b.rc - b.cgy * b.rs), b.py - (b.cgx * b.rs + b.cgy * b.rc)); }
+BP_DEV void bd_set_origin(BdBody& b, V2 pos) {
+    // p = transform_vect(cog) + position
+    b.px = (b.rc * b.cgx + (-b.rs) * b.cgy) + pos.x;
+    b.py = (b.rs * b.cgx + b.rc * b.cgy) + pos.y;
+}
+// body.local_to_world(v)
+BP_DEV V2 bd_local_to_world(const BdBody& b, double x, double y) {
+    double tx = b.px - (b.cgx * b.rc - b.cgy * b.rs), ty = b.py - (b.cgx * b.rs + b.cgy * b.rc);
+    return mk(b.rc * x + (-b.rs) * y + tx, b.rs * x + b.rc * y + ty);
+}
+
+// statics: world vertices / normals / AABB from the creation pose (run once per handle)
+BP_DEV void bd_init_static(BdShapes& S, int k) {
+    double s, c; bp_sincos(S.st_pose[k][2], &s, &c);
+    // static bodies carry no mass: cog = 0, p = position
+    S.st_p[k][0] = S.st_pose[k][0]; S.st_p[k][1] = S.st_pose[k][1];
+    cache_shape(&S.st_lv[k][0][0], S.st_nv[k], S.st_rad[k], c, s, S.st_pose[k][0], S.st_pose[k][1], 0.0, 0.0, &S.st_v[k][0][0], &S.st_bb[k]);
+    for (int i = 0; i < S.st_nv[k]; i++) {
+        double nx = S.st_ln[k][i][0], ny = S.st_ln[k][i][1];
+        S.st_n[k][i][0] = c * nx + (-s) * ny; S.st_n[k][i][1] = s * nx + c * ny;
+    }
+}
+
+// ------------------------------------------------------------------ narrowphase of one shape pair
+BP_DEV void bd_manifold(const ShapeRef& A, const ShapeRef& B, const Closest& pts, Manifold* m) {
+    m->count = 0;
+    Poly PA; PA.v = A.v; PA.n = A.n; Poly PB; PB.v = B.v; PB.n = B.n;
+    double ra = A.rad, rb = B.rad;
+    if (pts.d - ra - rb <= 0.0) {
+        EdgeW e1 = support_edge(PA, A.ln, A.rc, A.rs, pts.n);
+        EdgeW e2 = support_edge(PB, B.ln, B.rc, B.rs, neg(pts.n));
+        double mindist = ra + rb;
+        if (pts.d <= mindist) {
+            V2 n = pts.n; m->n = n;
+            double d_e1_a = cross(e1.a, n), d_e1_b = cross(e1.b, n);
+            double d_e2_a = cross(e2.a, n), d_e2_b = cross(e2.b, n);
+            double e1_denom = 1.0 / (d_e1_b - d_e1_a + DBL_MIN);
+            double e2_denom = 1.0 / (d_e2_b - d_e2_a + DBL_MIN);
+            {
+                V2 p1 = n * ra + lerp(e1.a, e1.b, clamp01((d_e2_b - d_e1_a) * e1_denom));
+                V2 p2 = n * (-rb) + lerp(e2.a, e2.b, clamp01((d_e1_a - d_e2_a) * e2_denom));
+                if (dot(p2 - p1, n) <= 0.0) { int k = m->count++; m->p1[k] = p1; m->p2[k] = p2; m->hash[k] = (unsigned)(e1.ia << 8 | e2.ib); }
+            }
+            {
+                V2 p1 = n * ra + lerp(e1.a, e1.b, clamp01((d_e2_a - d_e1_a) * e1_denom));
+                V2 p2 = n * (-rb) + lerp(e2.a, e2.b, clamp01((d_e1_b - d_e2_a) * e2_denom));
+                if (dot(p2 - p1, n) <= 0.0) { int k = m->count++; m->p1[k] = p1; m->p2[k] = p2; m->hash[k] = (unsigned)(e1.ib << 8 | e2.ia); }
+            }
+        }
+    }
+}
+
+// body record of shape-ref body index (-1 = static: zero velocity, infinite mass, position st_p)
+struct BodyV { double px, py, vx, vy, vw, minv, iinv; };
+BP_DEV BodyV body_view(const BdConst& C, const BdEnv* E, int s, int body) {
+    BodyV b;
+    if (body >= 0) { const BdBody& q = E->body[body]; b.px = q.px; b.py = q.py; b.vx = q.vx; b.vy = q.vy; b.vw = q.vw; b.minv = q.minv; b.iinv = q.iinv; }
+    else { int k = s - NROBOT - C.P.NB; b.px = C.S.st_p[k][0]; b.py = C.S.st_p[k][1]; b.vx = b.vy = b.vw = 0.0; b.minv = b.iinv = 0.0; }
+    return b;
+}
+
+// cpArbiterUpdate for candidate q (manifold already computed); returns nothing, marks the slot touched this step
+BP_DEV void bd_arb_update(const BdConst& C, BdEnv* E, int q) {
+    int p = E->cand[q];
+    const Manifold& m = E->cman[q];
+    BdSlot& S = bd_slots(E)[p];
+    int sa = C.pair_a[p], sb = C.pair_b[p];
+    ShapeRef A = shape_ref(C, E, sa), B = shape_ref(C, E, sb);
+    BodyV ba = body_view(C, E, sa, A.body), bb = body_view(C, E, sb, B.body);
+    bool fresh = (S.state == SL_NONE);
+    int oc = fresh ? 0 : S.cnt;
+    double jn_new[2] = {0, 0}, jt_new[2] = {0, 0};
+    for (int i = 0; i < m.count; i++)
+        for (int j = 0; j < oc; j++)
+            if (m.hash[i] == S.c[j].hash) { jn_new[i] = S.c[j].jn; jt_new[i] = S.c[j].jt; }
+    for (int i = 0; i < m.count; i++) {
+        ContactRec& c = S.c[i];
+        c.r1x = m.p1[i].x - ba.px; c.r1y = m.p1[i].y - ba.py;
+        c.r2x = m.p2[i].x - bb.px; c.r2y = m.p2[i].y - bb.py;
+        c.hash = m.hash[i]; c.jn = jn_new[i]; c.jt = jt_new[i];
+    }
+    S.cnt = (unsigned char)m.count;
+    S.nx = m.n.x; S.ny = m.n.y;
+    S.e = A.e * B.e; S.u = A.u * B.u;
+    if (fresh || S.state == SL_CACHED) S.state = SL_FIRST;
+    S.stamp = E->stamp;
+}
+
+// prevent_boundary_intersection (box_delivery_env.py:294-311) for candidate q = (moving shape a, type-3 static b).
+// shapes[0] is always `a` here (robot chassis or box precede the statics in shape order: not swapped).
+BP_DEV bool bd_boundary_presolve(const BdConst& C, BdEnv* E, int q) {
+    int p = E->cand[q];
+    BdSlot& S = bd_slots(E)[p];
+    int sa = C.pair_a[p], sb = C.pair_b[p];
+    int body = (sa < NROBOT) ? 0 : 1 + (sa - NROBOT);
+    BdBody& A = E->body[body];
+    int k = sb - NROBOT - C.P.NB;
+    V2 n = mk(S.nx, S.ny);
+    V2 p1 = mk(A.px + S.c[0].r1x, A.py + S.c[0].r1y);
+    V2 p2 = mk(C.S.st_p[k][0] + S.c[0].r2x, C.S.st_p[k][1] + S.c[0].r2y);
+    double depth = dot(p2 - p1, n);
+    V2 cv = mk(A.vx, A.vy);
+    double kk = 2 * dot(cv, n);
+    V2 refl = cv - n * kk;
+    V2 nv = refl * 0.5;
+    V2 corr = n * depth;
+    bd_set_origin(A, bd_origin(A) + corr);
+    A.vx = nv.x; A.vy = nv.y;
+    return depth < 0;
+}
+
+BP_DEV void bd_prestep(const BdConst& C, BdEnv* E, int p) {
+    BdSlot& S = bd_slots(E)[p];
+    int sa = C.pair_a[p], sb = C.pair_b[p];
+    int NB = C.P.NB;
+    BodyV A = body_view(C, E, sa, sa < NROBOT ? 0 : (sa < NROBOT + NB ? 1 + sa - NROBOT : -1));
+    BodyV B = body_view(C, E, sb, sb < NROBOT ? 0 : (sb < NROBOT + NB ? 1 + sb - NROBOT : -1));
+    V2 n = mk(S.nx, S.ny), tn = perp(n);
+    V2 delta = mk(B.px - A.px, B.py - A.py);
+    V2 va = mk(A.vx, A.vy), vb = mk(B.vx, B.vy);
+    for (int i = 0; i < S.cnt; i++) {
+        ContactRec& c = S.c[i];
+        V2 r1 = mk(c.r1x, c.r1y), r2 = mk(c.r2x, c.r2y);
+        double r1n = cross(r1, n), r2n = cross(r2, n);
+        double kn = (A.minv + A.iinv * r1n * r1n) + (B.minv + B.iinv * r2n * r2n);
+        double r1t = cross(r1, tn), r2t = cross(r2, tn);
+        double kt = (A.minv + A.iinv * r1t * r1t) + (B.minv + B.iinv * r2t * r2t);
+        c.nm = 1.0 / kn; c.tm = 1.0 / kt;
+        double dist = dot((r2 - r1) + delta, n);
+        c.bias = -C.P.bias_coef * fmin(0.0, dist + C.P.slop) / C.P.dt;
+        c.jb = 0.0;
+        V2 vr = (vb + perp(r2) * B.vw) - (va + perp(r1) * A.vw);
+        c.bounce = dot(vr, n) * S.e;
+    }
+}
+
+// One solver visit of slot p: warm == true applies the cached impulses (cpArbiterApplyCachedImpulse), otherwise
+// one cpArbiterApplyImpulse.  Bodies of infinite mass are read-only.
+BP_DEV void bd_solve(const BdConst& C, BdEnv* E, int p, bool warm, double dt_coef) {
+    BdSlot& S = bd_slots(E)[p];
+    if (warm && S.state == SL_FIRST) return;
+    int sa = C.pair_a[p], sb = C.pair_b[p];
+    int NB = C.P.NB;
+    int ia_ = sa < NROBOT ? 0 : (sa < NROBOT + NB ? 1 + sa - NROBOT : -1);
+    int ib_ = sb < NROBOT ? 0 : (sb < NROBOT + NB ? 1 + sb - NROBOT : -1);
+    BdBody zero; zero.vx = zero.vy = zero.vw = zero.bx = zero.by = zero.bw = 0.0; zero.minv = zero.iinv = 0.0;
+    BdBody* PA = ia_ >= 0 ? &E->body[ia_] : &zero;
+    BdBody* PB = ib_ >= 0 ? &E->body[ib_] : &zero;
+    double ma = PA->minv, ia = PA->iinv, mb = PB->minv, ib = PB->iinv;
+    V2 n = mk(S.nx, S.ny), tn = perp(n);
+    V2 va = mk(PA->vx, PA->vy), vb = mk(PB->vx, PB->vy);
+    double wa = PA->vw, wb = PB->vw;
+    V2 ba = mk(PA->bx, PA->by), bb = mk(PB->bx, PB->by);
+    double bwa = PA->bw, bwb = PB->bw;
+    for (int i = 0; i < S.cnt; i++) {
+        ContactRec& c = S.c[i];
+        V2 r1 = mk(c.r1x, c.r1y), r2 = mk(c.r2x, c.r2y);
+        if (warm) {
+            V2 j = rotv(n, mk(c.jn, c.jt)) * dt_coef, nj = neg(j);
+            va = va + nj * ma; wa += ia * cross(r1, nj);
+            vb = vb + j * mb; wb += ib * cross(r2, j);
+            continue;
+        }
+        V2 vb1 = ba + perp(r1) * bwa, vb2 = bb + perp(r2) * bwb;
+        V2 vr = (vb + perp(r2) * wb) - (va + perp(r1) * wa);
+        double vbn = dot(vb2 - vb1, n), vrn = dot(vr, n), vrt = dot(vr, tn);
+        double jbn = (c.bias - vbn) * c.nm;
+        double jbnOld = c.jb;
+        double jb = fmax(jbnOld + jbn, 0.0);
+        double jn = -(c.bounce + vrn) * c.nm;
+        double jnOld = c.jn;
+        double jnAcc = fmax(jnOld + jn, 0.0);
+        double jtMax = S.u * jnAcc;
+        double jt = -vrt * c.tm;
+        double jtOld = c.jt;
+        double jtAcc = clampd(jtOld + jt, -jtMax, jtMax);
+        c.jb = jb; c.jn = jnAcc; c.jt = jtAcc;
+        V2 jbv = n * (jb - jbnOld), njbv = neg(jbv);
+        ba = ba + njbv * ma; bwa += ia * cross(r1, njbv);
+        bb = bb + jbv * mb; bwb += ib * cross(r2, jbv);
+        V2 j = rotv(n, mk(jnAcc - jnOld, jtAcc - jtOld)), nj = neg(j);
+        va = va + nj * ma; wa += ia * cross(r1, nj);
+        vb = vb + j * mb; wb += ib * cross(r2, j);
+    }
+    if (ma != 0.0 || ia != 0.0) { PA->vx = va.x; PA->vy = va.y; PA->vw = wa; PA->bx = ba.x; PA->by = ba.y; PA->bw = bwa; }
+    if (mb != 0.0 || ib != 0.0) { PB->vx = vb.x; PB->vy = vb.y; PB->vw = wb; PB->bx = bb.x; PB->by = bb.y; PB->bw = bwb; }
+}
+
+// ------------------------------------------------------------------ one substep (cpSpaceStep) for one env, one warp
+BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
+    const int lane = bp_lane();
+    const BdParams& P = C.P;
+    const int NB = P.NB;
+    const BdLayout& L = C.layouts[E->layout];
+    BdSlot* slots = bd_slots(E);
+    const double dt = P.dt;
+    // arbiters solved in the previous step leave FIRST_COLLISION
+    for (int k = lane; k < E->n_order; k += BP_NL) { BdSlot& S = slots[E->order[k]]; if (S.state != SL_NONE) S.state = SL_NORMAL; }
+    bp_wsync();
+    if (lane == 0) { E->stamp++; E->stat_substeps++; }
+    // 1. integrate positions (kinematic robot + live boxes), refresh the shapes
+    for (int b = lane; b <= NB; b += BP_NL) {
+        BdBody& B = E->body[b];
+        if (b > 0 && !B.alive) continue;
+        B.px = B.px + (B.vx + B.bx) * dt; B.py = B.py + (B.vy + B.by) * dt;
+        B.pa = B.pa + (B.vw + B.bw) * dt;
+        bp_sincos(B.pa, &B.rs, &B.rc);
+        B.bx = 0.0; B.by = 0.0; B.bw = 0.0;
+    }
+    bp_wsync();
+    for (int s = lane; s < NROBOT + NB; s += BP_NL) {
+        if (s < NROBOT) {
+            const BdBody& B = E->body[0];
+            cache_shape(&C.S.rb_lv[s][0][0], C.S.rb_nv[s], C.S.rb_rad[s], B.rc, B.rs, B.px, B.py, 0.0, 0.0, &E->wv[s][0][0], &E->bb[s]);
+        } else {
+            int i = s - NROBOT; const BdBody& B = E->body[1 + i];
+            if (!B.alive) continue;
+            cache_shape(&L.box_lv[i][0][0], SV, C.S.box_rad, B.rc, B.rs, B.px, B.py, B.cgx, B.cgy, &E->wv[s][0][0], &E->bb[s]);
+        }
+    }
+    bp_wsync();
+    const int stamp = E->stamp;
+    // 2. broadphase over the dense pair table (ballot compaction keeps the canonical order)
+    int nc = 0;
+    for (int base = 0; base < P.n_slots; base += BP_NL) {
+        int p = base + lane;
+        bool take = false;
+        if (p < P.n_slots) {
+            int sa = C.pair_a[p], sb = C.pair_b[p];
+            bool alive = true;
+            if (sa >= NROBOT) alive = E->body[1 + sa - NROBOT].alive;
+            if (sb >= NROBOT && sb < NROBOT + NB) alive = alive && E->body[1 + sb - NROBOT].alive;
+            if (alive) {
+                BBox A = E->bb[sa];
+                BBox B = (sb < NROBOT + NB) ? E->bb[sb] : C.S.st_bb[sb - NROBOT - NB];
+                take = (A.l <= B.r && B.l <= A.r && A.b <= B.t && B.b <= A.t);
+            }
+        }
+        int tot; int rk = bp_wrank(take, &tot);
+        if (take && nc + rk < MAXCAND) E->cand[nc + rk] = (short)p;
+        nc += tot;
+    }
+    if (nc > MAXCAND) { nc = MAXCAND; if (lane == 0) E->status |= BD_CAND_OVERFLOW; }
+    bp_wsync();
+    // 3. narrowphase, lanes over candidates (pure geometry on the cached world vertices)
+    for (int q = lane; q < nc; q += BP_NL) {
+        int p = E->cand[q];
+        int sa = C.pair_a[p], sb = C.pair_b[p];
+        ShapeRef A = shape_ref(C, E, sa), B = shape_ref(C, E, sb);
+        Poly PA; PA.v = A.v; PA.n = A.n; Poly PB; PB.v = B.v; PB.n = B.n;
+        BdSlot& S = slots[p];
+        unsigned gid = (S.state != SL_NONE) ? S.gjk : 0u;
+        Closest pts; unsigned hint = 0; int iters = 0, capped = 0;
+        bool inside = gjk_only(PA, PB, bb_centre(A.bb), bb_centre(B.bb), gid, &pts, &hint, &iters, &capped);
+        if (inside) pts = gjk_epa(PA, PB, hint, &capped);
+        Manifold m; bd_manifold(A, B, pts, &m);
+        E->cman[q] = m; E->ccnt[q] = (unsigned char)m.count;
+        if (S.state != SL_NONE || m.count > 0) S.gjk = pts.id;
+    }
+    bp_wsync();
+    // 4. arbiter updates + handlers, in an order equivalent to the sequential canonical sweep:
+    //    (chassis, box) -> (chassis, wall)* sequential, edits the robot -> everything else except (box, wall)
+    //    -> (box i, wall)* sequential per box, boxes in parallel.
+    const int seg0 = NB, seg1 = NB + P.n_s3;
+    for (int q = lane; q < nc; q += BP_NL) if (E->ccnt[q] && E->cand[q] < seg0) bd_arb_update(C, E, q);
+    bp_wsync();
+    if (lane == 0) {
+        for (int q = 0; q < nc; q++) {
+            int p = E->cand[q];
+            if (p < seg0 || p >= seg1 || !E->ccnt[q]) continue;
+            bd_arb_update(C, E, q);
+            E->robot_hit = bd_boundary_presolve(C, E, q) ? 1 : 0;
+            // kinematic vs static: never solved — contacts dropped, state back to NORMAL
+            BdSlot& S = slots[p]; S.cnt = 0; S.state = SL_NORMAL;
+        }
+    }
+    bp_wsync();
+    for (int q = lane; q < nc; q += BP_NL) {
+        int p = E->cand[q];
+        if (p < seg1 || !E->ccnt[q]) continue;
+        if (C.pair_b[p] >= NROBOT + NB) continue;       // (box, wall): next pass
+        bd_arb_update(C, E, q);
+    }
+    bp_wsync();
+    for (int i = lane; i < NB; i += BP_NL) {
+        if (!E->body[1 + i].alive) continue;
+        for (int q = 0; q < nc; q++) {
+            int p = E->cand[q];
+            if (!E->ccnt[q] || C.pair_a[p] != NROBOT + i || C.pair_b[p] < NROBOT + NB) continue;
+            bd_arb_update(C, E, q);
+            bd_boundary_presolve(C, E, q);
+        }
+    }
+    bp_wsync();
+    // 5. cache expiry (cpSpaceArbiterSetFilter)
+    for (int p = lane; p < P.n_slots; p += BP_NL) {
+        BdSlot& S = slots[p];
+        if (S.state == SL_NONE || S.stamp == stamp) continue;
+        int ticks = stamp - S.stamp;
+        if (ticks >= 1 && S.state != SL_CACHED) S.state = SL_CACHED;
+        if (ticks >= P.persistence) S.state = SL_NONE;
+    }
+    // 6. solve list in canonical order, then greedy colours over the dynamic bodies (lane 0; <= a few dozen entries)
+    if (lane == 0) {
+        int n = 0;
+        short list[MAXCAND]; unsigned char col[MAXCAND];
+        unsigned used[1 + MAXBOX];
+        for (int b = 0; b <= NB; b++) used[b] = 0u;
+        int maxc = 0;
+        for (int q = 0; q < nc; q++) {
+            int p = E->cand[q];
+            if (!E->ccnt[q] || (p >= seg0 && p < seg1)) continue;
+            int sa = C.pair_a[p], sb = C.pair_b[p];
+            int ba = sa < NROBOT ? 0 : 1 + sa - NROBOT;
+            int bb = sb < NROBOT + NB ? 1 + sb - NROBOT : -1;
+            unsigned m = (ba > 0 ? used[ba] : 0u) | (bb > 0 ? used[bb] : 0u);
+            int c = __ffs(~m) - 1;
+            if (c < 0 || c >= MAXCOLOUR) { c = MAXCOLOUR - 1; E->status |= BD_COLOUR_OVERFLOW; }
+            if (ba > 0) used[ba] |= 1u << c;
+            if (bb > 0) used[bb] |= 1u << c;
+            list[n] = (short)p; col[n] = (unsigned char)c; n++;
+            if (c > maxc) maxc = c;
+        }
+        int k = 0;
+        for (int c = 0; c <= maxc && n > 0; c++)
+            for (int i = 0; i < n; i++) if (col[i] == c) { E->order[k] = list[i]; E->cman[k].count = c; k++; }   // cman[k].count reused: colour of order[k]
+        E->n_order = n;
+        E->stat_cand += nc; E->stat_arb += n;
+    }
+    bp_wsync();
+    const int n_order = E->n_order;
+    // 7. pre-step, velocity update (dynamic bodies only), warm start, iterations
+    for (int k = lane; k < n_order; k += BP_NL) bd_prestep(C, E, E->order[k]);
+    bp_wsync();
+    for (int b = 1 + lane; b <= NB; b += BP_NL) {
+        BdBody& B = E->body[b];
+        if (!B.alive) continue;
+        B.vx = B.vx * P.damp + (0.0 + 0.0 * B.minv) * dt;
+        B.vy = B.vy * P.damp + (0.0 + 0.0 * B.minv) * dt;
+        B.vw = B.vw * P.damp + 0.0 * B.iinv * dt;
+    }
+    bp_wsync();
+    const double dt_coef = (E->prev_dt == 0.0) ? 0.0 : dt / E->prev_dt;
+    for (int it = -1; it < P.iterations; it++) {
+        int k0 = 0;
+        while (k0 < n_order) {
+            int c = E->cman[k0].count, k1 = k0;
+            while (k1 < n_order && E->cman[k1].count == c) k1++;
+            for (int k = k0 + lane; k < k1; k += BP_NL) bd_solve(C, E, E->order[k], it < 0, dt_coef);
+            bp_wsync();
+            k0 = k1;
+        }
+    }
+    if (lane == 0) E->prev_dt = dt;
+    bp_wsync();
+}
+
+// space.remove(box.body, box): the body leaves the world, its arbiters are dropped
+BP_DEV void bd_remove_box(const BdConst& C, BdEnv* E, int i) {
+    E->body[1 + i].alive = 0;
+    BdSlot* slots = bd_slots(E);
+    for (int p = 0; p < C.P.n_slots; p++)
+        if (C.pair_a[p] == NROBOT + i || C.pair_b[p] == NROBOT + i) slots[p].state = SL_NONE;
+}
+
+// Space.point_query(p, 0, ShapeFilter()) restricted to the static shapes: bit (1 << ctype) per shape that strictly
+// contains p (cpPolyShapePointQuery: distance = (outside ? d : -d) - r, reported when < 0)
+BP_DEV int bd_point_query_static(const BdConst& C, V2 p) {
+    int mask = 0;
+    for (int k = 0; k < C.P.n_static; k++) {
+        const BBox& bb = C.S.st_bb[k];
+        if (!(p.x <= bb.r && bb.l <= p.x && p.y <= bb.t && bb.b <= p.y)) continue;
+        int n = C.S.st_nv[k];
+        V2 v0 = mk(C.S.st_v[k][n - 1][0], C.S.st_v[k][n - 1][1]);
+        double minDist = INFINITY; bool outside = false;
+        for (int i = 0; i < n; i++) {
+            V2 v1 = mk(C.S.st_v[k][i][0], C.S.st_v[k][i][1]);
+            V2 nn = mk(C.S.st_n[k][i][0], C.S.st_n[k][i][1]);
+            if (dot(nn, p - v1) > 0.0) outside = true;
+            V2 d2 = v0 - v1;
+            double t = clamp01(dot(d2, p - v1) / dot(d2, d2));
+            V2 closest = v1 + d2 * t;
+            V2 dd = p - closest;
+            double dist = sqrt(dot(dd, dd));
+            if (dist < minDist) minDist = dist;
+            v0 = v1;
+        }
+        double dist = (outside ? minDist : -minDist) - C.S.st_rad[k];
+        if (dist < 0.0) mask |= 1 << C.S.st_ctype[k];
+    }
+    return mask;
+}
+
+}  // namespace bd
+}  // namespace bp

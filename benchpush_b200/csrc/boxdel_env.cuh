@@ -1,0 +1,471 @@
+// box-delivery-v0 environment logic on top of boxdel_core.cuh: reset, the position-control chain, the
+// controller / until-still substep loops, rewards, work, termination.
+//
+// Follows BoxDeliveryEnv (reference benchpush/environments/box_delivery/box_delivery_env.py):
+//   reset :571-632 (init_box_delivery_env :231-292, 1000 settle substeps :278-279),
+//   step :634-830, controller :867-889 (DP.ideal_control dp.py:217-248, TargetCourse dp.py:63-117 with
+//   metrics.py:176-181 path_length), execute_robot_path :891-988, step_simulation_until_still :990-1023,
+//   shortest_path :1209-1264 (== position_controller.py:126-181), shortest_path_distance :1266-1268,
+//   PositionController.get_waypoints_to_spatial_action position_controller.py:56-124.
+// Third-party primitives restated: skimage.draw.line (Bresenham of skimage/draw/_draw.pyx::_line),
+// skimage.measure.approximate_polygon (iterative Douglas-Peucker, skimage/measure/_polygon.py).
+#pragma once
+#include "boxdel_core.cuh"
+#include "spfa.cuh"
+
+namespace bp {
+namespace bd {
+
+constexpr double BD_PI = 3.141592653589793;
+constexpr double MOVE_STEP_SIZE = 0.05;
+constexpr double TURN_STEP_SIZE = 0.2617993877991494;          // np.radians(15)
+constexpr double WAYPOINT_MOVING_THRESHOLD = 0.6;
+constexpr double WAYPOINT_TURNING_THRESHOLD = 0.17453292519943295;   // np.radians(10)
+constexpr double NOT_MOVING_THRESHOLD = 0.005;
+constexpr double NONMOVEMENT_DIST_THRESHOLD = 0.05;
+constexpr double NONMOVEMENT_TURN_THRESHOLD = 0.0008726646259971648; // np.radians(0.05)
+constexpr int STEP_LIMIT = 10000;
+
+struct BdOut {                    // device pointers owned by the caller (all optional)
+    double* reward;               // [E]
+    unsigned char* terminated;    // [E]
+    unsigned char* truncated;     // [E]
+    double* info;                 // [E][8]: state x, y, angle (2 dp), cumulative_distance, cumulative_reward, total_work, ministeps, work
+    int* info_i;                  // [E][4]: cumulative_boxes, inactivity, boxes left, status
+    unsigned char* completed;     // [E][NB] box_completed_statuses
+    double* box_verts;            // [E][NB][4][2] info['obs'] (first `boxes left` rows valid)
+};
+
+// np.mod(h + pi, 2 pi) - pi
+BP_DEV double np_mod(double a, double b) {
+    double m = fmod(a, b);
+    if (m != 0.0) { if ((b < 0) != (m < 0)) m += b; } else m = copysign(0.0, b);
+    return m;
+}
+BP_DEV double restrict_heading(double h) { return np_mod(h + BD_PI, 2 * BD_PI) - BD_PI; }
+BP_DEV double heading_diff(double a, double b) { return restrict_heading(a - b); }
+BP_DEV double dist2(double ax, double ay, double bx, double by) { double dx = ax - bx, dy = ay - by; return sqrt(dx * dx + dy * dy); }
+BP_DEV double sgn(double x) { return (x > 0) - (x < 0); }
+BP_DEV double round2dp(double x) { return rint(x * 100.0) / 100.0; }
+
+BP_DEV void pos_to_pixel(const BdParams& P, double x, double y, int* i, int* j) {
+    int pi = (int)floor(P.H / 2.0 - y * P.ppm), pj = (int)floor(P.W / 2.0 + x * P.ppm);
+    *i = pi < 0 ? 0 : (pi > P.H - 1 ? P.H - 1 : pi);
+    *j = pj < 0 ? 0 : (pj > P.W - 1 ? P.W - 1 : pj);
+}
+BP_DEV void pixel_to_pos(const BdParams& P, int i, int j, double* x, double* y) {
+    *x = (j - P.W / 2.0) / P.ppm; *y = (P.H / 2.0 - i) / P.ppm;
+}
+BP_DEV void closest_valid(const BdConst& C, int i, int j, int* ci, int* cj) {
+    size_t nv = (size_t)C.P.H * C.P.W;
+    *ci = C.closest[(size_t)i * C.P.W + j]; *cj = C.closest[nv + (size_t)i * C.P.W + j];
+}
+
+// skimage.draw.line iterator: calls f(r, c) for every pixel, both ends included
+template <class F>
+BP_DEV void sk_line(int r0, int c0, int r1, int c1, F f) {
+    int steep = 0, r = r0, c = c0;
+    int dr = abs(r1 - r0), dc = abs(c1 - c0);
+    int sc = (c1 - c) > 0 ? 1 : -1, sr = (r1 - r) > 0 ? 1 : -1;
+    if (dr > dc) { steep = 1; int t = c; c = r; r = t; t = dc; dc = dr; dr = t; t = sc; sc = sr; sr = t; }
+    int d = 2 * dr - dc;
+    for (int i = 0; i < dc; i++) {
+        if (steep) f(c, r); else f(r, c);
+        while (d >= 0) { r += sr; d -= 2 * dc; }
+        c += sc; d += 2 * dr;
+    }
+    f(r1, c1);
+}
+BP_DEV bool line_free(const uint8_t* map, int W, int r0, int c0, int r1, int c1) {
+    int blocked = 0;
+    sk_line(r0, c0, r1, c1, [&](int r, int c) { if (!map[(size_t)r * W + c]) blocked++; });
+    return blocked == 0;
+}
+
+// ------------------------------------------------------------------ reset
+BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) {
+    const int lane = bp_lane();
+    const BdParams& P = C.P;
+    const BdLayout& L = C.layouts[layout];
+    BdSlot* slots = bd_slots(E);
+    for (int p = lane; p < P.n_slots; p += BP_NL) { slots[p].state = SL_NONE; slots[p].cnt = 0; slots[p].stamp = 0; slots[p].gjk = 0; }
+    if (lane == 0) {
+        E->layout = layout; E->episode = episode; E->t = 0; E->status = 0; E->stamp = 0; E->n_order = 0; E->robot_hit = 0;
+        E->inactivity = 0; E->cum_boxes = 0; E->done = 0; E->truncated = 0; E->n_path = 0; E->need_spfa = 0;
+        E->prev_dt = 0.0; E->cum_distance = 0.0; E->cum_reward = 0.0; E->total_work = 0.0; E->last_work = 0.0; E->reward = 0.0; E->ministeps = 0.0;
+        E->stat_substeps = 0; E->stat_cand = 0; E->stat_arb = 0;
+        BdBody& R = E->body[0];
+        R.px = L.start[0]; R.py = L.start[1]; R.pa = L.start[2];
+        R.vx = R.vy = R.vw = R.bx = R.by = R.bw = 0.0; R.minv = R.iinv = 0.0; R.cgx = R.cgy = 0.0; R.alive = 1; R.idx = -1;
+        bp_sincos(R.pa, &R.rs, &R.rc);
+    }
+    for (int i = lane; i < P.NB; i += BP_NL) {
+        BdBody& B = E->body[1 + i];
+        B.alive = i < L.n_boxes; B.idx = i;
+        B.pa = L.box_init[i][2];
+        bp_sincos(B.pa, &B.rs, &B.rc);
+        B.cgx = L.box_cog[i][0]; B.cgy = L.box_cog[i][1];
+        B.minv = L.box_minv[i]; B.iinv = L.box_iinv[i];
+        B.vx = B.vy = B.vw = B.bx = B.by = B.bw = 0.0;
+        bd_set_origin(B, mk(L.box_init[i][0], L.box_init[i][1]));
+        E->completed[i] = 0;
+    }
+    bp_wsync();
+    for (int k = 0; k < P.settle_steps; k++) bd_substep(C, E);
+    // prev_boxes = CostMap.get_obs_from_poly(self.boxes)
+    for (int i = lane; i < P.NB; i += BP_NL) {
+        const BdBody& B = E->body[1 + i];
+        for (int v = 0; v < SV; v++) {
+            V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
+            E->prev_boxes[i][v][0] = w.x; E->prev_boxes[i][v][1] = w.y;
+        }
+    }
+    if (lane == 0) E->n_prev = L.n_boxes;
+    bp_wsync();
+}
+
+// ------------------------------------------------------------------ step, part 1: action -> target, straight-line test
+// Scalar; run by one lane.  action: pixel index (position control) or heading in [-1, 1].
+BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action) {
+    const BdParams& P = C.P;
+    E->t++;
+    E->robot_hit = 0;
+    const BdBody& R = E->body[0];
+    double x0 = R.px, y0 = R.py, h0 = restrict_heading(R.pa);
+    E->init_pos[0] = x0; E->init_pos[1] = y0; E->init_heading = h0;
+    long long spatial;
+    const int LW = P.LW;
+    if (P.action_type == 1) {
+        // box_delivery_env.py:706-723
+        double angle = (action + 1) * BD_PI + BD_PI / 2;
+        double xm = P.step_size * cos(angle), ym = P.step_size * sin(angle);
+        int xp = (int)(LW / 2.0 + xm * P.ppm), yp = (int)(LW / 2.0 - ym * P.ppm);
+        spatial = (long long)yp * LW + xp;
+    } else spatial = (long long)action;
+    int row = (int)(spatial / LW), col = (int)(spatial % LW);
+    // position_controller.py:56-88
+    double x_movement = -P.local_map_width / 2 + (double)col / P.ppm;
+    double y_movement = P.local_map_width / 2 - (double)row / P.ppm;
+    double sld = sqrt(x_movement * x_movement + y_movement * y_movement);
+    double turn = atan2(-x_movement, y_movement);
+    double slh = restrict_heading(h0 + turn);
+    double tx = x0 + sld * cos(slh), ty = y0 + sld * sin(slh);
+    double dxx = tx - x0, dyy = ty - y0;
+    double ratio_x = 1, ratio_y = 1;
+    double bound_x = sgn(tx) * P.room_length / 2, bound_y = sgn(ty) * P.room_width / 2;
+    if (fabs(tx) > fabs(bound_x)) ratio_x = (bound_x - x0) / (tx - x0);
+    if (fabs(ty) > fabs(bound_y)) ratio_y = (bound_y - y0) / (ty - y0);
+    double ratio = fmin(ratio_x, ratio_y);
+    tx = x0 + ratio * dxx; ty = y0 + ratio * dyy;
+    E->tgt[0] = tx; E->tgt[1] = ty;
+    // shortest_path(check_straight=True), first half
+    int si, sj, ti, tj;
+    pos_to_pixel(P, x0, y0, &si, &sj); pos_to_pixel(P, tx, ty, &ti, &tj);
+    if (line_free(C.cspace_thin, P.W, si, sj, ti, tj)) {
+        E->need_spfa = 0; E->n_path = 2;
+        E->path[0][0] = x0; E->path[0][1] = y0; E->path[1][0] = tx; E->path[1][1] = ty;
+    } else {
+        E->need_spfa = 1;
+        closest_valid(C, si, sj, &E->src_i, &E->src_j);
+        closest_valid(C, ti, tj, &E->tgt_i, &E->tgt_j);
+    }
+}
+
+// ------------------------------------------------------------------ path from a distance field (second half of shortest_path)
+// dist = raw spfa_relax output for source (si, sj).  coords / chain / stk: scratch of H*W ints each.  Serial.
+// Writes the waypoints (source first) to out[][2]; returns their count (0 = overflow).
+BP_DEV int bd_extract_path(const BdConst& C, const int* dist, int si, int sj, int ti, int tj,
+                           double sx, double sy, double gx, double gy, int* coords, int* chain, int* stk, double (*out)[3], int max_out) {
+    const BdParams& P = C.P;
+    const int W = P.W, H = P.H;
+    const int s = si * W + sj;
+    // parents walk from the target (coords[0]) towards the source
+    int n = 0, v = ti * W + tj;
+    coords[n++] = v;
+    while (v != s) {
+        int u = spfa_parent_of(C.cspace, H, W, dist, s, v);
+        if (u < 0) break;
+        v = u; coords[n++] = v;
+        if (n >= H * W) break;
+    }
+    // approximate_polygon(coords, tolerance=1)
+    for (int i = 0; i < n; i++) chain[i] = 0;
+    chain[0] = 1; chain[n - 1] = 1;
+    int sp = 0;
+    stk[sp++] = 0; stk[sp++] = n - 1;
+    while (sp > 0) {
+        int end = stk[--sp], start = stk[--sp];
+        double r0 = coords[start] / W, c0 = coords[start] % W, r1 = coords[end] / W, c1 = coords[end] % W;
+        double dr = r1 - r0, dc = c1 - c0;
+        double ang = -atan2(dr, dc);
+        double sa = sin(ang), ca = cos(ang);
+        double segment_dist = c0 * sa + r0 * ca;
+        double best = -INFINITY; int besti = -1; bool any = false;
+        for (int k = start + 1; k < end; k++) {
+            double r = coords[k] / W, c = coords[k] % W;
+            double dr0 = r - r0, dc0 = c - c0, dr1 = r - r1, dc1 = c - c1;
+            double pl0 = dr0 * dr + dc0 * dc, pl1 = -dr1 * dr - dc1 * dc;
+            double d;
+            if (pl0 > 0 && pl1 > 0) d = fabs(r * ca + c * sa - segment_dist);
+            else d = fmin(sqrt(dc0 * dc0 + dr0 * dr0), sqrt(dc1 * dc1 + dr1 * dr1));
+            if (d > 1.0) any = true;
+            if (d > best) { best = d; besti = k; }      // np.argmax: first maximum
+        }
+        if (any) {
+            // push (new_end, end) then (start, new_end): the latter is popped first
+            stk[sp++] = besti; stk[sp++] = end;
+            stk[sp++] = start; stk[sp++] = besti;
+            chain[besti] = 1;
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < n; i++) if (chain[i]) stk[m++] = coords[i];      // stk reused: the simplified chain
+    // line-of-sight pruning on the configuration space
+    int nn = 0;
+    chain[nn++] = stk[0];
+    for (int i = 1; i < m - 1; i++) {
+        int a = chain[nn - 1], b = stk[i + 1];
+        if (!line_free(C.cspace, W, a / W, a % W, b / W, b % W)) chain[nn++] = stk[i];
+    }
+    if (m > 1) chain[nn++] = stk[m - 1];
+    // pixel -> position, reversed (source first)
+    if (nn > max_out) return 0;
+    if (nn < 2) {
+        out[0][0] = sx; out[0][1] = sy; out[1][0] = gx; out[1][1] = gy;
+        return 2;
+    }
+    for (int k = 0; k < nn; k++) {
+        int c = chain[nn - 1 - k];
+        pixel_to_pos(P, c / W, c % W, &out[k][0], &out[k][1]);
+    }
+    out[0][0] = sx; out[0][1] = sy; out[nn - 1][0] = gx; out[nn - 1][1] = gy;
+    return nn;
+}
+
+// ------------------------------------------------------------------ waypoint headings, final-waypoint back-off
+BP_DEV void bd_finalize_path(const BdConst& C, BdEnv* E) {
+    int n = E->n_path;
+    double (*wp)[3] = E->path;
+    wp[0][2] = 0.0;   // None
+    for (int i = 1; i < n; i++) wp[i][2] = restrict_heading(atan2(wp[i][1] - wp[i - 1][1], wp[i][0] - wp[i - 1][0]));
+    double d_end = dist2(wp[n - 2][0], wp[n - 2][1], wp[n - 1][0], wp[n - 1][1]);
+    double signed_dist = d_end - C.P.robot_radius;
+    int move_sign = (int)sgn(signed_dist);
+    if (n > 2 && signed_dist < 0) {
+        wp[n - 2][0] = wp[n - 1][0]; wp[n - 2][1] = wp[n - 1][1];
+        wp[n - 2][2] = restrict_heading(atan2(wp[n - 2][1] - wp[n - 3][1], wp[n - 2][0] - wp[n - 3][0]));
+        move_sign = 1;
+    }
+    E->move_sign = move_sign;
+}
+
+// ------------------------------------------------------------------ step, part 2: execute_robot_path + step_simulation_until_still
+struct BdLoop { int flag; int dp_none; double sp_x, sp_y, al, pl; double cx[2], cy[2]; };
+
+BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS) {
+    const int lane = bp_lane();
+    const BdParams& P = C.P;
+    const BdLayout& L = C.layouts[E->layout];
+    const int n = E->n_path;
+    double (*wp)[3] = E->path;
+    // execute_robot_path (scalar state lives in registers of every lane; only lane 0's copy is used for stores)
+    double pos_x = E->init_pos[0], pos_y = E->init_pos[1], heading = E->init_heading;
+    double robot_distance = 0.0;
+    int wi = 1, sim_steps = 0;
+    bool done_turning = false;
+    double prev_heading_diff = 0.0;
+    if (lane == 0) LS.dp_none = 1;
+    bp_wsync();
+    for (;;) {
+        double hd = heading_diff(heading, wp[wi][2]);
+        if (!(fabs(hd) > TURN_STEP_SIZE && fabs(hd - prev_heading_diff) > 0.001)) done_turning = true;
+        if (lane == 0) {
+            // controller(): DP over the course (wp[wi-1], wp[wi])
+            if (LS.dp_none) {
+                LS.cx[0] = wp[wi - 1][0]; LS.cy[0] = wp[wi - 1][1]; LS.cx[1] = wp[wi][0]; LS.cy[1] = wp[wi][1];
+                double d0 = hypot(pos_x - LS.cx[0], pos_y - LS.cy[0]), d1 = hypot(pos_x - LS.cx[1], pos_y - LS.cy[1]);
+                int ind = (d1 < d0) ? 1 : 0;
+                double ddx = LS.cx[1] - LS.cx[0], ddy = LS.cy[1] - LS.cy[0];
+                LS.pl = sqrt(ddx * ddx + ddy * ddy);
+                LS.al = LS.pl;
+                LS.sp_x = LS.cx[ind]; LS.sp_y = LS.cy[ind];
+                LS.dp_none = 0;
+            }
+            double theta_d = atan2(LS.sp_y - pos_y, LS.sp_x - pos_x);
+            double theta_e = theta_d - heading;
+            theta_e = atan2(sin(theta_e), cos(theta_e));
+            double omega = 1.0 * theta_e / P.ctrl_dt;
+            double ch = cos(heading), sh = sin(heading);
+            double vx = ch * P.target_speed + (-sh) * 0.0, vy = sh * P.target_speed + ch * 0.0;
+            LS.al = LS.al + P.target_speed * P.ctrl_dt;
+            int ind = (LS.pl < LS.al) ? 1 : 0;
+            LS.sp_x = LS.cx[ind]; LS.sp_y = LS.cy[ind];
+            BdBody& R = E->body[0];
+            R.vw = omega * 3;
+            if (!done_turning) { vx = vx * 0; vy = vy * 0; }
+            R.vx = vx * 2; R.vy = vy * 2;
+        }
+        bp_wsync();
+        bd_substep(C, E);
+        pos_x = E->body[0].px; pos_y = E->body[0].py; heading = restrict_heading(E->body[0].pa);
+        prev_heading_diff = hd;
+        if (dist2(wp[wi - 1][0], wp[wi - 1][1], pos_x, pos_y) > MOVE_STEP_SIZE && E->robot_hit) break;
+        if (dist2(pos_x, pos_y, wp[wi][0], wp[wi][1]) < WAYPOINT_MOVING_THRESHOLD && fabs(heading - wp[wi][2]) < WAYPOINT_TURNING_THRESHOLD) {
+            robot_distance += dist2(wp[wi - 1][0], wp[wi - 1][1], pos_x, pos_y);
+            if (wi == n - 1) break;
+            wi++;
+            done_turning = false;
+            if (lane == 0) LS.dp_none = 1;
+            bp_wsync();
+        }
+        sim_steps++;
+        if (sim_steps > STEP_LIMIT) { if (lane == 0) E->status |= BD_STEP_LIMIT; break; }
+    }
+    if (lane == 0) E->robot_distance = robot_distance;
+    bp_wsync();
+    // step_simulation_until_still
+    double prev_x = 0, prev_y = 0;       // lane b < NB: box b; lane NB: robot  (NB + 1 <= 32 lanes; the single-lane emulation loops)
+    bool have_prev = false;
+    sim_steps = 0;
+#if defined(BP_HOST_EMU) || !defined(__CUDACC__)
+    double pvx[1 + MAXBOX], pvy[1 + MAXBOX];
+#endif
+    for (;;) {
+        // un-stick boxes from the walls
+        for (int i = lane; i < P.NB; i += BP_NL) {
+            BdBody& B = E->body[1 + i];
+            if (!B.alive) continue;
+            bool stuck = false;
+            for (int v = 0; v < SV && !stuck; v++) {
+                V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
+                if (bd_point_query_static(C, w) & (1 << 3)) stuck = true;
+            }
+            if (stuck) {
+                V2 o = bd_origin(B);
+                int pi, pj, ni, nj; pos_to_pixel(P, o.x, o.y, &pi, &pj);
+                closest_valid(C, pi, pj, &ni, &nj);
+                double nx, ny; pixel_to_pos(P, ni, nj, &nx, &ny);
+                bd_set_origin(B, mk(nx, ny));
+                B.vx = 0.0; B.vy = 0.0;
+            }
+        }
+        bp_wsync();
+        bool moved = false;
+#if defined(BP_HOST_EMU) || !defined(__CUDACC__)
+        for (int b = 0; b <= P.NB; b++) {
+            const BdBody& B = E->body[b == P.NB ? 0 : 1 + b];
+            if (b < P.NB && !B.alive) continue;
+            V2 o = bd_origin(B);
+            if (have_prev && dist2(pvx[b], pvy[b], o.x, o.y) > NOT_MOVING_THRESHOLD) moved = true;
+            pvx[b] = o.x; pvy[b] = o.y;
+        }
+#else
+        if (lane <= P.NB) {
+            const BdBody& B = E->body[lane == P.NB ? 0 : 1 + lane];
+            if (lane == P.NB || B.alive) {
+                V2 o = bd_origin(B);
+                if (have_prev && dist2(prev_x, prev_y, o.x, o.y) > NOT_MOVING_THRESHOLD) moved = true;
+                prev_x = o.x; prev_y = o.y;
+            }
+        }
+#endif
+        bool done = have_prev && !bp_wany(moved);
+        have_prev = true;
+        bd_substep(C, E);                 // the reference steps once more after deciding that everything is still (:1007-1019)
+        if (done) break;
+        sim_steps++;
+        if (sim_steps > STEP_LIMIT) { if (lane == 0) E->status |= BD_STEP_LIMIT; break; }
+    }
+    (void)prev_x; (void)prev_y;
+    bp_wsync();
+}
+
+// ------------------------------------------------------------------ step, part 3: rewards, removal, work, termination
+// Scalar; run by one lane.
+BP_DEV void bd_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out) {
+    const BdParams& P = C.P;
+    const BdLayout& L = C.layouts[E->layout];
+    double reward = 0.0;
+    int robot_boxes = 0;
+    for (int i = 0; i < P.NB; i++) {
+        BdBody& B = E->body[1 + i];
+        if (!B.alive) continue;
+        double dist_moved = E->init_dist[i] - E->final_dist[i];
+        if (P.use_correct && dist_moved > 0) dist_moved *= P.correct_scale;
+        reward += P.partial_scale * dist_moved;
+        bool inside = true;
+        for (int v = 0; v < SV && inside; v++) {
+            V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
+            if (!(bd_point_query_static(C, w) & (1 << 4))) inside = false;
+        }
+        if (inside) {
+            E->completed[B.idx] = 1; E->inactivity = 0; robot_boxes++; reward += P.goal_reward;
+            B.alive = 2;          // marked; removed below (after the loop, as the reference does)
+        }
+    }
+    for (int i = 0; i < P.NB; i++) if (E->body[1 + i].alive == 2) bd_remove_box(C, E, i);
+    if (E->robot_hit) reward -= P.collision_penalty;
+    const BdBody& R = E->body[0];
+    double heading = restrict_heading(R.pa);
+    double turn = heading_diff(E->init_heading, heading);
+    if (E->robot_distance < NONMOVEMENT_DIST_THRESHOLD && fabs(turn) < NONMOVEMENT_TURN_THRESHOLD) reward -= P.nonmove_penalty;
+    E->cum_distance += E->robot_distance; E->cum_boxes += robot_boxes; E->cum_reward += reward;
+    // work = total_work_done(prev_boxes, updated_boxes): zip pairs the k-th previous polygon with the k-th live box (D10)
+    double work = 0.0;
+    int k = 0;
+    double upd[MAXBOX][SV][2];
+    for (int i = 0; i < P.NB; i++) {
+        const BdBody& B = E->body[1 + i];
+        if (B.alive != 1) continue;
+        for (int v = 0; v < SV; v++) { V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]); upd[k][v][0] = w.x; upd[k][v][1] = w.y; }
+        k++;
+    }
+    int nz = k < E->n_prev ? k : E->n_prev;
+    for (int q = 0; q < nz; q++) {
+        double A, ax, ay, A2, bx, by;
+        area_centroid_abs(&E->prev_boxes[q][0][0], SV, &A, &ax, &ay);
+        area_centroid_abs(&upd[q][0][0], SV, &A2, &bx, &by);
+        double dx = ax - bx, dy = ay - by;
+        work += sqrt(dx * dx + dy * dy) * A;
+    }
+    for (int q = 0; q < k; q++) for (int v = 0; v < SV; v++) { E->prev_boxes[q][v][0] = upd[q][v][0]; E->prev_boxes[q][v][1] = upd[q][v][1]; }
+    E->n_prev = k;
+    E->total_work += work; E->last_work = work;
+    if (robot_boxes == 0) E->inactivity++;
+    int terminated = (E->cum_boxes == P.num_boxes), truncated = 0;
+    if (E->inactivity >= P.inactivity_cutoff) { terminated = 1; truncated = 1; }
+    E->done = terminated; E->truncated = truncated; E->reward = reward;
+    E->ministeps = E->robot_distance / P.ministep;
+    if (out.reward) out.reward[env] = reward;
+    if (out.terminated) out.terminated[env] = (unsigned char)terminated;
+    if (out.truncated) out.truncated[env] = (unsigned char)truncated;
+    if (out.info) {
+        double* o = out.info + (size_t)env * 8;
+        o[0] = round2dp(R.px); o[1] = round2dp(R.py); o[2] = round2dp(R.pa);
+        o[3] = E->cum_distance; o[4] = E->cum_reward; o[5] = E->total_work; o[6] = E->ministeps; o[7] = work;
+    }
+    if (out.info_i) { int* o = out.info_i + (size_t)env * 4; o[0] = E->cum_boxes; o[1] = E->inactivity; o[2] = k; o[3] = E->status; }
+    if (out.completed) for (int i = 0; i < P.NB; i++) out.completed[(size_t)env * P.NB + i] = E->completed[i];
+    if (out.box_verts) {
+        double* o = out.box_verts + (size_t)env * P.NB * SV * 2;
+        for (int q = 0; q < k; q++) for (int v = 0; v < SV; v++) { o[(q * SV + v) * 2] = upd[q][v][0]; o[(q * SV + v) * 2 + 1] = upd[q][v][1]; }
+    }
+}
+// info after reset (box_delivery_env.py:618-630)
+BP_DEV void bd_reset_out(const BdConst& C, BdEnv* E, int env, const BdOut& out) {
+    const BdParams& P = C.P;
+    const BdBody& R = E->body[0];
+    if (out.reward) out.reward[env] = 0.0;
+    if (out.terminated) out.terminated[env] = 0;
+    if (out.truncated) out.truncated[env] = 0;
+    if (out.info) { double* o = out.info + (size_t)env * 8; o[0] = round2dp(R.px); o[1] = round2dp(R.py); o[2] = round2dp(R.pa); o[3] = o[4] = o[5] = o[6] = o[7] = 0.0; }
+    if (out.info_i) { int* o = out.info_i + (size_t)env * 4; o[0] = 0; o[1] = 0; o[2] = E->n_prev; o[3] = E->status; }
+    if (out.completed) for (int i = 0; i < P.NB; i++) out.completed[(size_t)env * P.NB + i] = 0;
+    if (out.box_verts) {
+        double* o = out.box_verts + (size_t)env * P.NB * SV * 2;
+        for (int q = 0; q < E->n_prev; q++) for (int v = 0; v < SV; v++) { o[(q * SV + v) * 2] = E->prev_boxes[q][v][0]; o[(q * SV + v) * 2 + 1] = E->prev_boxes[q][v][1]; }
+    }
+}
+
+}  // namespace bd
+}  // namespace bp

@@ -770,3 +770,5 @@ int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batc
 }
 
 }  // extern "C"
+
+#include "boxdel_api.cuh"

@@ -34,9 +34,9 @@ BP_DEV float i2f(int i) { float f; memcpy(&f, &i, 4); return f; }
 
 struct SpfaShared { int n_next; };
 
+// Relaxation only: on return dist_out holds the fp32 bit patterns of the least fixed point, unreachable cells = 2*H*W.
 // scratch: q0[HW], q1[HW], mark[HW] (ints).  dist_out doubles as the working distance array.
-BP_DEV void spfa_block(SpfaShared& S, const uint8_t* map, int H, int W, int si, int sj, float* dist_out, int32_t* parents,
-                       int* q0, int* q1, int* mark) {
+BP_DEV void spfa_relax(SpfaShared& S, const uint8_t* map, int H, int W, int si, int sj, float* dist_out, int* q0, int* q1, int* mark) {
     const int tid = BP_TID, nt = BP_NT;
     const int nv = H * W;
     const float inf = 2.0f * (float)nv;
@@ -79,6 +79,40 @@ BP_DEV void spfa_block(SpfaShared& S, const uint8_t* map, int H, int W, int si, 
         iter++;
         BP_BSYNC();
     }
+}
+
+// The parent the kernels assign to cell v: the first neighbour u (reference direction order, u + dir[k] = v) with
+// fl32(d[u] + w_k) == d[v]; -1 for the source, blocked and unreachable cells.  `dist` = raw output of spfa_relax.
+BP_DEV int spfa_parent_of(const uint8_t* map, int H, int W, const int* dist, int s, int v) {
+    const float inf = 2.0f * (float)(H * W);
+    const float s2 = sqrtf(2.0f);
+    const int di[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+    const int dj[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
+    float d = i2f(dist[v]);
+    if (v == s || !(d < inf) || !map[v]) return -1;
+    int vi = v / W, vj = v - vi * W;
+    for (int k = 0; k < 8; k++) {
+        int ip = vi - di[k], jp = vj - dj[k];
+        if (ip < 0 || jp < 0 || ip >= H || jp >= W) continue;
+        int u = ip * W + jp;
+        if (!map[u]) continue;
+        float du = i2f(dist[u]);
+        if (du < inf && du + ((k & 1) ? 1.0f : s2) == d) return u;
+    }
+    return -1;
+}
+
+BP_DEV void spfa_block(SpfaShared& S, const uint8_t* map, int H, int W, int si, int sj, float* dist_out, int32_t* parents,
+                       int* q0, int* q1, int* mark) {
+    const int tid = BP_TID, nt = BP_NT;
+    const int nv = H * W;
+    const float inf = 2.0f * (float)nv;
+    const float s2 = sqrtf(2.0f);
+    const int di[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+    const int dj[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
+    int* dist = (int*)dist_out;
+    const int s = si * W + sj;
+    spfa_relax(S, map, H, W, si, sj, dist_out, q0, q1, mark);
     // parents + output convention
     for (int v = tid; v < nv; v += nt) {
         float d = i2f(dist[v]);

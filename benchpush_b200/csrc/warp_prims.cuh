@@ -81,6 +81,7 @@ BP_DEV void bp_prefetch(const void* p, int n_lines) { (void)p; (void)n_lines; }
 #ifndef __CUDACC__
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 #endif
 #endif
 

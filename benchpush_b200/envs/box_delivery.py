@@ -1,0 +1,373 @@
+"""``box-delivery-v0`` as a batched environment on one B200.
+
+Keeps the reference's gym-style API (``BoxDeliveryEnv``, box_delivery_env.py:68-830): ``reset() -> (obs, info)``,
+``step(action) -> (obs, reward, terminated, truncated, info)``, the cfg dict with the same keys and the same
+one-level merge, and the same ``info`` keys — every value with a leading batch dimension, on the GPU as
+torch tensors.  The physics, the position-control chain, the 2 N + 2 shortest-path solves per step and the
+224 x 224 x 4 observation run in ``libbenchpush_b200.so`` (CUDA, sm_100a; csrc/boxdel_*.cuh).
+
+Host work done here, once per handle (not on the hot path): the room's configuration spaces and the
+nearest-free-cell map (``update_configuration_space``, box_delivery_env.py:1140-1175), built with the same
+library calls as the reference (cv2.fillPoly, scipy binary_dilation with a disk footprint, scipy
+distance_transform_edt).  They depend on the room only, so all envs of a handle share them.
+
+Implemented: ``obstacle_config: small_empty`` (any room size without columns / dividers), ``action_type``
+``heading`` and ``position``.  ``velocity`` control, ``low_dim_state`` and the column / divider rooms raise
+NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .. import _lib
+from ..layouts import sample_box_delivery_layout
+from ..utils import DotDict, merge_cfg
+
+# box_delivery/config.yaml restated (reference defaults that reach the hot path)
+DEFAULT_CFG = {
+    "teleop_mode": False, "low_dim_state": False, "fixed_trial_idx": 1, "output_dir": "logs/",
+    "render": {"log_obs": False, "show": False, "show_obs": False, "frequency": 20},
+    "sim": {"t_max": 2000, "steps": 100, "gravity": (0, 0), "iterations": 10, "damping": 0},
+    "controller": {"dt": 0.2, "target_speed": 0.3},
+    "boxes": {"num_boxes_small": 10, "num_boxes_large": 20, "box_size": 0.44, "min_box_dist": 0.62, "box_density": 0.001},
+    "agent": {
+        "action_type": "position", "step_size": 1.75, "random_start": True, "mass": 1, "padding": 0.25,
+        "length": 0.6, "width": 0.92,
+        "vertices": [[0.26, -0.35], [-0.31, -0.35], [-0.31, 0.35], [0.26, 0.35]],
+        "front_bumper_vertices": [[0.31, -0.53], [0.20, -0.39], [0.20, 0.39], [0.31, 0.53]],
+        "wheel_vertices": [
+            [[0.09, 0.35], [0.09, 0.39], [0.24, 0.39], [0.24, 0.35]],
+            [[0.09, -0.39], [0.09, -0.35], [0.24, -0.35], [0.24, -0.39]],
+            [[-0.09, 0.35], [-0.09, 0.39], [-0.24, 0.39], [-0.24, 0.35]],
+            [[-0.09, -0.35], [-0.09, -0.39], [-0.24, -0.39], [-0.24, -0.35]],
+        ],
+    },
+    "env": {"obstacle_config": "small_empty", "room_length": 10, "room_width_small": 5, "room_width_large": 10,
+            "receptacle_width": 1.5, "shortest_path_channel_scale": 0.25, "local_map_pixel_width": 224,
+            "local_map_pixel_width_sam": 96, "local_map_width": 10, "wall_thickness": 14, "invert_receptacle_map": False},
+    "misc": {"ministep_size": 2.5, "inactivity_cutoff_sam": 100, "inactivity_cutoff": 200, "random_seed": 42},
+    "rewards": {"partial_rewards_scale": 0.2, "goal_reward": 10.0, "collision_penalty": 0.25, "non_movement_penalty": 0,
+                "correct_direction_reward_scale": 3},
+    "rewards_sam": {"partial_rewards_scale": 0.2, "goal_reward": 1.0, "collision_penalty": 0.25, "non_movement_penalty": 0.25,
+                    "correct_direction_reward_scale": 1},
+    "train": {"job_type": "ppo", "use_correct_direction_reward": False},
+}
+
+
+class BoxDelConfig(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("num_boxes", C.c_int32), ("device", C.c_int32), ("action_type", C.c_int32),
+        ("steps", C.c_int32), ("iterations", C.c_int32), ("settle_steps", C.c_int32), ("inactivity_cutoff", C.c_int32),
+        ("local_map_pixel_width", C.c_int32), ("use_correct_direction_reward", C.c_int32),
+        ("ctrl_dt", C.c_double), ("target_speed", C.c_double), ("damping", C.c_double),
+        ("box_size", C.c_double), ("box_density", C.c_double),
+        ("room_length", C.c_double), ("room_width", C.c_double), ("receptacle_width", C.c_double),
+        ("local_map_width", C.c_double), ("step_size", C.c_double), ("robot_length", C.c_double), ("robot_width", C.c_double),
+        ("partial_rewards_scale", C.c_double), ("goal_reward", C.c_double), ("collision_penalty", C.c_double),
+        ("non_movement_penalty", C.c_double), ("correct_direction_reward_scale", C.c_double),
+        ("ministep_size", C.c_double), ("shortest_path_channel_scale", C.c_double),
+        ("chassis_verts", C.c_double * 8), ("bumper_verts", C.c_double * 8), ("wheel_verts", C.c_double * 32),
+    ]
+
+
+class BoxDelOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "reward", "terminated", "truncated", "info", "info_i", "completed", "box_verts")]
+
+
+def bind(L):
+    """Declare the bp_boxdel_* signatures on a loaded library (the product library, or the test-only emulation)."""
+    L.bp_boxdel_default_config.argtypes = [C.POINTER(BoxDelConfig)]
+    L.bp_boxdel_default_config.restype = None
+    L.bp_boxdel_create.argtypes = [C.POINTER(BoxDelConfig), C.POINTER(C.c_void_p)]
+    L.bp_boxdel_destroy.argtypes = [C.c_void_p]
+    L.bp_boxdel_load.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + \
+                                [C.c_int32, C.c_int32] + [C.c_void_p] * 5
+    L.bp_boxdel_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
+    L.bp_boxdel_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
+    L.bp_boxdel_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs)]
+    L.bp_boxdel_get_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.bp_boxdel_get_step_debug.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bp_boxdel_launch_count.argtypes = [C.c_void_p]
+    L.bp_boxdel_launch_count.restype = C.c_int64
+    L.bp_boxdel_env_bytes.argtypes = [C.c_void_p]
+    L.bp_boxdel_env_bytes.restype = C.c_size_t
+    return L
+
+
+def disk(radius: int) -> np.ndarray:
+    """skimage.morphology.disk"""
+    r = int(radius)
+    L = np.arange(-r, r + 1)
+    X, Y = np.meshgrid(L, L)
+    return np.array((X ** 2 + Y ** 2) <= r ** 2, dtype=np.uint8)
+
+
+class RoomMaps:
+    """Static shapes and maps of one room (box_delivery_env.py:322-335, 342-358, 472-489, 1098-1175; sim_utils.py:78-131)."""
+
+    def __init__(self, cfg):
+        import cv2
+        from scipy.ndimage import binary_dilation, distance_transform_edt
+        env = cfg["env"]
+        small = env["obstacle_config"].split("_")[0] == "small"
+        self.room_length = rl = env["room_length"]
+        self.room_width = rw = env["room_width_small"] if small else env["room_width_large"]
+        wt = env["wall_thickness"]
+        size = env["receptacle_width"]
+        self.LW = LW = env["local_map_pixel_width"] if cfg["train"]["job_type"] != "sam" else env["local_map_pixel_width_sam"]
+        self.lmw = lmw = env["local_map_width"]
+        self.ppm = ppm = LW / lmw
+        ag = cfg["agent"]
+        self.robot_radius = ((ag["length"] ** 2 + ag["width"] ** 2) ** 0.5 / 2) * 1.2
+        self.robot_half_width = max(ag["length"], ag["width"]) / 2
+        self.receptacle_position = (rl / 2 - size / 2, rw / 2 - size / 2)
+        rect = lambda x, y, l, w: [[x - l / 2, y - w / 2], [x + l / 2, y - w / 2], [x + l / 2, y + w / 2], [x - l / 2, y + w / 2]]
+        # shape creation order: receptacle, walls, corners (generate_sim_bounds)
+        st = [(rect(*self.receptacle_position, size, size), (0.0, 0.0, 0.0), 0.0, 4)]
+        for (x, y, length, width) in [(-rl / 2 - wt / 2, 0, wt, rw), (rl / 2 + wt / 2, 0, wt, rw),
+                                      (0, -rw / 2 - wt / 2, rl + 2 * wt, wt), (0, rw / 2 + wt / 2, rl + 2 * wt, wt)]:
+            st.append((rect(x, y, length, width), (0.0, 0.0, 0.0), 0.0, 3))
+        s225, c225 = np.sin(22.5 * np.pi / 180), np.cos(22.5 * np.pi / 180)
+        tri = [[(0, 0), (0, -1), (0.5 * s225, -1 + 0.5 * c225)],
+               [(0, 0), (0.5 * s225, -1 + 0.5 * c225), (1 - 0.5 * c225, -0.5 * s225)],
+               [(0, 0), (1, 0), (1 - 0.5 * c225, -0.5 * s225)]]
+        for i, (x, y) in enumerate([(-rl / 2, rw / 2), (rl / 2, rw / 2), (rl / 2, -rw / 2), (-rl / 2, -rw / 2)]):
+            if i == 1:
+                continue                      # the receptacle corner
+            heading = -np.radians(i * 90)
+            for vs in tri:
+                st.append(([list(map(float, v)) for v in vs], (float(x), float(y), float(heading)), 0.02, 3))
+        self.statics = st
+        ns = len(st)
+        self.st_nv = np.array([len(s[0]) for s in st], dtype=np.int32)
+        self.st_verts = np.zeros((ns, 4, 2), dtype=np.float64)
+        for k, s in enumerate(st):
+            self.st_verts[k, :len(s[0])] = np.asarray(s[0], dtype=np.float64)
+        self.st_pose = np.array([s[1] for s in st], dtype=np.float64)
+        self.st_rad = np.array([s[2] for s in st], dtype=np.float64)
+        self.st_ctype = np.array([s[3] for s in st], dtype=np.int32)
+        # ---- maps
+        shape = (int(2 * np.ceil((rw * ppm + LW * np.sqrt(2)) / 2)), int(2 * np.ceil((rl * ppm + LW * np.sqrt(2)) / 2)))
+        self.shape = shape
+        obstacle_map = np.ones(shape, dtype=np.float32)
+        small_map = np.zeros((LW + 20, LW + 20), dtype=np.float32)
+        off = int(lmw * ppm / 2) + 10
+        for verts, pose, _, ctype in st:
+            if ctype != 3:
+                continue
+            cs, sn = np.cos(pose[2]), np.sin(pose[2])
+            v = np.asarray(verts, dtype=np.float64)
+            world = np.stack([cs * v[:, 0] - sn * v[:, 1] + pose[0], sn * v[:, 0] + cs * v[:, 1] + pose[1]], axis=1)
+            px = (world * ppm).astype(np.int32)
+            px[:, 0] += off
+            px[:, 1] += off
+            px[:, 1] = small_map.shape[0] - px[:, 1]
+            cv2.fillPoly(small_map, [px], color=1)
+        si, sj = int(shape[0] / 2 - small_map.shape[0] / 2), int(shape[1] / 2 - small_map.shape[1] / 2)
+        obstacle_map[si:si + small_map.shape[0], sj:sj + small_map.shape[1]] = small_map
+        self.configuration_space = 1 - binary_dilation(obstacle_map, disk(np.floor(self.robot_radius * ppm))).astype(np.float32)
+        self.configuration_space_thin = 1 - binary_dilation(obstacle_map, disk(np.floor(self.robot_half_width * ppm))).astype(np.float32)
+        self.closest_cspace_indices = distance_transform_edt(1 - self.configuration_space, return_distances=False, return_indices=True)
+        self.small_obstacle_map = 1 - small_map
+        W = LW
+        robot_pixel_width = int(2 * self.robot_radius * ppm)
+        chan = np.zeros((W, W), dtype=np.float32)
+        start = int(np.floor(W / 2 - robot_pixel_width / 2))
+        ii = np.arange(start, start + robot_pixel_width)
+        I, J = np.meshgrid(ii, ii, indexing="ij")
+        inside = (((I + 0.5) - W / 2) ** 2 + ((J + 0.5) - W / 2) ** 2) ** 0.5 < robot_pixel_width / 2
+        chan[I[inside], J[inside]] = 1
+        self.robot_state_channel = chan
+
+
+class BoxDeliveryVecEnv:
+    metadata = {"render_modes": []}
+
+    def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
+                 seed: Optional[int] = None, _backend=None):
+        self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
+        c = self.cfg
+        if c["env"]["obstacle_config"] not in ("small_empty", "large_empty"):
+            raise NotImplementedError("only the rooms without columns / dividers are implemented (obstacle_config small_empty)")
+        if c["agent"]["action_type"] not in ("heading", "position"):
+            raise NotImplementedError("action_type 'velocity' is not implemented")
+        if c["low_dim_state"] or c["teleop_mode"]:
+            raise NotImplementedError("low_dim_state / teleop_mode are not implemented")
+        if tuple(c["sim"]["gravity"]) != (0, 0):
+            raise NotImplementedError("non-zero gravity is not supported")
+        self.num_envs = E = int(num_envs)
+        self._emu = _backend is not None
+        if self._emu:
+            self._L = bind(_backend)                 # tests/emu only: the kernel sources compiled for the host
+            self.device = None
+            self.device_index = 0
+        else:
+            import torch
+            if not torch.cuda.is_available():
+                raise _lib.BenchPushError("BoxDeliveryVecEnv needs a CUDA device (there is no CPU fallback)")
+            self._L = bind(_lib.lib())
+            self.device_index = torch.cuda.current_device() if device is None else int(device)
+            self.device = torch.device("cuda", self.device_index)
+        small = c["env"]["obstacle_config"].split("_")[0] == "small"
+        self.num_boxes = NB = int(c["boxes"]["num_boxes_small"] if small else c["boxes"]["num_boxes_large"])
+        self.num_channels = 4
+        self.room = RoomMaps(c)
+        self.local_map_pixel_width = LW = self.room.LW
+        self.goal_points = [self.room.receptacle_position]
+        if layouts is None:
+            base = int(c["misc"]["random_seed"]) if seed is None else int(seed)
+            layouts = [sample_box_delivery_layout(np.random.RandomState(base + e), c) for e in range(E)]
+        self.layouts = list(layouts)
+        # ---- native handle
+        L = self._L
+        k = BoxDelConfig()
+        L.bp_boxdel_default_config(C.byref(k))
+        rw = c["rewards_sam"] if c["train"]["job_type"] == "sam" else c["rewards"]
+        k.n_envs = E; k.num_boxes = NB; k.device = self.device_index
+        k.action_type = 1 if c["agent"]["action_type"] == "heading" else 0
+        k.steps = int(c["sim"]["steps"]); k.iterations = int(c["sim"]["iterations"]); k.settle_steps = 1000
+        k.inactivity_cutoff = int(c["misc"]["inactivity_cutoff"] if c["train"]["job_type"] != "sam" else c["misc"]["inactivity_cutoff_sam"])
+        k.local_map_pixel_width = LW; k.use_correct_direction_reward = 1 if c["train"]["use_correct_direction_reward"] else 0
+        k.ctrl_dt = float(c["controller"]["dt"]); k.target_speed = float(c["controller"]["target_speed"]); k.damping = float(c["sim"]["damping"])
+        k.box_size = float(c["boxes"]["box_size"]); k.box_density = float(c["boxes"]["box_density"])
+        k.room_length = float(self.room.room_length); k.room_width = float(self.room.room_width)
+        k.receptacle_width = float(c["env"]["receptacle_width"])
+        k.local_map_width = float(c["env"]["local_map_width"]); k.step_size = float(c["agent"]["step_size"])
+        k.robot_length = float(c["agent"]["length"]); k.robot_width = float(c["agent"]["width"])
+        k.partial_rewards_scale = float(rw["partial_rewards_scale"]); k.goal_reward = float(rw["goal_reward"])
+        k.collision_penalty = float(rw["collision_penalty"]); k.non_movement_penalty = float(rw["non_movement_penalty"])
+        k.correct_direction_reward_scale = float(rw["correct_direction_reward_scale"])
+        k.ministep_size = float(c["misc"]["ministep_size"]); k.shortest_path_channel_scale = float(c["env"]["shortest_path_channel_scale"])
+        for i, v in enumerate(np.asarray(c["agent"]["vertices"], dtype=np.float64).reshape(-1)):
+            k.chassis_verts[i] = float(v)
+        for i, v in enumerate(np.asarray(c["agent"]["front_bumper_vertices"], dtype=np.float64).reshape(-1)):
+            k.bumper_verts[i] = float(v)
+        for i, v in enumerate(np.asarray(c["agent"]["wheel_vertices"], dtype=np.float64).reshape(-1)):
+            k.wheel_verts[i] = float(v)
+        self._h = C.c_void_p()
+        self._check(L.bp_boxdel_create(C.byref(k), C.byref(self._h)))
+        nl = len(self.layouts)
+        starts = np.array([l["start"] for l in self.layouts], dtype=np.float64)
+        nbx = np.array([len(l["boxes"]) for l in self.layouts], dtype=np.int32)
+        boxes = np.zeros((nl, NB, 3), dtype=np.float64)
+        for i, l in enumerate(self.layouts):
+            boxes[i, :len(l["boxes"])] = np.asarray(l["boxes"], dtype=np.float64).reshape(-1, 3)
+        r = self.room
+        cs = np.ascontiguousarray(r.configuration_space.astype(np.uint8))
+        th = np.ascontiguousarray(r.configuration_space_thin.astype(np.uint8))
+        cl = np.ascontiguousarray(r.closest_cspace_indices.astype(np.int32))
+        sm = np.ascontiguousarray(r.small_obstacle_map.astype(np.uint8))
+        rc = np.ascontiguousarray((r.robot_state_channel * 255).astype(np.uint8))
+        self._check(L.bp_boxdel_load(self._h, nl, starts.ctypes.data, nbx.ctypes.data, boxes.ctypes.data, len(r.statics),
+                                     r.st_nv.ctypes.data, r.st_verts.ctypes.data, r.st_pose.ctypes.data, r.st_rad.ctypes.data, r.st_ctype.ctypes.data,
+                                     r.shape[0], r.shape[1], cs.ctypes.data, th.ctypes.data, cl.ctypes.data, sm.ctypes.data, rc.ctypes.data))
+        # ---- buffers
+        self._buf = {}
+        self._alloc("obs", (E, LW, LW, 4), "uint8"); self._alloc("reward", (E,), "float64")
+        self._alloc("terminated", (E,), "uint8"); self._alloc("truncated", (E,), "uint8")
+        self._alloc("info", (E, 8), "float64"); self._alloc("info_i", (E, 4), "int32")
+        self._alloc("completed", (E, NB), "uint8"); self._alloc("box_verts", (E, NB, 4, 2), "float64")
+        self._alloc("actions", (E,), "float32"); self._alloc("layout_ids", (E,), "int32"); self._alloc("mask", (E,), "uint8")
+        o = BoxDelOutputs()
+        for n in ("obs", "reward", "terminated", "truncated", "info", "info_i", "completed", "box_verts"):
+            setattr(o, n, self._ptr(n))
+        self._out = o
+        self.episode_idx = None
+
+    # ---- buffers: torch CUDA tensors (product) or numpy arrays (emulation)
+    def _alloc(self, name, shape, dtype):
+        if self._emu:
+            self._buf[name] = np.zeros(shape, dtype=dtype)
+        else:
+            import torch
+            self._buf[name] = torch.zeros(shape, dtype=getattr(torch, dtype), device=self.device)
+
+    def _ptr(self, name):
+        b = self._buf[name]
+        return b.ctypes.data if self._emu else b.data_ptr()
+
+    def _put(self, name, values):
+        if self._emu:
+            self._buf[name][...] = np.asarray(values, dtype=self._buf[name].dtype).reshape(self._buf[name].shape)
+        else:
+            import torch
+            t = values if isinstance(values, torch.Tensor) else torch.as_tensor(np.asarray(values))
+            self._buf[name].copy_(t.to(self.device).reshape(self._buf[name].shape).to(self._buf[name].dtype))
+
+    def _stream(self):
+        if self._emu:
+            return None
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc < 0:
+            raise _lib.BenchPushError("benchpush_b200 error %d: %s" % (rc, self._L.bp_last_error().decode("utf-8", "replace")
+                                                                       if hasattr(self._L, "bp_last_error") and self._L.bp_last_error.restype is not None
+                                                                       else rc))
+        return rc
+
+    @property
+    def obs(self):
+        return self._buf["obs"]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.bp_boxdel_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- gym API
+    def reset(self, seed=None, options=None, mask=None):
+        """Every env (or those in ``mask``) starts episode ``episode_idx`` on layout (env + episode * num_envs) % n_layouts."""
+        self.episode_idx = 0 if self.episode_idx is None else self.episode_idx + 1
+        ids = (np.arange(self.num_envs) + self.episode_idx * self.num_envs) % len(self.layouts)
+        self._put("layout_ids", ids.astype(np.int32))
+        mptr = None
+        if mask is not None:
+            self._put("mask", mask)
+            mptr = self._ptr("mask")
+        self._check(self._L.bp_boxdel_reset(self._h, self._ptr("layout_ids"), mptr, C.byref(self._out), self._stream()))
+        return self._buf["obs"], self._info()
+
+    def step(self, action, mask=None):
+        self._put("actions", action)
+        mptr = None
+        if mask is not None:
+            self._put("mask", mask)
+            mptr = self._ptr("mask")
+        self._check(self._L.bp_boxdel_step(self._h, self._ptr("actions"), mptr, C.byref(self._out), self._stream()))
+        b = self._buf
+        term = b["terminated"].astype(bool) if self._emu else b["terminated"].bool()
+        trunc = b["truncated"].astype(bool) if self._emu else b["truncated"].bool()
+        return b["obs"], b["reward"], term, trunc, self._info()
+
+    def _info(self):
+        b = self._buf
+        info, ii = b["info"], b["info_i"]
+        return {"state": info[:, 0:3], "cumulative_distance": info[:, 3], "cumulative_boxes": ii[:, 0], "cumulative_reward": info[:, 4],
+                "total_work": info[:, 5], "obs": b["box_verts"], "n_boxes_left": ii[:, 2], "box_completed_statuses": b["completed"],
+                "goal_positions": self.goal_points, "ministeps": info[:, 6], "inactivity": ii[:, 1], "status": ii[:, 3], "work": info[:, 7]}
+
+    # ---- parity / debugging aids
+    def get_bodies(self, e: int) -> np.ndarray:
+        out = np.zeros((1 + self.num_boxes, 7), dtype=np.float64)
+        self._check(self._L.bp_boxdel_get_bodies(self._h, int(e), out.ctypes.data))
+        return out
+
+    def get_step_debug(self, e: int):
+        o = np.zeros(16, dtype=np.float64)
+        d = np.zeros((2, self.num_boxes), dtype=np.float64)
+        p = np.zeros((24, 3), dtype=np.float64)
+        self._check(self._L.bp_boxdel_get_step_debug(self._h, int(e), o.ctypes.data, d.ctypes.data, p.ctypes.data))
+        return {"n_path": int(o[0]), "move_sign": int(o[1]), "need_spfa": int(o[2]), "status": int(o[3]), "robot_hit": int(o[4]),
+                "substeps": int(o[5]), "candidates": int(o[6]), "arbiters": int(o[7]), "robot_distance": float(o[8]),
+                "init_dist": d[0], "final_dist": d[1], "path": p[:int(o[0])]}

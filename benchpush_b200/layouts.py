@@ -265,3 +265,45 @@ def pack_maze_layouts(layouts, max_boxes: int | None = None):
         if len(l):
             cen[i, :len(l)] = np.asarray(l, dtype=np.float64).reshape(-1, 2)
     return nb, cen
+
+
+def sample_box_delivery_layout(random_state, cfg) -> dict:
+    """One box-delivery episode layout drawn the way the reference draws it (box_delivery_env.py:313-320
+    get_random_robot_start, :509-546 generate_boxes) for a room without columns / dividers: the robot start
+    first (when cfg.agent.random_start), then boxes by rejection sampling against the receptacle and the boxes
+    placed so far.  ``random_state`` is a numpy RandomState (the reference shares RandomState(cfg.misc.random_seed)
+    across episodes; a vector env gives each env its own stream)."""
+    env, ag, bx = cfg["env"], cfg["agent"], cfg["boxes"]
+    room_length = env["room_length"]
+    small = env["obstacle_config"].split("_")[0] == "small"
+    room_width = env["room_width_small"] if small else env["room_width_large"]
+    num_boxes = bx["num_boxes_small"] if small else bx["num_boxes_large"]
+    if ag["random_start"]:
+        size = max(ag["length"], ag["width"])
+        x = random_state.uniform(-room_length / 2 + size, room_length / 2 - size)
+        y = random_state.uniform(-room_width / 2 + size, room_width / 2 - size)
+        heading = random_state.uniform(0, 2 * np.pi)
+        start = (float(x), float(y), float(heading))
+    else:
+        start = (5.0, 1.5, float(np.pi * 3 / 2))
+    rsize = env["receptacle_width"]
+    rx, ry = room_length / 2 - rsize / 2, room_width / 2 - rsize / 2
+    half = bx["box_size"] / 2
+    dmin = bx["min_box_dist"]
+    min_x, max_x = -room_length / 2 + half, room_length / 2 - half
+    min_y, max_y = -room_width / 2 + half, room_width / 2 - half
+    boxes = []
+    while len(boxes) < num_boxes:
+        cx = random_state.uniform(min_x, max_x)
+        cy = random_state.uniform(min_y, max_y)
+        hd = random_state.uniform(0, 2 * np.pi)
+        # the receptacle is the only boundary that is neither wall nor corner in an empty room ('width' = its size)
+        ok = not (((cx - rx) ** 2 + (cy - ry) ** 2) ** 0.5 <= (dmin / 2 + rsize / 2) * 1.2)
+        if ok:
+            for px, py, _ in boxes:
+                if ((cx - px) ** 2 + (cy - py) ** 2) ** 0.5 <= dmin:
+                    ok = False
+                    break
+        if ok:
+            boxes.append([float(cx), float(cy), float(hd)])
+    return {"start": start, "boxes": boxes}

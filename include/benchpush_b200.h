@@ -239,6 +239,62 @@ int bp_spfa_batch(const uint8_t* maps, const int32_t* sources, int32_t batch, in
 int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t height, int32_t width,
                        float* dists, int32_t* parents);
 
+/* ------------------------------------------------------------------------------------------------
+ * box-delivery-v0.  Replaces BoxDeliveryEnv.reset / step / generate_observation
+ * (benchpush/environments/box_delivery/box_delivery_env.py:571-632, 634-830, 1045-1059), the
+ * pymunk.Space it drives with its collision handlers (:185-229, 294-311, 765-767), the position-control
+ * chain (benchpush/common/controller/position_controller.py:56-181, dp.py:217-248) and the 2 N + 2..3
+ * spfa.spfa calls per step (:651-655, 736-740, 1115-1138, 1226) for a batch of independent environments.
+ * The room maps (configuration spaces, closest-free-cell indices, small obstacle map: :1140-1175) are
+ * per-handle inputs built by the host mirror with the libraries the reference itself calls.
+ * Observation: u8 [n_envs][224][224][4] (HWC, as the reference stacks the channels on axis 2).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bp_boxdel bp_boxdel_t;
+
+typedef struct bp_boxdel_config {
+    int32_t n_envs, num_boxes, device;
+    int32_t action_type;          /* 0 = position (pixel index), 1 = heading in [-1, 1] (cfg.agent.action_type) */
+    int32_t steps, iterations, settle_steps, inactivity_cutoff;   /* cfg.sim.steps / iterations, 1000, cfg.misc.inactivity_cutoff */
+    int32_t local_map_pixel_width, use_correct_direction_reward;
+    double ctrl_dt, target_speed, damping;                        /* cfg.controller.dt / target_speed, cfg.sim.damping */
+    double box_size, box_density;
+    double room_length, room_width, receptacle_width;
+    double local_map_width, step_size, robot_length, robot_width;
+    double partial_rewards_scale, goal_reward, collision_penalty, non_movement_penalty, correct_direction_reward_scale;
+    double ministep_size, shortest_path_channel_scale;
+    double chassis_verts[8], bumper_verts[8], wheel_verts[32];   /* cfg.agent.vertices / front_bumper_vertices / wheel_vertices */
+} bp_boxdel_config;
+
+typedef struct bp_boxdel_outputs {  /* every pointer optional */
+    uint8_t* obs;                 /* [E][224][224][4] */
+    double* reward;               /* [E] */
+    uint8_t* terminated;          /* [E] */
+    uint8_t* truncated;           /* [E] */
+    double* info;                 /* [E][8]: state x, y, angle (2 dp), cumulative_distance, cumulative_reward, total_work, ministeps, work of this step */
+    int32_t* info_i;              /* [E][4]: cumulative_boxes, inactivity, boxes left, env status bits */
+    uint8_t* completed;           /* [E][num_boxes] box_completed_statuses */
+    double* box_verts;            /* [E][num_boxes][4][2] info['obs'] (first `boxes left` polygons valid) */
+} bp_boxdel_outputs;
+
+void bp_boxdel_default_config(bp_boxdel_config* cfg);
+int bp_boxdel_create(const bp_boxdel_config* cfg, bp_boxdel_t** out);
+int bp_boxdel_destroy(bp_boxdel_t* h);
+/* HOST pointers; see csrc/boxdel_api.cuh for the array shapes */
+int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                   int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                   int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
+                   const uint8_t* small_free, const uint8_t* robot_chan);
+/* DEVICE pointers, enqueued on `stream`, no host synchronisation */
+int bp_boxdel_reset(bp_boxdel_t* h, const int32_t* layout_ids, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream);
+int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream);
+/* HOST buffers: copies in, steps, copies out, synchronises */
+int bp_boxdel_step_host(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host);
+/* HOST out[(1 + num_boxes)][7]: origin x, y, angle, vx, vy, w, alive; row 0 = robot */
+int bp_boxdel_get_bodies(bp_boxdel_t* h, int32_t env, double* out);
+int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double* dists, double* path);
+int64_t bp_boxdel_launch_count(bp_boxdel_t* h);
+size_t bp_boxdel_env_bytes(bp_boxdel_t* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,7 @@ struct Body {
     V f; cpFloat t;
     Transform tr;
     std::vector<int> shapes;
+    bool removed = false;   // space.remove(body, shape): box_delivery_env.py:765-767
 };
 
 struct Plane { V v0, n; };
@@ -215,6 +216,12 @@ struct Space {
     // collision-handler bookkeeping: number of pre_solve calls this far for shape pairs whose
     // collision types are {1, 3} (robot chassis vs maze wall: maze_NAMO_env.py:203-216)
     long long hits_13;
+    // handler_mode 1 = box-delivery / area-clearing handler set (box_delivery_env.py:196-229):
+    //   (1,3) and (2,3) pre_solve = prevent_boundary_intersection (:294-311) on shapes[0] (the type-1 / type-2
+    //   shape), (1,4) begin -> False (ignored), (2,4) pre_solve -> False (never solved).
+    // robot_hit = the value the LAST (1,3) pre_solve assigned to env.robot_hit_obstacle (:201-203), -1 = no call yet.
+    int handler_mode = 0;
+    int robot_hit = -1;
     // sweep scratch
     std::vector<int> order_y;
 };
@@ -683,7 +690,7 @@ static void space_step(Space* sp, cpFloat dt) {
     // integrate positions (dynamic + kinematic)
     long long moved = 0;
     for (Body& b : sp->bodies) {
-        if (b.type == BODY_STATIC) continue;
+        if (b.type == BODY_STATIC || b.removed) continue;
         if (b.vel.x != 0 || b.vel.y != 0 || b.w != 0 || b.v_bias.x != 0 || b.v_bias.y != 0 || b.w_bias != 0) moved++;
         b.p = vadd(b.p, vmult(vadd(b.vel, b.v_bias), dt));
         b.a = b.a + (b.w + b.w_bias) * dt;
@@ -691,7 +698,7 @@ static void space_step(Space* sp, cpFloat dt) {
         b.v_bias = v(0, 0); b.w_bias = 0.0;
     }
     sp->st.moved_bodies += moved; if (moved > sp->st.max_moved) sp->st.max_moved = moved;
-    for (Shape& s : sp->shapes) if (sp->bodies[s.body].type != BODY_STATIC) shape_cache_data(sp, s);
+    for (Shape& s : sp->shapes) if (sp->bodies[s.body].type != BODY_STATIC && !sp->bodies[s.body].removed) shape_cache_data(sp, s);
 
     // broadphase: sweep along y, then canonical order
     int ns = (int)sp->shapes.size();
@@ -708,6 +715,7 @@ static void space_step(Space* sp, cpFloat dt) {
             if (b.bb_b > a.bb_t) break;
             if (!(a.bb_l <= b.bb_r && b.bb_l <= a.bb_r && a.bb_b <= b.bb_t && b.bb_b <= a.bb_t)) continue;
             if (a.body == b.body) continue;
+            if (sp->bodies[a.body].removed || sp->bodies[b.body].removed) continue;
             int p = sp->order_y[ii], q = sp->order_y[jj];
             if (sp->bodies[a.body].type == BODY_STATIC && sp->bodies[b.body].type == BODY_STATIC) continue;
             if (p > q) std::swap(p, q);
@@ -733,13 +741,42 @@ static void space_step(Space* sp, cpFloat dt) {
         arb->gjk_id = gid;
         arb->body_a = sp->shapes[ia].body; arb->body_b = sp->shapes[ib].body;
         arbiter_update(sp, arb, info);
-        {   // pre_solve of handler (1, 3) — called for every touching pair, solved or not
-            int ta = sp->shapes[ia].ctype, tb = sp->shapes[ib].ctype;
+        int ta = sp->shapes[ia].ctype, tb = sp->shapes[ib].ctype;
+        bool solve_ok = true;
+        if (sp->handler_mode == 0) {
+            // pre_solve of handler (1, 3) — called for every touching pair, solved or not
             if ((ta == 1 && tb == 3) || (ta == 3 && tb == 1)) sp->hits_13++;
+        } else {
+            int lo = ta < tb ? ta : tb, hi = ta < tb ? tb : ta;
+            // begin of handler (1,4) returns False: cpArbiterIgnore until the shapes separate
+            if (arb->state == ARB_FIRST && lo == 1 && hi == 4) arb->state = ARB_IGNORE;
+            if (arb->state != ARB_IGNORE) {
+                if ((lo == 1 || lo == 2) && hi == 3) {
+                    // prevent_boundary_intersection (box_delivery_env.py:294-311).  arbiter.shapes[0] is the shape
+                    // whose type equals the handler's first type; contact_point_set (cpArbiterGetContactPointSet):
+                    // normal = swapped ? -n : n, points[0].distance = dot((b.p + r2) - (a.p + r1), n).
+                    bool swapped = (ta != lo);
+                    Body& A = sp->bodies[arb->body_a]; Body& B = sp->bodies[arb->body_b];
+                    V nrm = swapped ? vneg(arb->n) : arb->n;
+                    V p1 = vadd(A.p, arb->con[0].r1), p2 = vadd(B.p, arb->con[0].r2);
+                    cpFloat depth = vdot(vsub(p2, p1), arb->n);
+                    Body& S0 = swapped ? B : A;
+                    V cv = S0.vel;
+                    cpFloat k = 2 * vdot(cv, nrm);                  // 2 * current_velocity.dot(normal)
+                    V refl = vsub(cv, vmult(nrm, k));               // current_velocity - k * normal
+                    V nv = vmult(refl, 0.5);                        // * elasticity
+                    bool collision = depth < 0;
+                    V corr = vmult(nrm, depth);
+                    body_set_position(S0, vadd(body_get_position(S0), corr));
+                    S0.vel = nv;
+                    if (lo == 1) { sp->robot_hit = collision ? 1 : 0; sp->hits_13++; }
+                }
+                if (lo == 2 && hi == 4) solve_ok = false;       // (2,4) pre_solve returns False
+            }
         }
         // handlers used by ship-ice only do bookkeeping (ship_ice_env.py:150-180): begin/pre_solve return True
         const Body& ba = sp->bodies[arb->body_a]; const Body& bb = sp->bodies[arb->body_b];
-        if (arb->state != ARB_IGNORE && !(ba.m == INFINITY && bb.m == INFINITY)) {
+        if (arb->state != ARB_IGNORE && solve_ok && !(ba.m == INFINITY && bb.m == INFINITY)) {
             arb->live = true;
             sp->arbiters.push_back(arb);
         } else {
@@ -767,7 +804,7 @@ static void space_step(Space* sp, cpFloat dt) {
 
     cpFloat damping = std::pow(sp->damping, dt);
     for (Body& b : sp->bodies) {
-        if (b.type != BODY_DYNAMIC) continue;       // cpBodyUpdateVelocity skips kinematic; static not in list
+        if (b.type != BODY_DYNAMIC || b.removed) continue;   // cpBodyUpdateVelocity skips kinematic; static not in list
         b.vel = vadd(vmult(b.vel, damping), vmult(vadd(sp->gravity, vmult(b.f, b.m_inv)), dt));
         b.w = b.w * damping + b.t * b.i_inv * dt;
         b.f = v(0, 0); b.t = 0.0;
@@ -946,14 +983,36 @@ int cpo_maze_substeps(void* h, int robot_body, int steps, double dt, double widt
     return flags;
 }
 long long cpo_hits_13(void* h) { return ((Space*)h)->hits_13; }
+void cpo_space_set_handler_mode(void* h, int mode) { ((Space*)h)->handler_mode = mode; }
+int cpo_robot_hit(void* h) { return ((Space*)h)->robot_hit; }
+void cpo_set_robot_hit(void* h, int v) { ((Space*)h)->robot_hit = v; }
+// pymunk `body.position = (x, y)` (cpBodySetPosition)
+void cpo_body_set_position(void* h, int b, double x, double y) { body_set_position(((Space*)h)->bodies[b], v(x, y)); }
+// pymunk `space.remove(body, shape)`: the body stops integrating, its shapes leave the broadphase and
+// every cached arbiter that references them is dropped (cpSpaceRemoveShape -> cpSpaceFilterArbiters).
+void cpo_body_remove(void* h, int b) {
+    Space* sp = (Space*)h; sp->bodies[b].removed = true;
+    std::vector<Arbiter*> keep;
+    for (Arbiter* arb : sp->arbiters) if (arb->body_a != b && arb->body_b != b) keep.push_back(arb);
+    sp->arbiters.swap(keep);
+    for (auto it = sp->cache.begin(); it != sp->cache.end();) {
+        if (sp->shapes[it->second.a].body == b || sp->shapes[it->second.b].body == b) it = sp->cache.erase(it); else ++it;
+    }
+}
+// body.local_to_world(v) = cpTransformPoint(body->transform, v)
+void cpo_body_local_to_world(void* h, int b, double x, double y, double* out2) {
+    V w = tpoint(((Space*)h)->bodies[b].tr, v(x, y)); out2[0] = w.x; out2[1] = w.y;
+}
 // pymunk Space.point_query(p, max_dist, ShapeFilter()) != []  — cpSpacePointQuery: a shape is reported
 // when its signed surface distance (rounded radius included) is strictly below max_dist
 // (NearestPointQuery: `if(info.distance < context->maxDistance)`); the candidate filter is the
 // shape's AABB against the box p +- max(max_dist, 0).
-int cpo_point_query_any(void* h, double px, double py, double max_dist) {
+static int point_query_mask(void* h, double px, double py, double max_dist, int stop_first) {
     Space* sp = (Space*)h; V p = v(px, py);
     cpFloat md = std::fmax(max_dist, 0.0);
+    int mask = 0;
     for (const Shape& s : sp->shapes) {
+        if (sp->bodies[s.body].removed) continue;
         if (!(p.x - md <= s.bb_r && s.bb_l <= p.x + md && p.y - md <= s.bb_t && s.bb_b <= p.y + md)) continue;
         cpFloat dist;
         if (s.kind == 1) {          // cpSegmentShapePointQuery
@@ -978,10 +1037,13 @@ int cpo_point_query_any(void* h, double px, double py, double max_dist) {
             (void)closestPoint;
             dist = (outside ? minDist : -minDist) - r;
         }
-        if (dist < max_dist) return 1;
+        if (dist < max_dist) { if (stop_first) return 1; mask |= 1 << s.ctype; }
     }
-    return 0;
+    return mask;
 }
+int cpo_point_query_any(void* h, double px, double py, double max_dist) { return point_query_mask(h, px, py, max_dist, 1); }
+// bit c set = some shape with collision_type c is reported by Space.point_query(p, max_dist, ShapeFilter())
+int cpo_point_query_types(void* h, double px, double py, double max_dist) { return point_query_mask(h, px, py, max_dist, 0); }
 void cpo_get_stats(void* h, long long* out11) { memcpy(out11, &((Space*)h)->st, sizeof(Stats)); }
 void cpo_reset_stats(void* h) { memset(&((Space*)h)->st, 0, sizeof(Stats)); }
 // number of live arbiters in the last step and their (a, b, count, jn0, jt0, jn1, jt1) rows

@@ -69,6 +69,13 @@ def lib():
         L.cpo_hits_13.argtypes = [C.c_void_p]
         L.cpo_hits_13.restype = C.c_longlong
         L.cpo_point_query_any.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.cpo_point_query_types.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.cpo_space_set_handler_mode.argtypes = [C.c_void_p, C.c_int]
+        L.cpo_robot_hit.argtypes = [C.c_void_p]
+        L.cpo_set_robot_hit.argtypes = [C.c_void_p, C.c_int]
+        L.cpo_body_set_position.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.cpo_body_remove.argtypes = [C.c_void_p, C.c_int]
+        L.cpo_body_local_to_world.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, dp]
         L.cpo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.cpo_reset_stats.argtypes = [C.c_void_p]
         L.cpo_get_arbiters.argtypes = [C.c_void_p, dp, C.c_int]
@@ -119,6 +126,31 @@ class Space:
     def point_query_any(self, p, max_dist):
         """bool(space.point_query(p, max_dist, ShapeFilter()))"""
         return bool(self.L.cpo_point_query_any(self.h, float(p[0]), float(p[1]), float(max_dist)))
+
+    def point_query_types(self, p, max_dist):
+        """bit c set = a shape of collision_type c is in space.point_query(p, max_dist, ShapeFilter())"""
+        return int(self.L.cpo_point_query_types(self.h, float(p[0]), float(p[1]), float(max_dist)))
+
+    def set_handler_mode(self, mode):
+        """1 = the box-delivery / area-clearing handler set (see chipmunk_oracle.cpp Space::handler_mode)"""
+        self.L.cpo_space_set_handler_mode(self.h, int(mode))
+
+    def robot_hit(self):
+        return int(self.L.cpo_robot_hit(self.h))
+
+    def set_robot_hit(self, v):
+        self.L.cpo_set_robot_hit(self.h, int(v))
+
+    def set_position(self, body, x, y):
+        self.L.cpo_body_set_position(self.h, body, float(x), float(y))
+
+    def remove_body(self, body):
+        self.L.cpo_body_remove(self.h, body)
+
+    def local_to_world(self, body, x, y):
+        out = np.empty(2, dtype=np.float64)
+        self.L.cpo_body_local_to_world(self.h, body, float(x), float(y), _dp(out))
+        return out
 
     def set_density(self, shape, rho):
         self.L.cpo_shape_set_density(self.h, shape, float(rho))
