@@ -6,14 +6,24 @@
 
 using namespace bp::bd;
 
+#ifndef BD_MOVE_MINB
+#define BD_MOVE_MINB 4          // resident 128-thread blocks per SM the warp-per-env kernels are compiled for (<= 128 registers)
+#endif
+
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void k_bd_init_statics(BdConst* C) {
     int k = threadIdx.x;
     if (k < C->P.n_static) bd_init_static(C->S, k);
 }
 
+// thread per cell: clears *flag when a free cell is not visible from the receptacle cell
+__global__ void k_bd_visibility(const BdConst* C, int* flag) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < C->P.H * C->P.W && !bd_cell_visible(*C, v)) atomicAnd(flag, 0);
+}
+
 // warp per env
-__global__ void __launch_bounds__(128) k_bd_reset(const BdConst* C, const int32_t* layout_ids, const uint8_t* mask, BdOut out) {
+__global__ void __launch_bounds__(128, BD_MOVE_MINB) k_bd_reset(const BdConst* C, const int32_t* layout_ids, const uint8_t* mask, BdOut out) {
     int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (env >= C->n_envs || (mask && !mask[env])) return;
     BdEnv* E = bd_env(*C, env);
@@ -47,7 +57,7 @@ __global__ void __launch_bounds__(256) k_bd_dist(const BdConst* C, const uint8_t
                 int env = it / per_env, k = it - env * per_env;
                 if (mask && !mask[env]) continue;
                 const BdEnv* E = bd_env(*C, env);
-                if (k < C->P.NB ? (E->body[1 + k].alive == 1) : (phase == 0 && E->need_spfa)) break;
+                if (k < C->P.NB ? (E->body[1 + k].alive == 1 && !C->P.recept_visible) : (phase == 0 && E->need_spfa)) break;
             }
             s_item = it;
         }
@@ -61,7 +71,7 @@ __global__ void __launch_bounds__(256) k_bd_dist(const BdConst* C, const uint8_t
 }
 
 // warp per env: waypoint headings, controller loop, until-still loop
-__global__ void __launch_bounds__(128) k_bd_move(const BdConst* C, const uint8_t* mask) {
+__global__ void __launch_bounds__(128, BD_MOVE_MINB) k_bd_move(const BdConst* C, const uint8_t* mask) {
     __shared__ BdLoop LS[4];
     int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (env >= C->n_envs || (mask && !mask[env])) return;
@@ -124,7 +134,7 @@ void bp_boxdel_default_config(bp_boxdel_config* c) {
     c->robot_length = 0.6; c->robot_width = 0.92;
     c->partial_rewards_scale = 0.2; c->goal_reward = 10.0; c->collision_penalty = 0.25; c->non_movement_penalty = 0.0;
     c->correct_direction_reward_scale = 3.0; c->use_correct_direction_reward = 0; c->ministep_size = 2.5;
-    c->shortest_path_channel_scale = 0.25;
+    c->shortest_path_channel_scale = 0.25; c->force_box_spfa = 0;
     const double chassis[8] = {0.26, -0.35, -0.31, -0.35, -0.31, 0.35, 0.26, 0.35};
     const double bumper[8] = {0.31, -0.53, 0.20, -0.39, 0.20, 0.39, 0.31, 0.53};
     const double wheels[32] = {0.09, 0.35, 0.09, 0.39, 0.24, 0.39, 0.24, 0.35,   0.09, -0.39, 0.09, -0.35, 0.24, -0.35, 0.24, -0.39,
@@ -221,6 +231,20 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
         if (rc != BP_OK) return rc;
         if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("receptacle spfa: ") + cudaGetErrorString(e));
     }
+    // can the receptacle cell see the whole free space?  (BdParams::recept_visible)
+    {
+        int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
+        pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
+        P.recept_ci = closest[(size_t)pi * W + pj]; P.recept_cj = closest[nv + (size_t)pi * W + pj]; P.recept_visible = 0;
+        CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdParams), cudaMemcpyHostToDevice));      // P is the first member of BdConst
+        int one = 1;
+        CUDA_TRY(cudaMemcpy(h->d_counter, &one, 4, cudaMemcpyHostToDevice));
+        k_bd_visibility<<<(int)((nv + 255) / 256), 256>>>(h->dC, h->d_counter);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy(&one, h->d_counter, 4, cudaMemcpyDeviceToHost));
+        P.recept_visible = (one != 0 && !h->cfg.force_box_spfa) ? 1 : 0;
+        CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdParams), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMemcpy(&K, h->dC, sizeof(BdConst), cudaMemcpyDeviceToHost));     // statics now in world space
     h->loaded = true;
     return BP_OK;
@@ -265,10 +289,13 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
     k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 0, h->d_scratch, h->d_counter);
     k_bd_move<<<(E * 32 + 127) / 128, 128, 0, st>>>(h->dC, mask);
-    CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
-    k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 1, h->d_scratch, h->d_counter);
+    if (!h->hC.P.recept_visible) {
+        CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
+        k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 1, h->d_scratch, h->d_counter);
+        h->launches++;
+    }
     k_bd_finish<<<(E + 127) / 128, 128, 0, st>>>(h->dC, mask, bd_out(out));
-    h->launches += 5;
+    h->launches += 4;
     CUDA_TRY(cudaGetLastError());
     return bd_launch_obs(h, mask, out ? out->obs : nullptr, st);
 }

@@ -57,6 +57,12 @@ struct BdParams {
     double partial_scale, goal_reward, collision_penalty, nonmove_penalty, correct_scale, ministep;
     int use_correct, inactivity_cutoff, num_boxes, action_type;   // action_type 0 = position (pixel index), 1 = heading
     double sp_div, sp_scale;      // (sqrt(2) * LW) / ppm ; cfg.env.shortest_path_channel_scale
+    // 1 when every free configuration-space cell is visible (skimage line, drawn from the receptacle cell) from the
+    // receptacle's cell: then shortest_path(box, receptacle) always prunes to [box, receptacle] whatever the spfa parent
+    // chain is (box_delivery_env.py:1243-1250 tests lines from coords[0] = the receptacle cell only while all are free),
+    // so shortest_path_distance is the Euclidean distance and needs no spfa solve.  Checked once per handle.
+    int recept_visible;
+    int recept_ci, recept_cj;     // closest valid cell of the receptacle position
 };
 
 struct BdBody {                   // 144 B
@@ -96,7 +102,7 @@ struct BdShapes {                 // immutable per handle: robot shapes (body-lo
 
 struct BdEnv {                    // mutable per env (header; the slot table follows it in the env block)
     int layout, episode, t, status, stamp, n_order, robot_hit, inactivity, cum_boxes, done, truncated, n_prev;
-    int n_path, move_sign, need_spfa, src_i, src_j, tgt_i, tgt_j, pad0;
+    int n_path, move_sign, need_spfa, src_i, src_j, tgt_i, tgt_j, n_live;      // n_live: slots with state != SL_NONE
     long long stat_substeps, stat_cand, stat_arb;
     double prev_dt, cum_distance, cum_reward, total_work, last_work, reward, ministeps;
     double init_pos[2], init_heading, robot_distance;
@@ -427,6 +433,19 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     }
     if (nc > MAXCAND) { nc = MAXCAND; if (lane == 0) E->status |= BD_CAND_OVERFLOW; }
     bp_wsync();
+    if (nc == 0 && E->n_live == 0) {
+        // nothing overlaps and no arbiter is cached: the rest of cpSpaceStep only applies the velocity update
+        for (int b = 1 + lane; b <= NB; b += BP_NL) {
+            BdBody& B = E->body[b];
+            if (!B.alive) continue;
+            B.vx = B.vx * P.damp + (0.0 + 0.0 * B.minv) * dt;
+            B.vy = B.vy * P.damp + (0.0 + 0.0 * B.minv) * dt;
+            B.vw = B.vw * P.damp + 0.0 * B.iinv * dt;
+        }
+        if (lane == 0) { E->n_order = 0; E->prev_dt = dt; }
+        bp_wsync();
+        return;
+    }
     // 3. narrowphase, lanes over candidates (pure geometry on the cached world vertices)
     for (int q = lane; q < nc; q += BP_NL) {
         int p = E->cand[q];
@@ -478,13 +497,23 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     }
     bp_wsync();
     // 5. cache expiry (cpSpaceArbiterSetFilter)
-    for (int p = lane; p < P.n_slots; p += BP_NL) {
-        BdSlot& S = slots[p];
-        if (S.state == SL_NONE || S.stamp == stamp) continue;
-        int ticks = stamp - S.stamp;
-        if (ticks >= 1 && S.state != SL_CACHED) S.state = SL_CACHED;
-        if (ticks >= P.persistence) S.state = SL_NONE;
+    int n_live = 0;
+    for (int base = 0; base < P.n_slots; base += BP_NL) {
+        int p = base + lane;
+        bool live = false;
+        if (p < P.n_slots) {
+            BdSlot& S = slots[p];
+            if (S.state != SL_NONE && S.stamp != stamp) {
+                int ticks = stamp - S.stamp;
+                if (ticks >= 1 && S.state != SL_CACHED) S.state = SL_CACHED;
+                if (ticks >= P.persistence) S.state = SL_NONE;
+            }
+            live = S.state != SL_NONE;
+        }
+        int tot; bp_wrank(live, &tot);
+        n_live += tot;
     }
+    if (lane == 0) E->n_live = n_live;
     // 6. solve list in canonical order, then greedy colours over the dynamic bodies (lane 0; <= a few dozen entries)
     if (lane == 0) {
         int n = 0;
@@ -545,7 +574,7 @@ BP_DEV void bd_remove_box(const BdConst& C, BdEnv* E, int i) {
     E->body[1 + i].alive = 0;
     BdSlot* slots = bd_slots(E);
     for (int p = 0; p < C.P.n_slots; p++)
-        if (C.pair_a[p] == NROBOT + i || C.pair_b[p] == NROBOT + i) slots[p].state = SL_NONE;
+        if ((C.pair_a[p] == NROBOT + i || C.pair_b[p] == NROBOT + i) && slots[p].state != SL_NONE) { slots[p].state = SL_NONE; E->n_live--; }
 }
 
 // Space.point_query(p, 0, ShapeFilter()) restricted to the static shapes: bit (1 << ctype) per shape that strictly

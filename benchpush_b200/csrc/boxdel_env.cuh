@@ -82,6 +82,17 @@ BP_DEV bool line_free(const uint8_t* map, int W, int r0, int c0, int r1, int c1)
     return blocked == 0;
 }
 
+// shortest_path_distance(box, receptacle) for every live box when the receptacle cell sees the whole free space
+// (BdParams::recept_visible): path = [box position, receptacle position] => one Euclidean distance.
+BP_DEV void bd_box_dists_visible(const BdConst& C, BdEnv* E, double* out) {
+    for (int i = 0; i < C.P.NB; i++) {
+        const BdBody& B = E->body[1 + i];
+        if (B.alive != 1) continue;
+        V2 o = bd_origin(B);
+        out[i] = 0.0 + dist2(o.x, o.y, C.P.recept_x, C.P.recept_y);
+    }
+}
+
 // ------------------------------------------------------------------ reset
 BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) {
     const int lane = bp_lane();
@@ -91,7 +102,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
     for (int p = lane; p < P.n_slots; p += BP_NL) { slots[p].state = SL_NONE; slots[p].cnt = 0; slots[p].stamp = 0; slots[p].gjk = 0; }
     if (lane == 0) {
         E->layout = layout; E->episode = episode; E->t = 0; E->status = 0; E->stamp = 0; E->n_order = 0; E->robot_hit = 0;
-        E->inactivity = 0; E->cum_boxes = 0; E->done = 0; E->truncated = 0; E->n_path = 0; E->need_spfa = 0;
+        E->inactivity = 0; E->cum_boxes = 0; E->done = 0; E->truncated = 0; E->n_path = 0; E->need_spfa = 0; E->n_live = 0;
         E->prev_dt = 0.0; E->cum_distance = 0.0; E->cum_reward = 0.0; E->total_work = 0.0; E->last_work = 0.0; E->reward = 0.0; E->ministeps = 0.0;
         E->stat_substeps = 0; E->stat_cand = 0; E->stat_arb = 0;
         BdBody& R = E->body[0];
@@ -169,6 +180,7 @@ BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action) {
         closest_valid(C, si, sj, &E->src_i, &E->src_j);
         closest_valid(C, ti, tj, &E->tgt_i, &E->tgt_j);
     }
+    if (P.recept_visible) bd_box_dists_visible(C, E, E->init_dist);
 }
 
 // ------------------------------------------------------------------ path from a distance field (second half of shortest_path)
@@ -387,6 +399,7 @@ BP_DEV void bd_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out
     const BdLayout& L = C.layouts[E->layout];
     double reward = 0.0;
     int robot_boxes = 0;
+    if (P.recept_visible) bd_box_dists_visible(C, E, E->final_dist);
     for (int i = 0; i < P.NB; i++) {
         BdBody& B = E->body[1 + i];
         if (!B.alive) continue;

@@ -36,7 +36,7 @@ BP_DEV void bd_dist_item(SpfaShared& S, const BdConst& C, BdEnv* E, int k, int p
     int si, sj, ti, tj;
     if (k < P.NB) {
         const BdBody& B = E->body[1 + k];
-        if (!B.alive) return;
+        if (!B.alive || P.recept_visible) return;
         V2 o = bd_origin(B);
         sx = o.x; sy = o.y; gx = P.recept_x; gy = P.recept_y;
         int pi, pj;
@@ -63,6 +63,13 @@ BP_DEV void bd_dist_item(SpfaShared& S, const BdConst& C, BdEnv* E, int k, int p
         }
     }
     BP_BSYNC();
+}
+
+// 1 when free cell v is visible from the receptacle cell (or v is not free)
+BP_DEV int bd_cell_visible(const BdConst& C, int v) {
+    const BdParams& P = C.P;
+    if (!C.cspace[v]) return 1;
+    return line_free(C.cspace, P.W, P.recept_ci, P.recept_cj, v / P.W, v % P.W) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ cv2.fillPoly (one convex polygon, <= 4 int vertices)

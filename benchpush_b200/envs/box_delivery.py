@@ -62,6 +62,7 @@ class BoxDelConfig(C.Structure):
         ("n_envs", C.c_int32), ("num_boxes", C.c_int32), ("device", C.c_int32), ("action_type", C.c_int32),
         ("steps", C.c_int32), ("iterations", C.c_int32), ("settle_steps", C.c_int32), ("inactivity_cutoff", C.c_int32),
         ("local_map_pixel_width", C.c_int32), ("use_correct_direction_reward", C.c_int32),
+        ("force_box_spfa", C.c_int32), ("reserved0", C.c_int32),
         ("ctrl_dt", C.c_double), ("target_speed", C.c_double), ("damping", C.c_double),
         ("box_size", C.c_double), ("box_density", C.c_double),
         ("room_length", C.c_double), ("room_width", C.c_double), ("receptacle_width", C.c_double),
@@ -187,7 +188,7 @@ class BoxDeliveryVecEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
-                 seed: Optional[int] = None, _backend=None):
+                 seed: Optional[int] = None, force_box_spfa: bool = False, _backend=None):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"]["obstacle_config"] not in ("small_empty", "large_empty"):
@@ -226,6 +227,7 @@ class BoxDeliveryVecEnv:
         k = BoxDelConfig()
         L.bp_boxdel_default_config(C.byref(k))
         rw = c["rewards_sam"] if c["train"]["job_type"] == "sam" else c["rewards"]
+        k.force_box_spfa = 1 if force_box_spfa else 0      # testing aid: solve spfa per box even when the exact shortcut applies
         k.n_envs = E; k.num_boxes = NB; k.device = self.device_index
         k.action_type = 1 if c["agent"]["action_type"] == "heading" else 0
         k.steps = int(c["sim"]["steps"]); k.iterations = int(c["sim"]["iterations"]); k.settle_steps = 1000

@@ -51,7 +51,7 @@ void bp_boxdel_default_config(bp_boxdel_config* c) {
     c->robot_length = 0.6; c->robot_width = 0.92;
     c->partial_rewards_scale = 0.2; c->goal_reward = 10.0; c->collision_penalty = 0.25; c->non_movement_penalty = 0.0;
     c->correct_direction_reward_scale = 3.0; c->use_correct_direction_reward = 0; c->ministep_size = 2.5;
-    c->shortest_path_channel_scale = 0.25;
+    c->shortest_path_channel_scale = 0.25; c->force_box_spfa = 0;
     const double chassis[8] = {0.26, -0.35, -0.31, -0.35, -0.31, 0.35, 0.26, 0.35};
     const double bumper[8] = {0.31, -0.53, 0.20, -0.39, 0.20, 0.39, 0.31, 0.53};
     const double wheels[32] = {0.09, 0.35, 0.09, 0.39, 0.24, 0.39, 0.24, 0.35,   0.09, -0.39, 0.09, -0.35, 0.24, -0.35, 0.24, -0.39,
@@ -93,6 +93,14 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
         std::vector<int32_t> par(nv);
         SpfaShared S;
         spfa_block(S, h->cspace.data(), H, W, si, sj, h->recept.data(), par.data(), h->scratch.data(), h->scratch.data() + nv, h->scratch.data() + 2 * nv);
+    }
+    {
+        int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
+        pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
+        K.P.recept_ci = closest[(size_t)pi * W + pj]; K.P.recept_cj = closest[nv + (size_t)pi * W + pj];
+        int vis = 1;
+        for (size_t v = 0; v < nv && vis; v++) if (!bd_cell_visible(K, (int)v)) vis = 0;
+        K.P.recept_visible = (vis && !h->cfg.force_box_spfa) ? 1 : 0;
     }
     h->loaded = true;
     return 0;
@@ -161,7 +169,7 @@ int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double*
     if (path) memcpy(path, E->path, sizeof(E->path));
     return 0;
 }
-int64_t bp_boxdel_launch_count(bp_boxdel_t* h) { return 0; }
+int64_t bp_boxdel_launch_count(bp_boxdel_t* h) { return h->HB.K.P.recept_visible; }   // emulation only: reports the visibility flag
 size_t bp_boxdel_env_bytes(bp_boxdel_t* h) { return h->HB.K.env_bytes; }
 
 }  // extern "C"

@@ -1,0 +1,119 @@
+"""box-delivery-v0 on the B200 through the C ABI (libbenchpush_b200.so) against the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.boxdel_common import DELIVERY_CFG, DELIVERY_LAYOUT, compare_step
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(cfg, layouts, n):
+    from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
+    return BoxDeliveryVecEnv(num_envs=n, cfg=cfg, layouts=layouts, device=0)
+
+
+def test_reset_and_heading_episode_match_the_oracle(portable_trig):
+    from oracle.box_delivery_oracle import BoxDeliveryOracleEnv, sample_layout
+    cfg = {"agent": {"action_type": "heading"}}
+    lays = [sample_layout(np.random.RandomState(40 + s)) for s in range(48)]
+    env = _mk(cfg, lays, 48)
+    picks = [2, 37]                                  # layout 2 == RandomState(42): starts next to the wall (spfa paths)
+    oras = {e: BoxDeliveryOracleEnv(cfg=cfg, layouts=[lays[e]]) for e in picks}
+    obs, info = env.reset()
+    for e, ora in oras.items():
+        oobs, oinfo = ora.reset()
+        assert np.array_equal(obs[e].cpu().numpy(), oobs), "reset observation differs from the oracle"
+        assert np.array_equal(env.get_bodies(e)[:, :6], ora.space.state()[:11])
+    rng = np.random.default_rng(0)
+    spfa = 0
+    for k in range(10):
+        a = rng.uniform(-1, 1, size=48).astype(np.float32)
+        out = env.step(a)
+        for e, ora in oras.items():
+            # tolerance: the controller's atan2 / sin / cos are CUDA's vs numpy's (<= 1 ulp apart); contacts amplify that slowly
+            d = compare_step(env, ora, e, None, float(a[e]), step_out=out, state_tol=1e-7)
+            spfa += d["spfa"]
+    assert spfa >= 1
+    assert int(env._buf["info_i"][:, 3].max()) == 0, "an env reported a capacity / step-limit status"
+    env.close()
+
+
+def test_delivery_and_position_actions_match_the_oracle(portable_trig):
+    from oracle.box_delivery_oracle import BoxDeliveryOracleEnv
+    env = _mk(DELIVERY_CFG, [DELIVERY_LAYOUT], 1)
+    ora = BoxDeliveryOracleEnv(cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT])
+    env.reset(); ora.reset()
+    for k in range(3):
+        compare_step(env, ora, 0, -1.0, -1.0, state_tol=1e-8)
+    assert int(env._buf["info_i"][0, 0]) == 1 and int(env._buf["info_i"][0, 2]) == 3
+    env.close()
+    cfg = dict(DELIVERY_CFG, agent={"action_type": "position"})
+    env = _mk(cfg, [DELIVERY_LAYOUT], 1)
+    ora = BoxDeliveryOracleEnv(cfg=cfg, layouts=[DELIVERY_LAYOUT])
+    env.reset(); ora.reset()
+    for pix in (40 * 224 + 112, 112 * 224 + 30, 200 * 224 + 200):
+        compare_step(env, ora, 0, float(pix), pix, state_tol=1e-8)
+    env.close()
+
+
+def test_batch_independence_masks_and_host_entry_point():
+    import torch
+    from oracle.box_delivery_oracle import sample_layout
+    cfg = {"agent": {"action_type": "heading"}}
+    lays = [sample_layout(np.random.RandomState(s)) for s in range(300, 332)]
+    big = _mk(cfg, lays, 32)
+    one = _mk(cfg, lays[17:18], 1)
+    big.reset(); one.reset()
+    rng = np.random.default_rng(3)
+    for k in range(3):
+        a = rng.uniform(-1, 1, size=32).astype(np.float32)
+        big.step(a)
+        one.step(a[17:18])
+    assert np.array_equal(big.get_bodies(17), one.get_bodies(0)), "an env's trajectory depends on its batch"
+    assert torch.equal(big.obs[17], one.obs[0])
+    before = big.get_bodies(5).copy()
+    m = np.ones(32, dtype=np.uint8); m[5] = 0
+    big.step(rng.uniform(-1, 1, size=32).astype(np.float32), mask=m)
+    assert np.array_equal(big.get_bodies(5), before)
+    # host-buffer entry point == device entry point
+    from benchpush_b200.envs.box_delivery import BoxDelOutputs
+    two = _mk(cfg, lays[17:18], 1)
+    two.reset()
+    a = np.array([0.25], dtype=np.float32)
+    ho = BoxDelOutputs()
+    hobs = np.zeros((1, 224, 224, 4), dtype=np.uint8); hrew = np.zeros(1); hinfo = np.zeros((1, 8))
+    ho.obs = hobs.ctypes.data; ho.reward = hrew.ctypes.data; ho.info = hinfo.ctypes.data
+    rc = two._L.bp_boxdel_step_host(two._h, a.ctypes.data, C.byref(ho))
+    assert rc == 0
+    three = _mk(cfg, lays[17:18], 1)
+    three.reset()
+    obs, rew, term, trunc, info = three.step(a)
+    assert np.array_equal(obs.cpu().numpy(), hobs) and float(rew[0]) == hrew[0]
+    assert np.array_equal(info["total_work"].cpu().numpy(), hinfo[:, 5])
+    for e in (big, one, two, three):
+        e.close()
+
+
+def test_full_size_batch_runs_clean():
+    """BASELINE.json config 2: 4096 envs, 10 boxes, heading actions — properties that do not need the oracle."""
+    import torch
+    n = 4096
+    env = _mk({"agent": {"action_type": "heading"}}, None, n)
+    obs, info = env.reset()
+    assert obs.shape == (n, 224, 224, 4)
+    rng = np.random.default_rng(0)
+    work0 = None
+    for k in range(2):
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(rng.uniform(-1, 1, size=n).astype(np.float32)))
+    torch.cuda.synchronize()
+    assert int(info["status"].max()) == 0
+    assert bool(torch.isfinite(rew).all()) and bool((info["total_work"] >= 0).all())
+    assert int(info["n_boxes_left"].max()) <= 10 and bool((info["cumulative_boxes"] + info["n_boxes_left"] == 10).all())
+    o = obs.cpu().numpy()
+    assert set(np.unique(o[..., 1])) <= {0, 255}
+    assert set(np.unique(o[..., 0])) <= {0, 31, 95, 127, 191}
+    # the robot footprint is always at the window centre
+    assert (o[:, 112, 112, 0] == 191).all()
+    env.close()

@@ -1,0 +1,56 @@
+"""TaskDrivenMetric (task_driven_metric.py:8-157) batched: the MST cost is pinned against networkx (the library the
+reference calls), the scores against a direct restatement of the reference formulas on the emulated env's info."""
+import numpy as np
+
+from benchpush_b200.metrics import TaskDrivenMetric, _mst_cost
+from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
+from tests.boxdel_common import DELIVERY_CFG, DELIVERY_LAYOUT
+from tests.emu import emu_bd
+
+
+def test_mst_cost_is_pinned_to_networkx():
+    import networkx as nx
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        n = int(rng.integers(2, 12))
+        p = rng.uniform(-5, 5, (n, 2))
+        w = np.full((n, n), np.inf)
+        G = nx.Graph()
+        G.add_nodes_from(range(n))
+        for i in range(n):
+            for j in range(i + 1, n):
+                if rng.random() < 0.7:
+                    w[i, j] = w[j, i] = np.linalg.norm(p[i] - p[j])
+                    G.add_edge(i, j, weight=w[i, j])
+        mst = nx.minimum_spanning_tree(G)
+        ref = sum(mst.edges[e]["weight"] for e in mst.edges)
+        assert abs(_mst_cost(w) - ref) < 1e-9
+
+
+def test_task_driven_metric_on_a_delivery_episode():
+    env = BoxDeliveryVecEnv(num_envs=1, cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT], _backend=emu_bd.lib())
+    m = TaskDrivenMetric("test", robot_mass=env.cfg.agent.mass)
+    obs, info = env.reset()
+    m.reset(info)
+    start = info["state"][0].copy()
+    box0 = info["obs"][0, 0].copy()
+    path = 0.0
+    prev = start
+    for k in range(3):
+        obs, rew, term, trunc, info = env.step(np.array([-1.0], dtype=np.float32))
+        path += np.linalg.norm(info["state"][0, :2] - prev[:2])
+        prev = info["state"][0].copy()
+        m.update(info, rew, eps_complete=(k == 2))
+    assert m.success_rates == [0.25]
+    # one completed box: MST = |start - c0| + |c0 - receptacle|
+    c0 = box0.mean(axis=0)
+    goal = np.array(env.goal_points[0])
+    mst = np.linalg.norm(start[:2] - c0) + np.linalg.norm(c0 - goal)
+    assert abs(m.efficiency_scores[0] - mst / path) < 1e-9
+    area = 0.44 * 0.44
+    effort = (1.0 * path + np.linalg.norm(c0 - goal) * area) / (1.0 * path + float(info["total_work"][0]))
+    assert abs(m.effort_scores[0] - effort) < 1e-6
+    assert abs(m.rewards[0] - float(info["cumulative_reward"][0])) < 1e-9
+    r = m.reduce()
+    assert r["episodes"] == 1 and r["success_rate"] == 0.25
+    env.close()
