@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total envs over all ranks (default: the metric's 65536)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--env", default="ship-ice", choices=["ship-ice", "box-delivery"],
+                    help="ship-ice (default, the BASELINE.json metric) or box-delivery (BASELINE config 2: 4096 envs, secondary line)")
     ap.add_argument("--desync", type=int, default=34,
                     help="spread the episode phases before the warm-up: env e is advanced (global id mod DESYNC) steps (1 = all envs start at reset)")
     return ap.parse_args()
@@ -336,9 +338,119 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------ box-delivery (secondary line)
+BD_METRIC = "env-steps/sec box-delivery-v0 @4096 envs"
+BD_CFG = {"agent": {"action_type": "heading"}}
+
+
+def _bd_cpu_worker(args):
+    idx, seed, budget, nsteps = args
+    from oracle.box_delivery_oracle import BoxDeliveryOracleEnv, sample_layout
+    env = BoxDeliveryOracleEnv(cfg=BD_CFG, layouts=[sample_layout(np.random.RandomState(42 + idx))])
+    env.reset()
+    rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        o, r, term, _, info = env.step(float(rng.uniform(-1, 1)))
+        n += 1
+        if term:
+            env.reset()
+        if (nsteps is not None and n >= nsteps) or (nsteps is None and time.perf_counter() - t0 > budget):
+            break
+    return n, time.perf_counter() - t0
+
+
+def _bd_cpu(budget_s, nsteps=None):
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_bd_cpu_worker, [(i, 1000 + i, budget_s, nsteps) for i in range(cores)])
+    steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return steps / wall, cores, steps, wall
+
+
+def run_boxdel(a):
+    """BASELINE config 2: box-delivery-v0, small_empty room, 10 boxes, heading actions, spfa distance-map observation.
+    One step = one step() of every env: action decode, position-control chain, ~800 physics substeps, rewards, 224x224x4 obs."""
+    n_envs = a.envs if a.envs != TOTAL_ENVS else 4096
+    if a.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        _bd_cpu(0.0, max(a.warmup, 1))
+        v, cores, n, wall = _bd_cpu(0.0, a.steps)
+        print(json.dumps({"impl": "reference", "metric": BD_METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": {"workload": "box-delivery-v0 small_empty, 10 boxes, heading actions; one env per host core",
+                                                           "note": "restated reference (oracle/box_delivery_oracle.py on the C++ Chipmunk restatement); the reference env cannot run here"},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d env steps per core on %d cores" % (a.steps, cores)},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    from benchpush_b200.envs import BoxDeliveryVecEnv
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    env = BoxDeliveryVecEnv(num_envs=n_envs, cfg=BD_CFG, device=0)
+    env.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    total = a.warmup + a.steps
+    actions = [(torch.rand(n_envs, generator=gen, device=dev) * 2 - 1).float() for _ in range(total)]
+    for k in range(a.warmup):
+        env.step(actions[k])
+    torch.cuda.synchronize()
+    env.kernel_ms(); env.set_profiling(True)
+    l0 = env.launch_count()
+    sampler = ClockSampler(0); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(a.warmup, total):
+        env.step(actions[k])
+    e1.record(); torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    km = env.kernel_ms(); env.set_profiling(False)
+    launches = env.launch_count() - l0
+    # end to end: actions from pinned host memory, rewards / flags / info read back every step
+    h_act = [torch.empty(n_envs, dtype=torch.float32).pin_memory().copy_(actions[k].cpu()) for k in range(a.warmup, total)]
+    env.step_host(h_act[0].numpy())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(a.steps):
+        hb = env.step_host(h_act[k].numpy())
+    t_e2e = time.perf_counter() - t0
+    NB = env.num_boxes
+    alg = 4 + 224 * 224 * 4 + 2 * (1 + NB) * 6 * 8 + 48           # action + observation + poses read and written + outputs (DESIGN.md §3.4)
+    move_ms = km["move_ms"] / max(km["steps"], 1)
+    peak, peak_src = peaks()
+    achieved = alg * n_envs / (move_ms * 1e-3) / 1e9 if move_ms > 0 else 0.0
+    cpu = None
+    if not a.no_cpu_baseline:
+        v, cores, n, wall = _bd_cpu(a.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "oracle (restated reference): one env per core on %d cores, %d env steps in %.1f s" % (cores, n, wall)}
+    print(json.dumps({
+        "metric": BD_METRIC, "value": n_envs * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "box-delivery-v0 (BASELINE config 2): small_empty room, 10 boxes, heading actions U(-1,1), %d envs, "
+                               "224x224x4 u8 obs with spfa distance channels" % n_envs,
+                   "l2": "inputs_exceed_l2 (per-env state %.0f KB x %d envs + %.0f MB spfa scratch)" % (env._L.bp_boxdel_env_bytes(env._h) / 1e3, n_envs, 592 * 3.8),
+                   "env_status_bits": int(env._buf["info_i"][:, 3].max()), "boxes_delivered": int(env._buf["info_i"][:, 0].sum())},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "k_bd_move", "kernel_ms": move_ms, "obs_kernel_ms": km["obs_ms"] / max(km["steps"], 1),
+                     "algorithmic_bytes_per_env_step": alg, "peak_source": peak_src,
+                     "note": "latency bound: ~800 dependent physics substeps per env step, 1-3 contacts each"},
+        "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": {"value": n_envs * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": n_envs * 4, "d2h_bytes_per_step": n_envs * (8 + 1 + 1 + 64 + 16 + NB),
+                "what": "bp_boxdel_step_host: actions from pinned host memory; reward / flags / info / completion read back every step; observations stay on the device"},
+        "gpu_launches": launches}), flush=True)
+
+
 def main():
     a = parse()
-    if a.impl == "reference":
+    if a.env == "box-delivery":
+        run_boxdel(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

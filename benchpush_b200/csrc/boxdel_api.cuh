@@ -118,6 +118,9 @@ struct bp_boxdel {
     char* d_envs = nullptr; int* d_scratch = nullptr; int* d_counter = nullptr; int n_blocks = 0;
     bool loaded = false;
     int64_t launches = 0;
+    // optional kernel timing (CUDA events on the launching stream around k_bd_move / k_bd_obs of every step)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;      // 4 per timed step: move start / stop, obs start / stop
 };
 
 
@@ -288,7 +291,10 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
     k_bd_begin<<<(E + 127) / 128, 128, 0, st>>>(h->dC, actions, mask);
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
     k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 0, h->d_scratch, h->d_counter);
+    cudaEvent_t e4[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (h->profiling) { for (auto& e : e4) { CUDA_TRY(cudaEventCreate(&e)); h->ev.push_back(e); } CUDA_TRY(cudaEventRecord(e4[0], st)); }
     k_bd_move<<<(E * 32 + 127) / 128, 128, 0, st>>>(h->dC, mask);
+    if (h->profiling) CUDA_TRY(cudaEventRecord(e4[1], st));
     if (!h->hC.P.recept_visible) {
         CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
         k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 1, h->d_scratch, h->d_counter);
@@ -297,7 +303,28 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
     k_bd_finish<<<(E + 127) / 128, 128, 0, st>>>(h->dC, mask, bd_out(out));
     h->launches += 4;
     CUDA_TRY(cudaGetLastError());
-    return bd_launch_obs(h, mask, out ? out->obs : nullptr, st);
+    if (h->profiling) CUDA_TRY(cudaEventRecord(e4[2], st));
+    int rc = bd_launch_obs(h, mask, out ? out->obs : nullptr, st);
+    if (h->profiling) CUDA_TRY(cudaEventRecord(e4[3], st));
+    return rc;
+}
+
+int bp_boxdel_set_profiling(bp_boxdel_t* h, int32_t on) { if (!h) return fail(BP_ERR_INVALID, "null handle"); h->profiling = on != 0; return BP_OK; }
+// HOST out[3]: summed k_bd_move ms, summed k_bd_obs ms, timed steps since the last call.  Synchronises; clears the events.
+int bp_boxdel_get_kernel_ms(bp_boxdel_t* h, double* out3) {
+    if (!h || !out3) return fail(BP_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    out3[0] = out3[1] = 0.0; out3[2] = (double)(h->ev.size() / 4);
+    for (size_t i = 0; i + 3 < h->ev.size(); i += 4) {
+        float a = 0, b = 0;
+        CUDA_TRY(cudaEventElapsedTime(&a, h->ev[i], h->ev[i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, h->ev[i + 2], h->ev[i + 3]));
+        out3[0] += a; out3[1] += b;
+    }
+    for (auto e : h->ev) cudaEventDestroy(e);
+    h->ev.clear();
+    return BP_OK;
 }
 
 // host-buffer variant: actions and every non-null output are HOST pointers; copies in, steps, copies out, synchronises

@@ -65,19 +65,28 @@ struct BdParams {
     int recept_ci, recept_cj;     // closest valid cell of the receptacle position
 };
 
-struct BdBody {                   // 144 B
+struct BdBody {                   // 176 B
     double px, py, pa;            // cog position (world), angle
     double vx, vy, vw, bx, by, bw;
     double minv, iinv, rc, rs, cgx, cgy;
+    double cpx, cpy, cpa;         // pose the cached world vertices / AABB of the body's shapes were computed from
     int alive, idx;
+    int moved, pad;               // pose differs from (cpx, cpy, cpa) in this substep: shapes re-cached, pairs re-evaluated
 };
 
 struct alignas(16) BdSlot {       // one shape pair of the dense table = cpArbiter while state != SL_NONE
     int stamp; unsigned gjk;
-    unsigned char state, cnt, live, pad;
-    int pad2;
+    unsigned char state, cnt;
+    // Geometry cache of the pair (independent of the arbiter life cycle): a world with damping 0 is quasi-static, most
+    // shapes do not move in most substeps, and a pair of two unmoved shapes has the same AABB test and the same
+    // closest-feature result as in the previous substep.  ov = AABBs overlapped at the last evaluation; mvalid = the
+    // manifold below is the narrowphase result for the current poses.
+    unsigned char ov, mvalid;
+    unsigned mgjk;
     double nx, ny, e, u;
     ContactRec c[2];
+    double mnx, mny, mp1[2][2], mp2[2][2];
+    unsigned mhash[2]; int mcnt, pad2;
 };
 
 struct BdLayout {                 // immutable per layout
@@ -395,17 +404,20 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         if (b > 0 && !B.alive) continue;
         B.px = B.px + (B.vx + B.bx) * dt; B.py = B.py + (B.vy + B.by) * dt;
         B.pa = B.pa + (B.vw + B.bw) * dt;
-        bp_sincos(B.pa, &B.rs, &B.rc);
         B.bx = 0.0; B.by = 0.0; B.bw = 0.0;
+        // handlers / teleports edit (px, py) after the shapes were cached, so the comparison also catches those
+        int mv = !(B.px == B.cpx && B.py == B.cpy && B.pa == B.cpa);
+        if (mv) { if (B.pa != B.cpa) bp_sincos(B.pa, &B.rs, &B.rc); B.cpx = B.px; B.cpy = B.py; B.cpa = B.pa; }
+        B.moved = mv;
     }
     bp_wsync();
     for (int s = lane; s < NROBOT + NB; s += BP_NL) {
         if (s < NROBOT) {
             const BdBody& B = E->body[0];
-            cache_shape(&C.S.rb_lv[s][0][0], C.S.rb_nv[s], C.S.rb_rad[s], B.rc, B.rs, B.px, B.py, 0.0, 0.0, &E->wv[s][0][0], &E->bb[s]);
+            if (B.moved) cache_shape(&C.S.rb_lv[s][0][0], C.S.rb_nv[s], C.S.rb_rad[s], B.rc, B.rs, B.px, B.py, 0.0, 0.0, &E->wv[s][0][0], &E->bb[s]);
         } else {
             int i = s - NROBOT; const BdBody& B = E->body[1 + i];
-            if (!B.alive) continue;
+            if (!B.alive || !B.moved) continue;
             cache_shape(&L.box_lv[i][0][0], SV, C.S.box_rad, B.rc, B.rs, B.px, B.py, B.cgx, B.cgy, &E->wv[s][0][0], &E->bb[s]);
         }
     }
@@ -422,9 +434,14 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
             if (sa >= NROBOT) alive = E->body[1 + sa - NROBOT].alive;
             if (sb >= NROBOT && sb < NROBOT + NB) alive = alive && E->body[1 + sb - NROBOT].alive;
             if (alive) {
-                BBox A = E->bb[sa];
-                BBox B = (sb < NROBOT + NB) ? E->bb[sb] : C.S.st_bb[sb - NROBOT - NB];
-                take = (A.l <= B.r && B.l <= A.r && A.b <= B.t && B.b <= A.t);
+                bool dirty = E->body[sa < NROBOT ? 0 : 1 + sa - NROBOT].moved || (sb < NROBOT + NB && E->body[1 + sb - NROBOT].moved);
+                BdSlot& S = slots[p];
+                if (dirty) {
+                    BBox A = E->bb[sa];
+                    BBox B = (sb < NROBOT + NB) ? E->bb[sb] : C.S.st_bb[sb - NROBOT - NB];
+                    take = (A.l <= B.r && B.l <= A.r && A.b <= B.t && B.b <= A.t);
+                    S.ov = take ? 1 : 0; S.mvalid = 0;
+                } else take = S.ov != 0;
             }
         }
         int tot; int rk = bp_wrank(take, &tot);
@@ -446,20 +463,33 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         bp_wsync();
         return;
     }
-    // 3. narrowphase, lanes over candidates (pure geometry on the cached world vertices)
+    // 3. narrowphase, lanes over candidates (pure geometry on the cached world vertices); a pair of two unmoved shapes
+    //    reuses the result of the substep in which it was last evaluated
     for (int q = lane; q < nc; q += BP_NL) {
         int p = E->cand[q];
-        int sa = C.pair_a[p], sb = C.pair_b[p];
-        ShapeRef A = shape_ref(C, E, sa), B = shape_ref(C, E, sb);
-        Poly PA; PA.v = A.v; PA.n = A.n; Poly PB; PB.v = B.v; PB.n = B.n;
         BdSlot& S = slots[p];
-        unsigned gid = (S.state != SL_NONE) ? S.gjk : 0u;
-        Closest pts; unsigned hint = 0; int iters = 0, capped = 0;
-        bool inside = gjk_only(PA, PB, bb_centre(A.bb), bb_centre(B.bb), gid, &pts, &hint, &iters, &capped);
-        if (inside) pts = gjk_epa(PA, PB, hint, &capped);
-        Manifold m; bd_manifold(A, B, pts, &m);
+        Manifold m;
+#ifdef BD_NO_PAIR_CACHE
+        S.mvalid = 0;       // testing aid: always run the narrowphase
+#endif
+        if (S.mvalid) {
+            m.count = S.mcnt; m.n = mk(S.mnx, S.mny);
+            for (int i = 0; i < 2; i++) { m.p1[i] = mk(S.mp1[i][0], S.mp1[i][1]); m.p2[i] = mk(S.mp2[i][0], S.mp2[i][1]); m.hash[i] = S.mhash[i]; }
+            if (S.state != SL_NONE || m.count > 0) S.gjk = S.mgjk;
+        } else {
+            int sa = C.pair_a[p], sb = C.pair_b[p];
+            ShapeRef A = shape_ref(C, E, sa), B = shape_ref(C, E, sb);
+            Poly PA; PA.v = A.v; PA.n = A.n; Poly PB; PB.v = B.v; PB.n = B.n;
+            unsigned gid = (S.state != SL_NONE) ? S.gjk : 0u;
+            Closest pts; unsigned hint = 0; int iters = 0, capped = 0;
+            bool inside = gjk_only(PA, PB, bb_centre(A.bb), bb_centre(B.bb), gid, &pts, &hint, &iters, &capped);
+            if (inside) pts = gjk_epa(PA, PB, hint, &capped);
+            bd_manifold(A, B, pts, &m);
+            if (S.state != SL_NONE || m.count > 0) S.gjk = pts.id;
+            S.mcnt = m.count; S.mnx = m.n.x; S.mny = m.n.y; S.mgjk = pts.id; S.mvalid = 1;
+            for (int i = 0; i < m.count; i++) { S.mp1[i][0] = m.p1[i].x; S.mp1[i][1] = m.p1[i].y; S.mp2[i][0] = m.p2[i].x; S.mp2[i][1] = m.p2[i].y; S.mhash[i] = m.hash[i]; }
+        }
         E->cman[q] = m; E->ccnt[q] = (unsigned char)m.count;
-        if (S.state != SL_NONE || m.count > 0) S.gjk = pts.id;
     }
     bp_wsync();
     // 4. arbiter updates + handlers, in an order equivalent to the sequential canonical sweep:

@@ -99,7 +99,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
     const BdParams& P = C.P;
     const BdLayout& L = C.layouts[layout];
     BdSlot* slots = bd_slots(E);
-    for (int p = lane; p < P.n_slots; p += BP_NL) { slots[p].state = SL_NONE; slots[p].cnt = 0; slots[p].stamp = 0; slots[p].gjk = 0; }
+    for (int p = lane; p < P.n_slots; p += BP_NL) { slots[p].state = SL_NONE; slots[p].cnt = 0; slots[p].stamp = 0; slots[p].gjk = 0; slots[p].ov = 0; slots[p].mvalid = 0; }
     if (lane == 0) {
         E->layout = layout; E->episode = episode; E->t = 0; E->status = 0; E->stamp = 0; E->n_order = 0; E->robot_hit = 0;
         E->inactivity = 0; E->cum_boxes = 0; E->done = 0; E->truncated = 0; E->n_path = 0; E->need_spfa = 0; E->n_live = 0;
@@ -107,7 +107,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
         E->stat_substeps = 0; E->stat_cand = 0; E->stat_arb = 0;
         BdBody& R = E->body[0];
         R.px = L.start[0]; R.py = L.start[1]; R.pa = L.start[2];
-        R.vx = R.vy = R.vw = R.bx = R.by = R.bw = 0.0; R.minv = R.iinv = 0.0; R.cgx = R.cgy = 0.0; R.alive = 1; R.idx = -1;
+        R.vx = R.vy = R.vw = R.bx = R.by = R.bw = 0.0; R.minv = R.iinv = 0.0; R.cgx = R.cgy = 0.0; R.alive = 1; R.idx = -1; R.cpx = R.cpy = R.cpa = NAN; R.moved = 1;
         bp_sincos(R.pa, &R.rs, &R.rc);
     }
     for (int i = lane; i < P.NB; i += BP_NL) {
@@ -118,6 +118,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
         B.cgx = L.box_cog[i][0]; B.cgy = L.box_cog[i][1];
         B.minv = L.box_minv[i]; B.iinv = L.box_iinv[i];
         B.vx = B.vy = B.vw = B.bx = B.by = B.bw = 0.0;
+        B.cpx = B.cpy = B.cpa = NAN; B.moved = 1;
         bd_set_origin(B, mk(L.box_init[i][0], L.box_init[i][1]));
         E->completed[i] = 0;
     }

@@ -93,6 +93,8 @@ def bind(L):
     L.bp_boxdel_get_step_debug.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bp_boxdel_launch_count.argtypes = [C.c_void_p]
     L.bp_boxdel_launch_count.restype = C.c_int64
+    L.bp_boxdel_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+    L.bp_boxdel_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
     L.bp_boxdel_env_bytes.argtypes = [C.c_void_p]
     L.bp_boxdel_env_bytes.restype = C.c_size_t
     return L
@@ -358,6 +360,32 @@ class BoxDeliveryVecEnv:
         return {"state": info[:, 0:3], "cumulative_distance": info[:, 3], "cumulative_boxes": ii[:, 0], "cumulative_reward": info[:, 4],
                 "total_work": info[:, 5], "obs": b["box_verts"], "n_boxes_left": ii[:, 2], "box_completed_statuses": b["completed"],
                 "goal_positions": self.goal_points, "ministeps": info[:, 6], "inactivity": ii[:, 1], "status": ii[:, 3], "work": info[:, 7]}
+
+    def step_host(self, actions: np.ndarray, out: Optional["BoxDelOutputs"] = None):
+        """bp_boxdel_step_host: actions and results in HOST buffers (copies inside the call, synchronises).
+        Returns a dict of numpy arrays (reward, terminated, truncated, info, info_i); observations stay on the device."""
+        if not hasattr(self, "_hb"):
+            E = self.num_envs
+            self._hb = {"reward": np.zeros(E), "terminated": np.zeros(E, dtype=np.uint8), "truncated": np.zeros(E, dtype=np.uint8),
+                        "info": np.zeros((E, 8)), "info_i": np.zeros((E, 4), dtype=np.int32), "completed": np.zeros((E, self.num_boxes), dtype=np.uint8)}
+            o = BoxDelOutputs()
+            for n, a in self._hb.items():
+                setattr(o, n, a.ctypes.data)
+            self._ho = o
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        self._check(self._L.bp_boxdel_step_host(self._h, a.ctypes.data, C.byref(self._ho)))
+        return self._hb
+
+    def set_profiling(self, on: bool):
+        self._check(self._L.bp_boxdel_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_ms(self):
+        o = np.zeros(3, dtype=np.float64)
+        self._check(self._L.bp_boxdel_get_kernel_ms(self._h, o.ctypes.data))
+        return {"move_ms": float(o[0]), "obs_ms": float(o[1]), "steps": int(o[2])}
+
+    def launch_count(self):
+        return int(self._L.bp_boxdel_launch_count(self._h))
 
     # ---- parity / debugging aids
     def get_bodies(self, e: int) -> np.ndarray:

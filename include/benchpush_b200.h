@@ -294,6 +294,9 @@ int bp_boxdel_step_host(bp_boxdel_t* h, const float* actions, const bp_boxdel_ou
 /* HOST out[(1 + num_boxes)][7]: origin x, y, angle, vx, vy, w, alive; row 0 = robot */
 int bp_boxdel_get_bodies(bp_boxdel_t* h, int32_t env, double* out);
 int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double* dists, double* path);
+/* kernel timing with CUDA events on the launching stream: out3 = summed k_bd_move ms, summed k_bd_obs ms, timed steps */
+int bp_boxdel_set_profiling(bp_boxdel_t* h, int32_t on);
+int bp_boxdel_get_kernel_ms(bp_boxdel_t* h, double* out3);
 int64_t bp_boxdel_launch_count(bp_boxdel_t* h);
 size_t bp_boxdel_env_bytes(bp_boxdel_t* h);
 

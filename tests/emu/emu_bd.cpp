@@ -171,5 +171,7 @@ int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double*
 }
 int64_t bp_boxdel_launch_count(bp_boxdel_t* h) { return h->HB.K.P.recept_visible; }   // emulation only: reports the visibility flag
 size_t bp_boxdel_env_bytes(bp_boxdel_t* h) { return h->HB.K.env_bytes; }
+int bp_boxdel_set_profiling(bp_boxdel_t*, int32_t) { return 0; }
+int bp_boxdel_get_kernel_ms(bp_boxdel_t*, double* o) { o[0] = o[1] = o[2] = 0.0; return 0; }
 
 }  // extern "C"
