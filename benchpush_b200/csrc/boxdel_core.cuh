@@ -161,9 +161,13 @@ static inline int bd_build_pairs(const BdParams& P, short* pa, short* pb) {
     return n;
 }
 
+// The leaves below are out of line on purpose (BP_DEVNI): a substep is one long pass over ~8 k dynamic instructions with
+// little reuse, 16 resident warps sit at 16 different places of it, and the first build (everything inlined, 125 KB of
+// SASS for the substep) was bound by instruction fetch (ncu: stall_no_instruction 6.6 of 14.7 cycles per issue, i-cache
+// hit rate 64 %).  One shared copy per leaf keeps the hot footprint inside the instruction cache.
 // ------------------------------------------------------------------ shape access
 struct ShapeRef { const double* v; const double* ln; int n; double rad, e, u; double rc, rs; int body; BBox bb; };   // body: -1 = static
-BP_DEV ShapeRef shape_ref(const BdConst& C, const BdEnv* E, int s) {
+BP_DEVNI ShapeRef shape_ref(const BdConst& C, const BdEnv* E, int s) {
     ShapeRef r; const int NB = C.P.NB;
     if (s < NROBOT) {
         r.v = &E->wv[s][0][0]; r.ln = &C.S.rb_ln[s][0][0]; r.n = C.S.rb_nv[s]; r.rad = C.S.rb_rad[s]; r.e = C.S.rb_e[s]; r.u = C.S.rb_u[s];
@@ -181,12 +185,13 @@ BP_DEV ShapeRef shape_ref(const BdConst& C, const BdEnv* E, int s) {
 }
 
 // world vertices + AABB of one shape from its body pose (cpPolyShapeCacheData)
-BP_DEV void cache_shape(const double* lv, int n, double rad, double c, double s, double px, double py, double cgx, double cgy,
+BP_DEVNI void cache_shape(const double* lv, int n, double rad, double c, double s, double px, double py, double cgx, double cgy,
                         double* wv, BBox* bb) {
     double tx = px - (cgx * c - cgy * s);
     double ty = py - (cgx * s + cgy * c);
     double ms = -s;
     double l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
+    #pragma unroll 1
     for (int i = 0; i < n; i++) {
         double qx = lv[2 * i], qy = lv[2 * i + 1];
         double wx = c * qx + ms * qy + tx;
@@ -222,7 +227,7 @@ BP_DEV void bd_init_static(BdShapes& S, int k) {
 }
 
 // ------------------------------------------------------------------ narrowphase of one shape pair
-BP_DEV void bd_manifold(const ShapeRef& A, const ShapeRef& B, const Closest& pts, Manifold* m) {
+BP_DEVNI void bd_manifold(const ShapeRef& A, const ShapeRef& B, const Closest& pts, Manifold* m) {
     m->count = 0;
     Poly PA; PA.v = A.v; PA.n = A.n; Poly PB; PB.v = B.v; PB.n = B.n;
     double ra = A.rad, rb = B.rad;
@@ -252,7 +257,7 @@ BP_DEV void bd_manifold(const ShapeRef& A, const ShapeRef& B, const Closest& pts
 
 // body record of shape-ref body index (-1 = static: zero velocity, infinite mass, position st_p)
 struct BodyV { double px, py, vx, vy, vw, minv, iinv; };
-BP_DEV BodyV body_view(const BdConst& C, const BdEnv* E, int s, int body) {
+BP_DEVNI BodyV body_view(const BdConst& C, const BdEnv* E, int s, int body) {
     BodyV b;
     if (body >= 0) { const BdBody& q = E->body[body]; b.px = q.px; b.py = q.py; b.vx = q.vx; b.vy = q.vy; b.vw = q.vw; b.minv = q.minv; b.iinv = q.iinv; }
     else { int k = s - NROBOT - C.P.NB; b.px = C.S.st_p[k][0]; b.py = C.S.st_p[k][1]; b.vx = b.vy = b.vw = 0.0; b.minv = b.iinv = 0.0; }
@@ -260,7 +265,7 @@ BP_DEV BodyV body_view(const BdConst& C, const BdEnv* E, int s, int body) {
 }
 
 // cpArbiterUpdate for candidate q (manifold already computed); returns nothing, marks the slot touched this step
-BP_DEV void bd_arb_update(const BdConst& C, BdEnv* E, int q) {
+BP_DEVNI void bd_arb_update(const BdConst& C, BdEnv* E, int q) {
     int p = E->cand[q];
     const Manifold& m = E->cman[q];
     BdSlot& S = bd_slots(E)[p];
@@ -270,9 +275,12 @@ BP_DEV void bd_arb_update(const BdConst& C, BdEnv* E, int q) {
     bool fresh = (S.state == SL_NONE);
     int oc = fresh ? 0 : S.cnt;
     double jn_new[2] = {0, 0}, jt_new[2] = {0, 0};
+    #pragma unroll 1
     for (int i = 0; i < m.count; i++)
+        #pragma unroll 1
         for (int j = 0; j < oc; j++)
             if (m.hash[i] == S.c[j].hash) { jn_new[i] = S.c[j].jn; jt_new[i] = S.c[j].jt; }
+    #pragma unroll 1
     for (int i = 0; i < m.count; i++) {
         ContactRec& c = S.c[i];
         c.r1x = m.p1[i].x - ba.px; c.r1y = m.p1[i].y - ba.py;
@@ -288,7 +296,7 @@ BP_DEV void bd_arb_update(const BdConst& C, BdEnv* E, int q) {
 
 // prevent_boundary_intersection (box_delivery_env.py:294-311) for candidate q = (moving shape a, type-3 static b).
 // shapes[0] is always `a` here (robot chassis or box precede the statics in shape order: not swapped).
-BP_DEV bool bd_boundary_presolve(const BdConst& C, BdEnv* E, int q) {
+BP_DEVNI bool bd_boundary_presolve(const BdConst& C, BdEnv* E, int q) {
     int p = E->cand[q];
     BdSlot& S = bd_slots(E)[p];
     int sa = C.pair_a[p], sb = C.pair_b[p];
@@ -309,7 +317,7 @@ BP_DEV bool bd_boundary_presolve(const BdConst& C, BdEnv* E, int q) {
     return depth < 0;
 }
 
-BP_DEV void bd_prestep(const BdConst& C, BdEnv* E, int p) {
+BP_DEVNI void bd_prestep(const BdConst& C, BdEnv* E, int p) {
     BdSlot& S = bd_slots(E)[p];
     int sa = C.pair_a[p], sb = C.pair_b[p];
     int NB = C.P.NB;
@@ -318,6 +326,7 @@ BP_DEV void bd_prestep(const BdConst& C, BdEnv* E, int p) {
     V2 n = mk(S.nx, S.ny), tn = perp(n);
     V2 delta = mk(B.px - A.px, B.py - A.py);
     V2 va = mk(A.vx, A.vy), vb = mk(B.vx, B.vy);
+    #pragma unroll 1
     for (int i = 0; i < S.cnt; i++) {
         ContactRec& c = S.c[i];
         V2 r1 = mk(c.r1x, c.r1y), r2 = mk(c.r2x, c.r2y);
@@ -336,7 +345,7 @@ BP_DEV void bd_prestep(const BdConst& C, BdEnv* E, int p) {
 
 // One solver visit of slot p: warm == true applies the cached impulses (cpArbiterApplyCachedImpulse), otherwise
 // one cpArbiterApplyImpulse.  Bodies of infinite mass are read-only.
-BP_DEV void bd_solve(const BdConst& C, BdEnv* E, int p, bool warm, double dt_coef) {
+BP_DEVNI void bd_solve(const BdConst& C, BdEnv* E, int p, bool warm, double dt_coef) {
     BdSlot& S = bd_slots(E)[p];
     if (warm && S.state == SL_FIRST) return;
     int sa = C.pair_a[p], sb = C.pair_b[p];
@@ -352,6 +361,7 @@ BP_DEV void bd_solve(const BdConst& C, BdEnv* E, int p, bool warm, double dt_coe
     double wa = PA->vw, wb = PB->vw;
     V2 ba = mk(PA->bx, PA->by), bb = mk(PB->bx, PB->by);
     double bwa = PA->bw, bwb = PB->bw;
+    #pragma unroll 1
     for (int i = 0; i < S.cnt; i++) {
         ContactRec& c = S.c[i];
         V2 r1 = mk(c.r1x, c.r1y), r2 = mk(c.r2x, c.r2y);
@@ -395,10 +405,12 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     BdSlot* slots = bd_slots(E);
     const double dt = P.dt;
     // arbiters solved in the previous step leave FIRST_COLLISION
+    #pragma unroll 1
     for (int k = lane; k < E->n_order; k += BP_NL) { BdSlot& S = slots[E->order[k]]; if (S.state != SL_NONE) S.state = SL_NORMAL; }
     bp_wsync();
     if (lane == 0) { E->stamp++; E->stat_substeps++; }
     // 1. integrate positions (kinematic robot + live boxes), refresh the shapes
+    #pragma unroll 1
     for (int b = lane; b <= NB; b += BP_NL) {
         BdBody& B = E->body[b];
         if (b > 0 && !B.alive) continue;
@@ -411,6 +423,7 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         B.moved = mv;
     }
     bp_wsync();
+    #pragma unroll 1
     for (int s = lane; s < NROBOT + NB; s += BP_NL) {
         if (s < NROBOT) {
             const BdBody& B = E->body[0];
@@ -425,6 +438,7 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     const int stamp = E->stamp;
     // 2. broadphase over the dense pair table (ballot compaction keeps the canonical order)
     int nc = 0;
+    #pragma unroll 1
     for (int base = 0; base < P.n_slots; base += BP_NL) {
         int p = base + lane;
         bool take = false;
@@ -452,6 +466,7 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     bp_wsync();
     if (nc == 0 && E->n_live == 0) {
         // nothing overlaps and no arbiter is cached: the rest of cpSpaceStep only applies the velocity update
+        #pragma unroll 1
         for (int b = 1 + lane; b <= NB; b += BP_NL) {
             BdBody& B = E->body[b];
             if (!B.alive) continue;
@@ -465,6 +480,7 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     }
     // 3. narrowphase, lanes over candidates (pure geometry on the cached world vertices); a pair of two unmoved shapes
     //    reuses the result of the substep in which it was last evaluated
+    #pragma unroll 1
     for (int q = lane; q < nc; q += BP_NL) {
         int p = E->cand[q];
         BdSlot& S = slots[p];
@@ -474,6 +490,7 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
 #endif
         if (S.mvalid) {
             m.count = S.mcnt; m.n = mk(S.mnx, S.mny);
+            #pragma unroll 1
             for (int i = 0; i < 2; i++) { m.p1[i] = mk(S.mp1[i][0], S.mp1[i][1]); m.p2[i] = mk(S.mp2[i][0], S.mp2[i][1]); m.hash[i] = S.mhash[i]; }
             if (S.state != SL_NONE || m.count > 0) S.gjk = S.mgjk;
         } else {
@@ -487,6 +504,7 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
             bd_manifold(A, B, pts, &m);
             if (S.state != SL_NONE || m.count > 0) S.gjk = pts.id;
             S.mcnt = m.count; S.mnx = m.n.x; S.mny = m.n.y; S.mgjk = pts.id; S.mvalid = 1;
+            #pragma unroll 1
             for (int i = 0; i < m.count; i++) { S.mp1[i][0] = m.p1[i].x; S.mp1[i][1] = m.p1[i].y; S.mp2[i][0] = m.p2[i].x; S.mp2[i][1] = m.p2[i].y; S.mhash[i] = m.hash[i]; }
         }
         E->cman[q] = m; E->ccnt[q] = (unsigned char)m.count;
@@ -496,9 +514,11 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     //    (chassis, box) -> (chassis, wall)* sequential, edits the robot -> everything else except (box, wall)
     //    -> (box i, wall)* sequential per box, boxes in parallel.
     const int seg0 = NB, seg1 = NB + P.n_s3;
+    #pragma unroll 1
     for (int q = lane; q < nc; q += BP_NL) if (E->ccnt[q] && E->cand[q] < seg0) bd_arb_update(C, E, q);
     bp_wsync();
     if (lane == 0) {
+        #pragma unroll 1
         for (int q = 0; q < nc; q++) {
             int p = E->cand[q];
             if (p < seg0 || p >= seg1 || !E->ccnt[q]) continue;
@@ -509,6 +529,7 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         }
     }
     bp_wsync();
+    #pragma unroll 1
     for (int q = lane; q < nc; q += BP_NL) {
         int p = E->cand[q];
         if (p < seg1 || !E->ccnt[q]) continue;
@@ -516,8 +537,10 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         bd_arb_update(C, E, q);
     }
     bp_wsync();
+    #pragma unroll 1
     for (int i = lane; i < NB; i += BP_NL) {
         if (!E->body[1 + i].alive) continue;
+        #pragma unroll 1
         for (int q = 0; q < nc; q++) {
             int p = E->cand[q];
             if (!E->ccnt[q] || C.pair_a[p] != NROBOT + i || C.pair_b[p] < NROBOT + NB) continue;
@@ -528,6 +551,7 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     bp_wsync();
     // 5. cache expiry (cpSpaceArbiterSetFilter)
     int n_live = 0;
+    #pragma unroll 1
     for (int base = 0; base < P.n_slots; base += BP_NL) {
         int p = base + lane;
         bool live = false;
@@ -549,8 +573,10 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         int n = 0;
         short list[MAXCAND]; unsigned char col[MAXCAND];
         unsigned used[1 + MAXBOX];
+        #pragma unroll 1
         for (int b = 0; b <= NB; b++) used[b] = 0u;
         int maxc = 0;
+        #pragma unroll 1
         for (int q = 0; q < nc; q++) {
             int p = E->cand[q];
             if (!E->ccnt[q] || (p >= seg0 && p < seg1)) continue;
@@ -566,7 +592,9 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
             if (c > maxc) maxc = c;
         }
         int k = 0;
+        #pragma unroll 1
         for (int c = 0; c <= maxc && n > 0; c++)
+            #pragma unroll 1
             for (int i = 0; i < n; i++) if (col[i] == c) { E->order[k] = list[i]; E->cman[k].count = c; k++; }   // cman[k].count reused: colour of order[k]
         E->n_order = n;
         E->stat_cand += nc; E->stat_arb += n;
@@ -574,8 +602,10 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     bp_wsync();
     const int n_order = E->n_order;
     // 7. pre-step, velocity update (dynamic bodies only), warm start, iterations
+    #pragma unroll 1
     for (int k = lane; k < n_order; k += BP_NL) bd_prestep(C, E, E->order[k]);
     bp_wsync();
+    #pragma unroll 1
     for (int b = 1 + lane; b <= NB; b += BP_NL) {
         BdBody& B = E->body[b];
         if (!B.alive) continue;
@@ -585,11 +615,15 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     }
     bp_wsync();
     const double dt_coef = (E->prev_dt == 0.0) ? 0.0 : dt / E->prev_dt;
+    #pragma unroll 1
     for (int it = -1; it < P.iterations; it++) {
         int k0 = 0;
+        #pragma unroll 1
         while (k0 < n_order) {
             int c = E->cman[k0].count, k1 = k0;
+            #pragma unroll 1
             while (k1 < n_order && E->cman[k1].count == c) k1++;
+            #pragma unroll 1
             for (int k = k0 + lane; k < k1; k += BP_NL) bd_solve(C, E, E->order[k], it < 0, dt_coef);
             bp_wsync();
             k0 = k1;
@@ -611,12 +645,14 @@ BP_DEV void bd_remove_box(const BdConst& C, BdEnv* E, int i) {
 // contains p (cpPolyShapePointQuery: distance = (outside ? d : -d) - r, reported when < 0)
 BP_DEV int bd_point_query_static(const BdConst& C, V2 p) {
     int mask = 0;
+    #pragma unroll 1
     for (int k = 0; k < C.P.n_static; k++) {
         const BBox& bb = C.S.st_bb[k];
         if (!(p.x <= bb.r && bb.l <= p.x && p.y <= bb.t && bb.b <= p.y)) continue;
         int n = C.S.st_nv[k];
         V2 v0 = mk(C.S.st_v[k][n - 1][0], C.S.st_v[k][n - 1][1]);
         double minDist = INFINITY; bool outside = false;
+        #pragma unroll 1
         for (int i = 0; i < n; i++) {
             V2 v1 = mk(C.S.st_v[k][i][0], C.S.st_v[k][i][1]);
             V2 nn = mk(C.S.st_n[k][i][0], C.S.st_n[k][i][1]);

@@ -99,6 +99,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
     const BdParams& P = C.P;
     const BdLayout& L = C.layouts[layout];
     BdSlot* slots = bd_slots(E);
+    #pragma unroll 1
     for (int p = lane; p < P.n_slots; p += BP_NL) { slots[p].state = SL_NONE; slots[p].cnt = 0; slots[p].stamp = 0; slots[p].gjk = 0; slots[p].ov = 0; slots[p].mvalid = 0; }
     if (lane == 0) {
         E->layout = layout; E->episode = episode; E->t = 0; E->status = 0; E->stamp = 0; E->n_order = 0; E->robot_hit = 0;
@@ -110,6 +111,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
         R.vx = R.vy = R.vw = R.bx = R.by = R.bw = 0.0; R.minv = R.iinv = 0.0; R.cgx = R.cgy = 0.0; R.alive = 1; R.idx = -1; R.cpx = R.cpy = R.cpa = NAN; R.moved = 1;
         bp_sincos(R.pa, &R.rs, &R.rc);
     }
+    #pragma unroll 1
     for (int i = lane; i < P.NB; i += BP_NL) {
         BdBody& B = E->body[1 + i];
         B.alive = i < L.n_boxes; B.idx = i;
@@ -123,10 +125,13 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
         E->completed[i] = 0;
     }
     bp_wsync();
+    #pragma unroll 1
     for (int k = 0; k < P.settle_steps; k++) bd_substep(C, E);
     // prev_boxes = CostMap.get_obs_from_poly(self.boxes)
+    #pragma unroll 1
     for (int i = lane; i < P.NB; i += BP_NL) {
         const BdBody& B = E->body[1 + i];
+        #pragma unroll 1
         for (int v = 0; v < SV; v++) {
             V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
             E->prev_boxes[i][v][0] = w.x; E->prev_boxes[i][v][1] = w.y;
@@ -275,6 +280,36 @@ BP_DEV void bd_finalize_path(const BdConst& C, BdEnv* E) {
 // ------------------------------------------------------------------ step, part 2: execute_robot_path + step_simulation_until_still
 struct BdLoop { int flag; int dp_none; double sp_x, sp_y, al, pl; double cx[2], cy[2]; };
 
+// controller() + apply_controller() of one loop iteration (box_delivery_env.py:867-889; dp.py:100-128, 217-248):
+// DP over the course (wp[wi-1], wp[wi]); scalar, run by one lane; out of line (libm atan2 / sin / cos are large).
+BP_DEVNI void bd_controller(const BdConst& C, BdEnv* E, BdLoop& LS, int wi, double pos_x, double pos_y, double heading, bool done_turning) {
+    const BdParams& P = C.P;
+    double (*wp)[3] = E->path;
+    if (LS.dp_none) {
+        LS.cx[0] = wp[wi - 1][0]; LS.cy[0] = wp[wi - 1][1]; LS.cx[1] = wp[wi][0]; LS.cy[1] = wp[wi][1];
+        double d0 = hypot(pos_x - LS.cx[0], pos_y - LS.cy[0]), d1 = hypot(pos_x - LS.cx[1], pos_y - LS.cy[1]);
+        int ind = (d1 < d0) ? 1 : 0;
+        double ddx = LS.cx[1] - LS.cx[0], ddy = LS.cy[1] - LS.cy[0];
+        LS.pl = sqrt(ddx * ddx + ddy * ddy);
+        LS.al = LS.pl;
+        LS.sp_x = LS.cx[ind]; LS.sp_y = LS.cy[ind];
+        LS.dp_none = 0;
+    }
+    double theta_d = atan2(LS.sp_y - pos_y, LS.sp_x - pos_x);
+    double theta_e = theta_d - heading;
+    theta_e = atan2(sin(theta_e), cos(theta_e));
+    double omega = 1.0 * theta_e / P.ctrl_dt;
+    double ch = cos(heading), sh = sin(heading);
+    double vx = ch * P.target_speed + (-sh) * 0.0, vy = sh * P.target_speed + ch * 0.0;
+    LS.al = LS.al + P.target_speed * P.ctrl_dt;
+    int ind = (LS.pl < LS.al) ? 1 : 0;
+    LS.sp_x = LS.cx[ind]; LS.sp_y = LS.cy[ind];
+    BdBody& R = E->body[0];
+    R.vw = omega * 3;
+    if (!done_turning) { vx = vx * 0; vy = vy * 0; }
+    R.vx = vx * 2; R.vy = vy * 2;
+}
+
 BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS) {
     const int lane = bp_lane();
     const BdParams& P = C.P;
@@ -289,35 +324,11 @@ BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS) {
     double prev_heading_diff = 0.0;
     if (lane == 0) LS.dp_none = 1;
     bp_wsync();
+    #pragma unroll 1
     for (;;) {
         double hd = heading_diff(heading, wp[wi][2]);
         if (!(fabs(hd) > TURN_STEP_SIZE && fabs(hd - prev_heading_diff) > 0.001)) done_turning = true;
-        if (lane == 0) {
-            // controller(): DP over the course (wp[wi-1], wp[wi])
-            if (LS.dp_none) {
-                LS.cx[0] = wp[wi - 1][0]; LS.cy[0] = wp[wi - 1][1]; LS.cx[1] = wp[wi][0]; LS.cy[1] = wp[wi][1];
-                double d0 = hypot(pos_x - LS.cx[0], pos_y - LS.cy[0]), d1 = hypot(pos_x - LS.cx[1], pos_y - LS.cy[1]);
-                int ind = (d1 < d0) ? 1 : 0;
-                double ddx = LS.cx[1] - LS.cx[0], ddy = LS.cy[1] - LS.cy[0];
-                LS.pl = sqrt(ddx * ddx + ddy * ddy);
-                LS.al = LS.pl;
-                LS.sp_x = LS.cx[ind]; LS.sp_y = LS.cy[ind];
-                LS.dp_none = 0;
-            }
-            double theta_d = atan2(LS.sp_y - pos_y, LS.sp_x - pos_x);
-            double theta_e = theta_d - heading;
-            theta_e = atan2(sin(theta_e), cos(theta_e));
-            double omega = 1.0 * theta_e / P.ctrl_dt;
-            double ch = cos(heading), sh = sin(heading);
-            double vx = ch * P.target_speed + (-sh) * 0.0, vy = sh * P.target_speed + ch * 0.0;
-            LS.al = LS.al + P.target_speed * P.ctrl_dt;
-            int ind = (LS.pl < LS.al) ? 1 : 0;
-            LS.sp_x = LS.cx[ind]; LS.sp_y = LS.cy[ind];
-            BdBody& R = E->body[0];
-            R.vw = omega * 3;
-            if (!done_turning) { vx = vx * 0; vy = vy * 0; }
-            R.vx = vx * 2; R.vy = vy * 2;
-        }
+        if (lane == 0) bd_controller(C, E, LS, wi, pos_x, pos_y, heading, done_turning);
         bp_wsync();
         bd_substep(C, E);
         pos_x = E->body[0].px; pos_y = E->body[0].py; heading = restrict_heading(E->body[0].pa);
@@ -343,12 +354,15 @@ BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS) {
 #if defined(BP_HOST_EMU) || !defined(__CUDACC__)
     double pvx[1 + MAXBOX], pvy[1 + MAXBOX];
 #endif
+    #pragma unroll 1
     for (;;) {
         // un-stick boxes from the walls
+        #pragma unroll 1
         for (int i = lane; i < P.NB; i += BP_NL) {
             BdBody& B = E->body[1 + i];
             if (!B.alive) continue;
             bool stuck = false;
+            #pragma unroll 1
             for (int v = 0; v < SV && !stuck; v++) {
                 V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
                 if (bd_point_query_static(C, w) & (1 << 3)) stuck = true;
@@ -365,6 +379,7 @@ BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS) {
         bp_wsync();
         bool moved = false;
 #if defined(BP_HOST_EMU) || !defined(__CUDACC__)
+        #pragma unroll 1
         for (int b = 0; b <= P.NB; b++) {
             const BdBody& B = E->body[b == P.NB ? 0 : 1 + b];
             if (b < P.NB && !B.alive) continue;
