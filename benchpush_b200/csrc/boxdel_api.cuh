@@ -138,6 +138,9 @@ void bp_boxdel_default_config(bp_boxdel_config* c) {
     c->partial_rewards_scale = 0.2; c->goal_reward = 10.0; c->collision_penalty = 0.25; c->non_movement_penalty = 0.0;
     c->correct_direction_reward_scale = 3.0; c->use_correct_direction_reward = 0; c->ministep_size = 2.5;
     c->shortest_path_channel_scale = 0.25; c->force_box_spfa = 0;
+    c->env_kind = 0; c->step_limit = 10000; c->post_steps = 0; c->t_max = 0; c->n_boundary = 0; c->n_goals = 0;
+    c->lfc = 0.0; c->omega_mul = 3.0; c->v_mul = 2.0; c->bound_x = c->room_length; c->bound_y = c->room_width;
+    c->static_e = 0.01; c->static_u = 1.0; c->robot_code = 6; c->box_code = 4; c->box_done_code = 4; c->n_footprint = 0;
     const double chassis[8] = {0.26, -0.35, -0.31, -0.35, -0.31, 0.35, 0.26, 0.35};
     const double bumper[8] = {0.31, -0.53, 0.20, -0.39, 0.20, 0.39, 0.31, 0.53};
     const double wheels[32] = {0.09, 0.35, 0.09, 0.39, 0.24, 0.39, 0.24, 0.35,   0.09, -0.39, 0.09, -0.35, 0.24, -0.35, 0.24, -0.39,
@@ -176,7 +179,7 @@ int bp_boxdel_destroy(bp_boxdel_t* h) {
 int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
                    int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
                    int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
-                   const uint8_t* small_free, const uint8_t* robot_chan) {
+                   const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map) {
     if (!h || !starts || !n_boxes || !boxes || !st_nv || !st_verts || !st_pose || !st_rad || !st_ctype || !cspace || !cspace_thin || !closest || !small_free || !robot_chan)
         return fail(BP_ERR_INVALID, "null argument");
     if (h->loaded) return fail(BP_ERR_STATE, "already loaded");
@@ -207,7 +210,7 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
     CUDA_TRY(cudaMalloc((void**)&h->d_rchan, (size_t)P.LW * P.LW)); CUDA_TRY(cudaMemcpy(h->d_rchan, robot_chan, (size_t)P.LW * P.LW, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void**)&h->d_recept, nv * 4));
     K.layouts = h->d_layouts; K.n_layouts = n_layouts; K.n_envs = c.n_envs; K.pair_a = h->d_pa; K.pair_b = h->d_pb;
-    K.cspace = h->d_cspace; K.cspace_thin = h->d_thin; K.closest = h->d_closest; K.small_free = h->d_small; K.robot_chan = h->d_rchan; K.recept_dist = h->d_recept;
+    K.cspace = h->d_cspace; K.cspace_thin = h->d_thin; K.closest = h->d_closest; K.small_free = h->d_small; K.robot_chan = h->d_rchan; K.ch3_map = h->d_recept;
     K.env_bytes = bd_env_bytes(P.n_slots);
     CUDA_TRY(cudaMalloc((void**)&h->d_envs, K.env_bytes * c.n_envs));
     CUDA_TRY(cudaMemset(h->d_envs, 0, K.env_bytes * c.n_envs));
@@ -220,8 +223,12 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
     CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdConst), cudaMemcpyHostToDevice));
     k_bd_init_statics<<<1, 32>>>(h->dC);
     CUDA_TRY(cudaGetLastError());
-    // receptacle-source distance field: static for the handle (the reference recomputes it every step, :1115-1129)
-    {
+    // fourth observation channel, static for the handle: the caller's map (area-clearing goal-point map), or the scaled
+    // receptacle-source distance field (the reference recomputes it every step, box_delivery_env.py:1115-1129)
+    if (ch3_map) {
+        CUDA_TRY(cudaMemcpy(h->d_recept, ch3_map, nv * 4, cudaMemcpyHostToDevice));
+    } else {
+        if (c.env_kind != 0) return fail(BP_ERR_INVALID, "area-clearing needs the goal-point map (ch3_map)");
         int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
         pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
         int32_t src[2] = {closest[(size_t)pi * W + pj], closest[nv + (size_t)pi * W + pj]};
@@ -233,6 +240,10 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
         cudaFree(d_src); cudaFree(d_par);
         if (rc != BP_OK) return rc;
         if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("receptacle spfa: ") + cudaGetErrorString(e));
+        std::vector<float> tmp(nv);
+        CUDA_TRY(cudaMemcpy(tmp.data(), h->d_recept, nv * 4, cudaMemcpyDeviceToHost));
+        bd_scale_receptacle_map(P, tmp.data(), nv);
+        CUDA_TRY(cudaMemcpy(h->d_recept, tmp.data(), nv * 4, cudaMemcpyHostToDevice));
     }
     // can the receptacle cell see the whole free space?  (BdParams::recept_visible)
     {
@@ -246,6 +257,7 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpy(&one, h->d_counter, 4, cudaMemcpyDeviceToHost));
         P.recept_visible = (one != 0 && !h->cfg.force_box_spfa) ? 1 : 0;
+        if (c.env_kind == 1) P.recept_visible = 1;          // no receptacle distances in area-clearing
         CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdParams), cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemcpy(&K, h->dC, sizeof(BdConst), cudaMemcpyDeviceToHost));     // statics now in world space

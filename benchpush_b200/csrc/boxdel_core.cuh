@@ -63,6 +63,19 @@ struct BdParams {
     // so shortest_path_distance is the Euclidean distance and needs no spfa solve.  Checked once per handle.
     int recept_visible;
     int recept_ci, recept_cj;     // closest valid cell of the receptacle position
+    // ---- env kind: 0 = box-delivery-v0, 1 = area-clearing-v0 (same control chain and handlers, different constants)
+    int kind;
+    int step_limit;               // STEP_LIMIT of execute_robot_path: 10000 (box_delivery_env.py:62) / 5000 (area_clearing.py:76)
+    int post_steps;               // area-clearing: cfg.sim.steps fixed substeps after the path (area_clearing.py:692-693)
+    int t_max;                    // area-clearing: cfg.sim.t_max
+    double lfc;                   // cfg.controller.Lfc (TargetCourse look-ahead, dp.py:74-84); 0 when absent
+    double omega_mul, v_mul;      // apply_controller: omega * 3, v * 2 (box_delivery_env.py:887-889) / omega / 2, v * 5 (area_clearing.py:903-906)
+    double bound_x, bound_y;      // PositionController room clamp: map_height (x) and map_width (y) as passed by the env (D17)
+    double robot_code, box_code, box_done_code;       // overhead-map segment indices (k / 8 is the pixel value)
+    int draw_recept, n_bnd, n_goal, pad1;
+    double bnd[8][2];             // area-clearing: clearance polygon (convex), cfg env `boundary`
+    double goal[64][2];           // area-clearing: goal points on the clearance boundary (area_clearing.py:225-263)
+    double r_boundary, r_cleared, r_putback, r_push_mult, r_terminal, r_truncation, r_nonmove;   // area_clearing.py:41-52
 };
 
 struct BdBody {                   // 176 B
@@ -100,6 +113,7 @@ struct BdLayout {                 // immutable per layout
 struct BdShapes {                 // immutable per handle: robot shapes (body-local) and static shapes (world)
     double rb_lv[NROBOT][SV][2], rb_ln[NROBOT][SV][2], rb_rad[NROBOT], rb_e[NROBOT], rb_u[NROBOT];
     int rb_nv[NROBOT];
+    double rb_foot[SV][2]; int n_foot, pad_foot;     // polygon drawn for the robot in the overhead map (body-local)
     double st_lv[MAXSTAT][SV][2], st_ln[MAXSTAT][SV][2], st_pose[MAXSTAT][3];   // as created (body-local + body pose)
     alignas(16) double st_v[MAXSTAT][SV][2];                                       // world (filled by bd_init_statics); 128-bit vertex loads
     double st_n[MAXSTAT][SV][2], st_p[MAXSTAT][2];
@@ -111,6 +125,7 @@ struct BdShapes {                 // immutable per handle: robot shapes (body-lo
 
 struct BdEnv {                    // mutable per env (header; the slot table follows it in the env block)
     int layout, episode, t, status, stamp, n_order, robot_hit, inactivity, cum_boxes, done, truncated, n_prev;
+    int cleared_count, pad_c;
     int n_path, move_sign, need_spfa, src_i, src_j, tgt_i, tgt_j, n_live;      // n_live: slots with state != SL_NONE
     long long stat_substeps, stat_cand, stat_arb;
     double prev_dt, cum_distance, cum_reward, total_work, last_work, reward, ministeps;
@@ -142,7 +157,8 @@ struct BdConst {
     const int32_t* closest;                                 // [2][H][W] distance_transform_edt indices
     const uint8_t* small_free;                              // [SMALL][SMALL] 1 = free floor (small_obstacle_map)
     const uint8_t* robot_chan;                              // [LW][LW] robot_state_channel * 255
-    const float* recept_dist;                               // [H][W] spfa from the receptacle cell, unscaled
+    const float* ch3_map;                                   // [H][W] fourth observation channel before the window shift: scaled spfa field of the
+                                                            //        receptacle (box-delivery) / goal-point map (area-clearing); static per handle
     char* envs; size_t env_bytes;
 };
 BP_DEV BdEnv* bd_env(const BdConst& C, int e) { return (BdEnv*)(C.envs + (size_t)e * C.env_bytes); }

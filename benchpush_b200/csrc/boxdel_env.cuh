@@ -103,7 +103,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
     for (int p = lane; p < P.n_slots; p += BP_NL) { slots[p].state = SL_NONE; slots[p].cnt = 0; slots[p].stamp = 0; slots[p].gjk = 0; slots[p].ov = 0; slots[p].mvalid = 0; }
     if (lane == 0) {
         E->layout = layout; E->episode = episode; E->t = 0; E->status = 0; E->stamp = 0; E->n_order = 0; E->robot_hit = 0;
-        E->inactivity = 0; E->cum_boxes = 0; E->done = 0; E->truncated = 0; E->n_path = 0; E->need_spfa = 0; E->n_live = 0;
+        E->inactivity = 0; E->cum_boxes = 0; E->done = 0; E->truncated = 0; E->n_path = 0; E->need_spfa = 0; E->n_live = 0; E->cleared_count = 0;
         E->prev_dt = 0.0; E->cum_distance = 0.0; E->cum_reward = 0.0; E->total_work = 0.0; E->last_work = 0.0; E->reward = 0.0; E->ministeps = 0.0;
         E->stat_substeps = 0; E->stat_cand = 0; E->stat_arb = 0;
         BdBody& R = E->body[0];
@@ -169,7 +169,7 @@ BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action) {
     double tx = x0 + sld * cos(slh), ty = y0 + sld * sin(slh);
     double dxx = tx - x0, dyy = ty - y0;
     double ratio_x = 1, ratio_y = 1;
-    double bound_x = sgn(tx) * P.room_length / 2, bound_y = sgn(ty) * P.room_width / 2;
+    double bound_x = sgn(tx) * P.bound_x / 2, bound_y = sgn(ty) * P.bound_y / 2;
     if (fabs(tx) > fabs(bound_x)) ratio_x = (bound_x - x0) / (tx - x0);
     if (fabs(ty) > fabs(bound_y)) ratio_y = (bound_y - y0) / (ty - y0);
     double ratio = fmin(ratio_x, ratio_y);
@@ -186,7 +186,7 @@ BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action) {
         closest_valid(C, si, sj, &E->src_i, &E->src_j);
         closest_valid(C, ti, tj, &E->tgt_i, &E->tgt_j);
     }
-    if (P.recept_visible) bd_box_dists_visible(C, E, E->init_dist);
+    if (P.kind == 0 && P.recept_visible) bd_box_dists_visible(C, E, E->init_dist);
 }
 
 // ------------------------------------------------------------------ path from a distance field (second half of shortest_path)
@@ -289,6 +289,8 @@ BP_DEVNI void bd_controller(const BdConst& C, BdEnv* E, BdLoop& LS, int wi, doub
         LS.cx[0] = wp[wi - 1][0]; LS.cy[0] = wp[wi - 1][1]; LS.cx[1] = wp[wi][0]; LS.cy[1] = wp[wi][1];
         double d0 = hypot(pos_x - LS.cx[0], pos_y - LS.cy[0]), d1 = hypot(pos_x - LS.cx[1], pos_y - LS.cy[1]);
         int ind = (d1 < d0) ? 1 : 0;
+        // TargetCourse.init_setpoint: look ahead while Lfc exceeds the distance to the course point (dp.py:74-84)
+        while (P.lfc > dist2(pos_x, pos_y, LS.cx[ind], LS.cy[ind])) { if (ind + 1 >= 2) break; ind++; }
         double ddx = LS.cx[1] - LS.cx[0], ddy = LS.cy[1] - LS.cy[0];
         LS.pl = sqrt(ddx * ddx + ddy * ddy);
         LS.al = LS.pl;
@@ -305,9 +307,9 @@ BP_DEVNI void bd_controller(const BdConst& C, BdEnv* E, BdLoop& LS, int wi, doub
     int ind = (LS.pl < LS.al) ? 1 : 0;
     LS.sp_x = LS.cx[ind]; LS.sp_y = LS.cy[ind];
     BdBody& R = E->body[0];
-    R.vw = omega * 3;
+    R.vw = omega * P.omega_mul;
     if (!done_turning) { vx = vx * 0; vy = vy * 0; }
-    R.vx = vx * 2; R.vy = vy * 2;
+    R.vx = vx * P.v_mul; R.vy = vy * P.v_mul;
 }
 
 BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS) {
@@ -343,10 +345,16 @@ BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS) {
             bp_wsync();
         }
         sim_steps++;
-        if (sim_steps > STEP_LIMIT) { if (lane == 0) E->status |= BD_STEP_LIMIT; break; }
+        if (sim_steps > P.step_limit) { if (lane == 0) E->status |= BD_STEP_LIMIT; break; }
     }
     if (lane == 0) E->robot_distance = robot_distance;
     bp_wsync();
+    if (P.kind == 1) {
+        // area-clearing: a fixed number of substeps follows the path (area_clearing.py:692-693); no until-still loop
+#pragma unroll 1
+        for (int k = 0; k < P.post_steps; k++) bd_substep(C, E);
+        return;
+    }
     // step_simulation_until_still
     double prev_x = 0, prev_y = 0;       // lane b < NB: box b; lane NB: robot  (NB + 1 <= 32 lanes; the single-lane emulation loops)
     bool have_prev = false;
@@ -410,8 +418,10 @@ BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS) {
 
 // ------------------------------------------------------------------ step, part 3: rewards, removal, work, termination
 // Scalar; run by one lane.
+BP_DEV void ac_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out);
 BP_DEV void bd_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out) {
     const BdParams& P = C.P;
+    if (P.kind == 1) { ac_finish_step(C, E, env, out); return; }
     const BdLayout& L = C.layouts[E->layout];
     double reward = 0.0;
     int robot_boxes = 0;
@@ -480,6 +490,91 @@ BP_DEV void bd_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out
         for (int q = 0; q < k; q++) for (int v = 0; v < SV; v++) { o[(q * SV + v) * 2] = upd[q][v][0]; o[(q * SV + v) * 2 + 1] = upd[q][v][1]; }
     }
 }
+// ------------------------------------------------------------------ area-clearing-v0: completion, rewards, truncation
+// shapely Polygon.intersects for two convex polygons: closed sets, touching counts (separating-axis test)
+BP_DEV bool convex_intersects(const double (*A)[2], int na, const double (*B)[2], int nb) {
+    for (int pass = 0; pass < 2; pass++) {
+        const double (*P)[2] = pass ? B : A; int np = pass ? nb : na;
+        const double (*Q)[2] = pass ? A : B; int nq = pass ? na : nb;
+        for (int i = 0; i < np; i++) {
+            int j = (i + 1) % np;
+            double ex = P[j][0] - P[i][0], ey = P[j][1] - P[i][1];
+            double nx = ey, ny = -ex;
+            double amax = -INFINITY, amin = INFINITY, bmax = -INFINITY, bmin = INFINITY;
+            for (int k = 0; k < np; k++) { double d = nx * P[k][0] + ny * P[k][1]; amax = fmax(amax, d); amin = fmin(amin, d); }
+            for (int k = 0; k < nq; k++) { double d = nx * Q[k][0] + ny * Q[k][1]; bmax = fmax(bmax, d); bmin = fmin(bmin, d); }
+            if (amax < bmin || bmax < amin) return false;
+        }
+    }
+    return true;
+}
+BP_DEV double min_goal_dist(const BdParams& P, double cx, double cy) {
+    double m = INFINITY;
+    for (int g = 0; g < P.n_goal; g++) m = fmin(m, dist2(cx, cy, P.goal[g][0], P.goal[g][1]));
+    return m;
+}
+// AreaClearingEnv.step after the substeps (area_clearing.py:695-778): boxes_completed (:1122-1140), obs_to_goal_difference
+// (evaluation/metrics.py:73-94, centroids abs-folded by poly_centroid: D4), total_work_done, reward, truncation clock (D13).
+// Scalar; run by one lane.
+BP_DEV void ac_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out) {
+    const BdParams& P = C.P;
+    const BdLayout& L = C.layouts[E->layout];
+    const int NB = L.n_boxes;
+    double upd[MAXBOX][SV][2];
+    for (int i = 0; i < NB; i++)
+        for (int v = 0; v < SV; v++) { V2 w = bd_local_to_world(E->body[1 + i], L.box_lv[i][v][0], L.box_lv[i][v][1]); upd[i][v][0] = w.x; upd[i][v][1] = w.y; }
+    double collision_penalty = E->robot_hit ? P.r_boundary : 0.0;
+    int num_completed = 0;
+    for (int i = 0; i < NB; i++) {
+        bool outside = !convex_intersects(P.bnd, P.n_bnd, upd[i], SV);
+        num_completed += outside ? 1 : 0;
+        E->completed[i] = outside ? 1 : 0;
+    }
+    bool all_completed = (num_completed == P.num_boxes);
+    double diff_reward = 0.0, work = 0.0;
+    for (int i = 0; i < NB; i++) {
+        double A, ax, ay, A2, bx, by;
+        area_centroid_abs(&E->prev_boxes[i][0][0], SV, &A, &ax, &ay);
+        area_centroid_abs(&upd[i][0][0], SV, &A2, &bx, &by);
+        if (convex_intersects(P.bnd, P.n_bnd, E->prev_boxes[i], SV)) diff_reward += min_goal_dist(P, ax, ay) - min_goal_dist(P, bx, by);
+        double dx = ax - bx, dy = ay - by;
+        work += sqrt(dx * dx + dy * dy) * A;
+    }
+    double pushing_reward = diff_reward * P.r_push_mult;
+    double box_completion_reward;
+    int delta = num_completed - E->cleared_count; if (delta < 0) delta = -delta;
+    if (num_completed > E->cleared_count) { box_completion_reward = delta * P.r_cleared; E->t = 0; }
+    else box_completion_reward = delta * P.r_putback;
+    E->cleared_count = num_completed;
+    const BdBody& R = E->body[0];
+    double heading = restrict_heading(R.pa);
+    double turn = heading_diff(E->init_heading, heading);
+    double nonmove = (E->robot_distance < NONMOVEMENT_DIST_THRESHOLD && fabs(turn) < NONMOVEMENT_TURN_THRESHOLD) ? P.r_nonmove : 0.0;
+    E->total_work += work; E->last_work = work;
+    for (int i = 0; i < NB; i++) for (int v = 0; v < SV; v++) { E->prev_boxes[i][v][0] = upd[i][v][0]; E->prev_boxes[i][v][1] = upd[i][v][1]; }
+    int terminated = all_completed ? 1 : 0;
+    double reward = box_completion_reward + collision_penalty + pushing_reward + nonmove;
+    int truncated = E->t >= P.t_max;
+    if (truncated) reward += P.r_truncation; else if (terminated) reward += P.r_terminal;
+    E->done = terminated; E->truncated = truncated; E->reward = reward; E->cum_boxes = num_completed; E->cum_reward += reward;
+    E->ministeps = E->robot_distance / 2.5;
+    E->robot_hit = 0;
+    if (out.reward) out.reward[env] = reward;
+    if (out.terminated) out.terminated[env] = (unsigned char)terminated;
+    if (out.truncated) out.truncated[env] = (unsigned char)truncated;
+    if (out.info) {
+        double* o = out.info + (size_t)env * 8;
+        o[0] = round2dp(R.px); o[1] = round2dp(R.py); o[2] = round2dp(R.pa);
+        o[3] = diff_reward; o[4] = box_completion_reward; o[5] = E->total_work; o[6] = E->ministeps; o[7] = work;
+    }
+    if (out.info_i) { int* o = out.info_i + (size_t)env * 4; o[0] = num_completed; o[1] = E->t; o[2] = NB; o[3] = E->status; }
+    if (out.completed) for (int i = 0; i < P.NB; i++) out.completed[(size_t)env * P.NB + i] = E->completed[i];
+    if (out.box_verts) {
+        double* o = out.box_verts + (size_t)env * P.NB * SV * 2;
+        for (int q = 0; q < NB; q++) for (int v = 0; v < SV; v++) { o[(q * SV + v) * 2] = upd[q][v][0]; o[(q * SV + v) * 2 + 1] = upd[q][v][1]; }
+    }
+}
+
 // info after reset (box_delivery_env.py:618-630)
 BP_DEV void bd_reset_out(const BdConst& C, BdEnv* E, int env, const BdOut& out) {
     const BdParams& P = C.P;

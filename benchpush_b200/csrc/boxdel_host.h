@@ -28,7 +28,7 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
     BdParams& P = K.P;
     P.NB = c.num_boxes; P.n_static = n_static; P.n_s3 = 0; P.recept = -1;
     for (int k = 0; k < n_static; k++) { if (st_ctype[k] == 3) P.s3[P.n_s3++] = k; else if (st_ctype[k] == 4) P.recept = k; }
-    if (P.recept < 0) return std::string("no receptacle (collision_type 4) among the static shapes");
+    if (P.recept < 0 && c.env_kind == 0) return std::string("no receptacle (collision_type 4) among the static shapes");
     P.n_slots = bd_build_pairs(P, nullptr, nullptr);
     P.iterations = c.iterations; P.persistence = 3; P.settle_steps = c.settle_steps;
     P.dt = c.ctrl_dt / c.steps; P.damp = std::pow(c.damping, P.dt);
@@ -46,6 +46,16 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
     P.nonmove_penalty = c.non_movement_penalty; P.correct_scale = c.correct_direction_reward_scale; P.ministep = c.ministep_size;
     P.use_correct = c.use_correct_direction_reward; P.inactivity_cutoff = c.inactivity_cutoff; P.num_boxes = c.num_boxes; P.action_type = c.action_type;
     P.sp_div = (std::sqrt(2.0) * P.LW) / P.ppm; P.sp_scale = c.shortest_path_channel_scale;
+    P.kind = c.env_kind; P.step_limit = c.step_limit; P.post_steps = c.post_steps; P.t_max = c.t_max;
+    P.lfc = c.lfc; P.omega_mul = c.omega_mul; P.v_mul = c.v_mul; P.bound_x = c.bound_x; P.bound_y = c.bound_y;
+    P.robot_code = c.robot_code; P.box_code = c.box_code; P.box_done_code = c.box_done_code; P.draw_recept = (c.env_kind == 0);
+    if (c.n_boundary < 0 || c.n_boundary > 8 || c.n_goals < 0 || c.n_goals > 64) return std::string("n_boundary / n_goals out of range");
+    P.n_bnd = c.n_boundary; P.n_goal = c.n_goals;
+    for (int i = 0; i < c.n_boundary; i++) { P.bnd[i][0] = c.boundary[2 * i]; P.bnd[i][1] = c.boundary[2 * i + 1]; }
+    for (int i = 0; i < c.n_goals; i++) { P.goal[i][0] = c.goals[2 * i]; P.goal[i][1] = c.goals[2 * i + 1]; }
+    P.r_boundary = c.r_boundary; P.r_cleared = c.r_cleared; P.r_putback = c.r_putback; P.r_push_mult = c.r_push_mult;
+    P.r_terminal = c.r_terminal; P.r_truncation = c.r_truncation; P.r_nonmove = c.r_nonmove;
+    if (c.env_kind == 1) { P.recept_x = 0.0; P.recept_y = 0.0; }
     // ---- shapes
     BdShapes& S = K.S;
     {
@@ -69,9 +79,18 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
             if (b.verts.size() < 3) return std::string("degenerate static shape");
             bd_fill_prep(b, S.st_lv[k], S.st_ln[k], &S.st_nv[k]);
             S.st_pose[k][0] = st_pose[3 * k]; S.st_pose[k][1] = st_pose[3 * k + 1]; S.st_pose[k][2] = st_pose[3 * k + 2];
-            S.st_rad[k] = st_rad[k]; S.st_e[k] = 0.01; S.st_u[k] = 1.0; S.st_ctype[k] = st_ctype[k];
+            S.st_rad[k] = st_rad[k]; S.st_e[k] = c.static_e; S.st_u[k] = c.static_u; S.st_ctype[k] = st_ctype[k];
         }
         S.box_rad = 0.02; S.box_e = 0.01; S.box_u = 1.0;     // create_polygon ignores its radius argument (D7)
+        // polygon drawn for the robot in the overhead map: cfg.agent.footprint_vertices (area-clearing) or the chassis hull
+        if (c.n_footprint > 0) {
+            if (c.n_footprint > SV) return std::string("n_footprint out of range");
+            S.n_foot = c.n_footprint;
+            for (int i = 0; i < c.n_footprint; i++) { S.rb_foot[i][0] = c.footprint_verts[2 * i]; S.rb_foot[i][1] = c.footprint_verts[2 * i + 1]; }
+        } else {
+            S.n_foot = S.rb_nv[0];
+            for (int i = 0; i < S.n_foot; i++) { S.rb_foot[i][0] = S.rb_lv[0][i][0]; S.rb_foot[i][1] = S.rb_lv[0][i][1]; }
+        }
     }
     // ---- layouts
     std::vector<BdLayout>& LY = HB.LY; LY.assign(n_layouts, BdLayout());
@@ -100,6 +119,16 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
     bd_build_pairs(P, HB.pa.data(), HB.pb.data());
     K.n_layouts = n_layouts; K.n_envs = c.n_envs; K.env_bytes = bd_env_bytes(P.n_slots);
     return "";
+}
+
+// fourth observation channel of box-delivery before the window shift: create_global_shortest_path_to_receptacle_map
+// (box_delivery_env.py:1115-1129): spfa field / ppm (f32), / ((sqrt 2 LW) / ppm) (f64, rounded to f32), * scale (f32)
+inline void bd_scale_receptacle_map(const BdParams& P, float* m, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        float a = m[i] / (float)P.ppm;
+        float b = (float)((double)a / P.sp_div);
+        m[i] = b * (float)P.sp_scale;
+    }
 }
 
 }  // namespace bd

@@ -146,7 +146,7 @@ BP_DEV void bd_obs_item(BdObsShared& S, const BdConst& C, const BdEnv* E, int* s
         BP_BSYNC();
     }
     // ---- small overhead map: floor / obstacle, receptacle, boxes, robot chassis (update_global_overhead_map)
-    for (int i = tid; i < N * N; i += nt) small[i] = C.small_free[i] ? 1 : 0;
+    for (int i = tid; i < N * N; i += nt) small[i] = C.small_free[i];        // static codes: 0 obstacle, 1 floor (3 goal area in area-clearing)
     BP_BSYNC();
     auto to_px = [&](double wx, double wy, int* x, int* y) {
         int ix = (int)(wx * P.ppm), iy = (int)(wy * P.ppm);       // astype(np.int32): truncation toward zero
@@ -158,17 +158,19 @@ BP_DEV void bd_obs_item(BdObsShared& S, const BdConst& C, const BdEnv* E, int* s
         bool skip = false;
         if (tid == 0) {
             if (q == 0) {
-                n = C.S.st_nv[P.recept]; code = 3;
-                for (int v = 0; v < n; v++) to_px(C.S.st_v[P.recept][v][0], C.S.st_v[P.recept][v][1], &S.px[v], &S.py[v]);
+                if (P.draw_recept) {
+                    n = C.S.st_nv[P.recept]; code = 3;
+                    for (int v = 0; v < n; v++) to_px(C.S.st_v[P.recept][v][0], C.S.st_v[P.recept][v][1], &S.px[v], &S.py[v]);
+                }
             } else if (q <= P.NB) {
                 const BdBody& B = E->body[q];
                 if (B.alive == 1) {
-                    n = SV; code = 4;
+                    n = SV; code = (unsigned char)(E->completed[q - 1] ? P.box_done_code : P.box_code);
                     for (int v = 0; v < SV; v++) { V2 w = bd_local_to_world(B, L.box_lv[q - 1][v][0], L.box_lv[q - 1][v][1]); to_px(w.x, w.y, &S.px[v], &S.py[v]); }
                 }
             } else {
-                n = C.S.rb_nv[0]; code = 6;
-                for (int v = 0; v < n; v++) { V2 w = bd_local_to_world(R, C.S.rb_lv[0][v][0], C.S.rb_lv[0][v][1]); to_px(w.x, w.y, &S.px[v], &S.py[v]); }
+                n = C.S.n_foot; code = (unsigned char)P.robot_code;
+                for (int v = 0; v < n; v++) { V2 w = bd_local_to_world(R, C.S.rb_foot[v][0], C.S.rb_foot[v][1]); to_px(w.x, w.y, &S.px[v], &S.py[v]); }
             }
             S.minbits[0] = n; S.minbits[1] = code;
         }
@@ -208,7 +210,7 @@ BP_DEV void bd_obs_item(BdObsShared& S, const BdConst& C, const BdEnv* E, int* s
         return gi * P.W + gj;
     };
     auto ch2 = [&](int g) -> float { if (g < 0) return 0.0f; float d = i2f(dist[g]); return bd_scale_sp(P, d < inf ? d : 0.0f); };
-    auto ch3 = [&](int g) -> float { if (g < 0) return 0.0f; return bd_scale_sp(P, C.recept_dist[g]); };
+    auto ch3 = [&](int g) -> float { if (g < 0) return 0.0f; return C.ch3_map[g]; };
     // ---- pass 1: minima of the two distance channels over the window
     if (tid == 0) { S.minbits[0] = f2i(INFINITY); S.minbits[1] = f2i(INFINITY); }
     BP_BSYNC();

@@ -1,9 +1,10 @@
 """Batched environments.  Ids follow the reference registry (benchpush/environments/__init__.py:3-51)."""
+from .area_clearing import AreaClearingVecEnv
 from .box_delivery import BoxDeliveryVecEnv
 from .maze_namo import MazeNamoVecEnv
 from .ship_ice import ShipIceVecEnv
 
-REGISTRY = {"ship-ice-v0": ShipIceVecEnv, "maze-NAMO-v0": MazeNamoVecEnv, "box-delivery-v0": BoxDeliveryVecEnv}
+REGISTRY = {"ship-ice-v0": ShipIceVecEnv, "maze-NAMO-v0": MazeNamoVecEnv, "box-delivery-v0": BoxDeliveryVecEnv, "area-clearing-v0": AreaClearingVecEnv}
 MAX_EPISODE_STEPS = {"ship-ice-v0": 300, "box-delivery-v0": 30000, "area-clearing-v0": 400, "maze-NAMO-v0": 30000}
 
 

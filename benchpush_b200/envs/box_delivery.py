@@ -71,6 +71,15 @@ class BoxDelConfig(C.Structure):
         ("non_movement_penalty", C.c_double), ("correct_direction_reward_scale", C.c_double),
         ("ministep_size", C.c_double), ("shortest_path_channel_scale", C.c_double),
         ("chassis_verts", C.c_double * 8), ("bumper_verts", C.c_double * 8), ("wheel_verts", C.c_double * 32),
+        ("env_kind", C.c_int32), ("step_limit", C.c_int32), ("post_steps", C.c_int32), ("t_max", C.c_int32),
+        ("n_boundary", C.c_int32), ("n_goals", C.c_int32),
+        ("lfc", C.c_double), ("omega_mul", C.c_double), ("v_mul", C.c_double), ("bound_x", C.c_double), ("bound_y", C.c_double),
+        ("static_e", C.c_double), ("static_u", C.c_double),
+        ("robot_code", C.c_double), ("box_code", C.c_double), ("box_done_code", C.c_double),
+        ("footprint_verts", C.c_double * 8), ("n_footprint", C.c_int32), ("reserved1", C.c_int32),
+        ("boundary", C.c_double * 16), ("goals", C.c_double * 128),
+        ("r_boundary", C.c_double), ("r_cleared", C.c_double), ("r_putback", C.c_double), ("r_push_mult", C.c_double),
+        ("r_terminal", C.c_double), ("r_truncation", C.c_double), ("r_nonmove", C.c_double),
     ]
 
 
@@ -85,7 +94,7 @@ def bind(L):
     L.bp_boxdel_create.argtypes = [C.POINTER(BoxDelConfig), C.POINTER(C.c_void_p)]
     L.bp_boxdel_destroy.argtypes = [C.c_void_p]
     L.bp_boxdel_load.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + \
-                                [C.c_int32, C.c_int32] + [C.c_void_p] * 5
+                                [C.c_int32, C.c_int32] + [C.c_void_p] * 6
     L.bp_boxdel_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
     L.bp_boxdel_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
     L.bp_boxdel_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs)]
@@ -251,6 +260,12 @@ class BoxDeliveryVecEnv:
             k.bumper_verts[i] = float(v)
         for i, v in enumerate(np.asarray(c["agent"]["wheel_vertices"], dtype=np.float64).reshape(-1)):
             k.wheel_verts[i] = float(v)
+        k.bound_x = float(self.room.room_length); k.bound_y = float(self.room.room_width)     # D17: x clamps with map_height = room_length
+        self._finish_init(k, self.room, ch3_map=None)
+
+    def _finish_init(self, k, r, ch3_map):
+        """Create the native handle from the filled config, upload layouts / room maps, allocate the output buffers."""
+        L, E, NB, LW = self._L, self.num_envs, self.num_boxes, self.local_map_pixel_width
         self._h = C.c_void_p()
         self._check(L.bp_boxdel_create(C.byref(k), C.byref(self._h)))
         nl = len(self.layouts)
@@ -259,15 +274,16 @@ class BoxDeliveryVecEnv:
         boxes = np.zeros((nl, NB, 3), dtype=np.float64)
         for i, l in enumerate(self.layouts):
             boxes[i, :len(l["boxes"])] = np.asarray(l["boxes"], dtype=np.float64).reshape(-1, 3)
-        r = self.room
         cs = np.ascontiguousarray(r.configuration_space.astype(np.uint8))
         th = np.ascontiguousarray(r.configuration_space_thin.astype(np.uint8))
         cl = np.ascontiguousarray(r.closest_cspace_indices.astype(np.int32))
         sm = np.ascontiguousarray(r.small_obstacle_map.astype(np.uint8))
         rc = np.ascontiguousarray((r.robot_state_channel * 255).astype(np.uint8))
+        c3 = None if ch3_map is None else np.ascontiguousarray(ch3_map, dtype=np.float32)
         self._check(L.bp_boxdel_load(self._h, nl, starts.ctypes.data, nbx.ctypes.data, boxes.ctypes.data, len(r.statics),
                                      r.st_nv.ctypes.data, r.st_verts.ctypes.data, r.st_pose.ctypes.data, r.st_rad.ctypes.data, r.st_ctype.ctypes.data,
-                                     r.shape[0], r.shape[1], cs.ctypes.data, th.ctypes.data, cl.ctypes.data, sm.ctypes.data, rc.ctypes.data))
+                                     r.shape[0], r.shape[1], cs.ctypes.data, th.ctypes.data, cl.ctypes.data, sm.ctypes.data, rc.ctypes.data,
+                                     None if c3 is None else c3.ctypes.data))
         # ---- buffers
         self._buf = {}
         self._alloc("obs", (E, LW, LW, 4), "uint8"); self._alloc("reward", (E,), "float64")

@@ -307,3 +307,23 @@ def sample_box_delivery_layout(random_state, cfg) -> dict:
         if ok:
             boxes.append([float(cx), float(cy), float(hd)])
     return {"start": start, "boxes": boxes}
+
+
+def sample_area_clearing_layout(rng, cfg, env_cfg) -> dict:
+    """One area-clearing episode layout drawn the way the reference draws it (area_clearing.py:363-368 robot start,
+    :515-541 generate_obstacles) from a ``random.Random`` (the reference uses the unseeded global ``random`` module)."""
+    b = env_cfg["boundary"]
+    min_x, max_x = min(p[0] for p in b), max(p[0] for p in b)
+    min_y, max_y = min(p[1] for p in b), max(p[1] for p in b)
+    if cfg["random_start"]:
+        start = ((min_x + 1) + rng.random() * ((max_x - min_x) - 2), min_y + 1.0, float(np.pi / 2))
+    else:
+        start = ((min_x + max_x) / 2, min_y + 1.0, float(np.pi / 2))
+    lo_x, hi_x, lo_y, hi_y = min_x + 1, max_x - 1, min_y + 1, max_y - 1
+    obs = []
+    while len(obs) < cfg["num_obstacles"]:
+        cx = rng.random() * (hi_x - lo_x) + lo_x
+        cy = rng.random() * (hi_y - lo_y) + lo_y
+        if all(((cx - px) ** 2 + (cy - py) ** 2) ** 0.5 > cfg["min_obs_dist"] for px, py in obs):
+            obs.append([float(cx), float(cy)])
+    return {"start": tuple(float(v) for v in start), "boxes": obs}

@@ -265,6 +265,20 @@ typedef struct bp_boxdel_config {
     double partial_rewards_scale, goal_reward, collision_penalty, non_movement_penalty, correct_direction_reward_scale;
     double ministep_size, shortest_path_channel_scale;
     double chassis_verts[8], bumper_verts[8], wheel_verts[32];   /* cfg.agent.vertices / front_bumper_vertices / wheel_vertices */
+    /* ---- area-clearing-v0 (env_kind 1) runs on the same handle type: AreaClearingEnv.reset / step / generate_observation
+     * (benchpush/environments/area_clearing/area_clearing.py:563-778, 927-950), same control chain and wall handlers. */
+    int32_t env_kind;             /* 0 = box-delivery-v0, 1 = area-clearing-v0 */
+    int32_t step_limit;           /* STEP_LIMIT: 10000 (box_delivery_env.py:62) / 5000 (area_clearing.py:76) */
+    int32_t post_steps, t_max;    /* area-clearing: cfg.sim.steps substeps after the path; cfg.sim.t_max */
+    int32_t n_boundary, n_goals;  /* area-clearing: clearance polygon vertices (<= 8), goal points (<= 64) */
+    double lfc, omega_mul, v_mul; /* cfg.controller.Lfc; apply_controller gains (3, 2 box-delivery; 0.5, 5 area-clearing) */
+    double bound_x, bound_y;      /* PositionController room clamp in x / y */
+    double static_e, static_u;    /* elasticity / friction of the static shapes (0.01, 1.0 box-delivery; 0, 0.99 area-clearing) */
+    double robot_code, box_code, box_done_code;   /* overhead-map segment indices of the robot, boxes, completed boxes */
+    double footprint_verts[8];    /* polygon drawn for the robot (area-clearing: cfg.agent.footprint_vertices; 0 = chassis hull) */
+    int32_t n_footprint, reserved1;
+    double boundary[16], goals[128];
+    double r_boundary, r_cleared, r_putback, r_push_mult, r_terminal, r_truncation, r_nonmove;   /* area_clearing.py:41-52 */
 } bp_boxdel_config;
 
 typedef struct bp_boxdel_outputs {  /* every pointer optional */
@@ -285,7 +299,7 @@ int bp_boxdel_destroy(bp_boxdel_t* h);
 int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
                    int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
                    int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
-                   const uint8_t* small_free, const uint8_t* robot_chan);
+                   const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map);
 /* DEVICE pointers, enqueued on `stream`, no host synchronisation */
 int bp_boxdel_reset(bp_boxdel_t* h, const int32_t* layout_ids, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream);
 int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream);

@@ -360,6 +360,12 @@ class BoxDeliveryOracleEnv:
         self.episode_idx = None
         self.path = None
         self.dp = None
+        # knobs the area-clearing restatement overrides (same control chain, different constants)
+        self.bound_x_half = self.room_length / 2      # PositionController clamps x with map_height, y with map_width (D17)
+        self.bound_y_half = self.room_width / 2
+        self.lfc = 0.0                                # cfg.controller.Lfc (absent in box-delivery => 0)
+        self.omega_gain, self.v_gain = 3, 2           # apply_controller (box_delivery_env.py:887-889)
+        self.step_limit = STEP_LIMIT
 
     # ---- sim construction (box_delivery_env.py:185-292; sim_utils.py:20-165)
     def _build_space(self, layout):
@@ -617,8 +623,8 @@ class BoxDeliveryOracleEnv:
         tgt = [p0[0] + straight_line_dist * np.cos(straight_line_heading), p0[1] + straight_line_dist * np.sin(straight_line_heading)]
         diff = np.asarray(tgt) - np.asarray(p0)
         ratio_x, ratio_y = (1, 1)
-        bound_x = np.sign(tgt[0]) * self.room_length / 2
-        bound_y = np.sign(tgt[1]) * self.room_width / 2
+        bound_x = np.sign(tgt[0]) * (2 * self.bound_x_half) / 2
+        bound_y = np.sign(tgt[1]) * (2 * self.bound_y_half) / 2
         if abs(tgt[0]) > abs(bound_x):
             ratio_x = (bound_x - p0[0]) / (tgt[0] - p0[0])
         if abs(tgt[1]) > abs(bound_y):
@@ -650,6 +656,11 @@ class BoxDeliveryOracleEnv:
             chh = [self.path[0][2], self.path[1][2]]
             d = np.hypot([x - cx[0], x - cx[1]], [y - cy[0], y - cy[1]])
             ind = int(np.argmin(d))
+            # TargetCourse.init_setpoint (dp.py:74-84): look-ahead while Lfc exceeds the distance to the course point
+            while self.lfc > ((x - cx[ind]) ** 2 + (y - cy[ind]) ** 2) ** 0.5:
+                if (ind + 1) >= len(cx):
+                    break
+                ind += 1
             # metrics.py:176-181 path_length(cumsum=True) of TWO points is the one-element array [d] (no leading 0), so
             # setpoint_al starts at d whatever `ind` is, and the first advance() already selects course point 1
             path_length = (np.sum(np.diff(np.asarray([cx, cy]).T, axis=0) ** 2, axis=1) ** 0.5).cumsum()
@@ -669,8 +680,8 @@ class BoxDeliveryOracleEnv:
         return omega, v
 
     def apply_controller(self, omega, v):
-        self.space.set_angular_velocity(self.robot_body, omega * 3)
-        vv = (v * 2).tolist()
+        self.space.set_angular_velocity(self.robot_body, omega * 3 if self.omega_gain == 3 else omega / 2)
+        vv = (v * self.v_gain).tolist()
         self.space.set_velocity(self.robot_body, vv[0], vv[1])
 
     def execute_robot_path(self, p_init, h_init, move_sign):
@@ -724,7 +735,7 @@ class BoxDeliveryOracleEnv:
                     self.dp = None
                     self.path = self.path[1:]
             sim_steps += 1
-            if sim_steps > STEP_LIMIT:
+            if sim_steps > self.step_limit:
                 break
         _, ang = self.robot_pose()
         heading = restrict_heading_range(ang)

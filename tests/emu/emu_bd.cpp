@@ -52,6 +52,9 @@ void bp_boxdel_default_config(bp_boxdel_config* c) {
     c->partial_rewards_scale = 0.2; c->goal_reward = 10.0; c->collision_penalty = 0.25; c->non_movement_penalty = 0.0;
     c->correct_direction_reward_scale = 3.0; c->use_correct_direction_reward = 0; c->ministep_size = 2.5;
     c->shortest_path_channel_scale = 0.25; c->force_box_spfa = 0;
+    c->env_kind = 0; c->step_limit = 10000; c->post_steps = 0; c->t_max = 0; c->n_boundary = 0; c->n_goals = 0;
+    c->lfc = 0.0; c->omega_mul = 3.0; c->v_mul = 2.0; c->bound_x = c->room_length; c->bound_y = c->room_width;
+    c->static_e = 0.01; c->static_u = 1.0; c->robot_code = 6; c->box_code = 4; c->box_done_code = 4; c->n_footprint = 0;
     const double chassis[8] = {0.26, -0.35, -0.31, -0.35, -0.31, 0.35, 0.26, 0.35};
     const double bumper[8] = {0.31, -0.53, 0.20, -0.39, 0.20, 0.39, 0.31, 0.53};
     const double wheels[32] = {0.09, 0.35, 0.09, 0.39, 0.24, 0.39, 0.24, 0.35,   0.09, -0.39, 0.09, -0.35, 0.24, -0.35, 0.24, -0.39,
@@ -70,7 +73,7 @@ int bp_boxdel_destroy(bp_boxdel_t* h) { delete h; return 0; }
 int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
                    int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
                    int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
-                   const uint8_t* small_free, const uint8_t* robot_chan) {
+                   const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map) {
     std::string err = bd_host_build(h->HB, h->cfg, n_layouts, starts, n_boxes, boxes, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype, H, W);
     if (!err.empty()) { fprintf(stderr, "emu_bd: %s\n", err.c_str()); return -1; }
     BdConst& K = h->HB.K;
@@ -81,26 +84,30 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
     h->recept.assign(nv, 0.0f);
     K.layouts = h->HB.LY.data(); K.pair_a = h->HB.pa.data(); K.pair_b = h->HB.pb.data();
     K.cspace = h->cspace.data(); K.cspace_thin = h->thin.data(); K.closest = h->closest.data(); K.small_free = h->small_free.data();
-    K.robot_chan = h->rchan.data(); K.recept_dist = h->recept.data();
+    K.robot_chan = h->rchan.data(); K.ch3_map = h->recept.data();
     h->envs.assign(K.env_bytes * h->cfg.n_envs, 0);
     K.envs = h->envs.data();
     h->scratch.assign(bd_scratch_ints(P), 0);
     for (int k = 0; k < P.n_static; k++) bd_init_static(K.S, k);
-    {
+    if (ch3_map) h->recept.assign(ch3_map, ch3_map + nv);
+    else {
         int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
         pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
         int si = closest[(size_t)pi * W + pj], sj = closest[nv + (size_t)pi * W + pj];
         std::vector<int32_t> par(nv);
         SpfaShared S;
         spfa_block(S, h->cspace.data(), H, W, si, sj, h->recept.data(), par.data(), h->scratch.data(), h->scratch.data() + nv, h->scratch.data() + 2 * nv);
+        bd_scale_receptacle_map(P, h->recept.data(), nv);
     }
+    K.ch3_map = h->recept.data();
     {
         int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
         pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
         K.P.recept_ci = closest[(size_t)pi * W + pj]; K.P.recept_cj = closest[nv + (size_t)pi * W + pj];
         int vis = 1;
-        for (size_t v = 0; v < nv && vis; v++) if (!bd_cell_visible(K, (int)v)) vis = 0;
+        if (h->cfg.env_kind == 0) for (size_t v = 0; v < nv && vis; v++) if (!bd_cell_visible(K, (int)v)) vis = 0;
         K.P.recept_visible = (vis && !h->cfg.force_box_spfa) ? 1 : 0;
+        if (h->cfg.env_kind == 1) K.P.recept_visible = 1;      // no receptacle distances in area-clearing
     }
     h->loaded = true;
     return 0;
@@ -167,6 +174,15 @@ int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double*
     }
     if (dists) for (int i = 0; i < h->cfg.num_boxes; i++) { dists[i] = E->init_dist[i]; dists[h->cfg.num_boxes + i] = E->final_dist[i]; }
     if (path) memcpy(path, E->path, sizeof(E->path));
+    return 0;
+}
+// host twin of bp_spfa_batch_host (same kernel source, one lane)
+int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t H, int32_t W, float* dists, int32_t* parents) {
+    size_t nv = (size_t)H * W;
+    std::vector<int> scratch(3 * nv);
+    SpfaShared S;
+    for (int m = 0; m < batch; m++)
+        spfa_block(S, maps + m * nv, H, W, sources[2 * m], sources[2 * m + 1], dists + m * nv, parents + m * nv, scratch.data(), scratch.data() + nv, scratch.data() + 2 * nv);
     return 0;
 }
 int64_t bp_boxdel_launch_count(bp_boxdel_t* h) { return h->HB.K.P.recept_visible; }   // emulation only: reports the visibility flag

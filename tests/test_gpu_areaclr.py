@@ -1,0 +1,67 @@
+"""area-clearing-v0 on the B200 through the C ABI (libbenchpush_b200.so, env_kind 1) against the CPU oracle."""
+import random
+
+import numpy as np
+import pytest
+
+from tests.areaclr_common import CLEARING_CFG, CLEARING_LAYOUT, compare_step
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reset_and_episode_match_the_oracle(portable_trig):
+    from benchpush_b200.envs import AreaClearingVecEnv
+    from oracle.area_clearing_oracle import AreaClearingOracleEnv, sample_layout
+    lays = [sample_layout(random.Random(s)) for s in range(1, 33)]
+    env = AreaClearingVecEnv(num_envs=32, layouts=lays, device=0)
+    picks = [0, 21]
+    oras = {e: AreaClearingOracleEnv(layouts=[lays[e]]) for e in picks}
+    obs, info = env.reset()
+    for e, ora in oras.items():
+        oobs, _ = ora.reset()
+        assert np.array_equal(env.goal_point_global_map, ora.goal_point_global_map)
+        assert np.array_equal(obs[e].cpu().numpy(), oobs), "reset observation differs from the oracle"
+        assert np.array_equal(env.get_bodies(e)[:, :6], ora.space.state()[:11])
+    rng = np.random.default_rng(1)
+    for k in range(8):
+        a = rng.uniform(-1, 1, size=32).astype(np.float32)
+        out = env.step(a)
+        for e, ora in oras.items():
+            compare_step(env, ora, e, float(a[e]), out, state_tol=1e-7)
+    env.close()
+
+
+def test_clearing_scenario_matches_the_oracle(portable_trig):
+    from benchpush_b200.envs import AreaClearingVecEnv
+    from oracle.area_clearing_oracle import AreaClearingOracleEnv
+    env = AreaClearingVecEnv(num_envs=1, cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT], device=0)
+    ora = AreaClearingOracleEnv(cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT])
+    env.reset(); ora.reset()
+    counts = []
+    for k in range(5):
+        out = env.step(np.array([-1.0], dtype=np.float32))
+        compare_step(env, ora, 0, -1.0, out, state_tol=1e-8)
+        counts.append(int(out[4]["box_count"][0]))
+    assert counts == [0, 0, 1, 1, 1]
+    env.close()
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json config 3: 16 384 envs, 10 boxes, heading actions."""
+    import torch
+    from benchpush_b200.envs import AreaClearingVecEnv
+    n = 16384
+    env = AreaClearingVecEnv(num_envs=n, device=0)
+    obs, info = env.reset()
+    assert obs.shape == (n, 224, 224, 4)
+    rng = np.random.default_rng(0)
+    for k in range(2):
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(rng.uniform(-1, 1, size=n).astype(np.float32)))
+    torch.cuda.synchronize()
+    assert int((info["status"] & ~16).max()) == 0
+    assert bool(torch.isfinite(rew).all()) and bool((info["total_work"] >= 0).all())
+    assert int(info["box_count"].max()) <= 10 and int(info["t"].max()) <= 2
+    o = obs[:256].cpu().numpy()
+    assert set(np.unique(o[..., 0])) <= {0, 31, 95, 127, 159, 223} and set(np.unique(o[..., 1])) <= {0, 255}
+    assert (o[:, 112, 112, 0] == 159).all()                       # the robot footprint is at the window centre
+    env.close()

@@ -1,0 +1,57 @@
+"""area-clearing-v0 kernel logic on a machine without a GPU: the kernel sources compiled for the host with one lane
+(tests/emu/emu_bd.cpp) against the oracle, through the Python mirror the product uses (AreaClearingVecEnv)."""
+import random
+
+import numpy as np
+
+from oracle.area_clearing_oracle import AreaClearingOracleEnv, sample_layout, convex_intersects
+from benchpush_b200.envs.area_clearing import AreaClearingVecEnv, DEFAULT_CFG, ENVS
+from benchpush_b200.layouts import sample_area_clearing_layout
+from benchpush_b200.utils import DotDict
+from tests.areaclr_common import CLEARING_CFG, CLEARING_LAYOUT, compare_step
+from tests.emu import emu_bd
+
+
+def test_layout_sampler_and_intersection_predicate():
+    a = sample_layout(random.Random(3))
+    b = sample_area_clearing_layout(random.Random(3), DotDict.to_dot_dict(DEFAULT_CFG), ENVS["clear_env"])
+    assert a["start"] == b["start"] and a["boxes"] == b["boxes"] and len(a["boxes"]) == 10
+    sq = [[-5.0, -5.0], [-5.0, 5.0], [5.0, 5.0], [5.0, -5.0]]
+    box = lambda cx, cy: [[cx + .5, cy + .5], [cx - .5, cy + .5], [cx - .5, cy - .5], [cx + .5, cy - .5]]
+    assert convex_intersects(sq, box(0, 0)) and convex_intersects(sq, box(5.2, 0)) and convex_intersects(sq, box(5.5, 5.5))   # touching counts
+    assert not convex_intersects(sq, box(5.51, 0)) and not convex_intersects(sq, box(-6, -6))
+
+
+def test_maps_reset_and_heading_episode_match_the_oracle(portable_trig):
+    lay = [sample_layout(random.Random(1))]
+    env = AreaClearingVecEnv(num_envs=1, layouts=lay, _backend=emu_bd.lib())
+    ora = AreaClearingOracleEnv(layouts=lay)
+    obs, info = env.reset()
+    oobs, oinfo = ora.reset()
+    r = env.room
+    assert r.shape == (468, 468)
+    assert np.array_equal(r.configuration_space, ora.configuration_space)
+    assert np.array_equal(r.closest_cspace_indices, ora.closest_cspace_indices)
+    assert np.array_equal(env.goal_point_global_map, ora.goal_point_global_map)
+    assert np.array_equal(np.array(env.goal_points), np.array(ora.goal_points)) and len(env.goal_points) == 40
+    assert np.array_equal(obs[0], oobs)
+    assert np.array_equal(env.get_bodies(0)[:, :6], ora.space.state()[:11])
+    rng = np.random.default_rng(1)
+    for k in range(12):
+        a = float(np.float32(rng.uniform(-1, 1)))
+        compare_step(env, ora, 0, a, env.step(np.array([a], dtype=np.float32)), state_tol=1e-9)
+    env.close()
+
+
+def test_clearing_a_box_resets_the_clock_and_marks_it_completed(portable_trig):
+    env = AreaClearingVecEnv(num_envs=1, cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT], _backend=emu_bd.lib())
+    ora = AreaClearingOracleEnv(cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT])
+    env.reset(); ora.reset()
+    counts, ts = [], []
+    for k in range(6):
+        out = env.step(np.array([-1.0], dtype=np.float32))
+        compare_step(env, ora, 0, -1.0, out, state_tol=1e-9)
+        counts.append(int(out[4]["box_count"][0])); ts.append(int(out[4]["t"][0]))
+    assert counts == [0, 0, 1, 1, 1, 1] and ts[2] == 0 and ts[3] == 1            # D13: the truncation clock restarts when a box is cleared
+    assert float(env._buf["reward"][0]) == -0.25                                  # pressed against the outer wall: BOUNDARY_PENALTY
+    env.close()
