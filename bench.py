@@ -42,8 +42,8 @@ def parse():
     ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total envs over all ranks (default: the metric's 65536)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--env", default="ship-ice", choices=["ship-ice", "box-delivery"],
-                    help="ship-ice (default, the BASELINE.json metric) or box-delivery (BASELINE config 2: 4096 envs, secondary line)")
+    ap.add_argument("--env", default="ship-ice", choices=["ship-ice", "box-delivery", "area-clearing"],
+                    help="ship-ice (default, the BASELINE.json metric); box-delivery (BASELINE config 2: 4096 envs) and area-clearing (config 3: 16384 envs) print secondary lines")
     ap.add_argument("--desync", type=int, default=34,
                     help="spread the episode phases before the warm-up: env e is advanced (global id mod DESYNC) steps (1 = all envs start at reset)")
     return ap.parse_args()
@@ -344,28 +344,33 @@ BD_CFG = {"agent": {"action_type": "heading"}}
 
 
 def _bd_cpu_worker(args):
-    idx, seed, budget, nsteps = args
-    from oracle.box_delivery_oracle import BoxDeliveryOracleEnv, sample_layout
-    env = BoxDeliveryOracleEnv(cfg=BD_CFG, layouts=[sample_layout(np.random.RandomState(42 + idx))])
+    idx, seed, budget, nsteps = args[:4]
+    if len(args) > 4 and args[4] == "area-clearing":
+        import random
+        from oracle.area_clearing_oracle import AreaClearingOracleEnv, sample_layout as ac_layout
+        env = AreaClearingOracleEnv(layouts=[ac_layout(random.Random(1 + idx))])
+    else:
+        from oracle.box_delivery_oracle import BoxDeliveryOracleEnv, sample_layout
+        env = BoxDeliveryOracleEnv(cfg=BD_CFG, layouts=[sample_layout(np.random.RandomState(42 + idx))])
     env.reset()
     rng = np.random.default_rng(seed)
     t0 = time.perf_counter()
     n = 0
     while True:
-        o, r, term, _, info = env.step(float(rng.uniform(-1, 1)))
+        o, r, term, trunc, info = env.step(float(rng.uniform(-1, 1)))
         n += 1
-        if term:
+        if term or trunc:
             env.reset()
         if (nsteps is not None and n >= nsteps) or (nsteps is None and time.perf_counter() - t0 > budget):
             break
     return n, time.perf_counter() - t0
 
 
-def _bd_cpu(budget_s, nsteps=None):
+def _bd_cpu(budget_s, nsteps=None, kind="box-delivery"):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     with mp.get_context("spawn").Pool(cores) as pool:
-        res = pool.map(_bd_cpu_worker, [(i, 1000 + i, budget_s, nsteps) for i in range(cores)])
+        res = pool.map(_bd_cpu_worker, [(i, 1000 + i, budget_s, nsteps, kind) for i in range(cores)])
     steps = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
     return steps / wall, cores, steps, wall
@@ -374,24 +379,28 @@ def _bd_cpu(budget_s, nsteps=None):
 def run_boxdel(a):
     """BASELINE config 2: box-delivery-v0, small_empty room, 10 boxes, heading actions, spfa distance-map observation.
     One step = one step() of every env: action decode, position-control chain, ~800 physics substeps, rewards, 224x224x4 obs."""
-    n_envs = a.envs if a.envs != TOTAL_ENVS else 4096
+    area = a.env == "area-clearing"
+    n_envs = a.envs if a.envs != TOTAL_ENVS else (16384 if area else 4096)
+    metric = ("env-steps/sec area-clearing-v0 @%d envs" % n_envs) if area else BD_METRIC
+    wl = ("area-clearing-v0 (BASELINE config 3): clear_env, 10 boxes of 1 m, heading actions U(-1,1)" if area
+          else "box-delivery-v0 (BASELINE config 2): small_empty room, 10 boxes, heading actions U(-1,1)")
     if a.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        _bd_cpu(0.0, max(a.warmup, 1))
-        v, cores, n, wall = _bd_cpu(0.0, a.steps)
-        print(json.dumps({"impl": "reference", "metric": BD_METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        _bd_cpu(0.0, max(a.warmup, 1), a.env)
+        v, cores, n, wall = _bd_cpu(0.0, a.steps, a.env)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                          "data": "synthetic", "config": {"workload": "box-delivery-v0 small_empty, 10 boxes, heading actions; one env per host core",
-                                                           "note": "restated reference (oracle/box_delivery_oracle.py on the C++ Chipmunk restatement); the reference env cannot run here"},
+                          "data": "synthetic", "config": {"workload": wl + "; one env per host core",
+                                                           "note": "restated reference (oracle/ on the C++ Chipmunk restatement); the reference env cannot run here"},
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d env steps per core on %d cores" % (a.steps, cores)},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
     import torch
-    from benchpush_b200.envs import BoxDeliveryVecEnv
+    from benchpush_b200.envs import AreaClearingVecEnv, BoxDeliveryVecEnv
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    env = BoxDeliveryVecEnv(num_envs=n_envs, cfg=BD_CFG, device=0)
+    env = AreaClearingVecEnv(num_envs=n_envs, device=0) if area else BoxDeliveryVecEnv(num_envs=n_envs, cfg=BD_CFG, device=0)
     env.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(1234)
     total = a.warmup + a.steps
@@ -426,16 +435,15 @@ def run_boxdel(a):
     achieved = alg * n_envs / (move_ms * 1e-3) / 1e9 if move_ms > 0 else 0.0
     cpu = None
     if not a.no_cpu_baseline:
-        v, cores, n, wall = _bd_cpu(a.cpu_seconds)
+        v, cores, n, wall = _bd_cpu(a.cpu_seconds, None, a.env)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle (restated reference): one env per core on %d cores, %d env steps in %.1f s" % (cores, n, wall)}
     print(json.dumps({
-        "metric": BD_METRIC, "value": n_envs * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "metric": metric, "value": n_envs * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "box-delivery-v0 (BASELINE config 2): small_empty room, 10 boxes, heading actions U(-1,1), %d envs, "
-                               "224x224x4 u8 obs with spfa distance channels" % n_envs,
+        "config": {"workload": wl + ", %d envs, 224x224x4 u8 obs with spfa distance channels" % n_envs,
                    "l2": "inputs_exceed_l2 (per-env state %.0f KB x %d envs + %.0f MB spfa scratch)" % (env._L.bp_boxdel_env_bytes(env._h) / 1e3, n_envs, 592 * 3.8),
-                   "env_status_bits": int(env._buf["info_i"][:, 3].max()), "boxes_delivered": int(env._buf["info_i"][:, 0].sum())},
+                   "env_status_bits": int(env._buf["info_i"][:, 3].max()), "boxes_delivered_or_cleared": int(env._buf["info_i"][:, 0].sum())},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "k_bd_move", "kernel_ms": move_ms, "obs_kernel_ms": km["obs_ms"] / max(km["steps"], 1),
                      "algorithmic_bytes_per_env_step": alg, "peak_source": peak_src,
@@ -448,7 +456,7 @@ def run_boxdel(a):
 
 def main():
     a = parse()
-    if a.env == "box-delivery":
+    if a.env in ("box-delivery", "area-clearing"):
         run_boxdel(a)
     elif a.impl == "reference":
         run_reference(a)

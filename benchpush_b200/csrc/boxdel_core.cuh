@@ -140,7 +140,6 @@ struct BdEnv {                    // mutable per env (header; the slot table fol
     unsigned char completed[MAXBOX];
     short order[MAXCAND];         // this step's solve list (slot ids), colour-sorted
     short cand[MAXCAND];
-    Closest cpts[MAXCAND];
     unsigned char ccnt[MAXCAND];
     Manifold cman[MAXCAND];
 };

@@ -119,7 +119,7 @@ class ClearingMaps:
 
 class AreaClearingVecEnv(BoxDeliveryVecEnv):
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
-                 seed: int = 1, _backend=None):
+                 seed: int = 1, env_offset: int = 0, _backend=None):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"] not in ENVS:
@@ -154,7 +154,8 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
             for i in range(10):
                 self.goal_points.append(tuple(p0 + ((((i + 1 / 2) / 10) * length) / length) * (p1 - p0)))
         if layouts is None:
-            layouts = [sample_area_clearing_layout(random.Random(seed + e), c, self.env_cfg) for e in range(E)]
+            # keyed by the GLOBAL env id (env_offset = first env of this rank's shard)
+            layouts = [sample_area_clearing_layout(random.Random(seed + int(env_offset) + e), c, self.env_cfg) for e in range(E)]
         self.layouts = [{"start": l["start"], "boxes": [[b[0], b[1], 0.0] for b in l["boxes"]]} for l in layouts]
         L = self._L
         k = BoxDelConfig()

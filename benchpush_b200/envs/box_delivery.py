@@ -199,7 +199,7 @@ class BoxDeliveryVecEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
-                 seed: Optional[int] = None, force_box_spfa: bool = False, _backend=None):
+                 seed: Optional[int] = None, force_box_spfa: bool = False, env_offset: int = 0, _backend=None):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"]["obstacle_config"] not in ("small_empty", "large_empty"):
@@ -231,7 +231,8 @@ class BoxDeliveryVecEnv:
         self.goal_points = [self.room.receptacle_position]
         if layouts is None:
             base = int(c["misc"]["random_seed"]) if seed is None else int(seed)
-            layouts = [sample_box_delivery_layout(np.random.RandomState(base + e), c) for e in range(E)]
+            # layouts are keyed by the GLOBAL env id (env_offset = first env of this rank's shard): results do not depend on the number of ranks
+            layouts = [sample_box_delivery_layout(np.random.RandomState(base + int(env_offset) + e), c) for e in range(E)]
         self.layouts = list(layouts)
         # ---- native handle
         L = self._L

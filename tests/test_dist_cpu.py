@@ -57,3 +57,46 @@ def test_metric_reduce_world2_gloo():
         np.testing.assert_allclose(red["efficiency_mean"], 0.5 * (8.0 / 8.0))
         np.testing.assert_allclose(red["effort_mean"], 8.0 / (8.0 + 2.0))
         np.testing.assert_allclose(red["reward_mean"], 3.0)
+
+
+def _worker_rooms(rank, world, port, q):
+    """box-delivery / area-clearing shards (CPU emulation backend): layouts keyed by the global env id, TaskDrivenMetric reduced over ranks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
+    from benchpush_b200.envs.area_clearing import AreaClearingVecEnv
+    from benchpush_b200.metrics import TaskDrivenMetric
+    from tests.emu import emu_bd
+    lo, hi = shard_range(4, rank, world)
+    env = BoxDeliveryVecEnv(num_envs=hi - lo, cfg={"agent": {"action_type": "heading"}}, env_offset=lo, _backend=emu_bd.lib())
+    ac = AreaClearingVecEnv(num_envs=hi - lo, env_offset=lo, _backend=emu_bd.lib())
+    m = TaskDrivenMetric("t", robot_mass=1)
+    obs, info = env.reset()
+    m.reset(info)
+    acts = np.linspace(-0.8, 0.8, 4).astype(np.float32)[lo:hi]
+    obs, rew, term, trunc, info = env.step(acts)
+    m.update(info, rew, eps_complete=True)
+    q.put((rank, [l["start"] for l in env.layouts], [l["start"] for l in ac.layouts], env.get_bodies(0)[0, :3].tolist(), m.reduce()))
+    env.close(); ac.close()
+    dist.destroy_process_group()
+
+
+def test_room_envs_shard_by_global_env_id_world2_gloo():
+    from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
+    from tests.emu import emu_bd
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_rooms, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=300) for _ in ps)
+    [p.join(timeout=60) for p in ps]
+    whole = BoxDeliveryVecEnv(num_envs=4, cfg={"agent": {"action_type": "heading"}}, _backend=emu_bd.lib())
+    assert res[0][1] + res[1][1] == [l["start"] for l in whole.layouts]          # same layouts as one rank with all envs
+    assert len(set(res[0][2] + res[1][2])) == 4
+    whole.reset()
+    whole.step(np.linspace(-0.8, 0.8, 4).astype(np.float32))
+    assert whole.get_bodies(2)[0, :3].tolist() == res[1][3]                        # env 2 = first env of rank 1: same trajectory
+    assert res[0][4]["episodes"] == 4 and res[0][4] == res[1][4]
+    whole.close()
