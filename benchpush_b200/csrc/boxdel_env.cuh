@@ -312,105 +312,129 @@ BP_DEVNI void bd_controller(const BdConst& C, BdEnv* E, BdLoop& LS, int wi, doub
     R.vx = vx * P.v_mul; R.vy = vy * P.v_mul;
 }
 
-BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS) {
+// All warps of a thread block call this together (participate == false: no env for this warp).  The three loops of the
+// reference (execute_robot_path, step_simulation_until_still / the fixed area-clearing substeps) are one state machine with a
+// block-wide barrier per substep: the warps of a block then walk through the ~75 KB of substep code roughly together, so
+// one instruction-cache line serves several environments (the kernel is bound by instruction fetch).
+#if defined(__CUDACC__) && !defined(BP_HOST_EMU)
+#define BP_BLOCK_ANY(p) __syncthreads_or(p)
+#else
+#define BP_BLOCK_ANY(p) (p)
+#endif
+BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS, bool participate) {
     const int lane = bp_lane();
     const BdParams& P = C.P;
-    const BdLayout& L = C.layouts[E->layout];
-    const int n = E->n_path;
-    double (*wp)[3] = E->path;
-    // execute_robot_path (scalar state lives in registers of every lane; only lane 0's copy is used for stores)
-    double pos_x = E->init_pos[0], pos_y = E->init_pos[1], heading = E->init_heading;
-    double robot_distance = 0.0;
-    int wi = 1, sim_steps = 0;
-    bool done_turning = false;
-    double prev_heading_diff = 0.0;
-    if (lane == 0) LS.dp_none = 1;
-    bp_wsync();
-    #pragma unroll 1
-    for (;;) {
-        double hd = heading_diff(heading, wp[wi][2]);
-        if (!(fabs(hd) > TURN_STEP_SIZE && fabs(hd - prev_heading_diff) > 0.001)) done_turning = true;
-        if (lane == 0) bd_controller(C, E, LS, wi, pos_x, pos_y, heading, done_turning);
-        bp_wsync();
-        bd_substep(C, E);
-        pos_x = E->body[0].px; pos_y = E->body[0].py; heading = restrict_heading(E->body[0].pa);
-        prev_heading_diff = hd;
-        if (dist2(wp[wi - 1][0], wp[wi - 1][1], pos_x, pos_y) > MOVE_STEP_SIZE && E->robot_hit) break;
-        if (dist2(pos_x, pos_y, wp[wi][0], wp[wi][1]) < WAYPOINT_MOVING_THRESHOLD && fabs(heading - wp[wi][2]) < WAYPOINT_TURNING_THRESHOLD) {
-            robot_distance += dist2(wp[wi - 1][0], wp[wi - 1][1], pos_x, pos_y);
-            if (wi == n - 1) break;
-            wi++;
-            done_turning = false;
-            if (lane == 0) LS.dp_none = 1;
-            bp_wsync();
-        }
-        sim_steps++;
-        if (sim_steps > P.step_limit) { if (lane == 0) E->status |= BD_STEP_LIMIT; break; }
-    }
-    if (lane == 0) E->robot_distance = robot_distance;
-    bp_wsync();
-    if (P.kind == 1) {
-        // area-clearing: a fixed number of substeps follows the path (area_clearing.py:692-693); no until-still loop
-#pragma unroll 1
-        for (int k = 0; k < P.post_steps; k++) bd_substep(C, E);
-        return;
-    }
-    // step_simulation_until_still
-    double prev_x = 0, prev_y = 0;       // lane b < NB: box b; lane NB: robot  (NB + 1 <= 32 lanes; the single-lane emulation loops)
-    bool have_prev = false;
-    sim_steps = 0;
+    enum { MV_EXEC = 0, MV_STILL = 1, MV_POST = 2, MV_DONE = 3 };
+    int state = participate ? MV_EXEC : MV_DONE;
+    const BdLayout* Lp = participate ? &C.layouts[E->layout] : nullptr;
+    const int n = participate ? E->n_path : 0;
+    double (*wp)[3] = participate ? E->path : nullptr;
+    // execute_robot_path state (registers of every lane; only lane 0's copy is used for stores)
+    double pos_x = 0, pos_y = 0, heading = 0, robot_distance = 0.0, prev_heading_diff = 0.0, hd = 0.0;
+    int wi = 1, sim_steps = 0, post_k = 0;
+    bool done_turning = false, have_prev = false, still_done = false;
+    double prev_x = 0, prev_y = 0;       // until-still: lane b < NB: box b; lane NB: robot (NB + 1 <= 32 lanes; the single-lane emulation loops)
 #if defined(BP_HOST_EMU) || !defined(__CUDACC__)
     double pvx[1 + MAXBOX], pvy[1 + MAXBOX];
 #endif
-    #pragma unroll 1
-    for (;;) {
-        // un-stick boxes from the walls
-        #pragma unroll 1
-        for (int i = lane; i < P.NB; i += BP_NL) {
-            BdBody& B = E->body[1 + i];
-            if (!B.alive) continue;
-            bool stuck = false;
-            #pragma unroll 1
-            for (int v = 0; v < SV && !stuck; v++) {
-                V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
-                if (bd_point_query_static(C, w) & (1 << 3)) stuck = true;
-            }
-            if (stuck) {
-                V2 o = bd_origin(B);
-                int pi, pj, ni, nj; pos_to_pixel(P, o.x, o.y, &pi, &pj);
-                closest_valid(C, pi, pj, &ni, &nj);
-                double nx, ny; pixel_to_pos(P, ni, nj, &nx, &ny);
-                bd_set_origin(B, mk(nx, ny));
-                B.vx = 0.0; B.vy = 0.0;
-            }
-        }
+    if (participate) {
+        pos_x = E->init_pos[0]; pos_y = E->init_pos[1]; heading = E->init_heading;
+        if (lane == 0) LS.dp_none = 1;
         bp_wsync();
-        bool moved = false;
-#if defined(BP_HOST_EMU) || !defined(__CUDACC__)
-        #pragma unroll 1
-        for (int b = 0; b <= P.NB; b++) {
-            const BdBody& B = E->body[b == P.NB ? 0 : 1 + b];
-            if (b < P.NB && !B.alive) continue;
-            V2 o = bd_origin(B);
-            if (have_prev && dist2(pvx[b], pvy[b], o.x, o.y) > NOT_MOVING_THRESHOLD) moved = true;
-            pvx[b] = o.x; pvy[b] = o.y;
-        }
-#else
-        if (lane <= P.NB) {
-            const BdBody& B = E->body[lane == P.NB ? 0 : 1 + lane];
-            if (lane == P.NB || B.alive) {
-                V2 o = bd_origin(B);
-                if (have_prev && dist2(prev_x, prev_y, o.x, o.y) > NOT_MOVING_THRESHOLD) moved = true;
-                prev_x = o.x; prev_y = o.y;
+    }
+#pragma unroll 1
+    for (;;) {
+        if (!BP_BLOCK_ANY(state != MV_DONE)) break;
+        if (state == MV_DONE) continue;
+        // ---- before the substep
+        if (state == MV_EXEC) {
+            hd = heading_diff(heading, wp[wi][2]);
+            if (!(fabs(hd) > TURN_STEP_SIZE && fabs(hd - prev_heading_diff) > 0.001)) done_turning = true;
+            if (lane == 0) bd_controller(C, E, LS, wi, pos_x, pos_y, heading, done_turning);
+            bp_wsync();
+        } else if (state == MV_STILL) {
+            const BdLayout& L = *Lp;
+            // un-stick boxes from the walls
+#pragma unroll 1
+            for (int i = lane; i < P.NB; i += BP_NL) {
+                BdBody& B = E->body[1 + i];
+                if (!B.alive) continue;
+                bool stuck = false;
+#pragma unroll 1
+                for (int v = 0; v < SV && !stuck; v++) {
+                    V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
+                    if (bd_point_query_static(C, w) & (1 << 3)) stuck = true;
+                }
+                if (stuck) {
+                    V2 o = bd_origin(B);
+                    int pi, pj, ni, nj; pos_to_pixel(P, o.x, o.y, &pi, &pj);
+                    closest_valid(C, pi, pj, &ni, &nj);
+                    double nx, ny; pixel_to_pos(P, ni, nj, &nx, &ny);
+                    bd_set_origin(B, mk(nx, ny));
+                    B.vx = 0.0; B.vy = 0.0;
+                }
             }
-        }
+            bp_wsync();
+            bool moved = false;
+#if defined(BP_HOST_EMU) || !defined(__CUDACC__)
+            for (int b = 0; b <= P.NB; b++) {
+                const BdBody& B = E->body[b == P.NB ? 0 : 1 + b];
+                if (b < P.NB && !B.alive) continue;
+                V2 o = bd_origin(B);
+                if (have_prev && dist2(pvx[b], pvy[b], o.x, o.y) > NOT_MOVING_THRESHOLD) moved = true;
+                pvx[b] = o.x; pvy[b] = o.y;
+            }
+#else
+            if (lane <= P.NB) {
+                const BdBody& B = E->body[lane == P.NB ? 0 : 1 + lane];
+                if (lane == P.NB || B.alive) {
+                    V2 o = bd_origin(B);
+                    if (have_prev && dist2(prev_x, prev_y, o.x, o.y) > NOT_MOVING_THRESHOLD) moved = true;
+                    prev_x = o.x; prev_y = o.y;
+                }
+            }
 #endif
-        bool done = have_prev && !bp_wany(moved);
-        have_prev = true;
-        bd_substep(C, E);                 // the reference steps once more after deciding that everything is still (:1007-1019)
-        if (done) break;
-        sim_steps++;
-        if (sim_steps > STEP_LIMIT) { if (lane == 0) E->status |= BD_STEP_LIMIT; break; }
+            still_done = have_prev && !bp_wany(moved);
+            have_prev = true;
+        }
+        // ---- the substep (the reference steps once more after deciding that everything is still, :1007-1019)
+        bd_substep(C, E);
+        // ---- after the substep
+        if (state == MV_EXEC) {
+            pos_x = E->body[0].px; pos_y = E->body[0].py; heading = restrict_heading(E->body[0].pa);
+            prev_heading_diff = hd;
+            bool stop = false;
+            if (dist2(wp[wi - 1][0], wp[wi - 1][1], pos_x, pos_y) > MOVE_STEP_SIZE && E->robot_hit) stop = true;
+            if (!stop && dist2(pos_x, pos_y, wp[wi][0], wp[wi][1]) < WAYPOINT_MOVING_THRESHOLD && fabs(heading - wp[wi][2]) < WAYPOINT_TURNING_THRESHOLD) {
+                robot_distance += dist2(wp[wi - 1][0], wp[wi - 1][1], pos_x, pos_y);
+                if (wi == n - 1) stop = true;
+                else {
+                    wi++;
+                    done_turning = false;
+                    if (lane == 0) LS.dp_none = 1;
+                    bp_wsync();
+                }
+            }
+            if (!stop) {
+                sim_steps++;
+                if (sim_steps > P.step_limit) { if (lane == 0) E->status |= BD_STEP_LIMIT; stop = true; }
+            }
+            if (stop) {
+                if (lane == 0) E->robot_distance = robot_distance;
+                bp_wsync();
+                sim_steps = 0;
+                // area-clearing: a fixed number of substeps follows the path (area_clearing.py:692-693); box-delivery: until still
+                state = (P.kind == 1) ? (P.post_steps > 0 ? MV_POST : MV_DONE) : MV_STILL;
+            }
+        } else if (state == MV_STILL) {
+            if (still_done) state = MV_DONE;
+            else {
+                sim_steps++;
+                if (sim_steps > STEP_LIMIT) { if (lane == 0) E->status |= BD_STEP_LIMIT; state = MV_DONE; }
+            }
+        } else {
+            if (++post_k >= P.post_steps) state = MV_DONE;
+        }
     }
     (void)prev_x; (void)prev_y;
     bp_wsync();

@@ -144,7 +144,7 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
         bd_begin_step(K, E, (double)actions[e]);
         for (int k = 0; k <= K.P.NB; k++) bd_dist_item(S, K, E, k, 0, h->scratch.data());
         bd_finalize_path(K, E);
-        bd_move(K, E, LS);
+        bd_move(K, E, LS, true);
         for (int k = 0; k < K.P.NB; k++) bd_dist_item(S, K, E, k, 1, h->scratch.data());
         bd_finish_step(K, E, e, o);
     }
