@@ -115,3 +115,84 @@ class MazeNamoEnvB200:
 
     def close(self):
         self._v.close()
+
+
+def _np(x):
+    return x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+
+
+class BoxDeliveryEnvB200:
+    """Single-environment view of :class:`BoxDeliveryVecEnv` with the reference's return types (``BoxDeliveryEnv``,
+    box_delivery_env.py:571-632, 634-830): obs ``np.uint8[224,224,4]``, python scalars / lists in ``info``
+    (``state``, ``cumulative_distance``, ``cumulative_boxes``, ``cumulative_reward``, ``total_work``, ``obs`` = list of
+    (4, 2) vertex arrays of the boxes left, ``box_completed_statuses``, ``goal_positions``, ``ministeps``, ``inactivity``).
+    ``TaskDrivenMetric`` of the reference reads ``goal.x / goal.y`` of ``goal_positions``; a small point type provides them."""
+    metadata = {"render_modes": []}
+
+    class _Point(tuple):
+        x = property(lambda self: self[0])
+        y = property(lambda self: self[1])
+
+    def __init__(self, cfg=None, **kw):
+        from .box_delivery import BoxDeliveryVecEnv
+        self._v = BoxDeliveryVecEnv(num_envs=1, cfg=cfg, **kw)
+        self.cfg = self._v.cfg
+        self.num_channels = self._v.num_channels
+        self.local_map_pixel_width = self._v.local_map_pixel_width
+        self.episode_idx = None
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def _info(self, info):
+        n = int(_np(info["n_boxes_left"])[0])
+        st = _np(info["state"])[0]
+        return {"state": (float(st[0]), float(st[1]), float(st[2])),
+                "cumulative_distance": float(_np(info["cumulative_distance"])[0]), "cumulative_boxes": int(_np(info["cumulative_boxes"])[0]),
+                "cumulative_reward": float(_np(info["cumulative_reward"])[0]), "total_work": float(_np(info["total_work"])[0]),
+                "obs": [v.copy() for v in _np(info["obs"])[0][:n]],
+                "box_completed_statuses": [bool(b) for b in _np(info["box_completed_statuses"])[0]],
+                "goal_positions": [self._Point(g) for g in info["goal_positions"]],
+                "ministeps": float(_np(info["ministeps"])[0]), "inactivity": int(_np(info["inactivity"])[0])}
+
+    def reset(self, seed=None, options=None):
+        self.episode_idx = 0 if self.episode_idx is None else self.episode_idx + 1
+        obs, info = self._v.reset()
+        return _np(obs)[0].copy(), self._info(info)
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float32).reshape(1)
+        obs, r, term, trunc, info = self._v.step(a)
+        return _np(obs)[0].copy(), float(_np(r)[0]), bool(_np(term)[0]), bool(_np(trunc)[0]), self._info(info)
+
+    def render(self):
+        raise NotImplementedError("rendering is out of scope for the batched simulator")
+
+    def close(self):
+        self._v.close()
+
+
+class AreaClearingEnvB200(BoxDeliveryEnvB200):
+    """Single-environment view of :class:`AreaClearingVecEnv` (``AreaClearingEnv``, area_clearing.py:563-778): info keys
+    ``state``, ``total_work``, ``collision reward``, ``diff_reward``, ``box_completed_reward``, ``obs``,
+    ``box_completed_statuses``, ``box_count``, ``ministeps`` (+ ``goal_positions`` / ``boundary`` as at reset)."""
+
+    def __init__(self, cfg=None, **kw):
+        from .area_clearing import AreaClearingVecEnv
+        self._v = AreaClearingVecEnv(num_envs=1, cfg=cfg, **kw)
+        self.cfg = self._v.cfg
+        self.num_channels = self._v.num_channels
+        self.local_map_pixel_width = self._v.local_map_pixel_width
+        self.episode_idx = None
+
+    def _info(self, info):
+        n = int(_np(info["n_boxes_left"])[0])
+        st = _np(info["state"])[0]
+        return {"state": (float(st[0]), float(st[1]), float(st[2])), "total_work": float(_np(info["total_work"])[0]),
+                "collision reward": float(_np(info["collision reward"])[0]), "diff_reward": float(_np(info["diff_reward"])[0]),
+                "box_completed_reward": float(_np(info["box_completed_reward"])[0]),
+                "obs": [v.copy() for v in _np(info["obs"])[0][:n]],
+                "box_completed_statuses": [bool(b) for b in _np(info["box_completed_statuses"])[0][:n]],
+                "box_count": int(_np(info["box_count"])[0]), "ministeps": float(_np(info["ministeps"])[0]),
+                "goal_positions": [self._Point(g) for g in info["goal_positions"]], "boundary": info["boundary"]}

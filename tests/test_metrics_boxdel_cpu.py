@@ -54,3 +54,33 @@ def test_task_driven_metric_on_a_delivery_episode():
     r = m.reduce()
     assert r["episodes"] == 1 and r["success_rate"] == 0.25
     env.close()
+
+
+def test_single_env_views_return_the_reference_types():
+    from benchpush_b200.envs.gym_single import AreaClearingEnvB200, BoxDeliveryEnvB200
+    from tests.areaclr_common import CLEARING_CFG, CLEARING_LAYOUT
+    env = BoxDeliveryEnvB200(cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT], _backend=emu_bd.lib())
+    obs, info = env.reset()
+    assert obs.shape == (224, 224, 4) and obs.dtype == np.uint8 and isinstance(info["state"], tuple) and len(info["obs"]) == 4
+    assert set(info) == {"state", "cumulative_distance", "cumulative_boxes", "cumulative_reward", "total_work", "obs",
+                         "box_completed_statuses", "goal_positions", "ministeps", "inactivity"}
+    for _ in range(2):
+        obs, r, term, trunc, info = env.step(-1.0)
+    assert isinstance(r, float) and isinstance(term, bool) and info["cumulative_boxes"] == 1 and len(info["obs"]) == 3
+    assert info["goal_positions"][0].x == 4.25 and info["goal_positions"][0].y == 1.75
+    env.close()
+    ac = AreaClearingEnvB200(cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT], _backend=emu_bd.lib())
+    obs, info = ac.reset()
+    for _ in range(3):
+        obs, r, term, trunc, info = ac.step(-1.0)
+    assert info["box_count"] == 1 and info["box_completed_statuses"] == [True, False, False] and r > 9
+    assert set(info) >= {"state", "total_work", "collision reward", "diff_reward", "box_completed_reward", "obs", "box_completed_statuses", "box_count", "ministeps"}
+    # the batched TaskDrivenMetric also consumes the area-clearing info (40 goal points on the clearance boundary)
+    m = TaskDrivenMetric("t", robot_mass=1)
+    v = ac._v
+    o, i0 = v.reset(); m.reset(i0)
+    for k in range(3):
+        o, rr, te, tr, i1 = v.step(np.array([-1.0], dtype=np.float32))
+        m.update(i1, rr, eps_complete=(k == 2))
+    assert m.success_rates == [1 / 3] and 0 < m.efficiency_scores[0] and 0 < m.effort_scores[0] <= 1.0 + 1e-9
+    ac.close()
