@@ -70,18 +70,18 @@ __global__ void __launch_bounds__(256) k_bd_dist(const BdConst* C, const uint8_t
     }
 }
 
-// warp per env: waypoint headings, then the substep state machine (block-synchronous: every warp of the block takes part)
+// one warp per BD_MOVE_K envs: waypoint headings, then the phase-major substep state machine (block-synchronous: every warp
+// of the block takes part)
 #ifndef BD_MOVE_BLOCK
 #define BD_MOVE_BLOCK 128
 #endif
 __global__ void __launch_bounds__(BD_MOVE_BLOCK, BD_MOVE_MINB * 128 / BD_MOVE_BLOCK) k_bd_move(const BdConst* C, const uint8_t* mask) {
-    __shared__ BdLoop LS[BD_MOVE_BLOCK / 32];
-    int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    bool participate = env < C->n_envs && !(mask && !mask[env]);
-    BdEnv* E = participate ? bd_env(*C, env) : nullptr;
-    if (participate && (threadIdx.x & 31) == 0) bd_finalize_path(*C, E);
-    __syncwarp();
-    bd_move(*C, E, LS[threadIdx.x >> 5], participate);
+    __shared__ MoveVars V[BD_MOVE_BLOCK / 32][BD_MOVE_K];
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int env0 = warp * BD_MOVE_K;
+    int nk = C->n_envs - env0;
+    nk = nk < 0 ? 0 : (nk > BD_MOVE_K ? BD_MOVE_K : nk);
+    bd_move(*C, env0, nk, mask, V[threadIdx.x >> 5]);
 }
 
 // thread per env
@@ -308,7 +308,10 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
     k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 0, h->d_scratch, h->d_counter);
     cudaEvent_t e4[4] = {nullptr, nullptr, nullptr, nullptr};
     if (h->profiling) { for (auto& e : e4) { CUDA_TRY(cudaEventCreate(&e)); h->ev.push_back(e); } CUDA_TRY(cudaEventRecord(e4[0], st)); }
-    k_bd_move<<<(E * 32 + BD_MOVE_BLOCK - 1) / BD_MOVE_BLOCK, BD_MOVE_BLOCK, 0, st>>>(h->dC, mask);
+    {
+        int warps = (E + BD_MOVE_K - 1) / BD_MOVE_K;
+        k_bd_move<<<(warps * 32 + BD_MOVE_BLOCK - 1) / BD_MOVE_BLOCK, BD_MOVE_BLOCK, 0, st>>>(h->dC, mask);
+    }
     if (h->profiling) CUDA_TRY(cudaEventRecord(e4[1], st));
     if (!h->hC.P.recept_visible) {
         CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));

@@ -126,6 +126,7 @@ struct BdShapes {                 // immutable per handle: robot shapes (body-lo
 struct BdEnv {                    // mutable per env (header; the slot table follows it in the env block)
     int layout, episode, t, status, stamp, n_order, robot_hit, inactivity, cum_boxes, done, truncated, n_prev;
     int cleared_count, pad_c;
+    int nc, fast;                 // this substep: candidate pairs; 1 = nothing overlaps and nothing is cached (phases B-D skipped)
     int n_path, move_sign, need_spfa, src_i, src_j, tgt_i, tgt_j, n_live;      // n_live: slots with state != SL_NONE
     long long stat_substeps, stat_cand, stat_arb;
     double prev_dt, cum_distance, cum_reward, total_work, last_work, reward, ministeps;
@@ -412,7 +413,10 @@ BP_DEVNI void bd_solve(const BdConst& C, BdEnv* E, int p, bool warm, double dt_c
 }
 
 // ------------------------------------------------------------------ one substep (cpSpaceStep) for one env, one warp
-BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
+// A substep is split into four phases so that a warp that steps several environments can run each phase for all of them
+// before moving on (boxdel_env.cuh: bd_move): the code of one phase is then fetched once and executed K times.
+// Phase A: integrate, re-cache moved shapes, broadphase; sets E->nc and E->fast.
+BP_DEVNI void bd_phase_a(const BdConst& C, BdEnv* E) {
     const int lane = bp_lane();
     const BdParams& P = C.P;
     const int NB = P.NB;
@@ -478,8 +482,10 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         nc += tot;
     }
     if (nc > MAXCAND) { nc = MAXCAND; if (lane == 0) E->status |= BD_CAND_OVERFLOW; }
+    const bool fast = (nc == 0 && E->n_live == 0);
+    if (lane == 0) { E->nc = nc; E->fast = fast ? 1 : 0; }
     bp_wsync();
-    if (nc == 0 && E->n_live == 0) {
+    if (fast) {
         // nothing overlaps and no arbiter is cached: the rest of cpSpaceStep only applies the velocity update
         #pragma unroll 1
         for (int b = 1 + lane; b <= NB; b += BP_NL) {
@@ -491,8 +497,15 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         }
         if (lane == 0) { E->n_order = 0; E->prev_dt = dt; }
         bp_wsync();
-        return;
     }
+    (void)stamp;
+}
+
+// Phase B: narrowphase.
+BP_DEVNI void bd_phase_b(const BdConst& C, BdEnv* E) {
+    const int lane = bp_lane();
+    BdSlot* slots = bd_slots(E);
+    const int nc = E->nc;
     // 3. narrowphase, lanes over candidates (pure geometry on the cached world vertices); a pair of two unmoved shapes
     //    reuses the result of the substep in which it was last evaluated
     #pragma unroll 1
@@ -525,6 +538,15 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         E->cman[q] = m; E->ccnt[q] = (unsigned char)m.count;
     }
     bp_wsync();
+}
+
+// Phase C: arbiter updates + handlers, cache expiry, solve order.
+BP_DEVNI void bd_phase_c(const BdConst& C, BdEnv* E) {
+    const int lane = bp_lane();
+    const BdParams& P = C.P;
+    const int NB = P.NB;
+    BdSlot* slots = bd_slots(E);
+    const int nc = E->nc, stamp = E->stamp;
     // 4. arbiter updates + handlers, in an order equivalent to the sequential canonical sweep:
     //    (chassis, box) -> (chassis, wall)* sequential, edits the robot -> everything else except (box, wall)
     //    -> (box i, wall)* sequential per box, boxes in parallel.
@@ -615,6 +637,14 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
         E->stat_cand += nc; E->stat_arb += n;
     }
     bp_wsync();
+}
+
+// Phase D: pre-step, velocity update, warm start, solver iterations.
+BP_DEVNI void bd_phase_d(const BdConst& C, BdEnv* E) {
+    const int lane = bp_lane();
+    const BdParams& P = C.P;
+    const int NB = P.NB;
+    const double dt = P.dt;
     const int n_order = E->n_order;
     // 7. pre-step, velocity update (dynamic bodies only), warm start, iterations
     #pragma unroll 1
@@ -646,6 +676,15 @@ BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
     }
     if (lane == 0) E->prev_dt = dt;
     bp_wsync();
+}
+
+// ------------------------------------------------------------------ one substep (cpSpaceStep) for one env, one warp
+BP_DEVNI void bd_substep(const BdConst& C, BdEnv* E) {
+    bd_phase_a(C, E);
+    if (E->fast) return;
+    bd_phase_b(C, E);
+    bd_phase_c(C, E);
+    bd_phase_d(C, E);
 }
 
 // space.remove(box.body, box): the body leaves the world, its arbiters are dropped

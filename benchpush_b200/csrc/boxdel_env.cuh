@@ -312,131 +312,161 @@ BP_DEVNI void bd_controller(const BdConst& C, BdEnv* E, BdLoop& LS, int wi, doub
     R.vx = vx * P.v_mul; R.vy = vy * P.v_mul;
 }
 
-// All warps of a thread block call this together (participate == false: no env for this warp).  The three loops of the
-// reference (execute_robot_path, step_simulation_until_still / the fixed area-clearing substeps) are one state machine with a
-// block-wide barrier per substep: the warps of a block then walk through the ~75 KB of substep code roughly together, so
-// one instruction-cache line serves several environments (the kernel is bound by instruction fetch).
+// A warp advances BD_MOVE_K environments, phase-major: every phase of the loop body (controller, the four substep phases,
+// the exit tests) runs for all of the warp's live envs before the next phase starts.  The three loops of the reference
+// (execute_robot_path, step_simulation_until_still / the fixed area-clearing substeps) are one state machine per env; the
+// warps of a block meet at one barrier per iteration.  Loop state lives in shared memory (MoveVars), written by lane 0.
+// Measured on B200 (profiles/r01e_room_kernels_envs_per_warp_sweep.txt, 16 384 area-clearing envs): K = 1 / 2 / 4 / 8 ->
+// 28.4 k / 24.8 k / 22.5 k / 21.1 k env-steps/s.  The kernel is bound by instruction supply (~0.7 IPC per SM whatever the
+// occupancy), but re-running a phase K times inside a warp does not help: the other 15 resident warps are in
+// other phases and the ~110 KB of kernel code still does not stay in the instruction cache, while K > 1 leaves fewer warps
+// to overlap.  Default K = 1; the knob stays for the phase-per-kernel design of DESIGN.md §8.
 #if defined(__CUDACC__) && !defined(BP_HOST_EMU)
 #define BP_BLOCK_ANY(p) __syncthreads_or(p)
 #else
 #define BP_BLOCK_ANY(p) (p)
 #endif
-BP_DEVNI void bd_move(const BdConst& C, BdEnv* E, BdLoop& LS, bool participate) {
+#ifndef BD_MOVE_K
+#define BD_MOVE_K 1
+#endif
+enum { MV_EXEC = 0, MV_STILL = 1, MV_POST = 2, MV_DONE = 3 };
+struct MoveVars {
+    int state, wi, sim_steps, post_k, n, done_turning, have_prev, still_done;
+    double pos_x, pos_y, heading, robot_distance, prev_heading_diff, hd;
+    double pvx[1 + MAXBOX], pvy[1 + MAXBOX];     // until-still: positions at the previous iteration ([NB] = robot)
+    BdLoop LS;
+};
+
+BP_DEVNI void mv_pre(const BdConst& C, BdEnv* E, MoveVars& V) {
     const int lane = bp_lane();
     const BdParams& P = C.P;
-    enum { MV_EXEC = 0, MV_STILL = 1, MV_POST = 2, MV_DONE = 3 };
-    int state = participate ? MV_EXEC : MV_DONE;
-    const BdLayout* Lp = participate ? &C.layouts[E->layout] : nullptr;
-    const int n = participate ? E->n_path : 0;
-    double (*wp)[3] = participate ? E->path : nullptr;
-    // execute_robot_path state (registers of every lane; only lane 0's copy is used for stores)
-    double pos_x = 0, pos_y = 0, heading = 0, robot_distance = 0.0, prev_heading_diff = 0.0, hd = 0.0;
-    int wi = 1, sim_steps = 0, post_k = 0;
-    bool done_turning = false, have_prev = false, still_done = false;
-    double prev_x = 0, prev_y = 0;       // until-still: lane b < NB: box b; lane NB: robot (NB + 1 <= 32 lanes; the single-lane emulation loops)
-#if defined(BP_HOST_EMU) || !defined(__CUDACC__)
-    double pvx[1 + MAXBOX], pvy[1 + MAXBOX];
-#endif
-    if (participate) {
-        pos_x = E->init_pos[0]; pos_y = E->init_pos[1]; heading = E->init_heading;
-        if (lane == 0) LS.dp_none = 1;
+    if (V.state == MV_EXEC) {
+        if (lane == 0) {
+            double (*wp)[3] = E->path;
+            double hd = heading_diff(V.heading, wp[V.wi][2]);
+            V.hd = hd;
+            if (!(fabs(hd) > TURN_STEP_SIZE && fabs(hd - V.prev_heading_diff) > 0.001)) V.done_turning = 1;
+            bd_controller(C, E, V.LS, V.wi, V.pos_x, V.pos_y, V.heading, V.done_turning != 0);
+        }
+        bp_wsync();
+    } else if (V.state == MV_STILL) {
+        const BdLayout& L = C.layouts[E->layout];
+        // un-stick boxes from the walls
+#pragma unroll 1
+        for (int i = lane; i < P.NB; i += BP_NL) {
+            BdBody& B = E->body[1 + i];
+            if (!B.alive) continue;
+            bool stuck = false;
+#pragma unroll 1
+            for (int v = 0; v < SV && !stuck; v++) {
+                V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
+                if (bd_point_query_static(C, w) & (1 << 3)) stuck = true;
+            }
+            if (stuck) {
+                V2 o = bd_origin(B);
+                int pi, pj, ni, nj; pos_to_pixel(P, o.x, o.y, &pi, &pj);
+                closest_valid(C, pi, pj, &ni, &nj);
+                double nx, ny; pixel_to_pos(P, ni, nj, &nx, &ny);
+                bd_set_origin(B, mk(nx, ny));
+                B.vx = 0.0; B.vy = 0.0;
+            }
+        }
+        bp_wsync();
+        bool moved = false;
+        const bool have_prev = V.have_prev != 0;
+#pragma unroll 1
+        for (int b = lane; b <= P.NB; b += BP_NL) {
+            const BdBody& B = E->body[b == P.NB ? 0 : 1 + b];
+            if (b < P.NB && !B.alive) continue;
+            V2 o = bd_origin(B);
+            if (have_prev && dist2(V.pvx[b], V.pvy[b], o.x, o.y) > NOT_MOVING_THRESHOLD) moved = true;
+            V.pvx[b] = o.x; V.pvy[b] = o.y;
+        }
+        bool any = bp_wany(moved);
+        if (lane == 0) { V.still_done = (have_prev && !any) ? 1 : 0; V.have_prev = 1; }
         bp_wsync();
     }
-#pragma unroll 1
-    for (;;) {
-        if (!BP_BLOCK_ANY(state != MV_DONE)) break;
-        if (state == MV_DONE) continue;
-        // ---- before the substep
-        if (state == MV_EXEC) {
-            hd = heading_diff(heading, wp[wi][2]);
-            if (!(fabs(hd) > TURN_STEP_SIZE && fabs(hd - prev_heading_diff) > 0.001)) done_turning = true;
-            if (lane == 0) bd_controller(C, E, LS, wi, pos_x, pos_y, heading, done_turning);
-            bp_wsync();
-        } else if (state == MV_STILL) {
-            const BdLayout& L = *Lp;
-            // un-stick boxes from the walls
-#pragma unroll 1
-            for (int i = lane; i < P.NB; i += BP_NL) {
-                BdBody& B = E->body[1 + i];
-                if (!B.alive) continue;
-                bool stuck = false;
-#pragma unroll 1
-                for (int v = 0; v < SV && !stuck; v++) {
-                    V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
-                    if (bd_point_query_static(C, w) & (1 << 3)) stuck = true;
-                }
-                if (stuck) {
-                    V2 o = bd_origin(B);
-                    int pi, pj, ni, nj; pos_to_pixel(P, o.x, o.y, &pi, &pj);
-                    closest_valid(C, pi, pj, &ni, &nj);
-                    double nx, ny; pixel_to_pos(P, ni, nj, &nx, &ny);
-                    bd_set_origin(B, mk(nx, ny));
-                    B.vx = 0.0; B.vy = 0.0;
-                }
-            }
-            bp_wsync();
-            bool moved = false;
-#if defined(BP_HOST_EMU) || !defined(__CUDACC__)
-            for (int b = 0; b <= P.NB; b++) {
-                const BdBody& B = E->body[b == P.NB ? 0 : 1 + b];
-                if (b < P.NB && !B.alive) continue;
-                V2 o = bd_origin(B);
-                if (have_prev && dist2(pvx[b], pvy[b], o.x, o.y) > NOT_MOVING_THRESHOLD) moved = true;
-                pvx[b] = o.x; pvy[b] = o.y;
-            }
-#else
-            if (lane <= P.NB) {
-                const BdBody& B = E->body[lane == P.NB ? 0 : 1 + lane];
-                if (lane == P.NB || B.alive) {
-                    V2 o = bd_origin(B);
-                    if (have_prev && dist2(prev_x, prev_y, o.x, o.y) > NOT_MOVING_THRESHOLD) moved = true;
-                    prev_x = o.x; prev_y = o.y;
-                }
-            }
-#endif
-            still_done = have_prev && !bp_wany(moved);
-            have_prev = true;
-        }
-        // ---- the substep (the reference steps once more after deciding that everything is still, :1007-1019)
-        bd_substep(C, E);
-        // ---- after the substep
-        if (state == MV_EXEC) {
-            pos_x = E->body[0].px; pos_y = E->body[0].py; heading = restrict_heading(E->body[0].pa);
-            prev_heading_diff = hd;
+}
+
+BP_DEVNI void mv_post(const BdConst& C, BdEnv* E, MoveVars& V) {
+    const BdParams& P = C.P;
+    if (bp_lane() == 0) {
+        if (V.state == MV_EXEC) {
+            double (*wp)[3] = E->path;
+            const int wi = V.wi;
+            double pos_x = E->body[0].px, pos_y = E->body[0].py, heading = restrict_heading(E->body[0].pa);
+            V.pos_x = pos_x; V.pos_y = pos_y; V.heading = heading;
+            V.prev_heading_diff = V.hd;
             bool stop = false;
             if (dist2(wp[wi - 1][0], wp[wi - 1][1], pos_x, pos_y) > MOVE_STEP_SIZE && E->robot_hit) stop = true;
             if (!stop && dist2(pos_x, pos_y, wp[wi][0], wp[wi][1]) < WAYPOINT_MOVING_THRESHOLD && fabs(heading - wp[wi][2]) < WAYPOINT_TURNING_THRESHOLD) {
-                robot_distance += dist2(wp[wi - 1][0], wp[wi - 1][1], pos_x, pos_y);
-                if (wi == n - 1) stop = true;
-                else {
-                    wi++;
-                    done_turning = false;
-                    if (lane == 0) LS.dp_none = 1;
-                    bp_wsync();
-                }
+                V.robot_distance += dist2(wp[wi - 1][0], wp[wi - 1][1], pos_x, pos_y);
+                if (wi == V.n - 1) stop = true;
+                else { V.wi = wi + 1; V.done_turning = 0; V.LS.dp_none = 1; }
             }
             if (!stop) {
-                sim_steps++;
-                if (sim_steps > P.step_limit) { if (lane == 0) E->status |= BD_STEP_LIMIT; stop = true; }
+                V.sim_steps++;
+                if (V.sim_steps > P.step_limit) { E->status |= BD_STEP_LIMIT; stop = true; }
             }
             if (stop) {
-                if (lane == 0) E->robot_distance = robot_distance;
-                bp_wsync();
-                sim_steps = 0;
+                E->robot_distance = V.robot_distance;
+                V.sim_steps = 0;
                 // area-clearing: a fixed number of substeps follows the path (area_clearing.py:692-693); box-delivery: until still
-                state = (P.kind == 1) ? (P.post_steps > 0 ? MV_POST : MV_DONE) : MV_STILL;
+                V.state = (P.kind == 1) ? (P.post_steps > 0 ? MV_POST : MV_DONE) : MV_STILL;
             }
-        } else if (state == MV_STILL) {
-            if (still_done) state = MV_DONE;
+        } else if (V.state == MV_STILL) {
+            // the reference steps once more after deciding that everything is still (:1007-1019)
+            if (V.still_done) V.state = MV_DONE;
             else {
-                sim_steps++;
-                if (sim_steps > STEP_LIMIT) { if (lane == 0) E->status |= BD_STEP_LIMIT; state = MV_DONE; }
+                V.sim_steps++;
+                if (V.sim_steps > STEP_LIMIT) { E->status |= BD_STEP_LIMIT; V.state = MV_DONE; }
             }
-        } else {
-            if (++post_k >= P.post_steps) state = MV_DONE;
+        } else if (V.state == MV_POST) {
+            if (++V.post_k >= P.post_steps) V.state = MV_DONE;
         }
     }
-    (void)prev_x; (void)prev_y;
+    bp_wsync();
+}
+
+// envs [env0, env0 + nk) of this warp; V[k] in shared memory.  Every warp of the block calls this (nk may be 0).
+BP_DEVNI void bd_move(const BdConst& C, int env0, int nk, const uint8_t* mask, MoveVars* V) {
+    const int lane = bp_lane();
+#pragma unroll 1
+    for (int k = 0; k < nk; k++) {
+        if (lane == 0) {
+            MoveVars& v = V[k];
+            bool part = !(mask && !mask[env0 + k]);
+            v.state = part ? MV_EXEC : MV_DONE;
+            if (part) {
+                BdEnv* E = bd_env(C, env0 + k);
+                bd_finalize_path(C, E);
+                v.wi = 1; v.sim_steps = 0; v.post_k = 0; v.n = E->n_path; v.done_turning = 0; v.have_prev = 0; v.still_done = 0;
+                v.pos_x = E->init_pos[0]; v.pos_y = E->init_pos[1]; v.heading = E->init_heading;
+                v.robot_distance = 0.0; v.prev_heading_diff = 0.0; v.hd = 0.0; v.LS.dp_none = 1;
+            }
+        }
+    }
+    bp_wsync();
+#pragma unroll 1
+    for (;;) {
+        unsigned act = 0;
+#pragma unroll 1
+        for (int k = 0; k < nk; k++) if (V[k].state != MV_DONE) act |= 1u << k;
+        if (!BP_BLOCK_ANY(act != 0)) break;
+        if (!act) continue;
+#pragma unroll 1
+        for (int k = 0; k < nk; k++) if (act >> k & 1) mv_pre(C, bd_env(C, env0 + k), V[k]);
+#pragma unroll 1
+        for (int k = 0; k < nk; k++) if (act >> k & 1) bd_phase_a(C, bd_env(C, env0 + k));
+#pragma unroll 1
+        for (int k = 0; k < nk; k++) if ((act >> k & 1) && !bd_env(C, env0 + k)->fast) bd_phase_b(C, bd_env(C, env0 + k));
+#pragma unroll 1
+        for (int k = 0; k < nk; k++) if ((act >> k & 1) && !bd_env(C, env0 + k)->fast) bd_phase_c(C, bd_env(C, env0 + k));
+#pragma unroll 1
+        for (int k = 0; k < nk; k++) if ((act >> k & 1) && !bd_env(C, env0 + k)->fast) bd_phase_d(C, bd_env(C, env0 + k));
+#pragma unroll 1
+        for (int k = 0; k < nk; k++) if (act >> k & 1) mv_post(C, bd_env(C, env0 + k), V[k]);
+    }
     bp_wsync();
 }
 

@@ -137,14 +137,20 @@ int bp_boxdel_reset(bp_boxdel_t* h, const int32_t* layout_ids, const uint8_t* ma
 int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream) {
     const BdConst& K = h->HB.K;
     BdOut o = bd_out(out);
-    SpfaShared S; BdLoop LS;
-    for (int e = 0; e < h->cfg.n_envs; e++) {
+    SpfaShared S;
+    static MoveVars V[BD_MOVE_K];
+    const int n = h->cfg.n_envs;
+    for (int e = 0; e < n; e++) {
         if (mask && !mask[e]) continue;
         BdEnv* E = bd_env(K, e);
         bd_begin_step(K, E, (double)actions[e]);
         for (int k = 0; k <= K.P.NB; k++) bd_dist_item(S, K, E, k, 0, h->scratch.data());
-        bd_finalize_path(K, E);
-        bd_move(K, E, LS, true);
+    }
+    // as the kernel: one "warp" per BD_MOVE_K consecutive envs, phase-major
+    for (int e0 = 0; e0 < n; e0 += BD_MOVE_K) bd_move(K, e0, (n - e0 < BD_MOVE_K) ? n - e0 : BD_MOVE_K, mask, V);
+    for (int e = 0; e < n; e++) {
+        if (mask && !mask[e]) continue;
+        BdEnv* E = bd_env(K, e);
         for (int k = 0; k < K.P.NB; k++) bd_dist_item(S, K, E, k, 1, h->scratch.data());
         bd_finish_step(K, E, e, o);
     }
