@@ -84,6 +84,53 @@ __global__ void __launch_bounds__(BD_MOVE_BLOCK, BD_MOVE_MINB * 128 / BD_MOVE_BL
     bd_move(*C, env0, nk, mask, V[threadIdx.x >> 5]);
 }
 
+// ---- phase-per-kernel variant of the substep loop: every warp of the GPU runs the same small piece of code at the same time
+// (one kernel per phase over the whole batch, warp per env, loop state in global memory), so the instruction working set of a
+// launch fits the instruction cache.  The host enqueues chunks of iterations and reads one flag per chunk.
+__global__ void __launch_bounds__(128) k_mv_init(const BdConst* C, const uint8_t* mask, MoveVars* mv) {
+    int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= C->n_envs || (threadIdx.x & 31)) return;
+    MoveVars& v = mv[env];
+    bool part = !(mask && !mask[env]);
+    v.state = part ? MV_EXEC : MV_DONE;
+    if (!part) return;
+    BdEnv* E = bd_env(*C, env);
+    bd_finalize_path(*C, E);
+    v.wi = 1; v.sim_steps = 0; v.post_k = 0; v.n = E->n_path; v.done_turning = 0; v.have_prev = 0; v.still_done = 0;
+    v.pos_x = E->init_pos[0]; v.pos_y = E->init_pos[1]; v.heading = E->init_heading;
+    v.robot_distance = 0.0; v.prev_heading_diff = 0.0; v.hd = 0.0; v.LS.dp_none = 1;
+}
+__global__ void __launch_bounds__(128) k_mv_pre_a(const BdConst* C, MoveVars* mv) {
+    int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= C->n_envs || mv[env].state == MV_DONE) return;
+    BdEnv* E = bd_env(*C, env);
+    mv_pre(*C, E, mv[env]);
+    bd_phase_a(*C, E);
+}
+__global__ void __launch_bounds__(128) k_mv_b(const BdConst* C, MoveVars* mv) {
+    int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= C->n_envs || mv[env].state == MV_DONE) return;
+    BdEnv* E = bd_env(*C, env);
+    if (!E->fast) bd_phase_b(*C, E);
+}
+__global__ void __launch_bounds__(128) k_mv_c(const BdConst* C, MoveVars* mv) {
+    int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= C->n_envs || mv[env].state == MV_DONE) return;
+    BdEnv* E = bd_env(*C, env);
+    if (!E->fast) bd_phase_c(*C, E);
+}
+__global__ void __launch_bounds__(128) k_mv_d_post(const BdConst* C, MoveVars* mv) {
+    int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= C->n_envs || mv[env].state == MV_DONE) return;
+    BdEnv* E = bd_env(*C, env);
+    if (!E->fast) bd_phase_d(*C, E);
+    mv_post(*C, E, mv[env]);
+}
+__global__ void k_mv_alive(const BdConst* C, const MoveVars* mv, int* flag) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < C->n_envs && mv[env].state != MV_DONE) *flag = 1;
+}
+
 // thread per env
 __global__ void k_bd_finish(const BdConst* C, const uint8_t* mask, BdOut out) {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,6 +171,7 @@ struct bp_boxdel {
     // optional kernel timing (CUDA events on the launching stream around k_bd_move / k_bd_obs of every step)
     bool profiling = false;
     std::vector<cudaEvent_t> ev;      // 4 per timed step: move start / stop, obs start / stop
+    MoveVars* d_mv = nullptr; int* h_flag = nullptr; int phase_chunk = 64;
 };
 
 
@@ -140,7 +188,7 @@ void bp_boxdel_default_config(bp_boxdel_config* c) {
     c->robot_length = 0.6; c->robot_width = 0.92;
     c->partial_rewards_scale = 0.2; c->goal_reward = 10.0; c->collision_penalty = 0.25; c->non_movement_penalty = 0.0;
     c->correct_direction_reward_scale = 3.0; c->use_correct_direction_reward = 0; c->ministep_size = 2.5;
-    c->shortest_path_channel_scale = 0.25; c->force_box_spfa = 0;
+    c->shortest_path_channel_scale = 0.25; c->force_box_spfa = 0; c->phase_kernels = 0;
     c->env_kind = 0; c->step_limit = 10000; c->post_steps = 0; c->t_max = 0; c->n_boundary = 0; c->n_goals = 0;
     c->lfc = 0.0; c->omega_mul = 3.0; c->v_mul = 2.0; c->bound_x = c->room_length; c->bound_y = c->room_width;
     c->static_e = 0.01; c->static_u = 1.0; c->robot_code = 6; c->box_code = 4; c->box_done_code = 4; c->n_footprint = 0;
@@ -169,7 +217,7 @@ int bp_boxdel_destroy(bp_boxdel_t* h) {
     if (!h) return BP_OK;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->dC); cudaFree(h->d_layouts); cudaFree(h->d_pa); cudaFree(h->d_pb); cudaFree(h->d_cspace); cudaFree(h->d_thin); cudaFree(h->d_small);
-    cudaFree(h->d_rchan); cudaFree(h->d_closest); cudaFree(h->d_recept); cudaFree(h->d_envs); cudaFree(h->d_scratch); cudaFree(h->d_counter);
+    cudaFree(h->d_rchan); cudaFree(h->d_closest); cudaFree(h->d_recept); cudaFree(h->d_envs); cudaFree(h->d_scratch); cudaFree(h->d_counter); cudaFree(h->d_mv); if (h->h_flag) cudaFreeHost(h->h_flag);
     delete h;
     return BP_OK;
 }
@@ -222,6 +270,8 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
     h->n_blocks = sms * 4;
     CUDA_TRY(cudaMalloc((void**)&h->d_scratch, (size_t)h->n_blocks * bd_scratch_ints(P) * sizeof(int)));
     CUDA_TRY(cudaMalloc((void**)&h->d_counter, 64));
+    CUDA_TRY(cudaMalloc((void**)&h->d_mv, sizeof(MoveVars) * (size_t)c.n_envs));
+    CUDA_TRY(cudaMallocHost((void**)&h->h_flag, 64));
     CUDA_TRY(cudaMalloc((void**)&h->dC, sizeof(BdConst)));
     CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdConst), cudaMemcpyHostToDevice));
     k_bd_init_statics<<<1, 32>>>(h->dC);
@@ -308,7 +358,27 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
     k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 0, h->d_scratch, h->d_counter);
     cudaEvent_t e4[4] = {nullptr, nullptr, nullptr, nullptr};
     if (h->profiling) { for (auto& e : e4) { CUDA_TRY(cudaEventCreate(&e)); h->ev.push_back(e); } CUDA_TRY(cudaEventRecord(e4[0], st)); }
-    {
+    if (h->cfg.phase_kernels) {
+        // one kernel per phase over the whole batch; the number of iterations is data dependent (until every env's loop has
+        // ended), so the host enqueues chunks and reads one flag per chunk (this path synchronises the stream once per chunk)
+        const int wb = (E * 32 + 127) / 128;
+        k_mv_init<<<wb, 128, 0, st>>>(h->dC, mask, h->d_mv);
+        int* d_flag = h->d_counter + 8;
+        for (long it = 0;; it += h->phase_chunk) {
+            for (int i = 0; i < h->phase_chunk; i++) {
+                k_mv_pre_a<<<wb, 128, 0, st>>>(h->dC, h->d_mv);
+                k_mv_b<<<wb, 128, 0, st>>>(h->dC, h->d_mv);
+                k_mv_c<<<wb, 128, 0, st>>>(h->dC, h->d_mv);
+                k_mv_d_post<<<wb, 128, 0, st>>>(h->dC, h->d_mv);
+            }
+            h->launches += 4L * h->phase_chunk + 1;
+            CUDA_TRY(cudaMemsetAsync(d_flag, 0, 4, st));
+            k_mv_alive<<<(E + 255) / 256, 256, 0, st>>>(h->dC, h->d_mv, d_flag);
+            CUDA_TRY(cudaMemcpyAsync(h->h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (!*h->h_flag || it > 40000) break;
+        }
+    } else {
         int warps = (E + BD_MOVE_K - 1) / BD_MOVE_K;
         k_bd_move<<<(warps * 32 + BD_MOVE_BLOCK - 1) / BD_MOVE_BLOCK, BD_MOVE_BLOCK, 0, st>>>(h->dC, mask);
     }

@@ -62,7 +62,7 @@ class BoxDelConfig(C.Structure):
         ("n_envs", C.c_int32), ("num_boxes", C.c_int32), ("device", C.c_int32), ("action_type", C.c_int32),
         ("steps", C.c_int32), ("iterations", C.c_int32), ("settle_steps", C.c_int32), ("inactivity_cutoff", C.c_int32),
         ("local_map_pixel_width", C.c_int32), ("use_correct_direction_reward", C.c_int32),
-        ("force_box_spfa", C.c_int32), ("reserved0", C.c_int32),
+        ("force_box_spfa", C.c_int32), ("phase_kernels", C.c_int32),
         ("ctrl_dt", C.c_double), ("target_speed", C.c_double), ("damping", C.c_double),
         ("box_size", C.c_double), ("box_density", C.c_double),
         ("room_length", C.c_double), ("room_width", C.c_double), ("receptacle_width", C.c_double),
@@ -266,6 +266,9 @@ class BoxDeliveryVecEnv:
 
     def _finish_init(self, k, r, ch3_map):
         """Create the native handle from the filled config, upload layouts / room maps, allocate the output buffers."""
+        import os
+        if os.environ.get("BENCHPUSH_BD_PHASED") is not None:          # development aid: A/B of the substep-loop variants
+            k.phase_kernels = int(os.environ["BENCHPUSH_BD_PHASED"])
         L, E, NB, LW = self._L, self.num_envs, self.num_boxes, self.local_map_pixel_width
         self._h = C.c_void_p()
         self._check(L.bp_boxdel_create(C.byref(k), C.byref(self._h)))

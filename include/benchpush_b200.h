@@ -257,7 +257,7 @@ typedef struct bp_boxdel_config {
     int32_t steps, iterations, settle_steps, inactivity_cutoff;   /* cfg.sim.steps / iterations, 1000, cfg.misc.inactivity_cutoff */
     int32_t local_map_pixel_width, use_correct_direction_reward;
     int32_t force_box_spfa;       /* 1: always solve spfa per box even when the exact visibility shortcut applies (testing aid) */
-    int32_t reserved0;
+    int32_t phase_kernels;        /* 1: substep loop as one kernel per phase over the whole batch (synchronises the stream once per 64 iterations) */
     double ctrl_dt, target_speed, damping;                        /* cfg.controller.dt / target_speed, cfg.sim.damping */
     double box_size, box_density;
     double room_length, room_width, receptacle_width;

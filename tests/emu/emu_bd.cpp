@@ -51,7 +51,7 @@ void bp_boxdel_default_config(bp_boxdel_config* c) {
     c->robot_length = 0.6; c->robot_width = 0.92;
     c->partial_rewards_scale = 0.2; c->goal_reward = 10.0; c->collision_penalty = 0.25; c->non_movement_penalty = 0.0;
     c->correct_direction_reward_scale = 3.0; c->use_correct_direction_reward = 0; c->ministep_size = 2.5;
-    c->shortest_path_channel_scale = 0.25; c->force_box_spfa = 0;
+    c->shortest_path_channel_scale = 0.25; c->force_box_spfa = 0; c->phase_kernels = 0;
     c->env_kind = 0; c->step_limit = 10000; c->post_steps = 0; c->t_max = 0; c->n_boundary = 0; c->n_goals = 0;
     c->lfc = 0.0; c->omega_mul = 3.0; c->v_mul = 2.0; c->bound_x = c->room_length; c->bound_y = c->room_width;
     c->static_e = 0.01; c->static_u = 1.0; c->robot_code = 6; c->box_code = 4; c->box_done_code = 4; c->n_footprint = 0;

@@ -12,7 +12,8 @@ def build():
     so = os.path.join(_HERE, "libbp_emu_bd.so")
     srcs = [os.path.join(_HERE, "emu_bd.cpp")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-o", so, os.path.join(_HERE, "emu_bd.cpp")])
+        # BD_MOVE_K=3: the emulation steps three envs per "warp" so that the phase-major multi-env path (and its ragged tail) is covered
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-DBD_MOVE_K=3", "-shared", "-o", so, os.path.join(_HERE, "emu_bd.cpp")])
     return so
 
 
