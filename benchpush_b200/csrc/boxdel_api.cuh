@@ -77,11 +77,14 @@ __global__ void __launch_bounds__(256) k_bd_dist(const BdConst* C, const uint8_t
 #endif
 __global__ void __launch_bounds__(BD_MOVE_BLOCK, BD_MOVE_MINB * 128 / BD_MOVE_BLOCK) k_bd_move(const BdConst* C, const uint8_t* mask) {
     __shared__ MoveVars V[BD_MOVE_BLOCK / 32][BD_MOVE_K];
+    // hot env headers of this block's envs stay in shared memory for the whole launch (6.6 KB each): the loop touches them
+    // ~100 times per substep, and with every resident warp streaming its own header L1 did not hold them (occupancy sweep)
+    __shared__ __align__(16) char hot[BD_MOVE_BLOCK / 32][BD_MOVE_K][(sizeof(BdEnv) + 15) / 16 * 16];
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int env0 = warp * BD_MOVE_K;
     int nk = C->n_envs - env0;
     nk = nk < 0 ? 0 : (nk > BD_MOVE_K ? BD_MOVE_K : nk);
-    bd_move(*C, env0, nk, mask, V[threadIdx.x >> 5]);
+    bd_move(*C, env0, nk, mask, V[threadIdx.x >> 5], &hot[threadIdx.x >> 5][0][0], (int)sizeof(hot[0][0]));
 }
 
 // ---- phase-per-kernel variant of the substep loop: every warp of the GPU runs the same small piece of code at the same time
@@ -462,16 +465,18 @@ int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double*
     if (!h || !h->loaded || env < 0 || env >= h->cfg.n_envs) return fail(BP_ERR_INVALID, "bad argument");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     CUDA_TRY(cudaDeviceSynchronize());
-    std::vector<char> buf(sizeof(BdEnv));
-    CUDA_TRY(cudaMemcpy(buf.data(), h->d_envs + h->hC.env_bytes * env, sizeof(BdEnv), cudaMemcpyDeviceToHost));
+    const size_t hdr = BP_ALIGN128(sizeof(BdEnv));
+    std::vector<char> buf(hdr + sizeof(BdEnvCold));
+    CUDA_TRY(cudaMemcpy(buf.data(), h->d_envs + h->hC.env_bytes * env, buf.size(), cudaMemcpyDeviceToHost));
     const BdEnv* E = (const BdEnv*)buf.data();
+    const BdEnvCold* K = (const BdEnvCold*)(buf.data() + hdr);
     if (out16) {
         out16[0] = E->n_path; out16[1] = E->move_sign; out16[2] = E->need_spfa; out16[3] = E->status; out16[4] = E->robot_hit;
         out16[5] = (double)E->stat_substeps; out16[6] = (double)E->stat_cand; out16[7] = (double)E->stat_arb; out16[8] = E->robot_distance;
         for (int i = 9; i < 16; i++) out16[i] = 0.0;
     }
-    if (dists) for (int i = 0; i < h->cfg.num_boxes; i++) { dists[i] = E->init_dist[i]; dists[h->cfg.num_boxes + i] = E->final_dist[i]; }
-    if (path) memcpy(path, E->path, sizeof(E->path));
+    if (dists) for (int i = 0; i < h->cfg.num_boxes; i++) { dists[i] = K->init_dist[i]; dists[h->cfg.num_boxes + i] = K->final_dist[i]; }
+    if (path) memcpy(path, K->path, sizeof(K->path));
     return BP_OK;
 }
 

@@ -123,7 +123,17 @@ struct BdShapes {                 // immutable per handle: robot shapes (body-lo
     double box_rad, box_e, box_u;
 };
 
-struct BdEnv {                    // mutable per env (header; the slot table follows it in the env block)
+struct BdSlot;
+struct BdEnvCold {                // per env, global memory only: touched once per substep or once per env step
+    double path[MAXWP][3];
+    double init_dist[MAXBOX], final_dist[MAXBOX];
+    double prev_boxes[MAXBOX][SV][2];   // CostMap.get_obs_from_poly at the previous env step (work accounting)
+    short order[MAXCAND];         // this step's solve list (slot ids), colour-sorted
+    short cand[MAXCAND];
+    unsigned char ccnt[MAXCAND];
+    Manifold cman[MAXCAND];
+};
+struct BdEnv {                    // mutable per env: the HOT header (6.6 KB) — k_bd_move keeps a copy in shared memory for the whole launch
     int layout, episode, t, status, stamp, n_order, robot_hit, inactivity, cum_boxes, done, truncated, n_prev;
     int cleared_count, pad_c;
     int nc, fast;                 // this substep: candidate pairs; 1 = nothing overlaps and nothing is cached (phases B-D skipped)
@@ -131,22 +141,17 @@ struct BdEnv {                    // mutable per env (header; the slot table fol
     long long stat_substeps, stat_cand, stat_arb;
     double prev_dt, cum_distance, cum_reward, total_work, last_work, reward, ministeps;
     double init_pos[2], init_heading, robot_distance;
-    double path[MAXWP][3];
     double tgt[2];
-    double init_dist[MAXBOX], final_dist[MAXBOX];
+    BdEnvCold* cold;              // the env block's cold part and dense pair table (pointers stay valid in any copy of the header)
+    BdSlot* slots;
     BdBody body[1 + MAXBOX];      // [0] robot (all six shapes), [1 + i] box i
     alignas(16) double wv[NMOV][SV][2];   // world vertices of the moving shapes: [0, 6) robot, [6 + i] box i (128-bit vertex loads)
     BBox bb[NMOV];
-    double prev_boxes[MAXBOX][SV][2];   // CostMap.get_obs_from_poly at the previous env step (work accounting)
     unsigned char completed[MAXBOX];
-    short order[MAXCAND];         // this step's solve list (slot ids), colour-sorted
-    short cand[MAXCAND];
-    unsigned char ccnt[MAXCAND];
-    Manifold cman[MAXCAND];
 };
 
-BP_HD size_t bd_env_bytes(int n_slots) { return BP_ALIGN128(sizeof(BdEnv)) + BP_ALIGN128((size_t)n_slots * sizeof(BdSlot)); }
-BP_DEV BdSlot* bd_slots(BdEnv* e) { return (BdSlot*)((char*)e + BP_ALIGN128(sizeof(BdEnv))); }
+// env block = [BdEnv header][BdEnvCold][BdSlot x n_slots]
+BP_HD size_t bd_env_bytes(int n_slots) { return BP_ALIGN128(sizeof(BdEnv)) + BP_ALIGN128(sizeof(BdEnvCold)) + BP_ALIGN128((size_t)n_slots * sizeof(BdSlot)); }
 
 struct BdConst {
     BdParams P; BdShapes S;
@@ -162,6 +167,12 @@ struct BdConst {
     char* envs; size_t env_bytes;
 };
 BP_DEV BdEnv* bd_env(const BdConst& C, int e) { return (BdEnv*)(C.envs + (size_t)e * C.env_bytes); }
+BP_DEV BdSlot* bd_slots(BdEnv* e) { return e->slots; }
+// pointers of the header into its env block (set at reset, from the header's GLOBAL address)
+BP_DEV void bd_link_env(BdEnv* g) {
+    g->cold = (BdEnvCold*)((char*)g + BP_ALIGN128(sizeof(BdEnv)));
+    g->slots = (BdSlot*)((char*)g + BP_ALIGN128(sizeof(BdEnv)) + BP_ALIGN128(sizeof(BdEnvCold)));
+}
 
 // dense pair table (ascending (shape a, shape b) with a < b):  shape ids: [0,6) robot, [6, 6+NB) boxes, then statics
 static inline int bd_build_pairs(const BdParams& P, short* pa, short* pb) {
@@ -282,8 +293,8 @@ BP_DEVNI BodyV body_view(const BdConst& C, const BdEnv* E, int s, int body) {
 
 // cpArbiterUpdate for candidate q (manifold already computed); returns nothing, marks the slot touched this step
 BP_DEVNI void bd_arb_update(const BdConst& C, BdEnv* E, int q) {
-    int p = E->cand[q];
-    const Manifold& m = E->cman[q];
+    int p = E->cold->cand[q];
+    const Manifold& m = E->cold->cman[q];
     BdSlot& S = bd_slots(E)[p];
     int sa = C.pair_a[p], sb = C.pair_b[p];
     ShapeRef A = shape_ref(C, E, sa), B = shape_ref(C, E, sb);
@@ -313,7 +324,7 @@ BP_DEVNI void bd_arb_update(const BdConst& C, BdEnv* E, int q) {
 // prevent_boundary_intersection (box_delivery_env.py:294-311) for candidate q = (moving shape a, type-3 static b).
 // shapes[0] is always `a` here (robot chassis or box precede the statics in shape order: not swapped).
 BP_DEVNI bool bd_boundary_presolve(const BdConst& C, BdEnv* E, int q) {
-    int p = E->cand[q];
+    int p = E->cold->cand[q];
     BdSlot& S = bd_slots(E)[p];
     int sa = C.pair_a[p], sb = C.pair_b[p];
     int body = (sa < NROBOT) ? 0 : 1 + (sa - NROBOT);
@@ -425,7 +436,7 @@ BP_DEVNI void bd_phase_a(const BdConst& C, BdEnv* E) {
     const double dt = P.dt;
     // arbiters solved in the previous step leave FIRST_COLLISION
     #pragma unroll 1
-    for (int k = lane; k < E->n_order; k += BP_NL) { BdSlot& S = slots[E->order[k]]; if (S.state != SL_NONE) S.state = SL_NORMAL; }
+    for (int k = lane; k < E->n_order; k += BP_NL) { BdSlot& S = slots[E->cold->order[k]]; if (S.state != SL_NONE) S.state = SL_NORMAL; }
     bp_wsync();
     if (lane == 0) { E->stamp++; E->stat_substeps++; }
     // 1. integrate positions (kinematic robot + live boxes), refresh the shapes
@@ -478,7 +489,7 @@ BP_DEVNI void bd_phase_a(const BdConst& C, BdEnv* E) {
             }
         }
         int tot; int rk = bp_wrank(take, &tot);
-        if (take && nc + rk < MAXCAND) E->cand[nc + rk] = (short)p;
+        if (take && nc + rk < MAXCAND) E->cold->cand[nc + rk] = (short)p;
         nc += tot;
     }
     if (nc > MAXCAND) { nc = MAXCAND; if (lane == 0) E->status |= BD_CAND_OVERFLOW; }
@@ -510,7 +521,7 @@ BP_DEVNI void bd_phase_b(const BdConst& C, BdEnv* E) {
     //    reuses the result of the substep in which it was last evaluated
     #pragma unroll 1
     for (int q = lane; q < nc; q += BP_NL) {
-        int p = E->cand[q];
+        int p = E->cold->cand[q];
         BdSlot& S = slots[p];
         Manifold m;
 #ifdef BD_NO_PAIR_CACHE
@@ -535,7 +546,7 @@ BP_DEVNI void bd_phase_b(const BdConst& C, BdEnv* E) {
             #pragma unroll 1
             for (int i = 0; i < m.count; i++) { S.mp1[i][0] = m.p1[i].x; S.mp1[i][1] = m.p1[i].y; S.mp2[i][0] = m.p2[i].x; S.mp2[i][1] = m.p2[i].y; S.mhash[i] = m.hash[i]; }
         }
-        E->cman[q] = m; E->ccnt[q] = (unsigned char)m.count;
+        E->cold->cman[q] = m; E->cold->ccnt[q] = (unsigned char)m.count;
     }
     bp_wsync();
 }
@@ -552,13 +563,13 @@ BP_DEVNI void bd_phase_c(const BdConst& C, BdEnv* E) {
     //    -> (box i, wall)* sequential per box, boxes in parallel.
     const int seg0 = NB, seg1 = NB + P.n_s3;
     #pragma unroll 1
-    for (int q = lane; q < nc; q += BP_NL) if (E->ccnt[q] && E->cand[q] < seg0) bd_arb_update(C, E, q);
+    for (int q = lane; q < nc; q += BP_NL) if (E->cold->ccnt[q] && E->cold->cand[q] < seg0) bd_arb_update(C, E, q);
     bp_wsync();
     if (lane == 0) {
         #pragma unroll 1
         for (int q = 0; q < nc; q++) {
-            int p = E->cand[q];
-            if (p < seg0 || p >= seg1 || !E->ccnt[q]) continue;
+            int p = E->cold->cand[q];
+            if (p < seg0 || p >= seg1 || !E->cold->ccnt[q]) continue;
             bd_arb_update(C, E, q);
             E->robot_hit = bd_boundary_presolve(C, E, q) ? 1 : 0;
             // kinematic vs static: never solved — contacts dropped, state back to NORMAL
@@ -568,8 +579,8 @@ BP_DEVNI void bd_phase_c(const BdConst& C, BdEnv* E) {
     bp_wsync();
     #pragma unroll 1
     for (int q = lane; q < nc; q += BP_NL) {
-        int p = E->cand[q];
-        if (p < seg1 || !E->ccnt[q]) continue;
+        int p = E->cold->cand[q];
+        if (p < seg1 || !E->cold->ccnt[q]) continue;
         if (C.pair_b[p] >= NROBOT + NB) continue;       // (box, wall): next pass
         bd_arb_update(C, E, q);
     }
@@ -579,8 +590,8 @@ BP_DEVNI void bd_phase_c(const BdConst& C, BdEnv* E) {
         if (!E->body[1 + i].alive) continue;
         #pragma unroll 1
         for (int q = 0; q < nc; q++) {
-            int p = E->cand[q];
-            if (!E->ccnt[q] || C.pair_a[p] != NROBOT + i || C.pair_b[p] < NROBOT + NB) continue;
+            int p = E->cold->cand[q];
+            if (!E->cold->ccnt[q] || C.pair_a[p] != NROBOT + i || C.pair_b[p] < NROBOT + NB) continue;
             bd_arb_update(C, E, q);
             bd_boundary_presolve(C, E, q);
         }
@@ -615,8 +626,8 @@ BP_DEVNI void bd_phase_c(const BdConst& C, BdEnv* E) {
         int maxc = 0;
         #pragma unroll 1
         for (int q = 0; q < nc; q++) {
-            int p = E->cand[q];
-            if (!E->ccnt[q] || (p >= seg0 && p < seg1)) continue;
+            int p = E->cold->cand[q];
+            if (!E->cold->ccnt[q] || (p >= seg0 && p < seg1)) continue;
             int sa = C.pair_a[p], sb = C.pair_b[p];
             int ba = sa < NROBOT ? 0 : 1 + sa - NROBOT;
             int bb = sb < NROBOT + NB ? 1 + sb - NROBOT : -1;
@@ -632,7 +643,7 @@ BP_DEVNI void bd_phase_c(const BdConst& C, BdEnv* E) {
         #pragma unroll 1
         for (int c = 0; c <= maxc && n > 0; c++)
             #pragma unroll 1
-            for (int i = 0; i < n; i++) if (col[i] == c) { E->order[k] = list[i]; E->cman[k].count = c; k++; }   // cman[k].count reused: colour of order[k]
+            for (int i = 0; i < n; i++) if (col[i] == c) { E->cold->order[k] = list[i]; E->cold->cman[k].count = c; k++; }   // cman[k].count reused: colour of order[k]
         E->n_order = n;
         E->stat_cand += nc; E->stat_arb += n;
     }
@@ -648,7 +659,7 @@ BP_DEVNI void bd_phase_d(const BdConst& C, BdEnv* E) {
     const int n_order = E->n_order;
     // 7. pre-step, velocity update (dynamic bodies only), warm start, iterations
     #pragma unroll 1
-    for (int k = lane; k < n_order; k += BP_NL) bd_prestep(C, E, E->order[k]);
+    for (int k = lane; k < n_order; k += BP_NL) bd_prestep(C, E, E->cold->order[k]);
     bp_wsync();
     #pragma unroll 1
     for (int b = 1 + lane; b <= NB; b += BP_NL) {
@@ -665,11 +676,11 @@ BP_DEVNI void bd_phase_d(const BdConst& C, BdEnv* E) {
         int k0 = 0;
         #pragma unroll 1
         while (k0 < n_order) {
-            int c = E->cman[k0].count, k1 = k0;
+            int c = E->cold->cman[k0].count, k1 = k0;
             #pragma unroll 1
-            while (k1 < n_order && E->cman[k1].count == c) k1++;
+            while (k1 < n_order && E->cold->cman[k1].count == c) k1++;
             #pragma unroll 1
-            for (int k = k0 + lane; k < k1; k += BP_NL) bd_solve(C, E, E->order[k], it < 0, dt_coef);
+            for (int k = k0 + lane; k < k1; k += BP_NL) bd_solve(C, E, E->cold->order[k], it < 0, dt_coef);
             bp_wsync();
             k0 = k1;
         }

@@ -98,6 +98,8 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
     const int lane = bp_lane();
     const BdParams& P = C.P;
     const BdLayout& L = C.layouts[layout];
+    if (lane == 0) bd_link_env(E);
+    bp_wsync();
     BdSlot* slots = bd_slots(E);
     #pragma unroll 1
     for (int p = lane; p < P.n_slots; p += BP_NL) { slots[p].state = SL_NONE; slots[p].cnt = 0; slots[p].stamp = 0; slots[p].gjk = 0; slots[p].ov = 0; slots[p].mvalid = 0; }
@@ -134,7 +136,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
         #pragma unroll 1
         for (int v = 0; v < SV; v++) {
             V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
-            E->prev_boxes[i][v][0] = w.x; E->prev_boxes[i][v][1] = w.y;
+            E->cold->prev_boxes[i][v][0] = w.x; E->cold->prev_boxes[i][v][1] = w.y;
         }
     }
     if (lane == 0) E->n_prev = L.n_boxes;
@@ -180,13 +182,13 @@ BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action) {
     pos_to_pixel(P, x0, y0, &si, &sj); pos_to_pixel(P, tx, ty, &ti, &tj);
     if (line_free(C.cspace_thin, P.W, si, sj, ti, tj)) {
         E->need_spfa = 0; E->n_path = 2;
-        E->path[0][0] = x0; E->path[0][1] = y0; E->path[1][0] = tx; E->path[1][1] = ty;
+        E->cold->path[0][0] = x0; E->cold->path[0][1] = y0; E->cold->path[1][0] = tx; E->cold->path[1][1] = ty;
     } else {
         E->need_spfa = 1;
         closest_valid(C, si, sj, &E->src_i, &E->src_j);
         closest_valid(C, ti, tj, &E->tgt_i, &E->tgt_j);
     }
-    if (P.kind == 0 && P.recept_visible) bd_box_dists_visible(C, E, E->init_dist);
+    if (P.kind == 0 && P.recept_visible) bd_box_dists_visible(C, E, E->cold->init_dist);
 }
 
 // ------------------------------------------------------------------ path from a distance field (second half of shortest_path)
@@ -263,7 +265,7 @@ BP_DEV int bd_extract_path(const BdConst& C, const int* dist, int si, int sj, in
 // ------------------------------------------------------------------ waypoint headings, final-waypoint back-off
 BP_DEV void bd_finalize_path(const BdConst& C, BdEnv* E) {
     int n = E->n_path;
-    double (*wp)[3] = E->path;
+    double (*wp)[3] = E->cold->path;
     wp[0][2] = 0.0;   // None
     for (int i = 1; i < n; i++) wp[i][2] = restrict_heading(atan2(wp[i][1] - wp[i - 1][1], wp[i][0] - wp[i - 1][0]));
     double d_end = dist2(wp[n - 2][0], wp[n - 2][1], wp[n - 1][0], wp[n - 1][1]);
@@ -284,7 +286,7 @@ struct BdLoop { int flag; int dp_none; double sp_x, sp_y, al, pl; double cx[2], 
 // DP over the course (wp[wi-1], wp[wi]); scalar, run by one lane; out of line (libm atan2 / sin / cos are large).
 BP_DEVNI void bd_controller(const BdConst& C, BdEnv* E, BdLoop& LS, int wi, double pos_x, double pos_y, double heading, bool done_turning) {
     const BdParams& P = C.P;
-    double (*wp)[3] = E->path;
+    double (*wp)[3] = E->cold->path;
     if (LS.dp_none) {
         LS.cx[0] = wp[wi - 1][0]; LS.cy[0] = wp[wi - 1][1]; LS.cx[1] = wp[wi][0]; LS.cy[1] = wp[wi][1];
         double d0 = hypot(pos_x - LS.cx[0], pos_y - LS.cy[0]), d1 = hypot(pos_x - LS.cx[1], pos_y - LS.cy[1]);
@@ -342,7 +344,7 @@ BP_DEVNI void mv_pre(const BdConst& C, BdEnv* E, MoveVars& V) {
     const BdParams& P = C.P;
     if (V.state == MV_EXEC) {
         if (lane == 0) {
-            double (*wp)[3] = E->path;
+            double (*wp)[3] = E->cold->path;
             double hd = heading_diff(V.heading, wp[V.wi][2]);
             V.hd = hd;
             if (!(fabs(hd) > TURN_STEP_SIZE && fabs(hd - V.prev_heading_diff) > 0.001)) V.done_turning = 1;
@@ -392,7 +394,7 @@ BP_DEVNI void mv_post(const BdConst& C, BdEnv* E, MoveVars& V) {
     const BdParams& P = C.P;
     if (bp_lane() == 0) {
         if (V.state == MV_EXEC) {
-            double (*wp)[3] = E->path;
+            double (*wp)[3] = E->cold->path;
             const int wi = V.wi;
             double pos_x = E->body[0].px, pos_y = E->body[0].py, heading = restrict_heading(E->body[0].pa);
             V.pos_x = pos_x; V.pos_y = pos_y; V.heading = heading;
@@ -429,16 +431,28 @@ BP_DEVNI void mv_post(const BdConst& C, BdEnv* E, MoveVars& V) {
 }
 
 // envs [env0, env0 + nk) of this warp; V[k] in shared memory.  Every warp of the block calls this (nk may be 0).
-BP_DEVNI void bd_move(const BdConst& C, int env0, int nk, const uint8_t* mask, MoveVars* V) {
+// hot != nullptr: the env headers are copied to hot[k * hot_stride] (shared memory) for the launch and written back at the end.
+BP_DEVNI void bd_move(const BdConst& C, int env0, int nk, const uint8_t* mask, MoveVars* V, char* hot, int hot_stride) {
     const int lane = bp_lane();
+    BdEnv* Es[BD_MOVE_K];
 #pragma unroll 1
     for (int k = 0; k < nk; k++) {
+        BdEnv* G = bd_env(C, env0 + k);
+        bool part = !(mask && !mask[env0 + k]);
+        Es[k] = G;
+        if (part && hot) {
+            BdEnv* Hh = (BdEnv*)(hot + (size_t)k * hot_stride);
+            const D2* src = (const D2*)G; D2* dst = (D2*)Hh;          // 16-byte moves
+#pragma unroll 1
+            for (int i = lane; i < (int)(sizeof(BdEnv) / 16); i += BP_NL) dst[i] = src[i];
+            Es[k] = Hh;
+        }
+        bp_wsync();
         if (lane == 0) {
             MoveVars& v = V[k];
-            bool part = !(mask && !mask[env0 + k]);
             v.state = part ? MV_EXEC : MV_DONE;
             if (part) {
-                BdEnv* E = bd_env(C, env0 + k);
+                BdEnv* E = Es[k];
                 bd_finalize_path(C, E);
                 v.wi = 1; v.sim_steps = 0; v.post_k = 0; v.n = E->n_path; v.done_turning = 0; v.have_prev = 0; v.still_done = 0;
                 v.pos_x = E->init_pos[0]; v.pos_y = E->init_pos[1]; v.heading = E->init_heading;
@@ -455,19 +469,30 @@ BP_DEVNI void bd_move(const BdConst& C, int env0, int nk, const uint8_t* mask, M
         if (!BP_BLOCK_ANY(act != 0)) break;
         if (!act) continue;
 #pragma unroll 1
-        for (int k = 0; k < nk; k++) if (act >> k & 1) mv_pre(C, bd_env(C, env0 + k), V[k]);
+        for (int k = 0; k < nk; k++) if (act >> k & 1) mv_pre(C, Es[k], V[k]);
 #pragma unroll 1
-        for (int k = 0; k < nk; k++) if (act >> k & 1) bd_phase_a(C, bd_env(C, env0 + k));
+        for (int k = 0; k < nk; k++) if (act >> k & 1) bd_phase_a(C, Es[k]);
 #pragma unroll 1
-        for (int k = 0; k < nk; k++) if ((act >> k & 1) && !bd_env(C, env0 + k)->fast) bd_phase_b(C, bd_env(C, env0 + k));
+        for (int k = 0; k < nk; k++) if ((act >> k & 1) && !Es[k]->fast) bd_phase_b(C, Es[k]);
 #pragma unroll 1
-        for (int k = 0; k < nk; k++) if ((act >> k & 1) && !bd_env(C, env0 + k)->fast) bd_phase_c(C, bd_env(C, env0 + k));
+        for (int k = 0; k < nk; k++) if ((act >> k & 1) && !Es[k]->fast) bd_phase_c(C, Es[k]);
 #pragma unroll 1
-        for (int k = 0; k < nk; k++) if ((act >> k & 1) && !bd_env(C, env0 + k)->fast) bd_phase_d(C, bd_env(C, env0 + k));
+        for (int k = 0; k < nk; k++) if ((act >> k & 1) && !Es[k]->fast) bd_phase_d(C, Es[k]);
 #pragma unroll 1
-        for (int k = 0; k < nk; k++) if (act >> k & 1) mv_post(C, bd_env(C, env0 + k), V[k]);
+        for (int k = 0; k < nk; k++) if (act >> k & 1) mv_post(C, Es[k], V[k]);
     }
     bp_wsync();
+    if (hot) {
+#pragma unroll 1
+        for (int k = 0; k < nk; k++) {
+            BdEnv* G = bd_env(C, env0 + k);
+            if (Es[k] == G) continue;
+            const D2* src = (const D2*)Es[k]; D2* dst = (D2*)G;
+#pragma unroll 1
+            for (int i = lane; i < (int)(sizeof(BdEnv) / 16); i += BP_NL) dst[i] = src[i];
+        }
+        bp_wsync();
+    }
 }
 
 // ------------------------------------------------------------------ step, part 3: rewards, removal, work, termination
@@ -479,11 +504,11 @@ BP_DEV void bd_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out
     const BdLayout& L = C.layouts[E->layout];
     double reward = 0.0;
     int robot_boxes = 0;
-    if (P.recept_visible) bd_box_dists_visible(C, E, E->final_dist);
+    if (P.recept_visible) bd_box_dists_visible(C, E, E->cold->final_dist);
     for (int i = 0; i < P.NB; i++) {
         BdBody& B = E->body[1 + i];
         if (!B.alive) continue;
-        double dist_moved = E->init_dist[i] - E->final_dist[i];
+        double dist_moved = E->cold->init_dist[i] - E->cold->final_dist[i];
         if (P.use_correct && dist_moved > 0) dist_moved *= P.correct_scale;
         reward += P.partial_scale * dist_moved;
         bool inside = true;
@@ -516,12 +541,12 @@ BP_DEV void bd_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out
     int nz = k < E->n_prev ? k : E->n_prev;
     for (int q = 0; q < nz; q++) {
         double A, ax, ay, A2, bx, by;
-        area_centroid_abs(&E->prev_boxes[q][0][0], SV, &A, &ax, &ay);
+        area_centroid_abs(&E->cold->prev_boxes[q][0][0], SV, &A, &ax, &ay);
         area_centroid_abs(&upd[q][0][0], SV, &A2, &bx, &by);
         double dx = ax - bx, dy = ay - by;
         work += sqrt(dx * dx + dy * dy) * A;
     }
-    for (int q = 0; q < k; q++) for (int v = 0; v < SV; v++) { E->prev_boxes[q][v][0] = upd[q][v][0]; E->prev_boxes[q][v][1] = upd[q][v][1]; }
+    for (int q = 0; q < k; q++) for (int v = 0; v < SV; v++) { E->cold->prev_boxes[q][v][0] = upd[q][v][0]; E->cold->prev_boxes[q][v][1] = upd[q][v][1]; }
     E->n_prev = k;
     E->total_work += work; E->last_work = work;
     if (robot_boxes == 0) E->inactivity++;
@@ -588,9 +613,9 @@ BP_DEV void ac_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out
     double diff_reward = 0.0, work = 0.0;
     for (int i = 0; i < NB; i++) {
         double A, ax, ay, A2, bx, by;
-        area_centroid_abs(&E->prev_boxes[i][0][0], SV, &A, &ax, &ay);
+        area_centroid_abs(&E->cold->prev_boxes[i][0][0], SV, &A, &ax, &ay);
         area_centroid_abs(&upd[i][0][0], SV, &A2, &bx, &by);
-        if (convex_intersects(P.bnd, P.n_bnd, E->prev_boxes[i], SV)) diff_reward += min_goal_dist(P, ax, ay) - min_goal_dist(P, bx, by);
+        if (convex_intersects(P.bnd, P.n_bnd, E->cold->prev_boxes[i], SV)) diff_reward += min_goal_dist(P, ax, ay) - min_goal_dist(P, bx, by);
         double dx = ax - bx, dy = ay - by;
         work += sqrt(dx * dx + dy * dy) * A;
     }
@@ -605,7 +630,7 @@ BP_DEV void ac_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out
     double turn = heading_diff(E->init_heading, heading);
     double nonmove = (E->robot_distance < NONMOVEMENT_DIST_THRESHOLD && fabs(turn) < NONMOVEMENT_TURN_THRESHOLD) ? P.r_nonmove : 0.0;
     E->total_work += work; E->last_work = work;
-    for (int i = 0; i < NB; i++) for (int v = 0; v < SV; v++) { E->prev_boxes[i][v][0] = upd[i][v][0]; E->prev_boxes[i][v][1] = upd[i][v][1]; }
+    for (int i = 0; i < NB; i++) for (int v = 0; v < SV; v++) { E->cold->prev_boxes[i][v][0] = upd[i][v][0]; E->cold->prev_boxes[i][v][1] = upd[i][v][1]; }
     int terminated = all_completed ? 1 : 0;
     double reward = box_completion_reward + collision_penalty + pushing_reward + nonmove;
     int truncated = E->t >= P.t_max;
@@ -641,7 +666,7 @@ BP_DEV void bd_reset_out(const BdConst& C, BdEnv* E, int env, const BdOut& out) 
     if (out.completed) for (int i = 0; i < P.NB; i++) out.completed[(size_t)env * P.NB + i] = 0;
     if (out.box_verts) {
         double* o = out.box_verts + (size_t)env * P.NB * SV * 2;
-        for (int q = 0; q < E->n_prev; q++) for (int v = 0; v < SV; v++) { o[(q * SV + v) * 2] = E->prev_boxes[q][v][0]; o[(q * SV + v) * 2 + 1] = E->prev_boxes[q][v][1]; }
+        for (int q = 0; q < E->n_prev; q++) for (int v = 0; v < SV; v++) { o[(q * SV + v) * 2] = E->cold->prev_boxes[q][v][0]; o[(q * SV + v) * 2 + 1] = E->cold->prev_boxes[q][v][1]; }
     }
 }
 

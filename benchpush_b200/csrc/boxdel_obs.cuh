@@ -26,7 +26,7 @@ namespace bd {
 BP_HD size_t bd_scratch_ints(const BdParams& P) { return (size_t)4 * P.H * P.W + (size_t)P.SMALL * P.SMALL / 4 + 64; }
 
 // ------------------------------------------------------------------ distance / path items
-// k < NB: shortest_path_distance(box k, receptacle) -> E->init_dist[k] (phase 0) or E->final_dist[k] (phase 1);
+// k < NB: shortest_path_distance(box k, receptacle) -> E->cold->init_dist[k] (phase 0) or E->cold->final_dist[k] (phase 1);
 // k == NB: the robot's waypoints when the straight line was blocked (phase 0 only).
 BP_DEV void bd_dist_item(SpfaShared& S, const BdConst& C, BdEnv* E, int k, int phase, int* scratch) {
     const BdParams& P = C.P;
@@ -56,9 +56,9 @@ BP_DEV void bd_dist_item(SpfaShared& S, const BdConst& C, BdEnv* E, int k, int p
         if (k < P.NB) {
             double d = 0.0;
             for (int i = 1; i < n; i++) d = d + dist2(wp[i - 1][0], wp[i - 1][1], wp[i][0], wp[i][1]);
-            if (phase == 0) E->init_dist[k] = d; else E->final_dist[k] = d;
+            if (phase == 0) E->cold->init_dist[k] = d; else E->cold->final_dist[k] = d;
         } else {
-            for (int i = 0; i < n; i++) { E->path[i][0] = wp[i][0]; E->path[i][1] = wp[i][1]; }
+            for (int i = 0; i < n; i++) { E->cold->path[i][0] = wp[i][0]; E->cold->path[i][1] = wp[i][1]; }
             E->n_path = n;
         }
     }

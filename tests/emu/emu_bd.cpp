@@ -147,7 +147,7 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
         for (int k = 0; k <= K.P.NB; k++) bd_dist_item(S, K, E, k, 0, h->scratch.data());
     }
     // as the kernel: one "warp" per BD_MOVE_K consecutive envs, phase-major
-    for (int e0 = 0; e0 < n; e0 += BD_MOVE_K) bd_move(K, e0, (n - e0 < BD_MOVE_K) ? n - e0 : BD_MOVE_K, mask, V);
+    for (int e0 = 0; e0 < n; e0 += BD_MOVE_K) bd_move(K, e0, (n - e0 < BD_MOVE_K) ? n - e0 : BD_MOVE_K, mask, V, nullptr, 0);
     for (int e = 0; e < n; e++) {
         if (mask && !mask[e]) continue;
         BdEnv* E = bd_env(K, e);
@@ -178,8 +178,8 @@ int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double*
         out16[5] = (double)E->stat_substeps; out16[6] = (double)E->stat_cand; out16[7] = (double)E->stat_arb; out16[8] = E->robot_distance;
         for (int i = 9; i < 16; i++) out16[i] = 0.0;
     }
-    if (dists) for (int i = 0; i < h->cfg.num_boxes; i++) { dists[i] = E->init_dist[i]; dists[h->cfg.num_boxes + i] = E->final_dist[i]; }
-    if (path) memcpy(path, E->path, sizeof(E->path));
+    if (dists) for (int i = 0; i < h->cfg.num_boxes; i++) { dists[i] = E->cold->init_dist[i]; dists[h->cfg.num_boxes + i] = E->cold->final_dist[i]; }
+    if (path) memcpy(path, E->cold->path, sizeof(E->cold->path));
     return 0;
 }
 // host twin of bp_spfa_batch_host (same kernel source, one lane)
