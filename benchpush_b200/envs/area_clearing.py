@@ -12,7 +12,7 @@ Host work done here once per handle: configuration space, nearest-free-cell map 
 (``create_global_shortest_path_to_goal_points``, area_clearing.py:1055-1082: one spfa solve per goal point — run on the
 GPU through ``bp_spfa_batch`` — min-combined, normalised and masked by the two boundary squares).
 
-Implemented: the environments without inner walls or static obstacles (``clear_env``), ``action_type`` heading / position.
+Implemented: the environments without inner walls or static obstacles (``clear_env``, ``clear_env_small``), ``action_type`` heading / position.
 Layouts are inputs or drawn by ``layouts.sample_area_clearing_layout`` (the reference uses the unseeded global ``random``).
 """
 from __future__ import annotations
@@ -32,6 +32,9 @@ ENVS = {   # area_clearing/envs/*.yaml restated (environments without inner wall
     "clear_env": {"outer_boundary": [[-8.0, -8.0], [-8.0, 8.0], [8.0, 8.0], [8.0, -8.0]],
                   "boundary": [[-5.0, -5.0], [-5.0, 5.0], [5.0, 5.0], [5.0, -5.0]],
                   "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 24},
+    "clear_env_small": {"outer_boundary": [[-6.0, -6.0], [-6.0, 6.0], [6.0, 6.0], [6.0, -6.0]],
+                        "boundary": [[-4.0, -4.0], [-4.0, 4.0], [4.0, 4.0], [4.0, -4.0]],
+                        "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 12},
 }
 
 DEFAULT_CFG = {   # area_clearing/config.yaml restated (keys that reach the hot path)
@@ -123,7 +126,7 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"] not in ENVS:
-            raise NotImplementedError("only the environments without inner walls are implemented (env: clear_env)")
+            raise NotImplementedError("only the environments without inner walls are implemented (env: clear_env, clear_env_small)")
         if c["agent"]["action_type"] not in ("heading", "position"):
             raise NotImplementedError("action_type 'velocity' is not implemented")
         if c["low_dim_state"]:

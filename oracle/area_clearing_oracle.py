@@ -41,6 +41,9 @@ ENVS = {   # area_clearing/envs/*.yaml (the two without walls)
     "clear_env": {"outer_boundary": [[-8.0, -8.0], [-8.0, 8.0], [8.0, 8.0], [8.0, -8.0]],
                   "boundary": [[-5.0, -5.0], [-5.0, 5.0], [5.0, 5.0], [5.0, -5.0]],
                   "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 24},
+    "clear_env_small": {"outer_boundary": [[-6.0, -6.0], [-6.0, 6.0], [6.0, 6.0], [6.0, -6.0]],
+                        "boundary": [[-4.0, -4.0], [-4.0, 4.0], [4.0, 4.0], [4.0, -4.0]],
+                        "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 12},
 }
 
 DEFAULT_CFG = {   # area_clearing/config.yaml (keys that reach the hot path)

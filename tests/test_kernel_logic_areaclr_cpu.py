@@ -55,3 +55,20 @@ def test_clearing_a_box_resets_the_clock_and_marks_it_completed(portable_trig):
     assert counts == [0, 0, 1, 1, 1, 1] and ts[2] == 0 and ts[3] == 1            # D13: the truncation clock restarts when a box is cleared
     assert float(env._buf["reward"][0]) == -0.25                                  # pressed against the outer wall: BOUNDARY_PENALTY
     env.close()
+
+
+def test_small_environment_matches_the_oracle(portable_trig):
+    """clear_env_small: 12 m room, 8 m clearance square, 18.67 px / m, 542 x 542 grid."""
+    cfg = {"env": "clear_env_small", "num_obstacles": 6, "min_obs_dist": 1.2}
+    lay = [sample_layout(random.Random(4), cfg)]
+    env = AreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=lay, _backend=emu_bd.lib())
+    ora = AreaClearingOracleEnv(cfg=cfg, layouts=lay)
+    obs, info = env.reset()
+    oobs, oinfo = ora.reset()
+    assert env.room.shape == (542, 542) and np.array_equal(env.goal_point_global_map, ora.goal_point_global_map)
+    assert np.array_equal(obs[0], oobs)
+    rng = np.random.default_rng(4)
+    for k in range(5):
+        a = float(np.float32(rng.uniform(-1, 1)))
+        compare_step(env, ora, 0, a, env.step(np.array([a], dtype=np.float32)), state_tol=1e-9)
+    env.close()
