@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(128, BD_MOVE_MINB) k_bd_reset(const BdConst* C
 __global__ void k_bd_begin(const BdConst* C, const float* actions, const uint8_t* mask) {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= C->n_envs || (mask && !mask[env])) return;
-    bd_begin_step(*C, bd_env(*C, env), (double)actions[env]);
+    if (C->P.action_type == 2) bd_begin_step(*C, bd_env(*C, env), (double)actions[2 * env], (double)actions[2 * env + 1]);
+    else bd_begin_step(*C, bd_env(*C, env), (double)actions[env]);
 }
 
 // block per (env, item) pulled from a counter; item k < NB: box distance, k == NB: robot path (phase 0)
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(128) k_mv_init(const BdConst* C, const uint8_t
     if (env >= C->n_envs || (threadIdx.x & 31)) return;
     MoveVars& v = mv[env];
     bool part = !(mask && !mask[env]);
-    v.state = part ? MV_EXEC : MV_DONE;
+    v.state = part ? (C->P.action_type == 2 ? MV_VEL : MV_EXEC) : MV_DONE;
     if (!part) return;
     BdEnv* E = bd_env(*C, env);
     bd_finalize_path(*C, E);
@@ -205,7 +206,7 @@ void bp_boxdel_default_config(bp_boxdel_config* c) {
 int bp_boxdel_create(const bp_boxdel_config* cfg, bp_boxdel_t** out) {
     if (!cfg || !out) return fail(BP_ERR_INVALID, "null argument");
     if (cfg->n_envs <= 0 || cfg->num_boxes <= 0 || cfg->num_boxes > MAXBOX) return fail(BP_ERR_INVALID, "n_envs / num_boxes out of range");
-    if (cfg->action_type != 0 && cfg->action_type != 1) return fail(BP_ERR_INVALID, "action_type must be 0 (position) or 1 (heading)");
+    if (cfg->action_type < 0 || cfg->action_type > 2 || (cfg->action_type == 2 && cfg->env_kind != 0)) return fail(BP_ERR_INVALID, "action_type must be 0 (position), 1 (heading) or 2 (velocity, box-delivery only)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(BP_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
     CUDA_TRY(cudaSetDevice(cfg->device));
@@ -425,8 +426,9 @@ int bp_boxdel_step_host(bp_boxdel_t* h, const float* actions, const bp_boxdel_ou
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const int E = h->cfg.n_envs, NB = h->cfg.num_boxes;
     const size_t obs_b = (size_t)E * h->hC.P.LW * h->hC.P.LW * 4;
-    float* d_act = nullptr; CUDA_TRY(cudaMalloc((void**)&d_act, 4 * (size_t)E));
-    CUDA_TRY(cudaMemcpy(d_act, actions, 4 * (size_t)E, cudaMemcpyHostToDevice));
+    const size_t act_b = 4 * (size_t)E * (h->cfg.action_type == 2 ? 2 : 1);
+    float* d_act = nullptr; CUDA_TRY(cudaMalloc((void**)&d_act, act_b));
+    CUDA_TRY(cudaMemcpy(d_act, actions, act_b, cudaMemcpyHostToDevice));
     bp_boxdel_outputs d; memset(&d, 0, sizeof(d));
     struct Item { void** dev; void* host; size_t bytes; };
     Item items[8] = {{(void**)&d.obs, out_host->obs, obs_b}, {(void**)&d.reward, out_host->reward, 8 * (size_t)E},

@@ -145,13 +145,23 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
 
 // ------------------------------------------------------------------ step, part 1: action -> target, straight-line test
 // Scalar; run by one lane.  action: pixel index (position control) or heading in [-1, 1].
-BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action) {
+BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action, double action2 = 0.0) {
     const BdParams& P = C.P;
     E->t++;
     E->robot_hit = 0;
     const BdBody& R = E->body[0];
     double x0 = R.px, y0 = R.py, h0 = restrict_heading(R.pa);
     E->init_pos[0] = x0; E->init_pos[1] = y0; E->init_heading = h0;
+    if (P.action_type == 2) {
+        // velocity control (box_delivery_env.py:667-700): action = float32 (linear, angular); |linear| is clamped to target_speed
+        // in float32 arithmetic (python float * np.float32 scalar -> float32 under NumPy >= 2 promotion)
+        float lin = (float)action;
+        if (fabsf(lin) >= (float)P.target_speed) lin = (float)P.target_speed * (float)sgn((double)lin);
+        E->tgt[0] = (double)lin; E->tgt[1] = action2;
+        E->n_path = 0; E->need_spfa = 0; E->move_sign = 1;
+        if (P.kind == 0 && P.recept_visible) bd_box_dists_visible(C, E, E->cold->init_dist);
+        return;
+    }
     long long spatial;
     const int LW = P.LW;
     if (P.action_type == 1) {
@@ -265,6 +275,7 @@ BP_DEV int bd_extract_path(const BdConst& C, const int* dist, int si, int sj, in
 // ------------------------------------------------------------------ waypoint headings, final-waypoint back-off
 BP_DEV void bd_finalize_path(const BdConst& C, BdEnv* E) {
     int n = E->n_path;
+    if (n < 2) return;          // velocity control: no path
     double (*wp)[3] = E->cold->path;
     wp[0][2] = 0.0;   // None
     for (int i = 1; i < n; i++) wp[i][2] = restrict_heading(atan2(wp[i][1] - wp[i - 1][1], wp[i][0] - wp[i - 1][0]));
@@ -331,7 +342,7 @@ BP_DEVNI void bd_controller(const BdConst& C, BdEnv* E, BdLoop& LS, int wi, doub
 #ifndef BD_MOVE_K
 #define BD_MOVE_K 1
 #endif
-enum { MV_EXEC = 0, MV_STILL = 1, MV_POST = 2, MV_DONE = 3 };
+enum { MV_EXEC = 0, MV_STILL = 1, MV_POST = 2, MV_DONE = 3, MV_VEL = 4 };
 struct MoveVars {
     int state, wi, sim_steps, post_k, n, done_turning, have_prev, still_done;
     double pos_x, pos_y, heading, robot_distance, prev_heading_diff, hd;
@@ -349,6 +360,15 @@ BP_DEVNI void mv_pre(const BdConst& C, BdEnv* E, MoveVars& V) {
             V.hd = hd;
             if (!(fabs(hd) > TURN_STEP_SIZE && fabs(hd - V.prev_heading_diff) > 0.001)) V.done_turning = 1;
             bd_controller(C, E, V.LS, V.wi, V.pos_x, V.pos_y, V.heading, V.done_turning != 0);
+        }
+        bp_wsync();
+    } else if (V.state == MV_VEL) {
+        if (lane == 0) {
+            // the robot keeps moving in the direction it is facing (box_delivery_env.py:687-690)
+            BdBody& R = E->body[0];
+            double ch = cos(R.pa), sh = sin(R.pa);
+            R.vw = E->tgt[1];
+            R.vx = ch * E->tgt[0] + (-sh) * 0.0; R.vy = sh * E->tgt[0] + ch * 0.0;
         }
         bp_wsync();
     } else if (V.state == MV_STILL) {
@@ -416,6 +436,13 @@ BP_DEVNI void mv_post(const BdConst& C, BdEnv* E, MoveVars& V) {
                 // area-clearing: a fixed number of substeps follows the path (area_clearing.py:692-693); box-delivery: until still
                 V.state = (P.kind == 1) ? (P.post_steps > 0 ? MV_POST : MV_DONE) : MV_STILL;
             }
+        } else if (V.state == MV_VEL) {
+            V.sim_steps++;
+            if (E->robot_hit || V.sim_steps >= P.post_steps) {
+                E->robot_distance = dist2(E->init_pos[0], E->init_pos[1], E->body[0].px, E->body[0].py);
+                V.sim_steps = 0;
+                V.state = MV_STILL;
+            }
         } else if (V.state == MV_STILL) {
             // the reference steps once more after deciding that everything is still (:1007-1019)
             if (V.still_done) V.state = MV_DONE;
@@ -450,7 +477,7 @@ BP_DEVNI void bd_move(const BdConst& C, int env0, int nk, const uint8_t* mask, M
         bp_wsync();
         if (lane == 0) {
             MoveVars& v = V[k];
-            v.state = part ? MV_EXEC : MV_DONE;
+            v.state = part ? (C.P.action_type == 2 ? MV_VEL : MV_EXEC) : MV_DONE;
             if (part) {
                 BdEnv* E = Es[k];
                 bd_finalize_path(C, E);

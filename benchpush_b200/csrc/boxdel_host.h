@@ -46,7 +46,8 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
     P.nonmove_penalty = c.non_movement_penalty; P.correct_scale = c.correct_direction_reward_scale; P.ministep = c.ministep_size;
     P.use_correct = c.use_correct_direction_reward; P.inactivity_cutoff = c.inactivity_cutoff; P.num_boxes = c.num_boxes; P.action_type = c.action_type;
     P.sp_div = (std::sqrt(2.0) * P.LW) / P.ppm; P.sp_scale = c.shortest_path_channel_scale;
-    P.kind = c.env_kind; P.step_limit = c.step_limit; P.post_steps = c.post_steps; P.t_max = c.t_max;
+    P.kind = c.env_kind; P.step_limit = c.step_limit; P.post_steps = (c.env_kind == 0) ? c.steps : c.post_steps;   // box-delivery velocity control runs cfg.sim.steps substeps
+    P.t_max = c.t_max;
     P.lfc = c.lfc; P.omega_mul = c.omega_mul; P.v_mul = c.v_mul; P.bound_x = c.bound_x; P.bound_y = c.bound_y;
     P.robot_code = c.robot_code; P.box_code = c.box_code; P.box_done_code = c.box_done_code; P.draw_recept = (c.env_kind == 0);
     if (c.n_boundary < 0 || c.n_boundary > 8 || c.n_goals < 0 || c.n_goals > 64) return std::string("n_boundary / n_goals out of range");

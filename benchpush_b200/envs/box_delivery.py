@@ -12,7 +12,7 @@ library calls as the reference (cv2.fillPoly, scipy binary_dilation with a disk 
 distance_transform_edt).  They depend on the room only, so all envs of a handle share them.
 
 Implemented: ``obstacle_config: small_empty`` (any room size without columns / dividers), ``action_type``
-``heading`` and ``position``.  ``velocity`` control, ``low_dim_state`` and the column / divider rooms raise
+``heading``, ``position`` and ``velocity`` (actions ``float32[B, 2]``).  ``low_dim_state`` and the column / divider rooms raise
 NotImplementedError.
 """
 from __future__ import annotations
@@ -204,8 +204,8 @@ class BoxDeliveryVecEnv:
         c = self.cfg
         if c["env"]["obstacle_config"] not in ("small_empty", "large_empty"):
             raise NotImplementedError("only the rooms without columns / dividers are implemented (obstacle_config small_empty)")
-        if c["agent"]["action_type"] not in ("heading", "position"):
-            raise NotImplementedError("action_type 'velocity' is not implemented")
+        if c["agent"]["action_type"] not in ("heading", "position", "velocity"):
+            raise NotImplementedError("unknown action_type %r" % (c["agent"]["action_type"],))
         if c["low_dim_state"] or c["teleop_mode"]:
             raise NotImplementedError("low_dim_state / teleop_mode are not implemented")
         if tuple(c["sim"]["gravity"]) != (0, 0):
@@ -241,7 +241,8 @@ class BoxDeliveryVecEnv:
         rw = c["rewards_sam"] if c["train"]["job_type"] == "sam" else c["rewards"]
         k.force_box_spfa = 1 if force_box_spfa else 0      # testing aid: solve spfa per box even when the exact shortcut applies
         k.n_envs = E; k.num_boxes = NB; k.device = self.device_index
-        k.action_type = 1 if c["agent"]["action_type"] == "heading" else 0
+        k.action_type = {"position": 0, "heading": 1, "velocity": 2}[c["agent"]["action_type"]]
+        self._action_dim = 2 if k.action_type == 2 else 1
         k.steps = int(c["sim"]["steps"]); k.iterations = int(c["sim"]["iterations"]); k.settle_steps = 1000
         k.inactivity_cutoff = int(c["misc"]["inactivity_cutoff"] if c["train"]["job_type"] != "sam" else c["misc"]["inactivity_cutoff_sam"])
         k.local_map_pixel_width = LW; k.use_correct_direction_reward = 1 if c["train"]["use_correct_direction_reward"] else 0
@@ -294,7 +295,7 @@ class BoxDeliveryVecEnv:
         self._alloc("terminated", (E,), "uint8"); self._alloc("truncated", (E,), "uint8")
         self._alloc("info", (E, 8), "float64"); self._alloc("info_i", (E, 4), "int32")
         self._alloc("completed", (E, NB), "uint8"); self._alloc("box_verts", (E, NB, 4, 2), "float64")
-        self._alloc("actions", (E,), "float32"); self._alloc("layout_ids", (E,), "int32"); self._alloc("mask", (E,), "uint8")
+        self._alloc("actions", (E,) if getattr(self, "_action_dim", 1) == 1 else (E, 2), "float32"); self._alloc("layout_ids", (E,), "int32"); self._alloc("mask", (E,), "uint8")
         o = BoxDelOutputs()
         for n in ("obs", "reward", "terminated", "truncated", "info", "info_i", "completed", "box_verts"):
             setattr(o, n, self._ptr(n))

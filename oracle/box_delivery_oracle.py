@@ -832,12 +832,31 @@ class BoxDeliveryOracleEnv:
         for k, b in enumerate(self.box_bodies):
             initial[self.box_idx[k]] = self.shortest_path_distance(list(self.space.body(b)[:2]), self.receptacle_position)
         at = self.cfg["agent"]["action_type"]
-        assert at in ("position", "heading")
-        if at == "heading":
-            action = self.heading_to_pixel_action(float(np.asarray(action).reshape(-1)[0]))
-        self.path, move_sign = self.get_waypoints_to_spatial_action(p_init, h_init, int(action))
-        self.last_path = [list(p) for p in self.path]
-        robot_distance, robot_turn_angle = self.execute_robot_path(p_init, h_init, move_sign)
+        assert at in ("position", "heading", "velocity")
+        if at == "velocity":
+            # box_delivery_env.py:667-700; the policy's action is a float32 array (action_space dtype)
+            action = np.asarray(action, dtype=np.float32)
+            linear_speed, angular_speed = action[0], action[1]
+            if abs(linear_speed) >= self.target_speed:
+                linear_speed = self.target_speed * np.sign(linear_speed)
+            self.space.set_angular_velocity(self.robot_body, float(angular_speed))
+            for _ in range(self.steps):
+                _, ang_now = self.robot_pose()
+                gv = R(ang_now) @ [linear_speed, 0]
+                self.space.set_velocity(self.robot_body, float(gv[0]), float(gv[1]))
+                self.space.step(self.dt / self.steps)
+                self.n_substeps += 1
+                if self.space.robot_hit() == 1:
+                    break
+            pos, _ = self.robot_pose()
+            robot_distance = distance(p_init, pos)
+            self.last_path = []
+        else:
+            if at == "heading":
+                action = self.heading_to_pixel_action(float(np.asarray(action).reshape(-1)[0]))
+            self.path, move_sign = self.get_waypoints_to_spatial_action(p_init, h_init, int(action))
+            self.last_path = [list(p) for p in self.path]
+            robot_distance, robot_turn_angle = self.execute_robot_path(p_init, h_init, move_sign)
         self.step_simulation_until_still()
         final = {}
         for k, b in enumerate(self.box_bodies):

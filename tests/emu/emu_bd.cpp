@@ -143,7 +143,8 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
     for (int e = 0; e < n; e++) {
         if (mask && !mask[e]) continue;
         BdEnv* E = bd_env(K, e);
-        bd_begin_step(K, E, (double)actions[e]);
+        if (K.P.action_type == 2) bd_begin_step(K, E, (double)actions[2 * e], (double)actions[2 * e + 1]);
+        else bd_begin_step(K, E, (double)actions[e]);
         for (int k = 0; k <= K.P.NB; k++) bd_dist_item(S, K, E, k, 0, h->scratch.data());
     }
     // as the kernel: one "warp" per BD_MOVE_K consecutive envs, phase-major

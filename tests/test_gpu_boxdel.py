@@ -139,3 +139,21 @@ def test_phase_per_kernel_loop_equals_the_fused_loop(monkeypatch):
     for e in (0, 7, 15):
         assert np.array_equal(a.get_bodies(e), b.get_bodies(e))
     a.close(); b.close()
+
+
+def test_velocity_actions_match_the_oracle(portable_trig):
+    from oracle.box_delivery_oracle import BoxDeliveryOracleEnv
+    cfg = dict(DELIVERY_CFG, agent={"action_type": "velocity"})
+    env = _mk(cfg, [DELIVERY_LAYOUT], 1)
+    ora = BoxDeliveryOracleEnv(cfg=cfg, layouts=[DELIVERY_LAYOUT])
+    env.reset(); ora.reset()
+    for act in ([0.25, 0.1], [0.9, -0.4], [-0.2, 0.0]):
+        a = np.array([act], dtype=np.float32)
+        out = env.step(a)
+        oobs, orr, oterm, otrunc, oinfo = ora.step(a[0])
+        gb = env.get_bodies(0); ob = ora.space.state()
+        alive = gb[1:, 6] == 1
+        assert np.abs(gb[0, :3] - ob[0, :3]).max() <= 1e-8 and np.abs(gb[1:][alive][:, :3] - ob[list(ora.box_bodies)][:, :3]).max() <= 1e-8
+        assert abs(float(out[1][0]) - orr) <= 1e-8 and env.get_step_debug(0)["substeps"] == 1000 + ora.n_substeps
+        assert int((out[0][0].cpu().numpy() != oobs).sum()) <= 4
+    env.close()

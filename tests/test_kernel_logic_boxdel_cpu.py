@@ -110,3 +110,20 @@ def test_envs_of_a_batch_are_independent(portable_trig):
     both.step(np.array([0.1, 0.1], dtype=np.float32), mask=np.array([0, 1], dtype=np.uint8))
     assert np.array_equal(both.get_bodies(0), before)
     both.close(); one.close()
+
+
+def test_velocity_actions_match_the_oracle(portable_trig):
+    cfg = dict(DELIVERY_CFG, agent={"action_type": "velocity"})
+    env, ora = _pair(cfg, [DELIVERY_LAYOUT])
+    env.reset(); ora.reset()
+    for act in ([0.25, 0.1], [0.9, -0.4], [-0.2, 0.0], [0.3, 0.2]):
+        a = np.array([act], dtype=np.float32)
+        out = env.step(a)
+        oobs, orr, oterm, otrunc, oinfo = ora.step(a[0])
+        gb = env.get_bodies(0); ob = ora.space.state()
+        alive = gb[1:, 6] == 1
+        assert np.abs(gb[0, :3] - ob[0, :3]).max() <= 1e-9 and np.abs(gb[1:][alive][:, :3] - ob[list(ora.box_bodies)][:, :3]).max() <= 1e-9
+        assert abs(float(out[1][0]) - orr) <= 1e-9 and env.get_step_debug(0)["substeps"] == 1000 + ora.n_substeps
+        assert abs(float(out[4]["cumulative_distance"][0]) - oinfo["cumulative_distance"]) <= 1e-9
+        assert int((out[0][0] != oobs).sum()) <= 4
+    env.close()
