@@ -353,6 +353,8 @@ class BoxDeliveryVecEnv:
     # ---- gym API
     def reset(self, seed=None, options=None, mask=None):
         """Every env (or those in ``mask``) starts episode ``episode_idx`` on layout (env + episode * num_envs) % n_layouts."""
+        if mask is not None and not self._emu and hasattr(mask, "cpu"):
+            mask = mask.to("cpu").numpy()
         self.episode_idx = 0 if self.episode_idx is None else self.episode_idx + 1
         ids = (np.arange(self.num_envs) + self.episode_idx * self.num_envs) % len(self.layouts)
         self._put("layout_ids", ids.astype(np.int32))
@@ -407,6 +409,31 @@ class BoxDeliveryVecEnv:
 
     def launch_count(self):
         return int(self._L.bp_boxdel_launch_count(self._h))
+
+    def low_dim_observation(self):
+        """``generate_observation_low_dim`` (box_delivery_env.py:1025-1037, area_clearing.py:908-920), batched: for every box left,
+        ``np.abs(poly_centroid(vertices))`` (x, y) in list order; zero padded to ``2 * num_boxes``.  Computed from ``info['obs']``."""
+        v = self._buf["box_verts"]
+        n = self._buf["info_i"][:, 2]
+        if self._emu:
+            x, y = v[..., 0], v[..., 1]
+            xp, yp = np.roll(x, 1, axis=2), np.roll(y, 1, axis=2)
+            A = 0.5 * np.abs((x * yp).sum(2) - (y * xp).sum(2))
+            u = x * yp - xp * y
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cx = np.abs(((x + xp) * u).sum(2) / (6 * A)); cy = np.abs(((y + yp) * u).sum(2) / (6 * A))
+            valid = np.arange(self.num_boxes)[None, :] < n[:, None]
+            out = np.stack([np.where(valid, cx, 0.0), np.where(valid, cy, 0.0)], axis=2)
+            return out.reshape(self.num_envs, 2 * self.num_boxes)
+        import torch
+        x, y = v[..., 0], v[..., 1]
+        xp, yp = torch.roll(x, 1, dims=2), torch.roll(y, 1, dims=2)
+        A = 0.5 * ((x * yp).sum(2) - (y * xp).sum(2)).abs()
+        u = x * yp - xp * y
+        cx = (((x + xp) * u).sum(2) / (6 * A)).abs(); cy = (((y + yp) * u).sum(2) / (6 * A)).abs()
+        valid = torch.arange(self.num_boxes, device=v.device)[None, :] < n[:, None]
+        zero = torch.zeros((), dtype=v.dtype, device=v.device)
+        return torch.stack([torch.where(valid, cx, zero), torch.where(valid, cy, zero)], dim=2).reshape(self.num_envs, 2 * self.num_boxes)
 
     # ---- parity / debugging aids
     def get_bodies(self, e: int) -> np.ndarray:

@@ -84,3 +84,27 @@ def test_single_env_views_return_the_reference_types():
         m.update(i1, rr, eps_complete=(k == 2))
     assert m.success_rates == [1 / 3] and 0 < m.efficiency_scores[0] and 0 < m.effort_scores[0] <= 1.0 + 1e-9
     ac.close()
+
+
+def test_low_dim_observation_and_batched_evaluate():
+    from oracle.raster_oracle import poly_centroid
+    from benchpush_b200.evaluate import evaluate
+    from tests.areaclr_common import CLEARING_CFG, CLEARING_LAYOUT
+    env = BoxDeliveryVecEnv(num_envs=1, cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT], _backend=emu_bd.lib())
+    obs, info = env.reset()
+    for _ in range(2):
+        obs, r, te, tr, info = env.step(np.array([-1.0], dtype=np.float32))
+    ld = env.low_dim_observation()
+    assert ld.shape == (1, 8) and np.all(ld[0, 6:] == 0)              # one box delivered: 3 left, zero padded
+    ref = np.concatenate([np.abs(poly_centroid(info["obs"][0, k])) for k in range(3)])
+    assert np.allclose(ld[0, :6], ref, atol=1e-12)
+    env.close()
+    # batched evaluate(): two area-clearing envs, each episode ends by truncation after t_max = 2 steps
+    from benchpush_b200.envs.area_clearing import AreaClearingVecEnv
+    cfg = dict(CLEARING_CFG, sim={"t_max": 2})
+    ac = AreaClearingVecEnv(num_envs=2, cfg=cfg, layouts=[CLEARING_LAYOUT, CLEARING_LAYOUT], _backend=emu_bd.lib())
+    m = TaskDrivenMetric("t", robot_mass=1)
+    res = evaluate(ac, lambda o: np.array([-1.0, -1.0], dtype=np.float32), m, num_episodes=4)
+    assert len(res["rewards"]) == 4 and len(res["efficiency_scores"]) == 4 and res["success_rates"] == [0.0] * 4
+    assert res["rewards"][0] == res["rewards"][1] == res["rewards"][2]   # identical layouts and actions: identical episodes, also after the masked reset
+    ac.close()
