@@ -57,6 +57,7 @@ class ShipIceVecEnv:
             raise NotImplementedError("cfg.random_start is not implemented: start poses come from the layouts")
         assert self.cfg.concentration in [0.1, 0.2, 0.3, 0.4, 0.5], "concentration must be one of 0.1 .. 0.5 (ship_ice_env.py:75)"
         self.num_envs = int(num_envs)
+        self.auto_reset = bool(auto_reset)
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         self.goal = (0, self.cfg.goal_y)

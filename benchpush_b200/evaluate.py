@@ -26,7 +26,7 @@ def evaluate(env, policy, metric, num_episodes: int, max_steps: int = 100000):
         done_t = (term | trunc) if hasattr(term, "device") else done
         metric.update(info, rew, eps_complete=done_t)
         if done.any() and not auto:
-            obs, info = env.reset(mask=done.astype(np.uint8))
+            obs, info = env.reset(mask=done_t if hasattr(done_t, "device") else done.astype(np.uint8))
             metric.reset(info, mask=done_t)
     n = num_episodes
     return {"success_rates": list(getattr(metric, "success_rates", []) or getattr(metric, "successes", []))[:n],

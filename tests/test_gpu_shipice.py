@@ -196,3 +196,18 @@ def test_no_cpu_fallback_errors():
     with pytest.raises(_lib.BenchPushError):
         trials = generate_experiment(1, 0.1, seed=1)
         ShipIceVecEnv(num_envs=1, cfg={"concentration": 0.1}, layouts=pack_trials(trials), device=99)
+
+
+def test_batched_evaluate_loop(golden_layouts):
+    """benchpush_b200.evaluate.evaluate on ship-ice: explicit masked resets, one score per finished episode."""
+    import torch
+    from benchpush_b200.envs import ShipIceVecEnv
+    from benchpush_b200.evaluate import evaluate
+    from benchpush_b200.metrics import ShipIceMetric
+    env = ShipIceVecEnv(num_envs=3, cfg={"concentration": 0.1}, layouts=golden_layouts["c10_t0"], device=0)
+    m = ShipIceMetric("straight", ship_mass=env.cfg.ship.mass, goal=env.goal)
+    res = evaluate(env, lambda obs: torch.zeros(3, dtype=torch.float32, device=obs.device), m, num_episodes=3, max_steps=80)
+    assert len(res["rewards"]) == 3 and len(res["efficiency_scores"]) == 3
+    assert all(0.0 <= e <= 1.0 + 1e-9 for e in res["effort_scores"])
+    assert res["rewards"][0] == res["rewards"][1] == res["rewards"][2]       # same layout, same actions
+    env.close()
