@@ -12,7 +12,23 @@
 #include "host_tables.h"
 #include "raster.cuh"
 #include "maze_raster.cuh"
+// the batched ship-ice / maze step, instantiated for 8 and for 4 envs per warp (sim_batch.cuh)
+#ifdef BP_BK
+#define BP_BK_MAIN BP_BK
+#undef BP_BK
+#else
+#define BP_BK_MAIN 8
+#endif
+#define BP_BK BP_BK_MAIN
+#define BP_BATCH_NS bk_main
 #include "sim_batch.cuh"
+#undef BP_BK
+#undef BP_BATCH_NS
+#define BP_BK 4
+#define BP_BATCH_NS bk_small
+#include "sim_batch.cuh"
+#undef BP_BK
+#undef BP_BATCH_NS
 #include "spfa.cuh"
 
 using namespace bp;
@@ -90,19 +106,22 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepAr
 }
 
 // Batched step: each warp claims BK consecutive envs and advances them together (sim_batch.cuh).
-__global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step(StepArgs a) {
-    __shared__ BatchShared SH[4];
-    BatchShared& S = SH[threadIdx.x >> 5];
-    load_shared_offsets(a.C->off);
-    for (;;) {
-        int env0 = 0;
-        if ((threadIdx.x & 31) == 0) env0 = atomicAdd(a.counter, BK);
-        env0 = __shfl_sync(0xffffffffu, env0, 0);
-        if (env0 >= a.d.n_envs) break;
-        shipice_step_batch(a.C, S, a.mem, a.env_bytes, env0, a.actions, a.mask, a.out, a.auto_reset);
-        __syncwarp();
+#define BP_DEFINE_STEP_KERNEL(NAME, NS)                                                                         \
+    __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) NAME(StepArgs a) {                                    \
+        __shared__ NS::BatchShared SH[4];                                                                        \
+        NS::BatchShared& S = SH[threadIdx.x >> 5];                                                               \
+        load_shared_offsets(a.C->off);                                                                           \
+        for (;;) {                                                                                               \
+            int env0 = 0;                                                                                        \
+            if ((threadIdx.x & 31) == 0) env0 = atomicAdd(a.counter, NS::BK);                                    \
+            env0 = __shfl_sync(0xffffffffu, env0, 0);                                                            \
+            if (env0 >= a.d.n_envs) break;                                                                       \
+            NS::shipice_step_batch(a.C, S, a.mem, a.env_bytes, env0, a.actions, a.mask, a.out, a.auto_reset);    \
+            __syncwarp();                                                                                        \
+        }                                                                                                        \
     }
-}
+BP_DEFINE_STEP_KERNEL(k_shipice_step, bk_main)
+BP_DEFINE_STEP_KERNEL(k_shipice_step_small, bk_small)
 
 struct ObsArgs {
     char* mem; size_t env_bytes; Dims d; LayoutTab T; ObsParams O;
@@ -434,11 +453,16 @@ static int sim_grid(bp_shipice* h) {
     return blocks < need ? blocks : need;
 }
 
+// envs per warp for this handle: the small instantiation when the batch cannot fill the resident warps of the GPU with 8 per warp
+static bool use_small_batches(bp_shipice* h) {
+    if (const char* e = getenv("BP_FORCE_BK")) return atoi(e) == bk_small::BK;       // tuning experiments only
+    return (long)h->d.n_envs * 2 <= (long)h->sm_count * BP_MIN_BLOCKS * 4 * bk_main::BK;
+}
 static int batch_grid(bp_shipice* h) {
     // 4 warps per block, BK envs per warp batch; never more warps than batches
     int blocks = h->sm_count * BP_MIN_BLOCKS;
     if (const char* e = getenv("BP_BLOCKS_PER_SM")) { int b = atoi(e); if (b > 0 && b < BP_MIN_BLOCKS) blocks = h->sm_count * b; }   // tuning experiments only
-    int per_block = 4 * BK;
+    int per_block = 4 * (use_small_batches(h) ? bk_small::BK : bk_main::BK);
     int need = (h->d.n_envs + per_block - 1) / per_block;
     return blocks < need ? blocks : need;
 }
@@ -472,6 +496,7 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
     a.actions = actions; a.layout_ids = nullptr; a.mask = mask; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset; a.C = h->d_const; a.use_snap = h->snap ? 1 : 0;
     prof_begin(h, 0, st);
     if (h->warp_impl) k_shipice_step_warp<<<sim_grid(h), 128, 0, st>>>(a);
+    else if (use_small_batches(h)) k_shipice_step_small<<<batch_grid(h), 128, 0, st>>>(a);
     else k_shipice_step<<<batch_grid(h), 128, 0, st>>>(a);
     prof_end(h, st);
     h->launches++;

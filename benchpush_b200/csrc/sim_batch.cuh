@@ -11,14 +11,21 @@
 // order, and envs never share memory.  Rare per-env events (neighbour-list rebuild, wake closure,
 // cache expiry, recolouring, sleep) reuse the warp-cooperative routines of sim_step.cuh, one env at
 // a time.
-#pragma once
+// This header may be included more than once with different (BP_BK, BP_BATCH_NS): the library carries the batched step for
+// BK = 8 (full GPUs) and BK = 4 (the small per-GPU batches of the 8-GPU strong-scaling point: more warps for the same envs;
+// measured +22 % at 8 192 envs, equal at 16 384 — profiles/r01f_shipice_bk_small_batches.txt).  Results do not depend on BK.
 #include "maze_env.cuh"
-
-namespace bp {
 
 #ifndef BP_BK
 #define BP_BK 8
 #endif
+#ifndef BP_BATCH_NS
+#define BP_BATCH_NS bk_default
+#endif
+
+namespace bp {
+namespace BP_BATCH_NS {
+
 constexpr int BK = BP_BK;        // envs per warp batch
 constexpr int BQ = 256;          // per-warp narrowphase queue (entries)
 constexpr int BQE = 96;          // per-warp EPA queue
@@ -528,4 +535,5 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
     }
 }
 
+}  // namespace BP_BATCH_NS
 }  // namespace bp

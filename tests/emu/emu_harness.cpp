@@ -14,6 +14,7 @@
 #include "../../benchpush_b200/csrc/spfa.cuh"
 
 using namespace bp;
+using namespace bp::bk_default;      // sim_batch.cuh, single instantiation
 
 struct Emu {
     Dims d; SimParams P; HostLayouts H; LayoutTab T;
