@@ -147,6 +147,25 @@ __global__ void __launch_bounds__(256) k_shipice_obs(ObsArgs a) {
     }
 }
 
+// cfg.egocentric_obs = false: the 2 x grid_h x grid_w observation (raster.cuh: render_obs_global), one block per env
+__global__ void __launch_bounds__(256) k_shipice_obs_global(ObsArgs a) {
+    __shared__ ObsGlobalSmem S;
+    int env = blockIdx.x;
+    if (a.mask && !a.mask[env]) return;
+    EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
+    const EnvScal* sc = ev.sc;
+    LayoutView L = layout_view(a.T, a.d, sc->layout);
+    int r = sc->robot;
+    V2 o = body_origin(ev, L, r);
+    uint8_t* out = a.obs + (size_t)env * 2 * a.O.grid_h * a.O.grid_w;
+    if (sc->obs_raw) {
+        size_t base = (size_t)sc->layout * a.d.NB;
+        render_obs_global(S, a.O, r, a.rawv + base * VMAX * 2, VMAX * 2, a.rawn + base, o.x, o.y, ev.body[r].pa, out);
+    } else {
+        render_obs_global(S, a.O, r, ev.wv, VMAX * 2, L.nv, o.x, o.y, ev.body[r].pa, out);
+    }
+}
+
 struct MazeObsArgs {
     char* mem; size_t env_bytes; Dims d; LayoutTab T; MazeObsParams O;
     const double* rawv; const int* rawn; const uint8_t* mask; uint8_t* obs;
@@ -189,6 +208,42 @@ __global__ void __launch_bounds__(512) k_spfa(const uint8_t* maps, const int32_t
         if (m >= batch) break;
         spfa_block(S, maps + m * nv, H, W, sources[2 * m], sources[2 * m + 1], dists + m * nv, parents + m * nv, q0, q0 + nv, q0 + 2 * nv);
     }
+}
+
+// generate_observation_low_dim (ship_ice_env.py:358-370; maze_NAMO_env.py:488-504): |poly_centroid| of every movable
+// polygon in creation order.  One warp per env: the |centroid| cache of the env block (cenx / ceny: refreshed by
+// step_work for every body that moved, set at reset) is compacted over the dynamic bodies below the robot.
+// maze = 1: <robot_x, robot_y> first, and — as the reference's loop starts at index 1 — obstacle 0 is never written
+// and the last pair stays 0.
+struct LowDimArgs { char* mem; size_t env_bytes; Dims d; LayoutTab T; double* out; int32_t* counts; int stride; int maze; };
+
+__global__ void __launch_bounds__(128) k_low_dim(LowDimArgs a) {
+    const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (env >= a.d.n_envs) return;
+    const int lane = threadIdx.x & 31;
+    EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
+    const EnvScal* sc = ev.sc;
+    LayoutView L = layout_view(a.T, a.d, sc->layout);
+    const int r = sc->robot;
+    double* row = a.out + (size_t)env * a.stride;
+    int n = 0;                                       // movable polygons seen so far (warp-uniform)
+    for (int b0 = 0; b0 < r; b0 += 32) {
+        int b = b0 + lane;
+        bool dyn = b < r && body_dynamic(L, b);
+        unsigned m = __ballot_sync(0xffffffffu, dyn);
+        if (dyn) {
+            int i = n + __popc(m & ((1u << lane) - 1u));
+            if (!(a.maze && i == 0)) { row[2 * i] = ev.cenx[b]; row[2 * i + 1] = ev.ceny[b]; }
+        }
+        n += __popc(m);
+    }
+    const int used = a.maze ? 2 * (n + 1) : 2 * n;
+    if (a.maze) {
+        if (lane == 0) { V2 o = body_origin(ev, L, r); row[0] = o.x; row[1] = o.y; }
+        if (lane == 1 && n > 0) { row[2 * n] = 0.0; row[2 * n + 1] = 0.0; }
+    }
+    for (int k = used + lane; k < a.stride; k += 32) row[k] = 0.0;
+    if (lane == 0 && a.counts) a.counts[env] = used;
 }
 
 // ------------------------------------------------------------------------------------------------ handle
@@ -444,6 +499,17 @@ static int launch_obs(bp_shipice* h, uint8_t* obs, const uint8_t* mask, cudaStre
     return BP_OK;
 }
 
+
+static int launch_low_dim(bp_shipice* h, double* out, int32_t* counts, int maze, cudaStream_t st) {
+    LowDimArgs la;
+    la.mem = h->mem; la.env_bytes = h->env_bytes; la.d = h->d; la.T = h->T; la.out = out; la.counts = counts; la.maze = maze;
+    la.stride = maze ? 2 * (h->max_boxes + 1) : 2 * h->cfg.max_floes;
+    k_low_dim<<<(h->d.n_envs + 3) / 4, 128, 0, st>>>(la);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BP_OK;
+}
+
 static int sim_grid(bp_shipice* h) {
     // 4 warps per block, 32 / BP_NL envs per warp; enough resident blocks to fill the SMs, never more groups than envs
     int blocks = h->sm_count * BP_MIN_BLOCKS;
@@ -548,6 +614,31 @@ static LayoutView host_layout_view(bp_shipice* h, int l) {
     L.lv = T.lv + o * VMAX * 2; L.ln = T.ln + o * VMAX * 2; L.nv = T.nv + o; L.rad = T.rad + o; L.rbound = T.rbound + o; L.minv = T.minv + o; L.iinv = T.iinv + o;
     L.cog = T.cog + o * 2; L.mat_e = T.mat_e + o; L.mat_u = T.mat_u + o; L.init = T.init + o * 3; L.nbody = T.nbody[l]; L.robot0 = H.robot0[l];
     return L;
+}
+
+int bp_shipice_obs_global(bp_shipice_t* h, uint8_t* obs, const uint8_t* mask, void* stream) {
+    if (!h || !obs) return fail(BP_ERR_INVALID, "null argument");
+    if (h->kind != KIND_SHIPICE) return fail(BP_ERR_INVALID, "not a ship-ice handle");
+    if (!h->was_reset) return fail(BP_ERR_STATE, "reset first");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ObsArgs oa;
+    oa.mem = h->mem; oa.env_bytes = h->env_bytes; oa.d = h->d; oa.T = h->T; oa.O = h->O;
+    oa.rawv = h->d_rawv; oa.rawn = h->d_rawn; oa.rawcen = h->d_rawcen; oa.mask = mask; oa.obs = obs;
+    prof_begin(h, 1, st);
+    k_shipice_obs_global<<<h->d.n_envs, 256, 0, st>>>(oa);
+    prof_end(h, st);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_shipice_low_dim(bp_shipice_t* h, double* out, int32_t* counts, void* stream) {
+    if (!h || !out) return fail(BP_ERR_INVALID, "null argument");
+    if (h->kind != KIND_SHIPICE) return fail(BP_ERR_INVALID, "not a ship-ice handle");
+    if (!h->was_reset) return fail(BP_ERR_STATE, "reset first");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    return launch_low_dim(h, out, counts, 0, (cudaStream_t)stream);
 }
 
 int bp_shipice_get_obstacles(bp_shipice_t* h, int32_t env, double* verts, int32_t* n_verts) {
@@ -739,6 +830,13 @@ int bp_maze_step_masked(bp_maze_t* h, const float* actions, const uint8_t* mask,
     return bp_shipice_step_masked(h, actions, mask, out, stream);
 }
 int bp_maze_step_host(bp_maze_t* h, const float* actions, const bp_maze_outputs* out_host) { return bp_shipice_step_host(h, actions, out_host); }
+int bp_maze_low_dim(bp_maze_t* h, double* out, int32_t* counts, void* stream) {
+    if (!h || !out) return fail(BP_ERR_INVALID, "null argument");
+    if (h->kind != KIND_MAZE) return fail(BP_ERR_INVALID, "not a maze handle");
+    if (!h->was_reset) return fail(BP_ERR_STATE, "reset first");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    return launch_low_dim(h, out, counts, 1, (cudaStream_t)stream);
+}
 int bp_maze_get_obstacles(bp_maze_t* h, int32_t env, double* verts, int32_t* n_verts) { return bp_shipice_get_obstacles(h, env, verts, n_verts); }
 int bp_maze_get_bodies(bp_maze_t* h, int32_t env, double* out) { return bp_shipice_get_bodies(h, env, out); }
 int bp_maze_get_maps(bp_maze_t* h, uint8_t* wall, double* dist_norm, double* dist_raw, int32_t* hw) {

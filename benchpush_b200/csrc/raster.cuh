@@ -262,4 +262,72 @@ BP_DEV void render_obs(ObsSmem& S, const ObsParams& O, int n_obst, const double*
     BP_BSYNC();
 }
 
+// ------------------------------------------------------------------ global (non-egocentric) observation
+// ShipIceEnv.generate_observation with cfg.egocentric_obs = false (ship_ice_env.py:397-409): two channels on the whole
+// grid_h x grid_w map, (x * 255).astype(u8):
+//   0  occupancy: compute_occ_img over ALL obstacles (no local range; occupancy_map.py:37-65) followed by
+//      compute_con_gridmap (:97-109), whose block_reduce block is int(grid * scale) = 1 x 1 for every grid the config
+//      can express with grid = 1 / scale (ship_ice_env.py:59-60), i.e. the identity — the host checks that;
+//   1  footprint: compute_ship_footprint_planner (:253-296): the configured ship vertices that fall inside the grid,
+//      draw.polygon without a shape argument, value 1.0; all zeros when no vertex is inside.
+// 600 KB per env does not fit in shared memory: the block zeroes its slice of HBM (32-bit stores), then groups of
+// 32 threads take one polygon each and store 255 into the pixels its inclusive crossing test accepts.
+struct ObsGlobalSmem { double fpv[2 * MAX_ROBOT_RAW]; int n_fp; };
+
+#if defined(__CUDACC__) && !defined(BP_HOST_EMU)
+constexpr int OBS_FILL_GROUP = 32;
+#else
+constexpr int OBS_FILL_GROUP = 1;
+#endif
+
+BP_DEV void fill_polygon_global(const ObsParams& O, const double* v, int n, unsigned char* chan, int lane, int nl, bool clip_to_grid) {
+    double rmin = INFINITY, rmax = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
+    for (int i = 0; i < n; i++) {
+        double x = v[2 * i] * O.scale, y = v[2 * i + 1] * O.scale;
+        cmin = fmin(cmin, x); cmax = fmax(cmax, x); rmin = fmin(rmin, y); rmax = fmax(rmax, y);
+    }
+    long long minr = (long long)fmax(0.0, rmin), maxr = (long long)ceil(rmax);
+    long long minc = (long long)fmax(0.0, cmin), maxc = (long long)ceil(cmax);
+    // draw.polygon(shape=...) clips the bounding box; without a shape the caller guarantees in-grid vertices, and a
+    // pixel beyond the last vertex row / column cannot pass the test — clipping there only protects the buffer
+    (void)clip_to_grid;
+    if (maxr > O.grid_h - 1) maxr = O.grid_h - 1;
+    if (maxc > O.grid_w - 1) maxc = O.grid_w - 1;
+    if (maxr < minr || maxc < minc) return;
+    int bw = (int)(maxc - minc + 1), bh = (int)(maxr - minr + 1);
+    for (int i = lane; i < bw * bh; i += nl) {
+        int rr = (int)minr + i / bw, cc = (int)minc + i % bw;
+        if (pip_inclusive(v, n, O.scale, (double)cc, (double)rr)) chan[(size_t)rr * O.grid_w + cc] = 255;
+    }
+}
+
+BP_DEV void render_obs_global(ObsGlobalSmem& S, const ObsParams& O, int n_obst, const double* verts, int poly_stride, const int* nverts,
+                              double rx, double ry, double ra, unsigned char* out /* [2][grid_h][grid_w] */) {
+    const int tid = BP_TID, nt = BP_NT;
+    const size_t npix = (size_t)O.grid_h * O.grid_w;
+    if (((2 * npix) & 3) == 0 && ((uintptr_t)out & 3) == 0) {
+        uint32_t* o4 = (uint32_t*)out;
+        for (size_t i = tid; i < (2 * npix) / 4; i += nt) o4[i] = 0u;
+    } else {
+        for (size_t i = tid; i < 2 * npix; i += nt) out[i] = 0;
+    }
+    if (tid == 0) {
+        double s, c; bp_sincos(ra, &s, &c);
+        int k = 0; double ms = -s;
+        for (int i = 0; i < O.n_robot_raw; i++) {
+            double vx = O.robot_raw[2 * i], vy = O.robot_raw[2 * i + 1];
+            double wx = vx * c + vy * ms + rx, wy = vx * s + vy * c + ry;
+            double gx = wx * O.scale, gy = wy * O.scale;
+            if (gy < 0 || gy >= O.grid_h || gx < 0 || gx >= O.grid_w) continue;
+            S.fpv[2 * k] = wx; S.fpv[2 * k + 1] = wy; k++;
+        }
+        S.n_fp = k;
+    }
+    BP_BSYNC();
+    const int lane = tid % OBS_FILL_GROUP, grp = tid / OBS_FILL_GROUP, ngrp = nt / OBS_FILL_GROUP;
+    for (int b = grp; b < n_obst; b += ngrp) fill_polygon_global(O, verts + (size_t)b * poly_stride, nverts[b], out, lane, OBS_FILL_GROUP, true);
+    if (S.n_fp > 0) fill_polygon_global(O, S.fpv, S.n_fp, out + npix, tid, nt, false);
+    BP_BSYNC();
+}
+
 }  // namespace bp

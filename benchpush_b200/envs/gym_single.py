@@ -11,6 +11,14 @@ import numpy as np
 from .ship_ice import ShipIceVecEnv
 
 
+def _obs0(v, obs):
+    """Observation of env 0 as numpy; a low-dimensional observation is cut to its valid length (the batched
+    tensor is zero padded to the largest layout)."""
+    if getattr(v, "low_dim_state", False):
+        return obs[0, : int(v._low_dim_counts[0])].cpu().numpy()
+    return obs[0].cpu().numpy()
+
+
 class ShipIceEnvB200:
     metadata = {"render_modes": []}
 
@@ -45,7 +53,7 @@ class ShipIceEnvB200:
         obs, info = self._v.reset()
         self.t = 0
         self.total_work = [0, []]
-        return obs[0].cpu().numpy(), self._info(info, True)
+        return _obs0(self._v, obs), self._info(info, True)
 
     def step(self, action):
         a = np.asarray(action, dtype=np.float32).reshape(1)
@@ -53,7 +61,7 @@ class ShipIceEnvB200:
         self.t += 1
         out = self._info(info, False)
         self.total_work[0] = out["total_work"]
-        return obs[0].cpu().numpy(), float(r[0]), bool(term[0]), bool(trunc[0]), out
+        return _obs0(self._v, obs), float(r[0]), bool(term[0]), bool(trunc[0]), out
 
     def render(self):
         raise NotImplementedError("rendering is out of scope for the batched simulator")
@@ -100,7 +108,7 @@ class MazeNamoEnvB200:
         obs, info = self._v.reset()
         self.t = 0
         self.total_work = [0, []]
-        return obs[0].cpu().numpy(), self._info(info, True)
+        return _obs0(self._v, obs), self._info(info, True)
 
     def step(self, action):
         a = np.asarray(action, dtype=np.float32).reshape(1)
@@ -108,7 +116,7 @@ class MazeNamoEnvB200:
         self.t += 1
         out = self._info(info, False)
         self.total_work[0] = out["total_work"]
-        return obs[0].cpu().numpy(), float(r[0]), bool(term[0]), bool(trunc[0]), out
+        return _obs0(self._v, obs), float(r[0]), bool(term[0]), bool(trunc[0]), out
 
     def render(self):
         raise NotImplementedError("rendering is out of scope for the batched simulator")

@@ -44,8 +44,7 @@ class MazeNamoVecEnv(ShipIceVecEnv):
             self.cfg.env = self.cfg.env2
         else:
             raise Exception("Invalid Maze Version!")
-        if self.cfg.low_dim_state:
-            raise NotImplementedError("only the 4-channel image observation is implemented (cfg.low_dim_state=false)")
+        self.low_dim_state = bool(self.cfg.low_dim_state)
         if self.cfg.random_start:
             raise NotImplementedError("cfg.random_start is not implemented: the start pose is the fixed one of the maze version")
         if int(self.cfg.occ.local_width) * int(self.cfg.occ.m_to_pix_scale) != 192 or int(self.cfg.occ.local_height) * int(self.cfg.occ.m_to_pix_scale) != 192:
@@ -132,11 +131,13 @@ class MazeNamoVecEnv(ShipIceVecEnv):
         o.scaled_collision_reward = self._scoll.data_ptr(); o.dist_reward = self._dist.data_ptr()
         o.trial_success = self._success.data_ptr(); o.status = self._status.data_ptr()
         self._out = o
+        self._init_low_dim(2 * (self.max_boxes + 1))
         if first_layout is None:
             first_layout = np.arange(E) % self.env_max_trial
         self._next_trial = torch.as_tensor(np.asarray(first_layout, dtype=np.int32), device=dev)
         self._actions = torch.zeros(E, dtype=torch.float32, device=dev)
-        self.observation_shape = _lib.MAZE_OBS_SHAPE
+        if not self.low_dim_state:
+            self.observation_shape = _lib.MAZE_OBS_SHAPE
         self.action_low, self.action_high = -1.0, 1.0
         self.check_status = True
 

@@ -51,8 +51,8 @@ class ShipIceVecEnv:
         if not torch.cuda.is_available():
             raise _lib.BenchPushError("ShipIceVecEnv needs a CUDA device (there is no CPU fallback)")
         self.cfg = merge_cfg(DotDict.load_from_file(_CFG_PATH), cfg)
-        if self.cfg.low_dim_state or not self.cfg.egocentric_obs:
-            raise NotImplementedError("only the egocentric image observation is implemented (cfg.egocentric_obs=true, low_dim_state=false)")
+        self.low_dim_state = bool(self.cfg.low_dim_state)
+        self.egocentric_obs = bool(self.cfg.egocentric_obs)
         if self.cfg.random_start:
             raise NotImplementedError("cfg.random_start is not implemented: start poses come from the layouts")
         assert self.cfg.concentration in [0.1, 0.2, 0.3, 0.4, 0.5], "concentration must be one of 0.1 .. 0.5 (ship_ice_env.py:75)"
@@ -72,6 +72,12 @@ class ShipIceVecEnv:
                 else:
                     trials = generate_experiment(n_synthetic_trials, self.cfg.concentration, seed=synthetic_seed)
             layouts = pack_trials(trials)
+        if self.low_dim_state:
+            # the reference runs every episode on trial cfg.fixed_trial_idx when low_dim_state (ship_ice_env.py:84-87, 189-190),
+            # which also fixes the observation length at 2 * n_floes of that trial
+            k = int(self.cfg.fixed_trial_idx) % layouts.n_layouts
+            layouts = PackedLayouts(layouts.n_floes[k:k + 1], layouts.n_verts[k:k + 1], layouts.verts[k:k + 1],
+                                    layouts.centres[k:k + 1], layouts.ship_state[k:k + 1])
         self.layouts = layouts
         self.env_max_trial = layouts.n_layouts
         # ---- native handle
@@ -107,7 +113,17 @@ class ShipIceVecEnv:
                                              ce.ctypes.data, ss.ctypes.data))
         # ---- buffers
         E, dev = self.num_envs, self.device
-        self.obs = torch.zeros((E,) + _lib.OBS_SHAPE, dtype=torch.uint8, device=dev)
+        self._global_obs = not self.low_dim_state and not self.egocentric_obs
+        if self._global_obs:
+            # generate_observation's second branch (ship_ice_env.py:397-407): occupancy + footprint on the whole map
+            scale, gw = int(self.cfg.occ.m_to_pix_scale), 1.0 / int(self.cfg.occ.m_to_pix_scale)
+            gh_, gw_ = int(float(self.cfg.occ.map_height) / gw), int(float(self.cfg.occ.map_width) / gw)   # occupancy_map.py:20-21
+            if int(gw * scale) != 1 or int(float(self.cfg.occ.map_height) * scale) != gh_ or int(float(self.cfg.occ.map_width) * scale) != gw_:
+                raise NotImplementedError("global observation: compute_con_gridmap's block_reduce is only the identity (1 x 1 block) here")
+            self._obs_shape = (2, gh_, gw_)
+            self.obs = torch.zeros((E,) + self._obs_shape, dtype=torch.uint8, device=dev)
+        else:
+            self.obs = torch.zeros((E,) + _lib.OBS_SHAPE, dtype=torch.uint8, device=dev)
         self._reward = torch.zeros(E, dtype=torch.float64, device=dev)
         self._terminated = torch.zeros(E, dtype=torch.uint8, device=dev)
         self._truncated = torch.zeros(E, dtype=torch.uint8, device=dev)
@@ -126,13 +142,48 @@ class ShipIceVecEnv:
         o.scaled_collision_reward = self._scoll.data_ptr(); o.dist_reward = self._dist.data_ptr()
         o.trial_success = self._success.data_ptr(); o.status = self._status.data_ptr()
         self._out = o
+        self._init_low_dim(2 * layouts.max_floes)
+        if self._global_obs:
+            self._out.obs = None                      # the egocentric kernel is not launched; _observation() renders
         if first_trial is None:
             first_trial = np.arange(E) % self.env_max_trial       # env e starts at trial e % n
         self._next_trial = torch.as_tensor(np.asarray(first_trial, dtype=np.int32), device=dev)
         self._actions = torch.zeros(E, dtype=torch.float32, device=dev)
-        self.observation_shape = _lib.OBS_SHAPE
+        if not self.low_dim_state:
+            self.observation_shape = self._obs_shape
         self.action_low, self.action_high = -1.0, 1.0
         self.check_status = True
+
+    # ------------------------------------------------------------------ low-dimensional observation
+    def _init_low_dim(self, width: int):
+        """cfg.low_dim_state: the observation is ``generate_observation_low_dim`` (ship_ice_env.py:358-370,
+        maze_NAMO_env.py:488-504) — float64 [E, width], zero padded — and the image kernel is not launched."""
+        self._low_dim_width = int(width)
+        self.low_dim_obs = None
+        if self.low_dim_state:
+            self.low_dim_obs = torch.zeros((self.num_envs, self._low_dim_width), dtype=torch.float64, device=self.device)
+            self._low_dim_counts = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+            self._out.obs = None                      # NULL: bp_*_step / reset skip the observation kernel
+            self.observation_shape = (self._low_dim_width,)
+
+    def low_dim_observation(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``generate_observation_low_dim`` of the current state for every env (available in both observation modes)."""
+        if out is None:
+            out = torch.empty((self.num_envs, self._low_dim_width), dtype=torch.float64, device=self.device)
+        cnt = getattr(self, "_low_dim_counts", None)
+        with torch.cuda.device(self.device):
+            _lib.check(self._fn("low_dim")(self._h, C.c_void_p(out.data_ptr()),
+                                           C.c_void_p(cnt.data_ptr()) if cnt is not None else None, self._stream()))
+        return out
+
+    def _observation(self, mask=None):
+        if self.low_dim_state:
+            return self.low_dim_observation(self.low_dim_obs)
+        if getattr(self, "_global_obs", False):
+            with torch.cuda.device(self.device):
+                mptr = C.c_void_p(mask.data_ptr()) if mask is not None else None
+                _lib.check(self._L.bp_shipice_obs_global(self._h, C.c_void_p(self.obs.data_ptr()), mptr, self._stream()))
+        return self.obs
 
     # ------------------------------------------------------------------ gym-style API
     @property
@@ -170,7 +221,7 @@ class ShipIceVecEnv:
             else:
                 self._next_trial = torch.where(mask.bool(), (self._next_trial + 1) % self.env_max_trial, self._next_trial)
         self._raise_on_status()
-        return self.obs, self._info(reset=True)
+        return self._observation(mask), self._info(reset=True)
 
     def step(self, action, mask: Optional[torch.Tensor] = None):
         """``mask`` (bool/uint8 [E], optional): step only the envs with mask set; the others keep their
@@ -180,7 +231,8 @@ class ShipIceVecEnv:
             self._actions.copy_(a)
             self.step_async_nocheck(self._actions, mask)
         self._raise_on_status()
-        return self.obs, self._reward, self._terminated.bool(), self._truncated.bool(), self._info(reset=False)
+        return (self._observation(getattr(self, "_mask", None) if mask is not None else None), self._reward, self._terminated.bool(),
+                self._truncated.bool(), self._info(reset=False))
 
     def step_async_nocheck(self, action_dev: torch.Tensor, mask: Optional[torch.Tensor] = None):
         """Enqueue one step without any host synchronisation (actions already on the device)."""
@@ -199,6 +251,8 @@ class ShipIceVecEnv:
                           "state": np.zeros((E, 3)), "total_work": np.zeros(E), "trial_success": np.zeros(E, np.uint8),
                           "status": np.zeros(E, np.int32), "obs": None}
         hb = self._host
+        if want_obs and (self.low_dim_state or getattr(self, "_global_obs", False)):
+            raise NotImplementedError("step_host returns the egocentric image only; use step() for the low-dimensional / global observation")
         if want_obs and hb["obs"] is None:
             hb["obs"] = np.zeros((E,) + self._obs_shape, np.uint8)
         o = _lib.ShipIceOutputs()

@@ -122,6 +122,17 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
  * obs / reward / terminated / truncated (and the non-NULL info arrays) back, and synchronises. */
 int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out_host);
 
+/* ShipIceEnv.generate_observation with cfg.egocentric_obs = false (ship_ice_env.py:397-409): DEVICE
+ * obs[E][2][grid_h][grid_w] u8 (grid = int(map_height * scale) x int(map_width * scale), 1000 x 300 by default):
+ * channel 0 the occupancy map of all floes, channel 1 the ship footprint (compute_ship_footprint_planner).
+ * Envs with mask[e] == 0 keep their previous contents (mask NULL = all).  Enqueued on `stream`. */
+int bp_shipice_obs_global(bp_shipice_t* h, uint8_t* obs, const uint8_t* mask, void* stream);
+
+/* ShipIceEnv.generate_observation_low_dim (ship_ice_env.py:358-370), the observation when cfg.low_dim_state:
+ * DEVICE out[E][2*max_floes] = |poly_centroid| (x, y) of every floe in creation order, zero padded;
+ * counts[E] (DEVICE, may be NULL) = valid entries per env (2 * n_floes).  Enqueued on `stream`. */
+int bp_shipice_low_dim(bp_shipice_t* h, double* out, int32_t* counts, void* stream);
+
 /* CostMap.get_obs_from_poly (cost_map.py:274-281) = info['obs']: world-space hull vertices of every
  * floe of env `env`.  HOST outputs: verts[max_floes*BP_VMAX*2], n_verts[max_floes]; returns n_floes. */
 int bp_shipice_get_obstacles(bp_shipice_t* h, int32_t env, double* verts, int32_t* n_verts);
@@ -213,6 +224,11 @@ int bp_maze_reset(bp_maze_t* h, const int32_t* layout_ids, const uint8_t* mask, 
 int bp_maze_step(bp_maze_t* h, const float* actions, const bp_maze_outputs* out, void* stream);
 int bp_maze_step_masked(bp_maze_t* h, const float* actions, const uint8_t* mask, const bp_maze_outputs* out, void* stream);
 int bp_maze_step_host(bp_maze_t* h, const float* actions, const bp_maze_outputs* out_host);
+
+/* MazeNAMO.generate_observation_low_dim (maze_NAMO_env.py:488-504): DEVICE out[E][2*(max_boxes+1)] =
+ * <robot_x, robot_y, |centroid| of obstacle 1, ..., obstacle n-1, 0, 0> — the reference's loop starts at index 1, so
+ * obstacle 0 never appears and the last pair stays zero (preserved).  counts[E] (may be NULL) = 2 * (n_boxes + 1). */
+int bp_maze_low_dim(bp_maze_t* h, double* out, int32_t* counts, void* stream);
 
 /* info['obs']: world-space hull vertices of every movable obstacle of env `env`.  HOST outputs:
  * verts[max_boxes*BP_VMAX*2], n_verts[max_boxes]; returns the obstacle count. */

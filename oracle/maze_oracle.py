@@ -408,6 +408,8 @@ class MazeNamoOracleEnv:
         px, py, pa = self.robot_pose()
         info = {"state": (round(px, 2), round(py, 2), round(pa, 2)), "total_work": self.total_work[0], "obs": updated,
                 "box_count": 0, "goal_dt": self.unnormalized_dist_map, "m_to_pix_scale": self.cfg["occ"]["m_to_pix_scale"]}
+        if self.cfg["low_dim_state"]:           # maze_NAMO_env.py:353-354
+            return self.generate_observation_low_dim(updated), info
         return self.generate_observation(), info
 
     @property
@@ -466,8 +468,24 @@ class MazeNamoOracleEnv:
         info = {"state": (round(px, 2), round(py, 2), round(pa, 2)), "total_work": self.total_work[0],
                 "collision reward": collision_reward, "scaled collision reward": collision_reward * self.beta,
                 "dist increment reward": dist_increment_reward, "trial_success": trial_success, "obs": updated}
-        observation = self.generate_observation() if want_obs else None
+        if self.cfg["low_dim_state"]:           # maze_NAMO_env.py:477-478
+            observation = self.generate_observation_low_dim(updated)
+        else:
+            observation = self.generate_observation() if want_obs else None
         return observation, reward, terminated, False, info
+
+    # maze_NAMO_env.py:488-504.  The loop starts at 1 (as in the reference): obstacle 0 is never written and the
+    # last pair stays zero.
+    def generate_observation_low_dim(self, updated_obstacles):
+        observation = np.zeros(((len(updated_obstacles) + 1) * 2))
+        px, py, _ = self.robot_pose()
+        observation[0] = px
+        observation[1] = py
+        for i in range(1, len(updated_obstacles)):
+            center = np.abs(poly_centroid(updated_obstacles[i]))
+            observation[i * 2] = center[0]
+            observation[i * 2 + 1] = center[1]
+        return observation
 
     # maze_NAMO_env.py:514-525
     def generate_observation(self):

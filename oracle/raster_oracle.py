@@ -224,6 +224,28 @@ class OccupancyGrid:
         g[rr, cc] = 1.0
         return g
 
+    # occupancy_map.py:253-296 (the planner / global-observation footprint: zeros, 1.0 inside the in-grid vertices' polygon)
+    def compute_ship_footprint_planner(self, ship_state, ship_vertices):
+        self.footprint = np.zeros((self.occ_map_height, self.occ_map_width))
+        sx = self.occ_map_width / self.map_width
+        sy = self.occ_map_height / self.map_height
+        position = ship_state[:2]
+        heading = ship_state[2]
+        R = np.asarray([[math.cos(heading), -math.sin(heading)], [math.sin(heading), math.cos(heading)]])
+        vertices = np.asarray(ship_vertices) @ R.T + np.asarray(position)
+        r, c = [], []
+        for x, y in vertices:
+            gx = x * sx
+            gy = y * sy
+            if gy < 0 or gy >= self.occ_map_height or gx < 0 or gx >= self.occ_map_width:
+                continue
+            r.append(gy)
+            c.append(gx)
+        if len(r) == 0 or len(c) == 0:
+            return
+        rr, cc = draw_polygon(r, c)
+        self.footprint[rr, cc] = 1.0
+
     # occupancy_map.py:379-410
     def ego_view_footprint(self, ship_state, ship_vertices, vertical_shift=2):
         g = self._compute_global_footprint(ship_state, ship_vertices)

@@ -102,6 +102,8 @@ class ShipIceOracleEnv:
     # ship_ice_env.py:186-220
     def init_ship_ice_env(self, settle=True):
         trial_idx = self.episode_idx % self.env_max_trial
+        if self.cfg["low_dim_state"]:           # ship_ice_env.py:189-190: always the fixed trial
+            trial_idx = self.cfg["fixed_trial_idx"]
         trial = self.experiment[trial_idx]
         self.start = trial["ship_state"]
         obs_dicts = [ob for ob in trial["obstacles"] if poly_area(np.asarray(ob["vertices"])) != 0]
@@ -159,6 +161,8 @@ class ShipIceOracleEnv:
         # NB: the reset observation rasterises the RAW trial vertices (self.obstacles, ship_ice_env.py:207,248)
         px, py, pa = self.ship_pose()
         info = {"state": (round(px, 2), round(py, 2), round(pa, 2)), "total_work": self.total_work[0], "obs": updated}
+        if self.cfg["low_dim_state"]:           # ship_ice_env.py:244-245
+            return self.generate_observation_low_dim(updated), info
         return self.generate_observation(), info
 
     def step(self, action, want_obs=True):
@@ -212,13 +216,33 @@ class ShipIceOracleEnv:
         info = {"state": (round(px, 2), round(py, 2), round(pa, 2)), "total_work": self.total_work[0],
                 "collision reward": collision_reward, "scaled collision reward": collision_reward * self.beta,
                 "dist reward": dist_reward, "trial_success": trial_success, "obs": updated}
-        observation = self.generate_observation() if want_obs else None
+        if self.cfg["low_dim_state"]:           # ship_ice_env.py:347-348
+            observation = self.generate_observation_low_dim(updated)
+        else:
+            observation = self.generate_observation() if want_obs else None
         return observation, reward, terminated, False, info
 
-    # ship_ice_env.py:378-409 (egocentric branch)
+    # ship_ice_env.py:358-370
+    def generate_observation_low_dim(self, updated_obstacles):
+        observation = np.zeros((len(updated_obstacles) * 2))
+        for i in range(len(updated_obstacles)):
+            center = np.abs(poly_centroid(updated_obstacles[i]))
+            observation[i * 2] = center[0]
+            observation[i * 2 + 1] = center[1]
+        return observation
+
+    # ship_ice_env.py:378-409
     def generate_observation(self):
         occ = self.cfg["occ"]
         pose = self.ship_pose()
+        if not self.cfg["egocentric_obs"]:      # :397-407: occupancy of all floes + planner footprint on the whole map
+            raw = self.occupancy.compute_occ_img(self.obstacles, ice_binary_w=int(self.occupancy.map_width * occ["m_to_pix_scale"]),
+                                                 ice_binary_h=int(self.occupancy.map_height * occ["m_to_pix_scale"]))
+            occupancy = np.copy(self.occupancy.compute_con_gridmap(raw))
+            self.occupancy.compute_ship_footprint_planner(pose, self.cfg["ship"]["vertices"])
+            footprint = np.copy(self.occupancy.footprint)
+            observation = np.concatenate((np.array([occupancy]), np.array([footprint])))
+            return (observation * 255).astype(np.uint8)
         raw = self.occupancy.compute_occ_img(self.obstacles, ice_binary_w=int(self.occupancy.map_width * occ["m_to_pix_scale"]),
                                              ice_binary_h=int(self.occupancy.map_height * occ["m_to_pix_scale"]),
                                              local_range=[12, 12], ship_state=pose)

@@ -1,0 +1,82 @@
+"""Oracle side of ``generate_observation_low_dim`` (ship_ice_env.py:358-370, maze_NAMO_env.py:488-504), CPU only:
+the restatement against a literal evaluation of the reference's formula on the oracle's own polygons, and the
+reference's quirks the CUDA path has to reproduce (fixed trial in ship-ice; maze: robot first, obstacle 0 skipped,
+last pair zero)."""
+import os
+
+import numpy as np
+
+from tests.conftest import GOLD, fixture_conc
+from benchpush_b200.layouts import unpack_trials
+from oracle.maze_oracle import MazeNamoOracleEnv
+from oracle.ship_ice_oracle import ShipIceOracleEnv
+
+
+def _centroid_literal(v):
+    # geometry/polygon.py:25-41, written out with np.roll exactly as the reference does
+    x, y = np.asarray(v).T
+    A = 0.5 * np.abs(np.dot(x, np.roll(y, 1)) - np.dot(y, np.roll(x, 1)))
+    u = x * np.roll(y, 1) - np.roll(x, 1) * y
+    return np.abs((1 / (6 * A) * np.dot(x + np.roll(x, 1), u), 1 / (6 * A) * np.dot(y + np.roll(y, 1), u)))
+
+
+def test_ship_ice_low_dim_oracle(golden_layouts):
+    name = "c10_t7"
+    trials = unpack_trials(golden_layouts[name])
+    ora = ShipIceOracleEnv({"concentration": fixture_conc(name), "low_dim_state": True, "fixed_trial_idx": 0}, experiment=trials, order_mode=1)
+    obs, info = ora.reset()
+    n = len(info["obs"])
+    assert obs.dtype == np.float64 and obs.shape == (2 * n,)
+    for k in range(2):
+        obs, rew, term, trunc, info = ora.step(0.5)
+        assert obs.shape == (2 * n,)
+        lit = np.concatenate([_centroid_literal(p) for p in info["obs"]])
+        assert np.array_equal(obs, lit)
+        assert (obs >= 0).all()
+    # the fixed trial is used for every episode (ship_ice_env.py:189-190)
+    obs2, info2 = ora.reset()
+    assert ora.episode_idx == 1 and len(info2["obs"]) == n
+
+
+def test_maze_low_dim_oracle_keeps_the_reference_indexing():
+    mg = np.load(os.path.join(GOLD, "maze_golden.npz"))
+    layouts = [[list(map(float, c)) for c in l] for l in mg["layouts"]][:1]
+    ora = MazeNamoOracleEnv({"low_dim_state": True}, layouts=layouts, order_mode=1)
+    obs, info = ora.reset()
+    n = len(info["obs"])
+    assert obs.shape == (2 * (n + 1),)
+    px, py, _ = ora.robot_pose()
+    assert obs[0] == px and obs[1] == py
+    assert obs[2 * n] == 0.0 and obs[2 * n + 1] == 0.0                 # never written by the reference's loop
+    for i in range(1, n):
+        assert np.array_equal(obs[2 * i: 2 * i + 2], _centroid_literal(info["obs"][i]))
+    c0 = _centroid_literal(info["obs"][0])
+    assert not np.any(np.all(obs.reshape(-1, 2)[1:] == c0, axis=1))     # obstacle 0 is absent
+
+
+def test_ship_ice_global_observation_oracle(golden_layouts):
+    """cfg.egocentric_obs = false (ship_ice_env.py:397-407): 2 x 1000 x 300, occupancy of ALL floes (also those beyond the
+    12 m local range of the egocentric channel) and the planner footprint; checked against the literal skimage loops."""
+    from oracle.raster_oracle import draw_polygon_literal
+    name = "c10_t0"
+    trials = unpack_trials(golden_layouts[name])
+    ora = ShipIceOracleEnv({"concentration": fixture_conc(name), "egocentric_obs": False}, experiment=trials, order_mode=1)
+    obs, info = ora.reset(settle=False)
+    assert obs.dtype == np.uint8 and obs.shape == (2, 1000, 300)
+    assert set(np.unique(obs)) <= {0, 255}
+    lit = np.zeros((1000, 300), dtype=np.uint8)
+    for ob in ora.obstacles[:40]:
+        v = np.asarray(ob) * 25
+        rr, cc = draw_polygon_literal(v[:, 1], v[:, 0], shape=lit.shape)
+        lit[rr, cc] = 255
+    assert np.array_equal(np.minimum(lit, obs[0]), lit)               # every literal pixel is set
+    far = [ob for ob in ora.obstacles if abs(np.asarray(ob)[:, 1].mean() - ora.ship_pose()[1]) > 14]
+    assert far, "fixture should have floes outside the egocentric range"
+    v = np.asarray(far[0]) * 25
+    rr, cc = draw_polygon_literal(v[:, 1], v[:, 0], shape=lit.shape)
+    assert len(rr) and (obs[0][rr, cc] == 255).all()
+    # footprint: zeros outside, the ship polygon inside; its pixel count is close to the hull area (2 x 0.5 m -> ~ 560 px)
+    n_fp = int((obs[1] == 255).sum())
+    assert 400 < n_fp < 800
+    px, py, _ = ora.ship_pose()
+    assert obs[1][int(py * 25), int(px * 25)] == 255
