@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_reset(StepArgs a
         if (env < a.d.n_envs && !(a.mask && !a.mask[env])) {
             EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
             int layout = a.layout_ids[env] % a.d.n_layouts;
-            if (a.use_snap) shipice_reset_from_snapshot(a.C, a.mem + a.env_bytes * (size_t)env, layout, env, a.out);
-            else shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
+            const double* sp = a.C->start_pose ? a.C->start_pose + 3 * (size_t)env : nullptr;
+            if (a.use_snap && !sp) shipice_reset_from_snapshot(a.C, a.mem + a.env_bytes * (size_t)env, layout, env, a.out);
+            else shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out, sp);
             if (bp_lane() == 0) { ev.sc->first_layout = layout; ev.sc->episode = 0; ev.sc->done = 0; ev.sc->obs_raw = 1; }
             bp_wsync();
         }
@@ -92,8 +93,9 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepAr
                 // ship_ice_env.py:188); this call returns the reset observation with reward 0.
                 int ep = ev.sc->episode + 1, first = ev.sc->first_layout;
                 int layout = (first + ep) % a.d.n_layouts;
-                if (a.use_snap) shipice_reset_from_snapshot(a.C, a.mem + a.env_bytes * (size_t)env, layout, env, a.out);
-                else shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out);
+                const double* sp = a.C->start_pose ? a.C->start_pose + 3 * (size_t)env : nullptr;
+                if (a.use_snap && !sp) shipice_reset_from_snapshot(a.C, a.mem + a.env_bytes * (size_t)env, layout, env, a.out);
+                else shipice_reset_env(ev, a.T, a.P, a.d, layout, env, a.out, sp);
                 if (bp_lane() == 0) { ev.sc->first_layout = first; ev.sc->episode = ep; ev.sc->done = 0; ev.sc->obs_raw = 1; }
             } else {
                 shipice_step_env(ev, a.T, a.P, a.d, (double)a.actions[env], env, a.out);
@@ -261,6 +263,7 @@ struct bp_shipice {
     char* mem = nullptr; size_t env_bytes = 0;
     int* counter = nullptr;
     DevConst* d_const = nullptr;   // Dims, SimParams, array offsets, layout tables (device copy)
+    DevConst hc_host;              // its host copy (bp_shipice_set_start_poses patches one pointer)
     char* snap = nullptr;          // post-reset env block of every layout (reset = copy)
     bool warp_impl = false;        // BP_STEP_IMPL=warp: one env per warp (A/B measurements)
     StepOut out;               // internal device outputs
@@ -397,7 +400,7 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
     h->d.n_layouts = n_layouts;
     DevConst hc;
     hc.d = h->d; hc.P = h->P; hc.off = env_offsets(h->d); hc.T = h->T;
-    hc.snap = nullptr; hc.env_bytes = h->env_bytes; hc.snap_pose = nullptr; hc.snap_status = nullptr;
+    hc.snap = nullptr; hc.env_bytes = h->env_bytes; hc.snap_pose = nullptr; hc.snap_status = nullptr; hc.start_pose = nullptr;
     CUDA_TRY(cudaMalloc((void**)&h->d_const, sizeof(DevConst)));
     h->dev_allocs.push_back(h->d_const);
     CUDA_TRY(cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice));
@@ -432,6 +435,7 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
         CUDA_TRY(cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice));
     }
     if (const char* e = getenv("BP_STEP_IMPL")) h->warp_impl = (strcmp(e, "warp") == 0);
+    h->hc_host = hc;
     h->layouts_loaded = true;
     return BP_OK;
 }
@@ -615,6 +619,16 @@ static LayoutView host_layout_view(bp_shipice* h, int l) {
     L.cog = T.cog + o * 2; L.mat_e = T.mat_e + o; L.mat_u = T.mat_u + o; L.init = T.init + o * 3; L.nbody = T.nbody[l]; L.robot0 = H.robot0[l];
     return L;
 }
+
+int bp_shipice_set_start_poses(bp_shipice_t* h, const double* poses) {
+    if (!h) return fail(BP_ERR_INVALID, "null argument");
+    if (!h->layouts_loaded) return fail(BP_ERR_STATE, "load layouts first");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->hc_host.start_pose = poses;
+    CUDA_TRY(cudaMemcpy(h->d_const, &h->hc_host, sizeof(DevConst), cudaMemcpyHostToDevice));
+    return BP_OK;
+}
+int bp_maze_set_start_poses(bp_maze_t* h, const double* poses) { return bp_shipice_set_start_poses(h, poses); }
 
 int bp_shipice_obs_global(bp_shipice_t* h, uint8_t* obs, const uint8_t* mask, void* stream) {
     if (!h || !obs) return fail(BP_ERR_INVALID, "null argument");

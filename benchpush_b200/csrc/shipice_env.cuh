@@ -53,11 +53,12 @@ BP_DEV bool settle_is_idle(const EnvView& ev, const EnvScal* sc) {
     return R.vx == 0.0 && R.vy == 0.0 && R.vw == 0.0 && R.bx == 0.0 && R.by == 0.0 && R.bw == 0.0;
 }
 
-BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, int layout_id, int env, const StepOut& out) {
+BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, int layout_id, int env, const StepOut& out,
+                                const double* start = nullptr) {
     LayoutView L = layout_view(T, d, layout_id);
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
-    init_env(ev, L, P, d, layout_id);
+    init_env(ev, L, P, d, layout_id, start);
     // 1000 settle substeps with the ship at rest (ship_ice_env.py:218-219)
     double prev_dt = 0.0;
     for (int k = 0; k < P.settle_steps; k++) {

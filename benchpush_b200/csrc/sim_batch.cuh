@@ -496,8 +496,9 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
             if (auto_reset && sc->done) {
                 int ep = sc->episode + 1, first = sc->first_layout;
                 int layout = (first + ep) % d.n_layouts;
-                if (C->snap) shipice_reset_from_snapshot(C, base, layout, env, out);
-                else shipice_reset_env(ev, C->T, P, d, layout, env, out);
+                const double* sp = C->start_pose ? C->start_pose + 3 * (size_t)env : nullptr;
+                if (C->snap && !sp) shipice_reset_from_snapshot(C, base, layout, env, out);
+                else shipice_reset_env(ev, C->T, P, d, layout, env, out, sp);
                 if (lane == 0) { sc->first_layout = first; sc->episode = ep; sc->done = 0; sc->obs_raw = 1; }
                 base = nullptr;
             } else {

@@ -253,6 +253,9 @@ struct DevConst {
     const char* snap; size_t env_bytes;
     const double* snap_pose;      // [L][3] ship pose after reset
     const int* snap_status;       // [L]
+    // cfg.random_start (ship_ice_env.py:201-203, maze_NAMO_env.py:229-238): per-env start pose of the robot, read at every
+    // reset of env e from start_pose[3e..3e+2] (caller-owned device memory); such resets cannot use the snapshots.  nullptr = the layout's.
+    const double* start_pose;
 };
 BP_DEV LayoutView layout_view(const LayoutTab& T, const Dims& d, int l) {
     LayoutView L;

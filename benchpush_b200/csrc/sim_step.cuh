@@ -838,7 +838,7 @@ BP_DEVNI void sleep_pass(const EnvView& ev, const LayoutView& L, const Dims& d) 
 }
 
 // Initialise an environment from a layout: poses, zero velocities, everything awake, empty cache.
-BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, int layout_id) {
+BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, int layout_id, const double* start = nullptr) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     const int nb = L.nbody;
@@ -853,12 +853,14 @@ BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& 
     }
     for (int b = lane; b < nb; b += BP_NL) {
         BodyRec& R = ev.body[b];
-        double a = L.init[3 * b + 2];
+        // every shape of the kinematic robot (bodies >= robot0) starts at the robot's pose
+        const double* ip = (start && b >= L.robot0) ? start : L.init + 3 * b;
+        double a = ip[2];
         double s, c; bp_sincos(a, &s, &c);
         double cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
         // cpBodySetPosition: p = position + rotate(cog)
-        R.px = (c * cx + (-s) * cy) + L.init[3 * b];
-        R.py = (s * cx + c * cy) + L.init[3 * b + 1];
+        R.px = (c * cx + (-s) * cy) + ip[0];
+        R.py = (s * cx + c * cy) + ip[1];
         R.pa = a;
         R.vx = R.vy = R.vw = 0.0; R.bx = R.by = R.bw = 0.0; R.D = 0.0;
         R.minv = L.minv[b]; R.iinv = L.iinv[b]; R.pad0 = R.pad1 = 0.0;

@@ -46,7 +46,9 @@ class MazeNamoVecEnv(ShipIceVecEnv):
             raise Exception("Invalid Maze Version!")
         self.low_dim_state = bool(self.cfg.low_dim_state)
         if self.cfg.random_start:
-            raise NotImplementedError("cfg.random_start is not implemented: the start pose is the fixed one of the maze version")
+            raise NotImplementedError("cfg.random_start is not implemented for the maze: the reference samples the obstacles around the drawn "
+                                      "start (maze_NAMO_env.py:229-301), so start poses and layouts have to be generated together; callers that "
+                                      "do so can pass them through set_start_poses()")
         if int(self.cfg.occ.local_width) * int(self.cfg.occ.m_to_pix_scale) != 192 or int(self.cfg.occ.local_height) * int(self.cfg.occ.m_to_pix_scale) != 192:
             raise NotImplementedError("the observation kernel is built for a 192 x 192 local window (occ.local_* x occ.m_to_pix_scale)")
         if tuple(self.cfg.sim.gravity) != (0, 0):
@@ -132,6 +134,8 @@ class MazeNamoVecEnv(ShipIceVecEnv):
         o.trial_success = self._success.data_ptr(); o.status = self._status.data_ptr()
         self._out = o
         self._init_low_dim(2 * (self.max_boxes + 1))
+        self._start_poses = None
+        self.random_start, self.redraw_starts = False, False
         if first_layout is None:
             first_layout = np.arange(E) % self.env_max_trial
         self._next_trial = torch.as_tensor(np.asarray(first_layout, dtype=np.int32), device=dev)

@@ -47,14 +47,14 @@ class ShipIceVecEnv:
 
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[PackedLayouts] = None,
                  trials: Optional[Sequence[dict]] = None, ice_file: Optional[str] = None, auto_reset: bool = False,
-                 first_trial: Optional[Sequence[int]] = None, synthetic_seed: int = 99, n_synthetic_trials: int = 100):
+                 first_trial: Optional[Sequence[int]] = None, synthetic_seed: int = 99, n_synthetic_trials: int = 100,
+                 start_seed: int = 0):
         if not torch.cuda.is_available():
             raise _lib.BenchPushError("ShipIceVecEnv needs a CUDA device (there is no CPU fallback)")
         self.cfg = merge_cfg(DotDict.load_from_file(_CFG_PATH), cfg)
         self.low_dim_state = bool(self.cfg.low_dim_state)
         self.egocentric_obs = bool(self.cfg.egocentric_obs)
-        if self.cfg.random_start:
-            raise NotImplementedError("cfg.random_start is not implemented: start poses come from the layouts")
+        self.random_start = bool(self.cfg.random_start)
         assert self.cfg.concentration in [0.1, 0.2, 0.3, 0.4, 0.5], "concentration must be one of 0.1 .. 0.5 (ship_ice_env.py:75)"
         self.num_envs = int(num_envs)
         self.auto_reset = bool(auto_reset)
@@ -143,6 +143,14 @@ class ShipIceVecEnv:
         o.trial_success = self._success.data_ptr(); o.status = self._status.data_ptr()
         self._out = o
         self._init_low_dim(2 * layouts.max_floes)
+        self._start_poses = None
+        self.redraw_starts = True          # False: keep the poses given to set_start_poses() (replaying recorded starts)
+        if self.random_start:
+            # ship_ice_env.py:201-203: x ~ 1 + U[0,1) * (start_x_range - 1), y = 1, theta = pi / 2, drawn per episode.  The
+            # reference uses the unseeded global `random`; here one seeded generator draws a fresh start for every env before
+            # each reset and after each step (an env that auto-resets inside the next step consumes its current one).
+            self._start_rng = np.random.default_rng(start_seed)
+            self.set_start_poses(self._sample_starts())
         if self._global_obs:
             self._out.obs = None                      # the egocentric kernel is not launched; _observation() renders
         if first_trial is None:
@@ -185,6 +193,28 @@ class ShipIceVecEnv:
                 _lib.check(self._L.bp_shipice_obs_global(self._h, C.c_void_p(self.obs.data_ptr()), mptr, self._stream()))
         return self.obs
 
+    # ------------------------------------------------------------------ cfg.random_start
+    def _sample_starts(self) -> np.ndarray:
+        E = self.num_envs
+        x = 1 + self._start_rng.random(E) * (float(self.cfg.start_x_range) - 1)
+        return np.stack([x, np.full(E, 1.0), np.full(E, np.pi / 2)], axis=1)
+
+    def set_start_poses(self, poses: Optional[np.ndarray]):
+        """Start pose (x, y, theta) of every env for its following resets (``bp_*_set_start_poses``); ``None`` restores
+        the layouts' poses.  ``start_poses`` keeps the host copy."""
+        if poses is None:
+            self._start_poses, self.start_poses = None, None
+            _lib.check(self._fn("set_start_poses")(self._h, None))
+            return
+        p = np.ascontiguousarray(poses, dtype=np.float64).reshape(self.num_envs, 3)
+        self.start_poses = p.copy()
+        t = torch.as_tensor(p, device=self.device)
+        if self._start_poses is None:
+            self._start_poses = t.clone()
+            _lib.check(self._fn("set_start_poses")(self._h, C.c_void_p(self._start_poses.data_ptr())))
+        else:
+            self._start_poses.copy_(t)           # same buffer: ordered after the kernels already enqueued
+
     # ------------------------------------------------------------------ gym-style API
     @property
     def unwrapped(self):
@@ -215,6 +245,8 @@ class ShipIceVecEnv:
             if mask is not None:
                 mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
                 mptr = C.c_void_p(mask.data_ptr())
+            if getattr(self, "random_start", False) and self.redraw_starts:
+                self.set_start_poses(self._sample_starts())
             _lib.check(self._fn("reset")(self._h, C.c_void_p(self._next_trial.data_ptr()), mptr, C.byref(self._out), self._stream()))
             if mask is None:
                 self._next_trial = (self._next_trial + 1) % self.env_max_trial
@@ -230,6 +262,8 @@ class ShipIceVecEnv:
             a = torch.as_tensor(action, dtype=torch.float32, device=self.device).reshape(self.num_envs)
             self._actions.copy_(a)
             self.step_async_nocheck(self._actions, mask)
+            if getattr(self, "random_start", False) and self.auto_reset and self.redraw_starts:
+                self.set_start_poses(self._sample_starts())
         self._raise_on_status()
         return (self._observation(getattr(self, "_mask", None) if mask is not None else None), self._reward, self._terminated.bool(),
                 self._truncated.bool(), self._info(reset=False))

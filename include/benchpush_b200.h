@@ -122,6 +122,13 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
  * obs / reward / terminated / truncated (and the non-NULL info arrays) back, and synchronises. */
 int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out_host);
 
+/* cfg.random_start (ship_ice_env.py:201-203; maze_NAMO_env.py:229-238): from now on every reset of env e — explicit or
+ * the next-step auto reset inside bp_*_step — starts the ship / robot at poses[3e..3e+2] = (x, y, theta) instead of the
+ * layout's start pose, through the full reset (init + settle substeps; the per-layout reset snapshots do not apply).
+ * poses: DEVICE, [E][3], owned by the caller and read by later kernels (it may be rewritten between calls to draw a
+ * new start for the next episode); NULL restores the layouts' poses.  Synchronous w.r.t. the host. */
+int bp_shipice_set_start_poses(bp_shipice_t* h, const double* poses);
+
 /* ShipIceEnv.generate_observation with cfg.egocentric_obs = false (ship_ice_env.py:397-409): DEVICE
  * obs[E][2][grid_h][grid_w] u8 (grid = int(map_height * scale) x int(map_width * scale), 1000 x 300 by default):
  * channel 0 the occupancy map of all floes, channel 1 the ship footprint (compute_ship_footprint_planner).
@@ -224,6 +231,9 @@ int bp_maze_reset(bp_maze_t* h, const int32_t* layout_ids, const uint8_t* mask, 
 int bp_maze_step(bp_maze_t* h, const float* actions, const bp_maze_outputs* out, void* stream);
 int bp_maze_step_masked(bp_maze_t* h, const float* actions, const uint8_t* mask, const bp_maze_outputs* out, void* stream);
 int bp_maze_step_host(bp_maze_t* h, const float* actions, const bp_maze_outputs* out_host);
+
+/* Same as bp_shipice_set_start_poses, for the maze robot (chassis and wheels share the pose). */
+int bp_maze_set_start_poses(bp_maze_t* h, const double* poses);
 
 /* MazeNAMO.generate_observation_low_dim (maze_NAMO_env.py:488-504): DEVICE out[E][2*(max_boxes+1)] =
  * <robot_x, robot_y, |centroid| of obstacle 1, ..., obstacle n-1, 0, 0> — the reference's loop starts at index 1, so

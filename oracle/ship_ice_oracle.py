@@ -88,6 +88,9 @@ class ShipIceOracleEnv:
         self.yaw_lim = (0, np.pi)
         self.boundary_violation_limit = 0.0
         self.order_mode = order_mode
+        import random as _random
+        self.rng = _random
+        self.start_override = None
 
     # ship_ice_env.py:109-183 (the KE / impulse / contact bookkeeping of the handlers has no reader)
     def init_ship_ice_sim(self):
@@ -106,6 +109,11 @@ class ShipIceOracleEnv:
             trial_idx = self.cfg["fixed_trial_idx"]
         trial = self.experiment[trial_idx]
         self.start = trial["ship_state"]
+        if self.cfg["random_start"]:            # ship_ice_env.py:201-203 (the reference draws from the global `random` module)
+            x_start = 1 + self.rng.random() * (self.cfg["start_x_range"] - 1)
+            self.start = (x_start, 1.0, np.pi / 2)
+            if self.start_override is not None:  # tests: replay the start the CUDA path drew
+                self.start = tuple(self.start_override)
         obs_dicts = [ob for ob in trial["obstacles"] if poly_area(np.asarray(ob["vertices"])) != 0]
         self.obs_dicts = obs_dicts
         self.obstacles = [np.asarray(ob["vertices"]) for ob in obs_dicts]

@@ -110,3 +110,56 @@ def test_ship_ice_global_observation(golden_layouts, pins, portable_trig):
             break
     assert not torch.equal(obs[0, 1], obs[1, 1])
     env.close()
+
+
+def test_ship_ice_random_start(golden_layouts, pins, portable_trig):
+    """cfg.random_start (ship_ice_env.py:201-203): x ~ 1 + U * (start_x_range - 1), y = 1, theta = pi / 2 per episode.  The full
+    reset (init + 1000 settle substeps with the ship at the drawn pose) and the following steps are bit-identical to the
+    oracle started at the same pose; the auto reset inside step() consumes a fresh draw."""
+    from benchpush_b200.envs import ShipIceVecEnv
+    name = "c30_t7"
+    p = golden_layouts[name]
+    conc = fixture_conc(name)
+    cfg = {"concentration": conc, "random_start": True}
+    env = ShipIceVecEnv(num_envs=3, cfg=cfg, layouts=p, device=0, start_seed=11)
+    obs, info = env.reset()
+    starts = env.start_poses.copy()
+    assert ((starts[:, 0] >= 1) & (starts[:, 0] < float(env.cfg.start_x_range))).all() and len(set(starts[:, 0])) == 3
+    assert (starts[:, 1] == 1.0).all() and (starts[:, 2] == np.pi / 2).all()
+    for e in (0, 2):
+        ora = ShipIceOracleEnv(cfg, experiment=unpack_trials(p), order_mode=1)
+        ora.start_override = starts[e]
+        oobs, oinfo = ora.reset()
+        assert np.array_equal(env.get_bodies(e), ora.space.state()), e
+        assert np.array_equal(obs[e].cpu().numpy(), oobs)
+        assert tuple(info["state"][e].tolist()) == tuple(float(x) for x in oinfo["state"])
+        if e == 0:
+            ora0 = ora
+    env.redraw_starts = False
+    for a in pins["%s_o1_actions" % name][:4]:
+        obs, rew, term, trunc, info = env.step(np.array([a, 0.0, 0.0], dtype=np.float32))
+        oobs, orew, oterm, _, oinfo = ora0.step(float(np.float32(a)))
+        assert np.array_equal(env.get_bodies(0), ora0.space.state())
+        assert np.array_equal(obs[0].cpu().numpy(), oobs)
+    env.close()
+    # the oracle's own draw follows the reference's formula
+    import random
+    ora = ShipIceOracleEnv(cfg, experiment=unpack_trials(p), order_mode=1)
+    ora.rng = random.Random(3)
+    ora.episode_idx = 0
+    ora.init_ship_ice_sim(); ora.init_ship_ice_env(settle=False)
+    assert ora.start == (1 + random.Random(3).random() * (ora.cfg["start_x_range"] - 1), 1.0, np.pi / 2)
+    # auto reset: a finished env restarts from the pose drawn after the previous step
+    env = ShipIceVecEnv(num_envs=2, cfg=dict(cfg, goal_y=1.5), layouts=p, device=0, start_seed=4, auto_reset=True)
+    env.reset()
+    seen = []
+    for k in range(6):
+        pending = env.start_poses.copy()
+        obs, rew, term, trunc, info = env.step(np.zeros(2, dtype=np.float32))
+        pose = info["pose"].cpu().numpy()
+        for e in range(2):
+            if abs(pose[e, 1] - 1.0) < 1e-9 and k > 0:            # this step was the auto reset
+                assert abs(pose[e, 0] - pending[e, 0]) < 1e-9
+                seen.append(e)
+    assert seen, "goal_y = 1.5 should end an episode within 6 steps"
+    env.close()
