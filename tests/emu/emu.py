@@ -100,6 +100,16 @@ class Emu:
         self.L.emu_render_obs(self.h, C.c_int(env), C.c_int(1 if raw else 0), out.ctypes.data_as(C.c_void_p))
         return out
 
+    def render_obs_global(self, env, raw, shape=(2, 1000, 300)):
+        out = np.full(shape, 7, dtype=np.uint8)              # the kernel must overwrite every byte
+        self.L.emu_render_obs_global(self.h, C.c_int(env), C.c_int(1 if raw else 0), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def centroid_cache(self, env, max_floes):
+        out = np.zeros(2 * max_floes, dtype=np.float64)
+        n = self.L.emu_centroid_cache(self.h, C.c_int(env), _dp(out))
+        return out[:2 * n]
+
     def spfa(self, m, source):
         m = np.ascontiguousarray(np.asarray(m).astype(bool).astype(np.uint8))
         H, W = m.shape

@@ -162,6 +162,30 @@ void emu_render_obs(void* h, int env, int raw, unsigned char* out) {
         render_obs(S, e->O, r, ev.wv, VMAX * 2, L.nv, ev.cenx, ev.ceny, 1, o.x, o.y, ev.body[r].pa, out);
     }
 }
+// cfg.egocentric_obs = false: render_obs_global on the same sources as k_shipice_obs_global; out [2][grid_h][grid_w]
+void emu_render_obs_global(void* h, int env, int raw, unsigned char* out) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    LayoutView L = layout_view(e->T, e->d, ev.sc->layout);
+    static ObsGlobalSmem S;
+    int r = ev.sc->robot;
+    V2 o = body_origin(ev, L, r);
+    if (raw) {
+        size_t base = (size_t)ev.sc->layout * e->d.NB;
+        render_obs_global(S, e->O, r, e->H.rawv.data() + base * VMAX * 2, VMAX * 2, e->H.rawn.data() + base, o.x, o.y, ev.body[r].pa, out);
+    } else {
+        render_obs_global(S, e->O, r, ev.wv, VMAX * 2, L.nv, o.x, o.y, ev.body[r].pa, out);
+    }
+}
+// the |centroid| cache k_low_dim compacts (cenx / ceny of the bodies below the robot); returns the count
+int emu_centroid_cache(void* h, int env, double* out) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    LayoutView L = layout_view(e->T, e->d, ev.sc->layout);
+    int n = 0;
+    for (int b = 0; b < ev.sc->robot; b++) if (body_dynamic(L, b)) { out[2 * n] = ev.cenx[b]; out[2 * n + 1] = ev.ceny[b]; n++; }
+    return n;
+}
 void emu_spfa(const uint8_t* map, int H, int W, int si, int sj, float* dist, int32_t* parents) {
     std::vector<int> scratch((size_t)3 * H * W);
     SpfaShared S;

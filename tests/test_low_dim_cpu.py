@@ -80,3 +80,26 @@ def test_ship_ice_global_observation_oracle(golden_layouts):
     assert 400 < n_fp < 800
     px, py, _ = ora.ship_pose()
     assert obs[1][int(py * 25), int(px * 25)] == 255
+
+
+def test_emulated_global_observation_and_centroid_cache_match_oracle(golden_layouts, pins, portable_trig):
+    """The kernel sources of k_shipice_obs_global (render_obs_global) and the |centroid| cache that k_low_dim compacts,
+    compiled for the host (tests/emu), against the oracle: rasters bit-exact at reset (raw polygons) and after steps
+    (hull polygons); low-dim entries within 1e-9 (sequential vs pairwise summation, see test_gpu_low_dim)."""
+    from tests.emu.emu import Emu
+    from tests.test_kernel_logic_cpu import SHIP_VERTS
+    name = "c10_t7"
+    p = golden_layouts[name]
+    emu = Emu(1, p, SHIP_VERTS)
+    cfg = {"concentration": fixture_conc(name), "egocentric_obs": False}
+    ora = ShipIceOracleEnv(cfg, experiment=unpack_trials(p), order_mode=1)
+    obs, info = ora.reset()
+    emu.reset(0, 0)
+    assert np.array_equal(obs, emu.render_obs_global(0, True))
+    for a in pins["%s_o1_actions" % name][:3]:
+        obs, r, term, _, info = ora.step(float(a))
+        emu.step(0, float(a))
+        assert np.array_equal(ora.space.state(), emu.bodies(0, 0))
+        assert np.array_equal(obs, emu.render_obs_global(0, False))
+        low = ora.generate_observation_low_dim(info["obs"])
+        np.testing.assert_allclose(emu.centroid_cache(0, p.max_floes), low, rtol=0, atol=1e-9)
