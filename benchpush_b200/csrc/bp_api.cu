@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(256) k_shipice_obs(ObsArgs a) {
     }
 }
 
-// cfg.egocentric_obs = false: the 2 x grid_h x grid_w observation (raster.cuh: render_obs_global), one block per env
-__global__ void __launch_bounds__(256) k_shipice_obs_global(ObsArgs a) {
+// cfg.egocentric_obs = false: the 2 x 200 x 60 cell-grid observation (raster.cuh: render_obs_global), one block per env
+__global__ void __launch_bounds__(256) k_shipice_obs_global(ObsArgs a, GlobalObsParams G) {
     __shared__ ObsGlobalSmem S;
     int env = blockIdx.x;
     if (a.mask && !a.mask[env]) return;
@@ -159,12 +159,12 @@ __global__ void __launch_bounds__(256) k_shipice_obs_global(ObsArgs a) {
     LayoutView L = layout_view(a.T, a.d, sc->layout);
     int r = sc->robot;
     V2 o = body_origin(ev, L, r);
-    uint8_t* out = a.obs + (size_t)env * 2 * a.O.grid_h * a.O.grid_w;
+    uint8_t* out = a.obs + (size_t)env * 2 * G.gh * G.gw;
     if (sc->obs_raw) {
         size_t base = (size_t)sc->layout * a.d.NB;
-        render_obs_global(S, a.O, r, a.rawv + base * VMAX * 2, VMAX * 2, a.rawn + base, o.x, o.y, ev.body[r].pa, out);
+        render_obs_global(S, a.O, G, r, a.rawv + base * VMAX * 2, VMAX * 2, a.rawn + base, o.x, o.y, ev.body[r].pa, out);
     } else {
-        render_obs_global(S, a.O, r, ev.wv, VMAX * 2, L.nv, o.x, o.y, ev.body[r].pa, out);
+        render_obs_global(S, a.O, G, r, ev.wv, VMAX * 2, L.nv, o.x, o.y, ev.body[r].pa, out);
     }
 }
 
@@ -630,17 +630,46 @@ int bp_shipice_set_start_poses(bp_shipice_t* h, const double* poses) {
 }
 int bp_maze_set_start_poses(bp_maze_t* h, const double* poses) { return bp_shipice_set_start_poses(h, poses); }
 
+// ship_ice_env.py:96 (OccupancyGrid with 0.2 m cells when egocentric_obs is false) and occupancy_map.py:20-21, 105
+static int global_obs_params(bp_shipice* h, GlobalObsParams* G) {
+    const double cell = 0.2, scale = (double)h->cfg.m_to_pix_scale;
+    G->raw_h = (int)(h->cfg.map_height * scale); G->raw_w = (int)(h->cfg.map_width * scale);
+    G->blk_y = (int)(cell * scale); G->blk_x = (int)(cell * scale);
+    G->gh = (int)(h->cfg.map_height / cell); G->gw = (int)(h->cfg.map_width / cell);
+    G->cell_scale = G->gw / h->cfg.map_width;
+    if (G->blk_y < 1 || G->gh < 1 || G->gw < 1) return fail(BP_ERR_INVALID, "global observation: m_to_pix_scale below 5 gives an empty block");
+    if ((long long)G->raw_h * G->raw_w > (long long)OBS_RAW_WORDS * 32) return fail(BP_ERR_INVALID, "global observation: map_height * map_width * scale^2 exceeds the 307200-pixel mask");
+    if (G->cell_scale != G->gh / h->cfg.map_height) return fail(BP_ERR_INVALID, "global observation: anisotropic cell scale is not supported");
+    // block_reduce pads the image up to a multiple of the block; its output must be the cell grid the footprint is drawn on
+    if ((G->raw_h + G->blk_y - 1) / G->blk_y != G->gh || (G->raw_w + G->blk_x - 1) / G->blk_x != G->gw)
+        return fail(BP_ERR_INVALID, "global observation: concentration grid and footprint grid differ (the reference's np.concatenate would fail)");
+    return BP_OK;
+}
+
+int bp_shipice_obs_global_shape(bp_shipice_t* h, int32_t* hw) {
+    if (!h || !hw) return fail(BP_ERR_INVALID, "null argument");
+    if (h->kind != KIND_SHIPICE) return fail(BP_ERR_INVALID, "not a ship-ice handle");
+    GlobalObsParams G;
+    int rc = global_obs_params(h, &G);
+    if (rc) return rc;
+    hw[0] = G.gh; hw[1] = G.gw;
+    return BP_OK;
+}
+
 int bp_shipice_obs_global(bp_shipice_t* h, uint8_t* obs, const uint8_t* mask, void* stream) {
     if (!h || !obs) return fail(BP_ERR_INVALID, "null argument");
     if (h->kind != KIND_SHIPICE) return fail(BP_ERR_INVALID, "not a ship-ice handle");
     if (!h->was_reset) return fail(BP_ERR_STATE, "reset first");
+    GlobalObsParams G;
+    int rc = global_obs_params(h, &G);
+    if (rc) return rc;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     ObsArgs oa;
     oa.mem = h->mem; oa.env_bytes = h->env_bytes; oa.d = h->d; oa.T = h->T; oa.O = h->O;
     oa.rawv = h->d_rawv; oa.rawn = h->d_rawn; oa.rawcen = h->d_rawcen; oa.mask = mask; oa.obs = obs;
     prof_begin(h, 1, st);
-    k_shipice_obs_global<<<h->d.n_envs, 256, 0, st>>>(oa);
+    k_shipice_obs_global<<<h->d.n_envs, 256, 0, st>>>(oa, G);
     prof_end(h, st);
     h->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -263,70 +263,106 @@ BP_DEV void render_obs(ObsSmem& S, const ObsParams& O, int n_obst, const double*
 }
 
 // ------------------------------------------------------------------ global (non-egocentric) observation
-// ShipIceEnv.generate_observation with cfg.egocentric_obs = false (ship_ice_env.py:397-409): two channels on the whole
-// grid_h x grid_w map, (x * 255).astype(u8):
-//   0  occupancy: compute_occ_img over ALL obstacles (no local range; occupancy_map.py:37-65) followed by
-//      compute_con_gridmap (:97-109), whose block_reduce block is int(grid * scale) = 1 x 1 for every grid the config
-//      can express with grid = 1 / scale (ship_ice_env.py:59-60), i.e. the identity — the host checks that;
-//   1  footprint: compute_ship_footprint_planner (:253-296): the configured ship vertices that fall inside the grid,
-//      draw.polygon without a shape argument, value 1.0; all zeros when no vertex is inside.
-// 600 KB per env does not fit in shared memory: the block zeroes its slice of HBM (32-bit stores), then groups of
-// 32 threads take one polygon each and store 255 into the pixels its inclusive crossing test accepts.
-struct ObsGlobalSmem { double fpv[2 * MAX_ROBOT_RAW]; int n_fp; };
+// ShipIceEnv.generate_observation with cfg.egocentric_obs = false (ship_ice_env.py:397-409).  In that mode the env builds its
+// OccupancyGrid with 0.2 m cells (ship_ice_env.py:96: 200 x 60 cells for the 40 x 12 m map), and the observation is two
+// channels on that cell grid, (x * 255).astype(u8):
+//   0  concentration: compute_occ_img over ALL obstacles (no local range; occupancy_map.py:37-65) at m_to_pix_scale
+//      (1000 x 300 pixels, union of the polygon fills), then compute_con_gridmap (:97-109) = skimage block_reduce(np.mean)
+//      over int(0.2 * scale) = 5 x 5 pixel blocks (zero padded when the image is not a multiple of the block);
+//   1  footprint: compute_ship_footprint_planner (:253-296): the configured ship vertices scaled to cells, those outside
+//      the cell grid dropped, draw.polygon without a shape argument, value 1.0; all zeros when no vertex is inside.
+// The 1000 x 300 binary image lives in shared memory as a bit mask (37.5 KB): groups of 32 threads take one floe each and
+// OR the pixels its inclusive crossing test accepts; a block-wide pass then counts the bits of every cell and writes the
+// 2 x 200 x 60 bytes of the env once.
+struct GlobalObsParams {
+    int raw_h, raw_w;            // int(map_height * scale), int(map_width * scale): 1000, 300
+    int blk_y, blk_x;            // int(0.2 * scale): 5, 5
+    int gh, gw;                  // int(map_height / 0.2), int(map_width / 0.2): 200, 60
+    double cell_scale;           // gw / map_width (= gh / map_height, checked on the host): 5.0
+};
+constexpr int OBS_RAW_WORDS = 9600;          // 307 200 bits >= 1000 x 300
+struct ObsGlobalSmem { unsigned int bits[OBS_RAW_WORDS]; double fpv[2 * MAX_ROBOT_RAW]; int n_fp; };
 
 #if defined(__CUDACC__) && !defined(BP_HOST_EMU)
 constexpr int OBS_FILL_GROUP = 32;
+#define BP_SMEM_ATOMIC_OR(p, v) atomicOr((p), (v))
 #else
 constexpr int OBS_FILL_GROUP = 1;
+#define BP_SMEM_ATOMIC_OR(p, v) (*(p) |= (v))
 #endif
 
-BP_DEV void fill_polygon_global(const ObsParams& O, const double* v, int n, unsigned char* chan, int lane, int nl, bool clip_to_grid) {
+// skimage _polygon bounding box of the scaled polygon, clipped to an H x W image; false when empty
+BP_DEV bool polygon_bbox(const double* v, int n, double scale, int H, int W, int* minr, int* minc, int* bw, int* bh) {
     double rmin = INFINITY, rmax = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
     for (int i = 0; i < n; i++) {
-        double x = v[2 * i] * O.scale, y = v[2 * i + 1] * O.scale;
+        double x = v[2 * i] * scale, y = v[2 * i + 1] * scale;
         cmin = fmin(cmin, x); cmax = fmax(cmax, x); rmin = fmin(rmin, y); rmax = fmax(rmax, y);
     }
-    long long minr = (long long)fmax(0.0, rmin), maxr = (long long)ceil(rmax);
-    long long minc = (long long)fmax(0.0, cmin), maxc = (long long)ceil(cmax);
-    // draw.polygon(shape=...) clips the bounding box; without a shape the caller guarantees in-grid vertices, and a
-    // pixel beyond the last vertex row / column cannot pass the test — clipping there only protects the buffer
-    (void)clip_to_grid;
-    if (maxr > O.grid_h - 1) maxr = O.grid_h - 1;
-    if (maxc > O.grid_w - 1) maxc = O.grid_w - 1;
-    if (maxr < minr || maxc < minc) return;
-    int bw = (int)(maxc - minc + 1), bh = (int)(maxr - minr + 1);
-    for (int i = lane; i < bw * bh; i += nl) {
-        int rr = (int)minr + i / bw, cc = (int)minc + i % bw;
-        if (pip_inclusive(v, n, O.scale, (double)cc, (double)rr)) chan[(size_t)rr * O.grid_w + cc] = 255;
-    }
+    long long r0 = (long long)fmax(0.0, rmin), r1 = (long long)ceil(rmax);
+    long long c0 = (long long)fmax(0.0, cmin), c1 = (long long)ceil(cmax);
+    if (r1 > H - 1) r1 = H - 1;
+    if (c1 > W - 1) c1 = W - 1;
+    if (r1 < r0 || c1 < c0) return false;
+    *minr = (int)r0; *minc = (int)c0; *bw = (int)(c1 - c0 + 1); *bh = (int)(r1 - r0 + 1);
+    return true;
 }
 
-BP_DEV void render_obs_global(ObsGlobalSmem& S, const ObsParams& O, int n_obst, const double* verts, int poly_stride, const int* nverts,
-                              double rx, double ry, double ra, unsigned char* out /* [2][grid_h][grid_w] */) {
+BP_DEV void render_obs_global(ObsGlobalSmem& S, const ObsParams& O, const GlobalObsParams& G, int n_obst, const double* verts,
+                              int poly_stride, const int* nverts, double rx, double ry, double ra, unsigned char* out /* [2][gh][gw] */) {
     const int tid = BP_TID, nt = BP_NT;
-    const size_t npix = (size_t)O.grid_h * O.grid_w;
-    if (((2 * npix) & 3) == 0 && ((uintptr_t)out & 3) == 0) {
-        uint32_t* o4 = (uint32_t*)out;
-        for (size_t i = tid; i < (2 * npix) / 4; i += nt) o4[i] = 0u;
-    } else {
-        for (size_t i = tid; i < 2 * npix; i += nt) out[i] = 0;
-    }
+    const int nwords = (G.raw_h * G.raw_w + 31) / 32;
+    for (int i = tid; i < nwords; i += nt) S.bits[i] = 0u;
     if (tid == 0) {
         double s, c; bp_sincos(ra, &s, &c);
         int k = 0; double ms = -s;
         for (int i = 0; i < O.n_robot_raw; i++) {
             double vx = O.robot_raw[2 * i], vy = O.robot_raw[2 * i + 1];
             double wx = vx * c + vy * ms + rx, wy = vx * s + vy * c + ry;
-            double gx = wx * O.scale, gy = wy * O.scale;
-            if (gy < 0 || gy >= O.grid_h || gx < 0 || gx >= O.grid_w) continue;
+            double gx = wx * G.cell_scale, gy = wy * G.cell_scale;
+            if (gy < 0 || gy >= G.gh || gx < 0 || gx >= G.gw) continue;
             S.fpv[2 * k] = wx; S.fpv[2 * k + 1] = wy; k++;
         }
         S.n_fp = k;
     }
     BP_BSYNC();
     const int lane = tid % OBS_FILL_GROUP, grp = tid / OBS_FILL_GROUP, ngrp = nt / OBS_FILL_GROUP;
-    for (int b = grp; b < n_obst; b += ngrp) fill_polygon_global(O, verts + (size_t)b * poly_stride, nverts[b], out, lane, OBS_FILL_GROUP, true);
-    if (S.n_fp > 0) fill_polygon_global(O, S.fpv, S.n_fp, out + npix, tid, nt, false);
+    for (int b = grp; b < n_obst; b += ngrp) {
+        const double* v = verts + (size_t)b * poly_stride;
+        const int n = nverts[b];
+        int minr, minc, bw, bh;
+        if (!polygon_bbox(v, n, O.scale, G.raw_h, G.raw_w, &minr, &minc, &bw, &bh)) continue;
+        for (int i = lane; i < bw * bh; i += OBS_FILL_GROUP) {
+            int rr = minr + i / bw, cc = minc + i % bw;
+            if (pip_inclusive(v, n, O.scale, (double)cc, (double)rr)) {
+                int bit = rr * G.raw_w + cc;
+                BP_SMEM_ATOMIC_OR(&S.bits[bit >> 5], 1u << (bit & 31));
+            }
+        }
+    }
+    BP_BSYNC();
+    const int ncell = G.gh * G.gw;
+    const double inv_n = (double)(G.blk_y * G.blk_x);
+    for (int i = tid; i < ncell; i += nt) {
+        int gi = i / G.gw, gj = i % G.gw;
+        int cnt = 0;
+        for (int y = gi * G.blk_y; y < (gi + 1) * G.blk_y && y < G.raw_h; y++)
+            for (int x = gj * G.blk_x; x < (gj + 1) * G.blk_x && x < G.raw_w; x++) {
+                int bit = y * G.raw_w + x;
+                cnt += (S.bits[bit >> 5] >> (bit & 31)) & 1u;
+            }
+        out[i] = (unsigned char)(int)(((double)cnt / inv_n) * 255.0);
+        out[ncell + i] = 0;
+    }
+    BP_BSYNC();
+    int minr, minc, bw, bh;
+    // draw.polygon(r, c) without a shape: the vertices are inside the cell grid, and a pixel beyond the last vertex row /
+    // column cannot pass the test, so clipping the box to the grid changes nothing and protects the buffer
+    if (S.n_fp > 0 && polygon_bbox(S.fpv, S.n_fp, G.cell_scale, G.gh, G.gw, &minr, &minc, &bw, &bh)) {
+        for (int i = tid; i < bw * bh; i += nt) {
+            int rr = minr + i / bw, cc = minc + i % bw;
+            if (pip_inclusive(S.fpv, S.n_fp, G.cell_scale, (double)cc, (double)rr)) out[ncell + rr * G.gw + cc] = 255;
+        }
+    }
     BP_BSYNC();
 }
 

@@ -115,12 +115,10 @@ class ShipIceVecEnv:
         E, dev = self.num_envs, self.device
         self._global_obs = not self.low_dim_state and not self.egocentric_obs
         if self._global_obs:
-            # generate_observation's second branch (ship_ice_env.py:397-407): occupancy + footprint on the whole map
-            scale, gw = int(self.cfg.occ.m_to_pix_scale), 1.0 / int(self.cfg.occ.m_to_pix_scale)
-            gh_, gw_ = int(float(self.cfg.occ.map_height) / gw), int(float(self.cfg.occ.map_width) / gw)   # occupancy_map.py:20-21
-            if int(gw * scale) != 1 or int(float(self.cfg.occ.map_height) * scale) != gh_ or int(float(self.cfg.occ.map_width) * scale) != gw_:
-                raise NotImplementedError("global observation: compute_con_gridmap's block_reduce is only the identity (1 x 1 block) here")
-            self._obs_shape = (2, gh_, gw_)
+            # generate_observation's second branch (ship_ice_env.py:96, 397-407): concentration + footprint on 0.2 m cells
+            hw = np.zeros(2, dtype=np.int32)
+            _lib.check(L.bp_shipice_obs_global_shape(self._h, hw.ctypes.data))
+            self._obs_shape = (2, int(hw[0]), int(hw[1]))
             self.obs = torch.zeros((E,) + self._obs_shape, dtype=torch.uint8, device=dev)
         else:
             self.obs = torch.zeros((E,) + _lib.OBS_SHAPE, dtype=torch.uint8, device=dev)

@@ -129,10 +129,13 @@ int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice
  * new start for the next episode); NULL restores the layouts' poses.  Synchronous w.r.t. the host. */
 int bp_shipice_set_start_poses(bp_shipice_t* h, const double* poses);
 
-/* ShipIceEnv.generate_observation with cfg.egocentric_obs = false (ship_ice_env.py:397-409): DEVICE
- * obs[E][2][grid_h][grid_w] u8 (grid = int(map_height * scale) x int(map_width * scale), 1000 x 300 by default):
- * channel 0 the occupancy map of all floes, channel 1 the ship footprint (compute_ship_footprint_planner).
+/* ShipIceEnv.generate_observation with cfg.egocentric_obs = false (ship_ice_env.py:96, 397-409): DEVICE
+ * obs[E][2][gh][gw] u8 on the 0.2 m cell grid the reference builds in that mode (gh = int(map_height / 0.2),
+ * gw = int(map_width / 0.2): 200 x 60 by default; bp_shipice_obs_global_shape returns them in hw[2]):
+ * channel 0 the ice concentration (5 x 5 block mean of the 1000 x 300 occupancy image of ALL floes, compute_con_gridmap),
+ * channel 1 the ship footprint (compute_ship_footprint_planner), both (x * 255) truncated to u8.
  * Envs with mask[e] == 0 keep their previous contents (mask NULL = all).  Enqueued on `stream`. */
+int bp_shipice_obs_global_shape(bp_shipice_t* h, int32_t* hw);
 int bp_shipice_obs_global(bp_shipice_t* h, uint8_t* obs, const uint8_t* mask, void* stream);
 
 /* ShipIceEnv.generate_observation_low_dim (ship_ice_env.py:358-370), the observation when cfg.low_dim_state:

@@ -81,7 +81,8 @@ class ShipIceOracleEnv:
         self.experiment = experiment
         self.env_max_trial = len(self.experiment)
         occ = self.cfg["occ"]
-        grid_size = 1 / occ["m_to_pix_scale"]
+        # ship_ice_env.py:91-97: cells of 1 / scale for the egocentric image, 0.2 m cells for the global observation
+        grid_size = 1 / occ["m_to_pix_scale"] if self.cfg["egocentric_obs"] else 0.2
         self.occupancy = OccupancyGrid(grid_width=grid_size, grid_height=grid_size, map_width=occ["map_width"],
                                        map_height=occ["map_height"], local_width=6, local_height=6,
                                        meter_to_pixel_scale=occ["m_to_pix_scale"])
@@ -243,7 +244,7 @@ class ShipIceOracleEnv:
     def generate_observation(self):
         occ = self.cfg["occ"]
         pose = self.ship_pose()
-        if not self.cfg["egocentric_obs"]:      # :397-407: occupancy of all floes + planner footprint on the whole map
+        if not self.cfg["egocentric_obs"]:      # :397-407: 5 x 5 block-mean concentration of all floes + planner footprint, 200 x 60 cells
             raw = self.occupancy.compute_occ_img(self.obstacles, ice_binary_w=int(self.occupancy.map_width * occ["m_to_pix_scale"]),
                                                  ice_binary_h=int(self.occupancy.map_height * occ["m_to_pix_scale"]))
             occupancy = np.copy(self.occupancy.compute_con_gridmap(raw))

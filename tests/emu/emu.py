@@ -100,7 +100,7 @@ class Emu:
         self.L.emu_render_obs(self.h, C.c_int(env), C.c_int(1 if raw else 0), out.ctypes.data_as(C.c_void_p))
         return out
 
-    def render_obs_global(self, env, raw, shape=(2, 1000, 300)):
+    def render_obs_global(self, env, raw, shape=(2, 200, 60)):
         out = np.full(shape, 7, dtype=np.uint8)              # the kernel must overwrite every byte
         self.L.emu_render_obs_global(self.h, C.c_int(env), C.c_int(1 if raw else 0), out.ctypes.data_as(C.c_void_p))
         return out

@@ -162,19 +162,21 @@ void emu_render_obs(void* h, int env, int raw, unsigned char* out) {
         render_obs(S, e->O, r, ev.wv, VMAX * 2, L.nv, ev.cenx, ev.ceny, 1, o.x, o.y, ev.body[r].pa, out);
     }
 }
-// cfg.egocentric_obs = false: render_obs_global on the same sources as k_shipice_obs_global; out [2][grid_h][grid_w]
+// cfg.egocentric_obs = false: render_obs_global on the same sources as k_shipice_obs_global; out [2][200][60]
 void emu_render_obs_global(void* h, int env, int raw, unsigned char* out) {
     Emu* e = (Emu*)h;
     EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
     LayoutView L = layout_view(e->T, e->d, ev.sc->layout);
     static ObsGlobalSmem S;
+    GlobalObsParams G;       // the default map: 40 x 12 m at 25 px/m, 0.2 m cells (bp_api.cu: global_obs_params)
+    G.raw_h = e->O.grid_h; G.raw_w = e->O.grid_w; G.blk_y = G.blk_x = 5; G.gh = 200; G.gw = 60; G.cell_scale = 5.0;
     int r = ev.sc->robot;
     V2 o = body_origin(ev, L, r);
     if (raw) {
         size_t base = (size_t)ev.sc->layout * e->d.NB;
-        render_obs_global(S, e->O, r, e->H.rawv.data() + base * VMAX * 2, VMAX * 2, e->H.rawn.data() + base, o.x, o.y, ev.body[r].pa, out);
+        render_obs_global(S, e->O, G, r, e->H.rawv.data() + base * VMAX * 2, VMAX * 2, e->H.rawn.data() + base, o.x, o.y, ev.body[r].pa, out);
     } else {
-        render_obs_global(S, e->O, r, ev.wv, VMAX * 2, L.nv, o.x, o.y, ev.body[r].pa, out);
+        render_obs_global(S, e->O, G, r, ev.wv, VMAX * 2, L.nv, o.x, o.y, ev.body[r].pa, out);
     }
 }
 // the |centroid| cache k_low_dim compacts (cenx / ceny of the bodies below the robot); returns the count

@@ -85,7 +85,7 @@ def test_maze_low_dim_steps(portable_trig):
 
 
 def test_ship_ice_global_observation(golden_layouts, pins, portable_trig):
-    """cfg.egocentric_obs = false: u8[E, 2, 1000, 300] from k_shipice_obs_global, bit-exact against the oracle at reset (raw
+    """cfg.egocentric_obs = false: u8[E, 2, 200, 60] (0.2 m cells: block-mean concentration + footprint) from k_shipice_obs_global, bit-exact against the oracle at reset (raw
     trial polygons) and after every step (hull polygons); the ship is steered to the map border so that part of the
     footprint's vertices leave the grid."""
     from benchpush_b200.envs import ShipIceVecEnv
@@ -97,9 +97,9 @@ def test_ship_ice_global_observation(golden_layouts, pins, portable_trig):
     obs, info = env.reset()
     ora = ShipIceOracleEnv(cfg, experiment=unpack_trials(p), order_mode=1)
     oobs, oinfo = ora.reset()
-    assert obs.shape == (2, 2, 1000, 300) and obs.dtype == torch.uint8
+    assert obs.shape == (2, 2, 200, 60) and obs.dtype == torch.uint8
     assert np.array_equal(obs[0].cpu().numpy(), oobs)
-    assert int((obs[0, 0] == 255).sum()) > 1000 and int((obs[0, 1] == 255).sum()) > 100
+    assert int((obs[0, 0] > 0).sum()) > 300 and int((obs[0, 1] == 255).sum()) > 10
     for k in range(8):
         a = 1.0 if k < 4 else -1.0
         obs, rew, term, trunc, info = env.step(np.array([a, -a], dtype=np.float32))

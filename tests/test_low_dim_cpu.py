@@ -55,31 +55,34 @@ def test_maze_low_dim_oracle_keeps_the_reference_indexing():
 
 
 def test_ship_ice_global_observation_oracle(golden_layouts):
-    """cfg.egocentric_obs = false (ship_ice_env.py:397-407): 2 x 1000 x 300, occupancy of ALL floes (also those beyond the
-    12 m local range of the egocentric channel) and the planner footprint; checked against the literal skimage loops."""
+    """cfg.egocentric_obs = false (ship_ice_env.py:96, 397-407): 2 x 200 x 60 on 0.2 m cells — the 5 x 5 block mean of the
+    1000 x 300 occupancy image of ALL floes (also those beyond the 12 m local range of the egocentric channel) and the planner
+    footprint; checked against the literal skimage loops and a literal block mean."""
     from oracle.raster_oracle import draw_polygon_literal
     name = "c10_t0"
     trials = unpack_trials(golden_layouts[name])
     ora = ShipIceOracleEnv({"concentration": fixture_conc(name), "egocentric_obs": False}, experiment=trials, order_mode=1)
     obs, info = ora.reset(settle=False)
-    assert obs.dtype == np.uint8 and obs.shape == (2, 1000, 300)
-    assert set(np.unique(obs)) <= {0, 255}
-    lit = np.zeros((1000, 300), dtype=np.uint8)
-    for ob in ora.obstacles[:40]:
+    assert obs.dtype == np.uint8 and obs.shape == (2, 200, 60)
+    assert (ora.occupancy.occ_map_height, ora.occupancy.occ_map_width) == (200, 60)
+    lit = np.zeros((1000, 300))
+    for ob in ora.obstacles:
         v = np.asarray(ob) * 25
         rr, cc = draw_polygon_literal(v[:, 1], v[:, 0], shape=lit.shape)
-        lit[rr, cc] = 255
-    assert np.array_equal(np.minimum(lit, obs[0]), lit)               # every literal pixel is set
-    far = [ob for ob in ora.obstacles if abs(np.asarray(ob)[:, 1].mean() - ora.ship_pose()[1]) > 14]
-    assert far, "fixture should have floes outside the egocentric range"
-    v = np.asarray(far[0]) * 25
-    rr, cc = draw_polygon_literal(v[:, 1], v[:, 0], shape=lit.shape)
-    assert len(rr) and (obs[0][rr, cc] == 255).all()
-    # footprint: zeros outside, the ship polygon inside; its pixel count is close to the hull area (2 x 0.5 m -> ~ 560 px)
-    n_fp = int((obs[1] == 255).sum())
-    assert 400 < n_fp < 800
+        lit[rr, cc] = 1.0
+    conc = np.zeros((200, 60))
+    for i in range(200):
+        for j in range(60):
+            conc[i, j] = np.mean(lit[5 * i: 5 * i + 5, 5 * j: 5 * j + 5])
+    assert np.array_equal(obs[0], (conc * 255).astype(np.uint8))
+    assert len(np.unique(obs[0])) > 5 and obs[0].max() == 255          # partial cells: k / 25 * 255 truncated
+    far = (np.abs(np.arange(200) * 0.2 - ora.ship_pose()[1]) > 14)
+    assert obs[0][far].any(), "floes outside the egocentric range must appear"
+    # footprint: zeros outside, 255 inside the ship polygon scaled to cells (2 x 0.5 m -> ~ 25 cells)
+    assert set(np.unique(obs[1])) == {0, 255}
+    assert 12 <= int((obs[1] == 255).sum()) <= 45
     px, py, _ = ora.ship_pose()
-    assert obs[1][int(py * 25), int(px * 25)] == 255
+    assert obs[1][int(py * 5), int(px * 5)] == 255
 
 
 def test_emulated_global_observation_and_centroid_cache_match_oracle(golden_layouts, pins, portable_trig):
