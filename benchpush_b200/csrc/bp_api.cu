@@ -13,10 +13,7 @@
 #include "raster.cuh"
 #include "maze_raster.cuh"
 // the batched ship-ice / maze step, instantiated for 8 and for 4 envs per warp (sim_batch.cuh)
-#ifdef BP_BK
-#define BP_BK_MAIN BP_BK
-#undef BP_BK
-#else
+#ifndef BP_BK_MAIN          // make BK=<n>: envs per warp of the main instantiation (tuning experiments)
 #define BP_BK_MAIN 8
 #endif
 #define BP_BK BP_BK_MAIN
