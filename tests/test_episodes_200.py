@@ -1,0 +1,93 @@
+"""BASELINE config 1 / north-star acceptance: ship-ice-v0, default config, 200 seeded episodes with random actions.
+Golden scores come from the CPU oracle (tests/golden/shipice_200ep.npz, made by tools/make_golden_200ep.py):
+``libm_*`` with the oracle's default cos / sin (what Chipmunk calls), ``portable_*`` with the routine the kernels use.
+
+* CPU: the oracle still reproduces its own golden episodes (no drift), and the two trig modes give statistically
+  indistinguishable score distributions.
+* GPU: the 200 episodes run as one batch of 200 envs through the C ABI.  Against ``portable_*``: episode lengths and success
+  flags exact, efficiency / effort / reward within 1e-9 relative (summation order of the work term).  Against ``libm_*``
+  (the reference's arithmetic): success rate within the binomial 95 % interval, two-sample KS p > 0.05 on efficiency and
+  effort."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLD, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "shipice_200ep.npz"))
+
+
+def _stat_agree(a_succ, b_succ, a_eff, b_eff, a_effort, b_effort):
+    from scipy.stats import ks_2samp
+    n = len(a_succ)
+    p = float(np.mean(b_succ))
+    half = 1.96 * np.sqrt(p * (1 - p) / n)
+    assert abs(float(np.mean(a_succ)) - p) <= half + 1e-12, (np.mean(a_succ), p, half)
+    assert ks_2samp(a_eff, b_eff).pvalue > 0.05
+    assert ks_2samp(a_effort, b_effort).pvalue > 0.05
+
+
+def test_oracle_reproduces_golden_episodes_and_trig_modes_agree(gold):
+    import make_golden_200ep as g
+    assert np.array_equal(gold["actions"], g.actions_table())
+    for k, portable in ((3, 0), (117, 1)):
+        tag = "portable" if portable else "libm"
+        _, n, succ, eff, effort, rew, work = g.run_episode((k, portable))
+        assert n == int(gold["%s_steps" % tag][k]) and succ == bool(gold["%s_success" % tag][k])
+        np.testing.assert_allclose([eff, effort, rew, work], [gold["%s_efficiency" % tag][k], gold["%s_effort" % tag][k],
+                                                               gold["%s_reward" % tag][k], gold["%s_total_work" % tag][k]], rtol=1e-12, atol=1e-12)
+    from oracle import cpo
+    cpo.set_portable_trig(False)
+    assert 0.5 < gold["libm_success"].mean() < 1.0 and gold["libm_steps"].max() <= 300
+    _stat_agree(gold["portable_success"], gold["libm_success"], gold["portable_efficiency"], gold["libm_efficiency"],
+                gold["portable_effort"], gold["libm_effort"])
+
+
+@pytest.mark.gpu
+def test_200_seeded_episodes_on_the_gpu_match_the_oracle_distributions(gold):
+    import torch
+    import make_golden_200ep as g
+    from benchpush_b200.envs import ShipIceVecEnv
+    from benchpush_b200.layouts import generate_experiment, pack_trials
+    from benchpush_b200.metrics import ShipIceMetric
+    E = g.N_EP
+    packed = pack_trials(generate_experiment(100, g.CONC, seed=g.SEED_LAYOUT))
+    env = ShipIceVecEnv(num_envs=E, cfg={"concentration": g.CONC}, layouts=packed, device=0, first_trial=np.arange(E) % 100)
+    obs, info = env.reset()
+    met = ShipIceMetric("gpu", ship_mass=env.cfg.ship.mass, goal=env.goal)
+    met.reset(info)
+    acts = torch.as_tensor(gold["actions"], device=env.device)
+    alive = torch.ones(E, dtype=torch.bool, device=env.device)
+    steps = np.zeros(E, dtype=np.int32)
+    succ = np.zeros(E, dtype=bool); eff = np.zeros(E); effort = np.zeros(E); rew = np.zeros(E)
+    for t in range(g.MAX_STEPS):
+        obs, r, term, trunc, info = env.step(acts[:, t], mask=alive)
+        done = (term | (t == g.MAX_STEPS - 1)) & alive
+        met.update(info, torch.where(alive, r, torch.zeros_like(r)), done)
+        steps += alive.cpu().numpy()
+        if bool(done.any()):
+            idx = torch.nonzero(done).flatten().cpu().numpy()
+            succ[idx] = info["trial_success"][idx].cpu().numpy()
+            eff[idx] = met.compute_efficiency_score()[idx].cpu().numpy()
+            effort[idx] = met.compute_effort_score()[idx].cpu().numpy()
+            rew[idx] = met.eps_reward[idx].cpu().numpy()
+        alive = alive & ~done
+        if not bool(alive.any()):
+            break
+    env.close()
+    assert len(met.rewards) == E
+    # the kernels' own arithmetic: episode by episode
+    assert np.array_equal(steps, gold["portable_steps"])
+    assert np.array_equal(succ, gold["portable_success"].astype(bool))
+    np.testing.assert_allclose(eff, gold["portable_efficiency"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(effort, gold["portable_effort"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(rew, gold["portable_reward"], rtol=1e-9, atol=1e-7)
+    # the reference's arithmetic (libm cos / sin): statistically indistinguishable
+    _stat_agree(succ, gold["libm_success"], eff, gold["libm_efficiency"], effort, gold["libm_effort"])
