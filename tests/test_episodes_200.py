@@ -24,6 +24,34 @@ def gold():
     return np.load(os.path.join(GOLD, "shipice_200ep.npz"))
 
 
+def _run_batch(env, met, actions, max_steps):
+    """All episodes as one batch: step the envs still alive with their recorded actions, collect per-env scores."""
+    import torch
+    E = env.num_envs
+    obs, info = env.reset()
+    met.reset(info)
+    acts = torch.as_tensor(actions, device=env.device)
+    alive = torch.ones(E, dtype=torch.bool, device=env.device)
+    steps = np.zeros(E, dtype=np.int32)
+    succ = np.zeros(E, dtype=bool); eff = np.zeros(E); effort = np.zeros(E); rew = np.zeros(E)
+    for t in range(max_steps):
+        obs, r, term, trunc, info = env.step(acts[:, t], mask=alive)
+        done = (term | (t == max_steps - 1)) & alive
+        met.update(info, torch.where(alive, r, torch.zeros_like(r)), done)
+        steps += alive.cpu().numpy()
+        if bool(done.any()):
+            idx = torch.nonzero(done).flatten().cpu().numpy()
+            succ[idx] = info["trial_success"][idx].cpu().numpy()
+            eff[idx] = met.compute_efficiency_score()[idx].cpu().numpy()
+            effort[idx] = met.compute_effort_score()[idx].cpu().numpy()
+            rew[idx] = met.eps_reward[idx].cpu().numpy()
+        alive = alive & ~done
+        if not bool(alive.any()):
+            break
+    assert len(met.rewards) == E
+    return steps, succ, eff, effort, rew
+
+
 def _stat_agree(a_succ, b_succ, a_eff, b_eff, a_effort, b_effort):
     from scipy.stats import ks_2samp
     n = len(a_succ)
@@ -60,29 +88,9 @@ def test_200_seeded_episodes_on_the_gpu_match_the_oracle_distributions(gold):
     E = g.N_EP
     packed = pack_trials(generate_experiment(100, g.CONC, seed=g.SEED_LAYOUT))
     env = ShipIceVecEnv(num_envs=E, cfg={"concentration": g.CONC}, layouts=packed, device=0, first_trial=np.arange(E) % 100)
-    obs, info = env.reset()
     met = ShipIceMetric("gpu", ship_mass=env.cfg.ship.mass, goal=env.goal)
-    met.reset(info)
-    acts = torch.as_tensor(gold["actions"], device=env.device)
-    alive = torch.ones(E, dtype=torch.bool, device=env.device)
-    steps = np.zeros(E, dtype=np.int32)
-    succ = np.zeros(E, dtype=bool); eff = np.zeros(E); effort = np.zeros(E); rew = np.zeros(E)
-    for t in range(g.MAX_STEPS):
-        obs, r, term, trunc, info = env.step(acts[:, t], mask=alive)
-        done = (term | (t == g.MAX_STEPS - 1)) & alive
-        met.update(info, torch.where(alive, r, torch.zeros_like(r)), done)
-        steps += alive.cpu().numpy()
-        if bool(done.any()):
-            idx = torch.nonzero(done).flatten().cpu().numpy()
-            succ[idx] = info["trial_success"][idx].cpu().numpy()
-            eff[idx] = met.compute_efficiency_score()[idx].cpu().numpy()
-            effort[idx] = met.compute_effort_score()[idx].cpu().numpy()
-            rew[idx] = met.eps_reward[idx].cpu().numpy()
-        alive = alive & ~done
-        if not bool(alive.any()):
-            break
+    steps, succ, eff, effort, rew = _run_batch(env, met, gold["actions"], g.MAX_STEPS)
     env.close()
-    assert len(met.rewards) == E
     # the kernels' own arithmetic: episode by episode
     assert np.array_equal(steps, gold["portable_steps"])
     assert np.array_equal(succ, gold["portable_success"].astype(bool))
@@ -91,3 +99,44 @@ def test_200_seeded_episodes_on_the_gpu_match_the_oracle_distributions(gold):
     np.testing.assert_allclose(rew, gold["portable_reward"], rtol=1e-9, atol=1e-7)
     # the reference's arithmetic (libm cos / sin): statistically indistinguishable
     _stat_agree(succ, gold["libm_success"], eff, gold["libm_efficiency"], effort, gold["libm_effort"])
+
+
+@pytest.fixture(scope="module")
+def gold_maze():
+    return np.load(os.path.join(GOLD, "maze_200ep.npz"))
+
+
+def test_maze_oracle_reproduces_golden_episodes(gold_maze):
+    import make_golden_200ep_maze as g
+    assert np.array_equal(gold_maze["actions"], g.actions_table())
+    for k, portable in ((11, 0), (150, 1)):
+        tag = "portable" if portable else "libm"
+        _, n, succ, eff, effort, rew, work = g.run_episode((k, portable))
+        assert n == int(gold_maze["%s_steps" % tag][k]) and succ == bool(gold_maze["%s_success" % tag][k])
+        np.testing.assert_allclose([eff, effort, rew, work], [gold_maze["%s_efficiency" % tag][k], gold_maze["%s_effort" % tag][k],
+                                                               gold_maze["%s_reward" % tag][k], gold_maze["%s_total_work" % tag][k]], rtol=1e-12, atol=1e-12)
+    from oracle import cpo
+    cpo.set_portable_trig(False)
+    # random steering never threads the maze: every episode ends on a wall (success 0, efficiency 0), lengths 46..132
+    assert gold_maze["libm_success"].sum() == 0 and gold_maze["libm_steps"].max() < g.MAX_STEPS
+    _stat_agree(gold_maze["portable_success"], gold_maze["libm_success"], gold_maze["portable_efficiency"], gold_maze["libm_efficiency"],
+                gold_maze["portable_effort"], gold_maze["libm_effort"])
+
+
+@pytest.mark.gpu
+def test_200_seeded_maze_episodes_on_the_gpu_match_the_oracle(gold_maze):
+    """maze-NAMO-v0, 200 seeded layouts with 5 movable obstacles, random actions: same criteria as ship-ice."""
+    import make_golden_200ep_maze as g
+    from benchpush_b200.envs import MazeNamoVecEnv
+    from benchpush_b200.metrics import MazeNamoMetric
+    E = g.N_EP
+    env = MazeNamoVecEnv(num_envs=E, layouts=g.layouts(), device=0, first_layout=np.arange(E))
+    met = MazeNamoMetric("gpu", robot_mass=1)
+    steps, succ, eff, effort, rew = _run_batch(env, met, gold_maze["actions"], g.MAX_STEPS)
+    env.close()
+    assert np.array_equal(steps, gold_maze["portable_steps"])
+    assert np.array_equal(succ, gold_maze["portable_success"].astype(bool))
+    np.testing.assert_allclose(eff, gold_maze["portable_efficiency"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(effort, gold_maze["portable_effort"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(rew, gold_maze["portable_reward"], rtol=1e-9, atol=1e-7)
+    _stat_agree(succ, gold_maze["libm_success"], eff, gold_maze["libm_efficiency"], effort, gold_maze["libm_effort"])
