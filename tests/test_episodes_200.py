@@ -140,3 +140,48 @@ def test_200_seeded_maze_episodes_on_the_gpu_match_the_oracle(gold_maze):
     np.testing.assert_allclose(effort, gold_maze["portable_effort"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(rew, gold_maze["portable_reward"], rtol=1e-9, atol=1e-7)
     _stat_agree(succ, gold_maze["libm_success"], eff, gold_maze["libm_efficiency"], effort, gold_maze["libm_effort"])
+
+
+@pytest.mark.gpu
+def test_200_seeded_area_clearing_episodes_match_the_oracle_distributions():
+    """area-clearing-v0 (BASELINE config 3): 200 seeded layouts, random heading actions, TaskDrivenMetric scores.  The room
+    envs are not bit-comparable over whole episodes (the controller's atan2 / sin / cos are libm's on the device and numpy's
+    in the oracle), so the criterion is the statistical one: two-sample KS p > 0.05 on episode length, success
+    fraction, efficiency and effort against the oracle's golden run (tools/make_golden_200ep_areaclr.py)."""
+    from scipy.stats import ks_2samp
+    import make_golden_200ep_areaclr as g
+    from benchpush_b200.envs import AreaClearingVecEnv
+    from benchpush_b200.metrics import TaskDrivenMetric
+    gold = np.load(os.path.join(GOLD, "areaclr_200ep.npz"))
+    E = g.N_EP
+    assert np.array_equal(gold["actions"], g.actions_table())
+    env = AreaClearingVecEnv(num_envs=E, layouts=[g.layout(k) for k in range(E)], device=0)
+    obs, info = env.reset()
+    met = TaskDrivenMetric("gpu", robot_mass=1)
+    met.reset(info)
+    acts = gold["actions"]
+    alive = np.ones(E, dtype=bool)
+    steps = np.zeros(E, dtype=np.int32)
+    succ = np.zeros(E); eff = np.zeros(E); effort = np.zeros(E)
+    for t in range(g.MAX_STEPS):
+        obs, r, term, trunc, info = env.step(acts[:, t], mask=alive.astype(np.uint8))
+        done = (term.cpu().numpy() | trunc.cpu().numpy() | (t == g.MAX_STEPS - 1)) & alive
+        rr = r.cpu().numpy().copy(); rr[~alive] = 0.0
+        n0 = len(met.rewards)
+        met.update(info, rr, done)
+        steps += alive
+        idx = np.nonzero(done)[0]
+        succ[idx] = met.success_rates[n0:]; eff[idx] = met.efficiency_scores[n0:]; effort[idx] = met.effort_scores[n0:]
+        alive &= ~done
+        if not alive.any():
+            break
+    env.close()
+    assert len(met.rewards) == E
+    same = float(np.mean(steps == gold["steps"]))
+    print("area-clearing: %.0f %% of the episodes have the oracle's length; success %.3f vs %.3f, effort %.4f vs %.4f"
+          % (100 * same, succ.mean(), gold["success"].mean(), effort.mean(), gold["effort"].mean()))
+    assert ks_2samp(steps, gold["steps"]).pvalue > 0.05
+    assert ks_2samp(succ, gold["success"]).pvalue > 0.05
+    assert ks_2samp(eff, gold["efficiency"]).pvalue > 0.05
+    assert ks_2samp(effort, gold["effort"]).pvalue > 0.05
+    assert abs(effort.mean() - gold["effort"].mean()) < 0.02
