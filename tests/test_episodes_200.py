@@ -185,3 +185,46 @@ def test_200_seeded_area_clearing_episodes_match_the_oracle_distributions():
     assert ks_2samp(eff, gold["efficiency"]).pvalue > 0.05
     assert ks_2samp(effort, gold["effort"]).pvalue > 0.05
     assert abs(effort.mean() - gold["effort"].mean()) < 0.02
+
+
+@pytest.mark.gpu
+def test_200_seeded_box_delivery_episodes_match_the_oracle_distributions():
+    """box-delivery-v0 (BASELINE config 2's env): 200 seeded small_empty layouts (the reference's sampler, RandomState(42 + k)),
+    random heading actions for up to 100 steps, TaskDrivenMetric scores; statistical criterion as for area-clearing."""
+    from scipy.stats import ks_2samp
+    import make_golden_200ep_boxdel as g
+    from benchpush_b200.envs import BoxDeliveryVecEnv
+    from benchpush_b200.metrics import TaskDrivenMetric
+    gold = np.load(os.path.join(GOLD, "boxdel_200ep.npz"))
+    E = g.N_EP
+    assert np.array_equal(gold["actions"], g.actions_table())
+    env = BoxDeliveryVecEnv(num_envs=E, cfg=g.CFG, layouts=[g.layout(k) for k in range(E)], device=0)
+    obs, info = env.reset()
+    met = TaskDrivenMetric("gpu", robot_mass=1)
+    met.reset(info)
+    acts = gold["actions"]
+    alive = np.ones(E, dtype=bool)
+    steps = np.zeros(E, dtype=np.int32)
+    succ = np.zeros(E); eff = np.zeros(E); effort = np.zeros(E)
+    for t in range(g.MAX_STEPS):
+        obs, r, term, trunc, info = env.step(acts[:, t], mask=alive.astype(np.uint8))
+        done = (term.cpu().numpy() | trunc.cpu().numpy() | (t == g.MAX_STEPS - 1)) & alive
+        rr = r.cpu().numpy().copy(); rr[~alive] = 0.0
+        n0 = len(met.rewards)
+        met.update(info, rr, done)
+        steps += alive
+        idx = np.nonzero(done)[0]
+        succ[idx] = met.success_rates[n0:]; eff[idx] = met.efficiency_scores[n0:]; effort[idx] = met.effort_scores[n0:]
+        alive &= ~done
+        if not alive.any():
+            break
+    env.close()
+    assert len(met.rewards) == E
+    same = float(np.mean(steps == gold["steps"]))
+    print("box-delivery: %.0f %% of the episodes have the oracle's length; success %.3f vs %.3f, efficiency %.4f vs %.4f, effort %.4f vs %.4f"
+          % (100 * same, succ.mean(), gold["success"].mean(), eff.mean(), gold["efficiency"].mean(), effort.mean(), gold["effort"].mean()))
+    assert ks_2samp(steps, gold["steps"]).pvalue > 0.05
+    assert ks_2samp(succ, gold["success"]).pvalue > 0.05
+    assert ks_2samp(eff, gold["efficiency"]).pvalue > 0.05
+    assert ks_2samp(effort, gold["effort"]).pvalue > 0.05
+    assert abs(effort.mean() - gold["effort"].mean()) < 0.02
