@@ -19,6 +19,9 @@
 #define BP_BK BP_BK_MAIN
 #define BP_BATCH_NS bk_main
 #include "sim_batch.cuh"
+// the resident step (awake world in shared memory) builds on the main instantiation
+#define BP_RES_NS bk_main
+#include "sim_res.cuh"
 #undef BP_BK
 #undef BP_BATCH_NS
 #define BP_BK 4
@@ -121,6 +124,23 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepAr
     }
 BP_DEFINE_STEP_KERNEL(k_shipice_step, bk_main)
 BP_DEFINE_STEP_KERNEL(k_shipice_step_small, bk_small)
+
+// Resident step: one warp per block, the awake world of its RK envs in dynamic shared memory (sim_res.cuh).
+__global__ void __launch_bounds__(32) k_shipice_step_res(StepArgs a) {
+    extern __shared__ __align__(128) unsigned char bp_res_smem[];
+    res::ResShared& S = *reinterpret_cast<res::ResShared*>(bp_res_smem);
+    load_shared_offsets(a.C->off);
+    if (threadIdx.x == 0) { bp_mbar_init(&S.mbar, 32); S.mbar_phase = 0; }
+    __syncwarp();
+    for (;;) {
+        int env0 = 0;
+        if (threadIdx.x == 0) env0 = atomicAdd(a.counter, res::RK);
+        env0 = __shfl_sync(0xffffffffu, env0, 0);
+        if (env0 >= a.d.n_envs) break;
+        res::shipice_step_resident(a.C, S, a.mem, a.env_bytes, env0, a.actions, a.mask, a.out, a.auto_reset);
+        __syncwarp();
+    }
+}
 
 struct ObsArgs {
     char* mem; size_t env_bytes; Dims d; LayoutTab T; ObsParams O;
@@ -263,6 +283,8 @@ struct bp_shipice {
     DevConst hc_host;              // its host copy (bp_shipice_set_start_poses patches one pointer)
     char* snap = nullptr;          // post-reset env block of every layout (reset = copy)
     bool warp_impl = false;        // BP_STEP_IMPL=warp: one env per warp (A/B measurements)
+    bool res_impl = false;         // resident step (sim_res.cuh): the default for ship-ice; BP_STEP_IMPL=batch selects sim_batch.cuh
+    int res_blocks_per_sm = 1;
     StepOut out;               // internal device outputs
     int32_t* d_layout_ids = nullptr;
     float* d_actions = nullptr; uint8_t* d_obs = nullptr;   // only for the host-buffer entry point
@@ -432,6 +454,22 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
         CUDA_TRY(cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice));
     }
     if (const char* e = getenv("BP_STEP_IMPL")) h->warp_impl = (strcmp(e, "warp") == 0);
+    // resident step (sim_res.cuh), ship-ice only (the per-substep checks of the maze run on the env block).  Selected with
+    // BP_STEP_IMPL=res: in fp64 only three pools fit an SM, and three warps per SM issue too slowly to beat the batched
+    // kernel (profiles/r02a_*), so the batched kernel stays the default.
+    h->res_impl = false;
+    if (const char* e = getenv("BP_STEP_IMPL")) if (strcmp(e, "res") == 0 && h->kind == KIND_SHIPICE) h->res_impl = true;
+    if (h->res_impl) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, h->cfg.device));
+        size_t need = sizeof(res::ResShared);
+        if (need > prop.sharedMemPerBlockOptin) return fail(BP_ERR_CUDA, "resident step needs more shared memory per block than the device offers");
+        CUDA_TRY(cudaFuncSetAttribute(k_shipice_step_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        int per_sm = (int)(prop.sharedMemPerMultiprocessor / (need + prop.reservedSharedMemPerBlock + sizeof(EnvOff) + 64));
+        if (per_sm < 1) per_sm = 1;
+        if (const char* e = getenv("BP_RES_BLOCKS_PER_SM")) { int b = atoi(e); if (b > 0 && b < per_sm) per_sm = b; }   // tuning experiments only
+        h->res_blocks_per_sm = per_sm;
+    }
     h->hc_host = hc;
     h->layouts_loaded = true;
     return BP_OK;
@@ -562,7 +600,13 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
     a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
     a.actions = actions; a.layout_ids = nullptr; a.mask = mask; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset; a.C = h->d_const; a.use_snap = h->snap ? 1 : 0;
     prof_begin(h, 0, st);
-    if (h->warp_impl) k_shipice_step_warp<<<sim_grid(h), 128, 0, st>>>(a);
+    if (h->res_impl) {
+        int blocks = h->sm_count * h->res_blocks_per_sm;
+        int need = (h->d.n_envs + res::RK - 1) / res::RK;
+        if (blocks > need) blocks = need;
+        k_shipice_step_res<<<blocks, 32, sizeof(res::ResShared), st>>>(a);
+    }
+    else if (h->warp_impl) k_shipice_step_warp<<<sim_grid(h), 128, 0, st>>>(a);
     else if (use_small_batches(h)) k_shipice_step_small<<<batch_grid(h), 128, 0, st>>>(a);
     else k_shipice_step<<<batch_grid(h), 128, 0, st>>>(a);
     prof_end(h, st);

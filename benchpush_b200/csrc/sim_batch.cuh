@@ -43,6 +43,7 @@ struct BatchShared {             // one per warp, in shared memory
     int off_col[BCOL + 1];
     int n_items;                 // merged list length, -1 = does not fit (per-env fallback)
     int n_col, wl_valid;
+    int skip_res;                // resident step (sim_res.cuh): gate == -2 marks a touching pair that is evaluated from shared memory
     unsigned char flags[BK];     // bit0 yaw violated, bit1 boundary violated (ship_ice_env.py:284-290)
     unsigned wl[BWL];            // (e << 16) | slot, grouped by colour
     unsigned q0[BQ], q1[BQ];     // (e << 24) | index into apairs
@@ -241,64 +242,10 @@ BP_DEVNI void batch_build_worklist(const DevConst* C, BatchShared& S) {
     bp_wsync();
 }
 
-// One physics substep (cpSpaceStep) for every env of the batch.
-BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double prev_dt) {
+// Collide phase of a substep for every env of the batch with S.base[e] != nullptr: gate scan -> need test -> GJK -> (EPA) over
+// the concatenated awake-pair lists.
+BP_DEVNI void batch_collide(const DevConst* C, BatchShared& S) {
     const int lane = bp_lane();
-    const SimParams& P = C->P;
-    const Dims& d = C->d;
-    // ---- 0. stamps, offsets of the concatenated awake list
-    for (int e = lane; e < BK; e += BP_NL)
-        if (S.base[e]) { EnvScal* sc = (EnvScal*)S.base[e]; sc->stamp++; sc->any_wake = 0; S.dmax_bits[e] = 0ull; }
-    if (lane == 0) {
-        int acc = 0;
-        for (int e = 0; e < BK; e++) { S.off_awake[e] = acc; if (S.base[e]) acc += ((const EnvScal*)S.base[e])->n_awake; }
-        S.off_awake[BK] = acc;
-    }
-    bp_wsync();
-    // ---- 1. integrate positions of the awake bodies
-    {
-        const int tot = S.off_awake[BK];
-        for (int i = lane; i < tot; i += BP_NL) {
-            int e = find_env(S.off_awake, i), k = i - S.off_awake[e];
-            char* base = S.base[e];
-            EnvView ev = view_s(base);
-            EnvScal* sc = ev.sc;
-            const LayoutView& L = S.L[e];
-            int b = ev.awake[k];
-            BodyRec& R = ev.body[b];
-            bp_prefetch(L.lv + (size_t)b * VMAX * 2, 2);
-            double vx = R.vx, vy = R.vy, vw = R.vw, bx = R.bx, by = R.by, bw = R.bw;
-            bool mv = (vx != 0.0 || vy != 0.0 || vw != 0.0 || bx != 0.0 || by != 0.0 || bw != 0.0);
-            if (mv) {
-                double dx = (vx + bx) * dt, dy = (vy + by) * dt, da = (vw + bw) * dt;
-                R.px = R.px + dx; R.py = R.py + dy; R.pa = R.pa + da;
-                double dD = (fabs(dx) + fabs(dy) + L.rbound[b] * fabs(da)) * 1.000001;
-                R.D += dD;
-                bp_atomic_max_u64(&S.dmax_bits[e], bp_d2bits(dD));
-                refresh_body_b(C, base, L, b);
-                double mg = body_margin(P, sc, b);
-                BBox c = ev.bb[b], o = ev.b0[b];
-                if (c.l < o.l - mg || c.r > o.r + mg || c.b < o.b - mg || c.t > o.t + mg) sc->rebuild = 1;
-                ev.moved_step[b] = 1; ev.mvrb[b] = 1;
-                R.bx = 0.0; R.by = 0.0; R.bw = 0.0;
-            }
-            ev.moved[b] = mv ? 1 : 0;
-        }
-    }
-    bp_wsync();
-    for (int e = lane; e < BK; e += BP_NL)
-        if (S.base[e]) { EnvScal* sc = (EnvScal*)S.base[e]; sc->G += 2.0 * bp_bits2d(S.dmax_bits[e]) * 1.000001; }
-    bp_wsync();
-    // ---- rare: neighbour-list rebuild, one env at a time
-    for (int e = 0; e < BK; e++) {
-        char* base = S.base[e];
-        if (base && ((const EnvScal*)base)->rebuild) {
-            EnvView ev = view_s(base);
-            rebuild_pairs_inc(ev, P, d);
-            build_apairs(ev);
-        }
-    }
-    // ---- 2. collide: gate scan -> need test -> GJK -> (EPA) over the concatenated awake-pair lists
     if (lane == 0) {
         int acc = 0;
         for (int e = 0; e < BK; e++) { S.off_ap[e] = acc; if (S.base[e]) acc += ((const EnvScal*)S.base[e])->n_apairs; }
@@ -317,7 +264,8 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
                 if (i < total) {
                     int e = find_env(S.off_ap, i), k = i - S.off_ap[e];
                     EnvView ev = view_s(S.base[e]);
-                    pass = ev.sc->G >= ev.ap_gate[k];
+                    double gt = ev.ap_gate[k];
+                    pass = ev.sc->G >= gt && !(S.skip_res && gt == -2.0);
                     ent = ((unsigned)e << 24) | (unsigned)k;
                 }
                 int t; int rk = bp_wrank(pass, &t);
@@ -398,6 +346,66 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
         }
     }
     bp_wsync();
+}
+
+// One physics substep (cpSpaceStep) for every env of the batch.
+BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double prev_dt) {
+    const int lane = bp_lane();
+    const SimParams& P = C->P;
+    const Dims& d = C->d;
+    // ---- 0. stamps, offsets of the concatenated awake list
+    for (int e = lane; e < BK; e += BP_NL)
+        if (S.base[e]) { EnvScal* sc = (EnvScal*)S.base[e]; sc->stamp++; sc->any_wake = 0; S.dmax_bits[e] = 0ull; }
+    if (lane == 0) {
+        int acc = 0;
+        for (int e = 0; e < BK; e++) { S.off_awake[e] = acc; if (S.base[e]) acc += ((const EnvScal*)S.base[e])->n_awake; }
+        S.off_awake[BK] = acc;
+    }
+    bp_wsync();
+    // ---- 1. integrate positions of the awake bodies
+    {
+        const int tot = S.off_awake[BK];
+        for (int i = lane; i < tot; i += BP_NL) {
+            int e = find_env(S.off_awake, i), k = i - S.off_awake[e];
+            char* base = S.base[e];
+            EnvView ev = view_s(base);
+            EnvScal* sc = ev.sc;
+            const LayoutView& L = S.L[e];
+            int b = ev.awake[k];
+            BodyRec& R = ev.body[b];
+            bp_prefetch(L.lv + (size_t)b * VMAX * 2, 2);
+            double vx = R.vx, vy = R.vy, vw = R.vw, bx = R.bx, by = R.by, bw = R.bw;
+            bool mv = (vx != 0.0 || vy != 0.0 || vw != 0.0 || bx != 0.0 || by != 0.0 || bw != 0.0);
+            if (mv) {
+                double dx = (vx + bx) * dt, dy = (vy + by) * dt, da = (vw + bw) * dt;
+                R.px = R.px + dx; R.py = R.py + dy; R.pa = R.pa + da;
+                double dD = (fabs(dx) + fabs(dy) + L.rbound[b] * fabs(da)) * 1.000001;
+                R.D += dD;
+                bp_atomic_max_u64(&S.dmax_bits[e], bp_d2bits(dD));
+                refresh_body_b(C, base, L, b);
+                double mg = body_margin(P, sc, b);
+                BBox c = ev.bb[b], o = ev.b0[b];
+                if (c.l < o.l - mg || c.r > o.r + mg || c.b < o.b - mg || c.t > o.t + mg) sc->rebuild = 1;
+                ev.moved_step[b] = 1; ev.mvrb[b] = 1;
+                R.bx = 0.0; R.by = 0.0; R.bw = 0.0;
+            }
+            ev.moved[b] = mv ? 1 : 0;
+        }
+    }
+    bp_wsync();
+    for (int e = lane; e < BK; e += BP_NL)
+        if (S.base[e]) { EnvScal* sc = (EnvScal*)S.base[e]; sc->G += 2.0 * bp_bits2d(S.dmax_bits[e]) * 1.000001; }
+    bp_wsync();
+    // ---- rare: neighbour-list rebuild, one env at a time
+    for (int e = 0; e < BK; e++) {
+        char* base = S.base[e];
+        if (base && ((const EnvScal*)base)->rebuild) {
+            EnvView ev = view_s(base);
+            rebuild_pairs_inc(ev, P, d);
+            build_apairs(ev);
+        }
+    }
+    batch_collide(C, S);
     // ---- rare per-env events: wake closure, cache expiry, recolouring
     for (int e = 0; e < BK; e++) {
         char* base = S.base[e];
@@ -510,7 +518,7 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
         if (lane == 0) { S.base[e] = base; S.env_id[e] = env; S.flags[e] = 0; }
         bp_wsync();
     }
-    if (lane == 0) S.wl_valid = 0;
+    if (lane == 0) { S.wl_valid = 0; S.skip_res = 0; }
     bp_wsync();
     bool any = false;
     for (int e = 0; e < BK; e++) any = any || (S.base[e] != nullptr);

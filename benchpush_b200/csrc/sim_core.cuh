@@ -477,14 +477,15 @@ struct Manifold { int count; V2 n; V2 p1[2], p2[2]; unsigned hash[2]; };
 BP_DEV Poly body_poly(const EnvView& ev, const LayoutView& L, int b) { Poly P; P.v = ev.wv + (size_t)b * VMAX * 2; P.n = L.nv[b]; return P; }
 BP_DEV V2 bb_centre(const BBox& r) { return mk((r.l + r.r) * 0.5, (r.b + r.t) * 0.5); }
 
-// Contact manifold (<= 2 points, world space) of bodies a, b from the closest-feature result.
-BP_DEV void make_manifold_impl(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {
-    Poly A = body_poly(ev, L, a), B = body_poly(ev, L, b);
+// Contact manifold (<= 2 points, world space) from the closest-feature result.  The polygons, radii, local edge normals and
+// rotations come in as plain values / pointers, so the same arithmetic serves the env block in global memory and the
+// shared-memory resident copy of the awake bodies (sim_res.cuh).
+BP_DEV void make_manifold_core(const Poly& A, const Poly& B, double ra, double rb, const double* lnA, const double* lnB,
+                               double rcA, double rsA, double rcB, double rsB, const Closest& pts, Manifold* m) {
     m->count = 0;
-    double ra = L.rad[a], rb = L.rad[b];
     if (pts.d - ra - rb <= 0.0) {
-        EdgeW e1 = support_edge(A, L.ln + (size_t)a * VMAX * 2, ev.body[a].rc, ev.body[a].rs, pts.n);
-        EdgeW e2 = support_edge(B, L.ln + (size_t)b * VMAX * 2, ev.body[b].rc, ev.body[b].rs, neg(pts.n));
+        EdgeW e1 = support_edge(A, lnA, rcA, rsA, pts.n);
+        EdgeW e2 = support_edge(B, lnB, rcB, rsB, neg(pts.n));
         double mindist = ra + rb;
         if (pts.d <= mindist) {
             V2 n = pts.n; m->n = n;
@@ -510,6 +511,10 @@ BP_DEV void make_manifold_impl(const EnvView& ev, const LayoutView& L, int a, in
             }
         }
     }
+}
+BP_DEV void make_manifold_impl(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) {
+    make_manifold_core(body_poly(ev, L, a), body_poly(ev, L, b), L.rad[a], L.rad[b], L.ln + (size_t)a * VMAX * 2, L.ln + (size_t)b * VMAX * 2,
+                       ev.body[a].rc, ev.body[a].rs, ev.body[b].rc, ev.body[b].rs, pts, m);
 }
 
 BP_DEVNI void make_manifold(const EnvView& ev, const LayoutView& L, int a, int b, const Closest& pts, Manifold* m) { make_manifold_impl(ev, L, a, b, pts, m); }

@@ -573,12 +573,11 @@ BP_DEVNI void build_order(const EnvView& ev, const LayoutView& L, const Dims& d)
 }
 
 // ------------------------------------------------------------------ solver pieces (cpArbiter.c)
-BP_DEV void arb_prestep(const EnvView& ev, const LayoutView& L, const SimParams& P, int s) {
-    SlotRec& S = ev.slot[s];
-    int a = S.a, b = S.b;
+// The three solver pieces work on references (one arbiter, its two bodies), so that the env block in global memory and the
+// shared-memory resident copy (sim_res.cuh) run the same arithmetic.  Only the first 112 bytes of a BodyRec are touched.
+BP_DEV void arb_prestep_core(SlotRec& S, const BodyRec& A, const BodyRec& B, const SimParams& P) {
     V2 n = mk(S.nx, S.ny);
     V2 tn = perp(n);
-    const BodyRec& A = ev.body[a]; const BodyRec& B = ev.body[b];
     double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     V2 delta = mk(B.px - A.px, B.py - A.py);
     V2 va = mk(A.vx, A.vy), vb = mk(B.vx, B.vy);
@@ -600,12 +599,13 @@ BP_DEV void arb_prestep(const EnvView& ev, const LayoutView& L, const SimParams&
         c.bounce = dot(vr, n) * S.e;
     }
 }
-BP_DEV void arb_warm(const EnvView& ev, const LayoutView& L, int s, double dt_coef) {
+BP_DEV void arb_prestep(const EnvView& ev, const LayoutView& L, const SimParams& P, int s) {
     SlotRec& S = ev.slot[s];
+    arb_prestep_core(S, ev.body[S.a], ev.body[S.b], P);
+}
+BP_DEV void arb_warm_core(const SlotRec& S, BodyRec& A, BodyRec& B, double dt_coef) {
     if (S.first) return;
-    int a = S.a, b = S.b;
     V2 n = mk(S.nx, S.ny);
-    BodyRec& A = ev.body[a]; BodyRec& B = ev.body[b];
     double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     int cnt = S.cnt;
 #pragma unroll 1
@@ -618,13 +618,14 @@ BP_DEV void arb_warm(const EnvView& ev, const LayoutView& L, int s, double dt_co
         B.vx = B.vx + j.x * mb; B.vy = B.vy + j.y * mb; B.vw += ib * cross(r2, j);
     }
 }
-BP_DEV void arb_solve(const EnvView& ev, const LayoutView& L, int s) {
+BP_DEV void arb_warm(const EnvView& ev, const LayoutView& L, int s, double dt_coef) {
     SlotRec& S = ev.slot[s];
-    int a = S.a, b = S.b;
+    arb_warm_core(S, ev.body[S.a], ev.body[S.b], dt_coef);
+}
+BP_DEV void arb_solve_core(SlotRec& S, BodyRec& A, BodyRec& B) {
     V2 n = mk(S.nx, S.ny);
     V2 tn = perp(n);
     double fr = S.u;
-    BodyRec& A = ev.body[a]; BodyRec& B = ev.body[b];
     double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     V2 va = mk(A.vx, A.vy), vb = mk(B.vx, B.vy);
     double wa = A.vw, wb = B.vw;
@@ -663,6 +664,10 @@ BP_DEV void arb_solve(const EnvView& ev, const LayoutView& L, int s) {
     // kinematic / static bodies have m_inv = i_inv = 0: their velocities are unchanged (x + 0), skip the stores
     if (ma != 0.0 || ia != 0.0) { A.vx = va.x; A.vy = va.y; A.vw = wa; A.bx = ba.x; A.by = ba.y; A.bw = bwa; }
     if (mb != 0.0 || ib != 0.0) { B.vx = vb.x; B.vy = vb.y; B.vw = wb; B.bx = bb.x; B.by = bb.y; B.bw = bwb; }
+}
+BP_DEV void arb_solve(const EnvView& ev, const LayoutView& L, int s) {
+    SlotRec& S = ev.slot[s];
+    arb_solve_core(S, ev.body[S.a], ev.body[S.b]);
 }
 
 // Steps 3-6 of a substep for ONE env: prestep, velocity update, warm start, iterations.
@@ -705,6 +710,7 @@ BP_DEVNI void solve_env(const EnvView& ev, const LayoutView& L, const SimParams&
 }
 
 // ------------------------------------------------------------------ one substep (cpSpaceStep)
+BP_DEVNI void substep_rest(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, double dt, double prev_dt);
 BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, double dt, double prev_dt) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
@@ -739,6 +745,12 @@ BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P
     if (lane == 0) sc->G += 2.0 * dmax * 1.000001;
     bp_wsync();
     BP_TOCK(sc, 0, tk);
+    substep_rest(ev, L, P, d, dt, prev_dt);
+}
+// Everything of a substep after the position update: neighbour-list rebuild, collide, wake closure, cache expiry, solve.
+BP_DEVNI void substep_rest(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, double dt, double prev_dt) {
+    EnvScal* sc = ev.sc;
+    BP_TICK(tk);
     if (sc->rebuild) { rebuild_pairs_inc(ev, P, d); build_apairs(ev); }
     BP_TOCK(sc, 1, tk);
     // 2. collide, then close the awake set over newly touching bodies

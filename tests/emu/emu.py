@@ -9,11 +9,15 @@ _CSRC = os.path.join(_HERE, "..", "..", "benchpush_b200", "csrc")
 
 
 def build():
-    so = os.path.join(_HERE, "libbp_emu.so")
+    # BP_EMU_FLAGS: extra compiler flags (e.g. "-DBP_RES_PA=20" to shrink the resident pool and exercise parking); each set of
+    # flags builds its own library
+    extra = os.environ.get("BP_EMU_FLAGS", "").split()
+    tag = ("_" + "".join(c if c.isalnum() else "_" for c in "".join(extra))) if extra else ""
+    so = os.path.join(_HERE, "libbp_emu%s.so" % tag)
     srcs = [os.path.join(_HERE, "emu_harness.cpp")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-o", so,
-                               os.path.join(_HERE, "emu_harness.cpp")])
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared"] + extra +
+                              ["-o", so, os.path.join(_HERE, "emu_harness.cpp")])
     return so
 
 
@@ -56,6 +60,10 @@ class Emu:
     def step_batch(self, env0, actions, auto_reset=False):
         a = np.ascontiguousarray(actions, dtype=np.float32)
         self.L.emu_step_batch(self.h, C.c_int(env0), a.ctypes.data_as(C.c_void_p), C.c_int(1 if auto_reset else 0))
+
+    def step_resident(self, env0, actions, auto_reset=False):
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        self.L.emu_step_resident(self.h, C.c_int(env0), a.ctypes.data_as(C.c_void_p), C.c_int(1 if auto_reset else 0))
 
     def batch_size(self):
         return int(self.L.emu_batch_size())

@@ -9,6 +9,8 @@
 #include <vector>
 #include "../../benchpush_b200/csrc/host_tables.h"
 #include "../../benchpush_b200/csrc/sim_batch.cuh"
+#define BP_RES_NS bk_default
+#include "../../benchpush_b200/csrc/sim_res.cuh"
 #include "../../benchpush_b200/csrc/raster.cuh"
 #include "../../benchpush_b200/csrc/maze_raster.cuh"
 #include "../../benchpush_b200/csrc/spfa.cuh"
@@ -84,6 +86,17 @@ void emu_step_batch(void* h, int env0, const float* actions, int auto_reset) {
     load_shared_offsets(C.off);
     shipice_step_batch(&C, S, e->mem.data(), e->env_bytes, env0, actions, nullptr, e->out, auto_reset);
 }
+// the resident path (sim_res.cuh): same contract, the awake world staged in a "shared memory" pool
+void emu_step_resident(void* h, int env0, const float* actions, int auto_reset) {
+    Emu* e = (Emu*)h;
+    static DevConst C;
+    C.d = e->d; C.P = e->P; C.off = env_offsets(e->d); C.T = e->T; C.snap = nullptr; C.env_bytes = e->env_bytes; C.snap_pose = nullptr; C.snap_status = nullptr;
+    C.start_pose = nullptr;
+    static res::ResShared S;
+    load_shared_offsets(C.off);
+    res::shipice_step_resident(&C, S, e->mem.data(), e->env_bytes, env0, actions, nullptr, e->out, auto_reset);
+}
+int emu_res_pool(int what) { return what == 0 ? res::R_PA : what == 1 ? res::R_PV : res::R_PS; }
 int emu_batch_size() { return BK; }
 // one raw physics substep (for per-substep parity); robot velocity set explicitly
 void emu_set_robot_velocity(void* h, int env, double vx, double vy, double w) {

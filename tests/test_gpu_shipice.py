@@ -214,3 +214,28 @@ def test_batched_evaluate_loop(golden_layouts):
     assert all(0.0 <= e <= 1.0 + 1e-9 for e in res["effort_scores"])
     assert res["rewards"][0] == res["rewards"][1] == res["rewards"][2]       # same layout, same actions
     env.close()
+
+
+def test_resident_step_equals_batched_step(monkeypatch):
+    """BP_STEP_IMPL=res (sim_res.cuh: the awake world of a batch staged in shared memory with cp.async.bulk, all 400 substeps
+    on the pool) against the default batched kernel: bit-identical body states, rewards and observations over whole episodes
+    with auto reset, at a batch that fills several pools and forces parking."""
+    packed = pack_trials(generate_experiment(6, 0.5, seed=5))
+    E = 96
+    envs = {}
+    for impl in ("batch", "res"):
+        monkeypatch.setenv("BP_STEP_IMPL", impl)
+        envs[impl] = _make_env(packed, 0.5, n=E, auto_reset=True)
+        envs[impl].reset()
+    monkeypatch.delenv("BP_STEP_IMPL")
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    for k in range(45):
+        a = torch.rand(E, generator=g, device="cuda") * 2 - 1
+        ra = envs["batch"].step(a)
+        rb = envs["res"].step(a)
+        assert torch.equal(ra[0], rb[0]), k
+        assert torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]), k
+        for e in (0, 7, 8, 50, E - 1):
+            assert np.array_equal(envs["batch"].get_bodies(e), envs["res"].get_bodies(e)), (k, e)
+    for v in envs.values():
+        v.close()

@@ -118,3 +118,29 @@ def test_product_hull_matches_oracle_hull_on_synthetic():
         m = env.space.shape_mass(s)
         np.testing.assert_allclose(1.0 / mi[0], m[0], rtol=1e-14)
         np.testing.assert_allclose(1.0 / mi[1], m[3], rtol=1e-12)
+
+
+@pytest.mark.parametrize("flags", ["", "-DBP_RES_PA=24 -DBP_RES_PV=300 -DBP_RES_PS=20 -DBP_RES_DEBUG", "-DBP_RES_PA=12 -DBP_RES_PV=150 -DBP_RES_PS=8"])
+def test_resident_path_equals_batched_path(flags, monkeypatch):
+    """sim_res.cuh (awake world of a batch staged in a shared-memory pool) against sim_batch.cuh: bit-identical over whole
+    episodes incl. auto reset.  The small pools force the rare paths: envs parked at a substep boundary, envs evicted in the
+    middle of a substep (completed from the env block), envs that do not fit an empty pool (one-env path)."""
+    if flags:
+        monkeypatch.setenv("BP_EMU_FLAGS", flags)
+    nl = 5
+    packed = pack_trials(generate_experiment(nl, 0.5, seed=11))
+    E = 10
+    kw = dict(pmax=8 * (packed.max_floes + 1), lmax=2 * (packed.max_floes + 1))
+    A, B = Emu(E, packed, SHIP_VERTS, **kw), Emu(E, packed, SHIP_VERTS, **kw)
+    for e in range(E):
+        A.reset(e, e % nl); B.reset(e, e % nl)
+    rng = np.random.default_rng(0)
+    big = int(np.argmax(packed.n_floes))
+    for k in range(45):
+        acts = rng.uniform(-1, 1, E).astype(np.float32)
+        for e0 in range(0, E, A.batch_size()):
+            A.step_batch(e0, acts, True)
+            B.step_resident(e0, acts, True)
+        for e in range(E):
+            assert np.array_equal(A.bodies(e, big), B.bodies(e, big)), (k, e)
+            assert A.out(e) == B.out(e), (k, e)

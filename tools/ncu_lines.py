@@ -18,8 +18,16 @@ for ln in dis:
     m = re.match(r"^(\$?[_A-Za-z0-9$]+):\s*$", ln)
     if m and not ln.startswith(".L_x"):
         name = m.group(1)
-        mm = re.search(r"_ZN2bp(\d+)([a-z_0-9]+)", name)
-        func = mm.group(2)[:int(mm.group(1))] if mm else name[:40]
+        func = name[:40]
+        name = name.split("$")[-1] if "$" in name else name
+        if name.startswith("_ZN"):
+            # nested names: <len><id><len><id>...; keep the last component (the function)
+            i = 3; parts = []
+            while i < len(name) and name[i].isdigit():
+                j = i
+                while name[j].isdigit(): j += 1
+                n = int(name[i:j]); parts.append(name[j:j + n]); i = j + n
+            if parts: func = parts[-1]
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
