@@ -61,14 +61,21 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle)
 def _cpu_worker(args):
-    """One host process: one env of the workload stepped with the oracle for ~budget seconds."""
-    idx, seed, budget, nsteps = args
+    """One host process: one env of the workload stepped with the oracle for ~budget seconds (or nsteps env steps).
+    ``pre`` untimed env steps come first, so that the timed steps sit at the same mix of episode phases as the GPU arm
+    (an episode lasts >= 34 steps and gets more expensive as the ship enters the ice)."""
+    idx, seed, budget, nsteps = args[:4]
+    pre = args[4] if len(args) > 4 else 0
     from benchpush_b200.layouts import generate_experiment
     from oracle.ship_ice_oracle import ShipIceOracleEnv
     trials = generate_experiment(1, CONC, seed=99 + idx)
     env = ShipIceOracleEnv({"concentration": CONC}, experiment=trials, order_mode=1)
     env.reset()
     rng = np.random.default_rng(seed)
+    for _ in range(pre):
+        o, r, term, _, info = env.step(float(rng.uniform(-1, 1)))
+        if term:
+            env.reset()
     t0 = time.perf_counter()
     n = 0
     while True:
@@ -84,13 +91,18 @@ def _cpu_worker(args):
     return n, time.perf_counter() - t0
 
 
-def cpu_sample(budget_s, nsteps=None, cores=None):
+def _phase(i, cores, desync):
+    """Untimed env steps of host core i before its timed sample: the cores are spread evenly over one episode."""
+    return (i * max(desync, 1)) // max(cores, 1) if desync > 1 else 0
+
+
+def cpu_sample(budget_s, nsteps=None, cores=None, desync=34):
     """Env-steps/s of the oracle with one env per host core, all cores busy at once."""
     import multiprocessing as mp
     cores = cores or (os.cpu_count() or 1)
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(i, 1000 + i, budget_s, nsteps) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(i, 1000 + i, budget_s, nsteps, _phase(i, cores, desync)) for i in range(cores)])
     steps = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
     return steps / wall, cores, steps, wall
@@ -107,8 +119,8 @@ def run_reference(a):
     ctx = mp.get_context("spawn")
     t_all = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(i, 1000 + i, 0.0, max(a.warmup, 1)) for i in range(cores)])          # warm-up (incl. reset)
-        res = pool.map(_cpu_worker, [(i, 2000 + i, 0.0, a.steps) for i in range(cores)])
+        # every core: reset, (its episode-phase offset + the warm-up steps) untimed, then the timed steps on the same env
+        res = pool.map(_cpu_worker, [(i, 2000 + i, 0.0, a.steps, _phase(i, cores, a.desync) + a.warmup) for i in range(cores)])
     steps = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
     val = steps / wall
@@ -117,6 +129,7 @@ def run_reference(a):
         "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "ship-ice-v0 concentration 0.5 (synthetic seeded layouts), one env per host core, random actions",
+                   "episode_phase": "core i advanced (i * %d // cores) + warm-up steps untimed before its timed steps (same spread over an episode as the GPU arm)" % a.desync,
                    "note": "the reference env cannot run here (pymunk/gymnasium absent): this is the restated reference (oracle/, fp64 C++ Chipmunk restatement + numpy rasters)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d env steps per core on %d cores (one env per core, incl. observation + reward)" % (a.steps, cores)},
@@ -256,23 +269,32 @@ def run_ours(a):
 
     # ---- end to end through the public host-buffer API: actions H2D (pinned) + results D2H every step
     h_actions = [torch.empty(E, dtype=torch.float32).pin_memory().copy_(actions[k].cpu()) for k in range(a.warmup, total)]
-    hb = env.step_host(h_actions[0].numpy())                                  # allocate host staging outside the timed region
+    hb = env.step_host(h_actions[0].numpy(), want_obs="device")               # allocate host staging outside the timed region
     # episode scoring (ShipIceMetric) runs on the host results, inside the end-to-end region, as evaluate() does
     def host_info(hb):
         return {"state": torch.from_numpy(hb["state"]), "total_work": torch.from_numpy(hb["total_work"]),
                 "trial_success": torch.from_numpy(hb["trial_success"]).bool()}
     metric = ShipIceMetric("random", ship_mass=env.cfg.ship.mass, goal=env.goal)
     metric.reset(host_info(hb))
+    prev_done = torch.from_numpy(hb["terminated"]).bool().clone()
     barrier()
+    e2e_l0 = env.launch_count()
     t0 = time.perf_counter()
     e2e_resets = 0
     for k in range(a.steps):
-        hb = env.step_host(h_actions[k].numpy())
+        # the step kernel AND the observation kernel run every step; the 4x150x150 image stays in the env's device tensor
+        hb = env.step_host(h_actions[k].numpy(), want_obs="device")
+        hi_ = host_info(hb)
+        if bool(prev_done.any()):
+            metric.reset(hi_, mask=prev_done)                                 # next-step auto reset: this call returned the reset state
         term = torch.from_numpy(hb["terminated"]).bool()
-        metric.update(host_info(hb), torch.from_numpy(hb["reward"]), term)
+        metric.update(hi_, torch.from_numpy(hb["reward"]), term)
+        prev_done = term.clone()
         e2e_resets += int(hb["terminated"].sum())
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    e2e_launches = env.launch_count() - e2e_l0
+    assert e2e_launches == 2 * a.steps, "end-to-end region must launch the step and the observation kernel every step (%d launches in %d steps)" % (e2e_launches, a.steps)
     # terminations of step k are resets of step k+1; the last step's are not inside the window, the priming step's are
     e2e_steps = E * a.steps - e2e_resets
     h2d = E * 4
@@ -293,22 +315,29 @@ def run_ours(a):
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         try:
-            v, cores, n, wall = cpu_sample(a.cpu_seconds)
+            v, cores, n, wall = cpu_sample(a.cpu_seconds, desync=a.desync)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "oracle (restated reference, fp64): one env per core on %d cores, %d env steps of the same workload in %.1f s" % (cores, n, wall)}
+                   "sample": "oracle (restated reference, fp64): one env per core on %d cores, %d env steps of the same workload in %.1f s, "
+                             "cores spread over the episode phases like the GPU envs" % (cores, n, wall)}
         except Exception as ex:                                               # the GPU numbers stand on their own
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
     if rank == 0:
         peak, peak_src = peaks()
         step_ms_avg = km["step_ms"] / max(km["step_launches"], 1)
-        alg_bytes_launch = alg_bytes_per_env * E
+        # algorithmic bytes of one launch = bytes per env step x the envs that STEPPED in it (auto-reset envs do not step)
+        stepped_per_launch = env_steps / max(a.steps, 1)
+        alg_bytes_launch = alg_bytes_per_env * stepped_per_launch
         achieved = alg_bytes_launch / (step_ms_avg * 1e-3) / 1e9 if step_ms_avg > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_env_step") * E
+                tj = json.load(open(tp))
+                # the ncu capture was taken on the full-GPU kernel; a small per-GPU batch runs another instantiation: no figure
+                if E >= int(tj.get("min_envs_per_gpu", 0)):
+                    traffic = tj.get("dram_bytes_per_env_step") * stepped_per_launch
+                    traffic_src = tj.get("source")
             except Exception:
                 traffic = None
         line = {
@@ -322,13 +351,17 @@ def run_ours(a):
                        "episode_phase": "steady state: env g advanced (g mod %d) steps before the warm-up, auto reset inside the timed region" % a.desync if a.desync > 1 else "all envs start at reset",
                        "env_steps_timed": int(tsum[2]), "resets_timed": n_resets, "env_status_bits": int(tmax[7])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src, "envs_stepped_per_launch": stepped_per_launch,
                          "kernel": "k_shipice_step", "kernel_ms": step_ms_avg, "obs_kernel_ms": km["obs_ms"] / max(km["obs_launches"], 1),
                          "algorithmic_bytes_per_env_step": alg_bytes_per_env, "peak_source": peak_src,
                          "note": "path is latency/issue bound by 400 sequential substeps (SURVEY.md §8d); HBM is the ceiling, not the limiter"},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "bp_shipice_step_host: actions from pinned host memory, reward/terminated/truncated/state/total_work/success/status read back every step; observations stay on the device for the policy"},
+                    "launches_in_region": int(e2e_launches),
+                    "what": "bp_shipice_step_host_obs_device: actions from pinned host memory, step kernel + observation kernel every step, "
+                            "reward/terminated/truncated/state/total_work/success/status read back every step and scored on the host (ShipIceMetric); "
+                            "the 4x150x150 u8 images are rendered into the env's device tensor for a policy on the GPU and not copied"},
             "gpu_launches": int(tsum[6]),
             "episode_metrics": red,
         }

@@ -88,6 +88,7 @@ def lib():
         L.bp_shipice_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
         L.bp_shipice_step_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
         L.bp_shipice_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs)]
+        L.bp_shipice_step_host_obs_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
         L.bp_shipice_get_obstacles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.bp_shipice_low_dim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bp_maze_low_dim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -123,7 +124,7 @@ def lib():
 
 EXPORTS = [
     "bp_version", "bp_last_error", "bp_device_count", "bp_shipice_default_config", "bp_shipice_create",
-    "bp_shipice_destroy", "bp_shipice_load_layouts", "bp_shipice_reset", "bp_shipice_step", "bp_shipice_step_masked", "bp_shipice_step_host",
+    "bp_shipice_destroy", "bp_shipice_load_layouts", "bp_shipice_reset", "bp_shipice_step", "bp_shipice_step_masked", "bp_shipice_step_host", "bp_shipice_step_host_obs_device",
     "bp_shipice_get_obstacles", "bp_shipice_get_bodies", "bp_shipice_get_counters", "bp_shipice_env_bytes", "bp_shipice_low_dim", "bp_maze_low_dim", "bp_shipice_obs_global", "bp_shipice_obs_global_shape", "bp_shipice_set_start_poses", "bp_maze_set_start_poses",
     "bp_shipice_set_profiling", "bp_shipice_get_kernel_ms",
     "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host",

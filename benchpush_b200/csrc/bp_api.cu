@@ -621,24 +621,29 @@ int bp_shipice_step(bp_shipice_t* h, const float* actions, const bp_shipice_outp
     return bp_shipice_step_masked(h, actions, nullptr, out, stream);
 }
 
-int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* oh) {
+static int step_host_impl(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* oh, uint8_t* obs_dev) {
     if (!h || !actions || !oh) return fail(BP_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     size_t E = h->d.n_envs;
     if (!h->d_actions) CUDA_TRY(cudaMalloc((void**)&h->d_actions, E * 4));
     const size_t obs_bytes = h->kind == KIND_MAZE ? (size_t)MZ_OBS_C * MZ_PIX : (size_t)BP_OBS_C * OBS_PIX;
-    if (oh->obs && !h->d_obs) CUDA_TRY(cudaMalloc((void**)&h->d_obs, E * obs_bytes));
+    if (oh->obs && !obs_dev && !h->d_obs) CUDA_TRY(cudaMalloc((void**)&h->d_obs, E * obs_bytes));
     CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions, E * 4, cudaMemcpyHostToDevice, 0));
     bp_shipice_outputs dev;
     memset(&dev, 0, sizeof(dev));
-    dev.obs = oh->obs ? h->d_obs : nullptr;
+    dev.obs = obs_dev ? obs_dev : (oh->obs ? h->d_obs : nullptr);
     int rc = bp_shipice_step(h, h->d_actions, &dev, nullptr);
     if (rc) return rc;
-    if (oh->obs) CUDA_TRY(cudaMemcpyAsync(oh->obs, h->d_obs, E * obs_bytes, cudaMemcpyDeviceToHost, 0));
+    if (oh->obs) CUDA_TRY(cudaMemcpyAsync(oh->obs, dev.obs, E * obs_bytes, cudaMemcpyDeviceToHost, 0));
     rc = copy_outputs(h, oh, 0, cudaMemcpyDeviceToHost);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(0));
     return BP_OK;
+}
+int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* oh) { return step_host_impl(h, actions, oh, nullptr); }
+int bp_shipice_step_host_obs_device(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* oh, uint8_t* obs_dev) {
+    if (!obs_dev) return fail(BP_ERR_INVALID, "null observation buffer");
+    return step_host_impl(h, actions, oh, obs_dev);
 }
 
 static int fetch_env(bp_shipice* h, int env, std::vector<char>& buf) {

@@ -5,7 +5,8 @@ from .maze_namo import MazeNamoVecEnv
 from .ship_ice import ShipIceVecEnv
 
 REGISTRY = {"ship-ice-v0": ShipIceVecEnv, "maze-NAMO-v0": MazeNamoVecEnv, "box-delivery-v0": BoxDeliveryVecEnv, "area-clearing-v0": AreaClearingVecEnv}
-MAX_EPISODE_STEPS = {"ship-ice-v0": 300, "box-delivery-v0": 30000, "area-clearing-v0": 400, "maze-NAMO-v0": 30000}
+# max_episode_steps of the reference registry (benchpush/environments/__init__.py:3-51)
+MAX_EPISODE_STEPS = {"ship-ice-v0": 300, "box-delivery-v0": 30000, "maze-NAMO-v0": 400, "area-clearing-v0": 30000}
 
 
 def make(env_id: str, num_envs: int, cfg=None, **kw):

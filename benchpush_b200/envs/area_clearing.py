@@ -26,7 +26,7 @@ import numpy as np
 from .. import _lib
 from ..layouts import sample_area_clearing_layout
 from ..utils import DotDict, merge_cfg
-from .box_delivery import BoxDelConfig, BoxDeliveryVecEnv, bind, disk
+from .box_delivery import LAYOUT_EPISODE_STRIDE, BoxDelConfig, BoxDeliveryVecEnv, bind, default_pool_episodes, disk
 
 ENVS = {   # area_clearing/envs/*.yaml restated (environments without inner walls)
     "clear_env": {"outer_boundary": [[-8.0, -8.0], [-8.0, 8.0], [8.0, 8.0], [8.0, -8.0]],
@@ -122,7 +122,7 @@ class ClearingMaps:
 
 class AreaClearingVecEnv(BoxDeliveryVecEnv):
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
-                 seed: int = 1, env_offset: int = 0, _backend=None):
+                 seed: int = 1, env_offset: int = 0, _backend=None, layout_pool_episodes: Optional[int] = None):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"] not in ENVS:
@@ -157,8 +157,10 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
             for i in range(10):
                 self.goal_points.append(tuple(p0 + ((((i + 1 / 2) / 10) * length) / length) * (p1 - p0)))
         if layouts is None:
-            # keyed by the GLOBAL env id (env_offset = first env of this rank's shard)
-            layouts = [sample_area_clearing_layout(random.Random(seed + int(env_offset) + e), c, self.env_cfg) for e in range(E)]
+            # pool of F episodes per env keyed by (GLOBAL env id, episode), see BoxDeliveryVecEnv (env_offset = first env of this rank's shard)
+            F = default_pool_episodes(E) if layout_pool_episodes is None else max(1, int(layout_pool_episodes))
+            layouts = [sample_area_clearing_layout(random.Random(seed + int(env_offset) + e + f * LAYOUT_EPISODE_STRIDE), c, self.env_cfg)
+                       for f in range(F) for e in range(E)]
         self.layouts = [{"start": l["start"], "boxes": [[b[0], b[1], 0.0] for b in l["boxes"]]} for l in layouts]
         L = self._L
         k = BoxDelConfig()

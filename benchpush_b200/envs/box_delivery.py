@@ -195,11 +195,20 @@ class RoomMaps:
         self.robot_state_channel = chan
 
 
+LAYOUT_EPISODE_STRIDE = 1000003
+
+
+def default_pool_episodes(num_envs: int) -> int:
+    """Episodes per env in the default layout pool: 4, fewer for very large batches (the pool is built on the host)."""
+    return max(1, min(4, 65536 // max(int(num_envs), 1)))
+
+
 class BoxDeliveryVecEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
-                 seed: Optional[int] = None, force_box_spfa: bool = False, env_offset: int = 0, _backend=None):
+                 seed: Optional[int] = None, force_box_spfa: bool = False, env_offset: int = 0, _backend=None,
+                 layout_pool_episodes: Optional[int] = None):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"]["obstacle_config"] not in ("small_empty", "large_empty"):
@@ -231,8 +240,13 @@ class BoxDeliveryVecEnv:
         self.goal_points = [self.room.receptacle_position]
         if layouts is None:
             base = int(c["misc"]["random_seed"]) if seed is None else int(seed)
-            # layouts are keyed by the GLOBAL env id (env_offset = first env of this rank's shard): results do not depend on the number of ranks
-            layouts = [sample_box_delivery_layout(np.random.RandomState(base + int(env_offset) + e), c) for e in range(E)]
+            # The reference draws a fresh layout at every reset (box_delivery_env.py:509-546 from RandomState(42)).  Here the
+            # layouts are inputs: a pool of F episodes per env, entry f * E + e drawn from RandomState(base + global env id +
+            # f * LAYOUT_EPISODE_STRIDE) — keyed by (GLOBAL env id, episode), so results depend neither on the number of ranks
+            # (env_offset = first env of this rank's shard) nor on when other envs finish; an env's episode k runs on entry k mod F.
+            F = default_pool_episodes(E) if layout_pool_episodes is None else max(1, int(layout_pool_episodes))
+            layouts = [sample_box_delivery_layout(np.random.RandomState(base + int(env_offset) + e + f * LAYOUT_EPISODE_STRIDE), c)
+                       for f in range(F) for e in range(E)]
         self.layouts = list(layouts)
         # ---- native handle
         L = self._L
@@ -352,11 +366,15 @@ class BoxDeliveryVecEnv:
 
     # ---- gym API
     def reset(self, seed=None, options=None, mask=None):
-        """Every env (or those in ``mask``) starts episode ``episode_idx`` on layout (env + episode * num_envs) % n_layouts."""
+        """Every env (or those in ``mask``) starts its next episode: env e keeps its own episode counter k_e (advanced only
+        when e is reset) and runs on layout (e + k_e * num_envs) % n_layouts."""
         if mask is not None and not self._emu and hasattr(mask, "cpu"):
             mask = mask.to("cpu").numpy()
-        self.episode_idx = 0 if self.episode_idx is None else self.episode_idx + 1
-        ids = (np.arange(self.num_envs) + self.episode_idx * self.num_envs) % len(self.layouts)
+        if self.episode_idx is None:
+            self.episode_idx = np.full(self.num_envs, -1, dtype=np.int64)
+        sel = np.ones(self.num_envs, dtype=bool) if mask is None else np.asarray(mask).astype(bool).reshape(self.num_envs)
+        self.episode_idx[sel] += 1
+        ids = (np.arange(self.num_envs) + np.maximum(self.episode_idx, 0) * self.num_envs) % len(self.layouts)
         self._put("layout_ids", ids.astype(np.int32))
         mptr = None
         if mask is not None:

@@ -45,6 +45,7 @@ class MazeNamoVecEnv(ShipIceVecEnv):
         else:
             raise Exception("Invalid Maze Version!")
         self.low_dim_state = bool(self.cfg.low_dim_state)
+        self.auto_reset = bool(auto_reset)
         if self.cfg.random_start:
             raise NotImplementedError("cfg.random_start is not implemented for the maze: the reference samples the obstacles around the drawn "
                                       "start (maze_NAMO_env.py:229-301), so start poses and layouts have to be generated together; callers that "

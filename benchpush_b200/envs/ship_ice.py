@@ -274,8 +274,10 @@ class ShipIceVecEnv:
             mptr = C.c_void_p(self._mask.data_ptr())
         _lib.check(self._fn("step_masked")(self._h, C.c_void_p(action_dev.data_ptr()), mptr, C.byref(self._out), self._stream()))
 
-    def step_host(self, actions: np.ndarray, want_obs: bool = False):
-        """The same step through host buffers (numpy in, numpy out; copies inside)."""
+    def step_host(self, actions: np.ndarray, want_obs=False):
+        """The same step through host buffers (numpy in, numpy out; copies inside).  ``want_obs``: False = the observation
+        kernel is not launched; True = the image is rendered and copied to the host; "device" = the image is rendered into the
+        env's device tensor (``self.obs``, for a policy that runs on the GPU) and not copied (ship-ice egocentric image only)."""
         E = self.num_envs
         a = np.ascontiguousarray(actions, dtype=np.float32).reshape(E)
         if not hasattr(self, "_host"):
@@ -285,15 +287,20 @@ class ShipIceVecEnv:
         hb = self._host
         if want_obs and (self.low_dim_state or getattr(self, "_global_obs", False)):
             raise NotImplementedError("step_host returns the egocentric image only; use step() for the low-dimensional / global observation")
-        if want_obs and hb["obs"] is None:
+        if want_obs is True and hb["obs"] is None:
             hb["obs"] = np.zeros((E,) + self._obs_shape, np.uint8)
         o = _lib.ShipIceOutputs()
         o.reward = hb["reward"].ctypes.data; o.terminated = hb["terminated"].ctypes.data; o.truncated = hb["truncated"].ctypes.data
         o.state = hb["state"].ctypes.data; o.total_work = hb["total_work"].ctypes.data
         o.trial_success = hb["trial_success"].ctypes.data; o.status = hb["status"].ctypes.data
-        if want_obs:
+        if want_obs is True:
             o.obs = hb["obs"].ctypes.data
-        _lib.check(self._fn("step_host")(self._h, a.ctypes.data, C.byref(o)))
+        if want_obs == "device":
+            if self._prefix != "shipice":
+                raise NotImplementedError('want_obs="device" is a ship-ice entry point')
+            _lib.check(self._L.bp_shipice_step_host_obs_device(self._h, a.ctypes.data, C.byref(o), C.c_void_p(self.obs.data_ptr())))
+        else:
+            _lib.check(self._fn("step_host")(self._h, a.ctypes.data, C.byref(o)))
         return hb
 
     def close(self):

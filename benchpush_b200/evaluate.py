@@ -18,13 +18,19 @@ def evaluate(env, policy, metric, num_episodes: int, max_steps: int = 100000):
     obs, info = env.reset()
     metric.reset(info)
     auto = bool(getattr(env, "auto_reset", False))
+    prev_done = None
     for _ in range(max_steps):
         if len(metric.rewards) >= num_episodes:
             break
         obs, rew, term, trunc, info = env.step(policy(obs))
+        if auto and prev_done is not None and bool(prev_done.any()):
+            # next-step auto reset: for the envs that finished in the previous step this call returned the reset state of their
+            # next episode (reward 0).  Start their score accumulators from it; the update below is then a no-op for them.
+            metric.reset(info, mask=prev_done)
         done = _np(term).astype(bool) | _np(trunc).astype(bool)
         done_t = (term | trunc) if hasattr(term, "device") else done
         metric.update(info, rew, eps_complete=done_t)
+        prev_done = done_t.clone() if hasattr(done_t, "clone") else done.copy()
         if done.any() and not auto:
             obs, info = env.reset(mask=done_t if hasattr(done_t, "device") else done.astype(np.uint8))
             metric.reset(info, mask=done_t)

@@ -121,6 +121,10 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
 /* Same call with HOST buffers (pageable or pinned): copies actions to the device, steps, copies
  * obs / reward / terminated / truncated (and the non-NULL info arrays) back, and synchronises. */
 int bp_shipice_step_host(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out_host);
+/* The same with the observation left on the device for a policy that runs there: actions and every scalar output are HOST
+ * buffers as above, the observation kernel writes obs_dev[E][4][150][150] (DEVICE, caller-owned); when out_host->obs is set
+ * the image is additionally copied to that host buffer. */
+int bp_shipice_step_host_obs_device(bp_shipice_t* h, const float* actions, const bp_shipice_outputs* out_host, uint8_t* obs_dev);
 
 /* cfg.random_start (ship_ice_env.py:201-203; maze_NAMO_env.py:229-238): from now on every reset of env e — explicit or
  * the next-step auto reset inside bp_*_step — starts the ship / robot at poses[3e..3e+2] = (x, y, theta) instead of the

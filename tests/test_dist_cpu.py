@@ -77,7 +77,9 @@ def _worker_rooms(rank, world, port, q):
     acts = np.linspace(-0.8, 0.8, 4).astype(np.float32)[lo:hi]
     obs, rew, term, trunc, info = env.step(acts)
     m.update(info, rew, eps_complete=True)
-    q.put((rank, [l["start"] for l in env.layouts], [l["start"] for l in ac.layouts], env.get_bodies(0)[0, :3].tolist(), m.reduce()))
+    n = hi - lo            # the pool holds several episodes per env: entry f * n + e = (env lo + e, episode f)
+    q.put((rank, [[l["start"] for l in env.layouts[f * n:(f + 1) * n]] for f in range(len(env.layouts) // n)],
+           [l["start"] for l in ac.layouts[:n]], env.get_bodies(0)[0, :3].tolist(), m.reduce()))
     env.close(); ac.close()
     dist.destroy_process_group()
 
@@ -93,7 +95,11 @@ def test_room_envs_shard_by_global_env_id_world2_gloo():
     res = sorted(q.get(timeout=300) for _ in ps)
     [p.join(timeout=60) for p in ps]
     whole = BoxDeliveryVecEnv(num_envs=4, cfg={"agent": {"action_type": "heading"}}, _backend=emu_bd.lib())
-    assert res[0][1] + res[1][1] == [l["start"] for l in whole.layouts]          # same layouts as one rank with all envs
+    F = len(whole.layouts) // 4
+    assert F == len(res[0][1]) == len(res[1][1]) and F > 1
+    for f in range(F):       # same layouts as one rank with all envs, for every episode of the pool
+        assert res[0][1][f] + res[1][1][f] == [l["start"] for l in whole.layouts[4 * f:4 * f + 4]]
+    assert len(set(l["start"] for l in whole.layouts)) == 4 * F                   # and every (env, episode) has its own layout
     assert len(set(res[0][2] + res[1][2])) == 4
     whole.reset()
     whole.step(np.linspace(-0.8, 0.8, 4).astype(np.float32))

@@ -239,3 +239,22 @@ def test_resident_step_equals_batched_step(monkeypatch):
             assert np.array_equal(envs["batch"].get_bodies(e), envs["res"].get_bodies(e)), (k, e)
     for v in envs.values():
         v.close()
+
+
+def test_evaluate_scores_every_episode_under_auto_reset(golden_layouts):
+    """evaluate() with next-step auto reset must score the second and later episodes of an env like the explicit
+    masked-reset path does (accumulators restarted from the reset state the auto-resetting step returns)."""
+    from benchpush_b200.envs import ShipIceVecEnv
+    from benchpush_b200.evaluate import evaluate
+    from benchpush_b200.metrics import ShipIceMetric
+    packed = _concat([golden_layouts["c10_t0"], golden_layouts["c10_t7"]])
+    res = {}
+    for auto in (False, True):
+        env = ShipIceVecEnv(num_envs=2, cfg={"concentration": 0.1}, layouts=packed, device=0, auto_reset=auto, first_trial=np.array([0, 1], dtype=np.int32))
+        m = ShipIceMetric("straight", ship_mass=env.cfg.ship.mass, goal=env.goal)
+        res[auto] = evaluate(env, lambda obs: torch.full((2,), 0.3, dtype=torch.float32, device=obs.device), m, num_episodes=4, max_steps=200)
+        env.close()
+    for key in ("rewards", "efficiency_scores", "effort_scores"):
+        assert len(res[True][key]) == 4
+        np.testing.assert_allclose(sorted(res[True][key]), sorted(res[False][key]), rtol=1e-12, atol=1e-12)
+    assert len(set(np.round(res[True]["rewards"], 9))) > 1          # the two trials differ, so a carried-over accumulator would show

@@ -127,3 +127,22 @@ def test_velocity_actions_match_the_oracle(portable_trig):
         assert abs(float(out[4]["cumulative_distance"][0]) - oinfo["cumulative_distance"]) <= 1e-9
         assert int((out[0][0] != oobs).sum()) <= 4
     env.close()
+
+
+def test_masked_reset_advances_only_the_masked_envs_episode():
+    """Every env keeps its own episode counter: a masked reset moves only the masked envs to their next layout, and the
+    default pool holds several (env, episode) layouts per env (the reference re-randomises at every reset)."""
+    from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
+    from tests.emu import emu_bd
+    env = BoxDeliveryVecEnv(num_envs=3, cfg={"agent": {"action_type": "heading"}}, _backend=emu_bd.lib())
+    assert len(env.layouts) == 3 * 4
+    env.reset()
+    s0 = [tuple(env.get_bodies(e)[0, :3]) for e in range(3)]
+    env.reset(mask=np.array([0, 1, 0], dtype=np.uint8))
+    s1 = [tuple(env.get_bodies(e)[0, :3]) for e in range(3)]
+    assert s1[0] == s0[0] and s1[2] == s0[2] and s1[1] != s0[1]
+    assert env.episode_idx.tolist() == [0, 1, 0]
+    assert np.allclose(s1[1], env.layouts[1 + 1 * 3]["start"])
+    env.reset(mask=np.array([1, 0, 0], dtype=np.uint8))
+    assert np.allclose(env.get_bodies(0)[0, :3], env.layouts[0 + 1 * 3]["start"])     # env 0's episode 1, whenever it is reached
+    env.close()
