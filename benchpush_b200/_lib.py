@@ -97,6 +97,12 @@ def lib():
         L.bp_shipice_obs_global_shape.argtypes = [C.c_void_p, C.c_void_p]
         L.bp_shipice_obs_global.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bp_shipice_get_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        for fam in ("shipice", "maze"):
+            getattr(L, "bp_%s_state_bytes" % fam).argtypes = [C.c_void_p]
+            getattr(L, "bp_%s_state_bytes" % fam).restype = C.c_size_t
+            getattr(L, "bp_%s_get_state" % fam).argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+            getattr(L, "bp_%s_set_state" % fam).argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+            getattr(L, "bp_%s_set_bodies" % fam).argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         L.bp_shipice_get_counters.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.bp_shipice_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.bp_shipice_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
@@ -125,6 +131,8 @@ def lib():
 EXPORTS = [
     "bp_version", "bp_last_error", "bp_device_count", "bp_shipice_default_config", "bp_shipice_create",
     "bp_shipice_destroy", "bp_shipice_load_layouts", "bp_shipice_reset", "bp_shipice_step", "bp_shipice_step_masked", "bp_shipice_step_host", "bp_shipice_step_host_obs_device",
+    "bp_shipice_state_bytes", "bp_shipice_get_state", "bp_shipice_set_state", "bp_shipice_set_bodies",
+    "bp_maze_state_bytes", "bp_maze_get_state", "bp_maze_set_state", "bp_maze_set_bodies",
     "bp_shipice_get_obstacles", "bp_shipice_get_bodies", "bp_shipice_get_counters", "bp_shipice_env_bytes", "bp_shipice_low_dim", "bp_maze_low_dim", "bp_shipice_obs_global", "bp_shipice_obs_global_shape", "bp_shipice_set_start_poses", "bp_maze_set_start_poses",
     "bp_shipice_set_profiling", "bp_shipice_get_kernel_ms",
     "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host",

@@ -82,6 +82,12 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_reset(StepArgs a
     }
 }
 
+// bp_*_set_bodies: one warp puts one env into an externally given body state.
+__global__ void __launch_bounds__(32) k_shipice_set_bodies(StepArgs a, int env, const double* bodies6) {
+    EnvView ev = make_view(a.mem + a.env_bytes * (size_t)env, a.d);
+    shipice_set_bodies_env(ev, a.T, a.P, a.d, bodies6);
+}
+
 // One env per warp (the first design; kept for A/B measurements: BP_STEP_IMPL=warp).
 __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepArgs a) {
     int env;
@@ -646,6 +652,42 @@ int bp_shipice_step_host_obs_device(bp_shipice_t* h, const float* actions, const
     return step_host_impl(h, actions, oh, obs_dev);
 }
 
+size_t bp_shipice_state_bytes(bp_shipice_t* h) { return h ? h->env_bytes : 0; }
+int bp_shipice_get_state(bp_shipice_t* h, int32_t env, void* out_host) {
+    if (!h || !out_host || env < 0 || env >= h->d.n_envs) return fail(BP_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out_host, h->mem + h->env_bytes * (size_t)env, h->env_bytes, cudaMemcpyDeviceToHost));
+    return BP_OK;
+}
+int bp_shipice_set_state(bp_shipice_t* h, int32_t env, const void* in_host) {
+    if (!h || !in_host || env < 0 || env >= h->d.n_envs) return fail(BP_ERR_INVALID, "bad argument");
+    if (!h->was_reset) return fail(BP_ERR_STATE, "reset before set_state");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(h->mem + h->env_bytes * (size_t)env, in_host, h->env_bytes, cudaMemcpyHostToDevice));
+    return BP_OK;
+}
+int bp_shipice_set_bodies(bp_shipice_t* h, int32_t env, const double* bodies6, int32_t n_bodies) {
+    if (!h || !bodies6 || env < 0 || env >= h->d.n_envs) return fail(BP_ERR_INVALID, "bad argument");
+    if (!h->was_reset) return fail(BP_ERR_STATE, "reset before set_bodies");
+    if (n_bodies <= 0 || n_bodies > h->d.NB) return fail(BP_ERR_INVALID, "body count out of range");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    double* dbuf = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dbuf, (size_t)h->d.NB * 6 * 8));
+    CUDA_TRY(cudaMemset(dbuf, 0, (size_t)h->d.NB * 6 * 8));
+    CUDA_TRY(cudaMemcpy(dbuf, bodies6, (size_t)n_bodies * 6 * 8, cudaMemcpyHostToDevice));
+    StepArgs a;
+    a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
+    a.actions = nullptr; a.layout_ids = nullptr; a.mask = nullptr; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const; a.use_snap = 0;
+    k_shipice_set_bodies<<<1, 32>>>(a, env, dbuf);
+    h->launches++;
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(dbuf);
+    if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("k_shipice_set_bodies: ") + cudaGetErrorString(e));
+    return BP_OK;
+}
+
 static int fetch_env(bp_shipice* h, int env, std::vector<char>& buf) {
     if (env < 0 || env >= h->d.n_envs) return fail(BP_ERR_INVALID, "env index out of range");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -928,6 +970,10 @@ int bp_maze_low_dim(bp_maze_t* h, double* out, int32_t* counts, void* stream) {
 }
 int bp_maze_get_obstacles(bp_maze_t* h, int32_t env, double* verts, int32_t* n_verts) { return bp_shipice_get_obstacles(h, env, verts, n_verts); }
 int bp_maze_get_bodies(bp_maze_t* h, int32_t env, double* out) { return bp_shipice_get_bodies(h, env, out); }
+size_t bp_maze_state_bytes(bp_maze_t* h) { return bp_shipice_state_bytes(h); }
+int bp_maze_get_state(bp_maze_t* h, int32_t env, void* out_host) { return bp_shipice_get_state(h, env, out_host); }
+int bp_maze_set_state(bp_maze_t* h, int32_t env, const void* in_host) { return bp_shipice_set_state(h, env, in_host); }
+int bp_maze_set_bodies(bp_maze_t* h, int32_t env, const double* bodies6, int32_t n_bodies) { return bp_shipice_set_bodies(h, env, bodies6, n_bodies); }
 int bp_maze_get_maps(bp_maze_t* h, uint8_t* wall, double* dist_norm, double* dist_raw, int32_t* hw) {
     if (!h || h->kind != KIND_MAZE) return fail(BP_ERR_INVALID, "not a maze handle");
     size_t n = h->wall_map.size();

@@ -96,6 +96,30 @@ BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const Sim
     bp_wsync();
 }
 
+// Put env into an externally given body state (bp_*_set_bodies): poses and velocities from bodies6[nbody][6], empty arbiter
+// cache (like a pymunk Space whose cached arbiters were dropped), every body awake, neighbour list rebuilt, the work
+// accounting (prev_obs) restarted from the new poses.  Episode counters, layout and accumulated work are kept.
+BP_DEVNI void shipice_set_bodies_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, const double* bodies6) {
+    EnvScal* sc = ev.sc;
+    const int lane = bp_lane();
+    const int layout = sc->layout, t = sc->t, episode = sc->episode, first = sc->first_layout, done = sc->done, obs_raw = sc->obs_raw;
+    const int wall_hit = sc->wall_hit, has_prev = sc->has_prev_dist;
+    const double total_work = sc->total_work, prev_dist = sc->prev_dist;
+    bp_wsync();
+    LayoutView L = layout_view(T, d, layout);
+    init_env(ev, L, P, d, layout, nullptr, bodies6);
+    int nb = sc->nbody;
+    for (int b = lane; b < nb; b += BP_NL) {
+        if (body_dynamic(L, b)) area_centroid_abs(ev.wv + (size_t)b * VMAX * 2, L.nv[b], &ev.area[b], &ev.cenx[b], &ev.ceny[b]);
+        ev.moved_step[b] = 0;
+    }
+    if (lane == 0) {
+        sc->t = t; sc->episode = episode; sc->first_layout = first; sc->done = done; sc->obs_raw = 0; (void)obs_raw;
+        sc->total_work = total_work; sc->wall_hit = wall_hit; sc->has_prev_dist = has_prev; sc->prev_dist = prev_dist;
+    }
+    bp_wsync();
+}
+
 // ShipIceEnv.reset through the per-layout snapshot (DevConst::snap): identical to shipice_reset_env
 // because the post-reset state is a pure function of the layout.
 BP_DEVNI void shipice_reset_from_snapshot(const DevConst* C, char* base, int layout_id, int env, const StepOut& out) {

@@ -850,7 +850,10 @@ BP_DEVNI void sleep_pass(const EnvView& ev, const LayoutView& L, const Dims& d) 
 }
 
 // Initialise an environment from a layout: poses, zero velocities, everything awake, empty cache.
-BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, int layout_id, const double* start = nullptr) {
+// poses6 (optional, [nbody][6] = body position x, y, angle, vx, vy, w): start from an externally given state instead of the
+// layout's (bp_*_set_bodies: parity fixtures taken in the middle of an episode).
+BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, int layout_id, const double* start = nullptr,
+                       const double* poses6 = nullptr) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     const int nb = L.nbody;
@@ -866,7 +869,7 @@ BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& 
     for (int b = lane; b < nb; b += BP_NL) {
         BodyRec& R = ev.body[b];
         // every shape of the kinematic robot (bodies >= robot0) starts at the robot's pose
-        const double* ip = (start && b >= L.robot0) ? start : L.init + 3 * b;
+        const double* ip = poses6 ? poses6 + 6 * b : ((start && b >= L.robot0) ? start : L.init + 3 * b);
         double a = ip[2];
         double s, c; bp_sincos(a, &s, &c);
         double cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
@@ -875,6 +878,7 @@ BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& 
         R.py = (s * cx + c * cy) + ip[1];
         R.pa = a;
         R.vx = R.vy = R.vw = 0.0; R.bx = R.by = R.bw = 0.0; R.D = 0.0;
+        if (poses6) { R.vx = ip[3]; R.vy = ip[4]; R.vw = ip[5]; }
         R.minv = L.minv[b]; R.iinv = L.iinv[b]; R.pad0 = R.pad1 = 0.0;
         refresh_body(ev, L, b);
         ev.awake[b] = b; ev.is_awake[b] = 1; ev.moved[b] = 0; ev.moved_step[b] = 0; ev.act[b] = 1;

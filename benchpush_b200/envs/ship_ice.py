@@ -330,6 +330,25 @@ class ShipIceVecEnv:
         n = _lib.check(self._fn("get_bodies")(self._h, e, out.ctypes.data))
         return out[:n]
 
+    def get_state(self, e: int) -> np.ndarray:
+        """Checkpoint of env ``e`` (``bp_*_get_state``): its whole state block as bytes; feed it to :meth:`set_state` of a
+        handle with the same configuration and layouts to resume exactly (bit-identical continuation)."""
+        buf = np.zeros(int(self._fn("state_bytes")(self._h)), dtype=np.uint8)
+        _lib.check(self._fn("get_state")(self._h, e, buf.ctypes.data))
+        return buf
+
+    def set_state(self, e: int, state: np.ndarray):
+        s = np.ascontiguousarray(state, dtype=np.uint8)
+        if s.size != int(self._fn("state_bytes")(self._h)):
+            raise ValueError("state block of %d bytes does not belong to this handle (%d)" % (s.size, int(self._fn("state_bytes")(self._h))))
+        _lib.check(self._fn("set_state")(self._h, e, s.ctypes.data))
+
+    def set_bodies(self, e: int, bodies: np.ndarray):
+        """Put env ``e`` into an externally given body state ([n_bodies, 6] = x, y, angle, vx, vy, w in :meth:`get_bodies`
+        order), e.g. one taken from the oracle in the middle of an episode; the arbiter cache starts empty."""
+        b = np.ascontiguousarray(bodies, dtype=np.float64)
+        _lib.check(self._fn("set_bodies")(self._h, e, b.ctypes.data, b.shape[0]))
+
     def counters(self, e: int) -> dict:
         o = np.zeros(32, dtype=np.int64)
         _lib.check(self._L.bp_shipice_get_counters(self._h, e, o.ctypes.data))

@@ -155,6 +155,19 @@ int bp_shipice_get_obstacles(bp_shipice_t* h, int32_t env, double* verts, int32_
  * position x, y, angle, vx, vy, w per body; the ship is the last row.  Returns the body count. */
 int bp_shipice_get_bodies(bp_shipice_t* h, int32_t env, double* out);
 
+/* State of one env for checkpoint / resume and parity fixtures (SURVEY §8b `bp_get_state / bp_set_state`; the reference never
+ * serialises env state).  The state is the env's whole block: body poses / velocities, arbiter cache with its
+ * accumulated impulses, neighbour list, awake set, step counters, accumulated work.  HOST buffers of bp_shipice_state_bytes(h)
+ * bytes; a block is only meaningful for a handle with the same configuration and layouts.  Both calls synchronise. */
+size_t bp_shipice_state_bytes(bp_shipice_t* h);
+int bp_shipice_get_state(bp_shipice_t* h, int32_t env, void* out_host);
+int bp_shipice_set_state(bp_shipice_t* h, int32_t env, const void* in_host);
+/* Put env `env` into an EXTERNALLY given body state (e.g. one taken from the reference / the oracle in the middle of an
+ * episode): HOST bodies6[n_bodies][6] = position x, y, angle, vx, vy, w in the order of bp_shipice_get_bodies.  The arbiter
+ * cache starts empty (as in a pymunk Space whose cached arbiters were dropped), every body is awake, the work accounting
+ * restarts from the new poses; layout, episode counters and accumulated work are kept.  Synchronises. */
+int bp_shipice_set_bodies(bp_shipice_t* h, int32_t env, const double* bodies6, int32_t n_bodies);
+
 /* Counters of env `env`, HOST out[32]: stamp, n_awake, n_pairs, n_free, n_order, n_colours, status,
  * n_apairs, n_cached, gjk_iters, pairs_evaluated, live_sum, awake_sum, recolours, rebuilds, substeps,
  * epa_pairs, pairs_skipped_by_motion_bound, then 8 per-phase clock sums (only with BP_PHASE_TIMERS). */
@@ -253,6 +266,11 @@ int bp_maze_get_obstacles(bp_maze_t* h, int32_t env, double* verts, int32_t* n_v
 /* Body state of env `env`, HOST out[n*6] (x, y, angle, vx, vy, w) in shape creation order: walls, obstacles,
  * robot chassis, wheels.  Returns the body count. */
 int bp_maze_get_bodies(bp_maze_t* h, int32_t env, double* out);
+/* Same as bp_shipice_state_bytes / get_state / set_state / set_bodies, for a maze handle. */
+size_t bp_maze_state_bytes(bp_maze_t* h);
+int bp_maze_get_state(bp_maze_t* h, int32_t env, void* out_host);
+int bp_maze_set_state(bp_maze_t* h, int32_t env, const void* in_host);
+int bp_maze_set_bodies(bp_maze_t* h, int32_t env, const double* bodies6, int32_t n_bodies);
 /* The constant maps, HOST outputs (each may be NULL): wall[H*W] u8, dist_norm[H*W] (global_distance_map),
  * dist_raw[H*W] (info['goal_dt'], the un-normalised hop counts); hw[2] = {H, W}. */
 int bp_maze_get_maps(bp_maze_t* h, uint8_t* wall, double* dist_norm, double* dist_raw, int32_t* hw);

@@ -844,6 +844,18 @@ void* cpo_space_new(void) {
     return sp;
 }
 void cpo_space_free(void* h) { delete (Space*)h; }
+// Deep copy of a space (bodies, shapes, arbiter cache with its accumulated impulses, step counters): lets a test advance
+// the SAME state with two solver orders, or compare one transition from an identical mid-episode state.
+void* cpo_space_clone(void* h) {
+    Space* src = (Space*)h;
+    Space* sp = new Space(*src);
+    sp->arbiters.clear();
+    for (Arbiter* arb : src->arbiters) {
+        auto it = sp->cache.find(((uint64_t)arb->a << 32) | (uint64_t)(uint32_t)arb->b);
+        if (it != sp->cache.end()) sp->arbiters.push_back(&it->second);
+    }
+    return sp;
+}
 void cpo_space_set(void* h, int iterations, double damping, double gx, double gy) {
     Space* sp = (Space*)h; sp->iterations = iterations; sp->damping = damping; sp->gravity = v(gx, gy);
 }
@@ -955,6 +967,26 @@ void cpo_get_state(void* h, double* out) {
         double* o = out + 6 * i;
         o[0] = pos.x; o[1] = pos.y; o[2] = bd.a; o[3] = bd.vel.x; o[4] = bd.vel.y; o[5] = bd.w;
     }
+}
+// Put every body into an externally given state ([nb][6] = position x, y, angle, vx, vy, w as in cpo_get_state):
+// cpBodySetAngle, cpBodySetPosition, cpBodySetVelocity, cpBodySetAngularVelocity; bias velocities cleared.
+void cpo_set_state(void* h, const double* in) {
+    Space* sp = (Space*)h;
+    for (size_t i = 0; i < sp->bodies.size(); i++) {
+        Body& bd = sp->bodies[i];
+        const double* o = in + 6 * i;
+        bd.a = o[2];
+        set_transform(bd);
+        body_set_position(bd, v(o[0], o[1]));
+        bd.vel = v(o[3], o[4]); bd.w = o[5];
+        bd.v_bias = v(0, 0); bd.w_bias = 0;
+    }
+}
+// Drop every cached arbiter (contacts and accumulated impulses), as if the shapes had been removed and re-added.
+void cpo_clear_cache(void* h) {
+    Space* sp = (Space*)h;
+    sp->arbiters.clear();
+    sp->cache.clear();
 }
 void cpo_step(void* h, double dt) { space_step((Space*)h, dt); }
 

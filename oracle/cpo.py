@@ -46,6 +46,8 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.cpo_space_new.restype = C.c_void_p
         L.cpo_space_free.argtypes = [C.c_void_p]
+        L.cpo_space_clone.restype = C.c_void_p
+        L.cpo_space_clone.argtypes = [C.c_void_p]
         L.cpo_space_set.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
         L.cpo_space_set_order.argtypes = [C.c_void_p, C.c_int]
         L.cpo_body_new.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
@@ -63,6 +65,8 @@ def lib():
         L.cpo_num_bodies.argtypes = [C.c_void_p]
         L.cpo_get_state.argtypes = [C.c_void_p, dp]
         L.cpo_step.argtypes = [C.c_void_p, C.c_double]
+        L.cpo_set_state.argtypes = [C.c_void_p, dp]
+        L.cpo_clear_cache.argtypes = [C.c_void_p]
         L.cpo_shipice_substeps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
         L.cpo_segment_new.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
         L.cpo_maze_substeps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
@@ -102,6 +106,13 @@ class Space:
             self.L.cpo_space_free(self.h)
         except Exception:
             pass
+
+    def clone(self):
+        """Deep copy (bodies, shapes, arbiter cache, counters)."""
+        c = Space.__new__(Space)
+        c.L = self.L
+        c.h = C.c_void_p(self.L.cpo_space_clone(self.h))
+        return c
 
     def set_order(self, mode):
         self.L.cpo_space_set_order(self.h, int(mode))
@@ -190,6 +201,15 @@ class Space:
         out = np.empty((self.num_bodies(), 6), dtype=np.float64)
         self.L.cpo_get_state(self.h, _dp(out))
         return out
+
+    def set_state(self, st):
+        """Counterpart of :meth:`state`: poses and velocities of every body from ``st`` [n, 6]."""
+        st = np.ascontiguousarray(st, dtype=np.float64)
+        assert st.shape == (self.num_bodies(), 6)
+        self.L.cpo_set_state(self.h, _dp(st))
+
+    def clear_cache(self):
+        self.L.cpo_clear_cache(self.h)
 
     def step(self, dt):
         self.L.cpo_step(self.h, float(dt))

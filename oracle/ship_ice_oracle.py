@@ -93,6 +93,17 @@ class ShipIceOracleEnv:
         self.rng = _random
         self.start_override = None
 
+    def clone(self, order_mode=None):
+        """Independent copy of the env in its current (mid-episode) state, optionally with another solver order."""
+        import copy
+        c = copy.copy(self)
+        c.space = self.space.clone()
+        c.total_work = [self.total_work[0], list(self.total_work[1])]
+        if order_mode is not None:
+            c.order_mode = order_mode
+            c.space.set_order(order_mode)
+        return c
+
     # ship_ice_env.py:109-183 (the KE / impulse / contact bookkeeping of the handlers has no reader)
     def init_ship_ice_sim(self):
         self.steps = self.cfg["sim"]["steps"]

@@ -102,6 +102,51 @@ def test_200_seeded_episodes_on_the_gpu_match_the_oracle_distributions(gold):
 
 
 @pytest.fixture(scope="module")
+def gold_ref():
+    return np.load(os.path.join(GOLD, "shipice_200ep_refdata.npz"))
+
+
+def test_oracle_reproduces_golden_episodes_on_the_reference_ice_fields(gold_ref):
+    """BASELINE config 1 on the reference's own data: the 100 trials of experiments_10_100_r06_d40x12.pk (packed in
+    tests/golden/ice_c10_all100.npz), episode k on trial k % 100 (ship_ice_env.py:188).  The canonical-order run (order_mode 0)
+    and the greedy-colour-order run are statistically indistinguishable: the solver order does not move the episode scores."""
+    import make_golden_200ep as g
+    for k, portable, order, tag in ((5, 0, 1, "libm"), (142, 1, 1, "portable"), (77, 0, 0, "canonical")):
+        _, n, succ, eff, effort, rew, work = g.run_episode((k, portable, True, order))
+        assert n == int(gold_ref["%s_steps" % tag][k]) and succ == bool(gold_ref["%s_success" % tag][k])
+        np.testing.assert_allclose([eff, effort, rew, work], [gold_ref["%s_efficiency" % tag][k], gold_ref["%s_effort" % tag][k],
+                                                               gold_ref["%s_reward" % tag][k], gold_ref["%s_total_work" % tag][k]], rtol=1e-12, atol=1e-12)
+    from oracle import cpo
+    cpo.set_portable_trig(False)
+    for tag in ("portable", "libm"):
+        _stat_agree(gold_ref["%s_success" % tag], gold_ref["canonical_success"], gold_ref["%s_efficiency" % tag], gold_ref["canonical_efficiency"],
+                    gold_ref["%s_effort" % tag], gold_ref["canonical_effort"])
+
+
+@pytest.mark.gpu
+def test_200_seeded_episodes_on_the_reference_ice_fields_gpu(gold_ref):
+    """The same 200 episodes as one GPU batch: episode by episode against the oracle in the kernels' arithmetic, statistically
+    against the reference's arithmetic (libm) and against the canonical solver order."""
+    import make_golden_200ep as g
+    from benchpush_b200.envs import ShipIceVecEnv
+    from benchpush_b200.layouts import load_packed
+    from benchpush_b200.metrics import ShipIceMetric
+    E = g.N_EP
+    packed = load_packed(g.REF_PACK)
+    env = ShipIceVecEnv(num_envs=E, cfg={"concentration": g.CONC}, layouts=packed, device=0, first_trial=np.arange(E) % 100)
+    met = ShipIceMetric("gpu", ship_mass=env.cfg.ship.mass, goal=env.goal)
+    steps, succ, eff, effort, rew = _run_batch(env, met, gold_ref["actions"], g.MAX_STEPS)
+    env.close()
+    assert np.array_equal(steps, gold_ref["portable_steps"])
+    assert np.array_equal(succ, gold_ref["portable_success"].astype(bool))
+    np.testing.assert_allclose(eff, gold_ref["portable_efficiency"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(effort, gold_ref["portable_effort"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(rew, gold_ref["portable_reward"], rtol=1e-9, atol=1e-7)
+    for tag in ("libm", "canonical"):
+        _stat_agree(succ, gold_ref["%s_success" % tag], eff, gold_ref["%s_efficiency" % tag], effort, gold_ref["%s_effort" % tag])
+
+
+@pytest.fixture(scope="module")
 def gold_maze():
     return np.load(os.path.join(GOLD, "maze_200ep.npz"))
 

@@ -258,3 +258,92 @@ def test_evaluate_scores_every_episode_under_auto_reset(golden_layouts):
         assert len(res[True][key]) == 4
         np.testing.assert_allclose(sorted(res[True][key]), sorted(res[False][key]), rtol=1e-12, atol=1e-12)
     assert len(set(np.round(res[True]["rewards"], 9))) > 1          # the two trials differ, so a carried-over accumulator would show
+
+
+def test_checkpoint_resume_is_bit_identical(golden_layouts):
+    """bp_shipice_get_state / set_state: an env restored from its state block continues exactly as the original did."""
+    name = "c30_t7"
+    p = golden_layouts[name]
+    env = _make_env(p, fixture_conc(name), n=2)
+    env.reset()
+    rng = np.random.default_rng(4)
+    for _ in range(6):
+        env.step(rng.uniform(-1, 1, 2).astype(np.float32))
+    ck = env.get_state(0)
+    acts = rng.uniform(-1, 1, (4, 2)).astype(np.float32)
+    want = []
+    for a in acts:
+        obs, rew, *_ = env.step(a)
+        want.append((env.get_bodies(0).copy(), float(rew[0]), obs[0].cpu().numpy().copy()))
+    env.set_state(0, ck)
+    for a, (bod, rew0, obs0) in zip(acts, want):
+        obs, rew, *_ = env.step(a)
+        assert np.array_equal(env.get_bodies(0), bod) and float(rew[0]) == rew0 and np.array_equal(obs[0].cpu().numpy(), obs0)
+    with pytest.raises(ValueError):
+        env.set_state(0, ck[:-8])
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["c30_t7", "c50_t0"])
+def test_set_mid_episode_oracle_state_then_step(name, golden_layouts, portable_trig):
+    """bp_shipice_set_bodies: a body state taken from the oracle in the MIDDLE of an episode is injected into a freshly reset
+    env (arbiter cache empty on both sides) and both advance: bit-identical transitions from an externally given state."""
+    p = golden_layouts[name]
+    conc = fixture_conc(name)
+    ora = ShipIceOracleEnv({"concentration": conc}, experiment=unpack_trials(p), order_mode=1)
+    ora.reset()
+    rng = np.random.default_rng(9)
+    for _ in range(14):
+        ora.step(float(np.float32(rng.uniform(-1, 1))), want_obs=False)
+    st = ora.space.state()
+    ora.space.clear_cache()
+    ora.prev_obs = ora.get_obs_from_poly()
+    env = _make_env(p, conc)
+    env.reset()
+    env.set_bodies(0, st)
+    assert np.array_equal(env.get_bodies(0)[:, :3], st[:, :3])
+    for _ in range(3):
+        a = np.float32(rng.uniform(-1, 1))
+        obs, rew, term, trunc, info = env.step(np.array([a], dtype=np.float32))
+        oobs, orew, oterm, _, oinfo = ora.step(float(a))
+        assert np.array_equal(env.get_bodies(0), ora.space.state())
+        assert np.array_equal(obs[0].cpu().numpy(), oobs)
+        np.testing.assert_allclose(float(rew[0]), orew, rtol=1e-9, atol=1e-7)
+    env.close()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_gpu_step_vs_canonical_order_oracle(name, golden_layouts, portable_trig):
+    """Ordering error measured on the GPU path: the kernels solve the arbiters in greedy-colour order, the oracle's canonical
+    order is ascending shape pair (Chipmunk's own order is unknowable offline).  At every env step the canonical-order oracle
+    starts from the state the GPU is in (the order-1 oracle tracks the GPU bit for bit, asserted) and both take the step:
+    per-step pose difference inside the envelope recorded in tests/test_oracle_cpu.py (concentration 0.1: exactly 0;
+    0.3 / 0.5: mean <= 1.5e-3 m, max <= 1e-2 m — the max exceeds SURVEY §8d's 1e-3 m wish, see the finding there)."""
+    from tests.test_oracle_cpu import ORDER_ENVELOPE
+    p = golden_layouts[name]
+    conc = fixture_conc(name)
+    env = _make_env(p, conc)
+    env.reset()
+    A = ShipIceOracleEnv({"concentration": conc}, experiment=unpack_trials(p), order_mode=1)
+    A.reset()
+    rng = np.random.default_rng(1)
+    rows = []
+    for k in range(20):
+        a = np.float32(rng.uniform(-1, 1))
+        B = A.clone(order_mode=0)
+        env.step(np.array([a], dtype=np.float32))
+        _, _, term, _, _ = A.step(float(a), want_obs=False)
+        B.step(float(a), want_obs=False)
+        g = env.get_bodies(0)
+        assert np.array_equal(g, A.space.state())
+        sb = B.space.state()
+        rows.append((np.abs(g[:, :2] - sb[:, :2]).max(), np.abs(g[:, 2] - sb[:, 2]).max()))
+        if term:
+            break
+    r = np.array(rows)
+    if name.startswith("c10"):
+        assert r.max() == 0.0
+    else:
+        assert r[:, 0].max() <= ORDER_ENVELOPE["pos_max"] and r[:, 0].mean() <= ORDER_ENVELOPE["pos_mean"]
+        assert r[:, 1].max() <= ORDER_ENVELOPE["ang_max"] and r[:, 1].mean() <= ORDER_ENVELOPE["ang_mean"]
+    env.close()

@@ -175,3 +175,66 @@ def test_metric_oracle_formulas():
     assert m.rewards == [199.0]
     np.testing.assert_allclose(m.efficiency_scores, [L / l0])
     np.testing.assert_allclose(m.effort_scores, [l0 / (l0 + 2.5)])
+
+
+# ---------------------------------------------------------------- ordering error (finding)
+ORDER_ENVELOPE = {"pos_max": 1e-2, "pos_mean": 1.5e-3, "ang_max": 2.5e-2, "ang_mean": 5e-3}
+
+
+def ordering_error_single_steps(name, n_steps, golden_layouts, seed=1):
+    """One env step (400 substeps) from IDENTICAL mid-episode states (bodies + arbiter cache, Space.clone) with the kernels'
+    greedy-colour solver order (order_mode 1) and with the canonical order (ascending shape pair, order_mode 0): max over
+    bodies of the pose difference, per step."""
+    from tests.conftest import fixture_conc
+    from benchpush_b200.layouts import unpack_trials
+    from oracle.ship_ice_oracle import ShipIceOracleEnv
+    A = ShipIceOracleEnv({"concentration": fixture_conc(name)}, experiment=unpack_trials(golden_layouts[name]), order_mode=1)
+    A.reset()
+    rng = np.random.default_rng(seed)
+    rows = []
+    for k in range(n_steps):
+        a = float(rng.uniform(-1, 1))
+        B = A.clone(order_mode=0)
+        _, _, term, _, _ = A.step(a, want_obs=False)
+        B.step(a, want_obs=False)
+        sa, sb = A.space.state(), B.space.state()
+        rows.append((np.abs(sa[:, :2] - sb[:, :2]).max(), np.abs(sa[:, 2] - sb[:, 2]).max()))
+        if term:
+            break
+    return np.array(rows)
+
+
+@pytest.mark.parametrize("name", ["c10_t7", "c30_t7", "c50_t0"])
+def test_solver_ordering_error_of_one_env_step(name, golden_layouts):
+    """FINDING (not a pass/fail of the 1e-3 m wish): Chipmunk's arbiter order comes from its BBTree and is unknowable offline, so
+    the kernels' order (greedy colours over ascending shape pairs) and the oracle's canonical order are two members of the same
+    family.  Measured over whole episodes, per env step from identical states: concentration 0.1: exactly 0 (no coupled
+    contacts); 0.3: <= 2.9e-3 m (mean 5.8e-4), <= 7.7e-3 rad; 0.5: <= 5.4e-3 m (mean 8.5e-4), <= 1.1e-2 rad.  The MEAN is
+    inside SURVEY §8d's 1e-3 m / 1e-2 rad, the MAX is not: a sequential-impulse transition is only defined up to the solver
+    order at that level, and episode scores are insensitive to it (tests/test_episodes_200.py).  The envelope below guards
+    against regressions of either ordering."""
+    r = ordering_error_single_steps(name, 34 if name != "c10_t7" else 12, golden_layouts)
+    if name.startswith("c10"):
+        assert r.max() == 0.0
+        return
+    assert r[:, 0].max() <= ORDER_ENVELOPE["pos_max"] and r[:, 0].mean() <= ORDER_ENVELOPE["pos_mean"], r[:, 0]
+    assert r[:, 1].max() <= ORDER_ENVELOPE["ang_max"] and r[:, 1].mean() <= ORDER_ENVELOPE["ang_mean"], r[:, 1]
+    assert r[:, 0].max() > 1e-6            # the two orders do differ once contacts are coupled
+
+
+def test_space_clone_and_set_state_roundtrip(golden_layouts):
+    from tests.conftest import fixture_conc
+    from benchpush_b200.layouts import unpack_trials
+    from oracle.ship_ice_oracle import ShipIceOracleEnv
+    name = "c30_t7"
+    A = ShipIceOracleEnv({"concentration": fixture_conc(name)}, experiment=unpack_trials(golden_layouts[name]), order_mode=1)
+    A.reset()
+    for a in (0.3, -0.5, 0.8, 0.1):
+        A.step(a, want_obs=False)
+    B = A.clone()
+    A.step(0.2, want_obs=False); B.step(0.2, want_obs=False)
+    assert np.array_equal(A.space.state(), B.space.state())               # clone carries the arbiter cache
+    st = A.space.state()
+    C_ = A.clone(); C_.space.clear_cache(); C_.space.set_state(st)
+    assert np.array_equal(C_.space.state()[:, :3], st[:, :3])
+    np.testing.assert_array_equal(C_.space.state()[:, 3:], st[:, 3:])
