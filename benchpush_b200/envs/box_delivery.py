@@ -279,8 +279,28 @@ class BoxDeliveryVecEnv:
         k.bound_x = float(self.room.room_length); k.bound_y = float(self.room.room_width)     # D17: x clamps with map_height = room_length
         self._finish_init(k, self.room, ch3_map=None)
 
+    def _init_spaces(self):
+        """The reference's spaces (box_delivery_env.py:157-173, area_clearing.py:200-221) as ``single_*``; ``action_space`` /
+        ``observation_space`` carry a leading axis of num_envs.  Area-clearing declares its position action as int32 (1,)."""
+        from .. import spaces
+        at = self.cfg["agent"]["action_type"]
+        LW = int(self.local_map_pixel_width)
+        area = type(self).__name__.startswith("AreaClearing")
+        if at == "velocity":
+            a = spaces.box(-1, 1, (2,), np.float32)
+        elif at == "heading":
+            a = spaces.box(-1, 1, (1,), np.float32)
+        else:
+            a = spaces.box(0, LW * LW, (1,), np.int32) if area else spaces.box(0, LW * LW, (), np.float32)
+        self.single_action_space = a
+        self.observation_shape = (LW, LW, self.num_channels)
+        self.single_observation_space = spaces.box(0, 255, self.observation_shape, np.uint8)
+        self.action_space = spaces.batched(a, self.num_envs)
+        self.observation_space = spaces.batched(self.single_observation_space, self.num_envs)
+
     def _finish_init(self, k, r, ch3_map):
         """Create the native handle from the filled config, upload layouts / room maps, allocate the output buffers."""
+        self._init_spaces()
         import os
         if os.environ.get("BENCHPUSH_BD_PHASED") is not None:          # development aid: A/B of the substep-loop variants
             k.phase_kernels = int(os.environ["BENCHPUSH_BD_PHASED"])

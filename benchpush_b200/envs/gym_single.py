@@ -27,8 +27,10 @@ class ShipIceEnvB200:
         self.cfg = self._v.cfg
         self.goal = self._v.goal
         self.max_yaw_rate_step = self._v.max_yaw_rate_step
+        self.action_space, self.observation_space = self._v.single_action_space, self._v.single_observation_space
         self.beta = self._v.beta
         self.num_channels = self._v.num_channels
+        self.action_space, self.observation_space = self._v.single_action_space, self._v.single_observation_space
         self.episode_idx = None
         self.t = 0
         self.total_work = [0, []]
@@ -81,6 +83,7 @@ class MazeNamoEnvB200:
         self.cfg = self._v.cfg
         self.goal = self._v.goal
         self.max_yaw_rate_step = self._v.max_yaw_rate_step
+        self.action_space, self.observation_space = self._v.single_action_space, self._v.single_observation_space
         self.beta = self._v.beta
         self.maze_walls = self._v.maze_walls
         self.episode_idx = None
@@ -146,6 +149,7 @@ class BoxDeliveryEnvB200:
         self._v = BoxDeliveryVecEnv(num_envs=1, cfg=cfg, **kw)
         self.cfg = self._v.cfg
         self.num_channels = self._v.num_channels
+        self.action_space, self.observation_space = self._v.single_action_space, self._v.single_observation_space
         self.local_map_pixel_width = self._v.local_map_pixel_width
         self.episode_idx = None
 
@@ -191,6 +195,7 @@ class AreaClearingEnvB200(BoxDeliveryEnvB200):
         self._v = AreaClearingVecEnv(num_envs=1, cfg=cfg, **kw)
         self.cfg = self._v.cfg
         self.num_channels = self._v.num_channels
+        self.action_space, self.observation_space = self._v.single_action_space, self._v.single_observation_space
         self.local_map_pixel_width = self._v.local_map_pixel_width
         self.episode_idx = None
 

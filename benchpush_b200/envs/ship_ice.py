@@ -161,6 +161,18 @@ class ShipIceVecEnv:
         self.check_status = True
 
     # ------------------------------------------------------------------ low-dimensional observation
+    def _init_spaces(self, action_dtype=np.float32):
+        """``single_action_space`` / ``single_observation_space`` = the reference's spaces (ship_ice_env.py:72, 84-99;
+        maze_NAMO_env.py:102-124); ``action_space`` / ``observation_space`` = the same with a leading axis of num_envs."""
+        from .. import spaces
+        self.single_action_space = spaces.box(-1, 1, (), action_dtype)
+        if self.low_dim_state:
+            self.single_observation_space = spaces.box(-10, 30, (self._low_dim_width,), np.float64)
+        else:
+            self.single_observation_space = spaces.box(0, 255, tuple(self._obs_shape), np.uint8)
+        self.action_space = spaces.batched(self.single_action_space, self.num_envs)
+        self.observation_space = spaces.batched(self.single_observation_space, self.num_envs)
+
     def _init_low_dim(self, width: int):
         """cfg.low_dim_state: the observation is ``generate_observation_low_dim`` (ship_ice_env.py:358-370,
         maze_NAMO_env.py:488-504) — float64 [E, width], zero padded — and the image kernel is not launched."""
@@ -171,6 +183,7 @@ class ShipIceVecEnv:
             self._low_dim_counts = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
             self._out.obs = None                      # NULL: bp_*_step / reset skip the observation kernel
             self.observation_shape = (self._low_dim_width,)
+        self._init_spaces(np.float64 if self._prefix == "maze" else np.float32)
 
     def low_dim_observation(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``generate_observation_low_dim`` of the current state for every env (available in both observation modes)."""

@@ -163,3 +163,30 @@ def test_ship_ice_random_start(golden_layouts, pins, portable_trig):
                 seen.append(e)
     assert seen, "goal_y = 1.5 should end an episode within 6 steps"
     env.close()
+
+
+def test_spaces_of_the_image_and_low_dim_modes(golden_layouts):
+    """action_space / observation_space of ship-ice and maze (ship_ice_env.py:72, 84-99; maze_NAMO_env.py:102-124)."""
+    from benchpush_b200.envs import MazeNamoVecEnv, ShipIceVecEnv
+    from benchpush_b200.envs.gym_single import ShipIceEnvB200
+    p = golden_layouts["c10_t0"]
+    e = ShipIceVecEnv(num_envs=3, cfg={"concentration": 0.1}, layouts=p, device=0)
+    assert e.single_action_space.shape == () and e.single_action_space.dtype == np.float32
+    assert e.single_observation_space.shape == (4, 150, 150) and e.single_observation_space.dtype == np.uint8
+    assert e.observation_space.shape == (3, 4, 150, 150) and e.action_space.shape == (3,)
+    obs, _ = e.reset()
+    assert tuple(obs.shape) == e.observation_space.shape
+    e.close()
+    g = ShipIceVecEnv(num_envs=1, cfg={"concentration": 0.1, "egocentric_obs": False}, layouts=p, device=0)
+    assert g.single_observation_space.shape == (2, 200, 60)
+    g.close()
+    l = ShipIceVecEnv(num_envs=1, cfg={"concentration": 0.1, "low_dim_state": True, "fixed_trial_idx": 0}, layouts=p, device=0)
+    assert l.single_observation_space.shape == (2 * p.max_floes,) and l.single_observation_space.dtype == np.float64
+    assert float(l.single_observation_space.low[0]) == -10 and float(l.single_observation_space.high[0]) == 30
+    l.close()
+    m = MazeNamoVecEnv(num_envs=2, device=0)
+    assert m.single_action_space.dtype == np.float64 and m.single_observation_space.shape == (4, 192, 192)
+    m.close()
+    s = ShipIceEnvB200(cfg={"concentration": 0.1}, layouts=p, device=0)
+    assert s.action_space.shape == () and s.observation_space.shape == (4, 150, 150)
+    s.close()

@@ -146,3 +146,26 @@ def test_masked_reset_advances_only_the_masked_envs_episode():
     env.reset(mask=np.array([1, 0, 0], dtype=np.uint8))
     assert np.allclose(env.get_bodies(0)[0, :3], env.layouts[0 + 1 * 3]["start"])     # env 0's episode 1, whenever it is reached
     env.close()
+
+
+def test_room_env_spaces_follow_the_reference():
+    """action_space / observation_space (box_delivery_env.py:157-173, area_clearing.py:200-221): shapes, bounds, dtypes."""
+    from benchpush_b200.envs.area_clearing import AreaClearingVecEnv
+    from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
+    from tests.emu import emu_bd
+    bd = BoxDeliveryVecEnv(num_envs=2, cfg={"agent": {"action_type": "heading"}}, _backend=emu_bd.lib())
+    assert bd.single_action_space.shape == (1,) and bd.single_action_space.dtype == np.float32
+    assert float(bd.single_action_space.low[0]) == -1 and float(bd.single_action_space.high[0]) == 1
+    assert bd.single_observation_space.shape == (bd.local_map_pixel_width, bd.local_map_pixel_width, 4) and bd.single_observation_space.dtype == np.uint8
+    assert bd.action_space.shape == (2, 1) and bd.observation_space.shape == (2,) + bd.single_observation_space.shape
+    assert bd.single_action_space.sample() in bd.single_action_space
+    bd.close()
+    bp = BoxDeliveryVecEnv(num_envs=1, cfg={"agent": {"action_type": "position"}}, _backend=emu_bd.lib())
+    assert bp.single_action_space.shape == () and float(bp.single_action_space.high) == bp.local_map_pixel_width ** 2
+    bp.close()
+    bv = BoxDeliveryVecEnv(num_envs=1, cfg={"agent": {"action_type": "velocity"}}, _backend=emu_bd.lib())
+    assert bv.single_action_space.shape == (2,)
+    bv.close()
+    ac = AreaClearingVecEnv(num_envs=1, cfg={"agent": {"action_type": "position"}}, _backend=emu_bd.lib())
+    assert ac.single_action_space.shape == (1,) and ac.single_action_space.dtype == np.int32
+    ac.close()
