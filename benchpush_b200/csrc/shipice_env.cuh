@@ -116,6 +116,10 @@ BP_DEVNI void shipice_set_bodies_env(const EnvView& ev, const LayoutTab& T, cons
     if (lane == 0) {
         sc->t = t; sc->episode = episode; sc->first_layout = first; sc->done = done; sc->obs_raw = 0; (void)obs_raw;
         sc->total_work = total_work; sc->wall_hit = wall_hit; sc->has_prev_dist = has_prev; sc->prev_dist = prev_dist;
+        // Nothing may be put to sleep before one substep has run on the injected state: a resting pair that overlaps deeper
+        // than the collision slop has no arbiter (hence no bias impulse) yet, so the sleep criterion cannot see that it is
+        // about to move.  The next env step keeps every body awake (like the first settle substep after a reset).
+        sc->pad_hw = 1;
     }
     bp_wsync();
 }
@@ -156,7 +160,13 @@ BP_DEVNI void shipice_step_begin(const EnvView& ev, const LayoutView& L, const S
         for (int q = r; q < sc->nbody; q++) { ev.body[q].vw = vw; ev.body[q].vx = vx; ev.body[q].vy = vy; }
     }
     bp_wsync();
-    sleep_pass(ev, L, d);
+    if (sc->pad_hw) {                 // state injected by bp_*_set_bodies: this step runs with every body awake
+        bp_wsync();
+        if (bp_lane() == 0) sc->pad_hw = 0;
+        bp_wsync();
+    } else {
+        sleep_pass(ev, L, d);
+    }
 }
 
 // ship_ice_env.py:284-290, after every substep: yaw limit (zero the yaw rate, never clamp the angle) and

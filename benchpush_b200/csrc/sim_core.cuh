@@ -98,7 +98,8 @@ struct EnvScal {
     double G;                     // monotone accumulator: bounds the growth of D[a] + D[b] of ANY pair
     int obs_raw, n_fixed, wall_hit, has_prev_dist;   // n_fixed: bodies that are not dynamic (robot shapes + walls)
     double prev_dist;                                 // maze: distance-map value at the previous step (prev_dist_value)
-    int slot_hw, pad_hw;          // every arbiter slot >= slot_hw is free: scans over the slots stop there
+    int slot_hw, pad_hw;          // every arbiter slot >= slot_hw is free: scans over the slots stop there; pad_hw != 0: the state was
+                                  // injected (bp_*_set_bodies) and the next env step must not start with a sleep pass
     double total_work;
     long long stat_gjk, stat_pairs_eval, stat_live_sum, stat_awake_sum, stat_recolour, stat_rebuild, stat_substeps;
     long long stat_epa, stat_skipped, t_phase[8];

@@ -65,6 +65,11 @@ class Emu:
         a = np.ascontiguousarray(actions, dtype=np.float32)
         self.L.emu_step_resident(self.h, C.c_int(env0), a.ctypes.data_as(C.c_void_p), C.c_int(1 if auto_reset else 0))
 
+    def set_bodies(self, env, bodies):
+        b = np.ascontiguousarray(bodies, dtype=np.float64)
+        pad = np.zeros((self.p.max_floes + 1, 6)); pad[:len(b)] = b
+        self.L.emu_set_bodies(self.h, C.c_int(env), _dp(pad))
+
     def batch_size(self):
         return int(self.L.emu_batch_size())
 

@@ -97,6 +97,11 @@ void emu_step_resident(void* h, int env0, const float* actions, int auto_reset) 
     res::shipice_step_resident(&C, S, e->mem.data(), e->env_bytes, env0, actions, nullptr, e->out, auto_reset);
 }
 int emu_res_pool(int what) { return what == 0 ? res::R_PA : what == 1 ? res::R_PV : res::R_PS; }
+void emu_set_bodies(void* h, int env, const double* bodies6) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    shipice_set_bodies_env(ev, e->T, e->P, e->d, bodies6);
+}
 int emu_batch_size() { return BK; }
 // one raw physics substep (for per-substep parity); robot velocity set explicitly
 void emu_set_robot_velocity(void* h, int env, double vx, double vy, double w) {

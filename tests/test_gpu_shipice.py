@@ -297,6 +297,7 @@ def test_set_mid_episode_oracle_state_then_step(name, golden_layouts, portable_t
         ora.step(float(np.float32(rng.uniform(-1, 1))), want_obs=False)
     st = ora.space.state()
     ora.space.clear_cache()
+    ora.space.set_state(st)            # poses and velocities as exported; the bias velocities (not part of the state) are dropped
     ora.prev_obs = ora.get_obs_from_poly()
     env = _make_env(p, conc)
     env.reset()

@@ -144,3 +144,34 @@ def test_resident_path_equals_batched_path(flags, monkeypatch):
         for e in range(E):
             assert np.array_equal(A.bodies(e, big), B.bodies(e, big)), (k, e)
             assert A.out(e) == B.out(e), (k, e)
+
+
+@pytest.mark.parametrize("mode", ["step", "batch", "res"])
+def test_injected_mid_episode_state_matches_oracle(mode, golden_layouts, portable_trig):
+    """bp_*_set_bodies semantics on the CPU build of the kernel sources: a body state exported by the oracle in the middle of
+    an episode (arbiter cache dropped on both sides) continues bit-identically on all three step paths.  The first step runs
+    with every body awake: a resting pair that overlaps deeper than the slop has no arbiter yet and must not be slept."""
+    name = "c50_t0"
+    p = golden_layouts[name]
+    ora = ShipIceOracleEnv({"concentration": fixture_conc(name)}, experiment=unpack_trials(p), order_mode=1)
+    ora.reset()
+    rng = np.random.default_rng(9)
+    for _ in range(14):
+        ora.step(float(np.float32(rng.uniform(-1, 1))), want_obs=False)
+    st = ora.space.state()
+    ora.space.clear_cache(); ora.space.set_state(st); ora.prev_obs = ora.get_obs_from_poly()
+    emu = Emu(1, p, SHIP_VERTS, pmax=8 * (p.max_floes + 1), lmax=2 * (p.max_floes + 1))
+    emu.reset(0, 0)
+    emu.set_bodies(0, st)
+    for k in range(2):
+        a = np.float32(rng.uniform(-1, 1))
+        if mode == "step":
+            emu.step(0, float(a))
+        elif mode == "batch":
+            emu.step_batch(0, np.array([a], dtype=np.float32))
+        else:
+            emu.step_resident(0, np.array([a], dtype=np.float32))
+        _, r, _, _, info = ora.step(float(a), want_obs=False)
+        assert np.array_equal(emu.bodies(0, 0), ora.space.state()), k
+        np.testing.assert_allclose(emu.out(0)["reward"], r, rtol=1e-9, atol=1e-7)
+    assert emu.scal(0)["n_awake"] < 200          # the sleep pass is back after the first step
