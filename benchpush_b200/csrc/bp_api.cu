@@ -53,6 +53,7 @@ struct StepArgs {
     char* mem; size_t env_bytes; Dims d; SimParams P; LayoutTab T; StepOut out;
     const float* actions; const int32_t* layout_ids; const uint8_t* mask; int* counter; int auto_reset;
     const DevConst* C; int use_snap;
+    const int* perm; int n_sched;      // step schedule (k_schedule): perm[n_sched], entries = env id or -1; nullptr = identity
 };
 
 // Claim the next batch of environments for this warp: one per lane group.  Returns false when the
@@ -113,6 +114,42 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepAr
     }
 }
 
+// Step schedule.  The cost of an env step varies by more than an order of magnitude with the size of its awake set and the
+// number of solver colours, and a warp batch runs as long as its slowest member (10 sweeps x the LARGEST colour count of the
+// batch).  One block sorts the envs by a cost key read from their env blocks (colours, awake bodies; descending) and writes
+// the order in which the step kernel's warps claim them:
+//   * many batches per resident warp: batches of similar envs (few wasted solver rounds), heaviest first (the light ones
+//     fill the tail: longest-processing-time-first);
+//   * about one batch per resident warp (the per-GPU share of the 8-GPU strong-scaling point): the sorted envs are dealt
+//     round-robin over the batches, so that every batch gets the same mix and the launch does not wait for one heavy batch.
+// Results do not depend on the schedule (envs never interact; tests run the same envs under different schedules).
+__global__ void __launch_bounds__(1024) k_schedule(const char* mem, size_t env_bytes, int n_envs, const uint8_t* mask, int auto_reset,
+                                                    int* perm, int bk, int n_batches, int balanced) {
+    __shared__ int hist[256];
+    __shared__ int start[256];
+    const int n_sched = n_batches * bk;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    for (int i = threadIdx.x; i < n_sched; i += blockDim.x) perm[i] = -1;
+    __syncthreads();
+    auto key_of = [&](int e) -> int {
+        if (mask && !mask[e]) return 255;                                   // not stepping: last
+        const EnvScal* sc = (const EnvScal*)(mem + env_bytes * (size_t)e);
+        if (auto_reset && sc->done) return 254;                             // reset = copy of a snapshot: light
+        int nc = sc->n_colours < 15 ? sc->n_colours : 15;
+        int na = sc->n_awake / 4; if (na > 14) na = 14;
+        return 253 - (nc * 15 + na);                                        // descending cost
+    };
+    for (int e = threadIdx.x; e < n_envs; e += blockDim.x) atomicAdd(&hist[key_of(e)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { int acc = 0; for (int i = 0; i < 256; i++) { start[i] = acc; acc += hist[i]; } }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_envs; e += blockDim.x) {
+        int p = atomicAdd(&start[key_of(e)], 1);
+        int idx = balanced ? (p % n_batches) * bk + p / n_batches : p;
+        perm[idx] = e;
+    }
+}
+
 // Batched step: each warp claims BK consecutive envs and advances them together (sim_batch.cuh).
 #define BP_DEFINE_STEP_KERNEL(NAME, NS)                                                                         \
     __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) NAME(StepArgs a) {                                    \
@@ -123,8 +160,8 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepAr
             int env0 = 0;                                                                                        \
             if ((threadIdx.x & 31) == 0) env0 = atomicAdd(a.counter, NS::BK);                                    \
             env0 = __shfl_sync(0xffffffffu, env0, 0);                                                            \
-            if (env0 >= a.d.n_envs) break;                                                                       \
-            NS::shipice_step_batch(a.C, S, a.mem, a.env_bytes, env0, a.actions, a.mask, a.out, a.auto_reset);    \
+            if (env0 >= (a.perm ? a.n_sched : a.d.n_envs)) break;                                                \
+            NS::shipice_step_batch(a.C, S, a.mem, a.env_bytes, env0, a.actions, a.mask, a.out, a.auto_reset, a.perm); \
             __syncwarp();                                                                                        \
         }                                                                                                        \
     }
@@ -142,8 +179,8 @@ __global__ void __launch_bounds__(32) k_shipice_step_res(StepArgs a) {
         int env0 = 0;
         if (threadIdx.x == 0) env0 = atomicAdd(a.counter, res::RK);
         env0 = __shfl_sync(0xffffffffu, env0, 0);
-        if (env0 >= a.d.n_envs) break;
-        res::shipice_step_resident(a.C, S, a.mem, a.env_bytes, env0, a.actions, a.mask, a.out, a.auto_reset);
+        if (env0 >= (a.perm ? a.n_sched : a.d.n_envs)) break;
+        res::shipice_step_resident(a.C, S, a.mem, a.env_bytes, env0, a.actions, a.mask, a.out, a.auto_reset, a.perm);
         __syncwarp();
     }
 }
@@ -289,6 +326,8 @@ struct bp_shipice {
     DevConst hc_host;              // its host copy (bp_shipice_set_start_poses patches one pointer)
     char* snap = nullptr;          // post-reset env block of every layout (reset = copy)
     bool warp_impl = false;        // BP_STEP_IMPL=warp: one env per warp (A/B measurements)
+    int* perm = nullptr; int perm_cap = 0;   // step schedule (k_schedule); BP_NO_SCHEDULE=1 keeps the identity order
+    bool use_schedule = true;
     bool res_impl = false;         // resident step (sim_res.cuh): the default for ship-ice; BP_STEP_IMPL=batch selects sim_batch.cuh
     int res_blocks_per_sm = 1;
     StepOut out;               // internal device outputs
@@ -394,6 +433,7 @@ int bp_shipice_destroy(bp_shipice_t* h) {
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->mem) cudaFree(h->mem);
     if (h->counter) cudaFree(h->counter);
+    if (h->perm) cudaFree(h->perm);
     if (h->d_actions) cudaFree(h->d_actions);
     if (h->d_obs) cudaFree(h->d_obs);
     if (h->h_actions) cudaFreeHost(h->h_actions);
@@ -451,7 +491,7 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
         CUDA_TRY(cudaMemset(h->counter, 0, 4));
         StepArgs a;
         a.mem = h->snap; a.env_bytes = h->env_bytes; a.d = h->d; a.d.n_envs = n_layouts; a.P = h->P; a.T = h->T; a.out = so;
-        a.actions = nullptr; a.layout_ids = ids; a.mask = nullptr; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const; a.use_snap = 0;
+        a.actions = nullptr; a.layout_ids = ids; a.mask = nullptr; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const; a.use_snap = 0; a.perm = nullptr; a.n_sched = 0;
         int blocks = (n_layouts + 3) / 4; if (blocks > h->sm_count * BP_MIN_BLOCKS) blocks = h->sm_count * BP_MIN_BLOCKS;
         k_shipice_reset<<<blocks, 128>>>(a);
         CUDA_TRY(cudaGetLastError());
@@ -460,6 +500,7 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
         CUDA_TRY(cudaMemcpy(h->d_const, &hc, sizeof(DevConst), cudaMemcpyHostToDevice));
     }
     if (const char* e = getenv("BP_STEP_IMPL")) h->warp_impl = (strcmp(e, "warp") == 0);
+    if (const char* e = getenv("BP_NO_SCHEDULE")) h->use_schedule = !(atoi(e) != 0);
     // resident step (sim_res.cuh), ship-ice only (the per-substep checks of the maze run on the env block).  Selected with
     // BP_STEP_IMPL=res: in fp64 only three pools fit an SM, and three warps per SM issue too slowly to beat the batched
     // kernel (profiles/r02a_*), so the batched kernel stays the default.
@@ -587,6 +628,7 @@ int bp_shipice_reset(bp_shipice_t* h, const int32_t* layout_ids, const uint8_t* 
     StepArgs a;
     a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
     a.actions = nullptr; a.layout_ids = layout_ids; a.mask = mask; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const; a.use_snap = h->snap ? 1 : 0;
+    a.perm = nullptr; a.n_sched = 0;
     k_shipice_reset<<<sim_grid(h), 128, 0, st>>>(a);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -605,7 +647,20 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
     StepArgs a;
     a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
     a.actions = actions; a.layout_ids = nullptr; a.mask = mask; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset; a.C = h->d_const; a.use_snap = h->snap ? 1 : 0;
+    a.perm = nullptr; a.n_sched = 0;
     prof_begin(h, 0, st);
+    if (h->use_schedule && !h->warp_impl) {
+        const int bk = h->res_impl ? res::RK : (use_small_batches(h) ? bk_small::BK : bk_main::BK);
+        const int n_batches = (h->d.n_envs + bk - 1) / bk;
+        const int warp_slots = h->res_impl ? h->sm_count * h->res_blocks_per_sm : h->sm_count * BP_MIN_BLOCKS * 4;
+        if (!h->perm || h->perm_cap < n_batches * bk) {
+            if (h->perm) cudaFree(h->perm);
+            CUDA_TRY(cudaMalloc((void**)&h->perm, (size_t)n_batches * bk * 4));
+            h->perm_cap = n_batches * bk;
+        }
+        k_schedule<<<1, 1024, 0, st>>>(h->mem, h->env_bytes, h->d.n_envs, mask, h->cfg.auto_reset, h->perm, bk, n_batches, n_batches < 2 * warp_slots ? 1 : 0);
+        a.perm = h->perm; a.n_sched = n_batches * bk;
+    }
     if (h->res_impl) {
         int blocks = h->sm_count * h->res_blocks_per_sm;
         int need = (h->d.n_envs + res::RK - 1) / res::RK;
@@ -679,7 +734,7 @@ int bp_shipice_set_bodies(bp_shipice_t* h, int32_t env, const double* bodies6, i
     CUDA_TRY(cudaMemcpy(dbuf, bodies6, (size_t)n_bodies * 6 * 8, cudaMemcpyHostToDevice));
     StepArgs a;
     a.mem = h->mem; a.env_bytes = h->env_bytes; a.d = h->d; a.P = h->P; a.T = h->T; a.out = h->out;
-    a.actions = nullptr; a.layout_ids = nullptr; a.mask = nullptr; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const; a.use_snap = 0;
+    a.actions = nullptr; a.layout_ids = nullptr; a.mask = nullptr; a.counter = h->counter; a.auto_reset = 0; a.C = h->d_const; a.use_snap = 0; a.perm = nullptr; a.n_sched = 0;
     k_shipice_set_bodies<<<1, 32>>>(a, env, dbuf);
     h->launches++;
     cudaError_t e = cudaDeviceSynchronize();

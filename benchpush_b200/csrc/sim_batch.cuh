@@ -489,15 +489,16 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
 // ShipIceEnv.step for the envs [env0, env0 + BK) of a handle (those >= n_envs are skipped).
 // auto_reset: an env whose previous step terminated is reset instead (next trial) and returns the
 // reset observation with reward 0, exactly like the one-env path in bp_api.cu.
+// perm (optional): the step schedule, entry i = env id or -1 (k_schedule in bp_api.cu); the batch is perm[env0 .. env0 + BK).
 BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, size_t env_bytes, int env0, const float* actions,
-                                 const unsigned char* mask, const StepOut& out, int auto_reset) {
+                                 const unsigned char* mask, const StepOut& out, int auto_reset, const int* perm = nullptr) {
     const int lane = bp_lane();
     const SimParams& P = C->P;
     const Dims& d = C->d;
     for (int e = 0; e < BK; e++) {
-        int env = env0 + e;
+        int env = perm ? perm[env0 + e] : env0 + e;
         char* base = nullptr;
-        if (env < d.n_envs && !(mask && !mask[env])) {
+        if (env >= 0 && env < d.n_envs && !(mask && !mask[env])) {
             base = mem + env_bytes * (size_t)env;
             EnvView ev = view_s(base);
             EnvScal* sc = ev.sc;

@@ -667,14 +667,14 @@ BP_DEVNI void res_substep(const DevConst* C, ResShared& S, const StepOut& out) {
 // ShipIceEnv.step for the envs [env0, env0 + RK) of a handle (those >= n_envs are skipped); same contract as
 // shipice_step_batch of sim_batch.cuh (auto reset included).
 BP_DEVNI void shipice_step_resident(const DevConst* C, ResShared& S, char* mem, size_t env_bytes, int env0, const float* actions,
-                                    const unsigned char* mask, const StepOut& out, int auto_reset) {
+                                    const unsigned char* mask, const StepOut& out, int auto_reset, const int* perm = nullptr) {
     const int lane = bp_lane();
     const SimParams& P = C->P;
     const Dims& d = C->d;
     for (int e = 0; e < RK; e++) {
-        int env = env0 + e;
+        int env = perm ? perm[env0 + e] : env0 + e;
         char* base = nullptr;
-        if (env < d.n_envs && !(mask && !mask[env])) {
+        if (env >= 0 && env < d.n_envs && !(mask && !mask[env])) {
             base = mem + env_bytes * (size_t)env;
             EnvView ev = view_s(base);
             EnvScal* sc = ev.sc;

@@ -34,7 +34,11 @@
 
 namespace {
 
+#ifdef CPO_FLOAT32
+typedef float cpFloat;      // precision experiment only (tools/fp32_experiment.py): every body, contact and solver quantity in fp32
+#else
 typedef double cpFloat;
+#endif
 struct V { cpFloat x, y; };
 static inline V v(cpFloat x, cpFloat y) { V r = {x, y}; return r; }
 static inline V vadd(V a, V b) { return v(a.x + b.x, a.y + b.y); }
@@ -272,8 +276,9 @@ static void trig(double a, double* sn, double* cs) {
 }
 
 static void set_transform(Body& b) {
-    cpFloat cs, sn;
-    trig(b.a, &sn, &cs);      // cpvforangle
+    double cs_d, sn_d;
+    trig((double)b.a, &sn_d, &cs_d);      // cpvforangle
+    cpFloat cs = (cpFloat)cs_d, sn = (cpFloat)sn_d;
     V c = b.cog;
     b.tr.a = cs; b.tr.b = sn; b.tr.c = -sn; b.tr.d = cs;
     b.tr.tx = b.p.x - (c.x * cs - c.y * sn);

@@ -32,8 +32,14 @@ def sincos(a):
 
 
 def build(force=False):
-    so = os.path.join(_HERE, "libbp_oracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("chipmunk_oracle.cpp", "spfa_oracle.cpp")]
+    if os.environ.get("BP_ORACLE_F32") == "1":
+        # precision experiment only (tools/fp32_experiment.py): the same restatement with cpFloat = float
+        so = os.path.join(_HERE, "libbp_oracle_f32.so")
+        if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-DCPO_FLOAT32", "-shared", "-o", so] + srcs)
+        return so
+    so = os.path.join(_HERE, "libbp_oracle.so")
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libbp_oracle.so"], stdout=subprocess.DEVNULL)
     return so
