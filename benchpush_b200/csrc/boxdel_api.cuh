@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) k_mv_init(const BdConst* C, const uint8_t
     if (env >= C->n_envs || (threadIdx.x & 31)) return;
     MoveVars& v = mv[env];
     bool part = !(mask && !mask[env]);
-    v.state = part ? (C->P.action_type == 2 ? MV_VEL : MV_EXEC) : MV_DONE;
+    v.state = part ? (C->P.action_type == 2 ? (C->P.kind == 1 ? (C->P.post_steps > 0 ? MV_POST : MV_DONE) : MV_VEL) : MV_EXEC) : MV_DONE;
     if (!part) return;
     BdEnv* E = bd_env(*C, env);
     bd_finalize_path(*C, E);
@@ -206,7 +206,7 @@ void bp_boxdel_default_config(bp_boxdel_config* c) {
 int bp_boxdel_create(const bp_boxdel_config* cfg, bp_boxdel_t** out) {
     if (!cfg || !out) return fail(BP_ERR_INVALID, "null argument");
     if (cfg->n_envs <= 0 || cfg->num_boxes <= 0 || cfg->num_boxes > MAXBOX) return fail(BP_ERR_INVALID, "n_envs / num_boxes out of range");
-    if (cfg->action_type < 0 || cfg->action_type > 2 || (cfg->action_type == 2 && cfg->env_kind != 0)) return fail(BP_ERR_INVALID, "action_type must be 0 (position), 1 (heading) or 2 (velocity, box-delivery only)");
+    if (cfg->action_type < 0 || cfg->action_type > 2) return fail(BP_ERR_INVALID, "action_type must be 0 (position), 1 (heading) or 2 (velocity: two floats per env)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(BP_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
     CUDA_TRY(cudaSetDevice(cfg->device));

@@ -152,6 +152,20 @@ BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action, double acti
     const BdBody& R = E->body[0];
     double x0 = R.px, y0 = R.py, h0 = restrict_heading(R.pa);
     E->init_pos[0] = x0; E->init_pos[1] = y0; E->init_heading = h0;
+    if (P.action_type == 2 && P.kind == 1) {
+        // area-clearing velocity control (area_clearing.py:656-663): yaw rate = max_yaw_rate_step * a[1] / 2 and surge =
+        // target_speed * a[0] are float32 products (float32 action array, NumPy >= 2 promotion); the velocity VECTOR is set
+        // once from the heading at step start and not refreshed during the cfg.sim.steps substeps that follow (D1)
+        float w32 = ((float)((BD_PI / 2) / 15) * (float)action2) / 2.0f;
+        float sv = (float)P.target_speed * (float)action;
+        BdBody& Rb = E->body[0];
+        double ch = cos(Rb.pa), sh = sin(Rb.pa);
+        Rb.vw = (double)w32;
+        Rb.vx = ch * (double)sv + (-sh) * 0.0; Rb.vy = sh * (double)sv + ch * 0.0;
+        E->tgt[0] = (double)sv; E->tgt[1] = (double)w32;
+        E->n_path = 0; E->need_spfa = 0; E->move_sign = 1; E->robot_distance = 0.0;
+        return;
+    }
     if (P.action_type == 2) {
         // velocity control (box_delivery_env.py:667-700): action = float32 (linear, angular); |linear| is clamped to target_speed
         // in float32 arithmetic (python float * np.float32 scalar -> float32 under NumPy >= 2 promotion)
@@ -477,7 +491,7 @@ BP_DEVNI void bd_move(const BdConst& C, int env0, int nk, const uint8_t* mask, M
         bp_wsync();
         if (lane == 0) {
             MoveVars& v = V[k];
-            v.state = part ? (C.P.action_type == 2 ? MV_VEL : MV_EXEC) : MV_DONE;
+            v.state = part ? (C.P.action_type == 2 ? (C.P.kind == 1 ? (C.P.post_steps > 0 ? MV_POST : MV_DONE) : MV_VEL) : MV_EXEC) : MV_DONE;
             if (part) {
                 BdEnv* E = Es[k];
                 bd_finalize_path(C, E);

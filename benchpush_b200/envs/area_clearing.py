@@ -12,7 +12,9 @@ Host work done here once per handle: configuration space, nearest-free-cell map 
 (``create_global_shortest_path_to_goal_points``, area_clearing.py:1055-1082: one spfa solve per goal point — run on the
 GPU through ``bp_spfa_batch`` — min-combined, normalised and masked by the two boundary squares).
 
-Implemented: the environments without inner walls or static obstacles (``clear_env``, ``clear_env_small``), ``action_type`` heading / position.
+Implemented: the four environments of ``area_clearing/envs/*.yaml`` (``clear_env``, ``clear_env_small``, ``walled_env``,
+``walled_env_with_columns``: inner walls and static obstacles are fixed per environment, so they are static shapes and
+map pixels of the handle), ``action_type`` heading / position / velocity.
 Layouts are inputs or drawn by ``layouts.sample_area_clearing_layout`` (the reference uses the unseeded global ``random``).
 """
 from __future__ import annotations
@@ -28,13 +30,32 @@ from ..layouts import sample_area_clearing_layout
 from ..utils import DotDict, merge_cfg
 from .box_delivery import LAYOUT_EPISODE_STRIDE, BoxDelConfig, BoxDeliveryVecEnv, bind, default_pool_episodes, disk
 
-ENVS = {   # area_clearing/envs/*.yaml restated (environments without inner walls)
+def polygon_from_line(line, width=0.2):
+    """``create_polygon_from_line`` (geometry/polygon.py:201-207: shapely ``LineString.buffer(width / 2, cap_style=2, join_style=2)``)
+    of a two-point wall: the rectangle of that width around the line, flat caps."""
+    p0, p1 = np.asarray(line[0], dtype=np.float64), np.asarray(line[1], dtype=np.float64)
+    d = p1 - p0
+    n = np.array([-d[1], d[0]]) / np.hypot(d[0], d[1]) * (width / 2)
+    return [list(p0 + n), list(p1 + n), list(p1 - n), list(p0 - n)]
+
+
+ENVS = {   # area_clearing/envs/*.yaml restated
     "clear_env": {"outer_boundary": [[-8.0, -8.0], [-8.0, 8.0], [8.0, 8.0], [8.0, -8.0]],
                   "boundary": [[-5.0, -5.0], [-5.0, 5.0], [5.0, 5.0], [5.0, -5.0]],
                   "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 24},
     "clear_env_small": {"outer_boundary": [[-6.0, -6.0], [-6.0, 6.0], [6.0, 6.0], [6.0, -6.0]],
                         "boundary": [[-4.0, -4.0], [-4.0, 4.0], [4.0, 4.0], [4.0, -4.0]],
                         "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 12},
+    "walled_env": {"outer_boundary": [[-8.0, -8.0], [-8.0, 8.0], [8.0, 8.0], [8.0, -8.0]],
+                   "boundary": [[-5.0, -5.0], [-5.0, 5.0], [5.0, 5.0], [5.0, -5.0]],
+                   "walls": [[[-6.0, -6.0], [-6.0, 6.0]], [[6.0, 6.0], [6.0, -6.0]]],
+                   "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 24},
+    "walled_env_with_columns": {"outer_boundary": [[-12.0, -12.0], [-12.0, 12.0], [12.0, 12.0], [12.0, -12.0]],
+                                "boundary": [[-7.5, -8.0], [-7.5, 8.0], [7.5, 8.0], [7.5, -8.0]],
+                                "walls": [[[-8.0, -8.0], [-8.0, 8.0]], [[8.0, 8.0], [8.0, -8.0]]],
+                                "static_obstacles": [[[-1.0, -6.0], [-1.0, -4.0], [1.0, -4.0], [1.0, -6.0]], [[-1.0, -1.0], [-1.0, 1.0], [1.0, 1.0], [1.0, -1.0]],
+                                                     [[-1.0, 4.0], [-1.0, 6.0], [1.0, 6.0], [1.0, 4.0]]],
+                                "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 24},
 }
 
 DEFAULT_CFG = {   # area_clearing/config.yaml restated (keys that reach the hot path)
@@ -73,9 +94,13 @@ class ClearingMaps:
         # outer walls: 4 rectangles of thickness 24 on the static body, radius .1 (generate_walls :488-513)
         room_length, room_width, wt = abs(outer[0][0]) * 2, abs(outer[0][1]) * 2, 24
         rect = lambda x, y, l, w: [[x - l / 2, y - w / 2], [x + l / 2, y - w / 2], [x + l / 2, y + w / 2], [x - l / 2, y + w / 2]]
-        st = [(rect(x, y, l, w), (0.0, 0.0, 0.0), 0.1, 3) for (x, y, l, w) in
-              [(-room_length / 2 - wt / 2, 0, wt, room_width), (room_length / 2 + wt / 2, 0, wt, room_width),
-               (0, -room_width / 2 - wt / 2, room_length + 2 * wt, wt), (0, room_width / 2 + wt / 2, room_length + 2 * wt, wt)]]
+        # static obstacles (generate_static_obstacles :437-453) and inner walls (polygons around their centre lines, :455-480)
+        # come first, in the reference's creation order; all statics are radius .1, friction .99, collision type 3 (:384-385)
+        st = [([list(map(float, p)) for p in o], (0.0, 0.0, 0.0), 0.1, 3) for o in env_cfg.get("static_obstacles", [])]
+        st += [(polygon_from_line(w), (0.0, 0.0, 0.0), 0.1, 3) for w in env_cfg.get("walls", [])]
+        st += [(rect(x, y, l, w), (0.0, 0.0, 0.0), 0.1, 3) for (x, y, l, w) in
+               [(-room_length / 2 - wt / 2, 0, wt, room_width), (room_length / 2 + wt / 2, 0, wt, room_width),
+                (0, -room_width / 2 - wt / 2, room_length + 2 * wt, wt), (0, room_width / 2 + wt / 2, room_length + 2 * wt, wt)]]
         self.statics = st
         self.st_nv = np.array([4] * len(st), dtype=np.int32)
         self.st_verts = np.array([s[0] for s in st], dtype=np.float64)
@@ -126,11 +151,9 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"] not in ENVS:
-            raise NotImplementedError("only the environments without inner walls are implemented (env: clear_env, clear_env_small)")
-        if c["agent"]["action_type"] not in ("heading", "position"):
-            raise NotImplementedError("action_type 'velocity' is not implemented")
-        if c["low_dim_state"]:
-            raise NotImplementedError("low_dim_state is not implemented")
+            raise KeyError("unknown area-clearing environment %r (have: %s)" % (c["env"], sorted(ENVS)))
+        if c["agent"]["action_type"] not in ("heading", "position", "velocity"):
+            raise NotImplementedError("unknown action_type %r" % (c["agent"]["action_type"],))
         self.env_cfg = ENVS[c["env"]]
         self.num_envs = E = int(num_envs)
         self._emu = _backend is not None
@@ -166,7 +189,8 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
         k = BoxDelConfig()
         L.bp_boxdel_default_config(C.byref(k))
         k.n_envs = E; k.num_boxes = NB; k.device = self.device_index
-        k.action_type = 1 if c["agent"]["action_type"] == "heading" else 0
+        k.action_type = {"position": 0, "heading": 1, "velocity": 2}[c["agent"]["action_type"]]
+        self._action_dim = 2 if k.action_type == 2 else 1
         k.steps = int(c["sim"]["steps"]); k.iterations = int(c["sim"]["iterations"]); k.settle_steps = 1000
         k.local_map_pixel_width = LW
         k.ctrl_dt = float(c["controller"]["dt"]); k.target_speed = float(c["controller"]["target_speed"]); k.damping = float(c["sim"]["damping"])
@@ -242,4 +266,4 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
         return {"state": info[:, 0:3], "total_work": info[:, 5], "collision reward": -info[:, 7], "diff_reward": info[:, 3],
                 "box_completed_reward": info[:, 4], "obs": b["box_verts"], "n_boxes_left": ii[:, 2], "box_completed_statuses": b["completed"],
                 "box_count": ii[:, 0], "ministeps": info[:, 6], "t": ii[:, 1], "status": ii[:, 3], "goal_positions": self.goal_points,
-                "boundary": self.env_cfg["boundary"]}
+                "boundary": self.env_cfg["boundary"], "walls": self.env_cfg.get("walls", []), "static_obstacles": self.env_cfg.get("static_obstacles", [])}

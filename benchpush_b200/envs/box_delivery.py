@@ -12,7 +12,7 @@ library calls as the reference (cv2.fillPoly, scipy binary_dilation with a disk 
 distance_transform_edt).  They depend on the room only, so all envs of a handle share them.
 
 Implemented: ``obstacle_config: small_empty`` (any room size without columns / dividers), ``action_type``
-``heading``, ``position`` and ``velocity`` (actions ``float32[B, 2]``).  ``low_dim_state`` and the column / divider rooms raise
+``heading``, ``position`` and ``velocity`` (actions ``float32[B, 2]``), ``low_dim_state``.  The column / divider rooms raise
 NotImplementedError.
 """
 from __future__ import annotations
@@ -215,8 +215,8 @@ class BoxDeliveryVecEnv:
             raise NotImplementedError("only the rooms without columns / dividers are implemented (obstacle_config small_empty)")
         if c["agent"]["action_type"] not in ("heading", "position", "velocity"):
             raise NotImplementedError("unknown action_type %r" % (c["agent"]["action_type"],))
-        if c["low_dim_state"] or c["teleop_mode"]:
-            raise NotImplementedError("low_dim_state / teleop_mode are not implemented")
+        if c["teleop_mode"]:
+            raise NotImplementedError("teleop_mode (keyboard tele-operation) is out of scope")
         if tuple(c["sim"]["gravity"]) != (0, 0):
             raise NotImplementedError("non-zero gravity is not supported")
         self.num_envs = E = int(num_envs)
@@ -335,6 +335,18 @@ class BoxDeliveryVecEnv:
             setattr(o, n, self._ptr(n))
         self._out = o
         self.episode_idx = None
+        # cfg.low_dim_state (box_delivery_env.py:166-169, 606-607; area_clearing.py:212-215, 599-600): the observation is
+        # generate_observation_low_dim and the image kernel is not launched (NULL observation pointer)
+        self.low_dim_state = bool(self.cfg["low_dim_state"])
+        if self.low_dim_state:
+            from .. import spaces
+            self._out.obs = None
+            self.observation_shape = (2 * NB,)
+            self.single_observation_space = spaces.box(-10, 30, self.observation_shape, np.float32)
+            self.observation_space = spaces.batched(self.single_observation_space, E)
+
+    def _observation(self):
+        return self.low_dim_observation() if self.low_dim_state else self._buf["obs"]
 
     # ---- buffers: torch CUDA tensors (product) or numpy arrays (emulation)
     def _alloc(self, name, shape, dtype):
@@ -401,7 +413,7 @@ class BoxDeliveryVecEnv:
             self._put("mask", mask)
             mptr = self._ptr("mask")
         self._check(self._L.bp_boxdel_reset(self._h, self._ptr("layout_ids"), mptr, C.byref(self._out), self._stream()))
-        return self._buf["obs"], self._info()
+        return self._observation(), self._info()
 
     def step(self, action, mask=None):
         self._put("actions", action)
@@ -413,7 +425,7 @@ class BoxDeliveryVecEnv:
         b = self._buf
         term = b["terminated"].astype(bool) if self._emu else b["terminated"].bool()
         trunc = b["truncated"].astype(bool) if self._emu else b["truncated"].bool()
-        return b["obs"], b["reward"], term, trunc, self._info()
+        return self._observation(), b["reward"], term, trunc, self._info()
 
     def _info(self):
         b = self._buf

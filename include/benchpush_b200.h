@@ -305,7 +305,8 @@ typedef struct bp_boxdel bp_boxdel_t;
 typedef struct bp_boxdel_config {
     int32_t n_envs, num_boxes, device;
     int32_t action_type;          /* 0 = position (pixel index), 1 = heading in [-1, 1], 2 = velocity (linear, angular: two floats per env;
-                                     box-delivery only) — cfg.agent.action_type */
+                                     box-delivery: refreshed every substep, box_delivery_env.py:667-700; area-clearing: scaled by
+                                     target_speed / max_yaw_rate_step / 2 and set once, area_clearing.py:656-663) — cfg.agent.action_type */
     int32_t steps, iterations, settle_steps, inactivity_cutoff;   /* cfg.sim.steps / iterations, 1000, cfg.misc.inactivity_cutoff */
     int32_t local_map_pixel_width, use_correct_direction_reward;
     int32_t force_box_spfa;       /* 1: always solve spfa per box even when the exact visibility shortcut applies (testing aid) */

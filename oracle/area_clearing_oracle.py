@@ -1,7 +1,8 @@
 """ORACLE — test infrastructure only.
 
-CPU restatement of ``AreaClearingEnv`` (reference benchpush/environments/area_clearing/area_clearing.py) for the
-obstacle-free environments (``clear_env`` / ``clear_env_small``: no inner walls, no static obstacles), on top of the
+CPU restatement of ``AreaClearingEnv`` (reference benchpush/environments/area_clearing/area_clearing.py) for the four
+environments of ``area_clearing/envs/*.yaml`` (``clear_env``, ``clear_env_small``, ``walled_env``,
+``walled_env_with_columns``: inner walls and static obstacles are fixed per environment), on top of the
 box-delivery restatement (same position-control chain, same collision handlers, same local-map machinery):
 
 * physics: oracle/chipmunk_oracle.cpp, handler_mode 1 — PARITY UNPINNED.  Shapes are created in the order robot,
@@ -37,14 +38,34 @@ DISTANCE_SCALE_MAX = 0.5
 FLOOR_SEG_INDEX, GOAL_AREA_SEG_INDEX, COMPLETED_CUBE_SEG_INDEX, CUBE_SEG_INDEX, ROBOT_SEG_INDEX, MAX_SEG_INDEX = 1, 3, 7, 4, 5, 8
 STEP_LIMIT = 5000
 
-ENVS = {   # area_clearing/envs/*.yaml (the two without walls)
+def polygon_from_line(line, width=0.2):
+    """``create_polygon_from_line`` (geometry/polygon.py:201-207): shapely ``LineString(line).buffer(width / 2, cap_style=2,
+    join_style=2)`` of a two-point line = the rectangle of that width around it, flat caps (restated; shapely is absent)."""
+    p0, p1 = np.asarray(line[0], dtype=np.float64), np.asarray(line[1], dtype=np.float64)
+    d = p1 - p0
+    n = np.array([-d[1], d[0]]) / np.hypot(d[0], d[1]) * (width / 2)
+    return np.array([p0 + n, p1 + n, p1 - n, p0 - n])
+
+
+ENVS = {   # area_clearing/envs/*.yaml
     "clear_env": {"outer_boundary": [[-8.0, -8.0], [-8.0, 8.0], [8.0, 8.0], [8.0, -8.0]],
                   "boundary": [[-5.0, -5.0], [-5.0, 5.0], [5.0, 5.0], [5.0, -5.0]],
                   "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 24},
     "clear_env_small": {"outer_boundary": [[-6.0, -6.0], [-6.0, 6.0], [6.0, 6.0], [6.0, -6.0]],
                         "boundary": [[-4.0, -4.0], [-4.0, 4.0], [4.0, 4.0], [4.0, -4.0]],
                         "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 12},
+    "walled_env": {"outer_boundary": [[-8.0, -8.0], [-8.0, 8.0], [8.0, 8.0], [8.0, -8.0]],
+                   "boundary": [[-5.0, -5.0], [-5.0, 5.0], [5.0, 5.0], [5.0, -5.0]],
+                   "walls": [[[-6.0, -6.0], [-6.0, 6.0]], [[6.0, 6.0], [6.0, -6.0]]],
+                   "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 24},
+    "walled_env_with_columns": {"outer_boundary": [[-12.0, -12.0], [-12.0, 12.0], [12.0, 12.0], [12.0, -12.0]],
+                                "boundary": [[-7.5, -8.0], [-7.5, 8.0], [7.5, 8.0], [7.5, -8.0]],
+                                "walls": [[[-8.0, -8.0], [-8.0, 8.0]], [[8.0, 8.0], [8.0, -8.0]]],
+                                "static_obstacles": [[[-1.0, -6.0], [-1.0, -4.0], [1.0, -4.0], [1.0, -6.0]], [[-1.0, -1.0], [-1.0, 1.0], [1.0, 1.0], [1.0, -1.0]],
+                                                     [[-1.0, 4.0], [-1.0, 6.0], [1.0, 6.0], [1.0, 4.0]]],
+                                "local_map_pixel_width": 224, "sam_local_map_pixel_width": 96, "local_map_width": 24},
 }
+MAX_YAW_RATE_STEP = (np.pi / 2) / 15          # area_clearing.py:199
 
 DEFAULT_CFG = {   # area_clearing/config.yaml (keys that reach the hot path)
     "env": "clear_env", "num_obstacles": 10, "obstacle_size": 0.5, "min_obs_dist": 1.5, "low_dim_state": False, "random_start": True,
@@ -181,10 +202,19 @@ class AreaClearingOracleEnv(BoxDeliveryOracleEnv):
             sp.set_density(s, c["sim"]["obstacle_density"])
             sp.set_material(s, 0.01, 1.0, 2)
             self.box_bodies.append(b); self.box_shapes.append(s); self.box_idx.append(i)
-        # outer walls (generate_walls :488-513): static body, radius .1, friction .99, default elasticity 0, type 3
+        # static obstacles (generate_static_obstacles :437-453), inner walls as polygons around their centre lines and the
+        # four outer walls (generate_walls :455-513): static body, radius .1, friction .99, default elasticity 0; all of them
+        # end up with collision type 3 (:384-385)
         room_length, room_width, wt = abs(self.outer[0][0]) * 2, abs(self.outer[0][1]) * 2, 24
         self.boundary_shapes = []
         rect = lambda x, y, l, w: np.array([[x - l / 2, y - w / 2], [x + l / 2, y - w / 2], [x + l / 2, y + w / 2], [x - l / 2, y + w / 2]])
+        for kind, polys in (("static", [np.asarray(o, dtype=np.float64) for o in self.env_cfg.get("static_obstacles", [])]),
+                            ("wall", [polygon_from_line(w) for w in self.env_cfg.get("walls", [])])):
+            for poly in polys:
+                b = sp.add_body(cpo.STATIC, 0, 0, 0)
+                s = sp.add_poly(b, poly, 0.1)
+                sp.set_material(s, 0.0, 0.99, 3)
+                self.boundary_shapes.append((b, s, kind))
         for (x, y, length, width) in [(-room_length / 2 - wt / 2, 0, wt, room_width), (room_length / 2 + wt / 2, 0, wt, room_width),
                                       (0, -room_width / 2 - wt / 2, room_length + 2 * wt, wt), (0, room_width / 2 + wt / 2, room_length + 2 * wt, wt)]:
             b = sp.add_body(cpo.STATIC, 0, 0, 0)
@@ -193,6 +223,11 @@ class AreaClearingOracleEnv(BoxDeliveryOracleEnv):
             self.boundary_shapes.append((b, s, "wall"))
         self.box_local = {s: sp.get_vertices(s) for s in self.box_shapes}
         self.robot_local = sp.get_vertices(self.robot_shape)
+
+    @staticmethod
+    def _R(theta):
+        from .box_delivery_oracle import R
+        return R(theta)
 
     # ---- maps (area_clearing.py:956-1120)
     def update_configuration_space(self):
@@ -323,17 +358,28 @@ class AreaClearingOracleEnv(BoxDeliveryOracleEnv):
         h_init = restrict_heading_range(ang)
         self.dp = None
         at = self.cfg["agent"]["action_type"]
-        assert at in ("position", "heading")
-        if at == "heading":
-            W, ppm = self.local_map_pixel_width, self.local_map_pixels_per_meter
-            angle = (float(np.asarray(action).reshape(-1)[0]) + 1) * np.pi + np.pi / 2
-            step_size = self.cfg["agent"]["movement_step_size"]
-            x_pixel = int(W / 2 + step_size * np.cos(angle) * ppm)
-            y_pixel = int(W / 2 - step_size * np.sin(angle) * ppm)
-            action = y_pixel * W + x_pixel
-        self.path, move_sign = self.get_waypoints_to_spatial_action(p_init, h_init, int(action))
-        self.last_path = [list(p) for p in self.path]
-        robot_distance, robot_turn_angle = self.execute_robot_path(p_init, h_init, move_sign)
+        assert at in ("position", "heading", "velocity")
+        robot_distance, robot_turn_angle = 0, 0
+        if at == "velocity":
+            # area_clearing.py:656-663: the velocity is set ONCE (not refreshed while the heading changes); the policy's action
+            # is a float32 array (action_space dtype), so the two products are float32 (NumPy >= 2 promotion)
+            action = np.asarray(action, dtype=np.float32)
+            self.space.set_angular_velocity(self.robot_body, float(MAX_YAW_RATE_STEP * action[1] / 2))
+            scaled_vel = self.target_speed * action[0]
+            gv = self._R(ang) @ np.array([scaled_vel, 0])
+            self.space.set_velocity(self.robot_body, float(gv[0]), float(gv[1]))
+            self.last_path = []
+        else:
+            if at == "heading":
+                W, ppm = self.local_map_pixel_width, self.local_map_pixels_per_meter
+                angle = (float(np.asarray(action).reshape(-1)[0]) + 1) * np.pi + np.pi / 2
+                step_size = self.cfg["agent"]["movement_step_size"]
+                x_pixel = int(W / 2 + step_size * np.cos(angle) * ppm)
+                y_pixel = int(W / 2 - step_size * np.sin(angle) * ppm)
+                action = y_pixel * W + x_pixel
+            self.path, move_sign = self.get_waypoints_to_spatial_action(p_init, h_init, int(action))
+            self.last_path = [list(p) for p in self.path]
+            robot_distance, robot_turn_angle = self.execute_robot_path(p_init, h_init, move_sign)
         for _ in range(self.steps):
             self.space.step(self.dt / self.steps)
             self.n_substeps += 1

@@ -65,3 +65,51 @@ def test_full_size_batch_properties():
     assert set(np.unique(o[..., 0])) <= {0, 31, 95, 127, 159, 223} and set(np.unique(o[..., 1])) <= {0, 255}
     assert (o[:, 112, 112, 0] == 159).all()                       # the robot footprint is at the window centre
     env.close()
+
+
+@pytest.mark.parametrize("name", ["walled_env", "walled_env_with_columns"])
+def test_walled_environments_match_the_oracle_gpu(name, portable_trig):
+    """Inner walls / static obstacles (area_clearing/envs/walled_env*.yaml) on the GPU: maps, reset and an episode per env."""
+    from benchpush_b200.envs import AreaClearingVecEnv
+    from oracle.area_clearing_oracle import AreaClearingOracleEnv, sample_layout
+    cfg = {"env": name, "num_obstacles": 6}
+    lays = [sample_layout(random.Random(s), cfg) for s in range(7, 15)]
+    env = AreaClearingVecEnv(num_envs=8, cfg=cfg, layouts=lays, device=0)
+    picks = [0, 5]
+    oras = {e: AreaClearingOracleEnv(cfg=cfg, layouts=[lays[e]]) for e in picks}
+    obs, info = env.reset()
+    for e, ora in oras.items():
+        oobs, _ = ora.reset()
+        assert np.array_equal(env.room.configuration_space, ora.configuration_space)
+        assert np.array_equal(env.goal_point_global_map, ora.goal_point_global_map)
+        assert np.array_equal(obs[e].cpu().numpy(), oobs)
+    rng = np.random.default_rng(2)
+    for k in range(8):
+        a = rng.uniform(-1, 1, size=8).astype(np.float32)
+        out = env.step(a)
+        for e, ora in oras.items():
+            compare_step(env, ora, e, float(a[e]), out, state_tol=1e-7)
+    env.close()
+
+
+def test_velocity_actions_and_low_dim_state_gpu(portable_trig):
+    """action_type velocity (area_clearing.py:656-663) against the oracle; cfg.low_dim_state returns the centroid vector."""
+    from benchpush_b200.envs import AreaClearingVecEnv
+    from oracle.area_clearing_oracle import AreaClearingOracleEnv, sample_layout
+    cfg = {"env": "walled_env", "num_obstacles": 5, "agent": {"action_type": "velocity"}}
+    lays = [sample_layout(random.Random(s), cfg) for s in (11, 12)]
+    env = AreaClearingVecEnv(num_envs=2, cfg=cfg, layouts=lays, device=0)
+    ora = AreaClearingOracleEnv(cfg=cfg, layouts=[lays[1]])
+    env.reset(); ora.reset()
+    rng = np.random.default_rng(3)
+    for k in range(10):
+        a = rng.uniform(-1, 1, (2, 2)).astype(np.float32)
+        a[:, 0] = np.abs(a[:, 0])
+        compare_step(env, ora, 1, a[1], env.step(a), state_tol=1e-7)
+    env.close()
+    low = AreaClearingVecEnv(num_envs=2, cfg={"low_dim_state": True, "num_obstacles": 5}, layouts=lays, device=0)
+    obs, _ = low.reset()
+    assert tuple(obs.shape) == (2, 10) and low.single_observation_space.shape == (10,)
+    want = np.abs(np.array(lays[0]["boxes"])).reshape(-1)
+    np.testing.assert_allclose(obs[0].cpu().numpy(), want, atol=1e-9)
+    low.close()

@@ -72,3 +72,51 @@ def test_small_environment_matches_the_oracle(portable_trig):
         a = float(np.float32(rng.uniform(-1, 1)))
         compare_step(env, ora, 0, a, env.step(np.array([a], dtype=np.float32)), state_tol=1e-9)
     env.close()
+
+
+import pytest
+
+
+@pytest.mark.parametrize("name,shape", [("walled_env", (468, 468)), ("walled_env_with_columns", (542, 542))])
+def test_walled_environments_match_the_oracle(name, shape, portable_trig):
+    """walled_env / walled_env_with_columns (area_clearing/envs/*.yaml): inner walls (polygons around their centre lines,
+    area_clearing.py:455-480) and static obstacles (:437-453) are static shapes of the handle and obstacle pixels of the
+    configuration space; maps, reset and a heading episode against the oracle."""
+    cfg = {"env": name, "num_obstacles": 6}
+    lay = [sample_layout(random.Random(7), cfg)]
+    env = AreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=lay, _backend=emu_bd.lib())
+    ora = AreaClearingOracleEnv(cfg=cfg, layouts=lay)
+    obs, info = env.reset()
+    oobs, oinfo = ora.reset()
+    r = env.room
+    assert r.shape == shape
+    assert len(r.statics) == 4 + len(ENVS[name].get("walls", [])) + len(ENVS[name].get("static_obstacles", []))
+    assert np.array_equal(r.configuration_space, ora.configuration_space)
+    assert np.array_equal(r.closest_cspace_indices, ora.closest_cspace_indices)
+    assert np.array_equal(env.goal_point_global_map, ora.goal_point_global_map)
+    assert np.array_equal(obs[0], oobs)
+    nb = len(lay[0]["boxes"])
+    assert np.array_equal(env.get_bodies(0)[:1 + nb, :6], ora.space.state()[:1 + nb])
+    rng = np.random.default_rng(2)
+    for k in range(8):
+        a = float(np.float32(rng.uniform(-1, 1)))
+        compare_step(env, ora, 0, a, env.step(np.array([a], dtype=np.float32)), state_tol=1e-9)
+    env.close()
+
+
+def test_velocity_actions_match_the_oracle(portable_trig):
+    """action_type velocity (area_clearing.py:656-663): yaw rate = max_yaw_rate_step * a[1] / 2, surge = target_speed * a[0]
+    set once per step, then cfg.sim.steps substeps."""
+    cfg = {"env": "walled_env", "num_obstacles": 5, "agent": {"action_type": "velocity"}}
+    lay = [sample_layout(random.Random(11), cfg)]
+    env = AreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=lay, _backend=emu_bd.lib())
+    ora = AreaClearingOracleEnv(cfg=cfg, layouts=lay)
+    env.reset(); ora.reset()
+    assert env.single_action_space.shape == (2,)
+    rng = np.random.default_rng(3)
+    for k in range(12):
+        a = rng.uniform(-1, 1, 2).astype(np.float32)
+        a[0] = abs(a[0])                                   # drive forward into the boxes
+        compare_step(env, ora, 0, a, env.step(a[None, :]), state_tol=1e-9)
+    assert ora.space.state()[0, 1] > lay[0]["start"][1] + 0.2
+    env.close()

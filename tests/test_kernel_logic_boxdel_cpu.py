@@ -169,3 +169,26 @@ def test_room_env_spaces_follow_the_reference():
     ac = AreaClearingVecEnv(num_envs=1, cfg={"agent": {"action_type": "position"}}, _backend=emu_bd.lib())
     assert ac.single_action_space.shape == (1,) and ac.single_action_space.dtype == np.int32
     ac.close()
+
+
+def test_low_dim_state_observation_of_the_room_envs():
+    """cfg.low_dim_state (box_delivery_env.py:166-169, 1025-1037; area_clearing.py:212-215, 908-920): reset / step return
+    <|cx|, |cy|> of every box left instead of the image, the space is Box(-10, 30, (2 * num_boxes,))."""
+    import random
+    from benchpush_b200.envs.area_clearing import AreaClearingVecEnv
+    from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
+    from oracle.area_clearing_oracle import sample_layout as ac_layout
+    from oracle.raster_oracle import poly_centroid
+    from tests.emu import emu_bd
+    for mk in (lambda: BoxDeliveryVecEnv(num_envs=2, cfg={"low_dim_state": True, "agent": {"action_type": "heading"}}, _backend=emu_bd.lib()),
+               lambda: AreaClearingVecEnv(num_envs=2, cfg={"low_dim_state": True}, layouts=[ac_layout(random.Random(s)) for s in (1, 2)], _backend=emu_bd.lib())):
+        env = mk()
+        obs, info = env.reset()
+        NB = env.num_boxes
+        assert obs.shape == (2, 2 * NB) and env.single_observation_space.shape == (2 * NB,)
+        obs, r, term, trunc, info = env.step(np.array([0.2, -0.4], dtype=np.float32))
+        for e in range(2):
+            want = np.concatenate([np.abs(poly_centroid(np.asarray(info["obs"][e][i]))) for i in range(int(info["n_boxes_left"][e]))])
+            np.testing.assert_allclose(obs[e][:len(want)], want, rtol=1e-12)
+            assert not obs[e][len(want):].any()
+        env.close()
