@@ -34,7 +34,7 @@ class MazeNamoVecEnv(ShipIceVecEnv):
 
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence] = None,
                  auto_reset: bool = False, first_layout: Optional[Sequence[int]] = None, synthetic_seed: int = 0,
-                 n_synthetic_layouts: int = 256):
+                 n_synthetic_layouts: int = 256, start_seed: int = 0):
         if not torch.cuda.is_available():
             raise _lib.BenchPushError("MazeNamoVecEnv needs a CUDA device (there is no CPU fallback)")
         self.cfg = merge_cfg(DotDict.load_from_file(_CFG_PATH), cfg)
@@ -46,10 +46,6 @@ class MazeNamoVecEnv(ShipIceVecEnv):
             raise Exception("Invalid Maze Version!")
         self.low_dim_state = bool(self.cfg.low_dim_state)
         self.auto_reset = bool(auto_reset)
-        if self.cfg.random_start:
-            raise NotImplementedError("cfg.random_start is not implemented for the maze: the reference samples the obstacles around the drawn "
-                                      "start (maze_NAMO_env.py:229-301), so start poses and layouts have to be generated together; callers that "
-                                      "do so can pass them through set_start_poses()")
         if int(self.cfg.occ.local_width) * int(self.cfg.occ.m_to_pix_scale) != 192 or int(self.cfg.occ.local_height) * int(self.cfg.occ.m_to_pix_scale) != 192:
             raise NotImplementedError("the observation kernel is built for a 192 x 192 local window (occ.local_* x occ.m_to_pix_scale)")
         if tuple(self.cfg.sim.gravity) != (0, 0):
@@ -136,15 +132,39 @@ class MazeNamoVecEnv(ShipIceVecEnv):
         self._out = o
         self._init_low_dim(2 * (self.max_boxes + 1))
         self._start_poses = None
-        self.random_start, self.redraw_starts = False, False
+        self.random_start, self.redraw_starts = bool(self.cfg.random_start), True
         if first_layout is None:
             first_layout = np.arange(E) % self.env_max_trial
         self._next_trial = torch.as_tensor(np.asarray(first_layout, dtype=np.int32), device=dev)
         self._actions = torch.zeros(E, dtype=torch.float32, device=dev)
+        if self.random_start:
+            self._start_rng = np.random.default_rng(start_seed)
+            self.set_start_poses(self._sample_starts())
         if not self.low_dim_state:
             self.observation_shape = _lib.MAZE_OBS_SHAPE
         self.action_low, self.action_high = -1.0, 1.0
         self.check_status = True
+
+    def _sample_starts(self) -> np.ndarray:
+        """cfg.random_start (maze_NAMO_env.py:229-238): x ~ 1 + U[0,1) (start_x_range - 1), y likewise, redrawn until no wall
+        segment (radius 0.5) is closer than cfg.robot.min_obstacle_dist (`space.point_query(p, min_dist)`: strict <), heading
+        3 pi / 2.  The obstacles are sampled independently of the start (:275-301).  The reference draws from the unseeded global
+        `random`; here one seeded generator serves all envs (drawn before each reset and after each step, like ship-ice)."""
+        E = self.num_envs
+        sx, sy = float(self.cfg.start_x_range), float(self.cfg.start_y_range)
+        md, wr = float(self.cfg.robot.min_obstacle_dist), 0.5
+        A = np.array([w[0] for w in self.maze_walls], dtype=np.float64); B = np.array([w[1] for w in self.maze_walls], dtype=np.float64)
+        out = np.zeros((E, 3)); out[:, 2] = np.pi * 3 / 2
+        todo = np.arange(E)
+        while todo.size:
+            p = np.stack([1 + self._start_rng.random(todo.size) * (sx - 1), 1 + self._start_rng.random(todo.size) * (sy - 1)], axis=1)
+            d = B - A                                                          # distance to every wall segment
+            t = np.clip(((p[:, None, :] - A[None]) * d[None]).sum(2) / (d * d).sum(1)[None], 0.0, 1.0)
+            dist = np.linalg.norm(p[:, None, :] - (A[None] + t[..., None] * d[None]), axis=2) - wr
+            ok = ~(dist < md).any(axis=1)
+            out[todo[ok], :2] = p[ok]
+            todo = todo[~ok]
+        return out
 
     def _info(self, reset: bool):
         info = {"state": self._state, "total_work": self._total_work, "obs": _LazyObstacles(self), "pose": self._pose}

@@ -300,6 +300,9 @@ class MazeNamoOracleEnv:
         assert layouts is not None, "obstacle layouts are inputs to the oracle"
         self.layouts = layouts
         self.order_mode = order_mode
+        import random as _random
+        self.rng = _random
+        self.start_override = None
         self._maps = None
 
     def construct_maze_walls(self):
@@ -328,7 +331,18 @@ class MazeNamoOracleEnv:
             body = self.space.add_body(cpo.STATIC, 0.0, 0.0, 0.0)
             seg = self.space.add_segment(body, a, b, 0.5)
             self.space.set_material(seg, 0.5, 0.5, 3)
-        if self.cfg["maze_version"] == 1:
+        if self.cfg["random_start"]:
+            # maze_NAMO_env.py:229-238: redraw until no wall is closer than min_obstacle_dist (point_query, strict <); the
+            # reference draws from the global `random` module (self.rng); tests replay the start the CUDA path drew
+            while True:
+                x_start = 1 + self.rng.random() * (self.cfg["start_x_range"] - 1)
+                y_start = 1 + self.rng.random() * (self.cfg["start_y_range"] - 1)
+                if not self.space.point_query_any((x_start, y_start), self.cfg["robot"]["min_obstacle_dist"]):
+                    break
+            self.start = (x_start, y_start, np.pi * 3 / 2)
+            if self.start_override is not None:
+                self.start = tuple(self.start_override)
+        elif self.cfg["maze_version"] == 1:
             self.start = (11.25, 3.75, np.pi / 2)
         else:
             self.start = (16.66, 16.66, 3 * np.pi / 2)

@@ -194,3 +194,41 @@ def test_full_size_properties_16384_envs():
     # observation sanity: the footprint channel holds the robot in the middle of the window, the wall channel is non-empty
     assert int(obs[0, 0, 96, 96]) == 255 and int(obs[:64, 2].max()) == 255
     env.close()
+
+
+def test_maze_random_start(portable_trig):
+    """cfg.random_start (maze_NAMO_env.py:229-238): start drawn in [1, start_range) x [1, start_range), rejected while a wall
+    segment (radius 0.5) is closer than robot.min_obstacle_dist, heading 3 pi / 2; reset and steps from the drawn pose are
+    bit-identical to the oracle started at the same pose, and the oracle's own sampler accepts exactly such poses."""
+    import random
+    from benchpush_b200.envs import MazeNamoVecEnv
+    from oracle.maze_oracle import MazeNamoOracleEnv
+    lay = [[[8.5, 11], [10, 9], [11.25, 11.5], [6, 10], [3.5, 8.5]]]
+    cfg = {"random_start": True, "start_x_range": 14, "start_y_range": 14}
+    env = MazeNamoVecEnv(num_envs=4, cfg=cfg, layouts=lay, device=0, start_seed=5)
+    obs, info = env.reset()
+    starts = env.start_poses.copy()
+    assert ((starts[:, :2] >= 1) & (starts[:, :2] < 14)).all() and (starts[:, 2] == np.pi * 3 / 2).all() and len(set(starts[:, 0])) == 4
+    for e in (0, 3):
+        ora = MazeNamoOracleEnv(cfg, layouts=lay, order_mode=1)
+        ora.start_override = starts[e]
+        oobs, oinfo = ora.reset()
+        assert not ora.space.point_query_any((starts[e, 0], starts[e, 1]), ora.cfg["robot"]["min_obstacle_dist"])    # an admissible draw
+        assert np.array_equal(env.get_bodies(e)[6:12], ora.space.state()[6:12])        # 5 obstacles + robot chassis
+        assert np.array_equal(obs[e].cpu().numpy(), oobs)
+        if e == 0:
+            ora0 = ora
+    env.redraw_starts = False
+    rng = np.random.default_rng(2)
+    for k in range(4):
+        a = rng.uniform(-1, 1, 4)
+        obs, rew, term, trunc, info = env.step(a.astype(np.float32))
+        oobs, orew, oterm, _, oinfo = ora0.step(float(np.float32(a[0])))
+        assert np.array_equal(env.get_bodies(0)[6:12], ora0.space.state()[6:12])
+        assert np.array_equal(obs[0].cpu().numpy(), oobs)
+        np.testing.assert_allclose(float(rew[0]), orew, rtol=1e-9, atol=1e-7)
+    env.close()
+    ora = MazeNamoOracleEnv(cfg, layouts=lay, order_mode=1)
+    ora.rng = random.Random(1)
+    ora.reset(settle=False)
+    assert 1 <= ora.start[0] < 14 and 1 <= ora.start[1] < 14 and ora.start[2] == np.pi * 3 / 2

@@ -191,10 +191,7 @@ def test_full_size_properties_synthetic_high_concentration():
 def test_no_cpu_fallback_errors():
     from benchpush_b200 import _lib
     from benchpush_b200.envs import ShipIceVecEnv
-    from benchpush_b200.envs import MazeNamoVecEnv
     with pytest.raises(NotImplementedError):                    # options that are not built fail loudly instead of being ignored
-        MazeNamoVecEnv(num_envs=1, cfg={"random_start": True}, device=0)
-    with pytest.raises(NotImplementedError):
         ShipIceVecEnv(num_envs=1, cfg={"concentration": 0.1, "sim": {"gravity": (0, -1)}}, layouts=pack_trials(generate_experiment(1, 0.1, seed=1)), device=0)
     with pytest.raises(_lib.BenchPushError):
         trials = generate_experiment(1, 0.1, seed=1)
