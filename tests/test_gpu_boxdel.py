@@ -157,3 +157,28 @@ def test_velocity_actions_match_the_oracle(portable_trig):
         assert abs(float(out[1][0]) - orr) <= 1e-8 and env.get_step_debug(0)["substeps"] == 1000 + ora.n_substeps
         assert int((out[0][0].cpu().numpy() != oobs).sum()) <= 4
     env.close()
+
+
+def test_literal_per_box_spfa_path_on_the_gpu(portable_trig):
+    """force_box_spfa: k_bd_dist solves spfa per box, walks the parents and runs Douglas-Peucker + line-of-sight pruning (the
+    reference's literal shortest_path_distance, box_delivery_env.py:1209-1268) instead of the exact visibility shortcut.
+    On the GPU both must give the same episode as the oracle and as each other."""
+    from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
+    from oracle.box_delivery_oracle import BoxDeliveryOracleEnv, sample_layout
+    cfg = {"agent": {"action_type": "heading"}}
+    lays = [sample_layout(np.random.RandomState(42 + s)) for s in range(4)]
+    fast = BoxDeliveryVecEnv(num_envs=4, cfg=cfg, layouts=lays, device=0)
+    slow = BoxDeliveryVecEnv(num_envs=4, cfg=cfg, layouts=lays, device=0, force_box_spfa=True)
+    ora = BoxDeliveryOracleEnv(cfg=cfg, layouts=[lays[0]])
+    fast.reset(); slow.reset(); ora.reset()
+    rng = np.random.default_rng(4)
+    for k in range(6):
+        a = rng.uniform(-1, 1, size=4).astype(np.float32)
+        out_f = fast.step(a)
+        out_s = slow.step(a)
+        compare_step(slow, ora, 0, None, float(a[0]), step_out=out_s, state_tol=1e-7)
+        assert np.array_equal(out_f[1].cpu().numpy(), out_s[1].cpu().numpy())                  # rewards (partial rewards use the box distances)
+        for e in range(4):
+            assert np.array_equal(fast.get_step_debug(e)["init_dist"], slow.get_step_debug(e)["init_dist"])
+            assert np.array_equal(fast.get_bodies(e), slow.get_bodies(e))
+    fast.close(); slow.close()

@@ -164,3 +164,24 @@ def test_maze_maps_and_observation_bit_exact(ref):
     for pose, want in zip(ref["maze_poses"], ref["maze_obs"]):
         got = (np.asarray(mo.ego_view_map_maze(tuple(pose), ref["maze_robot_verts"], boxes, walls, norm)) * 255).astype(np.uint8)   # :142-202
         assert np.array_equal(got, want), int((got != want).sum())
+
+
+def test_position_controller_waypoints(ref):
+    """PositionController.get_waypoints_to_spatial_action (position_controller.py:56-181) — the reference class run with the
+    reference's own compiled spfa on the walled_env_with_columns configuration space — against the oracle's restatement:
+    same waypoint count, positions and move sign on straight-line, clamped and spfa + Douglas-Peucker + pruning cases."""
+    import random
+    from oracle.area_clearing_oracle import AreaClearingOracleEnv, sample_layout
+    acfg = {"env": "walled_env_with_columns", "num_obstacles": 4}
+    ora = AreaClearingOracleEnv(cfg=acfg, layouts=[sample_layout(random.Random(3), acfg)])
+    ora.reset()
+    assert ora.configuration_space.sum() == ref["pc_cspace_sum"][0]
+    off, multi = 0, 0
+    for x, y, h, action, sign, n in ref["pc_rows"]:
+        n = int(n)
+        want = ref["pc_paths"][off:off + 2 * n].reshape(n, 2); off += 2 * n
+        path, s = ora.get_waypoints_to_spatial_action([x, y], h, int(action))
+        assert len(path) == n and float(s) == float(sign), (len(path), n, s, sign)
+        np.testing.assert_allclose(np.asarray([p[:2] for p in path], dtype=np.float64), want, rtol=0, atol=1e-12)
+        multi += n > 2
+    assert multi >= 2, "the fixture should contain paths that go around the columns"

@@ -302,6 +302,28 @@ def main():
     out["maze_poses"] = np.array(mposes)
     out["maze_obs"] = np.stack([(np.asarray(mo.ego_view_map_maze(p, rv, mboxes, walls, dist_map)) * 255).astype(np.uint8) for p in mposes])
     out["maze_robot_verts"] = rv
+    # ---- PositionController (C1): the reference class with the reference's own compiled spfa (oracle/_ref), on the
+    # configuration space of walled_env_with_columns so that both the straight-line and the spfa + Douglas-Peucker branch run
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    from benchpush.common.controller.position_controller import PositionController
+    from oracle.area_clearing_oracle import AreaClearingOracleEnv, sample_layout
+    import random as _random
+    acfg = {"env": "walled_env_with_columns", "num_obstacles": 4}
+    ora = AreaClearingOracleEnv(cfg=acfg, layouts=[sample_layout(_random.Random(3), acfg)])
+    ora.reset()
+    pc = PositionController(None, ora.robot_radius, ora.map_width, ora.map_height, ora.configuration_space, ora.configuration_space_thin,
+                            ora.closest_cspace_indices, ora.local_map_pixel_width, ora.local_map_width, ora.local_map_pixels_per_meter,
+                            np.radians(15), 0.05, 0.03, np.radians(1))
+    LW = ora.local_map_pixel_width
+    pc_rows, pc_paths = [], []
+    for (x, y, h, i, j) in [(0.0, -7.0, np.pi / 2, 20, 112), (-3.0, -5.5, 0.3, 60, 200), (3.5, 0.0, -2.0, 112, 10), (0.0, -7.0, np.pi / 2, 5, 112),
+                            (-6.0, 6.5, -1.2, 30, 180), (2.0, 2.0, 2.5, 200, 60), (0.5, -3.0, 1.6, 40, 112), (6.5, -7.0, 3.0, 100, 20)]:
+        path, sign = pc.get_waypoints_to_spatial_action([x, y], h, int(i * LW + j))
+        pc_rows.append([x, y, h, i * LW + j, sign, len(path)])
+        pc_paths.append(np.asarray(path, dtype=np.float64)[:, :2].reshape(-1))
+    out["pc_rows"] = np.array(pc_rows)
+    out["pc_paths"] = np.concatenate(pc_paths)
+    out["pc_cspace_sum"] = np.array([ora.configuration_space.sum()])
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, {k: v.shape for k, v in out.items()})
 
