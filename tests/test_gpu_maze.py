@@ -202,6 +202,7 @@ def test_maze_random_start(portable_trig):
     bit-identical to the oracle started at the same pose, and the oracle's own sampler accepts exactly such poses."""
     import random
     from benchpush_b200.envs import MazeNamoVecEnv
+    from oracle import cpo
     from oracle.maze_oracle import MazeNamoOracleEnv
     lay = [[[8.5, 11], [10, 9], [11.25, 11.5], [6, 10], [3.5, 8.5]]]
     cfg = {"random_start": True, "start_x_range": 14, "start_y_range": 14}
@@ -213,7 +214,10 @@ def test_maze_random_start(portable_trig):
         ora = MazeNamoOracleEnv(cfg, layouts=lay, order_mode=1)
         ora.start_override = starts[e]
         oobs, oinfo = ora.reset()
-        assert not ora.space.point_query_any((starts[e, 0], starts[e, 1]), ora.cfg["robot"]["min_obstacle_dist"])    # an admissible draw
+        walls_only = cpo.Space()                                  # the reference samples the start when only the walls exist
+        for a_, b_ in ora.maze_walls:
+            walls_only.add_segment(walls_only.add_body(cpo.STATIC, 0.0, 0.0, 0.0), a_, b_, 0.5)
+        assert not walls_only.point_query_any((starts[e, 0], starts[e, 1]), ora.cfg["robot"]["min_obstacle_dist"])    # an admissible draw
         assert np.array_equal(env.get_bodies(e)[6:12], ora.space.state()[6:12])        # 5 obstacles + robot chassis
         assert np.array_equal(obs[e].cpu().numpy(), oobs)
         if e == 0:
