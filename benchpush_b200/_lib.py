@@ -13,6 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 # BENCHPUSH_B200_LIB: development aid to load a differently-tuned build of the same CUDA library
 LIB_PATH = os.environ.get("BENCHPUSH_B200_LIB") or os.path.join(CSRC, "libbenchpush_b200.so")
+# The same sources built with fp32 body state / contacts / solver (csrc/Makefile, -DBP_F32): ship-ice and maze only.
+LIB_PATH_F32 = os.environ.get("BENCHPUSH_B200_LIB_F32") or os.path.join(CSRC, "libbenchpush_b200_f32.so")
 
 BP_VMAX = 20
 OBS_SHAPE = (4, 150, 150)
@@ -66,16 +68,24 @@ def build(verbose: bool = False) -> str:
 
 
 _LIB = None
+_LIBS = {}
 
 
-def lib():
+def lib(precision: str = "fp64"):
+    """``precision``: "fp64" = libbenchpush_b200.so (bit-comparable with the fp64 oracle; every env family), "fp32" =
+    libbenchpush_b200_f32.so (ship-ice / maze with fp32 body state, contacts and solver; same C ABI, outputs stay double)."""
     global _LIB
-    if _LIB is None:
-        if not os.path.exists(LIB_PATH):
+    if precision not in ("fp64", "fp32"):
+        raise ValueError("precision must be 'fp64' or 'fp32'")
+    if precision in _LIBS:
+        return _LIBS[precision]
+    if True:
+        path = LIB_PATH if precision == "fp64" else LIB_PATH_F32
+        if not os.path.exists(path):
             raise BenchPushError(
-                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         L.bp_version.restype = C.c_int
         L.bp_last_error.restype = C.c_char_p
         L.bp_device_count.restype = C.c_int
@@ -124,8 +134,10 @@ def lib():
         L.bp_maze_get_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bp_spfa_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bp_spfa_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
-        _LIB = L
-    return _LIB
+        _LIBS[precision] = L
+        if precision == "fp64":
+            _LIB = L
+    return _LIBS[precision]
 
 
 EXPORTS = [

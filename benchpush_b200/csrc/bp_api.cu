@@ -1084,4 +1084,7 @@ int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batc
 
 }  // extern "C"
 
+// box-delivery-v0 / area-clearing-v0 keep fp64 state (their own small-world core, boxdel_*.cuh): not part of the fp32 build
+#ifndef BP_F32
 #include "boxdel_api.cuh"
+#endif

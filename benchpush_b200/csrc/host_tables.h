@@ -13,7 +13,7 @@ namespace bp {
 
 struct HostLayouts {
     int NB = 0, L = 0;
-    std::vector<double> lv, ln, rad, rbound, minv, iinv, cog, mat_e, mat_u, init;
+    std::vector<real> lv, ln, rad, rbound, minv, iinv, cog, mat_e, mat_u, init;      // body-state precision of the build
     std::vector<int> nv, nbody, robot0;
     // raw (un-hulled) world-space trial vertices: the reset observation rasterises these
     // (ship_ice_env.py:207,248), plus |centroid| of each raw polygon for the local-range test

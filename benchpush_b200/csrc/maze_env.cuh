@@ -64,7 +64,7 @@ BP_DEVNI void maze_step_finish(const EnvView& ev, const LayoutView& L, const Sim
         double gx = o.x - P.goal_x, gy = o.y - P.goal_gy;
         bool reached = sqrt(gx * gx + gy * gy) <= P.goal_reach;
         bool terminated = reached || wall;
-        double incr = 0.0;
+        double incr = RC(0.0);
         if (o.x != P.goal_x || o.y != P.goal_gy) {
             double dv = maze_distance_value(P, o.x, o.y);
             if (sc->has_prev_dist) incr = (sc->prev_dist - dv) * P.k_increment;

@@ -84,7 +84,8 @@ BP_DEV double mz_fma(double a, double b, double c) { return fma(a, b, c); }
 
 // Rasterise polygon (verts in metres) into bit `bit` of the crop; draw.polygon bounding box, clipped to
 // `clip_h x clip_w` when clip != 0 (the shape= argument), then to the crop window.
-BP_DEV void mz_fill_poly(MazeObsSmem& S, const double* v, int n, double scale, int clip, int grid_h, int grid_w, int g0i, int g0j, unsigned char bit) {
+template <typename VT>
+BP_DEV void mz_fill_poly(MazeObsSmem& S, const VT* v, int n, double scale, int clip, int grid_h, int grid_w, int g0i, int g0j, unsigned char bit) {
     const int tid = BP_TID, nt = BP_NT;
     double rmin = INFINITY, rmax = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
     for (int i = 0; i < n; i++) {
@@ -111,7 +112,8 @@ BP_DEV void mz_fill_poly(MazeObsSmem& S, const double* v, int n, double scale, i
 
 // verts / nverts: the movable obstacles as world-space polygons (hull vertices after a step, the raw
 // layout vertices at reset: the reference keeps self.obstacles from before the settle steps).
-BP_DEV void render_maze_obs(MazeObsSmem& S, const MazeObsParams& O, int n_obst, const double* verts, int poly_stride, const int* nverts,
+template <typename VT>
+BP_DEV void render_maze_obs(MazeObsSmem& S, const MazeObsParams& O, int n_obst, const VT* verts, int poly_stride, const int* nverts,
                             double rx, double ry, double ra, unsigned char* out /* [4][192][192] */) {
     const int tid = BP_TID, nt = BP_NT;
     double s, c; bp_sincos(ra, &s, &c);

@@ -53,7 +53,8 @@ struct ObsParams {
 };
 
 // skimage point_in_polygon on vertices (px[i], py[i]) = (vx[2i]*sx, vx[2i+1]*sy); != 0 means inside.
-BP_DEV bool pip_inclusive(const double* v, int n, double scale, double x, double y) {
+template <typename VT>
+BP_DEV bool pip_inclusive(const VT* v, int n, double scale, double x, double y) {
     const double eps = 1e-12;
     unsigned r_cross = 0, l_cross = 0;
     double x1 = v[2 * (n - 1)] * scale - x;
@@ -163,8 +164,9 @@ struct ObsSmem {
 // Compose the observation of one env.  verts/nverts/cen describe the obstacles as world-space
 // polygons: after a step these are the hull vertices wv (get_obs_from_poly), at reset the raw trial
 // vertices.  poly_stride = doubles between consecutive polygons.
-BP_DEV void render_obs(ObsSmem& S, const ObsParams& O, int n_obst, const double* verts, int poly_stride, const int* nverts,
-                       const double* cenx, const double* ceny, int cen_stride, double rx, double ry, double ra,
+template <typename VT, typename CT>
+BP_DEV void render_obs(ObsSmem& S, const ObsParams& O, int n_obst, const VT* verts, int poly_stride, const int* nverts,
+                       const CT* cenx, const CT* ceny, int cen_stride, double rx, double ry, double ra,
                        unsigned char* out /* [4][150][150] */) {
     const int tid = BP_TID, nt = BP_NT;
     double s, c; bp_sincos(ra, &s, &c);
@@ -193,7 +195,7 @@ BP_DEV void render_obs(ObsSmem& S, const ObsParams& O, int n_obst, const double*
     for (int b = tid; b < n_obst; b += nt) {
         double cx = cenx[(size_t)b * cen_stride], cy = ceny[(size_t)b * cen_stride];
         if (fabs(rx - cx) > O.range_x || fabs(ry - cy) > O.range_y) continue;
-        const double* v = verts + (size_t)b * poly_stride;
+        const VT* v = verts + (size_t)b * poly_stride;
         int n = nverts[b];
         double l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
         for (int i = 0; i < n; i++) {
@@ -208,7 +210,7 @@ BP_DEV void render_obs(ObsSmem& S, const ObsParams& O, int n_obst, const double*
     int nc = S.n_cand < MAX_CAND ? S.n_cand : MAX_CAND;
     for (int k = 0; k < nc; k++) {
         int b = S.cand[k];
-        const double* v = verts + (size_t)b * poly_stride;
+        const VT* v = verts + (size_t)b * poly_stride;
         int n = nverts[b];
         double rmin = INFINITY, rmax = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
         for (int i = 0; i < n; i++) {
@@ -292,7 +294,8 @@ constexpr int OBS_FILL_GROUP = 1;
 #endif
 
 // skimage _polygon bounding box of the scaled polygon, clipped to an H x W image; false when empty
-BP_DEV bool polygon_bbox(const double* v, int n, double scale, int H, int W, int* minr, int* minc, int* bw, int* bh) {
+template <typename VT>
+BP_DEV bool polygon_bbox(const VT* v, int n, double scale, int H, int W, int* minr, int* minc, int* bw, int* bh) {
     double rmin = INFINITY, rmax = -INFINITY, cmin = INFINITY, cmax = -INFINITY;
     for (int i = 0; i < n; i++) {
         double x = v[2 * i] * scale, y = v[2 * i + 1] * scale;
@@ -307,7 +310,8 @@ BP_DEV bool polygon_bbox(const double* v, int n, double scale, int H, int W, int
     return true;
 }
 
-BP_DEV void render_obs_global(ObsGlobalSmem& S, const ObsParams& O, const GlobalObsParams& G, int n_obst, const double* verts,
+template <typename VT>
+BP_DEV void render_obs_global(ObsGlobalSmem& S, const ObsParams& O, const GlobalObsParams& G, int n_obst, const VT* verts,
                               int poly_stride, const int* nverts, double rx, double ry, double ra, unsigned char* out /* [2][gh][gw] */) {
     const int tid = BP_TID, nt = BP_NT;
     const int nwords = (G.raw_h * G.raw_w + 31) / 32;
@@ -327,7 +331,7 @@ BP_DEV void render_obs_global(ObsGlobalSmem& S, const ObsParams& O, const Global
     BP_BSYNC();
     const int lane = tid % OBS_FILL_GROUP, grp = tid / OBS_FILL_GROUP, ngrp = nt / OBS_FILL_GROUP;
     for (int b = grp; b < n_obst; b += ngrp) {
-        const double* v = verts + (size_t)b * poly_stride;
+        const VT* v = verts + (size_t)b * poly_stride;
         const int n = nverts[b];
         int minr, minc, bw, bh;
         if (!polygon_bbox(v, n, O.scale, G.raw_h, G.raw_w, &minr, &minc, &bw, &bh)) continue;

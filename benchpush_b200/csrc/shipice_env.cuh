@@ -23,26 +23,26 @@ struct StepOut {
 };
 
 // geometry/polygon.py:25-41 on the world-space hull vertices of body b (np.roll(y, 1)[i] = y[i-1]).
-BP_DEVNI void area_centroid_abs(const double* wv, int n, double* area, double* cx, double* cy) {
-    double s1 = 0.0, s2 = 0.0;
+BP_DEVNI void area_centroid_abs(const real* wv, int n, real* area, real* cx, real* cy) {
+    real s1 = RC(0.0), s2 = RC(0.0);
     for (int i = 0; i < n; i++) {
         int j = (i == 0) ? n - 1 : i - 1;
         s1 += wv[2 * i] * wv[2 * j + 1];
         s2 += wv[2 * i + 1] * wv[2 * j];
     }
-    double A = 0.5 * fabs(s1 - s2);
-    double sx = 0.0, sy = 0.0;
+    real A = RC(0.5) * fabs(s1 - s2);
+    real sx = RC(0.0), sy = RC(0.0);
     for (int i = 0; i < n; i++) {
         int j = (i == 0) ? n - 1 : i - 1;
-        double u = wv[2 * i] * wv[2 * j + 1] - wv[2 * j] * wv[2 * i + 1];
+        real u = wv[2 * i] * wv[2 * j + 1] - wv[2 * j] * wv[2 * i + 1];
         sx += (wv[2 * i] + wv[2 * j]) * u;
         sy += (wv[2 * i + 1] + wv[2 * j + 1]) * u;
     }
-    double k = 1.0 / (6.0 * A);
+    real k = RC(1.0) / (RC(6.0) * A);
     *area = A; *cx = fabs(k * sx); *cy = fabs(k * sy);
 }
 
-BP_DEV double round2(double x) { return rint(x * 100.0) / 100.0; }
+BP_DEV double round2(double x) { return rint(x * RC(100.0)) / RC(100.0); }
 
 // True when a substep can change nothing: the ship is the only awake body and does not move, and
 // no arbiter is touching or cached (so no stamp-based expiry is pending either).
@@ -50,7 +50,7 @@ BP_DEV bool settle_is_idle(const EnvView& ev, const EnvScal* sc) {
     // bodies that are not dynamic never leave the awake list, so "only they are awake" is a count
     if (sc->n_awake != sc->n_fixed || sc->n_order != 0 || sc->n_cached != 0 || sc->dirty || sc->rebuild) return false;
     const BodyRec& R = ev.body[sc->robot];
-    return R.vx == 0.0 && R.vy == 0.0 && R.vw == 0.0 && R.bx == 0.0 && R.by == 0.0 && R.bw == 0.0;
+    return R.vx == RC(0.0) && R.vy == RC(0.0) && R.vw == RC(0.0) && R.bx == RC(0.0) && R.by == RC(0.0) && R.bw == RC(0.0);
 }
 
 BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const SimParams& P, const Dims& d, int layout_id, int env, const StepOut& out,
@@ -60,7 +60,7 @@ BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const Sim
     const int lane = bp_lane();
     init_env(ev, L, P, d, layout_id, start);
     // 1000 settle substeps with the ship at rest (ship_ice_env.py:218-219)
-    double prev_dt = 0.0;
+    real prev_dt = RC(0.0);
     for (int k = 0; k < P.settle_steps; k++) {
         substep(ev, L, P, d, P.dt, prev_dt);
         prev_dt = P.dt;
@@ -86,12 +86,12 @@ BP_DEVNI void shipice_reset_env(const EnvView& ev, const LayoutTab& T, const Sim
         V2 o = body_origin(ev, L, r);
         out.pose[3 * env] = o.x; out.pose[3 * env + 1] = o.y; out.pose[3 * env + 2] = ev.body[r].pa;
         out.state[3 * env] = round2(o.x); out.state[3 * env + 1] = round2(o.y); out.state[3 * env + 2] = round2(ev.body[r].pa);
-        out.total_work[env] = 0.0; out.reward[env] = 0.0; out.terminated[env] = 0; out.truncated[env] = 0;
-        out.collision_reward[env] = 0.0; out.scaled_collision_reward[env] = 0.0; out.dist_reward[env] = 0.0;
+        out.total_work[env] = RC(0.0); out.reward[env] = RC(0.0); out.terminated[env] = 0; out.truncated[env] = 0;
+        out.collision_reward[env] = RC(0.0); out.scaled_collision_reward[env] = RC(0.0); out.dist_reward[env] = RC(0.0);
         out.trial_success[env] = 0; out.status[env] = sc->status;
-        sc->t = 0; sc->total_work = 0.0;
+        sc->t = 0; sc->total_work = RC(0.0);
         // maze: wall_collision and prev_dist_value are cleared after the settle steps (maze_NAMO_env.py:337-341)
-        sc->wall_hit = 0; sc->has_prev_dist = 0; sc->prev_dist = 0.0;
+        sc->wall_hit = 0; sc->has_prev_dist = 0; sc->prev_dist = RC(0.0);
     }
     bp_wsync();
 }
@@ -138,8 +138,8 @@ BP_DEVNI void shipice_reset_from_snapshot(const DevConst* C, char* base, int lay
         const double* p = C->snap_pose + 3 * layout_id;
         out.pose[3 * env] = p[0]; out.pose[3 * env + 1] = p[1]; out.pose[3 * env + 2] = p[2];
         out.state[3 * env] = round2(p[0]); out.state[3 * env + 1] = round2(p[1]); out.state[3 * env + 2] = round2(p[2]);
-        out.total_work[env] = 0.0; out.reward[env] = 0.0; out.terminated[env] = 0; out.truncated[env] = 0;
-        out.collision_reward[env] = 0.0; out.scaled_collision_reward[env] = 0.0; out.dist_reward[env] = 0.0;
+        out.total_work[env] = RC(0.0); out.reward[env] = RC(0.0); out.terminated[env] = 0; out.truncated[env] = 0;
+        out.collision_reward[env] = RC(0.0); out.scaled_collision_reward[env] = RC(0.0); out.dist_reward[env] = RC(0.0);
         out.trial_success[env] = 0; out.status[env] = C->snap_status[layout_id];
     }
     bp_wsync();
@@ -151,11 +151,11 @@ BP_DEVNI void shipice_step_begin(const EnvView& ev, const LayoutView& L, const S
     const int r = sc->robot;
     if (bp_lane() == 0) {
         sc->t++;
-        double a = ev.body[r].pa;
-        double s, c; bp_sincos(a, &s, &c);
-        double vw = action * P.yaw_step;
-        double vx = c * P.target_speed + (-s) * 0.0;
-        double vy = s * P.target_speed + c * 0.0;
+        real a = ev.body[r].pa;
+        real s, c; bp_sincos(a, &s, &c);
+        real vw = action * P.yaw_step;
+        real vx = c * P.target_speed + (-s) * RC(0.0);
+        real vy = s * P.target_speed + c * RC(0.0);
         // every shape of the kinematic robot is one body record with the same pose and velocity
         for (int q = r; q < sc->nbody; q++) { ev.body[q].vw = vw; ev.body[q].vx = vx; ev.body[q].vy = vy; }
     }
@@ -173,8 +173,8 @@ BP_DEVNI void shipice_step_begin(const EnvView& ev, const LayoutView& L, const S
 // boundary flag.  Executed by ONE lane for its env; returns bit0 = yaw violated, bit1 = boundary violated.
 BP_DEV int shipice_substep_checks(const EnvView& ev, const LayoutView& L, const SimParams& P, int r) {
     int f = 0;
-    double a = ev.body[r].pa;
-    if (a <= P.yaw_lo || a >= P.yaw_hi) { ev.body[r].vw = 0.0; f |= 1; }
+    real a = ev.body[r].pa;
+    if (a <= P.yaw_lo || a >= P.yaw_hi) { ev.body[r].vw = RC(0.0); f |= 1; }
     V2 o = body_origin(ev, L, r);
     if (o.x < 0 || o.x > P.map_w) f |= 2;
     return f;
@@ -183,17 +183,17 @@ BP_DEV int shipice_substep_checks(const EnvView& ev, const LayoutView& L, const 
 // total_work_done(prev_obs, updated) (evaluation/metrics.py:96-126):
 // work = sum_i area(a_i) * || |c(a_i)| - |c(b_i)| || over the movable polygons in creation order; only
 // bodies that moved this step can contribute.  Warp-cooperative; the sum is returned on lane 0.
-BP_DEVNI double step_work(const EnvView& ev, const LayoutView& L) {
+BP_DEVNI real step_work(const EnvView& ev, const LayoutView& L) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     int na = sc->n_awake;
     for (int k = lane; k < na; k += BP_NL) {
         int b = ev.awake[k];
-        double w = 0.0;
+        real w = RC(0.0);
         if (body_dynamic(L, b) && ev.moved_step[b]) {
-            double A, cx, cy;
+            real A, cx, cy;
             area_centroid_abs(ev.wv + (size_t)b * VMAX * 2, L.nv[b], &A, &cx, &cy);
-            double dx = ev.cenx[b] - cx, dy = ev.ceny[b] - cy;
+            real dx = ev.cenx[b] - cx, dy = ev.ceny[b] - cy;
             w = sqrt(dx * dx + dy * dy) * ev.area[b];
             ev.cenx[b] = cx; ev.ceny[b] = cy; ev.area[b] = A;
             ev.moved_step[b] = 0;
@@ -201,7 +201,7 @@ BP_DEVNI double step_work(const EnvView& ev, const LayoutView& L) {
         ev.tmp[b] = w;
     }
     bp_wsync();
-    double work = 0.0;
+    double work = RC(0.0);
     if (lane == 0) {
         // ascending body index, like zip(prev_obs, updated) in the reference
         const int r = sc->robot;
@@ -225,11 +225,11 @@ BP_DEVNI void shipice_step_finish(const EnvView& ev, const LayoutView& L, const 
         sc->total_work += work;
         double y = o.y;
         bool terminated = (y >= P.goal_y) || boundary_terminal;
-        double dist_reward = 0.0;
+        double dist_reward = RC(0.0);
         if (y < P.goal_y) {
-            double a = ev.body[r].pa;
-            double s, c; bp_sincos(a, &s, &c);
-            dist_reward = 1.0 * (c * 0.0 + s * 1.0);
+            real a = ev.body[r].pa;
+            real s, c; bp_sincos(a, &s, &c);
+            dist_reward = RC(1.0) * (c * RC(0.0) + s * RC(1.0));
         }
         double collision_reward = -work;
         double reward = P.beta * collision_reward + dist_reward;

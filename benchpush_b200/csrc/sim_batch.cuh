@@ -89,12 +89,12 @@ BP_DEVNI void pair_finish_lane(const DevConst* C, char* base, const LayoutView& 
     if (touching) {
         SlotRec& S = ev.slot[slot];
         bool was = !fresh && S.touch;
-        double jn_new[2] = {0, 0}, jt_new[2] = {0, 0};
+        real jn_new[2] = {0, 0}, jt_new[2] = {0, 0};
         int oc = fresh ? 0 : S.cnt;
         for (int x = 0; x < m.count; x++)
             for (int j = 0; j < oc; j++)
                 if (m.hash[x] == S.c[j].hash) { jn_new[x] = S.c[j].jn; jt_new[x] = S.c[j].jt; }
-        double ax = ev.body[a].px, ay = ev.body[a].py, bx = ev.body[b].px, by = ev.body[b].py;
+        real ax = ev.body[a].px, ay = ev.body[a].py, bx = ev.body[b].px, by = ev.body[b].py;
         for (int x = 0; x < m.count; x++) {
             ContactRec& c = S.c[x];
             c.r1x = m.p1[x].x - ax; c.r1y = m.p1[x].y - ay;
@@ -111,8 +111,8 @@ BP_DEVNI void pair_finish_lane(const DevConst* C, char* base, const LayoutView& 
         }
         S.stamp = sc->stamp;
         pr[p].flags |= 1;
-        pr[p].skip = -1.0;
-        ev.ap_gate[i] = -1.0;
+        pr[p].skip = -RC(1.0);
+        ev.ap_gate[i] = -RC(1.0);
         if ((!ev.is_awake[a] && body_dynamic(L, a)) || (!ev.is_awake[b] && body_dynamic(L, b))) sc->any_wake = 1;
     } else {
         pair_apart_b(C, base, i, p, a, b, pts.d - L.rad[a] - L.rad[b]);
@@ -265,7 +265,7 @@ BP_DEVNI void batch_collide(const DevConst* C, BatchShared& S) {
                     int e = find_env(S.off_ap, i), k = i - S.off_ap[e];
                     EnvView ev = view_s(S.base[e]);
                     double gt = ev.ap_gate[k];
-                    pass = ev.sc->G >= gt && !(S.skip_res && gt == -2.0);
+                    pass = ev.sc->G >= gt && !(S.skip_res && gt == -RC(2.0));
                     ent = ((unsigned)e << 24) | (unsigned)k;
                 }
                 int t; int rk = bp_wrank(pass, &t);
@@ -291,21 +291,21 @@ BP_DEVNI void batch_collide(const DevConst* C, BatchShared& S) {
                     int a = (int)(pq.key >> 16), b = (int)(pq.key & 0xFFFF);
                     bool mv = ev.moved[a] || ev.moved[b];
                     double dsum = ev.body[a].D + ev.body[b].D;
-                    bool need = !(pq.flags & 1) || (mv && (pq.skip < 0.0 || dsum >= pq.skip));
+                    bool need = !(pq.flags & 1) || (mv && (pq.skip < RC(0.0) || dsum >= pq.skip));
                     if (!need) {
-                        if (pq.skip >= 0.0) ev.ap_gate[i] = sc->G + (pq.skip - dsum);
+                        if (pq.skip >= RC(0.0)) ev.ap_gate[i] = sc->G + (pq.skip - dsum);
                     } else {
                         BBox A = ev.bb[a], B = ev.bb[b];
                         bool bbhit = (A.l <= B.r && B.l <= A.r && A.b <= B.t && B.b <= A.t);
-                        if (bbhit && !(L.minv[a] == 0.0 && L.minv[b] == 0.0)) {
+                        if (bbhit && !(L.minv[a] == RC(0.0) && L.minv[b] == RC(0.0))) {
                             take = true;
                             // the narrowphase below scans both polygons several times: start the loads now
                             bp_prefetch(ev.wv + (size_t)a * VMAX * 2, 3);
                             bp_prefetch(ev.wv + (size_t)b * VMAX * 2, 3);
                             if (pq.live >= 0) bp_prefetch(&ev.slot[pq.live], 2);
                         } else {
-                            double gap = fmax(fmax(A.l - B.r, B.l - A.r), fmax(A.b - B.t, B.b - A.t));
-                            pair_apart_b(C, base, i, p, a, b, bbhit ? 0.0 : gap);
+                            real gap = fmax(fmax(A.l - B.r, B.l - A.r), fmax(A.b - B.t, B.b - A.t));
+                            pair_apart_b(C, base, i, p, a, b, bbhit ? RC(0.0) : gap);
                         }
                     }
                 }
@@ -349,7 +349,7 @@ BP_DEVNI void batch_collide(const DevConst* C, BatchShared& S) {
 }
 
 // One physics substep (cpSpaceStep) for every env of the batch.
-BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double prev_dt) {
+BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, real dt, real prev_dt) {
     const int lane = bp_lane();
     const SimParams& P = C->P;
     const Dims& d = C->d;
@@ -374,27 +374,27 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
             int b = ev.awake[k];
             BodyRec& R = ev.body[b];
             bp_prefetch(L.lv + (size_t)b * VMAX * 2, 2);
-            double vx = R.vx, vy = R.vy, vw = R.vw, bx = R.bx, by = R.by, bw = R.bw;
-            bool mv = (vx != 0.0 || vy != 0.0 || vw != 0.0 || bx != 0.0 || by != 0.0 || bw != 0.0);
+            real vx = R.vx, vy = R.vy, vw = R.vw, bx = R.bx, by = R.by, bw = R.bw;
+            bool mv = (vx != RC(0.0) || vy != RC(0.0) || vw != RC(0.0) || bx != RC(0.0) || by != RC(0.0) || bw != RC(0.0));
             if (mv) {
-                double dx = (vx + bx) * dt, dy = (vy + by) * dt, da = (vw + bw) * dt;
+                real dx = (vx + bx) * dt, dy = (vy + by) * dt, da = (vw + bw) * dt;
                 R.px = R.px + dx; R.py = R.py + dy; R.pa = R.pa + da;
-                double dD = (fabs(dx) + fabs(dy) + L.rbound[b] * fabs(da)) * 1.000001;
+                real dD = (fabs(dx) + fabs(dy) + L.rbound[b] * fabs(da)) * RC(1.000001);
                 R.D += dD;
                 bp_atomic_max_u64(&S.dmax_bits[e], bp_d2bits(dD));
                 refresh_body_b(C, base, L, b);
-                double mg = body_margin(P, sc, b);
+                real mg = body_margin(P, sc, b);
                 BBox c = ev.bb[b], o = ev.b0[b];
                 if (c.l < o.l - mg || c.r > o.r + mg || c.b < o.b - mg || c.t > o.t + mg) sc->rebuild = 1;
                 ev.moved_step[b] = 1; ev.mvrb[b] = 1;
-                R.bx = 0.0; R.by = 0.0; R.bw = 0.0;
+                R.bx = RC(0.0); R.by = RC(0.0); R.bw = RC(0.0);
             }
             ev.moved[b] = mv ? 1 : 0;
         }
     }
     bp_wsync();
     for (int e = lane; e < BK; e += BP_NL)
-        if (S.base[e]) { EnvScal* sc = (EnvScal*)S.base[e]; sc->G += 2.0 * bp_bits2d(S.dmax_bits[e]) * 1.000001; }
+        if (S.base[e]) { EnvScal* sc = (EnvScal*)S.base[e]; sc->G += RC(2.0) * bp_bits2d(S.dmax_bits[e]) * RC(1.000001); }
     bp_wsync();
     // ---- rare: neighbour-list rebuild, one env at a time
     for (int e = 0; e < BK; e++) {
@@ -420,7 +420,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
     }
     bp_wsync();
     if (!S.wl_valid) batch_build_worklist(C, S);
-    const double dt_coef = (prev_dt == 0.0) ? 0.0 : dt / prev_dt;
+    const real dt_coef = (prev_dt == RC(0.0)) ? RC(0.0) : dt / prev_dt;
     if (S.n_items < 0) {
         // the merged list does not fit: solve env by env (same arithmetic, same order)
         for (int e = 0; e < BK; e++)
@@ -449,7 +449,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, double dt, double
             int b = ev.awake[k];
             if (body_dynamic(S.L[e], b)) {
                 BodyRec& R = ev.body[b];
-                R.vx = R.vx * P.damp + 0.0; R.vy = R.vy * P.damp + 0.0; R.vw = R.vw * P.damp + 0.0;
+                R.vx = R.vx * P.damp + RC(0.0); R.vy = R.vy * P.damp + RC(0.0); R.vw = R.vw * P.damp + RC(0.0);
             }
         }
     }
@@ -513,7 +513,7 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
             } else {
                 LayoutView L = layout_view(C->T, d, sc->layout);
                 if (lane == 0) S.L[e] = L;
-                shipice_step_begin(ev, L, P, d, (double)actions[env]);
+                shipice_step_begin(ev, L, P, d, (real)actions[env]);
             }
         }
         if (lane == 0) { S.base[e] = base; S.env_id[e] = env; S.flags[e] = 0; }

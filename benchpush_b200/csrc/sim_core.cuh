@@ -40,26 +40,26 @@ struct SimParams {
     int persistence;              // collision_persistence = 3
     int substeps;                 // cfg.sim.steps = 400
     int settle_steps;             // 1000 (ship_ice_env.py:218)
-    double dt;                    // cfg.dt / cfg.sim.steps
-    double damp;                  // pow(cfg.sim.damping, dt)
-    double bias_coef;             // 1 - pow(collision_bias, dt)
-    double slop;                  // collision_slop = 0.1
-    double target_speed;          // cfg.target_speed
-    double yaw_step;              // max_yaw_rate_step = (pi/2)/7
-    double yaw_lo, yaw_hi;        // (0, pi)
-    double map_w, map_h;          // cfg.occ.map_width / map_height
-    double goal_y;                // cfg.goal_y
-    double beta;                  // 30
-    double boundary_limit;        // 0.0
-    double boundary_penalty, terminal_reward, yaw_penalty;   // -50, 200, 0
-    double margin_body, margin_robot;                        // neighbour-list margins (m)
+    real dt;                    // cfg.dt / cfg.sim.steps
+    real damp;                  // pow(cfg.sim.damping, dt)
+    real bias_coef;             // 1 - pow(collision_bias, dt)
+    real slop;                  // collision_slop = 0.1
+    real target_speed;          // cfg.target_speed
+    real yaw_step;              // max_yaw_rate_step = (pi/2)/7
+    real yaw_lo, yaw_hi;        // (0, pi)
+    real map_w, map_h;          // cfg.occ.map_width / map_height
+    real goal_y;                // cfg.goal_y
+    real beta;                  // 30
+    real boundary_limit;        // 0.0
+    real boundary_penalty, terminal_reward, yaw_penalty;   // -50, 200, 0
+    real margin_body, margin_robot;                        // neighbour-list margins (m)
     // ---- env kind and the maze-NAMO constants (maze_NAMO_env.py:80-82, 406-410, 528-536)
     int kind;                     // 0 = ship-ice-v0, 1 = maze-NAMO-v0
     int n_walls;                  // static wall segments: bodies [0, n_walls) of a maze layout
-    double goal_x, goal_gy;       // cfg.env.goal_x / goal_y
-    double goal_reach;            // cfg.goal_radius + cfg.robot.min_r
-    double k_increment;           // 150
-    double pix_scale;             // cfg.occ.m_to_pix_scale (16)
+    real goal_x, goal_gy;       // cfg.env.goal_x / goal_y
+    real goal_reach;            // cfg.goal_radius + cfg.robot.min_r
+    real k_increment;           // 150
+    real pix_scale;             // cfg.occ.m_to_pix_scale (16)
     const double* dist_map;       // [dist_h][dist_w] normalised goal-point distance map (occupancy_map.py:435-485)
     int dist_h, dist_w;
 };
@@ -75,17 +75,17 @@ struct Dims {
 
 // Immutable per-layout geometry (shared by every env that currently runs that layout).
 struct LayoutTab {
-    const double* lv;             // [L][NB][VMAX][2] hull vertices, body-local, CCW
-    const double* ln;             // [L][NB][VMAX][2] edge normals (edge ending at vertex i)
+    const real* lv;             // [L][NB][VMAX][2] hull vertices, body-local, CCW
+    const real* ln;             // [L][NB][VMAX][2] edge normals (edge ending at vertex i)
     const int* nv;                // [L][NB]
-    const double* rad;            // [L][NB] shape radius
-    const double* rbound;         // [L][NB] max |vertex - cog|: bounds the motion caused by rotation
-    const double* minv;           // [L][NB]
-    const double* iinv;           // [L][NB]
-    const double* cog;            // [L][NB][2]
-    const double* mat_e;          // [L][NB]
-    const double* mat_u;          // [L][NB]
-    const double* init;           // [L][NB][3] body position x, y, angle
+    const real* rad;            // [L][NB] shape radius
+    const real* rbound;         // [L][NB] max |vertex - cog|: bounds the motion caused by rotation
+    const real* minv;           // [L][NB]
+    const real* iinv;           // [L][NB]
+    const real* cog;            // [L][NB][2]
+    const real* mat_e;          // [L][NB]
+    const real* mat_u;          // [L][NB]
+    const real* init;           // [L][NB][3] body position x, y, angle
     const int* nbody;             // [L] bodies incl. robot
     const int* robot0;            // [L] first body of the kinematic robot: its shapes are bodies [robot0, nbody), all
                                   //     carrying the same pose and velocity (a compound pymunk body, one record per shape)
@@ -109,25 +109,25 @@ struct EnvScal {
 // env).  Records are arrays-of-structs sized to cache lines: a lane that works on one body / one
 // arbiter touches 1-2 lines instead of one line per field.
 struct alignas(16) BodyRec {      // 128 B = one L1/L2 line: everything the solver needs of a body
-    double px, py, pa;              // cog position (world), angle
-    double vx, vy, vw;              // velocity
-    double bx, by, bw;              // bias (pseudo) velocity
-    double minv, iinv;              // inverse mass / moment (0 for the kinematic robot)
-    double rc, rs;                  // cos / sin of pa
+    real px, py, pa;              // cog position (world), angle
+    real vx, vy, vw;              // velocity
+    real bx, by, bw;              // bias (pseudo) velocity
+    real minv, iinv;              // inverse mass / moment (0 for the kinematic robot)
+    real rc, rs;                  // cos / sin of pa
     double D;                       // monotone bound on the path length travelled by any point of the body
-    double pad0, pad1;
+    real pad0, pad1;
 };
-struct BBox { double l, b, r, t; }; // AABB incl. shape radius
+struct BBox { real l, b, r, t; }; // AABB incl. shape radius
 struct ContactRec {                 // 96 B
-    double r1x, r1y, r2x, r2y, jn, jt, jb, nm, tm, bias, bounce;
+    real r1x, r1y, r2x, r2y, jn, jt, jb, nm, tm, bias, bounce;
     unsigned hash, pad;
 };
 struct alignas(16) SlotRec {      // 256 B = two lines: one (recently) touching shape pair = cpArbiter
     int a, b, pair, cnt, stamp;
     unsigned char touch, first, keep, pad;
-    double nx, ny, e, u;
+    real nx, ny, e, u;
     ContactRec c[2];
-    double pad2;
+    real pad2;
 };
 struct PairRec {                    // 24 B: neighbour-list entry
     unsigned key, gjk;              // (i << 16) | j ; GJK warm-start id
@@ -141,8 +141,8 @@ struct EnvView {
     BodyRec* body;                                                           // [NB]
     BBox* bb;                                                                // [NB] current AABB
     BBox* b0;                                                                // [NB] AABB at neighbour-list build
-    double* wv;                                                              // [NB][VMAX][2] world vertices
-    double *cenx, *ceny, *area, *tmp;                                        // [NB] |centroid|, area at last env step; scratch
+    real* wv;                                                              // [NB][VMAX][2] world vertices
+    real *cenx, *ceny, *area, *tmp;                                        // [NB] |centroid|, area at last env step; scratch
     int* awake;                                                              // [NB]
     unsigned char *is_awake, *moved, *moved_step, *act;                      // [NB]
     unsigned char* mvrb;                                                     // [NB] AABB changed since the last neighbour-list build
@@ -176,8 +176,8 @@ BP_HD EnvView carve_env(char* base, const Dims& d, size_t* total) {
     TAKE(v.body, BodyRec, NB * sizeof(BodyRec))
     TAKE(v.slot, SlotRec, Lm * sizeof(SlotRec))
     TAKE(v.bb, BBox, NB * sizeof(BBox)) TAKE(v.b0, BBox, NB * sizeof(BBox))
-    TAKE(v.wv, double, NB * VMAX * 2 * 8)
-    TAKE(v.cenx, double, NB * 8) TAKE(v.ceny, double, NB * 8) TAKE(v.area, double, NB * 8) TAKE(v.tmp, double, NB * 8)
+    TAKE(v.wv, real, NB * VMAX * 2 * sizeof(real))
+    TAKE(v.cenx, real, NB * sizeof(real)) TAKE(v.ceny, real, NB * sizeof(real)) TAKE(v.area, real, NB * sizeof(real)) TAKE(v.tmp, real, NB * sizeof(real))
     TAKE(v.awake, int, NB * 4)
     TAKE(v.is_awake, unsigned char, NB) TAKE(v.moved, unsigned char, NB)
     TAKE(v.moved_step, unsigned char, NB) TAKE(v.act, unsigned char, NB)
@@ -201,8 +201,8 @@ static inline size_t env_mem_size(const Dims& d) { size_t t = 0; carve_env((char
 // on the host (env_offsets) so that device code can form `base + constant` for just the arrays it
 // touches (view_at is inlined and dead fields disappear), instead of re-deriving the whole carve.
 #define BP_ENV_FIELD_LIST(X)                                                                         \
-    X(0, sc, EnvScal) X(1, body, BodyRec) X(2, slot, SlotRec) X(3, bb, BBox) X(4, b0, BBox) X(5, wv, double)      \
-    X(6, cenx, double) X(7, ceny, double) X(8, area, double) X(9, tmp, double) X(10, awake, int)                 \
+    X(0, sc, EnvScal) X(1, body, BodyRec) X(2, slot, SlotRec) X(3, bb, BBox) X(4, b0, BBox) X(5, wv, real)      \
+    X(6, cenx, real) X(7, ceny, real) X(8, area, real) X(9, tmp, real) X(10, awake, int)                 \
     X(11, is_awake, unsigned char) X(12, moved, unsigned char) X(13, moved_step, unsigned char)                  \
     X(14, act, unsigned char) X(15, colmask, unsigned long long) X(16, pair[0], PairRec) X(17, pair[1], PairRec) \
     X(18, adj_start, int) X(19, adj, int) X(20, deg, int) X(21, queue, int) X(22, queue0, int) X(23, apairs, int) \
@@ -241,7 +241,7 @@ static inline void load_shared_offsets(const EnvOff& O) { bp_soff = O; }
 BP_DEV EnvView view_s(char* base) { return view_at(base, bp_soff); }
 
 struct LayoutView {
-    const double *lv, *ln, *rad, *rbound, *minv, *iinv, *cog, *mat_e, *mat_u, *init;
+    const real *lv, *ln, *rad, *rbound, *minv, *iinv, *cog, *mat_e, *mat_u, *init;
     const int* nv;
     int nbody, robot0;
 };
@@ -268,47 +268,47 @@ BP_DEV LayoutView layout_view(const LayoutTab& T, const Dims& d, int l) {
 }
 
 // ------------------------------------------------------------------ small vector helpers
-struct V2 { double x, y; };
-struct alignas(16) D2 { double x, y; };      // one vertex in memory: moved with a single 128-bit load / store
-BP_DEV V2 mk(double x, double y) { V2 r; r.x = x; r.y = y; return r; }
+struct V2 { real x, y; };
+struct alignas(2 * sizeof(real)) D2 { real x, y; };      // one vertex in memory: moved with a single 128-bit load / store
+BP_DEV V2 mk(real x, real y) { V2 r; r.x = x; r.y = y; return r; }
 BP_DEV V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
 BP_DEV V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
-BP_DEV V2 operator*(V2 a, double s) { return mk(a.x * s, a.y * s); }
+BP_DEV V2 operator*(V2 a, real s) { return mk(a.x * s, a.y * s); }
 BP_DEV V2 neg(V2 a) { return mk(-a.x, -a.y); }
-BP_DEV double dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
-BP_DEV double cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+BP_DEV real dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+BP_DEV real cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
 BP_DEV V2 perp(V2 a) { return mk(-a.y, a.x); }
 BP_DEV V2 rperp(V2 a) { return mk(a.y, -a.x); }
-BP_DEV double clampd(double f, double lo, double hi) { return fmin(fmax(f, lo), hi); }
-BP_DEV double clamp01(double f) { return fmax(0.0, fmin(f, 1.0)); }
-BP_DEV V2 lerp(V2 a, V2 b, double t) { return a * (1.0 - t) + b * t; }
+BP_DEV real clampd(real f, real lo, real hi) { return fmin(fmax(f, lo), hi); }
+BP_DEV real clamp01(real f) { return fmax(RC(0.0), fmin(f, RC(1.0))); }
+BP_DEV V2 lerp(V2 a, V2 b, real t) { return a * (RC(1.0) - t) + b * t; }
 BP_DEV V2 rotv(V2 a, V2 b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 // ------------------------------------------------------------------ geometry refresh of one body
 BP_DEV void refresh_body_impl(const EnvView& ev, const LayoutView& L, int b) {
-    double s, c;
+    real s, c;
     bp_sincos(ev.body[b].pa, &s, &c);
     ev.body[b].rc = c; ev.body[b].rs = s;
-    double cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
-    double tx = ev.body[b].px - (cx * c - cy * s);
-    double ty = ev.body[b].py - (cx * s + cy * c);
-    double ms = -s;
-    const double* lv = L.lv + (size_t)b * VMAX * 2;
-    double* wv = ev.wv + (size_t)b * VMAX * 2;
+    real cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
+    real tx = ev.body[b].px - (cx * c - cy * s);
+    real ty = ev.body[b].py - (cx * s + cy * c);
+    real ms = -s;
+    const real* lv = L.lv + (size_t)b * VMAX * 2;
+    real* wv = ev.wv + (size_t)b * VMAX * 2;
     int n = L.nv[b];
-    double l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
+    real l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
     const D2* lv2 = (const D2*)lv;
     D2* wv2 = (D2*)wv;
 #pragma unroll 2
     for (int i = 0; i < n; i++) {
         D2 q = lv2[i];
-        double wx = c * q.x + ms * q.y + tx;
-        double wy = s * q.x + c * q.y + ty;
+        real wx = c * q.x + ms * q.y + tx;
+        real wy = s * q.x + c * q.y + ty;
         D2 w; w.x = wx; w.y = wy;
         wv2[i] = w;
         l = fmin(l, wx); r = fmax(r, wx); bt = fmin(bt, wy); tp = fmax(tp, wy);
     }
-    double rad = L.rad[b];
+    real rad = L.rad[b];
     BBox bx; bx.l = l - rad; bx.b = bt - rad; bx.r = r + rad; bx.t = tp + rad;
     ev.bb[b] = bx;
 }
@@ -317,14 +317,14 @@ BP_DEVNI void refresh_body(const EnvView& ev, const LayoutView& L, int b) { refr
 BP_DEVNI void refresh_body_b(const DevConst* C, char* base, const LayoutView& L, int b) { refresh_body_impl(view_s(base), L, b); }
 // body position (pymunk Body.position = local origin in world space)
 BP_DEV V2 body_origin(const EnvView& ev, const LayoutView& L, int b) {
-    double c = ev.body[b].rc, s = ev.body[b].rs;
-    double cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
+    real c = ev.body[b].rc, s = ev.body[b].rs;
+    real cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
     return mk(ev.body[b].px - (cx * c - cy * s), ev.body[b].py - (cx * s + cy * c));
 }
 
 // ------------------------------------------------------------------ narrowphase: GJK / EPA on world vertices
 struct MPoint { V2 ab; unsigned id; };       // Minkowski difference vertex; id = (index_a << 8) | index_b
-struct Poly { const double* v; int n; };
+struct Poly { const real* v; int n; };
 
 // The one copy of the support scan (GJK, EPA and the manifold builder all call it): the hot path is
 // instruction-fetch bound (profiles/), so shared out-of-line leaves beat inlined copies.
@@ -332,11 +332,11 @@ BP_DEVNI int support_index(const Poly& P, V2 n) {
     // a 2-vertex shape is a cpSegmentShape (walls): SegmentSupportPoint returns ta only when strictly greater
     if (P.n == 2) return (P.v[0] * n.x + P.v[1] * n.y > P.v[2] * n.x + P.v[3] * n.y) ? 0 : 1;
     const D2* v = (const D2*)P.v;
-    double mx = -INFINITY; int idx = 0;
+    real mx = -INFINITY; int idx = 0;
 #pragma unroll 4
     for (int i = 0; i < P.n; i++) {
         D2 q = v[i];
-        double d = q.x * n.x + q.y * n.y;
+        real d = q.x * n.x + q.y * n.y;
         if (d > mx) { mx = d; idx = i; }
     }
     return idx;
@@ -348,29 +348,29 @@ BP_DEV MPoint mpoint(const Poly& A, const Poly& B, int ia, int ib) {
 BP_DEV MPoint msupport(const Poly& A, const Poly& B, V2 n) {
     return mpoint(A, B, support_index(A, neg(n)), support_index(B, n));
 }
-BP_DEV double closest_t(V2 a, V2 b) {
+BP_DEV real closest_t(V2 a, V2 b) {
     V2 delta = b - a;
-    return -clampd(dot(delta, a + b) / (dot(delta, delta) + DBL_MIN), -1.0, 1.0);
+    return -clampd(dot(delta, a + b) / (dot(delta, delta) + BP_RMIN), -RC(1.0), RC(1.0));
 }
-BP_DEV V2 lerp_t(V2 a, V2 b, double t) {
-    double ht = 0.5 * t;
-    return a * (0.5 - ht) + b * (0.5 + ht);
+BP_DEV V2 lerp_t(V2 a, V2 b, real t) {
+    real ht = RC(0.5) * t;
+    return a * (RC(0.5) - ht) + b * (RC(0.5) + ht);
 }
-BP_DEV double closest_dist(V2 a, V2 b) { V2 p = lerp_t(a, b, closest_t(a, b)); return dot(p, p); }
+BP_DEV real closest_dist(V2 a, V2 b) { V2 p = lerp_t(a, b, closest_t(a, b)); return dot(p, p); }
 BP_DEV bool point_greater(V2 a, V2 b, V2 c) {
     return (b.y - a.y) * (a.x + b.x - 2 * c.x) > (b.x - a.x) * (a.y + b.y - 2 * c.y);
 }
-struct Closest { V2 n; double d; unsigned id; };
+struct Closest { V2 n; real d; unsigned id; };
 BP_DEVNI Closest closest_points(const MPoint& v0, const MPoint& v1) {
-    double t = closest_t(v0.ab, v1.ab);
+    real t = closest_t(v0.ab, v1.ab);
     V2 p = lerp_t(v0.ab, v1.ab, t);
     V2 delta = v1.ab - v0.ab;
     V2 rp = rperp(delta);
-    V2 n = rp * (1.0 / (sqrt(dot(rp, rp)) + DBL_MIN));
-    double d = dot(n, p);
+    V2 n = rp * (RC(1.0) / (sqrt(dot(rp, rp)) + BP_RMIN));
+    real d = dot(n, p);
     Closest c; c.id = (v0.id & 0xFFFF) << 16 | (v1.id & 0xFFFF);
-    if (d <= 0.0 || (-1.0 < t && t < 1.0)) { c.n = n; c.d = d; }
-    else { double d2 = sqrt(dot(p, p)); c.n = p * (1.0 / (d2 + DBL_MIN)); c.d = d2; }
+    if (d <= RC(0.0) || (-RC(1.0) < t && t < RC(1.0))) { c.n = n; c.d = d; }
+    else { real d2 = sqrt(dot(p, p)); c.n = p * (RC(1.0) / (d2 + BP_RMIN)); c.d = d2; }
     return c;
 }
 
@@ -382,10 +382,10 @@ BP_DEVNI Closest epa(const Poly& A, const Poly& B, MPoint h0, MPoint h1, MPoint 
     hull[0] = h0; hull[1] = h1; hull[2] = h2;
     int count = 3, iteration = 1;
     for (;;) {
-        int mini = 0; double minDist = INFINITY;
+        int mini = 0; real minDist = INFINITY;
 #pragma unroll 1
         for (int j = 0, i = count - 1; j < count; i = j, j++) {
-            double d = closest_dist(hull[i].ab, hull[j].ab);
+            real d = closest_dist(hull[i].ab, hull[j].ab);
             if (d < minDist) { minDist = d; mini = i; }
         }
         MPoint v0 = hull[mini], v1 = hull[(mini + 1) % count];
@@ -429,8 +429,8 @@ BP_DEVNI bool gjk_only(const Poly& A, const Poly& B, V2 cenA, V2 cenB, unsigned 
         (*iters)++;
         if (iteration > GJK_MAX_IT) { *capped = 1; *out = closest_points(v0, v1); return false; }
         if (point_greater(v1.ab, v0.ab, mk(0, 0))) { MPoint t = v0; v0 = v1; v1 = t; }
-        double t = closest_t(v0.ab, v1.ab);
-        V2 n = (-1.0 < t && t < 1.0) ? perp(v1.ab - v0.ab) : neg(lerp_t(v0.ab, v1.ab, t));
+        real t = closest_t(v0.ab, v1.ab);
+        V2 n = (-RC(1.0) < t && t < RC(1.0)) ? perp(v1.ab - v0.ab) : neg(lerp_t(v0.ab, v1.ab, t));
         MPoint p = msupport(A, B, n);
         if (point_greater(p.ab, v0.ab, mk(0, 0)) && point_greater(v1.ab, p.ab, mk(0, 0))) {
             *hint = (v0.id & 0xFFFF) << 16 | (v1.id & 0xFFFF);
@@ -445,21 +445,21 @@ BP_DEVNI bool gjk_only(const Poly& A, const Poly& B, V2 cenA, V2 cenB, unsigned 
 BP_DEVNI Closest gjk_epa(const Poly& A, const Poly& B, unsigned hint, int* capped) {
     MPoint v0 = mpoint(A, B, (hint >> 24) & 0xFF, (hint >> 16) & 0xFF);
     MPoint v1 = mpoint(A, B, (hint >> 8) & 0xFF, hint & 0xFF);
-    double t = closest_t(v0.ab, v1.ab);
-    V2 n = (-1.0 < t && t < 1.0) ? perp(v1.ab - v0.ab) : neg(lerp_t(v0.ab, v1.ab, t));
+    real t = closest_t(v0.ab, v1.ab);
+    V2 n = (-RC(1.0) < t && t < RC(1.0)) ? perp(v1.ab - v0.ab) : neg(lerp_t(v0.ab, v1.ab, t));
     MPoint p = msupport(A, B, n);
     return epa(A, B, v0, p, v1, capped);
 }
 
 struct EdgeW { V2 a, b; int ia, ib; };
-BP_DEV EdgeW support_edge(const Poly& P, const double* ln, double rc, double rs, V2 n) {
+BP_DEV EdgeW support_edge(const Poly& P, const real* ln, real rc, real rs, V2 n) {
     int count = P.n;
-    double ms = -rs;
+    real ms = -rs;
     if (count == 2) {
         // SupportEdgeForSegment (cpCollision.c): ln[0] is the segment normal rperp(normalize(b - a))
         V2 tn = mk(rc * ln[0] + ms * ln[1], rs * ln[0] + rc * ln[1]);
         EdgeW e;
-        if (dot(tn, n) > 0.0) { e.a = pvert(P, 0); e.b = pvert(P, 1); e.ia = 0; e.ib = 1; }
+        if (dot(tn, n) > RC(0.0)) { e.a = pvert(P, 0); e.b = pvert(P, 1); e.ia = 0; e.ib = 1; }
         else { e.a = pvert(P, 1); e.b = pvert(P, 0); e.ia = 1; e.ib = 0; }
         return e;
     }
@@ -476,28 +476,28 @@ BP_DEV EdgeW support_edge(const Poly& P, const double* ln, double rc, double rs,
 struct Manifold { int count; V2 n; V2 p1[2], p2[2]; unsigned hash[2]; };
 
 BP_DEV Poly body_poly(const EnvView& ev, const LayoutView& L, int b) { Poly P; P.v = ev.wv + (size_t)b * VMAX * 2; P.n = L.nv[b]; return P; }
-BP_DEV V2 bb_centre(const BBox& r) { return mk((r.l + r.r) * 0.5, (r.b + r.t) * 0.5); }
+BP_DEV V2 bb_centre(const BBox& r) { return mk((r.l + r.r) * RC(0.5), (r.b + r.t) * RC(0.5)); }
 
 // Contact manifold (<= 2 points, world space) from the closest-feature result.  The polygons, radii, local edge normals and
 // rotations come in as plain values / pointers, so the same arithmetic serves the env block in global memory and the
 // shared-memory resident copy of the awake bodies (sim_res.cuh).
-BP_DEV void make_manifold_core(const Poly& A, const Poly& B, double ra, double rb, const double* lnA, const double* lnB,
-                               double rcA, double rsA, double rcB, double rsB, const Closest& pts, Manifold* m) {
+BP_DEV void make_manifold_core(const Poly& A, const Poly& B, real ra, real rb, const real* lnA, const real* lnB,
+                               real rcA, real rsA, real rcB, real rsB, const Closest& pts, Manifold* m) {
     m->count = 0;
-    if (pts.d - ra - rb <= 0.0) {
+    if (pts.d - ra - rb <= RC(0.0)) {
         EdgeW e1 = support_edge(A, lnA, rcA, rsA, pts.n);
         EdgeW e2 = support_edge(B, lnB, rcB, rsB, neg(pts.n));
-        double mindist = ra + rb;
+        real mindist = ra + rb;
         if (pts.d <= mindist) {
             V2 n = pts.n; m->n = n;
-            double d_e1_a = cross(e1.a, n), d_e1_b = cross(e1.b, n);
-            double d_e2_a = cross(e2.a, n), d_e2_b = cross(e2.b, n);
-            double e1_denom = 1.0 / (d_e1_b - d_e1_a + DBL_MIN);
-            double e2_denom = 1.0 / (d_e2_b - d_e2_a + DBL_MIN);
+            real d_e1_a = cross(e1.a, n), d_e1_b = cross(e1.b, n);
+            real d_e2_a = cross(e2.a, n), d_e2_b = cross(e2.b, n);
+            real e1_denom = RC(1.0) / (d_e1_b - d_e1_a + BP_RMIN);
+            real e2_denom = RC(1.0) / (d_e2_b - d_e2_a + BP_RMIN);
             {
                 V2 p1 = n * ra + lerp(e1.a, e1.b, clamp01((d_e2_b - d_e1_a) * e1_denom));
                 V2 p2 = n * (-rb) + lerp(e2.a, e2.b, clamp01((d_e1_a - d_e2_a) * e2_denom));
-                if (dot(p2 - p1, n) <= 0.0) {
+                if (dot(p2 - p1, n) <= RC(0.0)) {
                     int k = m->count++;
                     m->p1[k] = p1; m->p2[k] = p2; m->hash[k] = (unsigned)(e1.ia << 8 | e2.ib);
                 }
@@ -505,7 +505,7 @@ BP_DEV void make_manifold_core(const Poly& A, const Poly& B, double ra, double r
             {
                 V2 p1 = n * ra + lerp(e1.a, e1.b, clamp01((d_e2_a - d_e1_a) * e1_denom));
                 V2 p2 = n * (-rb) + lerp(e2.a, e2.b, clamp01((d_e1_b - d_e2_a) * e2_denom));
-                if (dot(p2 - p1, n) <= 0.0) {
+                if (dot(p2 - p1, n) <= RC(0.0)) {
                     int k = m->count++;
                     m->p1[k] = p1; m->p2[k] = p2; m->hash[k] = (unsigned)(e1.ib << 8 | e2.ia);
                 }

@@ -51,23 +51,23 @@ constexpr int R_PA = BP_RES_PA, R_PV = BP_RES_PV, R_PS = BP_RES_PS;
 static_assert(R_PS <= BWL, "merged colour list too short");
 enum ResState { RS_NONE = 0, RS_WAIT = 1, RS_RES = 2, RS_PARK = 3, RS_DONE = 4 };
 
-struct alignas(16) RBody { double px, py, pa, vx, vy, vw, bx, by, bw, minv, iinv, rc, rs, D; };   // = the first 112 B of a BodyRec
-static_assert(sizeof(RBody) == 112, "RBody must mirror the head of BodyRec");
+struct alignas(16) RBody { real px, py, pa, vx, vy, vw, bx, by, bw, minv, iinv, rc, rs; double D; };   // = the head of a BodyRec (112 B in fp64, 64 B in fp32)
+static_assert(sizeof(RBody) % 16 == 0 && sizeof(RBody) <= sizeof(BodyRec) && offsetof(RBody, D) == offsetof(BodyRec, D), "RBody must mirror the head of BodyRec");
 struct alignas(16) RBodyX {
-    double liml, limr, limb, limt;      // the body leaves its neighbour-list margin when its AABB crosses these
+    real liml, limr, limb, limt;        // the body leaves its neighbour-list margin when its AABB crosses these
     BBox bb;                            // current AABB incl. radius
-    double rbound, rad, cogx, cogy;
+    real rbound, rad, cogx, cogy;
     unsigned short gid, voff;           // body id in the env block; first vertex in rv
     unsigned char nv, env, moved, pad0;
-    double pad1;
+    real pad1;
 };
-static_assert(sizeof(RBodyX) == 112, "RBodyX layout");
+static_assert(sizeof(RBodyX) % 16 == 0 && offsetof(RBodyX, bb) % 16 == 0, "RBodyX layout (bulk copies land on 16-byte boundaries)");
 struct alignas(16) RSlot {
     SlotRec s;                          // bulk copy of the env block's arbiter (a, b stay body ids)
     unsigned short ka, kb, ai, env;     // pool indices of the two bodies, index into the env's awake-pair list, env of the batch
     unsigned gjk; int sid;              // GJK warm-start id of the pair; arbiter slot in the env block
 };
-static_assert(sizeof(RSlot) == 272, "RSlot layout");
+static_assert(sizeof(RSlot) % 16 == 0 && sizeof(SlotRec) % 16 == 0, "RSlot layout");
 
 struct ResShared {
     BatchShared B;                      // env blocks, layouts, narrowphase queues, merged colour list (wl) of sim_batch.cuh
@@ -86,8 +86,10 @@ struct ResShared {
 };
 
 BP_DEV BodyRec& as_body(RBody& r) { return *reinterpret_cast<BodyRec*>(&r); }
-BP_DEV Poly res_poly(ResShared& S, const RBodyX& X) { Poly P; P.v = (const double*)(S.rv + X.voff); P.n = X.nv; return P; }
+BP_DEV Poly res_poly(ResShared& S, const RBodyX& X) { Poly P; P.v = (const real*)(S.rv + X.voff); P.n = X.nv; return P; }
 BP_DEV double bp_wmin_d(double v) { return -bp_wmax(-v); }
+BP_DEV unsigned res_ring_bytes(int nv) { return (unsigned)((nv * sizeof(D2) + 15) / 16 * 16); }      // bulk copies move multiples of 16 bytes
+static_assert(sizeof(BBox) % 16 == 0 && (VMAX * sizeof(D2)) % 16 == 0, "bulk-copy granularity");
 
 #if defined(BP_RES_DEBUG) && defined(BP_HOST_EMU)
 static void res_check(const DevConst* C, ResShared& S, int e, const char* tag) {
@@ -147,7 +149,8 @@ BP_DEVNI bool res_gather_env(const DevConst* C, ResShared& S, int e, int a_cur, 
     for (int bs = 0; bs < na; bs += BP_NL) {
         int k = bs + lane;
         int nv = (k < na) ? L.nv[ev.awake[k]] : 0;
-        int tot; int ex = bp_wscan_excl(nv, &tot);
+        int nva = (int)((nv * sizeof(D2) + 15) / 16 * 16 / sizeof(D2));      // vertex rings start and end on 16-byte boundaries
+        int tot; int ex = bp_wscan_excl(nva, &tot);
         if (k < na) { RBodyX& X = S.rx[a_cur + k]; X.voff = (unsigned short)(v_cur + vacc + ex); X.nv = (unsigned char)nv; }
         vacc += tot;
     }
@@ -156,7 +159,7 @@ BP_DEVNI bool res_gather_env(const DevConst* C, ResShared& S, int e, int a_cur, 
     bp_wsync();
     // bulk copies: body record, AABB, vertex ring per awake body; the arbiter per touching pair
     unsigned mybytes = 0;
-    for (int k = lane; k < na; k += BP_NL) mybytes += (unsigned)(sizeof(RBody) + sizeof(BBox)) + 16u * S.rx[a_cur + k].nv;
+    for (int k = lane; k < na; k += BP_NL) mybytes += (unsigned)(sizeof(RBody) + sizeof(BBox)) + res_ring_bytes(S.rx[a_cur + k].nv);
     for (int j = lane; j < ns; j += BP_NL) mybytes += (unsigned)sizeof(SlotRec);
     bp_mbar_arrive_tx(&S.mbar, mybytes);
     for (int k = lane; k < na; k += BP_NL) {
@@ -164,8 +167,8 @@ BP_DEVNI bool res_gather_env(const DevConst* C, ResShared& S, int e, int a_cur, 
         RBodyX& X = S.rx[a_cur + k];
         bp_bulk_g2s(&S.rb[a_cur + k], &ev.body[b], (unsigned)sizeof(RBody), &S.mbar);
         bp_bulk_g2s(&X.bb, &ev.bb[b], (unsigned)sizeof(BBox), &S.mbar);
-        bp_bulk_g2s(&S.rv[X.voff], ev.wv + (size_t)b * VMAX * 2, 16u * X.nv, &S.mbar);
-        double mg = body_margin(P, sc, b);
+        bp_bulk_g2s(&S.rv[X.voff], ev.wv + (size_t)b * VMAX * 2, res_ring_bytes(X.nv), &S.mbar);
+        real mg = body_margin(P, sc, b);
         BBox o = ev.b0[b];
         X.liml = o.l - mg; X.limr = o.r + mg; X.limb = o.b - mg; X.limt = o.t + mg;
         X.rbound = L.rbound[b]; X.rad = L.rad[b]; X.cogx = L.cog[2 * b]; X.cogy = L.cog[2 * b + 1];
@@ -211,10 +214,10 @@ BP_DEVNI bool res_gather_env(const DevConst* C, ResShared& S, int e, int a_cur, 
         int hit = -1;
         for (int j = 0; j < ns; j++)
             if (S.rs[s_cur + j].s.pair == p) hit = j;
-        if (hit >= 0) { S.rs[s_cur + hit].ai = (unsigned short)i; ev.ap_gate[i] = -2.0; }
+        if (hit >= 0) { S.rs[s_cur + hit].ai = (unsigned short)i; ev.ap_gate[i] = -RC(2.0); }
         else {
             double g = ev.ap_gate[i];
-            if (g == -2.0) { g = -1.0; ev.ap_gate[i] = -1.0; }      // was resident, is not any more: always evaluate
+            if (g == -RC(2.0)) { g = -RC(1.0); ev.ap_gate[i] = -RC(1.0); }      // was resident, is not any more: always evaluate
             gmin = fmin(gmin, g);
         }
     }
@@ -232,7 +235,7 @@ BP_DEVNI void res_gate_min(const DevConst* C, ResShared& S, int e) {
     double gmin = INFINITY;
     for (int i = lane; i < nap; i += BP_NL) {
         double g = ev.ap_gate[i];
-        if (g != -2.0) gmin = fmin(gmin, g);
+        if (g != -RC(2.0)) gmin = fmin(gmin, g);
     }
     gmin = bp_wmin_d(gmin);
     if (lane == 0) S.gate_min[e] = gmin;
@@ -274,9 +277,9 @@ BP_DEV int res_shipice_checks(ResShared& S, const SimParams& P, int e) {
     int f = 0;
     RBody& R = S.rb[S.robk[e]];
     const RBodyX& X = S.rx[S.robk[e]];
-    double a = R.pa;
-    if (a <= P.yaw_lo || a >= P.yaw_hi) { R.vw = 0.0; f |= 1; }
-    double ox = R.px - (X.cogx * R.rc - X.cogy * R.rs);
+    real a = R.pa;
+    if (a <= P.yaw_lo || a >= P.yaw_hi) { R.vw = RC(0.0); f |= 1; }
+    real ox = R.px - (X.cogx * R.rc - X.cogy * R.rs);
     if (ox < 0 || ox > P.map_w) f |= 2;
     return f;
 }
@@ -353,7 +356,7 @@ BP_DEVNI void res_repack(const DevConst* C, ResShared& S, const StepOut& out, in
 // ------------------------------------------------------------------ narrowphase of the touching pairs, on the pool
 // The pair of pool arbiter q is found apart (pair_apart_impl of sim_step.cuh): the arbiter stays cached for `persistence`
 // steps, the env block's pair entry gets its separation bound and gate.
-BP_DEVNI void res_pair_apart(const DevConst* C, ResShared& S, int q, double gap) {
+BP_DEVNI void res_pair_apart(const DevConst* C, ResShared& S, int q, real gap) {
     RSlot& T = S.rs[q];
     const int e = T.env;
     EnvView ev = view_s(S.base[e]);
@@ -361,7 +364,7 @@ BP_DEVNI void res_pair_apart(const DevConst* C, ResShared& S, int q, double gap)
     PairRec* pr = ev.pair[sc->cur];
     const int p = T.s.pair;
     pr[p].flags |= 1;
-    double g = gap * 0.999999 - 1e-9;
+    double g = gap * RC(0.999999) - RC(1e-9);
     pr[p].skip = S.rb[T.ka].D + S.rb[T.kb].D + g;
     ev.ap_gate[T.ai] = S.G[e] + g;
     if (T.s.touch) {
@@ -389,12 +392,12 @@ BP_DEVNI void res_pair_finish(const DevConst* C, ResShared& S, int q, const Clos
     T.gjk = pts.id;
     if (m.count > 0) {
         SlotRec& R = T.s;
-        double jn_new[2] = {0, 0}, jt_new[2] = {0, 0};
+        real jn_new[2] = {0, 0}, jt_new[2] = {0, 0};
         int oc = R.cnt;
         for (int x = 0; x < m.count; x++)
             for (int j = 0; j < oc; j++)
                 if (m.hash[x] == R.c[j].hash) { jn_new[x] = R.c[j].jn; jt_new[x] = R.c[j].jt; }
-        double ax = A.px, ay = A.py, bx = B.px, by = B.py;
+        real ax = A.px, ay = A.py, bx = B.px, by = B.py;
         for (int x = 0; x < m.count; x++) {
             ContactRec& c = R.c[x];
             c.r1x = m.p1[x].x - ax; c.r1y = m.p1[x].y - ay;
@@ -479,7 +482,7 @@ BP_DEVNI void res_substep(const DevConst* C, ResShared& S, const StepOut& out) {
     const int lane = bp_lane();
     const SimParams& P = C->P;
     const Dims& d = C->d;
-    const double dt = P.dt;
+    const real dt = P.dt;
     // ---- 0. stamps
     for (int e = lane; e < RK; e += BP_NL)
         if (S.st[e] == RS_RES) { EnvScal* sc = (EnvScal*)S.base[e]; S.stamp[e]++; sc->stamp = S.stamp[e]; S.B.dmax_bits[e] = 0ull; }
@@ -494,42 +497,42 @@ BP_DEVNI void res_substep(const DevConst* C, ResShared& S, const StepOut& out) {
             RBody& R = S.rb[i];
             EnvView ev = view_s(S.base[e]);
             const int b = X.gid;
-            double vx = R.vx, vy = R.vy, vw = R.vw, bx = R.bx, by = R.by, bw = R.bw;
-            bool mv = (vx != 0.0 || vy != 0.0 || vw != 0.0 || bx != 0.0 || by != 0.0 || bw != 0.0);
+            real vx = R.vx, vy = R.vy, vw = R.vw, bx = R.bx, by = R.by, bw = R.bw;
+            bool mv = (vx != RC(0.0) || vy != RC(0.0) || vw != RC(0.0) || bx != RC(0.0) || by != RC(0.0) || bw != RC(0.0));
             if (mv) {
-                double dx = (vx + bx) * dt, dy = (vy + by) * dt, da = (vw + bw) * dt;
+                real dx = (vx + bx) * dt, dy = (vy + by) * dt, da = (vw + bw) * dt;
                 R.px = R.px + dx; R.py = R.py + dy; R.pa = R.pa + da;
-                double dD = (fabs(dx) + fabs(dy) + X.rbound * fabs(da)) * 1.000001;
+                real dD = (fabs(dx) + fabs(dy) + X.rbound * fabs(da)) * RC(1.000001);
                 R.D += dD;
                 bp_atomic_max_u64(&S.B.dmax_bits[e], bp_d2bits(dD));
                 // refresh_body_impl on the pool
-                double s, c;
+                real s, c;
                 bp_sincos(R.pa, &s, &c);
                 R.rc = c; R.rs = s;
-                double cx = X.cogx, cy = X.cogy;
-                double tx = R.px - (cx * c - cy * s);
-                double ty = R.py - (cx * s + cy * c);
-                double ms = -s;
+                real cx = X.cogx, cy = X.cogy;
+                real tx = R.px - (cx * c - cy * s);
+                real ty = R.py - (cx * s + cy * c);
+                real ms = -s;
                 const D2* lv2 = (const D2*)(S.B.L[e].lv + (size_t)b * VMAX * 2);
                 D2* wv2 = (D2*)(ev.wv + (size_t)b * VMAX * 2);
                 D2* sv2 = S.rv + X.voff;
                 const int n = X.nv;
-                double l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
+                real l = INFINITY, r = -INFINITY, bt = INFINITY, tp = -INFINITY;
 #pragma unroll 2
                 for (int v = 0; v < n; v++) {
                     D2 qv = lv2[v];
-                    double wx = c * qv.x + ms * qv.y + tx;
-                    double wy = s * qv.x + c * qv.y + ty;
+                    real wx = c * qv.x + ms * qv.y + tx;
+                    real wy = s * qv.x + c * qv.y + ty;
                     D2 w; w.x = wx; w.y = wy;
                     sv2[v] = w; wv2[v] = w;
                     l = fmin(l, wx); r = fmax(r, wx); bt = fmin(bt, wy); tp = fmax(tp, wy);
                 }
-                double rad = X.rad;
+                real rad = X.rad;
                 BBox box; box.l = l - rad; box.b = bt - rad; box.r = r + rad; box.t = tp + rad;
                 X.bb = box; ev.bb[b] = box;
                 if (box.l < X.liml || box.r > X.limr || box.b < X.limb || box.t > X.limt) { S.f_rebuild[e] = 1; ev.sc->rebuild = 1; }
                 ev.moved_step[b] = 1; ev.mvrb[b] = 1;
-                R.bx = 0.0; R.by = 0.0; R.bw = 0.0;
+                R.bx = RC(0.0); R.by = RC(0.0); R.bw = RC(0.0);
                 BodyRec& GB = ev.body[b];
                 GB.px = R.px; GB.py = R.py; GB.pa = R.pa; GB.rc = c; GB.rs = s; GB.D = R.D;
             }
@@ -539,7 +542,7 @@ BP_DEVNI void res_substep(const DevConst* C, ResShared& S, const StepOut& out) {
     }
     bp_wsync();
     for (int e = lane; e < RK; e += BP_NL)
-        if (S.st[e] == RS_RES) { S.G[e] += 2.0 * bp_bits2d(S.B.dmax_bits[e]) * 1.000001; ((EnvScal*)S.base[e])->G = S.G[e]; }
+        if (S.st[e] == RS_RES) { S.G[e] += RC(2.0) * bp_bits2d(S.B.dmax_bits[e]) * RC(1.000001); ((EnvScal*)S.base[e])->G = S.G[e]; }
     bp_wsync();
     // ---- rare: neighbour-list rebuild (env block), then re-pack
     {
@@ -629,7 +632,7 @@ BP_DEVNI void res_substep(const DevConst* C, ResShared& S, const StepOut& out) {
         for (int i = lane; i < tot; i += BP_NL) {
             if (S.st[S.rx[i].env] != RS_RES) continue;
             RBody& R = S.rb[i];
-            if (R.minv != 0.0) { R.vx = R.vx * P.damp + 0.0; R.vy = R.vy * P.damp + 0.0; R.vw = R.vw * P.damp + 0.0; }
+            if (R.minv != RC(0.0)) { R.vx = R.vx * P.damp + RC(0.0); R.vy = R.vy * P.damp + RC(0.0); R.vw = R.vw * P.damp + RC(0.0); }
         }
     }
     bp_wsync();
@@ -640,7 +643,7 @@ BP_DEVNI void res_substep(const DevConst* C, ResShared& S, const StepOut& out) {
         for (int j = c0 + lane; j < c1; j += BP_NL) {
             RSlot& T = S.rs[S.B.wl[j]];
             if (S.st[T.env] != RS_RES) continue;
-            arb_warm_core(T.s, as_body(S.rb[T.ka]), as_body(S.rb[T.kb]), 1.0);
+            arb_warm_core(T.s, as_body(S.rb[T.ka]), as_body(S.rb[T.kb]), RC(1.0));
         }
         bp_wsync();
     }
@@ -691,7 +694,7 @@ BP_DEVNI void shipice_step_resident(const DevConst* C, ResShared& S, char* mem, 
                 if (lane == 0) S.B.L[e] = L;
                 S.base[e] = base; S.kdone[e] = -1;
                 BP_RCHECK(e, "pre-begin");
-                shipice_step_begin(ev, L, P, d, (double)actions[env]);
+                shipice_step_begin(ev, L, P, d, (real)actions[env]);
                 BP_RCHECK(e, "begin");
             }
         }

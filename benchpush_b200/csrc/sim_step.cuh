@@ -8,8 +8,8 @@
 namespace bp {
 
 BP_DEV unsigned pair_key(int i, int j) { return ((unsigned)i << 16) | (unsigned)j; }
-BP_DEV double body_margin(const SimParams& P, const EnvScal* sc, int b) { return b >= sc->robot ? P.margin_robot : P.margin_body; }
-BP_DEV bool body_dynamic(const LayoutView& L, int b) { return L.minv[b] != 0.0; }
+BP_DEV real body_margin(const SimParams& P, const EnvScal* sc, int b) { return b >= sc->robot ? P.margin_robot : P.margin_body; }
+BP_DEV bool body_dynamic(const LayoutView& L, int b) { return L.minv[b] != RC(0.0); }
 
 #if defined(BP_PHASE_TIMERS) && defined(__CUDACC__) && !defined(BP_HOST_EMU)
 #define BP_TICK(var) long long var = clock64()
@@ -96,14 +96,14 @@ BP_DEVNI void rebuild_pairs(const EnvView& ev, const SimParams& P, const Dims& d
     int np = 0;
     bool overflow = false;
     for (int i = 0; i < nb - 1; i++) {
-        double mi = body_margin(P, sc, i);
+        real mi = body_margin(P, sc, i);
         BBox bi = ev.b0[i];
-        double il = bi.l - mi, ib = bi.b - mi, ir = bi.r + mi, it = bi.t + mi;
+        real il = bi.l - mi, ib = bi.b - mi, ir = bi.r + mi, it = bi.t + mi;
         for (int base = i + 1; base < nb; base += BP_NL) {
             int j = base + lane;
             bool hit = false;
             if (j < nb) {
-                double mj = body_margin(P, sc, j);
+                real mj = body_margin(P, sc, j);
                 BBox bj = ev.b0[j];
                 hit = (il <= bj.r + mj && bj.l - mj <= ir && ib <= bj.t + mj && bj.b - mj <= it);
             }
@@ -120,7 +120,7 @@ BP_DEVNI void rebuild_pairs(const EnvView& ev, const SimParams& P, const Dims& d
     const PairRec* op = ev.pair[cur];
     for (int p = lane; p < np; p += BP_NL) {
         unsigned key = np_[p].key;
-        unsigned gj = 0; int lv = -1; unsigned fl = 0; double sk = 0.0;
+        unsigned gj = 0; int lv = -1; unsigned fl = 0; real sk = RC(0.0);
         if (carry) {
             int lo = 0, hi = old_n - 1;
             while (lo <= hi) {
@@ -172,14 +172,14 @@ BP_DEVNI void rebuild_pairs_inc(const EnvView& ev, const SimParams& P, const Dim
     int nf = 0;
     for (int k = 0; k < nm; k++) {
         const int m = mlist[k];
-        double mm = body_margin(P, sc, m);
+        real mm = body_margin(P, sc, m);
         BBox bm = ev.b0[m];
-        double il = bm.l - mm, ib = bm.b - mm, ir = bm.r + mm, it = bm.t + mm;
+        real il = bm.l - mm, ib = bm.b - mm, ir = bm.r + mm, it = bm.t + mm;
         for (int base = 0; base < nb; base += BP_NL) {
             int x = base + lane;
             bool hit = false;
             if (x < nb && x != m && !(x < m && ev.mvrb[x])) {      // a pair of two moved bodies is emitted by the smaller id
-                double mx = body_margin(P, sc, x);
+                real mx = body_margin(P, sc, x);
                 BBox bx = ev.b0[x];
                 hit = (il <= bx.r + mx && bx.l - mx <= ir && ib <= bx.t + mx && bx.b - mx <= it);
             }
@@ -225,7 +225,7 @@ BP_DEVNI void rebuild_pairs_inc(const EnvView& ev, const SimParams& P, const Dim
         int lo = 0, hi = old_n;                    // first old entry with key >= this key
         while (lo < hi) { int mid = (lo + hi) >> 1; if (op[mid].key < key) lo = mid + 1; else hi = mid; }
         int sr = srank[lo]; if (sr < 0) sr = -sr - 1;
-        PairRec q; q.key = key; q.gjk = 0; q.live = -1; q.flags = 0; q.skip = 0.0;
+        PairRec q; q.key = key; q.gjk = 0; q.live = -1; q.flags = 0; q.skip = RC(0.0);
         if (lo < old_n && op[lo].key == key) { q.gjk = op[lo].gjk; q.live = op[lo].live; q.flags = op[lo].flags & 1; q.skip = op[lo].skip; }
         np_[sr + i] = q;
     }
@@ -245,7 +245,7 @@ BP_DEV void add_body_pairs(const EnvView& ev, int bdy) {
         bool take = false; int p = -1;
         if (e < s1) { p = ev.adj[e]; take = !(pr[p].flags & 2); }
         int tot; int rk = bp_wrank(take, &tot);
-        if (take) { ev.apairs[n + rk] = p; ev.ap_gate[n + rk] = -1.0; pr[p].flags |= 2; }
+        if (take) { ev.apairs[n + rk] = p; ev.ap_gate[n + rk] = -RC(1.0); pr[p].flags |= 2; }
         n += tot;
     }
     bp_wsync();
@@ -275,9 +275,9 @@ BP_DEVNI void build_apairs(const EnvView& ev) {
 // Compaction between the stages keeps lanes on the same code path (GJK/EPA are long and divergent).
 
 // Not-touching outcome for pair p: slot bookkeeping + separation bound.
-BP_DEV void pair_apart_impl(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, double gap) {
+BP_DEV void pair_apart_impl(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, real gap) {
     pr[p].flags |= 1;
-    double g = gap * 0.999999 - 1e-9;
+    double g = gap * RC(0.999999) - RC(1e-9);
     pr[p].skip = ev.body[a].D + ev.body[b].D + g;
     ev.ap_gate[i] = sc->G + g;
     int slot = pr[p].live;
@@ -291,8 +291,8 @@ BP_DEV void pair_apart_impl(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, 
     }
 }
 
-BP_DEVNI void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, double gap) { pair_apart_impl(ev, sc, pr, i, p, a, b, gap); }
-BP_DEVNI void pair_apart_b(const DevConst* C, char* base, int i, int p, int a, int b, double gap) {
+BP_DEVNI void pair_apart(const EnvView& ev, EnvScal* sc, PairRec* pr, int i, int p, int a, int b, real gap) { pair_apart_impl(ev, sc, pr, i, p, a, b, gap); }
+BP_DEVNI void pair_apart_b(const DevConst* C, char* base, int i, int p, int a, int b, real gap) {
     EnvView ev = view_s(base);
     pair_apart_impl(ev, ev.sc, ev.pair[ev.sc->cur], i, p, a, b, gap);
 }
@@ -331,12 +331,12 @@ BP_DEVNI void pair_finish(const EnvView& ev, const LayoutView& L, const Dims& d,
         if (touching) {
             SlotRec& S = ev.slot[slot];
             bool was = !fresh && S.touch;
-            double jn_new[2] = {0, 0}, jt_new[2] = {0, 0};
+            real jn_new[2] = {0, 0}, jt_new[2] = {0, 0};
             int oc = fresh ? 0 : S.cnt;
             for (int i = 0; i < m.count; i++)
                 for (int j = 0; j < oc; j++)
                     if (m.hash[i] == S.c[j].hash) { jn_new[i] = S.c[j].jn; jt_new[i] = S.c[j].jt; }
-            double ax = ev.body[a].px, ay = ev.body[a].py, bx = ev.body[b].px, by = ev.body[b].py;
+            real ax = ev.body[a].px, ay = ev.body[a].py, bx = ev.body[b].px, by = ev.body[b].py;
             for (int i = 0; i < m.count; i++) {
                 ContactRec& c = S.c[i];
                 c.r1x = m.p1[i].x - ax; c.r1y = m.p1[i].y - ay;
@@ -354,8 +354,8 @@ BP_DEVNI void pair_finish(const EnvView& ev, const LayoutView& L, const Dims& d,
             }
             S.stamp = sc->stamp;
             pr[p].flags |= 1;
-            pr[p].skip = -1.0;
-            ev.ap_gate[i] = -1.0;
+            pr[p].skip = -RC(1.0);
+            ev.ap_gate[i] = -RC(1.0);
             // a touching pair with an awake endpoint wakes the other (dynamic) endpoint
             if ((!ev.is_awake[a] && body_dynamic(L, a)) || (!ev.is_awake[b] && body_dynamic(L, b))) sc->any_wake = 1;
         } else {
@@ -395,17 +395,17 @@ BP_DEVNI int eval_pairs(const EnvView& ev, const LayoutView& L, const Dims& d, i
             int a = q.key >> 16, b = q.key & 0xFFFF;
             bool mv = ev.moved[a] || ev.moved[b];
             double dsum = ev.body[a].D + ev.body[b].D;
-            bool need = !(q.flags & 1) || (mv && (q.skip < 0.0 || dsum >= q.skip));
+            bool need = !(q.flags & 1) || (mv && (q.skip < RC(0.0) || dsum >= q.skip));
             if (!need) {
-                if (q.skip >= 0.0) { ev.ap_gate[i] = G + (q.skip - dsum); if (mv) n_skip++; }
+                if (q.skip >= RC(0.0)) { ev.ap_gate[i] = G + (q.skip - dsum); if (mv) n_skip++; }
             } else {
                 n_eval++;
                 BBox A = ev.bb[a], B = ev.bb[b];
                 bool bbhit = (A.l <= B.r && B.l <= A.r && A.b <= B.t && B.b <= A.t);
-                if (bbhit && !(L.minv[a] == 0.0 && L.minv[b] == 0.0)) take = true;
+                if (bbhit && !(L.minv[a] == RC(0.0) && L.minv[b] == RC(0.0))) take = true;
                 else {
-                    double gap = fmax(fmax(A.l - B.r, B.l - A.r), fmax(A.b - B.t, B.b - A.t));
-                    pair_apart(ev, sc, pr, i, p, a, b, bbhit ? 0.0 : gap);
+                    real gap = fmax(fmax(A.l - B.r, B.l - A.r), fmax(A.b - B.t, B.b - A.t));
+                    pair_apart(ev, sc, pr, i, p, a, b, bbhit ? RC(0.0) : gap);
                 }
             }
         }
@@ -578,23 +578,23 @@ BP_DEVNI void build_order(const EnvView& ev, const LayoutView& L, const Dims& d)
 BP_DEV void arb_prestep_core(SlotRec& S, const BodyRec& A, const BodyRec& B, const SimParams& P) {
     V2 n = mk(S.nx, S.ny);
     V2 tn = perp(n);
-    double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
+    real ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     V2 delta = mk(B.px - A.px, B.py - A.py);
     V2 va = mk(A.vx, A.vy), vb = mk(B.vx, B.vy);
-    double wa = A.vw, wb = B.vw;
+    real wa = A.vw, wb = B.vw;
     int cnt = S.cnt;
 #pragma unroll 1
     for (int i = 0; i < cnt; i++) {
         ContactRec& c = S.c[i];
         V2 r1 = mk(c.r1x, c.r1y), r2 = mk(c.r2x, c.r2y);
-        double r1n = cross(r1, n), r2n = cross(r2, n);
-        double kn = (ma + ia * r1n * r1n) + (mb + ib * r2n * r2n);
-        double r1t = cross(r1, tn), r2t = cross(r2, tn);
-        double kt = (ma + ia * r1t * r1t) + (mb + ib * r2t * r2t);
-        c.nm = 1.0 / kn; c.tm = 1.0 / kt;
-        double dist = dot((r2 - r1) + delta, n);
-        c.bias = -P.bias_coef * fmin(0.0, dist + P.slop) / P.dt;
-        c.jb = 0.0;
+        real r1n = cross(r1, n), r2n = cross(r2, n);
+        real kn = (ma + ia * r1n * r1n) + (mb + ib * r2n * r2n);
+        real r1t = cross(r1, tn), r2t = cross(r2, tn);
+        real kt = (ma + ia * r1t * r1t) + (mb + ib * r2t * r2t);
+        c.nm = RC(1.0) / kn; c.tm = RC(1.0) / kt;
+        real dist = dot((r2 - r1) + delta, n);
+        c.bias = -P.bias_coef * fmin(RC(0.0), dist + P.slop) / P.dt;
+        c.jb = RC(0.0);
         V2 vr = (vb + perp(r2) * wb) - (va + perp(r1) * wa);
         c.bounce = dot(vr, n) * S.e;
     }
@@ -603,10 +603,10 @@ BP_DEV void arb_prestep(const EnvView& ev, const LayoutView& L, const SimParams&
     SlotRec& S = ev.slot[s];
     arb_prestep_core(S, ev.body[S.a], ev.body[S.b], P);
 }
-BP_DEV void arb_warm_core(const SlotRec& S, BodyRec& A, BodyRec& B, double dt_coef) {
+BP_DEV void arb_warm_core(const SlotRec& S, BodyRec& A, BodyRec& B, real dt_coef) {
     if (S.first) return;
     V2 n = mk(S.nx, S.ny);
-    double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
+    real ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     int cnt = S.cnt;
 #pragma unroll 1
     for (int i = 0; i < cnt; i++) {
@@ -618,41 +618,41 @@ BP_DEV void arb_warm_core(const SlotRec& S, BodyRec& A, BodyRec& B, double dt_co
         B.vx = B.vx + j.x * mb; B.vy = B.vy + j.y * mb; B.vw += ib * cross(r2, j);
     }
 }
-BP_DEV void arb_warm(const EnvView& ev, const LayoutView& L, int s, double dt_coef) {
+BP_DEV void arb_warm(const EnvView& ev, const LayoutView& L, int s, real dt_coef) {
     SlotRec& S = ev.slot[s];
     arb_warm_core(S, ev.body[S.a], ev.body[S.b], dt_coef);
 }
 BP_DEV void arb_solve_core(SlotRec& S, BodyRec& A, BodyRec& B) {
     V2 n = mk(S.nx, S.ny);
     V2 tn = perp(n);
-    double fr = S.u;
-    double ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
+    real fr = S.u;
+    real ma = A.minv, ia = A.iinv, mb = B.minv, ib = B.iinv;
     V2 va = mk(A.vx, A.vy), vb = mk(B.vx, B.vy);
-    double wa = A.vw, wb = B.vw;
+    real wa = A.vw, wb = B.vw;
     V2 ba = mk(A.bx, A.by), bb = mk(B.bx, B.by);
-    double bwa = A.bw, bwb = B.bw;
+    real bwa = A.bw, bwb = B.bw;
     int cnt = S.cnt;
 #pragma unroll 1
     for (int i = 0; i < cnt; i++) {
         ContactRec& c = S.c[i];
         V2 r1 = mk(c.r1x, c.r1y), r2 = mk(c.r2x, c.r2y);
-        double nMass = c.nm;
+        real nMass = c.nm;
         V2 vb1 = ba + perp(r1) * bwa;
         V2 vb2 = bb + perp(r2) * bwb;
         V2 vr = (vb + perp(r2) * wb) - (va + perp(r1) * wa);
-        double vbn = dot(vb2 - vb1, n);
-        double vrn = dot(vr, n);
-        double vrt = dot(vr, tn);
-        double jbn = (c.bias - vbn) * nMass;
-        double jbnOld = c.jb;
-        double jb = fmax(jbnOld + jbn, 0.0);
-        double jn = -(c.bounce + vrn) * nMass;
-        double jnOld = c.jn;
-        double jnAcc = fmax(jnOld + jn, 0.0);
-        double jtMax = fr * jnAcc;
-        double jt = -vrt * c.tm;
-        double jtOld = c.jt;
-        double jtAcc = clampd(jtOld + jt, -jtMax, jtMax);
+        real vbn = dot(vb2 - vb1, n);
+        real vrn = dot(vr, n);
+        real vrt = dot(vr, tn);
+        real jbn = (c.bias - vbn) * nMass;
+        real jbnOld = c.jb;
+        real jb = fmax(jbnOld + jbn, RC(0.0));
+        real jn = -(c.bounce + vrn) * nMass;
+        real jnOld = c.jn;
+        real jnAcc = fmax(jnOld + jn, RC(0.0));
+        real jtMax = fr * jnAcc;
+        real jt = -vrt * c.tm;
+        real jtOld = c.jt;
+        real jtAcc = clampd(jtOld + jt, -jtMax, jtMax);
         c.jb = jb; c.jn = jnAcc; c.jt = jtAcc;
         V2 jbv = n * (jb - jbnOld), njbv = neg(jbv);
         ba = ba + njbv * ma; bwa += ia * cross(r1, njbv);
@@ -662,8 +662,8 @@ BP_DEV void arb_solve_core(SlotRec& S, BodyRec& A, BodyRec& B) {
         vb = vb + j * mb; wb += ib * cross(r2, j);
     }
     // kinematic / static bodies have m_inv = i_inv = 0: their velocities are unchanged (x + 0), skip the stores
-    if (ma != 0.0 || ia != 0.0) { A.vx = va.x; A.vy = va.y; A.vw = wa; A.bx = ba.x; A.by = ba.y; A.bw = bwa; }
-    if (mb != 0.0 || ib != 0.0) { B.vx = vb.x; B.vy = vb.y; B.vw = wb; B.bx = bb.x; B.by = bb.y; B.bw = bwb; }
+    if (ma != RC(0.0) || ia != RC(0.0)) { A.vx = va.x; A.vy = va.y; A.vw = wa; A.bx = ba.x; A.by = ba.y; A.bw = bwa; }
+    if (mb != RC(0.0) || ib != RC(0.0)) { B.vx = vb.x; B.vy = vb.y; B.vw = wb; B.bx = bb.x; B.by = bb.y; B.bw = bwb; }
 }
 BP_DEV void arb_solve(const EnvView& ev, const LayoutView& L, int s) {
     SlotRec& S = ev.slot[s];
@@ -671,7 +671,7 @@ BP_DEV void arb_solve(const EnvView& ev, const LayoutView& L, int s) {
 }
 
 // Steps 3-6 of a substep for ONE env: prestep, velocity update, warm start, iterations.
-BP_DEVNI void solve_env(const EnvView& ev, const LayoutView& L, const SimParams& P, double dt, double prev_dt) {
+BP_DEVNI void solve_env(const EnvView& ev, const LayoutView& L, const SimParams& P, real dt, real prev_dt) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     // 3. prestep (uses the pre-damping velocities for the bounce term)
@@ -684,12 +684,12 @@ BP_DEVNI void solve_env(const EnvView& ev, const LayoutView& L, const SimParams&
         int b = ev.awake[k];
         if (body_dynamic(L, b)) {
             BodyRec& R = ev.body[b];
-            R.vx = R.vx * P.damp + 0.0; R.vy = R.vy * P.damp + 0.0; R.vw = R.vw * P.damp + 0.0;
+            R.vx = R.vx * P.damp + RC(0.0); R.vy = R.vy * P.damp + RC(0.0); R.vw = R.vw * P.damp + RC(0.0);
         }
     }
     bp_wsync();
     // 5. warm start + iterations, colour by colour (same-colour arbiters touch disjoint dynamic bodies)
-    double dt_coef = (prev_dt == 0.0) ? 0.0 : dt / prev_dt;
+    real dt_coef = (prev_dt == RC(0.0)) ? RC(0.0) : dt / prev_dt;
     int nc = sc->n_colours;
     for (int c = 0; c < nc; c++) {
         int c0 = ev.col_start[c], c1 = ev.col_start[c + 1];
@@ -710,8 +710,8 @@ BP_DEVNI void solve_env(const EnvView& ev, const LayoutView& L, const SimParams&
 }
 
 // ------------------------------------------------------------------ one substep (cpSpaceStep)
-BP_DEVNI void substep_rest(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, double dt, double prev_dt);
-BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, double dt, double prev_dt) {
+BP_DEVNI void substep_rest(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, real dt, real prev_dt);
+BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, real dt, real prev_dt) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     BP_TICK(tk);
@@ -719,36 +719,36 @@ BP_DEVNI void substep(const EnvView& ev, const LayoutView& L, const SimParams& P
     bp_wsync();
     // 1. integrate positions of the awake bodies (everything else has v = v_bias = 0 exactly)
     int na = sc->n_awake;
-    double dmax = 0.0;
+    real dmax = RC(0.0);
     for (int k = lane; k < na; k += BP_NL) {
         int b = ev.awake[k];
         BodyRec& R = ev.body[b];
-        double vx = R.vx, vy = R.vy, vw = R.vw, bx = R.bx, by = R.by, bw = R.bw;
-        bool mv = (vx != 0.0 || vy != 0.0 || vw != 0.0 || bx != 0.0 || by != 0.0 || bw != 0.0);
+        real vx = R.vx, vy = R.vy, vw = R.vw, bx = R.bx, by = R.by, bw = R.bw;
+        bool mv = (vx != RC(0.0) || vy != RC(0.0) || vw != RC(0.0) || bx != RC(0.0) || by != RC(0.0) || bw != RC(0.0));
         if (mv) {
-            double dx = (vx + bx) * dt, dy = (vy + by) * dt, da = (vw + bw) * dt;
+            real dx = (vx + bx) * dt, dy = (vy + by) * dt, da = (vw + bw) * dt;
             R.px = R.px + dx; R.py = R.py + dy; R.pa = R.pa + da;
             // motion bound of any point of the body (rotation about the cog), rounded up
-            double dD = (fabs(dx) + fabs(dy) + L.rbound[b] * fabs(da)) * 1.000001;
+            real dD = (fabs(dx) + fabs(dy) + L.rbound[b] * fabs(da)) * RC(1.000001);
             R.D += dD;
             dmax = fmax(dmax, dD);
             refresh_body(ev, L, b);
-            double mg = body_margin(P, sc, b);
+            real mg = body_margin(P, sc, b);
             BBox c = ev.bb[b], o = ev.b0[b];
             if (c.l < o.l - mg || c.r > o.r + mg || c.b < o.b - mg || c.t > o.t + mg) sc->rebuild = 1;
             ev.moved_step[b] = 1; ev.mvrb[b] = 1;
-            R.bx = 0.0; R.by = 0.0; R.bw = 0.0;
+            R.bx = RC(0.0); R.by = RC(0.0); R.bw = RC(0.0);
         }
         ev.moved[b] = mv ? 1 : 0;
     }
     dmax = bp_wmax(dmax);
-    if (lane == 0) sc->G += 2.0 * dmax * 1.000001;
+    if (lane == 0) sc->G += RC(2.0) * dmax * RC(1.000001);
     bp_wsync();
     BP_TOCK(sc, 0, tk);
     substep_rest(ev, L, P, d, dt, prev_dt);
 }
 // Everything of a substep after the position update: neighbour-list rebuild, collide, wake closure, cache expiry, solve.
-BP_DEVNI void substep_rest(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, double dt, double prev_dt) {
+BP_DEVNI void substep_rest(const EnvView& ev, const LayoutView& L, const SimParams& P, const Dims& d, real dt, real prev_dt) {
     EnvScal* sc = ev.sc;
     BP_TICK(tk);
     if (sc->rebuild) { rebuild_pairs_inc(ev, P, d); build_apairs(ev); }
@@ -777,7 +777,7 @@ BP_DEVNI void sleep_pass(const EnvView& ev, const LayoutView& L, const Dims& d) 
     for (int k = lane; k < na; k += BP_NL) {
         int b = ev.awake[k];
         const BodyRec& R = ev.body[b];
-        bool nz = (R.vx != 0.0 || R.vy != 0.0 || R.vw != 0.0 || R.bx != 0.0 || R.by != 0.0 || R.bw != 0.0);
+        bool nz = (R.vx != RC(0.0) || R.vy != RC(0.0) || R.vw != RC(0.0) || R.bx != RC(0.0) || R.by != RC(0.0) || R.bw != RC(0.0));
         ev.act[b] = (nz || !body_dynamic(L, b)) ? 1 : 0;
     }
     bp_wsync();
@@ -787,7 +787,7 @@ BP_DEVNI void sleep_pass(const EnvView& ev, const LayoutView& L, const Dims& d) 
         if (S.pair < 0) continue;
         bool seed = false;
         for (int i = 0; i < S.cnt; i++)
-            if (S.c[i].jn != 0.0 || S.c[i].jt != 0.0 || S.c[i].jb != 0.0) seed = true;
+            if (S.c[i].jn != RC(0.0) || S.c[i].jt != RC(0.0) || S.c[i].jb != RC(0.0)) seed = true;
         if (S.touch && (!body_dynamic(L, S.a) || !body_dynamic(L, S.b))) seed = true;   // touches the robot
         if (seed) { ev.act[S.a] = 1; ev.act[S.b] = 1; }
     }
@@ -860,8 +860,8 @@ BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& 
     if (lane == 0) {
         sc->stamp = 0; sc->n_awake = nb; sc->n_pairs = 0; sc->cur = 0; sc->n_free = d.LMAX; sc->n_order = 0; sc->n_colours = 0;
         sc->dirty = 1; sc->status = 0; sc->layout = layout_id; sc->nbody = nb; sc->robot = L.robot0; sc->t = 0; sc->rebuild = 0;
-        sc->n_apairs = 0; sc->n_cached = 0; sc->any_wake = 0; sc->total_work = 0.0; sc->G = 0.0;
-        sc->wall_hit = 0; sc->has_prev_dist = 0; sc->prev_dist = 0.0; sc->slot_hw = 0; sc->pad_hw = 0;
+        sc->n_apairs = 0; sc->n_cached = 0; sc->any_wake = 0; sc->total_work = RC(0.0); sc->G = RC(0.0);
+        sc->wall_hit = 0; sc->has_prev_dist = 0; sc->prev_dist = RC(0.0); sc->slot_hw = 0; sc->pad_hw = 0;
         int nf = 0;
         for (int b = 0; b < nb; b++) nf += body_dynamic(L, b) ? 0 : 1;
         sc->n_fixed = nf;
@@ -869,17 +869,21 @@ BP_DEVNI void init_env(const EnvView& ev, const LayoutView& L, const SimParams& 
     for (int b = lane; b < nb; b += BP_NL) {
         BodyRec& R = ev.body[b];
         // every shape of the kinematic robot (bodies >= robot0) starts at the robot's pose
-        const double* ip = poses6 ? poses6 + 6 * b : ((start && b >= L.robot0) ? start : L.init + 3 * b);
-        double a = ip[2];
-        double s, c; bp_sincos(a, &s, &c);
-        double cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
+        double ipd[6] = {0, 0, 0, 0, 0, 0};                  // the layout's pose (real) or an injected one (double)
+        if (poses6) { for (int q = 0; q < 6; q++) ipd[q] = poses6[6 * b + q]; }
+        else if (start && b >= L.robot0) { for (int q = 0; q < 3; q++) ipd[q] = start[q]; }
+        else { for (int q = 0; q < 3; q++) ipd[q] = (double)L.init[3 * b + q]; }
+        const real ip[6] = {(real)ipd[0], (real)ipd[1], (real)ipd[2], (real)ipd[3], (real)ipd[4], (real)ipd[5]};
+        real a = ip[2];
+        real s, c; bp_sincos(a, &s, &c);
+        real cx = L.cog[2 * b], cy = L.cog[2 * b + 1];
         // cpBodySetPosition: p = position + rotate(cog)
         R.px = (c * cx + (-s) * cy) + ip[0];
         R.py = (s * cx + c * cy) + ip[1];
         R.pa = a;
-        R.vx = R.vy = R.vw = 0.0; R.bx = R.by = R.bw = 0.0; R.D = 0.0;
+        R.vx = R.vy = R.vw = RC(0.0); R.bx = R.by = R.bw = RC(0.0); R.D = RC(0.0);
         if (poses6) { R.vx = ip[3]; R.vy = ip[4]; R.vw = ip[5]; }
-        R.minv = L.minv[b]; R.iinv = L.iinv[b]; R.pad0 = R.pad1 = 0.0;
+        R.minv = L.minv[b]; R.iinv = L.iinv[b]; R.pad0 = R.pad1 = RC(0.0);
         refresh_body(ev, L, b);
         ev.awake[b] = b; ev.is_awake[b] = 1; ev.moved[b] = 0; ev.moved_step[b] = 0; ev.act[b] = 1;
     }

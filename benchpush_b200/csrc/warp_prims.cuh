@@ -6,6 +6,22 @@
 // library never contains or calls that build).
 #pragma once
 #include <stdint.h>
+#include <float.h>
+
+// Arithmetic type of the body state, contacts and solver ("real").  The library is built twice from the same sources:
+// libbenchpush_b200.so with real = double and no FMA contraction (bit-comparable with the fp64 CPU oracle), and
+// libbenchpush_b200_f32.so with -DBP_F32 (real = float, FMA allowed): half the bytes per env, twice the ALU rate; its
+// transitions agree with the oracle within the tolerance stated in tests/test_gpu_fp32.py and its episode scores are
+// statistically indistinguishable (profiles/r02b_fp32_experiment.json).  Bookkeeping that has to stay conservative or
+// accumulates over an episode (motion bounds D / G, pair gates, accumulated work, outputs) is double in both builds.
+#ifdef BP_F32
+typedef float real;
+#define BP_RMIN FLT_MIN
+#else
+typedef double real;
+#define BP_RMIN DBL_MIN
+#endif
+#define RC(x) ((real)(x))
 
 #if defined(__CUDACC__) && !defined(BP_HOST_EMU)
 #define BP_DEV __device__ __forceinline__
@@ -129,6 +145,10 @@ BP_DEV void bp_sincos(double x, double* sn, double* cs) {
     *sn = (n == 0) ? ks : (n == 1) ? kc : (n == 2) ? -ks : -kc;
     *cs = (n == 0) ? kc : (n == 1) ? -ks : (n == 2) ? -kc : ks;
 }
+
+#ifdef BP_F32
+BP_DEV void bp_sincos(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+#endif
 
 // atomics (device) / plain ops (single-lane host emulation)
 #if defined(__CUDACC__) && !defined(BP_HOST_EMU)

@@ -34,7 +34,7 @@ class MazeNamoVecEnv(ShipIceVecEnv):
 
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence] = None,
                  auto_reset: bool = False, first_layout: Optional[Sequence[int]] = None, synthetic_seed: int = 0,
-                 n_synthetic_layouts: int = 256, start_seed: int = 0):
+                 n_synthetic_layouts: int = 256, start_seed: int = 0, precision: str = "fp64"):
         if not torch.cuda.is_available():
             raise _lib.BenchPushError("MazeNamoVecEnv needs a CUDA device (there is no CPU fallback)")
         self.cfg = merge_cfg(DotDict.load_from_file(_CFG_PATH), cfg)
@@ -71,7 +71,8 @@ class MazeNamoVecEnv(ShipIceVecEnv):
         nb, cen = pack_maze_layouts(self.layouts)
         self.max_boxes = int(cen.shape[1])
         # ---- native handle
-        L = _lib.lib()
+        self.precision = precision
+        L = _lib.lib(precision)
         c = _lib.MazeConfig()
         L.bp_maze_default_config(C.byref(c), int(self.cfg.maze_version))
         c.n_envs = self.num_envs; c.max_boxes = self.max_boxes; c.device = self.device_index; c.auto_reset = 1 if auto_reset else 0

@@ -48,7 +48,7 @@ class ShipIceVecEnv:
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[PackedLayouts] = None,
                  trials: Optional[Sequence[dict]] = None, ice_file: Optional[str] = None, auto_reset: bool = False,
                  first_trial: Optional[Sequence[int]] = None, synthetic_seed: int = 99, n_synthetic_trials: int = 100,
-                 start_seed: int = 0):
+                 start_seed: int = 0, precision: str = "fp64"):
         if not torch.cuda.is_available():
             raise _lib.BenchPushError("ShipIceVecEnv needs a CUDA device (there is no CPU fallback)")
         self.cfg = merge_cfg(DotDict.load_from_file(_CFG_PATH), cfg)
@@ -81,7 +81,8 @@ class ShipIceVecEnv:
         self.layouts = layouts
         self.env_max_trial = layouts.n_layouts
         # ---- native handle
-        L = _lib.lib()
+        self.precision = precision          # "fp64": bit-comparable with the oracle; "fp32": fp32 body state / contacts / solver (tolerance parity)
+        L = _lib.lib(precision)
         c = _lib.ShipIceConfig()
         L.bp_shipice_default_config(C.byref(c))
         c.n_envs = self.num_envs

@@ -175,3 +175,27 @@ def test_injected_mid_episode_state_matches_oracle(mode, golden_layouts, portabl
         assert np.array_equal(emu.bodies(0, 0), ora.space.state()), k
         np.testing.assert_allclose(emu.out(0)["reward"], r, rtol=1e-9, atol=1e-7)
     assert emu.scal(0)["n_awake"] < 200          # the sleep pass is back after the first step
+
+
+def test_fp32_build_of_the_kernel_sources_stays_within_tolerance(golden_layouts, monkeypatch):
+    """-DBP_F32 (real = float): the same sources with fp32 body state / contacts / solver.  One env step from reset within
+    1e-3 m / 1e-2 rad of the fp64 oracle, five steps within 2e-3 m; the three step paths stay bit-identical
+    to each other in fp32 as well."""
+    monkeypatch.setenv("BP_EMU_FLAGS", "-DBP_F32")
+    name = "c30_t7"
+    p = golden_layouts[name]
+    ora = ShipIceOracleEnv({"concentration": fixture_conc(name)}, experiment=unpack_trials(p), order_mode=1)
+    ora.reset()
+    kw = dict(pmax=8 * (p.max_floes + 1), lmax=2 * (p.max_floes + 1))
+    A, B, C_ = Emu(1, p, SHIP_VERTS, **kw), Emu(1, p, SHIP_VERTS, **kw), Emu(1, p, SHIP_VERTS, **kw)
+    for e in (A, B, C_):
+        e.reset(0, 0)
+    rng = np.random.default_rng(1)
+    for k in range(5):
+        a = np.float32(rng.uniform(-1, 1))
+        A.step(0, float(a)); B.step_batch(0, np.array([a], dtype=np.float32)); C_.step_resident(0, np.array([a], dtype=np.float32))
+        ora.step(float(a), want_obs=False)
+        g, o = A.bodies(0, 0), ora.space.state()
+        assert np.array_equal(g, B.bodies(0, 0)) and np.array_equal(g, C_.bodies(0, 0))
+        lim = 1e-3 if k == 0 else 2e-3
+        assert np.abs(g[:, :2] - o[:, :2]).max() <= lim and np.abs(g[:, 2] - o[:, 2]).max() <= 1e-2, k

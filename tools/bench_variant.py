@@ -9,7 +9,7 @@ from benchpush_b200.layouts import generate_experiment, pack_trials
 E = int(sys.argv[1]); conc = float(sys.argv[2]); warm = int(sys.argv[3]); steps = int(sys.argv[4])
 desync = int(sys.argv[5]) if len(sys.argv) > 5 else 1      # > 1: spread the episode phases first (steady state, like bench.py)
 packed = pack_trials(generate_experiment(32, conc, seed=99))
-env = ShipIceVecEnv(num_envs=E, cfg={"concentration": conc}, layouts=packed, device=0, auto_reset=True)
+env = ShipIceVecEnv(num_envs=E, cfg={"concentration": conc}, layouts=packed, device=0, auto_reset=True, precision=os.environ.get("BP_PRECISION", "fp64"))
 env.check_status = False
 env.reset()
 g = torch.Generator(device="cuda"); g.manual_seed(0)
