@@ -839,7 +839,7 @@ int bp_shipice_get_obstacles(bp_shipice_t* h, int32_t env, double* verts, int32_
     for (int b = 0; b < ev.sc->robot; b++) {
         if (L.minv[b] == 0.0) continue;              // static walls
         n_verts[nf] = L.nv[b];
-        memcpy(verts + (size_t)nf * VMAX * 2, ev.wv + (size_t)b * VMAX * 2, sizeof(double) * 2 * L.nv[b]);
+        for (int i = 0; i < 2 * L.nv[b]; i++) verts[(size_t)nf * VMAX * 2 + i] = (double)ev.wv[(size_t)b * VMAX * 2 + i];
         nf++;
     }
     return nf;

@@ -10,7 +10,7 @@
 
 // Arithmetic type of the body state, contacts and solver ("real").  The library is built twice from the same sources:
 // libbenchpush_b200.so with real = double and no FMA contraction (bit-comparable with the fp64 CPU oracle), and
-// libbenchpush_b200_f32.so with -DBP_F32 (real = float, FMA allowed): half the bytes per env, twice the ALU rate; its
+// libbenchpush_b200_f32.so with -DBP_F32 (real = float): half the bytes per env, twice the ALU rate; its
 // transitions agree with the oracle within the tolerance stated in tests/test_gpu_fp32.py and its episode scores are
 // statistically indistinguishable (profiles/r02b_fp32_experiment.json).  Bookkeeping that has to stay conservative or
 // accumulates over an episode (motion bounds D / G, pair gates, accumulated work, outputs) is double in both builds.

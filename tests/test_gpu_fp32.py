@@ -1,5 +1,5 @@
 """The fp32-state build of the same kernel sources (libbenchpush_b200_f32.so: real = float for body state, contacts and
-solver, FMA allowed; motion bounds, gates, accumulated work and outputs stay double) against the fp64 oracle.
+solver; motion bounds, gates, accumulated work and outputs stay double) against the fp64 oracle.
 
 Stated tolerances (SURVEY.md §8d asks 1e-3 m / 1e-2 rad per env step on active floes, rasters bit-exact on identical states,
 episode scores statistically indistinguishable over 200 seeded episodes):
