@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=TOTAL_ENVS, help="total envs over all ranks (default: the metric's 65536)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the secondary measurement of the fp32-state build (field fp32_state)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--env", default="ship-ice", choices=["ship-ice", "box-delivery", "area-clearing"],
                     help="ship-ice (default, the BASELINE.json metric); box-delivery (BASELINE config 2: 4096 envs) and area-clearing (config 3: 16384 envs) print secondary lines")
@@ -212,6 +213,7 @@ def run_ours(a):
     first = (np.arange(lo, hi) % N_LAYOUTS).astype(np.int32)
     env = ShipIceVecEnv(num_envs=E, cfg={"concentration": CONC}, layouts=packed, device=local, auto_reset=True, first_trial=first)
     env.check_status = False
+    state_bytes = env.env_bytes()
     n_floes = packed.n_floes[first].astype(np.float64)
     sum_v = np.array([packed.n_verts[l, : packed.n_floes[l]].sum() for l in range(N_LAYOUTS)], dtype=np.float64)[first]
     # algorithmic bytes per env step (SURVEY.md §8d / BASELINE.md §3): B = 56 N + 8 sum(V) + 90 036
@@ -312,6 +314,49 @@ def run_ours(a):
     e2e_value = float(tsum[3]) / e2e_max
     red = metric.reduce()                                                   # NCCL all-reduce of episode-metric sums (only collective)
 
+    # ---- secondary measurement: the fp32-state build of the same sources (libbenchpush_b200_f32.so), same workload and timing
+    # rules; reported next to the headline, which stays the fp64 build (bit-comparable with the oracle)
+    fp32 = None
+    if not a.no_fp32:
+        try:
+            env.close()
+            del env
+            torch.cuda.empty_cache()
+            env32 = ShipIceVecEnv(num_envs=E, cfg={"concentration": CONC}, layouts=packed, device=local, auto_reset=True, first_trial=first, precision="fp32")
+            env32.check_status = False
+            env32.reset()
+            g32 = torch.Generator(device=dev); g32.manual_seed(1234 + rank)
+            if a.desync > 1:
+                for r in range(a.desync - 1):
+                    env32.step_async_nocheck((torch.rand(E, generator=g32, device=dev) * 2 - 1).float(), mask=(phase > r))
+            resets32 = torch.zeros(total + 1, dtype=torch.int64, device=dev)
+            for k in range(a.warmup):
+                env32.step_async_nocheck(actions[k])
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for k in range(a.warmup, total):
+                env32.step_async_nocheck(actions[k])
+                resets32[k + 1] = env32._terminated.sum()
+            f1.record()
+            barrier()
+            ms32 = f0.elapsed_time(f1)
+            steps32 = E * a.steps - int(resets32[a.warmup: total].sum().item())
+            t32 = torch.tensor([ms32, float(steps32)], dtype=torch.float64, device=dev)
+            if world > 1:
+                m32 = t32.clone(); dist.all_reduce(m32, op=dist.ReduceOp.MAX)
+                s32 = t32.clone(); dist.all_reduce(s32, op=dist.ReduceOp.SUM)
+            else:
+                m32, s32 = t32, t32
+            fp32 = {"value": float(s32[1]) / (float(m32[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(m32[0]) / a.steps, "dtype": "f32 body state / contacts / solver, f64 motion bounds / work / outputs",
+                    "env_steps_timed": int(s32[1]), "env_bytes": int(env32.env_bytes()),
+                    "parity": "tolerance (tests/test_gpu_fp32.py): <= 1e-3 m / 1e-2 rad per env step vs the fp64 oracle, rasters bit-exact on the state, 200 seeded episodes statistically indistinguishable"}
+            env32.close()
+        except Exception as ex:
+            fp32 = {"value": None, "error": repr(ex)}
+            if world > 1:
+                raise
+
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         try:
@@ -347,7 +392,7 @@ def run_ours(a):
             "config": {"workload": "ship-ice-v0 concentration 0.5 (BASELINE config 5), %d envs total (%d per GPU), 400 substeps/step, "
                                    "4x150x150 u8 obs, U(-1,1) actions, next-step auto reset" % (a.envs, E),
                        "layouts": "%d synthetic seeded ice fields (benchpush_b200.layouts.generate_ice_field, seed 99), mean %.0f floes" % (N_LAYOUTS, float(n_floes.mean())),
-                       "l2": "inputs_exceed_l2 (per-env state %.2f MB x %d envs per GPU)" % (env.env_bytes() / 1e6, E),
+                       "l2": "inputs_exceed_l2 (per-env state %.2f MB x %d envs per GPU)" % (state_bytes / 1e6, E),
                        "episode_phase": "steady state: env g advanced (g mod %d) steps before the warm-up, auto reset inside the timed region" % a.desync if a.desync > 1 else "all envs start at reset",
                        "env_steps_timed": int(tsum[2]), "resets_timed": n_resets, "env_status_bits": int(tmax[7])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -364,6 +409,7 @@ def run_ours(a):
                             "the 4x150x150 u8 images are rendered into the env's device tensor for a policy on the GPU and not copied"},
             "gpu_launches": int(tsum[6]),
             "episode_metrics": red,
+            "fp32_state": fp32,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
