@@ -23,22 +23,25 @@ struct StepOut {
 };
 
 // geometry/polygon.py:25-41 on the world-space hull vertices of body b (np.roll(y, 1)[i] = y[i-1]).
-BP_DEVNI void area_centroid_abs(const real* wv, int n, real* area, real* cx, real* cy) {
-    real s1 = RC(0.0), s2 = RC(0.0);
+// Always accumulated in double (also in the fp32-state build): the shoelace sums cancel from ~1e3 m^2 down to a floe area
+// below 1 m^2, and the work term differences centroids that move by millimetres per step.
+BP_DEVNI void area_centroid_abs(const real* wv, int n, double* area, double* cx, double* cy) {
+    double s1 = 0.0, s2 = 0.0;
     for (int i = 0; i < n; i++) {
         int j = (i == 0) ? n - 1 : i - 1;
-        s1 += wv[2 * i] * wv[2 * j + 1];
-        s2 += wv[2 * i + 1] * wv[2 * j];
+        s1 += (double)wv[2 * i] * (double)wv[2 * j + 1];
+        s2 += (double)wv[2 * i + 1] * (double)wv[2 * j];
     }
-    real A = RC(0.5) * fabs(s1 - s2);
-    real sx = RC(0.0), sy = RC(0.0);
+    double A = 0.5 * fabs(s1 - s2);
+    double sx = 0.0, sy = 0.0;
     for (int i = 0; i < n; i++) {
         int j = (i == 0) ? n - 1 : i - 1;
-        real u = wv[2 * i] * wv[2 * j + 1] - wv[2 * j] * wv[2 * i + 1];
-        sx += (wv[2 * i] + wv[2 * j]) * u;
-        sy += (wv[2 * i + 1] + wv[2 * j + 1]) * u;
+        double xi = wv[2 * i], yi = wv[2 * i + 1], xj = wv[2 * j], yj = wv[2 * j + 1];
+        double u = xi * yj - xj * yi;
+        sx += (xi + xj) * u;
+        sy += (yi + yj) * u;
     }
-    real k = RC(1.0) / (RC(6.0) * A);
+    double k = 1.0 / (6.0 * A);
     *area = A; *cx = fabs(k * sx); *cy = fabs(k * sy);
 }
 
@@ -183,17 +186,17 @@ BP_DEV int shipice_substep_checks(const EnvView& ev, const LayoutView& L, const 
 // total_work_done(prev_obs, updated) (evaluation/metrics.py:96-126):
 // work = sum_i area(a_i) * || |c(a_i)| - |c(b_i)| || over the movable polygons in creation order; only
 // bodies that moved this step can contribute.  Warp-cooperative; the sum is returned on lane 0.
-BP_DEVNI real step_work(const EnvView& ev, const LayoutView& L) {
+BP_DEVNI double step_work(const EnvView& ev, const LayoutView& L) {
     EnvScal* sc = ev.sc;
     const int lane = bp_lane();
     int na = sc->n_awake;
     for (int k = lane; k < na; k += BP_NL) {
         int b = ev.awake[k];
-        real w = RC(0.0);
+        double w = 0.0;
         if (body_dynamic(L, b) && ev.moved_step[b]) {
-            real A, cx, cy;
+            double A, cx, cy;
             area_centroid_abs(ev.wv + (size_t)b * VMAX * 2, L.nv[b], &A, &cx, &cy);
-            real dx = ev.cenx[b] - cx, dy = ev.ceny[b] - cy;
+            double dx = ev.cenx[b] - cx, dy = ev.ceny[b] - cy;
             w = sqrt(dx * dx + dy * dy) * ev.area[b];
             ev.cenx[b] = cx; ev.ceny[b] = cy; ev.area[b] = A;
             ev.moved_step[b] = 0;

@@ -142,7 +142,7 @@ struct EnvView {
     BBox* bb;                                                                // [NB] current AABB
     BBox* b0;                                                                // [NB] AABB at neighbour-list build
     real* wv;                                                              // [NB][VMAX][2] world vertices
-    real *cenx, *ceny, *area, *tmp;                                        // [NB] |centroid|, area at last env step; scratch
+    double *cenx, *ceny, *area, *tmp;                                       // [NB] |centroid|, area at last env step; scratch
     int* awake;                                                              // [NB]
     unsigned char *is_awake, *moved, *moved_step, *act;                      // [NB]
     unsigned char* mvrb;                                                     // [NB] AABB changed since the last neighbour-list build
@@ -177,7 +177,7 @@ BP_HD EnvView carve_env(char* base, const Dims& d, size_t* total) {
     TAKE(v.slot, SlotRec, Lm * sizeof(SlotRec))
     TAKE(v.bb, BBox, NB * sizeof(BBox)) TAKE(v.b0, BBox, NB * sizeof(BBox))
     TAKE(v.wv, real, NB * VMAX * 2 * sizeof(real))
-    TAKE(v.cenx, real, NB * sizeof(real)) TAKE(v.ceny, real, NB * sizeof(real)) TAKE(v.area, real, NB * sizeof(real)) TAKE(v.tmp, real, NB * sizeof(real))
+    TAKE(v.cenx, double, NB * sizeof(double)) TAKE(v.ceny, double, NB * sizeof(double)) TAKE(v.area, double, NB * sizeof(double)) TAKE(v.tmp, double, NB * sizeof(double))
     TAKE(v.awake, int, NB * 4)
     TAKE(v.is_awake, unsigned char, NB) TAKE(v.moved, unsigned char, NB)
     TAKE(v.moved_step, unsigned char, NB) TAKE(v.act, unsigned char, NB)
@@ -202,7 +202,7 @@ static inline size_t env_mem_size(const Dims& d) { size_t t = 0; carve_env((char
 // touches (view_at is inlined and dead fields disappear), instead of re-deriving the whole carve.
 #define BP_ENV_FIELD_LIST(X)                                                                         \
     X(0, sc, EnvScal) X(1, body, BodyRec) X(2, slot, SlotRec) X(3, bb, BBox) X(4, b0, BBox) X(5, wv, real)      \
-    X(6, cenx, real) X(7, ceny, real) X(8, area, real) X(9, tmp, real) X(10, awake, int)                 \
+    X(6, cenx, double) X(7, ceny, double) X(8, area, double) X(9, tmp, double) X(10, awake, int)                 \
     X(11, is_awake, unsigned char) X(12, moved, unsigned char) X(13, moved_step, unsigned char)                  \
     X(14, act, unsigned char) X(15, colmask, unsigned long long) X(16, pair[0], PairRec) X(17, pair[1], PairRec) \
     X(18, adj_start, int) X(19, adj, int) X(20, deg, int) X(21, queue, int) X(22, queue0, int) X(23, apairs, int) \

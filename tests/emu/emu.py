@@ -123,6 +123,11 @@ class Emu:
         n = self.L.emu_centroid_cache(self.h, C.c_int(env), _dp(out))
         return out[:2 * n]
 
+    def world_verts(self, env, b):
+        out = np.zeros(2 * 64, dtype=np.float64)
+        n = self.L.emu_world_verts(self.h, C.c_int(env), C.c_int(b), _dp(out))
+        return out[:2 * n].reshape(n, 2).copy()
+
     def spfa(self, m, source):
         m = np.ascontiguousarray(np.asarray(m).astype(bool).astype(np.uint8))
         H, W = m.shape

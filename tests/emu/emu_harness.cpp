@@ -206,6 +206,15 @@ int emu_centroid_cache(void* h, int env, double* out) {
     for (int b = 0; b < ev.sc->robot; b++) if (body_dynamic(L, b)) { out[2 * n] = ev.cenx[b]; out[2 * n + 1] = ev.ceny[b]; n++; }
     return n;
 }
+// world-space hull vertices of body b as the kernels hold them (ev.wv), widened to double; returns the vertex count
+int emu_world_verts(void* h, int env, int b, double* out) {
+    Emu* e = (Emu*)h;
+    EnvView ev = make_view(e->mem.data() + e->env_bytes * env, e->d);
+    LayoutView L = layout_view(e->T, e->d, ev.sc->layout);
+    int n = L.nv[b];
+    for (int i = 0; i < 2 * n; i++) out[i] = ev.wv[(size_t)b * VMAX * 2 + i];
+    return n;
+}
 void emu_spfa(const uint8_t* map, int H, int W, int si, int sj, float* dist, int32_t* parents) {
     std::vector<int> scratch((size_t)3 * H * W);
     SpfaShared S;

@@ -61,7 +61,7 @@ def test_fp32_transitions_within_tolerance_and_rasters_exact(name, golden_layout
         assert np.array_equal(obs[0].cpu().numpy(), want), int((obs[0].cpu().numpy() != want).sum())
         # work of the step recomputed in fp64 from the env's own before / after vertices
         w = total_work_done(prev, cur)
-        np.testing.assert_allclose(-float(info["collision reward"][0]), w, rtol=2e-3, atol=2e-5)
+        np.testing.assert_allclose(-float(info["collision reward"][0]), w, rtol=1e-7, atol=1e-12)
         prev = cur
     env.close()
 

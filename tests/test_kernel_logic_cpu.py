@@ -6,7 +6,7 @@ import pytest
 from tests.conftest import FIXTURES, SHIP_VERTS, fixture_conc
 from benchpush_b200.layouts import generate_experiment, pack_trials, unpack_trials
 from oracle import cpo
-from oracle.ship_ice_oracle import ShipIceOracleEnv
+from oracle.ship_ice_oracle import ShipIceOracleEnv, total_work_done
 from tests.emu.emu import Emu
 
 
@@ -191,6 +191,8 @@ def test_fp32_build_of_the_kernel_sources_stays_within_tolerance(golden_layouts,
     for e in (A, B, C_):
         e.reset(0, 0)
     rng = np.random.default_rng(1)
+    nfl = len(ora.space.state()) - 1
+    prev = [A.world_verts(0, b) for b in range(nfl)]
     for k in range(5):
         a = np.float32(rng.uniform(-1, 1))
         A.step(0, float(a)); B.step_batch(0, np.array([a], dtype=np.float32)); C_.step_resident(0, np.array([a], dtype=np.float32))
@@ -199,3 +201,11 @@ def test_fp32_build_of_the_kernel_sources_stays_within_tolerance(golden_layouts,
         assert np.array_equal(g, B.bodies(0, 0)) and np.array_equal(g, C_.bodies(0, 0))
         lim = 1e-3 if k == 0 else 2e-3
         assert np.abs(g[:, :2] - o[:, :2]).max() <= lim and np.abs(g[:, 2] - o[:, 2]).max() <= 1e-2, k
+        # the work term is accumulated in double from the fp32 vertices (shipice_env.cuh area_centroid_abs): it equals the
+        # fp64 restatement of metrics.py:96-126 on the kernel's own before / after vertices
+        cur = [A.world_verts(0, b) for b in range(nfl)]
+        w = total_work_done(prev, cur)
+        assert w > 0
+        for e in (A, B, C_):
+            np.testing.assert_allclose(-e.out(0)["collision_reward"], w, rtol=1e-7, atol=1e-12)
+        prev = cur

@@ -56,3 +56,14 @@ for f, v in byf.most_common(20):
 print("\ntop lines by samples")
 for (f, l), v in sl.most_common(top):
     print("%-18s %-22s %7.2f%% samples %7.2f%% inst" % (f, "%s:%s" % l if l else "?", 100 * v / max(tot_s, 1), 100 * byl[(f, l)] / tot_i))
+# optional: absolute per-line counts for one file range:  ... topN file.cuh lo hi
+if len(sys.argv) > 7:
+    fn, lo, hi = sys.argv[5], int(sys.argv[6]), int(sys.argv[7])
+    agg = collections.Counter(); th = collections.Counter(); ns = collections.Counter()
+    for r in data:
+        off = int(r[0], 16) - base
+        f, l, txt = fmap.get(off, ("?", None, ""))
+        if l and l[0] == fn and lo <= l[1] <= hi:
+            agg[l[1]] += int(r[ci["Instructions Executed"]] or 0); th[l[1]] += int(r[ci["Thread Instructions Executed"]] or 0); ns[l[1]] += 1
+    for l in sorted(agg):
+        print("%s:%d  warp-inst %d  (%d SASS)  per-SASS %.0f  avg thr %.1f" % (fn, l, agg[l], ns[l], agg[l] / ns[l], th[l] / max(agg[l], 1)))
