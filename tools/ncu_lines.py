@@ -67,3 +67,11 @@ if len(sys.argv) > 7:
             agg[l[1]] += int(r[ci["Instructions Executed"]] or 0); th[l[1]] += int(r[ci["Thread Instructions Executed"]] or 0); ns[l[1]] += 1
     for l in sorted(agg):
         print("%s:%d  warp-inst %d  (%d SASS)  per-SASS %.0f  avg thr %.1f" % (fn, l, agg[l], ns[l], agg[l] / ns[l], th[l] / max(agg[l], 1)))
+# optional: top lines by instruction count inside one function:  ... topN FUNC
+if len(sys.argv) == 6:
+    fn = sys.argv[5]
+    items = [(v, l) for (f, l), v in byl.items() if f == fn]
+    items.sort(reverse=True)
+    print("\ntop lines by inst in", fn)
+    for v, l in items[:top]:
+        print("%-24s %6.2f%% inst %6.2f%% samples" % ("%s:%s" % l if l else "?", 100 * v / tot_i, 100 * sl[(fn, l)] / max(tot_s, 1)))
