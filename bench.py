@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--env", default="ship-ice", choices=["ship-ice", "box-delivery", "area-clearing"],
                     help="ship-ice (default, the BASELINE.json metric); box-delivery (BASELINE config 2: 4096 envs) and area-clearing (config 3: 16384 envs) print secondary lines")
+    ap.add_argument("--obstacle-config", default="small_empty", choices=["small_empty", "small_columns", "large_columns", "large_divider"],
+                    help="box-delivery room (cfg.env.obstacle_config); the column / divider rooms use a pool of --rooms layouts with their own maps")
+    ap.add_argument("--rooms", type=int, default=64)
+    ap.add_argument("--exact-parents", action="store_true", help="box-delivery / area-clearing: reference-order spfa parents (slow parity mode)")
     ap.add_argument("--desync", type=int, default=34,
                     help="spread the episode phases before the warm-up: env e is advanced (global id mod DESYNC) steps (1 = all envs start at reset)")
     return ap.parse_args()
@@ -422,6 +426,10 @@ BD_METRIC = "env-steps/sec box-delivery-v0 @4096 envs"
 BD_CFG = {"agent": {"action_type": "heading"}}
 
 
+def bd_cfg(obstacle_config):
+    return {"agent": {"action_type": "heading"}, "env": {"obstacle_config": obstacle_config}}
+
+
 def _bd_cpu_worker(args):
     idx, seed, budget, nsteps = args[:4]
     if len(args) > 4 and args[4] == "area-clearing":
@@ -430,7 +438,8 @@ def _bd_cpu_worker(args):
         env = AreaClearingOracleEnv(layouts=[ac_layout(random.Random(1 + idx))])
     else:
         from oracle.box_delivery_oracle import BoxDeliveryOracleEnv, sample_layout
-        env = BoxDeliveryOracleEnv(cfg=BD_CFG, layouts=[sample_layout(np.random.RandomState(42 + idx))])
+        cfg = bd_cfg(args[5] if len(args) > 5 else "small_empty")
+        env = BoxDeliveryOracleEnv(cfg=cfg, layouts=[sample_layout(np.random.RandomState(42 + idx), cfg)])
     env.reset()
     rng = np.random.default_rng(seed)
     t0 = time.perf_counter()
@@ -445,11 +454,11 @@ def _bd_cpu_worker(args):
     return n, time.perf_counter() - t0
 
 
-def _bd_cpu(budget_s, nsteps=None, kind="box-delivery"):
+def _bd_cpu(budget_s, nsteps=None, kind="box-delivery", oc="small_empty"):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     with mp.get_context("spawn").Pool(cores) as pool:
-        res = pool.map(_bd_cpu_worker, [(i, 1000 + i, budget_s, nsteps, kind) for i in range(cores)])
+        res = pool.map(_bd_cpu_worker, [(i, 1000 + i, budget_s, nsteps, kind, oc) for i in range(cores)])
     steps = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
     return steps / wall, cores, steps, wall
@@ -460,14 +469,17 @@ def run_boxdel(a):
     One step = one step() of every env: action decode, position-control chain, ~800 physics substeps, rewards, 224x224x4 obs."""
     area = a.env == "area-clearing"
     n_envs = a.envs if a.envs != TOTAL_ENVS else (16384 if area else 4096)
-    metric = ("env-steps/sec area-clearing-v0 @%d envs" % n_envs) if area else BD_METRIC
+    oc = a.obstacle_config
+    metric = ("env-steps/sec area-clearing-v0 @%d envs" % n_envs) if area else ("env-steps/sec box-delivery-v0 @%d envs" % n_envs)
     wl = ("area-clearing-v0 (BASELINE config 3): clear_env, 10 boxes of 1 m, heading actions U(-1,1)" if area
-          else "box-delivery-v0 (BASELINE config 2): small_empty room, 10 boxes, heading actions U(-1,1)")
+          else "box-delivery-v0 (BASELINE config 2): %s room, %d boxes, heading actions U(-1,1)%s" % (
+              oc, 10 if oc.startswith("small") else 20,
+              "" if oc.endswith("_empty") else ", a pool of %d rooms, %s spfa parents" % (a.rooms, "reference-order" if a.exact_parents else "deterministic")))
     if a.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        _bd_cpu(0.0, max(a.warmup, 1), a.env)
-        v, cores, n, wall = _bd_cpu(0.0, a.steps, a.env)
+        _bd_cpu(0.0, max(a.warmup, 1), a.env, oc)
+        v, cores, n, wall = _bd_cpu(0.0, a.steps, a.env, oc)
         print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": {"workload": wl + "; one env per host core",
@@ -479,7 +491,8 @@ def run_boxdel(a):
     from benchpush_b200.envs import AreaClearingVecEnv, BoxDeliveryVecEnv
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    env = AreaClearingVecEnv(num_envs=n_envs, device=0) if area else BoxDeliveryVecEnv(num_envs=n_envs, cfg=BD_CFG, device=0)
+    env = AreaClearingVecEnv(num_envs=n_envs, device=0) if area else BoxDeliveryVecEnv(num_envs=n_envs, cfg=bd_cfg(oc), device=0, max_rooms=a.rooms,
+                                                                                         exact_spfa_parents=a.exact_parents)
     env.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(1234)
     total = a.warmup + a.steps
@@ -514,7 +527,7 @@ def run_boxdel(a):
     achieved = alg * n_envs / (move_ms * 1e-3) / 1e9 if move_ms > 0 else 0.0
     cpu = None
     if not a.no_cpu_baseline:
-        v, cores, n, wall = _bd_cpu(a.cpu_seconds, None, a.env)
+        v, cores, n, wall = _bd_cpu(a.cpu_seconds, None, a.env, oc)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle (restated reference): one env per core on %d cores, %d env steps in %.1f s" % (cores, n, wall)}
     print(json.dumps({

@@ -134,6 +134,8 @@ def lib(precision: str = "fp64"):
         L.bp_maze_get_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bp_spfa_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bp_spfa_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.bp_spfa_batch_exact.argtypes = L.bp_spfa_batch.argtypes
+        L.bp_spfa_batch_exact_host.argtypes = L.bp_spfa_batch_host.argtypes
         _LIBS[precision] = L
         if precision == "fp64":
             _LIB = L
@@ -147,10 +149,10 @@ EXPORTS = [
     "bp_maze_state_bytes", "bp_maze_get_state", "bp_maze_set_state", "bp_maze_set_bodies",
     "bp_shipice_get_obstacles", "bp_shipice_get_bodies", "bp_shipice_get_counters", "bp_shipice_env_bytes", "bp_shipice_low_dim", "bp_maze_low_dim", "bp_shipice_obs_global", "bp_shipice_obs_global_shape", "bp_shipice_set_start_poses", "bp_maze_set_start_poses",
     "bp_shipice_set_profiling", "bp_shipice_get_kernel_ms",
-    "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host",
+    "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host", "bp_spfa_batch_exact", "bp_spfa_batch_exact_host",
     "bp_maze_default_config", "bp_maze_create", "bp_maze_destroy", "bp_maze_load_layouts", "bp_maze_reset", "bp_maze_step",
     "bp_maze_step_masked", "bp_maze_step_host", "bp_maze_get_obstacles", "bp_maze_get_bodies", "bp_maze_get_maps",
-    "bp_boxdel_default_config", "bp_boxdel_create", "bp_boxdel_destroy", "bp_boxdel_load", "bp_boxdel_reset", "bp_boxdel_step",
+    "bp_boxdel_default_config", "bp_boxdel_create", "bp_boxdel_destroy", "bp_boxdel_load", "bp_boxdel_load_rooms", "bp_boxdel_reset", "bp_boxdel_step",
     "bp_boxdel_step_host", "bp_boxdel_get_bodies", "bp_boxdel_get_step_debug", "bp_boxdel_launch_count", "bp_boxdel_env_bytes", "bp_boxdel_set_profiling", "bp_boxdel_get_kernel_ms",
 ]
 

@@ -11,15 +11,15 @@ using namespace bp::bd;
 #endif
 
 // ------------------------------------------------------------------------------------------------ kernels
-__global__ void k_bd_init_statics(BdConst* C) {
+__global__ void k_bd_init_statics(BdStatics* rooms, int n_static) {
     int k = threadIdx.x;
-    if (k < C->P.n_static) bd_init_static(C->S, k);
+    if (k < n_static) bd_init_static(rooms[blockIdx.x], k);
 }
 
 // thread per cell: clears *flag when a free cell is not visible from the receptacle cell
 __global__ void k_bd_visibility(const BdConst* C, int* flag) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < C->P.H * C->P.W && !bd_cell_visible(*C, v)) atomicAnd(flag, 0);
+    if (v < C->P.H * C->P.W && !bd_cell_visible(*C, blockIdx.y, v)) atomicAnd(flag, 0);
 }
 
 // warp per env
@@ -57,8 +57,9 @@ __global__ void __launch_bounds__(256) k_bd_dist(const BdConst* C, const uint8_t
                 if (it >= total) break;
                 int env = it / per_env, k = it - env * per_env;
                 if (mask && !mask[env]) continue;
-                const BdEnv* E = bd_env(*C, env);
-                if (k < C->P.NB ? (E->body[1 + k].alive == 1 && !C->P.recept_visible) : (phase == 0 && E->need_spfa)) break;
+                BdEnv* E = bd_env(*C, env);
+                if (k < C->P.NB) { if (E->body[1 + k].alive == 1 && !C->P.recept_visible && !bd_box_dist_cached(E, k, phase, true)) break; }
+                else if (phase == 0 && E->need_spfa) break;
             }
             s_item = it;
         }
@@ -167,7 +168,7 @@ struct bp_boxdel {
     bp_boxdel_config cfg;
     BdConst hC;                      // host copy (device pointers inside)
     BdConst* dC = nullptr;
-    BdLayout* d_layouts = nullptr; short* d_pa = nullptr; short* d_pb = nullptr;
+    BdLayout* d_layouts = nullptr; BdStatics* d_rooms = nullptr; short* d_pa = nullptr; short* d_pb = nullptr;
     uint8_t *d_cspace = nullptr, *d_thin = nullptr, *d_small = nullptr, *d_rchan = nullptr; int32_t* d_closest = nullptr; float* d_recept = nullptr;
     char* d_envs = nullptr; int* d_scratch = nullptr; int* d_counter = nullptr; int n_blocks = 0;
     bool loaded = false;
@@ -220,7 +221,7 @@ int bp_boxdel_create(const bp_boxdel_config* cfg, bp_boxdel_t** out) {
 int bp_boxdel_destroy(bp_boxdel_t* h) {
     if (!h) return BP_OK;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->dC); cudaFree(h->d_layouts); cudaFree(h->d_pa); cudaFree(h->d_pb); cudaFree(h->d_cspace); cudaFree(h->d_thin); cudaFree(h->d_small);
+    cudaFree(h->dC); cudaFree(h->d_layouts); cudaFree(h->d_rooms); cudaFree(h->d_pa); cudaFree(h->d_pb); cudaFree(h->d_cspace); cudaFree(h->d_thin); cudaFree(h->d_small);
     cudaFree(h->d_rchan); cudaFree(h->d_closest); cudaFree(h->d_recept); cudaFree(h->d_envs); cudaFree(h->d_scratch); cudaFree(h->d_counter); cudaFree(h->d_mv); if (h->h_flag) cudaFreeHost(h->h_flag);
     delete h;
     return BP_OK;
@@ -235,15 +236,25 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
                    int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
                    int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
                    const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map) {
+    return bp_boxdel_load_rooms(h, n_layouts, starts, n_boxes, boxes, 1, nullptr, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype,
+                                H, W, cspace, cspace_thin, closest, small_free, robot_chan, ch3_map);
+}
+
+// As bp_boxdel_load with a leading room axis on every room-dependent array (include/benchpush_b200.h).
+int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                         int32_t n_rooms, const int32_t* layout_room,
+                         int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                         int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
+                         const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map) {
     if (!h || !starts || !n_boxes || !boxes || !st_nv || !st_verts || !st_pose || !st_rad || !st_ctype || !cspace || !cspace_thin || !closest || !small_free || !robot_chan)
         return fail(BP_ERR_INVALID, "null argument");
     if (h->loaded) return fail(BP_ERR_STATE, "already loaded");
-    if (n_layouts <= 0 || n_static <= 0 || n_static > MAXSTAT) return fail(BP_ERR_INVALID, "n_layouts / n_static out of range");
+    if (n_layouts <= 0 || n_static <= 0 || n_static > MAXSTAT || n_rooms <= 0) return fail(BP_ERR_INVALID, "n_layouts / n_static / n_rooms out of range");
     const bp_boxdel_config& c = h->cfg;
     CUDA_TRY(cudaSetDevice(c.device));
     BdHost HB;
     {
-        std::string err = bd_host_build(HB, c, n_layouts, starts, n_boxes, boxes, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype, H, W);
+        std::string err = bd_host_build(HB, c, n_layouts, starts, n_boxes, boxes, n_rooms, layout_room, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype, H, W);
         if (!err.empty()) return fail(BP_ERR_INVALID, err);
     }
     h->hC = HB.K;
@@ -251,20 +262,32 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
     BdParams& P = K.P;
     std::vector<BdLayout>& LY = HB.LY;
     // ---- upload
-    const size_t nv = (size_t)H * W;
+    const size_t nv = (size_t)H * W, R = (size_t)n_rooms;
     std::vector<short>& pa = HB.pa; std::vector<short>& pb = HB.pb;
     CUDA_TRY(cudaMalloc((void**)&h->d_layouts, sizeof(BdLayout) * n_layouts));
     CUDA_TRY(cudaMemcpy(h->d_layouts, LY.data(), sizeof(BdLayout) * n_layouts, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void**)&h->d_pa, 2 * P.n_slots)); CUDA_TRY(cudaMalloc((void**)&h->d_pb, 2 * P.n_slots));
     CUDA_TRY(cudaMemcpy(h->d_pa, pa.data(), 2 * P.n_slots, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_pb, pb.data(), 2 * P.n_slots, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc((void**)&h->d_cspace, nv)); CUDA_TRY(cudaMemcpy(h->d_cspace, cspace, nv, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc((void**)&h->d_thin, nv)); CUDA_TRY(cudaMemcpy(h->d_thin, cspace_thin, nv, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc((void**)&h->d_closest, nv * 8)); CUDA_TRY(cudaMemcpy(h->d_closest, closest, nv * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc((void**)&h->d_small, (size_t)P.SMALL * P.SMALL)); CUDA_TRY(cudaMemcpy(h->d_small, small_free, (size_t)P.SMALL * P.SMALL, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_cspace, R * nv)); CUDA_TRY(cudaMemcpy(h->d_cspace, cspace, R * nv, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_thin, R * nv)); CUDA_TRY(cudaMemcpy(h->d_thin, cspace_thin, R * nv, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_closest, R * nv * 8)); CUDA_TRY(cudaMemcpy(h->d_closest, closest, R * nv * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_small, R * P.SMALL * P.SMALL)); CUDA_TRY(cudaMemcpy(h->d_small, small_free, R * P.SMALL * P.SMALL, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void**)&h->d_rchan, (size_t)P.LW * P.LW)); CUDA_TRY(cudaMemcpy(h->d_rchan, robot_chan, (size_t)P.LW * P.LW, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc((void**)&h->d_recept, nv * 4));
+    CUDA_TRY(cudaMalloc((void**)&h->d_recept, R * nv * 4));
+    // receptacle cell of every room (closest valid cell of the receptacle position)
+    {
+        int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
+        pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
+        for (size_t r = 0; r < R; r++) {
+            const int32_t* cl = closest + r * 2 * nv;
+            HB.RM[r].recept_ci = cl[(size_t)pi * W + pj]; HB.RM[r].recept_cj = cl[nv + (size_t)pi * W + pj];
+        }
+    }
+    CUDA_TRY(cudaMalloc((void**)&h->d_rooms, sizeof(BdStatics) * R));
+    CUDA_TRY(cudaMemcpy(h->d_rooms, HB.RM.data(), sizeof(BdStatics) * R, cudaMemcpyHostToDevice));
     K.layouts = h->d_layouts; K.n_layouts = n_layouts; K.n_envs = c.n_envs; K.pair_a = h->d_pa; K.pair_b = h->d_pb;
+    K.rooms = h->d_rooms; K.n_rooms = n_rooms;
     K.cspace = h->d_cspace; K.cspace_thin = h->d_thin; K.closest = h->d_closest; K.small_free = h->d_small; K.robot_chan = h->d_rchan; K.ch3_map = h->d_recept;
     K.env_bytes = bd_env_bytes(P.n_slots);
     CUDA_TRY(cudaMalloc((void**)&h->d_envs, K.env_bytes * c.n_envs));
@@ -278,46 +301,48 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
     CUDA_TRY(cudaMallocHost((void**)&h->h_flag, 64));
     CUDA_TRY(cudaMalloc((void**)&h->dC, sizeof(BdConst)));
     CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdConst), cudaMemcpyHostToDevice));
-    k_bd_init_statics<<<1, 32>>>(h->dC);
+    k_bd_init_statics<<<n_rooms, 32>>>(h->d_rooms, P.n_static);
     CUDA_TRY(cudaGetLastError());
-    // fourth observation channel, static for the handle: the caller's map (area-clearing goal-point map), or the scaled
+    // fourth observation channel, static per room: the caller's map (area-clearing goal-point map), or the scaled
     // receptacle-source distance field (the reference recomputes it every step, box_delivery_env.py:1115-1129)
     if (ch3_map) {
-        CUDA_TRY(cudaMemcpy(h->d_recept, ch3_map, nv * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d_recept, ch3_map, R * nv * 4, cudaMemcpyHostToDevice));
     } else {
         if (c.env_kind != 0) return fail(BP_ERR_INVALID, "area-clearing needs the goal-point map (ch3_map)");
-        int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
-        pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
-        int32_t src[2] = {closest[(size_t)pi * W + pj], closest[nv + (size_t)pi * W + pj]};
+        std::vector<int32_t> src(2 * R);
+        for (size_t r = 0; r < R; r++) { src[2 * r] = HB.RM[r].recept_ci; src[2 * r + 1] = HB.RM[r].recept_cj; }
         int32_t* d_src = nullptr; int32_t* d_par = nullptr;
-        CUDA_TRY(cudaMalloc((void**)&d_src, 8)); CUDA_TRY(cudaMalloc((void**)&d_par, nv * 4));
-        CUDA_TRY(cudaMemcpy(d_src, src, 8, cudaMemcpyHostToDevice));
-        int rc = bp_spfa_batch(h->d_cspace, d_src, 1, H, W, h->d_recept, d_par, nullptr);
-        cudaError_t e = cudaDeviceSynchronize();
+        // one spfa solve per room, in chunks (the parents are not needed but the solver writes them)
+        const int chunk = (int)(R < 64 ? R : 64);
+        CUDA_TRY(cudaMalloc((void**)&d_src, 8 * R)); CUDA_TRY(cudaMalloc((void**)&d_par, (size_t)chunk * nv * 4));
+        CUDA_TRY(cudaMemcpy(d_src, src.data(), 8 * R, cudaMemcpyHostToDevice));
+        int rc = BP_OK; cudaError_t e = cudaSuccess;
+        for (size_t r0 = 0; r0 < R && rc == BP_OK && e == cudaSuccess; r0 += chunk) {
+            int nb = (int)((R - r0) < (size_t)chunk ? (R - r0) : chunk);
+            rc = bp_spfa_batch(h->d_cspace + r0 * nv, d_src + 2 * r0, nb, H, W, h->d_recept + r0 * nv, d_par, nullptr);
+            e = cudaDeviceSynchronize();
+        }
         cudaFree(d_src); cudaFree(d_par);
         if (rc != BP_OK) return rc;
         if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("receptacle spfa: ") + cudaGetErrorString(e));
-        std::vector<float> tmp(nv);
-        CUDA_TRY(cudaMemcpy(tmp.data(), h->d_recept, nv * 4, cudaMemcpyDeviceToHost));
-        bd_scale_receptacle_map(P, tmp.data(), nv);
-        CUDA_TRY(cudaMemcpy(h->d_recept, tmp.data(), nv * 4, cudaMemcpyHostToDevice));
+        std::vector<float> tmp(R * nv);
+        CUDA_TRY(cudaMemcpy(tmp.data(), h->d_recept, R * nv * 4, cudaMemcpyDeviceToHost));
+        bd_scale_receptacle_map(P, tmp.data(), R * nv);
+        CUDA_TRY(cudaMemcpy(h->d_recept, tmp.data(), R * nv * 4, cudaMemcpyHostToDevice));
     }
-    // can the receptacle cell see the whole free space?  (BdParams::recept_visible)
+    // can the receptacle cell see the whole free space of every room?  (BdParams::recept_visible)
     {
-        int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
-        pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
-        P.recept_ci = closest[(size_t)pi * W + pj]; P.recept_cj = closest[nv + (size_t)pi * W + pj]; P.recept_visible = 0;
+        P.recept_visible = 0;
         CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdParams), cudaMemcpyHostToDevice));      // P is the first member of BdConst
         int one = 1;
         CUDA_TRY(cudaMemcpy(h->d_counter, &one, 4, cudaMemcpyHostToDevice));
-        k_bd_visibility<<<(int)((nv + 255) / 256), 256>>>(h->dC, h->d_counter);
+        k_bd_visibility<<<dim3((unsigned)((nv + 255) / 256), (unsigned)n_rooms), 256>>>(h->dC, h->d_counter);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpy(&one, h->d_counter, 4, cudaMemcpyDeviceToHost));
         P.recept_visible = (one != 0 && !h->cfg.force_box_spfa) ? 1 : 0;
         if (c.env_kind == 1) P.recept_visible = 1;          // no receptacle distances in area-clearing
         CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdParams), cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMemcpy(&K, h->dC, sizeof(BdConst), cudaMemcpyDeviceToHost));     // statics now in world space
     h->loaded = true;
     return BP_OK;
 }

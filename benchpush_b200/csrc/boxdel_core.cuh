@@ -27,7 +27,7 @@ namespace bd {
 
 constexpr int MAXBOX = 20;        // cfg.boxes.num_boxes_large
 constexpr int NROBOT = 6;         // chassis, 4 wheels, front bumper (sim_utils.py:20-76)
-constexpr int MAXSTAT = 16;       // receptacle + 4 walls + 3 corners x 3 triangles = 14 in an empty room
+constexpr int MAXSTAT = 24;       // receptacle + 4 walls + 3 corners x 3 triangles = 14 in an empty room; + <= 7 columns, or a divider + 2 x 3 triangles = 21
 constexpr int SV = 4;             // vertices per shape (rectangles, the bumper trapezoid, corner triangles)
 constexpr int NMOV = NROBOT + MAXBOX;
 constexpr int MAXCAND = 128;      // AABB-overlapping pairs per substep
@@ -61,8 +61,9 @@ struct BdParams {
     // receptacle's cell: then shortest_path(box, receptacle) always prunes to [box, receptacle] whatever the spfa parent
     // chain is (box_delivery_env.py:1243-1250 tests lines from coords[0] = the receptacle cell only while all are free),
     // so shortest_path_distance is the Euclidean distance and needs no spfa solve.  Checked once per handle.
-    int recept_visible;
-    int recept_ci, recept_cj;     // closest valid cell of the receptacle position
+    int recept_visible;           // (AND over the rooms of the handle)
+    int exact_parents;            // 1: paths follow the reference solver's own parent tie-breaks (spfa_serial_parents; slow, for parity runs)
+    int pad_rv;
     // ---- env kind: 0 = box-delivery-v0, 1 = area-clearing-v0 (same control chain and handlers, different constants)
     int kind;
     int step_limit;               // STEP_LIMIT of execute_robot_path: 10000 (box_delivery_env.py:62) / 5000 (area_clearing.py:76)
@@ -104,22 +105,27 @@ struct alignas(16) BdSlot {       // one shape pair of the dense table = cpArbit
 
 struct BdLayout {                 // immutable per layout
     double start[3];
-    int n_boxes, pad;
+    int n_boxes, room;            // room: index of the layout's static shapes / maps (BdConst::rooms)
     double box_init[MAXBOX][3];
     double box_lv[MAXBOX][SV][2], box_ln[MAXBOX][SV][2];
     double box_cog[MAXBOX][2], box_minv[MAXBOX], box_iinv[MAXBOX];
 };
 
-struct BdShapes {                 // immutable per handle: robot shapes (body-local) and static shapes (world)
-    double rb_lv[NROBOT][SV][2], rb_ln[NROBOT][SV][2], rb_rad[NROBOT], rb_e[NROBOT], rb_u[NROBOT];
-    int rb_nv[NROBOT];
-    double rb_foot[SV][2]; int n_foot, pad_foot;     // polygon drawn for the robot in the overhead map (body-local)
+struct BdStatics {                // immutable per ROOM: static shapes (world) + the receptacle's cell in the room's configuration space
     double st_lv[MAXSTAT][SV][2], st_ln[MAXSTAT][SV][2], st_pose[MAXSTAT][3];   // as created (body-local + body pose)
-    alignas(16) double st_v[MAXSTAT][SV][2];                                       // world (filled by bd_init_statics); 128-bit vertex loads
+    alignas(16) double st_v[MAXSTAT][SV][2];                                       // world (filled by bd_init_static); 128-bit vertex loads
     double st_n[MAXSTAT][SV][2], st_p[MAXSTAT][2];
     BBox st_bb[MAXSTAT];
     double st_rad[MAXSTAT], st_e[MAXSTAT], st_u[MAXSTAT];
-    int st_nv[MAXSTAT], st_ctype[MAXSTAT];
+    int st_nv[MAXSTAT], st_ctype[MAXSTAT];           // st_nv == 0: slot not used in this room (fewer columns than the handle's maximum)
+    int recept_ci, recept_cj;                        // closest valid cell of the receptacle position
+    int pad[2];
+};
+
+struct BdShapes {                 // immutable per handle: robot shapes (body-local), box material
+    double rb_lv[NROBOT][SV][2], rb_ln[NROBOT][SV][2], rb_rad[NROBOT], rb_e[NROBOT], rb_u[NROBOT];
+    int rb_nv[NROBOT];
+    double rb_foot[SV][2]; int n_foot, pad_foot;     // polygon drawn for the robot in the overhead map (body-local)
     double box_rad, box_e, box_u;
 };
 
@@ -127,6 +133,8 @@ struct BdSlot;
 struct BdEnvCold {                // per env, global memory only: touched once per substep or once per env step
     double path[MAXWP][3];
     double init_dist[MAXBOX], final_dist[MAXBOX];
+    double dist_key[MAXBOX][2], dist_val[MAXBOX];   // last solved shortest_path_distance(box, receptacle) and the box origin it was solved for
+    unsigned char dist_ok[MAXBOX];
     double prev_boxes[MAXBOX][SV][2];   // CostMap.get_obs_from_poly at the previous env step (work accounting)
     short order[MAXCAND];         // this step's solve list (slot ids), colour-sorted
     short cand[MAXCAND];
@@ -135,7 +143,7 @@ struct BdEnvCold {                // per env, global memory only: touched once p
 };
 struct BdEnv {                    // mutable per env: the HOT header (6.6 KB) — k_bd_move keeps a copy in shared memory for the whole launch
     int layout, episode, t, status, stamp, n_order, robot_hit, inactivity, cum_boxes, done, truncated, n_prev;
-    int cleared_count, pad_c;
+    int cleared_count, room;      // room = layouts[layout].room
     int nc, fast;                 // this substep: candidate pairs; 1 = nothing overlaps and nothing is cached (phases B-D skipped)
     int n_path, move_sign, need_spfa, src_i, src_j, tgt_i, tgt_j, n_live;      // n_live: slots with state != SL_NONE
     long long stat_substeps, stat_cand, stat_arb;
@@ -157,15 +165,23 @@ struct BdConst {
     BdParams P; BdShapes S;
     const BdLayout* layouts; int n_layouts, n_envs;
     const short* pair_a; const short* pair_b;      // [n_slots] shape ids of the dense pair table (a < b)
-    // static maps of the room (box_delivery_env.py:1140-1175), identical for every env of the handle
-    const uint8_t* cspace; const uint8_t* cspace_thin;      // [H][W] 1 = free
-    const int32_t* closest;                                 // [2][H][W] distance_transform_edt indices
-    const uint8_t* small_free;                              // [SMALL][SMALL] 1 = free floor (small_obstacle_map)
+    // rooms: static shapes and maps (box_delivery_env.py:1140-1175).  One room per handle in the obstacle-free configurations;
+    // one per layout when the reference redraws columns / a divider at every reset (box_delivery_env.py:358-471).
+    const BdStatics* rooms; int n_rooms, pad_r;
+    const uint8_t* cspace; const uint8_t* cspace_thin;      // [n_rooms][H][W] 1 = free
+    const int32_t* closest;                                 // [n_rooms][2][H][W] distance_transform_edt indices
+    const uint8_t* small_free;                              // [n_rooms][SMALL][SMALL] 1 = free floor (small_obstacle_map)
     const uint8_t* robot_chan;                              // [LW][LW] robot_state_channel * 255
-    const float* ch3_map;                                   // [H][W] fourth observation channel before the window shift: scaled spfa field of the
-                                                            //        receptacle (box-delivery) / goal-point map (area-clearing); static per handle
+    const float* ch3_map;                                   // [n_rooms][H][W] fourth observation channel before the window shift: scaled spfa field of the
+                                                            //        receptacle (box-delivery) / goal-point map (area-clearing); static per room
     char* envs; size_t env_bytes;
 };
+BP_DEV const BdStatics& bd_room(const BdConst& C, const BdEnv* E) { return C.rooms[E->room]; }
+BP_DEV const uint8_t* bd_cspace(const BdConst& C, int room) { return C.cspace + (size_t)room * C.P.H * C.P.W; }
+BP_DEV const uint8_t* bd_cspace_thin(const BdConst& C, int room) { return C.cspace_thin + (size_t)room * C.P.H * C.P.W; }
+BP_DEV const int32_t* bd_closest(const BdConst& C, int room) { return C.closest + (size_t)room * 2 * C.P.H * C.P.W; }
+BP_DEV const uint8_t* bd_small_free(const BdConst& C, int room) { return C.small_free + (size_t)room * C.P.SMALL * C.P.SMALL; }
+BP_DEV const float* bd_ch3_map(const BdConst& C, int room) { return C.ch3_map + (size_t)room * C.P.H * C.P.W; }
 BP_DEV BdEnv* bd_env(const BdConst& C, int e) { return (BdEnv*)(C.envs + (size_t)e * C.env_bytes); }
 BP_DEV BdSlot* bd_slots(BdEnv* e) { return e->slots; }
 // pointers of the header into its env block (set at reset, from the header's GLOBAL address)
@@ -204,9 +220,9 @@ BP_DEVNI ShapeRef shape_ref(const BdConst& C, const BdEnv* E, int s) {
         r.v = &E->wv[s][0][0]; r.ln = &L.box_ln[i][0][0]; r.n = SV; r.rad = C.S.box_rad; r.e = C.S.box_e; r.u = C.S.box_u;
         r.rc = E->body[1 + i].rc; r.rs = E->body[1 + i].rs; r.body = 1 + i; r.bb = E->bb[s];
     } else {
-        int k = s - NROBOT - NB;
-        r.v = &C.S.st_v[k][0][0]; r.ln = &C.S.st_n[k][0][0]; r.n = C.S.st_nv[k]; r.rad = C.S.st_rad[k]; r.e = C.S.st_e[k]; r.u = C.S.st_u[k];
-        r.rc = 1.0; r.rs = 0.0; r.body = -1; r.bb = C.S.st_bb[k];
+        int k = s - NROBOT - NB; const BdStatics& T = bd_room(C, E);
+        r.v = &T.st_v[k][0][0]; r.ln = &T.st_n[k][0][0]; r.n = T.st_nv[k]; r.rad = T.st_rad[k]; r.e = T.st_e[k]; r.u = T.st_u[k];
+        r.rc = 1.0; r.rs = 0.0; r.body = -1; r.bb = T.st_bb[k];
     }
     return r;
 }
@@ -242,7 +258,12 @@ BP_DEV V2 bd_local_to_world(const BdBody& b, double x, double y) {
 }
 
 // statics: world vertices / normals / AABB from the creation pose (run once per handle)
-BP_DEV void bd_init_static(BdShapes& S, int k) {
+BP_DEV void bd_init_static(BdStatics& S, int k) {
+    if (S.st_nv[k] == 0) {        // unused slot: an AABB nothing overlaps
+        S.st_bb[k].l = INFINITY; S.st_bb[k].b = INFINITY; S.st_bb[k].r = -INFINITY; S.st_bb[k].t = -INFINITY;
+        S.st_p[k][0] = 0.0; S.st_p[k][1] = 0.0;
+        return;
+    }
     double s, c; bp_sincos(S.st_pose[k][2], &s, &c);
     // static bodies carry no mass: cog = 0, p = position
     S.st_p[k][0] = S.st_pose[k][0]; S.st_p[k][1] = S.st_pose[k][1];
@@ -287,7 +308,7 @@ struct BodyV { double px, py, vx, vy, vw, minv, iinv; };
 BP_DEVNI BodyV body_view(const BdConst& C, const BdEnv* E, int s, int body) {
     BodyV b;
     if (body >= 0) { const BdBody& q = E->body[body]; b.px = q.px; b.py = q.py; b.vx = q.vx; b.vy = q.vy; b.vw = q.vw; b.minv = q.minv; b.iinv = q.iinv; }
-    else { int k = s - NROBOT - C.P.NB; b.px = C.S.st_p[k][0]; b.py = C.S.st_p[k][1]; b.vx = b.vy = b.vw = 0.0; b.minv = b.iinv = 0.0; }
+    else { int k = s - NROBOT - C.P.NB; b.px = bd_room(C, E).st_p[k][0]; b.py = bd_room(C, E).st_p[k][1]; b.vx = b.vy = b.vw = 0.0; b.minv = b.iinv = 0.0; }
     return b;
 }
 
@@ -332,7 +353,7 @@ BP_DEVNI bool bd_boundary_presolve(const BdConst& C, BdEnv* E, int q) {
     int k = sb - NROBOT - C.P.NB;
     V2 n = mk(S.nx, S.ny);
     V2 p1 = mk(A.px + S.c[0].r1x, A.py + S.c[0].r1y);
-    V2 p2 = mk(C.S.st_p[k][0] + S.c[0].r2x, C.S.st_p[k][1] + S.c[0].r2y);
+    V2 p2 = mk(bd_room(C, E).st_p[k][0] + S.c[0].r2x, bd_room(C, E).st_p[k][1] + S.c[0].r2y);
     double depth = dot(p2 - p1, n);
     V2 cv = mk(A.vx, A.vy);
     double kk = 2 * dot(cv, n);
@@ -482,7 +503,7 @@ BP_DEVNI void bd_phase_a(const BdConst& C, BdEnv* E) {
                 BdSlot& S = slots[p];
                 if (dirty) {
                     BBox A = E->bb[sa];
-                    BBox B = (sb < NROBOT + NB) ? E->bb[sb] : C.S.st_bb[sb - NROBOT - NB];
+                    BBox B = (sb < NROBOT + NB) ? E->bb[sb] : bd_room(C, E).st_bb[sb - NROBOT - NB];
                     take = (A.l <= B.r && B.l <= A.r && A.b <= B.t && B.b <= A.t);
                     S.ov = take ? 1 : 0; S.mvalid = 0;
                 } else take = S.ov != 0;
@@ -708,19 +729,21 @@ BP_DEV void bd_remove_box(const BdConst& C, BdEnv* E, int i) {
 
 // Space.point_query(p, 0, ShapeFilter()) restricted to the static shapes: bit (1 << ctype) per shape that strictly
 // contains p (cpPolyShapePointQuery: distance = (outside ? d : -d) - r, reported when < 0)
-BP_DEV int bd_point_query_static(const BdConst& C, V2 p) {
+BP_DEV int bd_point_query_static(const BdConst& C, const BdEnv* E, V2 p) {
     int mask = 0;
+    const BdStatics& T = bd_room(C, E);
     #pragma unroll 1
     for (int k = 0; k < C.P.n_static; k++) {
-        const BBox& bb = C.S.st_bb[k];
+        const BBox& bb = T.st_bb[k];
         if (!(p.x <= bb.r && bb.l <= p.x && p.y <= bb.t && bb.b <= p.y)) continue;
-        int n = C.S.st_nv[k];
-        V2 v0 = mk(C.S.st_v[k][n - 1][0], C.S.st_v[k][n - 1][1]);
+        int n = T.st_nv[k];
+        if (n == 0) continue;
+        V2 v0 = mk(T.st_v[k][n - 1][0], T.st_v[k][n - 1][1]);
         double minDist = INFINITY; bool outside = false;
         #pragma unroll 1
         for (int i = 0; i < n; i++) {
-            V2 v1 = mk(C.S.st_v[k][i][0], C.S.st_v[k][i][1]);
-            V2 nn = mk(C.S.st_n[k][i][0], C.S.st_n[k][i][1]);
+            V2 v1 = mk(T.st_v[k][i][0], T.st_v[k][i][1]);
+            V2 nn = mk(T.st_n[k][i][0], T.st_n[k][i][1]);
             if (dot(nn, p - v1) > 0.0) outside = true;
             V2 d2 = v0 - v1;
             double t = clamp01(dot(d2, p - v1) / dot(d2, d2));
@@ -730,8 +753,8 @@ BP_DEV int bd_point_query_static(const BdConst& C, V2 p) {
             if (dist < minDist) minDist = dist;
             v0 = v1;
         }
-        double dist = (outside ? minDist : -minDist) - C.S.st_rad[k];
-        if (dist < 0.0) mask |= 1 << C.S.st_ctype[k];
+        double dist = (outside ? minDist : -minDist) - T.st_rad[k];
+        if (dist < 0.0) mask |= 1 << T.st_ctype[k];
     }
     return mask;
 }

@@ -56,9 +56,10 @@ BP_DEV void pos_to_pixel(const BdParams& P, double x, double y, int* i, int* j) 
 BP_DEV void pixel_to_pos(const BdParams& P, int i, int j, double* x, double* y) {
     *x = (j - P.W / 2.0) / P.ppm; *y = (P.H / 2.0 - i) / P.ppm;
 }
-BP_DEV void closest_valid(const BdConst& C, int i, int j, int* ci, int* cj) {
+BP_DEV void closest_valid(const BdConst& C, int room, int i, int j, int* ci, int* cj) {
     size_t nv = (size_t)C.P.H * C.P.W;
-    *ci = C.closest[(size_t)i * C.P.W + j]; *cj = C.closest[nv + (size_t)i * C.P.W + j];
+    const int32_t* cl = bd_closest(C, room);
+    *ci = cl[(size_t)i * C.P.W + j]; *cj = cl[nv + (size_t)i * C.P.W + j];
 }
 
 // skimage.draw.line iterator: calls f(r, c) for every pixel, both ends included
@@ -104,7 +105,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
     #pragma unroll 1
     for (int p = lane; p < P.n_slots; p += BP_NL) { slots[p].state = SL_NONE; slots[p].cnt = 0; slots[p].stamp = 0; slots[p].gjk = 0; slots[p].ov = 0; slots[p].mvalid = 0; }
     if (lane == 0) {
-        E->layout = layout; E->episode = episode; E->t = 0; E->status = 0; E->stamp = 0; E->n_order = 0; E->robot_hit = 0;
+        E->layout = layout; E->room = L.room; E->episode = episode; E->t = 0; E->status = 0; E->stamp = 0; E->n_order = 0; E->robot_hit = 0;
         E->inactivity = 0; E->cum_boxes = 0; E->done = 0; E->truncated = 0; E->n_path = 0; E->need_spfa = 0; E->n_live = 0; E->cleared_count = 0;
         E->prev_dt = 0.0; E->cum_distance = 0.0; E->cum_reward = 0.0; E->total_work = 0.0; E->last_work = 0.0; E->reward = 0.0; E->ministeps = 0.0;
         E->stat_substeps = 0; E->stat_cand = 0; E->stat_arb = 0;
@@ -117,6 +118,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
     for (int i = lane; i < P.NB; i += BP_NL) {
         BdBody& B = E->body[1 + i];
         B.alive = i < L.n_boxes; B.idx = i;
+        E->cold->dist_ok[i] = 0;
         B.pa = L.box_init[i][2];
         bp_sincos(B.pa, &B.rs, &B.rc);
         B.cgx = L.box_cog[i][0]; B.cgy = L.box_cog[i][1];
@@ -204,13 +206,13 @@ BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action, double acti
     // shortest_path(check_straight=True), first half
     int si, sj, ti, tj;
     pos_to_pixel(P, x0, y0, &si, &sj); pos_to_pixel(P, tx, ty, &ti, &tj);
-    if (line_free(C.cspace_thin, P.W, si, sj, ti, tj)) {
+    if (line_free(bd_cspace_thin(C, E->room), P.W, si, sj, ti, tj)) {
         E->need_spfa = 0; E->n_path = 2;
         E->cold->path[0][0] = x0; E->cold->path[0][1] = y0; E->cold->path[1][0] = tx; E->cold->path[1][1] = ty;
     } else {
         E->need_spfa = 1;
-        closest_valid(C, si, sj, &E->src_i, &E->src_j);
-        closest_valid(C, ti, tj, &E->tgt_i, &E->tgt_j);
+        closest_valid(C, E->room, si, sj, &E->src_i, &E->src_j);
+        closest_valid(C, E->room, ti, tj, &E->tgt_i, &E->tgt_j);
     }
     if (P.kind == 0 && P.recept_visible) bd_box_dists_visible(C, E, E->cold->init_dist);
 }
@@ -218,7 +220,7 @@ BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action, double acti
 // ------------------------------------------------------------------ path from a distance field (second half of shortest_path)
 // dist = raw spfa_relax output for source (si, sj).  coords / chain / stk: scratch of H*W ints each.  Serial.
 // Writes the waypoints (source first) to out[][2]; returns their count (0 = overflow).
-BP_DEV int bd_extract_path(const BdConst& C, const int* dist, int si, int sj, int ti, int tj,
+BP_DEV int bd_extract_path(const BdConst& C, const uint8_t* cspace, const int* parents, const int* dist, int si, int sj, int ti, int tj,
                            double sx, double sy, double gx, double gy, int* coords, int* chain, int* stk, double (*out)[3], int max_out) {
     const BdParams& P = C.P;
     const int W = P.W, H = P.H;
@@ -227,7 +229,7 @@ BP_DEV int bd_extract_path(const BdConst& C, const int* dist, int si, int sj, in
     int n = 0, v = ti * W + tj;
     coords[n++] = v;
     while (v != s) {
-        int u = spfa_parent_of(C.cspace, H, W, dist, s, v);
+        int u = parents ? parents[v] : spfa_parent_of(cspace, H, W, dist, s, v);
         if (u < 0) break;
         v = u; coords[n++] = v;
         if (n >= H * W) break;
@@ -269,7 +271,7 @@ BP_DEV int bd_extract_path(const BdConst& C, const int* dist, int si, int sj, in
     chain[nn++] = stk[0];
     for (int i = 1; i < m - 1; i++) {
         int a = chain[nn - 1], b = stk[i + 1];
-        if (!line_free(C.cspace, W, a / W, a % W, b / W, b % W)) chain[nn++] = stk[i];
+        if (!line_free(cspace, W, a / W, a % W, b / W, b % W)) chain[nn++] = stk[i];
     }
     if (m > 1) chain[nn++] = stk[m - 1];
     // pixel -> position, reversed (source first)
@@ -396,12 +398,12 @@ BP_DEVNI void mv_pre(const BdConst& C, BdEnv* E, MoveVars& V) {
 #pragma unroll 1
             for (int v = 0; v < SV && !stuck; v++) {
                 V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
-                if (bd_point_query_static(C, w) & (1 << 3)) stuck = true;
+                if (bd_point_query_static(C, E, w) & (1 << 3)) stuck = true;
             }
             if (stuck) {
                 V2 o = bd_origin(B);
                 int pi, pj, ni, nj; pos_to_pixel(P, o.x, o.y, &pi, &pj);
-                closest_valid(C, pi, pj, &ni, &nj);
+                closest_valid(C, E->room, pi, pj, &ni, &nj);
                 double nx, ny; pixel_to_pos(P, ni, nj, &nx, &ny);
                 bd_set_origin(B, mk(nx, ny));
                 B.vx = 0.0; B.vy = 0.0;
@@ -555,7 +557,7 @@ BP_DEV void bd_finish_step(const BdConst& C, BdEnv* E, int env, const BdOut& out
         bool inside = true;
         for (int v = 0; v < SV && inside; v++) {
             V2 w = bd_local_to_world(B, L.box_lv[i][v][0], L.box_lv[i][v][1]);
-            if (!(bd_point_query_static(C, w) & (1 << 4))) inside = false;
+            if (!(bd_point_query_static(C, E, w) & (1 << 4))) inside = false;
         }
         if (inside) {
             E->completed[B.idx] = 1; E->inactivity = 0; robot_boxes++; reward += P.goal_reward;

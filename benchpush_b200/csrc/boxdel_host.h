@@ -12,20 +12,24 @@
 namespace bp {
 namespace bd {
 
-struct BdHost { BdConst K; std::vector<BdLayout> LY; std::vector<short> pa, pb; };
+struct BdHost { BdConst K; std::vector<BdLayout> LY; std::vector<BdStatics> RM; std::vector<short> pa, pb; };
 
 inline void bd_fill_prep(const bp_prep::BodyPrep& b, double (*lv)[2], double (*ln)[2], int* nv) {
     *nv = (int)b.verts.size();
     for (int i = 0; i < *nv && i < SV; i++) { lv[i][0] = b.verts[i].x; lv[i][1] = b.verts[i].y; ln[i][0] = b.normals[i].x; ln[i][1] = b.normals[i].y; }
 }
 
-// Returns "" or an error message.
+// Returns "" or an error message.  Static-shape arrays carry a leading room axis: st_nv[n_rooms][n_static], st_verts[n_rooms][n_static][4][2],
+// st_pose[n_rooms][n_static][3], st_rad[n_rooms][n_static], st_ctype[n_rooms][n_static] (the same slot types in every room; st_nv 0 = slot
+// unused in that room).  layout_room[n_layouts] (nullptr: every layout uses room 0).
 inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                                 int n_rooms, const int32_t* layout_room,
                                  int n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad,
                                  const int32_t* st_ctype, int H, int W) {
     memset(&HB.K, 0, sizeof(HB.K));
     BdConst& K = HB.K;
     BdParams& P = K.P;
+    P.exact_parents = c.exact_spfa_parents ? 1 : 0;
     P.NB = c.num_boxes; P.n_static = n_static; P.n_s3 = 0; P.recept = -1;
     for (int k = 0; k < n_static; k++) { if (st_ctype[k] == 3) P.s3[P.n_s3++] = k; else if (st_ctype[k] == 4) P.recept = k; }
     if (P.recept < 0 && c.env_kind == 0) return std::string("no receptacle (collision_type 4) among the static shapes");
@@ -72,15 +76,24 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
             if (b.verts.size() < 3 || b.verts.size() > SV) return std::string("wheel / bumper hull vertex count out of range");
             bd_fill_prep(b, S.rb_lv[1 + w], S.rb_ln[1 + w], &S.rb_nv[1 + w]); S.rb_rad[1 + w] = 0.02; S.rb_e[1 + w] = 0.01; S.rb_u[1 + w] = 0.0;
         }
-        for (int k = 0; k < n_static; k++) {
-            if (st_nv[k] < 3 || st_nv[k] > SV) return std::string("static shape vertex count out of range");
-            std::vector<bp_prep::P2> sv(st_nv[k]);
-            for (int i = 0; i < st_nv[k]; i++) sv[i] = bp_prep::P2{st_verts[(k * SV + i) * 2], st_verts[(k * SV + i) * 2 + 1]};
-            bp_prep::BodyPrep b = bp_prep::prep_body(sv, st_rad[k], 0.0, false);
-            if (b.verts.size() < 3) return std::string("degenerate static shape");
-            bd_fill_prep(b, S.st_lv[k], S.st_ln[k], &S.st_nv[k]);
-            S.st_pose[k][0] = st_pose[3 * k]; S.st_pose[k][1] = st_pose[3 * k + 1]; S.st_pose[k][2] = st_pose[3 * k + 2];
-            S.st_rad[k] = st_rad[k]; S.st_e[k] = c.static_e; S.st_u[k] = c.static_u; S.st_ctype[k] = st_ctype[k];
+        HB.RM.assign(n_rooms, BdStatics());
+        for (int r = 0; r < n_rooms; r++) {
+            BdStatics& T = HB.RM[r];
+            memset(&T, 0, sizeof(T));
+            for (int k = 0; k < n_static; k++) {
+                const int q = r * n_static + k;
+                if (st_ctype[q] != st_ctype[k]) return std::string("static slot types differ between rooms");
+                T.st_ctype[k] = st_ctype[q];
+                if (st_nv[q] == 0 && st_ctype[q] == 3) { T.st_nv[k] = 0; continue; }     // slot unused in this room
+                if (st_nv[q] < 3 || st_nv[q] > SV) return std::string("static shape vertex count out of range");
+                std::vector<bp_prep::P2> sv(st_nv[q]);
+                for (int i = 0; i < st_nv[q]; i++) sv[i] = bp_prep::P2{st_verts[((size_t)q * SV + i) * 2], st_verts[((size_t)q * SV + i) * 2 + 1]};
+                bp_prep::BodyPrep b = bp_prep::prep_body(sv, st_rad[q], 0.0, false);
+                if (b.verts.size() < 3) return std::string("degenerate static shape");
+                bd_fill_prep(b, T.st_lv[k], T.st_ln[k], &T.st_nv[k]);
+                T.st_pose[k][0] = st_pose[3 * q]; T.st_pose[k][1] = st_pose[3 * q + 1]; T.st_pose[k][2] = st_pose[3 * q + 2];
+                T.st_rad[k] = st_rad[q]; T.st_e[k] = c.static_e; T.st_u[k] = c.static_u;
+            }
         }
         S.box_rad = 0.02; S.box_e = 0.01; S.box_u = 1.0;     // create_polygon ignores its radius argument (D7)
         // polygon drawn for the robot in the overhead map: cfg.agent.footprint_vertices (area-clearing) or the chassis hull
@@ -102,6 +115,8 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
         L.start[0] = starts[3 * l]; L.start[1] = starts[3 * l + 1]; L.start[2] = starts[3 * l + 2];
         if (n_boxes[l] < 0 || n_boxes[l] > c.num_boxes) return std::string("n_boxes out of range");
         L.n_boxes = n_boxes[l];
+        L.room = layout_room ? layout_room[l] : 0;
+        if (L.room < 0 || L.room >= n_rooms) return std::string("layout_room out of range");
         for (int i = 0; i < L.n_boxes; i++) {
             const double* b = boxes + ((size_t)l * c.num_boxes + i) * 3;
             double x = b[0], y = b[1];
@@ -118,7 +133,7 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
     }
     HB.pa.assign(P.n_slots, 0); HB.pb.assign(P.n_slots, 0);
     bd_build_pairs(P, HB.pa.data(), HB.pb.data());
-    K.n_layouts = n_layouts; K.n_envs = c.n_envs; K.env_bytes = bd_env_bytes(P.n_slots);
+    K.n_layouts = n_layouts; K.n_rooms = n_rooms; K.n_envs = c.n_envs; K.env_bytes = bd_env_bytes(P.n_slots);
     return "";
 }
 

@@ -23,7 +23,20 @@ namespace bp {
 namespace bd {
 
 // scratch layout per block (ints): dist[nv] q0[nv] q1[nv] mark[nv] small[SMALL*SMALL/4 + 1]
-BP_HD size_t bd_scratch_ints(const BdParams& P) { return (size_t)4 * P.H * P.W + (size_t)P.SMALL * P.SMALL / 4 + 64; }
+// exact-parents mode adds parents[nv] behind it (the serial solver's ring and flags live in q0 / q1 / mark until the path is extracted)
+BP_HD size_t bd_scratch_ints(const BdParams& P) { return (size_t)(P.exact_parents ? 5 : 4) * P.H * P.W + (size_t)P.SMALL * P.SMALL / 4 + 64; }
+
+// shortest_path_distance(box k, receptacle) is a function of the box origin and the room alone.  A box that has not moved since
+// its last solve reuses the value: every box between the end of a step and the start of the next (final_dist of step t is
+// init_dist of step t + 1), and the boxes the robot did not touch within a step.  Bitwise the same result as solving again.
+BP_DEV bool bd_box_dist_cached(BdEnv* E, int k, int phase, bool write) {
+    BdEnvCold* K = E->cold;
+    if (!K->dist_ok[k]) return false;
+    V2 o = bd_origin(E->body[1 + k]);
+    if (o.x != K->dist_key[k][0] || o.y != K->dist_key[k][1]) return false;
+    if (write) { if (phase == 0) K->init_dist[k] = K->dist_val[k]; else K->final_dist[k] = K->dist_val[k]; }
+    return true;
+}
 
 // ------------------------------------------------------------------ distance / path items
 // k < NB: shortest_path_distance(box k, receptacle) -> E->cold->init_dist[k] (phase 0) or E->cold->final_dist[k] (phase 1);
@@ -37,26 +50,36 @@ BP_DEV void bd_dist_item(SpfaShared& S, const BdConst& C, BdEnv* E, int k, int p
     if (k < P.NB) {
         const BdBody& B = E->body[1 + k];
         if (!B.alive || P.recept_visible) return;
+        if (bd_box_dist_cached(E, k, phase, BP_TID == 0)) return;
         V2 o = bd_origin(B);
         sx = o.x; sy = o.y; gx = P.recept_x; gy = P.recept_y;
         int pi, pj;
-        pos_to_pixel(P, sx, sy, &pi, &pj); closest_valid(C, pi, pj, &si, &sj);
-        pos_to_pixel(P, gx, gy, &pi, &pj); closest_valid(C, pi, pj, &ti, &tj);
+        pos_to_pixel(P, sx, sy, &pi, &pj); closest_valid(C, E->room, pi, pj, &si, &sj);
+        pos_to_pixel(P, gx, gy, &pi, &pj); closest_valid(C, E->room, pi, pj, &ti, &tj);
     } else {
         if (phase != 0 || !E->need_spfa) return;
         sx = E->init_pos[0]; sy = E->init_pos[1]; gx = E->tgt[0]; gy = E->tgt[1];
         si = E->src_i; sj = E->src_j; ti = E->tgt_i; tj = E->tgt_j;
     }
-    spfa_relax(S, C.cspace, P.H, P.W, si, sj, (float*)dist, q0, q1, mark);
+    int* parents = nullptr;
+    if (P.exact_parents) {
+        // the reference's own parent order (ties between equal-cost predecessors decide which staircase the path takes, and the
+        // Douglas-Peucker / line-of-sight pruning downstream amplifies that): one thread restates its queue
+        parents = scratch + (size_t)4 * nv + (size_t)P.SMALL * P.SMALL / 4 + 64;
+        if (BP_TID == 0) spfa_serial_parents(bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, parents, q0, (unsigned char*)mark);
+    } else {
+        spfa_relax(S, bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, q0, q1, mark);
+    }
     BP_BSYNC();
     if (BP_TID == 0) {
         double wp[MAXWP][3];
-        int n = bd_extract_path(C, dist, si, sj, ti, tj, sx, sy, gx, gy, q0, q1, mark, wp, MAXWP);
+        int n = bd_extract_path(C, bd_cspace(C, E->room), parents, dist, si, sj, ti, tj, sx, sy, gx, gy, q0, q1, mark, wp, MAXWP);
         if (n == 0) { E->status |= BD_PATH_OVERFLOW; n = 2; wp[0][0] = sx; wp[0][1] = sy; wp[1][0] = gx; wp[1][1] = gy; }
         if (k < P.NB) {
             double d = 0.0;
             for (int i = 1; i < n; i++) d = d + dist2(wp[i - 1][0], wp[i - 1][1], wp[i][0], wp[i][1]);
             if (phase == 0) E->cold->init_dist[k] = d; else E->cold->final_dist[k] = d;
+            E->cold->dist_key[k][0] = sx; E->cold->dist_key[k][1] = sy; E->cold->dist_val[k] = d; E->cold->dist_ok[k] = 1;
         } else {
             for (int i = 0; i < n; i++) { E->cold->path[i][0] = wp[i][0]; E->cold->path[i][1] = wp[i][1]; }
             E->n_path = n;
@@ -66,10 +89,11 @@ BP_DEV void bd_dist_item(SpfaShared& S, const BdConst& C, BdEnv* E, int k, int p
 }
 
 // 1 when free cell v is visible from the receptacle cell (or v is not free)
-BP_DEV int bd_cell_visible(const BdConst& C, int v) {
+BP_DEV int bd_cell_visible(const BdConst& C, int room, int v) {
     const BdParams& P = C.P;
-    if (!C.cspace[v]) return 1;
-    return line_free(C.cspace, P.W, P.recept_ci, P.recept_cj, v / P.W, v % P.W) ? 1 : 0;
+    const uint8_t* cs = bd_cspace(C, room);
+    if (!cs[v]) return 1;
+    return line_free(cs, P.W, C.rooms[room].recept_ci, C.rooms[room].recept_cj, v / P.W, v % P.W) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ cv2.fillPoly (one convex polygon, <= 4 int vertices)
@@ -141,12 +165,12 @@ BP_DEV void bd_obs_item(BdObsShared& S, const BdConst& C, const BdEnv* E, int* s
     // ---- robot-source distance field (create_global_shortest_path_map)
     {
         int pi, pj, si, sj;
-        pos_to_pixel(P, R.px, R.py, &pi, &pj); closest_valid(C, pi, pj, &si, &sj);
-        spfa_relax(S.sp, C.cspace, P.H, P.W, si, sj, (float*)dist, q0, q1, mark);
+        pos_to_pixel(P, R.px, R.py, &pi, &pj); closest_valid(C, E->room, pi, pj, &si, &sj);
+        spfa_relax(S.sp, bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, q0, q1, mark);
         BP_BSYNC();
     }
     // ---- small overhead map: floor / obstacle, receptacle, boxes, robot chassis (update_global_overhead_map)
-    for (int i = tid; i < N * N; i += nt) small[i] = C.small_free[i];        // static codes: 0 obstacle, 1 floor (3 goal area in area-clearing)
+    { const uint8_t* sf = bd_small_free(C, E->room); for (int i = tid; i < N * N; i += nt) small[i] = sf[i]; }        // static codes: 0 obstacle, 1 floor (3 goal area in area-clearing)
     BP_BSYNC();
     auto to_px = [&](double wx, double wy, int* x, int* y) {
         int ix = (int)(wx * P.ppm), iy = (int)(wy * P.ppm);       // astype(np.int32): truncation toward zero
@@ -159,8 +183,9 @@ BP_DEV void bd_obs_item(BdObsShared& S, const BdConst& C, const BdEnv* E, int* s
         if (tid == 0) {
             if (q == 0) {
                 if (P.draw_recept) {
-                    n = C.S.st_nv[P.recept]; code = 3;
-                    for (int v = 0; v < n; v++) to_px(C.S.st_v[P.recept][v][0], C.S.st_v[P.recept][v][1], &S.px[v], &S.py[v]);
+                    const BdStatics& T = bd_room(C, E);
+                    n = T.st_nv[P.recept]; code = 3;
+                    for (int v = 0; v < n; v++) to_px(T.st_v[P.recept][v][0], T.st_v[P.recept][v][1], &S.px[v], &S.py[v]);
                 }
             } else if (q <= P.NB) {
                 const BdBody& B = E->body[q];
@@ -210,7 +235,8 @@ BP_DEV void bd_obs_item(BdObsShared& S, const BdConst& C, const BdEnv* E, int* s
         return gi * P.W + gj;
     };
     auto ch2 = [&](int g) -> float { if (g < 0) return 0.0f; float d = i2f(dist[g]); return bd_scale_sp(P, d < inf ? d : 0.0f); };
-    auto ch3 = [&](int g) -> float { if (g < 0) return 0.0f; return C.ch3_map[g]; };
+    const float* ch3m = bd_ch3_map(C, E->room);
+    auto ch3 = [&](int g) -> float { if (g < 0) return 0.0f; return ch3m[g]; };
     // ---- pass 1: minima of the two distance channels over the window
     if (tid == 0) { S.minbits[0] = f2i(INFINITY); S.minbits[1] = f2i(INFINITY); }
     BP_BSYNC();

@@ -272,6 +272,18 @@ __global__ void __launch_bounds__(512) k_spfa(const uint8_t* maps, const int32_t
     }
 }
 
+// one thread per map: the reference solver's queue restated (spfa_serial_parents), reference output convention (unreachable -> 0)
+__global__ void k_spfa_serial(const uint8_t* maps, const int32_t* sources, int batch, int H, int W, float* dists, int32_t* parents,
+                              int* ring, unsigned char* inq) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= batch) return;
+    const size_t nv = (size_t)H * W;
+    float* d = dists + m * nv;
+    spfa_serial_parents(maps + m * nv, H, W, sources[2 * m], sources[2 * m + 1], d, parents + m * nv, ring + m * (nv + 2), inq + m * nv);
+    const float inf = 2.0f * (float)nv;
+    for (size_t v = 0; v < nv; v++) if (!(d[v] < inf)) d[v] = 0.0f;
+}
+
 // generate_observation_low_dim (ship_ice_env.py:358-370; maze_NAMO_env.py:488-504): |poly_centroid| of every movable
 // polygon in creation order.  One warp per env: the |centroid| cache of the env block (cenx / ceny: refreshed by
 // step_work for every body that moved, set at reset) is compacted over the dynamic bodies below the robot.
@@ -1073,6 +1085,43 @@ int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batc
     CUDA_TRY(cudaMemcpy(dm, maps, nv, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(ds, sources, (size_t)batch * 8, cudaMemcpyHostToDevice));
     int rc = bp_spfa_batch(dm, ds, batch, H, W, dd, dp, nullptr);
+    if (rc == BP_OK) {
+        cudaError_t e1 = cudaMemcpy(dists, dd, nv * 4, cudaMemcpyDeviceToHost);
+        cudaError_t e2 = cudaMemcpy(parents, dp, nv * 4, cudaMemcpyDeviceToHost);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(BP_ERR_CUDA, "spfa result copy failed");
+    }
+    cudaFree(dm); cudaFree(ds); cudaFree(dd); cudaFree(dp);
+    return rc;
+}
+
+// Reference-order parents (spfa.cuh spfa_serial_parents): one THREAD per map restates the reference solver's queue, so that
+// parents[] equals spfa.spfa's own output also where several predecessors tie.  Distances are the same as bp_spfa_batch's.
+// Slow by construction (a sequential algorithm per map); meant for parity runs and for callers that walk the parents.
+int bp_spfa_batch_exact(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t H, int32_t W, float* dists, int32_t* parents, void* stream) {
+    if (!maps || !sources || !dists || !parents) return fail(BP_ERR_INVALID, "null argument");
+    if (batch <= 0 || H <= 0 || W <= 0 || (long long)H * W > (1ll << 26)) return fail(BP_ERR_INVALID, "bad batch / grid size");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nv = (size_t)H * W;
+    int* ring = nullptr; unsigned char* inq = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&ring, (size_t)batch * (nv + 2) * sizeof(int)));
+    if (cudaMalloc((void**)&inq, (size_t)batch * nv) != cudaSuccess) { cudaFree(ring); return fail(BP_ERR_CUDA, "spfa scratch allocation failed"); }
+    k_spfa_serial<<<(batch + 31) / 32, 32, 0, st>>>(maps, sources, batch, H, W, dists, parents, ring, inq);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // the scratch is released below
+    cudaFree(ring); cudaFree(inq);
+    if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("bp_spfa_batch_exact: ") + cudaGetErrorString(e));
+    return BP_OK;
+}
+
+int bp_spfa_batch_exact_host(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t H, int32_t W, float* dists, int32_t* parents) {
+    if (!maps || !sources || !dists || !parents) return fail(BP_ERR_INVALID, "null argument");
+    size_t nv = (size_t)H * W * batch;
+    uint8_t* dm = nullptr; int32_t* ds = nullptr; float* dd = nullptr; int32_t* dp = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dm, nv)); CUDA_TRY(cudaMalloc((void**)&ds, (size_t)batch * 8));
+    CUDA_TRY(cudaMalloc((void**)&dd, nv * 4)); CUDA_TRY(cudaMalloc((void**)&dp, nv * 4));
+    CUDA_TRY(cudaMemcpy(dm, maps, nv, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ds, sources, (size_t)batch * 8, cudaMemcpyHostToDevice));
+    int rc = bp_spfa_batch_exact(dm, ds, batch, H, W, dd, dp, nullptr);
     if (rc == BP_OK) {
         cudaError_t e1 = cudaMemcpy(dists, dd, nv * 4, cudaMemcpyDeviceToHost);
         cudaError_t e2 = cudaMemcpy(parents, dp, nv * 4, cudaMemcpyDeviceToHost);

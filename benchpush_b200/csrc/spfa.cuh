@@ -102,6 +102,53 @@ BP_DEV int spfa_parent_of(const uint8_t* map, int H, int W, const int* dist, int
     return -1;
 }
 
+// Reference-ORDER parents: the queue discipline of the reference solver restated literally (deps/spfa/src/main.cpp:62-85 — a
+// FIFO label-correcting queue; a vertex pushed with a smaller label than the queue's front is swapped to the front; a parent
+// is recorded at every strict improvement), run by ONE thread.  The parent of a vertex with several equal-cost predecessors
+// is whichever improved it last in that processing order, which no order-free relaxation can reproduce; the env kernels use
+// this only in their exact-parents mode (box distances / robot paths that must follow the reference's tie-breaks waypoint by
+// waypoint).  dist[nv] receives the fp32 labels (2*H*W where unreachable), parents[nv] the predecessors (-1 = none).
+// ring: at least nv + 2 ints (at most nv vertices are queued at a time, so the reference's 8*nv linear queue folds into a
+// ring without changing which entries meet); inq: nv bytes.
+BP_DEV void spfa_serial_parents(const uint8_t* map, int H, int W, int si, int sj, float* dist, int* parents, int* ring, unsigned char* inq) {
+    const int nv = H * W;
+    const int cap = nv + 2;
+    const float inf = 2.0f * (float)nv;
+    const float s2 = sqrtf(2.0f);
+    const int di[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+    const int dj[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
+    for (int v = 0; v < nv; v++) { dist[v] = inf; parents[v] = -1; inq[v] = 0; }
+    const int s = si * W + sj;
+    long long head = 0, tail = 0;                 // positions grow like the reference's; slot = position mod cap
+    dist[s] = 0.0f;
+    ring[(int)(++tail % cap)] = s;
+    inq[s] = 1;
+    if (!map[s]) return;                          // a blocked source has no edges
+    while (head < tail) {
+        const int u = ring[(int)(++head % cap)];
+        inq[u] = 0;
+        const int ui = u / W, uj = u - ui * W;
+        const float du = dist[u];
+        for (int k = 0; k < 8; k++) {
+            const int ip = ui + di[k], jp = uj + dj[k];
+            if (ip < 0 || jp < 0 || ip >= H || jp >= W) continue;
+            const int v = ip * W + jp;
+            if (!map[v]) continue;
+            const float nd = du + ((k & 1) ? 1.0f : s2);
+            if (nd < dist[v]) {
+                parents[v] = u;
+                dist[v] = nd;
+                if (!inq[v]) {
+                    const int pt = (int)(++tail % cap), pf = (int)((head + 1) % cap);
+                    ring[pt] = v;
+                    inq[v] = 1;
+                    if (dist[ring[pt]] < dist[ring[pf]]) { int t = ring[pt]; ring[pt] = ring[pf]; ring[pf] = t; }
+                }
+            }
+        }
+    }
+}
+
 BP_DEV void spfa_block(SpfaShared& S, const uint8_t* map, int H, int W, int si, int sj, float* dist_out, int32_t* parents,
                        int* q0, int* q1, int* mark) {
     const int tid = BP_TID, nt = BP_NT;

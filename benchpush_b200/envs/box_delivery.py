@@ -11,9 +11,11 @@ nearest-free-cell map (``update_configuration_space``, box_delivery_env.py:1140-
 library calls as the reference (cv2.fillPoly, scipy binary_dilation with a disk footprint, scipy
 distance_transform_edt).  They depend on the room only, so all envs of a handle share them.
 
-Implemented: ``obstacle_config: small_empty`` (any room size without columns / dividers), ``action_type``
-``heading``, ``position`` and ``velocity`` (actions ``float32[B, 2]``), ``low_dim_state``.  The column / divider rooms raise
-NotImplementedError.
+Implemented: every ``obstacle_config`` (``small_empty``, ``small_columns``, ``large_columns``, ``large_divider``; a
+``*_empty`` room of any size), ``action_type`` ``heading``, ``position`` and ``velocity`` (actions ``float32[B, 2]``),
+``low_dim_state``.  In the column / divider configurations the reference redraws the obstacles at every reset and rebuilds
+its configuration space; here every layout of the pool carries its own room (static shapes + maps, built with the same
+library calls), the pool is capped at ``max_rooms`` layouts and the kernels index the room tables by layout.
 """
 from __future__ import annotations
 
@@ -76,7 +78,7 @@ class BoxDelConfig(C.Structure):
         ("lfc", C.c_double), ("omega_mul", C.c_double), ("v_mul", C.c_double), ("bound_x", C.c_double), ("bound_y", C.c_double),
         ("static_e", C.c_double), ("static_u", C.c_double),
         ("robot_code", C.c_double), ("box_code", C.c_double), ("box_done_code", C.c_double),
-        ("footprint_verts", C.c_double * 8), ("n_footprint", C.c_int32), ("reserved1", C.c_int32),
+        ("footprint_verts", C.c_double * 8), ("n_footprint", C.c_int32), ("exact_spfa_parents", C.c_int32),
         ("boundary", C.c_double * 16), ("goals", C.c_double * 128),
         ("r_boundary", C.c_double), ("r_cleared", C.c_double), ("r_putback", C.c_double), ("r_push_mult", C.c_double),
         ("r_terminal", C.c_double), ("r_truncation", C.c_double), ("r_nonmove", C.c_double),
@@ -95,6 +97,8 @@ def bind(L):
     L.bp_boxdel_destroy.argtypes = [C.c_void_p]
     L.bp_boxdel_load.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + \
                                 [C.c_int32, C.c_int32] + [C.c_void_p] * 6
+    L.bp_boxdel_load_rooms.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + \
+                                      [C.c_int32, C.c_int32] + [C.c_void_p] * 6
     L.bp_boxdel_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
     L.bp_boxdel_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
     L.bp_boxdel_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs)]
@@ -120,7 +124,11 @@ def disk(radius: int) -> np.ndarray:
 class RoomMaps:
     """Static shapes and maps of one room (box_delivery_env.py:322-335, 342-358, 472-489, 1098-1175; sim_utils.py:78-131)."""
 
-    def __init__(self, cfg):
+    # static-shape slots of the obstacle configurations (the same slot list for every room of a handle; a room that draws
+    # fewer columns leaves slots empty): receptacle, 4 walls, [columns | divider], 3 room corners x 3 triangles, [2 divider corners x 3]
+    MAX_COLUMNS = {"small_columns": 2, "large_columns": 7}      # randint(1, 3) / randint(1, 8): box_delivery_env.py:466-469
+
+    def __init__(self, cfg, layout=None):
         import cv2
         from scipy.ndimage import binary_dilation, distance_transform_edt
         env = cfg["env"]
@@ -142,22 +150,38 @@ class RoomMaps:
         for (x, y, length, width) in [(-rl / 2 - wt / 2, 0, wt, rw), (rl / 2 + wt / 2, 0, wt, rw),
                                       (0, -rw / 2 - wt / 2, rl + 2 * wt, wt), (0, rw / 2 + wt / 2, rl + 2 * wt, wt)]:
             st.append((rect(x, y, length, width), (0.0, 0.0, 0.0), 0.0, 3))
+        # random obstacles of the layout (generate_boundary :358-471; create_static: world vertices, no radius)
+        oc = env["obstacle_config"]
+        columns = list((layout or {}).get("columns") or [])
+        divider = (layout or {}).get("divider")
+        empty = ([], (0.0, 0.0, 0.0), 0.0, 3)
+        if oc in self.MAX_COLUMNS:
+            assert len(columns) <= self.MAX_COLUMNS[oc]
+            for k in range(self.MAX_COLUMNS[oc]):
+                st.append((rect(columns[k][0], columns[k][1], 1, 1), (0.0, 0.0, 0.0), 0.0, 3) if k < len(columns) else empty)
+        elif oc == "large_divider":
+            st.append((rect(divider[0], divider[1], 8, 0.5), (0.0, 0.0, 0.0), 0.0, 3) if divider is not None else empty)
         s225, c225 = np.sin(22.5 * np.pi / 180), np.cos(22.5 * np.pi / 180)
         tri = [[(0, 0), (0, -1), (0.5 * s225, -1 + 0.5 * c225)],
                [(0, 0), (0.5 * s225, -1 + 0.5 * c225), (1 - 0.5 * c225, -0.5 * s225)],
                [(0, 0), (1, 0), (1 - 0.5 * c225, -0.5 * s225)]]
+        corners = []
         for i, (x, y) in enumerate([(-rl / 2, rw / 2), (rl / 2, rw / 2), (rl / 2, -rw / 2), (-rl / 2, -rw / 2)]):
             if i == 1:
                 continue                      # the receptacle corner
-            heading = -np.radians(i * 90)
+            corners.append((x, y, -np.radians(i * 90)))
+        if oc == "large_divider":             # corners where the divider meets the right wall (:491-505)
+            corners += [(rl / 2, divider[1] - 0.5 / 2, np.radians(-90)), (rl / 2, divider[1] + 0.5 / 2, np.radians(180))] if divider is not None else [None, None]
+        for cr in corners:
             for vs in tri:
-                st.append(([list(map(float, v)) for v in vs], (float(x), float(y), float(heading)), 0.02, 3))
+                st.append(([list(map(float, v)) for v in vs], (float(cr[0]), float(cr[1]), float(cr[2])), 0.02, 3) if cr is not None else empty)
         self.statics = st
         ns = len(st)
         self.st_nv = np.array([len(s[0]) for s in st], dtype=np.int32)
         self.st_verts = np.zeros((ns, 4, 2), dtype=np.float64)
         for k, s in enumerate(st):
-            self.st_verts[k, :len(s[0])] = np.asarray(s[0], dtype=np.float64)
+            if len(s[0]):
+                self.st_verts[k, :len(s[0])] = np.asarray(s[0], dtype=np.float64)
         self.st_pose = np.array([s[1] for s in st], dtype=np.float64)
         self.st_rad = np.array([s[2] for s in st], dtype=np.float64)
         self.st_ctype = np.array([s[3] for s in st], dtype=np.int32)
@@ -168,7 +192,7 @@ class RoomMaps:
         small_map = np.zeros((LW + 20, LW + 20), dtype=np.float32)
         off = int(lmw * ppm / 2) + 10
         for verts, pose, _, ctype in st:
-            if ctype != 3:
+            if ctype != 3 or len(verts) == 0:
                 continue
             cs, sn = np.cos(pose[2]), np.sin(pose[2])
             v = np.asarray(verts, dtype=np.float64)
@@ -208,11 +232,12 @@ class BoxDeliveryVecEnv:
 
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
                  seed: Optional[int] = None, force_box_spfa: bool = False, env_offset: int = 0, _backend=None,
-                 layout_pool_episodes: Optional[int] = None):
+                 layout_pool_episodes: Optional[int] = None, max_rooms: Optional[int] = 64,
+                 exact_spfa_parents: bool = False):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
-        if c["env"]["obstacle_config"] not in ("small_empty", "large_empty"):
-            raise NotImplementedError("only the rooms without columns / dividers are implemented (obstacle_config small_empty)")
+        if c["env"]["obstacle_config"] not in ("small_empty", "large_empty", "small_columns", "large_columns", "large_divider"):
+            raise ValueError("Invalid obstacle config: %r" % (c["env"]["obstacle_config"],))
         if c["agent"]["action_type"] not in ("heading", "position", "velocity"):
             raise NotImplementedError("unknown action_type %r" % (c["agent"]["action_type"],))
         if c["teleop_mode"]:
@@ -235,7 +260,8 @@ class BoxDeliveryVecEnv:
         small = c["env"]["obstacle_config"].split("_")[0] == "small"
         self.num_boxes = NB = int(c["boxes"]["num_boxes_small"] if small else c["boxes"]["num_boxes_large"])
         self.num_channels = 4
-        self.room = RoomMaps(c)
+        per_layout_rooms = not c["env"]["obstacle_config"].endswith("_empty")
+        self.room = RoomMaps(c, {"columns": [], "divider": [0.0, 0.0]} if per_layout_rooms else None)      # sizes and constants only
         self.local_map_pixel_width = LW = self.room.LW
         self.goal_points = [self.room.receptacle_position]
         if layouts is None:
@@ -245,14 +271,21 @@ class BoxDeliveryVecEnv:
             # f * LAYOUT_EPISODE_STRIDE) — keyed by (GLOBAL env id, episode), so results depend neither on the number of ranks
             # (env_offset = first env of this rank's shard) nor on when other envs finish; an env's episode k runs on entry k mod F.
             F = default_pool_episodes(E) if layout_pool_episodes is None else max(1, int(layout_pool_episodes))
+            keys = [(f, e) for f in range(F) for e in range(E)]
+            if per_layout_rooms and max_rooms is not None:
+                # every layout of a column / divider configuration carries its own room maps (3 - 4 MB each on the device,
+                # built on the host): the pool is capped; env e's episode k then runs on entry (e + k * E) mod len(pool)
+                keys = keys[:max(1, int(max_rooms))]
             layouts = [sample_box_delivery_layout(np.random.RandomState(base + int(env_offset) + e + f * LAYOUT_EPISODE_STRIDE), c)
-                       for f in range(F) for e in range(E)]
+                       for f, e in keys]
         self.layouts = list(layouts)
+        self.rooms = [RoomMaps(c, l) for l in self.layouts] if per_layout_rooms else [self.room]
         # ---- native handle
         L = self._L
         k = BoxDelConfig()
         L.bp_boxdel_default_config(C.byref(k))
         rw = c["rewards_sam"] if c["train"]["job_type"] == "sam" else c["rewards"]
+        k.exact_spfa_parents = 1 if exact_spfa_parents else 0      # parity aid: the reference solver's own parent tie-breaks (slow)
         k.force_box_spfa = 1 if force_box_spfa else 0      # testing aid: solve spfa per box even when the exact shortcut applies
         k.n_envs = E; k.num_boxes = NB; k.device = self.device_index
         k.action_type = {"position": 0, "heading": 1, "velocity": 2}[c["agent"]["action_type"]]
@@ -277,7 +310,7 @@ class BoxDeliveryVecEnv:
         for i, v in enumerate(np.asarray(c["agent"]["wheel_vertices"], dtype=np.float64).reshape(-1)):
             k.wheel_verts[i] = float(v)
         k.bound_x = float(self.room.room_length); k.bound_y = float(self.room.room_width)     # D17: x clamps with map_height = room_length
-        self._finish_init(k, self.room, ch3_map=None)
+        self._finish_init(k, self.rooms, ch3_map=None)
 
     def _init_spaces(self):
         """The reference's spaces (box_delivery_env.py:157-173, area_clearing.py:200-221) as ``single_*``; ``action_space`` /
@@ -313,16 +346,25 @@ class BoxDeliveryVecEnv:
         boxes = np.zeros((nl, NB, 3), dtype=np.float64)
         for i, l in enumerate(self.layouts):
             boxes[i, :len(l["boxes"])] = np.asarray(l["boxes"], dtype=np.float64).reshape(-1, 3)
-        cs = np.ascontiguousarray(r.configuration_space.astype(np.uint8))
-        th = np.ascontiguousarray(r.configuration_space_thin.astype(np.uint8))
-        cl = np.ascontiguousarray(r.closest_cspace_indices.astype(np.int32))
-        sm = np.ascontiguousarray(r.small_obstacle_map.astype(np.uint8))
+        # rooms: one for the handle, or one per layout (column / divider configurations); every room array gains a leading axis
+        rooms = list(r) if isinstance(r, (list, tuple)) else [r]
+        r = rooms[0]
+        if len(rooms) > 1:
+            assert len(rooms) == nl, "one room per layout"
+        layout_room = np.arange(nl, dtype=np.int32) if len(rooms) > 1 else np.zeros(nl, dtype=np.int32)
+        stack = lambda f, dt: np.ascontiguousarray(np.stack([f(q) for q in rooms]).astype(dt))
+        cs = stack(lambda q: q.configuration_space, np.uint8)
+        th = stack(lambda q: q.configuration_space_thin, np.uint8)
+        cl = stack(lambda q: q.closest_cspace_indices, np.int32)
+        sm = stack(lambda q: q.small_obstacle_map, np.uint8)
         rc = np.ascontiguousarray((r.robot_state_channel * 255).astype(np.uint8))
         c3 = None if ch3_map is None else np.ascontiguousarray(ch3_map, dtype=np.float32)
-        self._check(L.bp_boxdel_load(self._h, nl, starts.ctypes.data, nbx.ctypes.data, boxes.ctypes.data, len(r.statics),
-                                     r.st_nv.ctypes.data, r.st_verts.ctypes.data, r.st_pose.ctypes.data, r.st_rad.ctypes.data, r.st_ctype.ctypes.data,
-                                     r.shape[0], r.shape[1], cs.ctypes.data, th.ctypes.data, cl.ctypes.data, sm.ctypes.data, rc.ctypes.data,
-                                     None if c3 is None else c3.ctypes.data))
+        st_nv = stack(lambda q: q.st_nv, np.int32); st_verts = stack(lambda q: q.st_verts, np.float64)
+        st_pose = stack(lambda q: q.st_pose, np.float64); st_rad = stack(lambda q: q.st_rad, np.float64); st_ctype = stack(lambda q: q.st_ctype, np.int32)
+        self._check(L.bp_boxdel_load_rooms(self._h, nl, starts.ctypes.data, nbx.ctypes.data, boxes.ctypes.data, len(rooms), layout_room.ctypes.data,
+                                           len(r.statics), st_nv.ctypes.data, st_verts.ctypes.data, st_pose.ctypes.data, st_rad.ctypes.data, st_ctype.ctypes.data,
+                                           r.shape[0], r.shape[1], cs.ctypes.data, th.ctypes.data, cl.ctypes.data, sm.ctypes.data, rc.ctypes.data,
+                                           None if c3 is None else c3.ctypes.data))
         # ---- buffers
         self._buf = {}
         self._alloc("obs", (E, LW, LW, 4), "uint8"); self._alloc("reward", (E,), "float64")

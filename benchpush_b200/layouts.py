@@ -267,38 +267,94 @@ def pack_maze_layouts(layouts, max_boxes: int | None = None):
     return nb, cen
 
 
+def _bd_robot_start(random_state, ag, room_length, room_width):
+    """get_random_robot_start (box_delivery_env.py:313-320)"""
+    size = max(ag["length"], ag["width"])
+    x = random_state.uniform(-room_length / 2 + size, room_length / 2 - size)
+    y = random_state.uniform(-room_width / 2 + size, room_width / 2 - size)
+    heading = random_state.uniform(0, 2 * np.pi)
+    return (float(x), float(y), float(heading))
+
+
+def _bd_columns(random_state, max_num_columns, room_length, room_width, rpos, rsize, start, robot_radius):
+    """add_random_columns (box_delivery_env.py:358-415): 1 .. max - 1 unit columns, 100 tries each.  A try that lands on the
+    receptacle or on the robot gives the column up (the reference ``break``s out of the retry loop there); a try that lands on
+    an earlier column is retried."""
+    num_columns = random_state.randint(1, max_num_columns)
+    column_length = column_width = 1
+    buffer_width = 0.8
+    col_min_dist = 2
+    cols = []
+    for _ in range(num_columns):
+        for _ in range(100):
+            x = random_state.uniform(-room_length / 2 + 2 * buffer_width + column_length / 2, room_length / 2 - 2 * buffer_width - column_length / 2)
+            y = random_state.uniform(-room_width / 2 + 2 * buffer_width + column_width / 2, room_width / 2 - 2 * buffer_width - column_width / 2)
+            if ((x - rpos[0]) ** 2 + (y - rpos[1]) ** 2) ** 0.5 <= col_min_dist / 2 + rsize / 2:
+                break
+            if ((x - start[0]) ** 2 + (y - start[1]) ** 2) ** 0.5 <= col_min_dist / 2 + robot_radius:
+                break
+            if any(((x - px) ** 2 + (y - py) ** 2) ** 0.5 <= col_min_dist for px, py in cols):
+                continue
+            cols.append([float(x), float(y)])
+            break
+    return cols
+
+
+def _bd_divider(random_state, ag, room_length, room_width, start, robot_radius):
+    """add_random_horiz_divider (box_delivery_env.py:417-462): an 8 x 0.5 divider attached to the right wall at a random y;
+    after 100 tries that touch the robot the ROBOT START is redrawn (robot_info['start_pos'], which is what the sim uses)."""
+    divider_length, divider_width, buffer_width = 8, 0.5, 3.5
+    for _ in range(100):
+        for _ in range(100):
+            x = room_length / 2 - divider_length / 2
+            y = random_state.uniform(-room_width / 2 + buffer_width + divider_width / 2, room_width / 2 - buffer_width - divider_width / 2)
+            if not (((x - start[0]) ** 2 + (y - start[1]) ** 2) ** 0.5 <= 3 * robot_radius):
+                return [float(x), float(y)], start
+        start = _bd_robot_start(random_state, ag, room_length, room_width)
+    return None, start
+
+
 def sample_box_delivery_layout(random_state, cfg) -> dict:
-    """One box-delivery episode layout drawn the way the reference draws it (box_delivery_env.py:313-320
-    get_random_robot_start, :509-546 generate_boxes) for a room without columns / dividers: the robot start
-    first (when cfg.agent.random_start), then boxes by rejection sampling against the receptacle and the boxes
-    placed so far.  ``random_state`` is a numpy RandomState (the reference shares RandomState(cfg.misc.random_seed)
-    across episodes; a vector env gives each env its own stream)."""
+    """One box-delivery episode layout drawn the way the reference draws it at every reset (box_delivery_env.py:246-252:
+    get_random_robot_start :313-320, generate_boundary :326-507 — the random columns / the divider of the obstacle_config —
+    then generate_boxes :509-546 by rejection sampling against the receptacle, the columns / divider and the boxes placed so
+    far).  ``random_state`` is a numpy RandomState (the reference shares RandomState(cfg.misc.random_seed) across episodes; a
+    vector env gives each (env, episode) its own stream).  Keys: start, boxes, columns [[x, y], ...], divider [x, y] | None."""
     env, ag, bx = cfg["env"], cfg["agent"], cfg["boxes"]
     room_length = env["room_length"]
-    small = env["obstacle_config"].split("_")[0] == "small"
+    oc = env["obstacle_config"]
+    small = oc.split("_")[0] == "small"
     room_width = env["room_width_small"] if small else env["room_width_large"]
     num_boxes = bx["num_boxes_small"] if small else bx["num_boxes_large"]
-    if ag["random_start"]:
-        size = max(ag["length"], ag["width"])
-        x = random_state.uniform(-room_length / 2 + size, room_length / 2 - size)
-        y = random_state.uniform(-room_width / 2 + size, room_width / 2 - size)
-        heading = random_state.uniform(0, 2 * np.pi)
-        start = (float(x), float(y), float(heading))
-    else:
-        start = (5.0, 1.5, float(np.pi * 3 / 2))
+    start = _bd_robot_start(random_state, ag, room_length, room_width) if ag["random_start"] else (5.0, 1.5, float(np.pi * 3 / 2))
     rsize = env["receptacle_width"]
     rx, ry = room_length / 2 - rsize / 2, room_width / 2 - rsize / 2
+    robot_radius = ((ag["length"] ** 2 + ag["width"] ** 2) ** 0.5 / 2) * 1.2
+    columns, divider = [], None
+    if oc in ("small_columns", "large_columns"):
+        columns = _bd_columns(random_state, 3 if small else 8, room_length, room_width, (rx, ry), rsize, start, robot_radius)
+    elif oc == "large_divider":
+        divider, start = _bd_divider(random_state, ag, room_length, room_width, start, robot_radius)
+    elif not oc.endswith("_empty"):
+        raise ValueError("Invalid obstacle config: %r" % (oc,))
     half = bx["box_size"] / 2
     dmin = bx["min_box_dist"]
     min_x, max_x = -room_length / 2 + half, room_length / 2 - half
     min_y, max_y = -room_width / 2 + half, room_width / 2 - half
+    # obstacles generate_boxes tests: (position, 'width'); the divider by its y distance only
+    round_obstacles = [((rx, ry), rsize)] + [((cx, cy), 1) for cx, cy in columns]
     boxes = []
     while len(boxes) < num_boxes:
         cx = random_state.uniform(min_x, max_x)
         cy = random_state.uniform(min_y, max_y)
         hd = random_state.uniform(0, 2 * np.pi)
-        # the receptacle is the only boundary that is neither wall nor corner in an empty room ('width' = its size)
-        ok = not (((cx - rx) ** 2 + (cy - ry) ** 2) ** 0.5 <= (dmin / 2 + rsize / 2) * 1.2)
+        ok = True
+        for (ox, oy), width in round_obstacles:
+            if ((cx - ox) ** 2 + (cy - oy) ** 2) ** 0.5 <= (dmin / 2 + width / 2) * 1.2:
+                ok = False
+                break
+        if ok and divider is not None and abs(cy - divider[1]) <= (dmin / 2 + 0.5 / 2) * 1.2:
+            ok = False
         if ok:
             for px, py, _ in boxes:
                 if ((cx - px) ** 2 + (cy - py) ** 2) ** 0.5 <= dmin:
@@ -306,7 +362,7 @@ def sample_box_delivery_layout(random_state, cfg) -> dict:
                     break
         if ok:
             boxes.append([float(cx), float(cy), float(hd)])
-    return {"start": start, "boxes": boxes}
+    return {"start": start, "boxes": boxes, "columns": columns, "divider": divider}
 
 
 def sample_area_clearing_layout(rng, cfg, env_cfg) -> dict:

@@ -11,9 +11,11 @@ import torch
 from . import _lib
 
 
-def spfa_batch(maps: torch.Tensor, sources: torch.Tensor):
+def spfa_batch(maps: torch.Tensor, sources: torch.Tensor, reference_parents: bool = False):
     """maps: [B,H,W] (any dtype; non-zero = free, like pybind's bool cast), sources: [B,2] (row, col).
-    Returns (dists f32 [B,H,W], parents i32 [B,H,W]) on the same CUDA device, enqueued on the current stream."""
+    Returns (dists f32 [B,H,W], parents i32 [B,H,W]) on the same CUDA device, enqueued on the current stream.
+    reference_parents: parents in the reference solver's own tie-break order (bp_spfa_batch_exact: one thread per map restates
+    its queue; slow, synchronises); the default parents are a valid shortest-path tree with a fixed direction-order tie-break."""
     if not maps.is_cuda:
         raise _lib.BenchPushError("spfa_batch needs CUDA tensors (there is no CPU fallback)")
     B, H, W = maps.shape
@@ -25,12 +27,13 @@ def spfa_batch(maps: torch.Tensor, sources: torch.Tensor):
     p = torch.empty((B, H, W), dtype=torch.int32, device=maps.device)
     with torch.cuda.device(maps.device):
         st = C.c_void_p(torch.cuda.current_stream(maps.device).cuda_stream)
-        _lib.check(_lib.lib().bp_spfa_batch(C.c_void_p(m.data_ptr()), C.c_void_p(s.data_ptr()), B, H, W,
+        fn = _lib.lib().bp_spfa_batch_exact if reference_parents else _lib.lib().bp_spfa_batch
+        _lib.check(fn(C.c_void_p(m.data_ptr()), C.c_void_p(s.data_ptr()), B, H, W,
                                             C.c_void_p(d.data_ptr()), C.c_void_p(p.data_ptr()), st))
     return d, p
 
 
-def spfa(input_map, source):
+def spfa(input_map, source, reference_parents: bool = False):
     """Drop-in for ``spfa.spfa(input_map, source)`` (numpy in, numpy out) running on the GPU."""
     m = np.ascontiguousarray(np.asarray(input_map).astype(bool).astype(np.uint8))
     H, W = m.shape
@@ -39,5 +42,6 @@ def spfa(input_map, source):
     src = np.array([[int(source[0]), int(source[1])]], dtype=np.int32)
     d = np.empty((H, W), dtype=np.float32)
     p = np.empty((H, W), dtype=np.int32)
-    _lib.check(_lib.lib().bp_spfa_batch_host(m.ctypes.data, src.ctypes.data, 1, H, W, d.ctypes.data, p.ctypes.data))
+    fn = _lib.lib().bp_spfa_batch_exact_host if reference_parents else _lib.lib().bp_spfa_batch_host
+    _lib.check(fn(m.ctypes.data, src.ctypes.data, 1, H, W, d.ctypes.data, p.ctypes.data))
     return d, p

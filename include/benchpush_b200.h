@@ -289,6 +289,14 @@ int bp_spfa_batch(const uint8_t* maps, const int32_t* sources, int32_t batch, in
 /* scratch-free host-buffer variant (copies in, runs, copies out, synchronises) */
 int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t height, int32_t width,
                        float* dists, int32_t* parents);
+/* Same signatures, REFERENCE-ORDER parents: the reference solver's queue discipline (main.cpp:62-85: FIFO with the
+ * small-label-first swap, parent recorded at every strict improvement) restated by one thread per map, so parents[] equals
+ * spfa.spfa's own output also where equal-cost predecessors tie.  Sequential per map by construction — for parity runs and for
+ * callers that walk the parent chain; bp_spfa_batch_exact synchronises `stream` before returning (it frees its scratch). */
+int bp_spfa_batch_exact(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t height, int32_t width,
+                        float* dists, int32_t* parents, void* stream);
+int bp_spfa_batch_exact_host(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t height, int32_t width,
+                             float* dists, int32_t* parents);
 
 /* ------------------------------------------------------------------------------------------------
  * box-delivery-v0.  Replaces BoxDeliveryEnv.reset / step / generate_observation
@@ -329,7 +337,9 @@ typedef struct bp_boxdel_config {
     double static_e, static_u;    /* elasticity / friction of the static shapes (0.01, 1.0 box-delivery; 0, 0.99 area-clearing) */
     double robot_code, box_code, box_done_code;   /* overhead-map segment indices of the robot, boxes, completed boxes */
     double footprint_verts[8];    /* polygon drawn for the robot (area-clearing: cfg.agent.footprint_vertices; 0 = chassis hull) */
-    int32_t n_footprint, reserved1;
+    int32_t n_footprint;
+    int32_t exact_spfa_parents;   /* 1: robot paths / box distances follow the reference solver's own parent tie-breaks (its queue restated by one
+                                   * thread per solve: slow; for parity runs).  0: deterministic parents, same distances */
     double boundary[16], goals[128];
     double r_boundary, r_cleared, r_putback, r_push_mult, r_terminal, r_truncation, r_nonmove;   /* area_clearing.py:41-52 */
 } bp_boxdel_config;
@@ -353,6 +363,19 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
                    int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
                    int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
                    const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map);
+/* Rooms that differ between layouts (obstacle_config small_columns / large_columns / large_divider: the reference redraws the
+ * columns / the divider at every reset, box_delivery_env.py:358-471, and rebuilds its configuration space, :1140-1175).
+ * Every array of bp_boxdel_load that describes the room gains a leading axis of n_rooms: st_nv / st_rad / st_ctype
+ * [n_rooms][n_static], st_verts [n_rooms][n_static][4][2], st_pose [n_rooms][n_static][3], cspace / cspace_thin
+ * [n_rooms][H][W], closest [n_rooms][2][H][W], small_free [n_rooms][S][S], ch3_map [n_rooms][H][W] or NULL (box-delivery:
+ * computed on the device, one spfa solve per room).  The static slots have the same types in every room; st_nv == 0 marks a
+ * collision_type-3 slot that room does not use (fewer columns than the maximum).  layout_room[n_layouts] names the room of
+ * each layout (NULL: room 0).  bp_boxdel_load is this call with n_rooms = 1. */
+int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                         int32_t n_rooms, const int32_t* layout_room,
+                         int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                         int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
+                         const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map);
 /* DEVICE pointers, enqueued on `stream`, no host synchronisation */
 int bp_boxdel_reset(bp_boxdel_t* h, const int32_t* layout_ids, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream);
 int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream);

@@ -281,23 +281,62 @@ def cv_line(img, p0, p1, color):
 
 # ---------------------------------------------------------------- layouts
 def sample_layout(random_state, cfg=None):
-    """One episode's robot start + boxes from the reference's sampler (box_delivery_env.py:313-320, 509-546)
-    for obstacle_config 'small_empty' / 'large_empty'-like rooms without columns or dividers."""
+    """One episode's robot start, random obstacles and boxes in the order init_box_delivery_env draws them
+    (box_delivery_env.py:241-252): get_random_robot_start :313-320, generate_boundary :326-507 (add_random_columns /
+    add_random_horiz_divider), generate_boxes :509-546.  Pinned to the reference's own methods by
+    tests/golden/ref_bd_layouts.npz (tools/make_ref_bd_layouts.py)."""
     cfg = merge_cfg(DEFAULT_CFG, cfg or {})
     room_length = cfg["env"]["room_length"]
-    small = cfg["env"]["obstacle_config"].split("_")[0] == "small"
+    oc = cfg["env"]["obstacle_config"]
+    small = oc.split("_")[0] == "small"
     room_width = cfg["env"]["room_width_small"] if small else cfg["env"]["room_width_large"]
     num_boxes = cfg["boxes"]["num_boxes_small"] if small else cfg["boxes"]["num_boxes_large"]
-    if cfg["agent"]["random_start"]:
-        size = max(cfg["agent"]["length"], cfg["agent"]["width"])
+    ag = cfg["agent"]
+
+    def random_start():
+        size = max(ag["length"], ag["width"])
         x = random_state.uniform(-room_length / 2 + size, room_length / 2 - size)
         y = random_state.uniform(-room_width / 2 + size, room_width / 2 - size)
         h = random_state.uniform(0, 2 * np.pi)
-        start = (x, y, h)
-    else:
-        start = (5, 1.5, np.pi * 3 / 2)
+        return (x, y, h)
+
+    start = random_start() if ag["random_start"] else (5, 1.5, np.pi * 3 / 2)
     rsize = cfg["env"]["receptacle_width"]
     rpos = (room_length / 2 - rsize / 2, room_width / 2 - rsize / 2)
+    robot_radius = ((ag["length"] ** 2 + ag["width"] ** 2) ** 0.5 / 2) * 1.2
+    columns, divider = [], None
+    if oc in ("small_columns", "large_columns"):
+        # add_random_columns: randint(1, max) columns, up to 100 tries each; hitting the receptacle / robot abandons the column
+        num_columns = random_state.randint(1, 3 if small else 8)
+        buffer_width, col_min_dist = 0.8, 2
+        for _ in range(num_columns):
+            for _ in range(100):
+                x = random_state.uniform(-room_length / 2 + 2 * buffer_width + 1 / 2, room_length / 2 - 2 * buffer_width - 1 / 2)
+                y = random_state.uniform(-room_width / 2 + 2 * buffer_width + 1 / 2, room_width / 2 - 2 * buffer_width - 1 / 2)
+                overlapped = False
+                if ((x - rpos[0]) ** 2 + (y - rpos[1]) ** 2) ** 0.5 <= col_min_dist / 2 + rsize / 2:
+                    break
+                if ((x - start[0]) ** 2 + (y - start[1]) ** 2) ** 0.5 <= col_min_dist / 2 + robot_radius:
+                    break
+                for pc in columns:
+                    if ((x - pc[0]) ** 2 + (y - pc[1]) ** 2) ** 0.5 <= col_min_dist:
+                        overlapped = True
+                        break
+                if not overlapped:
+                    columns.append([x, y])
+                    break
+    elif oc == "large_divider":
+        # add_random_horiz_divider: 100 x 100 tries; the robot start is redrawn after every 100 failures
+        for _ in range(100):
+            for _ in range(100):
+                x = room_length / 2 - 8 / 2
+                y = random_state.uniform(-room_width / 2 + 3.5 + 0.5 / 2, room_width / 2 - 3.5 - 0.5 / 2)
+                if not ((x - start[0]) ** 2 + (y - start[1]) ** 2) ** 0.5 <= 3 * robot_radius:
+                    divider = [x, y]
+                    break
+            if divider is not None:
+                break
+            start = random_start()
     box_size = cfg["boxes"]["box_size"] / 2
     dmin = cfg["boxes"]["min_box_dist"]
     min_x, max_x = -room_length / 2 + box_size, room_length / 2 - box_size
@@ -308,8 +347,12 @@ def sample_layout(random_state, cfg=None):
         cy = random_state.uniform(min_y, max_y)
         hd = random_state.uniform(0, 2 * np.pi)
         overlapped = False
-        # the only non-wall, non-corner boundary of an empty room is the receptacle ('width' = size)
-        if ((cx - rpos[0]) ** 2 + (cy - rpos[1]) ** 2) ** 0.5 <= (dmin / 2 + rsize / 2) * 1.2:
+        # boundary_dicts that are neither wall nor corner: the receptacle ('width' = size), columns ('width' = 1), the divider (y only)
+        for (ox, oy), width in [(rpos, rsize)] + [((c[0], c[1]), 1) for c in columns]:
+            if ((cx - ox) ** 2 + (cy - oy) ** 2) ** 0.5 <= (dmin / 2 + width / 2) * 1.2:
+                overlapped = True
+                break
+        if not overlapped and divider is not None and abs(cy - divider[1]) <= (dmin / 2 + 0.5 / 2) * 1.2:
             overlapped = True
         if not overlapped:
             for px, py, _ in boxes:
@@ -318,7 +361,8 @@ def sample_layout(random_state, cfg=None):
                     break
         if not overlapped:
             boxes.append([cx, cy, hd])
-    return {"start": tuple(float(v) for v in start), "boxes": [[float(a) for a in b] for b in boxes]}
+    return {"start": tuple(float(v) for v in start), "boxes": [[float(a) for a in b] for b in boxes],
+            "columns": [[float(a) for a in c] for c in columns], "divider": None if divider is None else [float(a) for a in divider]}
 
 
 # ---------------------------------------------------------------- the environment
@@ -326,7 +370,7 @@ class BoxDeliveryOracleEnv:
     def __init__(self, cfg=None, layouts=None, order_mode=1):
         self.cfg = merge_cfg(DEFAULT_CFG, cfg or {})
         c = self.cfg
-        assert c["env"]["obstacle_config"] in ("small_empty",), "only the obstacle-free rooms are restated"
+        assert c["env"]["obstacle_config"] in ("small_empty", "large_empty", "small_columns", "large_columns", "large_divider")
         self.order_mode = order_mode
         self.layouts = layouts
         self.local_map_pixel_width = c["env"]["local_map_pixel_width"] if c["train"]["job_type"] != "sam" else c["env"]["local_map_pixel_width_sam"]
@@ -431,14 +475,31 @@ class BoxDeliveryOracleEnv:
             s = sp.add_poly(b, rect(x, y, length, width), 0.0)
             sp.set_material(s, 0.01, 1.0, 3)
             self.boundary_shapes.append((b, s, "wall"))
+        # random obstacles of the layout (generate_boundary :358-471; create_static: no radius): unit columns, or the 8 x 0.5 divider
+        for (x, y) in layout.get("columns") or []:
+            b = sp.add_body(cpo.STATIC, 0, 0, 0)
+            s = sp.add_poly(b, rect(x, y, 1, 1), 0.0)
+            sp.set_material(s, 0.01, 1.0, 3)
+            self.boundary_shapes.append((b, s, "column"))
+        divider = layout.get("divider")
+        if divider is not None:
+            b = sp.add_body(cpo.STATIC, 0, 0, 0)
+            s = sp.add_poly(b, rect(divider[0], divider[1], 8, 0.5), 0.0)
+            sp.set_material(s, 0.01, 1.0, 3)
+            self.boundary_shapes.append((b, s, "divider"))
         s225, c225 = np.sin(22.5 * np.pi / 180), np.cos(22.5 * np.pi / 180)
         vs1 = [(0, 0), (0, -1), (0.5 * s225, -1 + 0.5 * c225)]
         vs2 = [(0, 0), (0.5 * s225, -1 + 0.5 * c225), (1 - 0.5 * c225, -0.5 * s225)]
         vs3 = [(0, 0), (1, 0), (1 - 0.5 * c225, -0.5 * s225)]
+        corners = []
         for i, (x, y) in enumerate([(-rl / 2, rwid / 2), (rl / 2, rwid / 2), (rl / 2, -rwid / 2), (-rl / 2, -rwid / 2)]):
             if i == 1:
                 continue
-            heading = -np.radians(i * 90)
+            corners.append((x, y, -np.radians(i * 90)))
+        if divider is not None:             # corners where the divider meets the right wall (:491-505)
+            corners.append((rl / 2, divider[1] - 0.5 / 2, np.radians(-90)))
+            corners.append((rl / 2, divider[1] + 0.5 / 2, np.radians(180)))
+        for (x, y, heading) in corners:
             for vs in (vs1, vs2, vs3):
                 b = sp.add_body(cpo.STATIC, x, y, heading)
                 s = sp.add_poly(b, np.asarray(vs, dtype=np.float64), 0.02)

@@ -123,6 +123,14 @@ class Emu:
         n = self.L.emu_centroid_cache(self.h, C.c_int(env), _dp(out))
         return out[:2 * n]
 
+    def spfa_serial(self, m, source):
+        m = np.ascontiguousarray(np.asarray(m).astype(bool).astype(np.uint8))
+        H, W = m.shape
+        d = np.zeros((H, W), dtype=np.float32); p = np.zeros((H, W), dtype=np.int32)
+        self.L.emu_spfa_serial(m.ctypes.data_as(C.c_void_p), C.c_int(H), C.c_int(W), C.c_int(int(source[0])), C.c_int(int(source[1])),
+                               d.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p))
+        return d, p
+
     def world_verts(self, env, b):
         out = np.zeros(2 * 64, dtype=np.float64)
         n = self.L.emu_world_verts(self.h, C.c_int(env), C.c_int(b), _dp(out))

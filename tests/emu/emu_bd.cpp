@@ -70,47 +70,55 @@ int bp_boxdel_create(const bp_boxdel_config* cfg, bp_boxdel_t** out) {
 }
 int bp_boxdel_destroy(bp_boxdel_t* h) { delete h; return 0; }
 
-int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
-                   int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
-                   int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
-                   const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map) {
-    std::string err = bd_host_build(h->HB, h->cfg, n_layouts, starts, n_boxes, boxes, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype, H, W);
+int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                         int32_t n_rooms, const int32_t* layout_room,
+                         int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                         int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
+                         const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map) {
+    std::string err = bd_host_build(h->HB, h->cfg, n_layouts, starts, n_boxes, boxes, n_rooms, layout_room, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype, H, W);
     if (!err.empty()) { fprintf(stderr, "emu_bd: %s\n", err.c_str()); return -1; }
     BdConst& K = h->HB.K;
     const BdParams& P = K.P;
-    size_t nv = (size_t)H * W;
-    h->cspace.assign(cspace, cspace + nv); h->thin.assign(cspace_thin, cspace_thin + nv); h->closest.assign(closest, closest + 2 * nv);
-    h->small_free.assign(small_free, small_free + (size_t)P.SMALL * P.SMALL); h->rchan.assign(robot_chan, robot_chan + (size_t)P.LW * P.LW);
-    h->recept.assign(nv, 0.0f);
+    const size_t nv = (size_t)H * W, R = (size_t)n_rooms;
+    h->cspace.assign(cspace, cspace + R * nv); h->thin.assign(cspace_thin, cspace_thin + R * nv); h->closest.assign(closest, closest + 2 * R * nv);
+    h->small_free.assign(small_free, small_free + R * P.SMALL * P.SMALL); h->rchan.assign(robot_chan, robot_chan + (size_t)P.LW * P.LW);
+    h->recept.assign(R * nv, 0.0f);
     K.layouts = h->HB.LY.data(); K.pair_a = h->HB.pa.data(); K.pair_b = h->HB.pb.data();
+    K.rooms = h->HB.RM.data(); K.n_rooms = n_rooms;
     K.cspace = h->cspace.data(); K.cspace_thin = h->thin.data(); K.closest = h->closest.data(); K.small_free = h->small_free.data();
     K.robot_chan = h->rchan.data(); K.ch3_map = h->recept.data();
     h->envs.assign(K.env_bytes * h->cfg.n_envs, 0);
     K.envs = h->envs.data();
     h->scratch.assign(bd_scratch_ints(P), 0);
-    for (int k = 0; k < P.n_static; k++) bd_init_static(K.S, k);
-    if (ch3_map) h->recept.assign(ch3_map, ch3_map + nv);
-    else {
-        int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
-        pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
-        int si = closest[(size_t)pi * W + pj], sj = closest[nv + (size_t)pi * W + pj];
-        std::vector<int32_t> par(nv);
-        SpfaShared S;
-        spfa_block(S, h->cspace.data(), H, W, si, sj, h->recept.data(), par.data(), h->scratch.data(), h->scratch.data() + nv, h->scratch.data() + 2 * nv);
-        bd_scale_receptacle_map(P, h->recept.data(), nv);
+    int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
+    pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
+    int vis = 1;
+    for (size_t r = 0; r < R; r++) {
+        BdStatics& T = h->HB.RM[r];
+        for (int k = 0; k < P.n_static; k++) bd_init_static(T, k);
+        const int32_t* cl = closest + r * 2 * nv;
+        T.recept_ci = cl[(size_t)pi * W + pj]; T.recept_cj = cl[nv + (size_t)pi * W + pj];
+        if (ch3_map) std::copy(ch3_map + r * nv, ch3_map + (r + 1) * nv, h->recept.begin() + r * nv);
+        else {
+            std::vector<int32_t> par(nv);
+            SpfaShared S;
+            spfa_block(S, h->cspace.data() + r * nv, H, W, T.recept_ci, T.recept_cj, h->recept.data() + r * nv, par.data(), h->scratch.data(), h->scratch.data() + nv, h->scratch.data() + 2 * nv);
+            bd_scale_receptacle_map(P, h->recept.data() + r * nv, nv);
+        }
+        if (h->cfg.env_kind == 0) for (size_t v = 0; v < nv && vis; v++) if (!bd_cell_visible(K, (int)r, (int)v)) vis = 0;
     }
-    K.ch3_map = h->recept.data();
-    {
-        int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
-        pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
-        K.P.recept_ci = closest[(size_t)pi * W + pj]; K.P.recept_cj = closest[nv + (size_t)pi * W + pj];
-        int vis = 1;
-        if (h->cfg.env_kind == 0) for (size_t v = 0; v < nv && vis; v++) if (!bd_cell_visible(K, (int)v)) vis = 0;
-        K.P.recept_visible = (vis && !h->cfg.force_box_spfa) ? 1 : 0;
-        if (h->cfg.env_kind == 1) K.P.recept_visible = 1;      // no receptacle distances in area-clearing
-    }
+    K.P.recept_visible = (vis && !h->cfg.force_box_spfa) ? 1 : 0;
+    if (h->cfg.env_kind == 1) K.P.recept_visible = 1;      // no receptacle distances in area-clearing
     h->loaded = true;
     return 0;
+}
+
+int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                   int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                   int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
+                   const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map) {
+    return bp_boxdel_load_rooms(h, n_layouts, starts, n_boxes, boxes, 1, nullptr, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype,
+                                H, W, cspace, cspace_thin, closest, small_free, robot_chan, ch3_map);
 }
 
 static void emu_obs(bp_boxdel* h, const uint8_t* mask, uint8_t* obs) {

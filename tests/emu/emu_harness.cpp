@@ -206,6 +206,14 @@ int emu_centroid_cache(void* h, int env, double* out) {
     for (int b = 0; b < ev.sc->robot; b++) if (body_dynamic(L, b)) { out[2 * n] = ev.cenx[b]; out[2 * n + 1] = ev.ceny[b]; n++; }
     return n;
 }
+// spfa_serial_parents (the reference solver's queue restated), reference output convention
+void emu_spfa_serial(const uint8_t* map, int H, int W, int si, int sj, float* dist, int32_t* parents) {
+    size_t nv = (size_t)H * W;
+    std::vector<int> ring(nv + 2); std::vector<unsigned char> inq(nv);
+    spfa_serial_parents(map, H, W, si, sj, dist, parents, ring.data(), inq.data());
+    const float inf = 2.0f * (float)nv;
+    for (size_t v = 0; v < nv; v++) if (!(dist[v] < inf)) dist[v] = 0.0f;
+}
 // world-space hull vertices of body b as the kernels hold them (ev.wv), widened to double; returns the vertex count
 int emu_world_verts(void* h, int env, int b, double* out) {
     Emu* e = (Emu*)h;

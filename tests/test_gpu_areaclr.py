@@ -98,6 +98,30 @@ def test_walled_environments_match_the_oracle_gpu(name, portable_trig):
     env.close()
 
 
+def test_walled_columns_with_the_reference_parent_order_gpu(portable_trig):
+    """exact_spfa_parents: the robot's spfa paths follow the reference solver's own parent tie-breaks (one thread restates its
+    queue, csrc/spfa.cuh spfa_serial_parents), so every step of every compared env matches the oracle — no tie allowance."""
+    from benchpush_b200.envs import AreaClearingVecEnv
+    from oracle.area_clearing_oracle import AreaClearingOracleEnv, sample_layout
+    cfg = {"env": "walled_env_with_columns", "num_obstacles": 6}
+    lays = [sample_layout(random.Random(s), cfg) for s in range(7, 11)]
+    env = AreaClearingVecEnv(num_envs=4, cfg=cfg, layouts=lays, device=0, exact_spfa_parents=True)
+    oras = {e: AreaClearingOracleEnv(cfg=cfg, layouts=[lays[e]]) for e in (0, 1, 3)}
+    env.reset()
+    for ora in oras.values():
+        ora.reset()
+    rng = np.random.default_rng(2)
+    spfa = 0
+    for k in range(8):
+        a = rng.uniform(-1, 1, size=4).astype(np.float32)
+        out = env.step(a)
+        for e, ora in oras.items():
+            compare_step(env, ora, e, float(a[e]), out, state_tol=1e-7)
+            spfa += env.get_step_debug(e)["need_spfa"]
+    assert spfa >= 1, "the scenario should route at least one path around a wall or column"
+    env.close()
+
+
 def test_velocity_actions_and_low_dim_state_gpu(portable_trig):
     """action_type velocity (area_clearing.py:656-663) against the oracle; cfg.low_dim_state returns the centroid vector."""
     from benchpush_b200.envs import AreaClearingVecEnv

@@ -182,3 +182,41 @@ def test_literal_per_box_spfa_path_on_the_gpu(portable_trig):
             assert np.array_equal(fast.get_step_debug(e)["init_dist"], slow.get_step_debug(e)["init_dist"])
             assert np.array_equal(fast.get_bodies(e), slow.get_bodies(e))
     fast.close(); slow.close()
+
+
+@pytest.mark.parametrize("oc,seeds,steps", [("small_columns", (4, 0, 2, 7), 8), ("large_columns", (7, 1), 4), ("large_divider", (2, 5), 6)])
+def test_column_and_divider_rooms_match_the_oracle_gpu(portable_trig, oc, seeds, steps):
+    """obstacle_config small_columns / large_columns / large_divider (box_delivery_env.py:358-471): every layout carries its own
+    room (bp_boxdel_load_rooms).  With the reference solver's parent order (exact_spfa_parents) reset and every step of every
+    env match the oracle; afterwards the default (deterministic parents) handle reproduces the same reset and the same physics
+    for the steps whose robot path is a straight line."""
+    from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
+    from oracle.box_delivery_oracle import BoxDeliveryOracleEnv, sample_layout
+    cfg = {"agent": {"action_type": "heading"}, "env": {"obstacle_config": oc}}
+    lays = [sample_layout(np.random.RandomState(s), cfg) for s in seeds]
+    n = len(lays)
+    env = BoxDeliveryVecEnv(num_envs=n, cfg=cfg, layouts=lays, device=0, exact_spfa_parents=True)
+    fast = BoxDeliveryVecEnv(num_envs=n, cfg=cfg, layouts=lays, device=0)
+    oras = [BoxDeliveryOracleEnv(cfg=cfg, layouts=[l]) for l in lays]
+    obs, info = env.reset()
+    fobs, _ = fast.reset()
+    assert np.array_equal(obs.cpu().numpy(), fobs.cpu().numpy())
+    for e, ora in enumerate(oras):
+        oobs, _ = ora.reset()
+        assert np.array_equal(env.rooms[e].configuration_space, ora.configuration_space)
+        assert np.array_equal(env.rooms[e].closest_cspace_indices, ora.closest_cspace_indices)
+        assert np.array_equal(obs[e].cpu().numpy(), oobs), e
+        assert np.array_equal(env.get_bodies(e)[:, :6], ora.space.state()[:1 + env.num_boxes])
+    rng = np.random.default_rng(0)
+    same = np.ones(n, dtype=bool)
+    for k in range(steps):
+        a = rng.uniform(-1, 1, size=n).astype(np.float32)
+        out = env.step(a)
+        fast.step(a)
+        for e, ora in enumerate(oras):
+            compare_step(env, ora, e, None, float(a[e]), step_out=out, state_tol=1e-7)
+            same[e] &= fast.get_step_debug(e)["need_spfa"] == 0
+            if same[e]:
+                assert np.array_equal(fast.get_bodies(e), env.get_bodies(e)), (k, e)
+    assert int((env._buf["info_i"][:, 3] & ~16).max()) == 0
+    env.close(); fast.close()

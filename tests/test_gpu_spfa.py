@@ -28,6 +28,37 @@ def test_spfa_matches_reference_golden(spfa_golden):
         _valid_tree(d, p, c["map"])
 
 
+def test_reference_order_parents_are_bit_identical(spfa_golden):
+    """reference_parents=True (bp_spfa_batch_exact[_host]): the reference solver's queue restated by one thread per map —
+    dists AND parents equal the reference's own outputs (golden fixtures from main.cpp compiled in place), and the oracle
+    port at box-delivery size."""
+    from benchpush_b200.spfa import spfa, spfa_batch
+    for c in spfa_golden:
+        d, p = spfa(c["map"], c["source"], reference_parents=True)
+        assert np.array_equal(d, c["dists"]) and np.array_equal(p, c["parents"])
+    rng = np.random.default_rng(8)
+    B, H, W = 3, 430, 542
+    maps = np.ones((B, H, W), dtype=np.uint8)
+    maps[:, :14, :] = 0; maps[:, -14:, :] = 0; maps[:, :, :14] = 0; maps[:, :, -14:] = 0
+    for b in range(B):
+        for _ in range(10):
+            i, j = rng.integers(20, H - 60), rng.integers(20, W - 60)
+            maps[b, i:i + rng.integers(10, 50), j:j + rng.integers(10, 50)] = 0
+    src = np.stack([rng.integers(15, 19, B), rng.integers(15, 19, B)], axis=1).astype(np.int32)
+    for b in range(B):
+        maps[b, src[b, 0], src[b, 1]] = 1
+    d, p = spfa_batch(torch.as_tensor(maps, device="cuda"), torch.as_tensor(src, device="cuda"), reference_parents=True)
+    d, p = d.cpu().numpy(), p.cpu().numpy()
+    ties = 0
+    d2, p2 = spfa_batch(torch.as_tensor(maps, device="cuda"), torch.as_tensor(src, device="cuda"))
+    for b in range(B):
+        od, op = cpo.spfa(maps[b], src[b])
+        assert np.array_equal(d[b], od) and np.array_equal(p[b], op)
+        ties += int((p2[b].cpu().numpy() != op).sum())
+    assert np.array_equal(d2.cpu().numpy(), d)
+    assert ties > 0            # the default parents do differ from the reference's on tie cells: that is what the exact mode is for
+
+
 def test_spfa_batch_box_delivery_size():
     from benchpush_b200.spfa import spfa_batch
     rng = np.random.default_rng(5)

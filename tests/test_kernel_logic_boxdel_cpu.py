@@ -192,3 +192,60 @@ def test_low_dim_state_observation_of_the_room_envs():
             np.testing.assert_allclose(obs[e][:len(want)], want, rtol=1e-12)
             assert not obs[e][len(want):].any()
         env.close()
+
+
+# ---- obstacle_config small_columns / large_columns / large_divider: per-layout rooms (static shapes + maps indexed by layout)
+@pytest.mark.parametrize("oc,seed,steps", [("small_columns", 4, 10), ("large_columns", 7, 4), ("large_divider", 2, 9)])
+def test_column_and_divider_rooms_match_the_oracle(portable_trig, oc, seed, steps):
+    """The reference redraws columns / the divider at every reset and rebuilds its configuration space
+    (box_delivery_env.py:358-471, 1140-1175).  Room maps per layout equal the oracle's; with the reference solver's own
+    parent order (exact_spfa_parents) reset and every step — poses, path, per-box path distances through the reward,
+    observation bytes — match the oracle; the receptacle no longer sees every free cell, so the per-box solves run."""
+    cfg = {"agent": {"action_type": "heading"}, "env": {"obstacle_config": oc}}
+    lay = [sample_layout(np.random.RandomState(seed), cfg)]
+    assert lay[0]["columns"] or lay[0]["divider"]
+    env = BoxDeliveryVecEnv(num_envs=1, cfg=cfg, layouts=lay, _backend=emu_bd.lib(), exact_spfa_parents=True)
+    ora = BoxDeliveryOracleEnv(cfg=cfg, layouts=lay)
+    assert env._L.bp_boxdel_launch_count(env._h) == 0            # emulation: reports recept_visible
+    obs, info = env.reset()
+    oobs, oinfo = ora.reset()
+    r = env.rooms[0]
+    assert np.array_equal(r.configuration_space, ora.configuration_space) and np.array_equal(r.configuration_space_thin, ora.configuration_space_thin)
+    assert np.array_equal(r.closest_cspace_indices, ora.closest_cspace_indices) and np.array_equal(r.small_obstacle_map, ora.small_obstacle_map)
+    assert np.array_equal(obs[0], oobs)
+    assert np.array_equal(env.get_bodies(0)[:, :6], ora.space.state()[:1 + env.num_boxes])
+    rng = np.random.default_rng(0)
+    spfa = 0
+    for k in range(steps):
+        a = float(np.float32(rng.uniform(-1, 1)))
+        spfa += compare_step(env, ora, 0, a, a, state_tol=1e-9)["spfa"]
+    if oc != "large_columns":
+        assert spfa >= 1
+    env.close()
+
+
+def test_rooms_are_indexed_by_layout_and_default_parents_keep_the_physics(portable_trig):
+    """Three envs on three different rooms of one handle (0, 1 and 2 columns): each matches its own oracle at reset (maps, raster,
+    bodies), and with the default deterministic parents the poses still match while the robot's path needs no spfa solve
+    (box path distances may follow another equal-cost staircase: DESIGN 5.4)."""
+    cfg = {"agent": {"action_type": "heading"}, "env": {"obstacle_config": "small_columns"}}
+    lays = [sample_layout(np.random.RandomState(s), cfg) for s in (2, 0, 4)]
+    assert [len(l["columns"]) for l in lays] == [0, 1, 2]
+    env = BoxDeliveryVecEnv(num_envs=3, cfg=cfg, layouts=lays, _backend=emu_bd.lib())
+    oras = [BoxDeliveryOracleEnv(cfg=cfg, layouts=[l]) for l in lays]
+    obs, info = env.reset()
+    for e, ora in enumerate(oras):
+        oobs, _ = ora.reset()
+        assert np.array_equal(env.rooms[e].configuration_space, ora.configuration_space)
+        assert np.array_equal(obs[e], oobs), e
+        assert np.array_equal(env.get_bodies(e)[:, :6], ora.space.state()[:1 + env.num_boxes])
+    acts = np.array([0.3, -0.6, 0.9], dtype=np.float32)
+    env.step(acts)
+    for e, ora in enumerate(oras):
+        ora.step(float(acts[e]), want_obs=False) if "want_obs" in ora.step.__code__.co_varnames else ora.step(float(acts[e]))
+        if env.get_step_debug(e)["need_spfa"] == 0:
+            gb = env.get_bodies(e)
+            alive = gb[1:, 6] == 1
+            assert np.abs(gb[0, :3] - ora.space.state()[0, :3]).max() <= 1e-9
+            assert np.abs(gb[1:][alive][:, :3] - ora.space.state()[list(ora.box_bodies)][:, :3]).max() <= 1e-9
+    env.close()

@@ -92,6 +92,31 @@ def test_awake_set_is_small_and_exact(golden_layouts):
     assert sc["status"] == 0
 
 
+def test_emulated_reference_order_parents_are_bit_identical(spfa_golden, golden_layouts):
+    """spfa_serial_parents (csrc/spfa.cuh, behind bp_spfa_batch_exact and the envs' exact_spfa_parents mode): dists and PARENTS
+    equal the reference's own outputs (golden fixtures), the compiled reference run live (oracle/_ref, when built) and the
+    oracle port on random maps incl. a blocked source."""
+    import os, sys
+    emu = Emu(1, golden_layouts["c10_t0"], SHIP_VERTS)
+    for c in spfa_golden:
+        d, p = emu.spfa_serial(c["map"], c["source"])
+        assert np.array_equal(d, c["dists"]) and np.array_equal(p, c["parents"])
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    ref_spfa = None
+    if os.path.isdir(ref_dir) and any(f.startswith("spfa") for f in os.listdir(ref_dir)):
+        sys.path.insert(0, ref_dir)
+        import spfa as ref_spfa
+    rng = np.random.default_rng(3)
+    for H, W in [(1, 1), (3, 4), (60, 45), (120, 150)]:
+        m = rng.random((H, W)) > 0.25
+        src = (int(rng.integers(0, H)), int(rng.integers(0, W)))
+        for blocked in (False, True):
+            m[src] = not blocked
+            d, p = emu.spfa_serial(m, src)
+            od, op = (ref_spfa.spfa(m, src) if ref_spfa is not None else cpo.spfa(m, src))
+            assert np.array_equal(d, od) and np.array_equal(p, op), (H, W, blocked)
+
+
 def test_emulated_spfa_matches_reference_golden(spfa_golden, golden_layouts):
     emu = Emu(1, golden_layouts["c10_t0"], SHIP_VERTS)
     for c in spfa_golden:

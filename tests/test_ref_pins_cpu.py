@@ -185,3 +185,32 @@ def test_position_controller_waypoints(ref):
         np.testing.assert_allclose(np.asarray([p[:2] for p in path], dtype=np.float64), want, rtol=0, atol=1e-12)
         multi += n > 2
     assert multi >= 2, "the fixture should contain paths that go around the columns"
+
+
+def test_box_delivery_layouts_follow_the_reference_sampler():
+    """get_random_robot_start + generate_boundary (random columns / divider) + generate_boxes of the reference's BoxDeliveryEnv
+    (box_delivery_env.py:313-320, 326-507, 509-559), run on seeded RandomStates by tools/make_ref_bd_layouts.py: the product's
+    sampler and the oracle's give the same start, obstacles and boxes for every obstacle_config."""
+    from benchpush_b200.envs.box_delivery import DEFAULT_CFG
+    from benchpush_b200.layouts import sample_box_delivery_layout
+    from benchpush_b200.utils import DotDict, merge_cfg
+    from oracle.box_delivery_oracle import sample_layout
+    g = np.load(os.path.join(GOLD, "ref_bd_layouts.npz"))
+    n_obst = 0
+    for oc in g["configs"]:
+        cfg = {"env": {"obstacle_config": str(oc)}}
+        full = merge_cfg(DotDict(DEFAULT_CFG), cfg)
+        for seed in g["seeds"]:
+            k = "%s_%d_" % (oc, seed)
+            for lay in (sample_box_delivery_layout(np.random.RandomState(int(seed)), full), sample_layout(np.random.RandomState(int(seed)), cfg)):
+                assert np.array_equal(np.array(lay["start"]), g[k + "start"]), k
+                assert np.array_equal(np.array(lay["columns"], dtype=np.float64).reshape(-1, 2), g[k + "columns"]), k
+                assert np.array_equal(np.array([lay["divider"]] if lay["divider"] is not None else [], dtype=np.float64).reshape(-1, 2), g[k + "divider"]), k
+                assert np.array_equal(np.array(lay["boxes"]), g[k + "boxes"]), k
+            n_obst += len(g[k + "columns"]) + len(g[k + "divider"])
+    assert n_obst > 40                # the fixtures do contain columns and dividers
+    # boundary order of a divider room: receptacle, walls, divider, 3 room corners, 2 divider corners (-90 deg below, 180 deg above)
+    assert list(g["large_divider_0_types"]) == ["receptacle"] + ["wall"] * 4 + ["divider"] + ["corner"] * 5
+    c = g["large_divider_0_corners"]; d = g["large_divider_0_divider"][0]
+    np.testing.assert_allclose(c[3], [5.0, d[1] - 0.25, np.radians(-90)], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(c[4], [5.0, d[1] + 0.25, np.radians(180)], rtol=0, atol=1e-15)
