@@ -491,7 +491,7 @@ def run_boxdel(a):
     from benchpush_b200.envs import AreaClearingVecEnv, BoxDeliveryVecEnv
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    env = AreaClearingVecEnv(num_envs=n_envs, device=0) if area else BoxDeliveryVecEnv(num_envs=n_envs, cfg=bd_cfg(oc), device=0, max_rooms=a.rooms,
+    env = AreaClearingVecEnv(num_envs=n_envs, device=0, exact_spfa_parents=a.exact_parents) if area else BoxDeliveryVecEnv(num_envs=n_envs, cfg=bd_cfg(oc), device=0, max_rooms=a.rooms,
                                                                                          exact_spfa_parents=a.exact_parents)
     env.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(1234)

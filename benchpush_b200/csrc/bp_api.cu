@@ -272,16 +272,20 @@ __global__ void __launch_bounds__(512) k_spfa(const uint8_t* maps, const int32_t
     }
 }
 
-// one thread per map: the reference solver's queue restated (spfa_serial_parents), reference output convention (unreachable -> 0)
-__global__ void k_spfa_serial(const uint8_t* maps, const int32_t* sources, int batch, int H, int W, float* dists, int32_t* parents,
-                              int* ring, unsigned char* inq) {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per map: the lanes initialise, lane 0 restates the reference solver's queue (spfa_serial_run), the lanes apply the
+// reference's output convention (unreachable -> 0)
+__global__ void __launch_bounds__(32) k_spfa_serial(const uint8_t* maps, const int32_t* sources, int batch, int H, int W, float* dists, int32_t* parents,
+                                                     int* ring, unsigned char* inq) {
+    const int m = blockIdx.x;
     if (m >= batch) return;
     const size_t nv = (size_t)H * W;
     float* d = dists + m * nv;
-    spfa_serial_parents(maps + m * nv, H, W, sources[2 * m], sources[2 * m + 1], d, parents + m * nv, ring + m * (nv + 2), inq + m * nv);
+    spfa_serial_init((int)nv, d, parents + m * nv, inq + m * nv, threadIdx.x, 32);
+    __syncwarp();
+    if (threadIdx.x == 0) spfa_serial_run(maps + m * nv, H, W, sources[2 * m], sources[2 * m + 1], d, parents + m * nv, ring + m * (nv + 2), inq + m * nv);
+    __syncwarp();
     const float inf = 2.0f * (float)nv;
-    for (size_t v = 0; v < nv; v++) if (!(d[v] < inf)) d[v] = 0.0f;
+    for (size_t v = threadIdx.x; v < nv; v += 32) if (!(d[v] < inf)) d[v] = 0.0f;
 }
 
 // generate_observation_low_dim (ship_ice_env.py:358-370; maze_NAMO_env.py:488-504): |poly_centroid| of every movable
@@ -340,6 +344,7 @@ struct bp_shipice {
     bool warp_impl = false;        // BP_STEP_IMPL=warp: one env per warp (A/B measurements)
     int* perm = nullptr; int perm_cap = 0;   // step schedule (k_schedule); BP_NO_SCHEDULE=1 keeps the identity order
     bool use_schedule = true;
+    bool pad_batches = true;           // BP_NO_PAD=1 turns the partly-filled-batch schedule off (A/B measurements)
     bool res_impl = false;         // resident step (sim_res.cuh): the default for ship-ice; BP_STEP_IMPL=batch selects sim_batch.cuh
     int res_blocks_per_sm = 1;
     StepOut out;               // internal device outputs
@@ -513,6 +518,7 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
     }
     if (const char* e = getenv("BP_STEP_IMPL")) h->warp_impl = (strcmp(e, "warp") == 0);
     if (const char* e = getenv("BP_NO_SCHEDULE")) h->use_schedule = !(atoi(e) != 0);
+    if (const char* e = getenv("BP_NO_PAD")) h->pad_batches = !(atoi(e) != 0);
     // resident step (sim_res.cuh), ship-ice only (the per-substep checks of the maze run on the env block).  Selected with
     // BP_STEP_IMPL=res: in fp64 only three pools fit an SM, and three warps per SM issue too slowly to beat the batched
     // kernel (profiles/r02a_*), so the batched kernel stays the default.
@@ -622,12 +628,12 @@ static bool use_small_batches(bp_shipice* h) {
     if (const char* e = getenv("BP_FORCE_BK")) return atoi(e) == bk_small::BK;       // tuning experiments only
     return (long)h->d.n_envs * 2 <= (long)h->sm_count * BP_MIN_BLOCKS * 4 * bk_main::BK;
 }
-static int batch_grid(bp_shipice* h) {
+static int batch_grid(bp_shipice* h, int sched_batches = 0) {
     // 4 warps per block, BK envs per warp batch; never more warps than batches
     int blocks = h->sm_count * BP_MIN_BLOCKS;
     if (const char* e = getenv("BP_BLOCKS_PER_SM")) { int b = atoi(e); if (b > 0 && b < BP_MIN_BLOCKS) blocks = h->sm_count * b; }   // tuning experiments only
     int per_block = 4 * (use_small_batches(h) ? bk_small::BK : bk_main::BK);
-    int need = (h->d.n_envs + per_block - 1) / per_block;
+    int need = sched_batches ? (sched_batches + 3) / 4 : (h->d.n_envs + per_block - 1) / per_block;
     return blocks < need ? blocks : need;
 }
 
@@ -661,10 +667,15 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
     a.actions = actions; a.layout_ids = nullptr; a.mask = mask; a.counter = h->counter; a.auto_reset = h->cfg.auto_reset; a.C = h->d_const; a.use_snap = h->snap ? 1 : 0;
     a.perm = nullptr; a.n_sched = 0;
     prof_begin(h, 0, st);
+    int sched_batches = 0;
     if (h->use_schedule && !h->warp_impl) {
         const int bk = h->res_impl ? res::RK : (use_small_batches(h) ? bk_small::BK : bk_main::BK);
-        const int n_batches = (h->d.n_envs + bk - 1) / bk;
+        int n_batches = (h->d.n_envs + bk - 1) / bk;
         const int warp_slots = h->res_impl ? h->sm_count * h->res_blocks_per_sm : h->sm_count * BP_MIN_BLOCKS * 4;
+        // Fewer batches than resident warps (the per-GPU share of a strong-scaling run): spread the envs over ALL warp slots with
+        // partly filled batches (perm entries -1) instead of leaving slots idle — the step is latency bound, extra warps are free.
+        if (h->pad_batches && n_batches < warp_slots) n_batches = warp_slots < h->d.n_envs ? warp_slots : h->d.n_envs;
+        sched_batches = n_batches;
         if (!h->perm || h->perm_cap < n_batches * bk) {
             if (h->perm) cudaFree(h->perm);
             CUDA_TRY(cudaMalloc((void**)&h->perm, (size_t)n_batches * bk * 4));
@@ -675,13 +686,13 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
     }
     if (h->res_impl) {
         int blocks = h->sm_count * h->res_blocks_per_sm;
-        int need = (h->d.n_envs + res::RK - 1) / res::RK;
+        int need = sched_batches ? sched_batches : (h->d.n_envs + res::RK - 1) / res::RK;
         if (blocks > need) blocks = need;
         k_shipice_step_res<<<blocks, 32, sizeof(res::ResShared), st>>>(a);
     }
     else if (h->warp_impl) k_shipice_step_warp<<<sim_grid(h), 128, 0, st>>>(a);
-    else if (use_small_batches(h)) k_shipice_step_small<<<batch_grid(h), 128, 0, st>>>(a);
-    else k_shipice_step<<<batch_grid(h), 128, 0, st>>>(a);
+    else if (use_small_batches(h)) k_shipice_step_small<<<batch_grid(h, sched_batches), 128, 0, st>>>(a);
+    else k_shipice_step<<<batch_grid(h, sched_batches), 128, 0, st>>>(a);
     prof_end(h, st);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1094,7 +1105,7 @@ int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batc
     return rc;
 }
 
-// Reference-order parents (spfa.cuh spfa_serial_parents): one THREAD per map restates the reference solver's queue, so that
+// Reference-order parents (spfa.cuh spfa_serial_run): one warp per map, lane 0 restates the reference solver's queue, so that
 // parents[] equals spfa.spfa's own output also where several predecessors tie.  Distances are the same as bp_spfa_batch's.
 // Slow by construction (a sequential algorithm per map); meant for parity runs and for callers that walk the parents.
 int bp_spfa_batch_exact(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t H, int32_t W, float* dists, int32_t* parents, void* stream) {
@@ -1105,7 +1116,7 @@ int bp_spfa_batch_exact(const uint8_t* maps, const int32_t* sources, int32_t bat
     int* ring = nullptr; unsigned char* inq = nullptr;
     CUDA_TRY(cudaMalloc((void**)&ring, (size_t)batch * (nv + 2) * sizeof(int)));
     if (cudaMalloc((void**)&inq, (size_t)batch * nv) != cudaSuccess) { cudaFree(ring); return fail(BP_ERR_CUDA, "spfa scratch allocation failed"); }
-    k_spfa_serial<<<(batch + 31) / 32, 32, 0, st>>>(maps, sources, batch, H, W, dists, parents, ring, inq);
+    k_spfa_serial<<<batch, 32, 0, st>>>(maps, sources, batch, H, W, dists, parents, ring, inq);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);          // the scratch is released below
     cudaFree(ring); cudaFree(inq);

@@ -110,43 +110,67 @@ BP_DEV int spfa_parent_of(const uint8_t* map, int H, int W, const int* dist, int
 // waypoint).  dist[nv] receives the fp32 labels (2*H*W where unreachable), parents[nv] the predecessors (-1 = none).
 // ring: at least nv + 2 ints (at most nv vertices are queued at a time, so the reference's 8*nv linear queue folds into a
 // ring without changing which entries meet); inq: nv bytes.
-BP_DEV void spfa_serial_parents(const uint8_t* map, int H, int W, int si, int sj, float* dist, int* parents, int* ring, unsigned char* inq) {
+// Split in two so that the O(nv) initialisation can be shared by the threads of a block (tid of nt) while the queue itself is
+// run by one thread.
+BP_DEV void spfa_serial_init(int nv, float* dist, int* parents, unsigned char* inq, int tid, int nt) {
+    const float inf = 2.0f * (float)nv;
+    for (int v = tid; v < nv; v += nt) { dist[v] = inf; parents[v] = -1; inq[v] = 0; }
+}
+BP_DEV void spfa_serial_run(const uint8_t* map, int H, int W, int si, int sj, float* dist, int* parents, int* ring, unsigned char* inq) {
     const int nv = H * W;
     const int cap = nv + 2;
-    const float inf = 2.0f * (float)nv;
     const float s2 = sqrtf(2.0f);
     const int di[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
     const int dj[8] = {-1, 0, 1, 1, 1, 0, -1, -1};
-    for (int v = 0; v < nv; v++) { dist[v] = inf; parents[v] = -1; inq[v] = 0; }
     const int s = si * W + sj;
-    long long head = 0, tail = 0;                 // positions grow like the reference's; slot = position mod cap
+    // the reference's head / tail only grow (queue[++tail] = v, u = queue[++head]); here they are slots of the ring and `live`
+    // counts the entries between them (head < tail  <=>  live > 0)
+    int head = 0, tail = 1, live = 1;
     dist[s] = 0.0f;
-    ring[(int)(++tail % cap)] = s;
+    ring[tail] = s;
     inq[s] = 1;
     if (!map[s]) return;                          // a blocked source has no edges
-    while (head < tail) {
-        const int u = ring[(int)(++head % cap)];
+    while (live > 0) {
+        if (++head == cap) head = 0;
+        live--;
+        const int u = ring[head];
         inq[u] = 0;
         const int ui = u / W, uj = u - ui * W;
         const float du = dist[u];
+        // neighbours in the reference's edge order; the labels are fetched up front (distinct cells: an update of one does not
+        // change another's), the updates then happen in order
+        int nbr[8]; float dv[8];
+#pragma unroll
         for (int k = 0; k < 8; k++) {
             const int ip = ui + di[k], jp = uj + dj[k];
-            if (ip < 0 || jp < 0 || ip >= H || jp >= W) continue;
-            const int v = ip * W + jp;
-            if (!map[v]) continue;
+            const bool in = !(ip < 0 || jp < 0 || ip >= H || jp >= W);
+            const int v = in ? ip * W + jp : -1;
+            nbr[k] = (in && map[v]) ? v : -1;
+            dv[k] = nbr[k] >= 0 ? dist[nbr[k]] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int v = nbr[k];
+            if (v < 0) continue;
             const float nd = du + ((k & 1) ? 1.0f : s2);
-            if (nd < dist[v]) {
+            if (nd < dv[k]) {
                 parents[v] = u;
                 dist[v] = nd;
                 if (!inq[v]) {
-                    const int pt = (int)(++tail % cap), pf = (int)((head + 1) % cap);
-                    ring[pt] = v;
+                    if (++tail == cap) tail = 0;
+                    live++;
+                    ring[tail] = v;
                     inq[v] = 1;
-                    if (dist[ring[pt]] < dist[ring[pf]]) { int t = ring[pt]; ring[pt] = ring[pf]; ring[pf] = t; }
+                    int pf = head + 1; if (pf == cap) pf = 0;          // the entry that will be popped next
+                    if (nd < dist[ring[pf]]) { ring[tail] = ring[pf]; ring[pf] = v; }
                 }
             }
         }
     }
+}
+BP_DEV void spfa_serial_parents(const uint8_t* map, int H, int W, int si, int sj, float* dist, int* parents, int* ring, unsigned char* inq) {
+    spfa_serial_init(H * W, dist, parents, inq, 0, 1);
+    spfa_serial_run(map, H, W, si, sj, dist, parents, ring, inq);
 }
 
 BP_DEV void spfa_block(SpfaShared& S, const uint8_t* map, int H, int W, int si, int sj, float* dist_out, int32_t* parents,

@@ -233,20 +233,25 @@ def test_200_seeded_area_clearing_episodes_match_the_oracle_distributions():
 
 
 @pytest.mark.gpu
-def test_200_seeded_box_delivery_episodes_match_the_oracle_distributions():
-    """box-delivery-v0 (BASELINE config 2's env): 200 seeded small_empty layouts (the reference's sampler, RandomState(42 + k)),
-    random heading actions for up to 100 steps, TaskDrivenMetric scores; statistical criterion as for area-clearing."""
+@pytest.mark.parametrize("oc,exact", [("small_empty", False), ("small_columns", False), ("small_columns", True)])
+def test_200_seeded_box_delivery_episodes_match_the_oracle_distributions(oc, exact):
+    """box-delivery-v0 (BASELINE config 2's env): 200 seeded layouts (the reference's sampler, RandomState(42 + k)), random heading
+    actions for up to 100 steps, TaskDrivenMetric scores; statistical criterion as for area-clearing.  small_columns: rooms with
+    1 - 2 random columns per layout, with the default deterministic spfa parents (paths may take another equal-cost staircase than
+    the reference's: the score distributions must not notice) and with the reference-order parents."""
     from scipy.stats import ks_2samp
     import make_golden_200ep_boxdel as g
     from benchpush_b200.envs import BoxDeliveryVecEnv
     from benchpush_b200.metrics import TaskDrivenMetric
-    path = os.path.join(GOLD, "boxdel_200ep.npz")
+    path = os.path.join(GOLD, "boxdel_200ep.npz" if oc == "small_empty" else "boxdel_200ep_%s.npz" % oc)
     if not os.path.exists(path):
-        pytest.skip("tests/golden/boxdel_200ep.npz not generated (python tools/make_golden_200ep_boxdel.py, ~10 min on 8 cores)")
+        pytest.skip("%s not generated (BOXDEL_OC=%s python tools/make_golden_200ep_boxdel.py)" % (path, oc))
     gold = np.load(path)
     E = g.N_EP
     assert np.array_equal(gold["actions"], g.actions_table())
-    env = BoxDeliveryVecEnv(num_envs=E, cfg=g.CFG, layouts=[g.layout(k) for k in range(E)], device=0)
+    g.OC = oc
+    g.CFG = {"agent": {"action_type": "heading"}} if oc == "small_empty" else {"agent": {"action_type": "heading"}, "env": {"obstacle_config": oc}}
+    env = BoxDeliveryVecEnv(num_envs=E, cfg=g.CFG, layouts=[g.layout(k) for k in range(E)], device=0, exact_spfa_parents=exact)
     obs, info = env.reset()
     met = TaskDrivenMetric("gpu", robot_mass=1)
     met.reset(info)

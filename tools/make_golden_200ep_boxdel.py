@@ -10,7 +10,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
 N_EP, MAX_STEPS, SEED_LAYOUT, SEED_ACT = 200, 100, 42, 3
-CFG = {"agent": {"action_type": "heading"}}
+# BOXDEL_OC=small_columns (or large_columns / large_divider): the same protocol in a room with random obstacles ->
+# tests/golden/boxdel_200ep_<config>.npz (the per-box spfa solves make the oracle ~3x slower there)
+OC = os.environ.get("BOXDEL_OC", "small_empty")
+CFG = {"agent": {"action_type": "heading"}} if OC == "small_empty" else {"agent": {"action_type": "heading"}, "env": {"obstacle_config": OC}}
 
 
 def actions_table():
@@ -19,7 +22,7 @@ def actions_table():
 
 def layout(k):
     from oracle.box_delivery_oracle import sample_layout
-    return sample_layout(np.random.RandomState(SEED_LAYOUT + k))
+    return sample_layout(np.random.RandomState(SEED_LAYOUT + k), CFG)
 
 
 def batched(info, reset):
@@ -63,4 +66,4 @@ if __name__ == "__main__":
            "total_work": np.array([r[6] for r in rows])}
     print("%.0f s" % (time.time() - t0), "success %.3f" % out["success"].mean(), "steps mean %.1f" % out["steps"].mean(),
           "eff %.4f effort %.4f reward %.3f" % (out["efficiency"].mean(), out["effort"].mean(), out["reward"].mean()), flush=True)
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "boxdel_200ep.npz"), **out)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "boxdel_200ep.npz" if OC == "small_empty" else "boxdel_200ep_%s.npz" % OC), **out)
