@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--obstacle-config", default="small_empty", choices=["small_empty", "small_columns", "large_columns", "large_divider"],
                     help="box-delivery room (cfg.env.obstacle_config); the column / divider rooms use a pool of --rooms layouts with their own maps")
     ap.add_argument("--rooms", type=int, default=64)
-    ap.add_argument("--exact-parents", action="store_true", help="box-delivery / area-clearing: reference-order spfa parents (slow parity mode)")
+    ap.add_argument("--fast-parents", dest="exact_parents", action="store_false",
+                    help="box-delivery / area-clearing: deterministic spfa parents from the parallel relaxation instead of the reference-order ones (default)")
     ap.add_argument("--desync", type=int, default=34,
                     help="spread the episode phases before the warm-up: env e is advanced (global id mod DESYNC) steps (1 = all envs start at reset)")
     return ap.parse_args()
@@ -474,7 +475,8 @@ def run_boxdel(a):
     wl = ("area-clearing-v0 (BASELINE config 3): clear_env, 10 boxes of 1 m, heading actions U(-1,1)" if area
           else "box-delivery-v0 (BASELINE config 2): %s room, %d boxes, heading actions U(-1,1)%s" % (
               oc, 10 if oc.startswith("small") else 20,
-              "" if oc.endswith("_empty") else ", a pool of %d rooms, %s spfa parents" % (a.rooms, "reference-order" if a.exact_parents else "deterministic")))
+              "" if oc.endswith("_empty") else ", a pool of %d rooms" % a.rooms))
+    wl += ", %s spfa parents" % ("reference-order" if a.exact_parents else "deterministic (--fast-parents)")
     if a.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return

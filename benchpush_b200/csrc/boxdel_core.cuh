@@ -62,7 +62,7 @@ struct BdParams {
     // chain is (box_delivery_env.py:1243-1250 tests lines from coords[0] = the receptacle cell only while all are free),
     // so shortest_path_distance is the Euclidean distance and needs no spfa solve.  Checked once per handle.
     int recept_visible;           // (AND over the rooms of the handle)
-    int exact_parents;            // 1: paths follow the reference solver's own parent tie-breaks (spfa_serial_parents; slow, for parity runs)
+    int exact_parents;            // 1: paths follow the reference solver's own parent tie-breaks (spfa_serial_run)
     int pad_rv;
     // ---- env kind: 0 = box-delivery-v0, 1 = area-clearing-v0 (same control chain and handlers, different constants)
     int kind;

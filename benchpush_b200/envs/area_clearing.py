@@ -148,7 +148,7 @@ class ClearingMaps:
 class AreaClearingVecEnv(BoxDeliveryVecEnv):
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
                  seed: int = 1, env_offset: int = 0, _backend=None, layout_pool_episodes: Optional[int] = None,
-                 exact_spfa_parents: bool = False):
+                 exact_spfa_parents: bool = True):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"] not in ENVS:
@@ -218,7 +218,7 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
         k.r_boundary = BOUNDARY_PENALTY; k.r_cleared = BOX_CLEARED_REWARD; k.r_putback = BOX_PUTBACK_PENALTY
         k.r_push_mult = BOX_PUSHING_REWARD_MULTIPLIER; k.r_terminal = TERMINAL_REWARD; k.r_truncation = TRUNCATION_PENALTY; k.r_nonmove = NONMOVEMENT_PENALTY
         self.goal_point_global_map = self._goal_point_map()
-        k.exact_spfa_parents = 1 if exact_spfa_parents else 0      # parity aid: the reference solver's own parent tie-breaks (slow)
+        k.exact_spfa_parents = 1 if exact_spfa_parents else 0      # see BoxDeliveryVecEnv
         self._finish_init(k, r, ch3_map=self.goal_point_global_map)
 
     def _spfa_many(self, cspace_u8, sources):

@@ -233,7 +233,7 @@ class BoxDeliveryVecEnv:
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
                  seed: Optional[int] = None, force_box_spfa: bool = False, env_offset: int = 0, _backend=None,
                  layout_pool_episodes: Optional[int] = None, max_rooms: Optional[int] = 64,
-                 exact_spfa_parents: bool = False):
+                 exact_spfa_parents: bool = True):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"]["obstacle_config"] not in ("small_empty", "large_empty", "small_columns", "large_columns", "large_divider"):
@@ -285,7 +285,9 @@ class BoxDeliveryVecEnv:
         k = BoxDelConfig()
         L.bp_boxdel_default_config(C.byref(k))
         rw = c["rewards_sam"] if c["train"]["job_type"] == "sam" else c["rewards"]
-        k.exact_spfa_parents = 1 if exact_spfa_parents else 0      # parity aid: the reference solver's own parent tie-breaks (slow)
+        # True (default): robot paths / box distances follow the reference solver's own parent tie-breaks (its queue restated by one
+        # thread per solve); False: parallel relaxation + deterministic parents — same distances, possibly another equal-cost path
+        k.exact_spfa_parents = 1 if exact_spfa_parents else 0
         k.force_box_spfa = 1 if force_box_spfa else 0      # testing aid: solve spfa per box even when the exact shortcut applies
         k.n_envs = E; k.num_boxes = NB; k.device = self.device_index
         k.action_type = {"position": 0, "heading": 1, "velocity": 2}[c["agent"]["action_type"]]

@@ -338,8 +338,8 @@ typedef struct bp_boxdel_config {
     double robot_code, box_code, box_done_code;   /* overhead-map segment indices of the robot, boxes, completed boxes */
     double footprint_verts[8];    /* polygon drawn for the robot (area-clearing: cfg.agent.footprint_vertices; 0 = chassis hull) */
     int32_t n_footprint;
-    int32_t exact_spfa_parents;   /* 1: robot paths / box distances follow the reference solver's own parent tie-breaks (its queue restated by one
-                                   * thread per solve: slow; for parity runs).  0: deterministic parents, same distances */
+    int32_t exact_spfa_parents;   /* 1 (default): robot paths / box distances follow the reference solver's own parent tie-breaks (its queue
+                                   * restated by one thread per solve).  0: parallel relaxation + deterministic parents: same distances, faster */
     double boundary[16], goals[128];
     double r_boundary, r_cleared, r_putback, r_push_mult, r_terminal, r_truncation, r_nonmove;   /* area_clearing.py:41-52 */
 } bp_boxdel_config;

@@ -224,14 +224,14 @@ def test_column_and_divider_rooms_match_the_oracle(portable_trig, oc, seed, step
     env.close()
 
 
-def test_rooms_are_indexed_by_layout_and_default_parents_keep_the_physics(portable_trig):
+def test_rooms_are_indexed_by_layout_and_deterministic_parents_keep_the_physics(portable_trig):
     """Three envs on three different rooms of one handle (0, 1 and 2 columns): each matches its own oracle at reset (maps, raster,
-    bodies), and with the default deterministic parents the poses still match while the robot's path needs no spfa solve
+    bodies), and with the deterministic parents of the fast mode (exact_spfa_parents=False) the poses still match while the robot's path needs no spfa solve
     (box path distances may follow another equal-cost staircase: DESIGN 5.4)."""
     cfg = {"agent": {"action_type": "heading"}, "env": {"obstacle_config": "small_columns"}}
     lays = [sample_layout(np.random.RandomState(s), cfg) for s in (2, 0, 4)]
     assert [len(l["columns"]) for l in lays] == [0, 1, 2]
-    env = BoxDeliveryVecEnv(num_envs=3, cfg=cfg, layouts=lays, _backend=emu_bd.lib())
+    env = BoxDeliveryVecEnv(num_envs=3, cfg=cfg, layouts=lays, _backend=emu_bd.lib(), exact_spfa_parents=False)
     oras = [BoxDeliveryOracleEnv(cfg=cfg, layouts=[l]) for l in lays]
     obs, info = env.reset()
     for e, ora in enumerate(oras):
