@@ -516,12 +516,15 @@ def run_boxdel(a):
     launches = env.launch_count() - l0
     # end to end: actions from pinned host memory, rewards / flags / info read back every step
     h_act = [torch.empty(n_envs, dtype=torch.float32).pin_memory().copy_(actions[k].cpu()) for k in range(a.warmup, total)]
-    env.step_host(h_act[0].numpy())
+    env.step_host(h_act[0].numpy(), want_obs="device")
     torch.cuda.synchronize()
+    l1 = env.launch_count()
     t0 = time.perf_counter()
     for k in range(a.steps):
-        hb = env.step_host(h_act[k].numpy())
+        hb = env.step_host(h_act[k].numpy(), want_obs="device")      # every kernel of a step incl. the observation kernel
     t_e2e = time.perf_counter() - t0
+    e2e_launches = env.launch_count() - l1
+    assert e2e_launches == launches, "the end-to-end region must launch what the device-timed region launches (%d vs %d)" % (e2e_launches, launches)
     NB = env.num_boxes
     alg = 4 + 224 * 224 * 4 + 2 * (1 + NB) * 6 * 8 + 48           # action + observation + poses read and written + outputs
     move_ms = km["move_ms"] / max(km["steps"], 1)
@@ -544,7 +547,8 @@ def run_boxdel(a):
                      "note": "latency bound: ~800 dependent physics substeps per env step, 1-3 contacts each"},
         "cpu_baseline": cpu, "clocks": clocks,
         "e2e": {"value": n_envs * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": n_envs * 4, "d2h_bytes_per_step": n_envs * (8 + 1 + 1 + 64 + 16 + NB),
-                "what": "bp_boxdel_step_host: actions from pinned host memory; reward / flags / info / completion read back every step; observations stay on the device"},
+                "launches_in_region": int(e2e_launches),
+                "what": "bp_boxdel_step_host_obs_device: actions from pinned host memory; every kernel of the step incl. the observation kernel; reward / flags / info / completion read back every step; the 224x224x4 u8 images are rendered into the env's device tensor for a policy on the GPU and not copied"},
         "gpu_launches": launches}), flush=True)
 
 

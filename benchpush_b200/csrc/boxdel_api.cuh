@@ -276,6 +276,7 @@ int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts
     CUDA_TRY(cudaMalloc((void**)&h->d_small, R * P.SMALL * P.SMALL)); CUDA_TRY(cudaMemcpy(h->d_small, small_free, R * P.SMALL * P.SMALL, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void**)&h->d_rchan, (size_t)P.LW * P.LW)); CUDA_TRY(cudaMemcpy(h->d_rchan, robot_chan, (size_t)P.LW * P.LW, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void**)&h->d_recept, R * nv * 4));
+    P.border_blocked = bd_border_blocked(cspace, R, H, W);
     // receptacle cell of every room (closest valid cell of the receptacle position)
     {
         int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
@@ -446,7 +447,15 @@ int bp_boxdel_get_kernel_ms(bp_boxdel_t* h, double* out3) {
 }
 
 // host-buffer variant: actions and every non-null output are HOST pointers; copies in, steps, copies out, synchronises
-int bp_boxdel_step_host(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host) {
+static int bd_step_host_impl(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host, uint8_t* obs_dev);
+int bp_boxdel_step_host(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host) { return bd_step_host_impl(h, actions, out_host, nullptr); }
+// As bp_boxdel_step_host, with the observation rendered into the DEVICE buffer obs_dev (u8[E][LW][LW][4]) instead of being copied
+// to the host: the call a GPU-resident policy makes (host actions in, host rewards / flags / info out, images stay on the device).
+int bp_boxdel_step_host_obs_device(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host, uint8_t* obs_dev) {
+    if (!obs_dev) return fail(BP_ERR_INVALID, "null obs_dev");
+    return bd_step_host_impl(h, actions, out_host, obs_dev);
+}
+static int bd_step_host_impl(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host, uint8_t* obs_dev) {
     if (!h || !h->loaded) return fail(BP_ERR_STATE, "bp_boxdel_load first");
     if (!actions || !out_host) return fail(BP_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -462,9 +471,13 @@ int bp_boxdel_step_host(bp_boxdel_t* h, const float* actions, const bp_boxdel_ou
                      {(void**)&d.info, out_host->info, 64 * (size_t)E}, {(void**)&d.info_i, out_host->info_i, 16 * (size_t)E},
                      {(void**)&d.completed, out_host->completed, (size_t)E * NB}, {(void**)&d.box_verts, out_host->box_verts, (size_t)E * NB * SV * 16}};
     int rc = BP_OK;
+    if (obs_dev) items[0].host = nullptr;          // rendered straight into the caller's device buffer
     for (auto& it : items) if (it.host && cudaMalloc(it.dev, it.bytes) != cudaSuccess) rc = fail(BP_ERR_CUDA, "cudaMalloc (step_host)");
+    if (obs_dev) d.obs = obs_dev;
     if (rc == BP_OK) rc = bp_boxdel_step(h, d_act, nullptr, &d, nullptr);
     if (rc == BP_OK) for (auto& it : items) if (it.host && cudaMemcpy(it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(BP_ERR_CUDA, "copy out (step_host)");
+    if (rc == BP_OK && obs_dev && cudaDeviceSynchronize() != cudaSuccess) rc = fail(BP_ERR_CUDA, "step_host_obs_device");
+    if (obs_dev) d.obs = nullptr;
     for (auto& it : items) if (*it.dev) cudaFree(*it.dev);
     cudaFree(d_act);
     return rc;

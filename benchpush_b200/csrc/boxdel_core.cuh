@@ -63,7 +63,7 @@ struct BdParams {
     // so shortest_path_distance is the Euclidean distance and needs no spfa solve.  Checked once per handle.
     int recept_visible;           // (AND over the rooms of the handle)
     int exact_parents;            // 1: paths follow the reference solver's own parent tie-breaks (spfa_serial_run)
-    int pad_rv;
+    int border_blocked;           // 1: the first / last rows and columns of every room's configuration space are blocked
     // ---- env kind: 0 = box-delivery-v0, 1 = area-clearing-v0 (same control chain and handlers, different constants)
     int kind;
     int step_limit;               // STEP_LIMIT of execute_robot_path: 10000 (box_delivery_env.py:62) / 5000 (area_clearing.py:76)

@@ -137,6 +137,17 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
     return "";
 }
 
+// 1 when the first / last rows and columns of every room's configuration space are blocked (BdParams::border_blocked)
+inline int bd_border_blocked(const uint8_t* cspace, size_t n_rooms, int H, int W) {
+    const size_t nv = (size_t)H * W;
+    for (size_t r = 0; r < n_rooms; r++) {
+        const uint8_t* m = cspace + r * nv;
+        for (int j = 0; j < W; j++) if (m[j] || m[(size_t)(H - 1) * W + j]) return 0;
+        for (int i = 0; i < H; i++) if (m[(size_t)i * W] || m[(size_t)i * W + W - 1]) return 0;
+    }
+    return 1;
+}
+
 // fourth observation channel of box-delivery before the window shift: create_global_shortest_path_to_receptacle_map
 // (box_delivery_env.py:1115-1129): spfa field / ppm (f32), / ((sqrt 2 LW) / ppm) (f64, rounded to f32), * scale (f32)
 inline void bd_scale_receptacle_map(const BdParams& P, float* m, size_t n) {

@@ -68,9 +68,12 @@ BP_DEV void bd_dist_item(SpfaShared& S, const BdConst& C, BdEnv* E, int k, int p
         parents = scratch + (size_t)4 * nv + (size_t)P.SMALL * P.SMALL / 4 + 64;
         // (labels in a shared-memory window of the room were measured slower: the solve is bound by the dependent instruction
         // chain of one thread, and the shared memory costs resident blocks)
-        spfa_serial_init(nv, (float*)dist, parents, (unsigned char*)mark, BP_TID, BP_NT);
+        spfa_serial_init(bd_cspace(C, E->room), nv, (float*)dist, parents, (unsigned char*)mark, BP_TID, BP_NT);
         BP_BSYNC();
-        if (BP_TID == 0) spfa_serial_run(bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, parents, q0, (unsigned char*)mark);
+        if (BP_TID == 0) {
+            if (P.border_blocked) spfa_serial_run<true>(bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, parents, q0, (unsigned char*)mark);
+            else spfa_serial_run<false>(bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, parents, q0, (unsigned char*)mark);
+        }
     } else {
         spfa_relax(S, bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, q0, q1, mark);
     }

@@ -280,12 +280,12 @@ __global__ void __launch_bounds__(32) k_spfa_serial(const uint8_t* maps, const i
     if (m >= batch) return;
     const size_t nv = (size_t)H * W;
     float* d = dists + m * nv;
-    spfa_serial_init((int)nv, d, parents + m * nv, inq + m * nv, threadIdx.x, 32);
+    spfa_serial_init(maps + m * nv, (int)nv, d, parents + m * nv, inq + m * nv, threadIdx.x, 32);
     __syncwarp();
     if (threadIdx.x == 0) spfa_serial_run(maps + m * nv, H, W, sources[2 * m], sources[2 * m + 1], d, parents + m * nv, ring + m * (nv + 2), inq + m * nv);
     __syncwarp();
     const float inf = 2.0f * (float)nv;
-    for (size_t v = threadIdx.x; v < nv; v += 32) if (!(d[v] < inf)) d[v] = 0.0f;
+    for (size_t v = threadIdx.x; v < nv; v += 32) if (!(d[v] < inf) || d[v] < 0.0f) d[v] = 0.0f;      // unreachable and blocked cells report 0
 }
 
 // generate_observation_low_dim (ship_ice_env.py:358-370; maze_NAMO_env.py:488-504): |poly_centroid| of every movable

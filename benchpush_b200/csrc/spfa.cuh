@@ -112,10 +112,14 @@ BP_DEV int spfa_parent_of(const uint8_t* map, int H, int W, const int* dist, int
 // ring without changing which entries meet); inq: nv bytes.
 // Split in two so that the O(nv) initialisation can be shared by the threads of a block (tid of nt) while the queue itself is
 // run by one thread.
-BP_DEV void spfa_serial_init(int nv, float* dist, int* parents, unsigned char* inq, int tid, int nt) {
+// Blocked cells get the label -1: no tentative label (>= 0) ever improves it, so the queue loop needs no look-up of the map.
+BP_DEV void spfa_serial_init(const uint8_t* map, int nv, float* dist, int* parents, unsigned char* inq, int tid, int nt) {
     const float inf = 2.0f * (float)nv;
-    for (int v = tid; v < nv; v += nt) { dist[v] = inf; parents[v] = -1; inq[v] = 0; }
+    for (int v = tid; v < nv; v += nt) { dist[v] = map[v] ? inf : -1.0f; parents[v] = -1; inq[v] = 0; }
 }
+// BORDER_BLOCKED: the caller guarantees that every cell of the first / last row and column is blocked (true for the padded room
+// maps of the envs), so a queued cell has all eight neighbours inside the grid and the scan works on linear indices only.
+template <bool BORDER_BLOCKED = false>
 BP_DEV void spfa_serial_run(const uint8_t* map, int H, int W, int si, int sj, float* dist, int* parents, int* ring, unsigned char* inq) {
     const int nv = H * W;
     const int cap = nv + 2;
@@ -126,27 +130,31 @@ BP_DEV void spfa_serial_run(const uint8_t* map, int H, int W, int si, int sj, fl
     // the reference's head / tail only grow (queue[++tail] = v, u = queue[++head]); here they are slots of the ring and `live`
     // counts the entries between them (head < tail  <=>  live > 0)
     int head = 0, tail = 1, live = 1;
+    if (!map[s]) return;                          // a blocked source has no edges
     dist[s] = 0.0f;
     ring[tail] = s;
     inq[s] = 1;
-    if (!map[s]) return;                          // a blocked source has no edges
     while (live > 0) {
         if (++head == cap) head = 0;
         live--;
         const int u = ring[head];
         inq[u] = 0;
-        const int ui = u / W, uj = u - ui * W;
         const float du = dist[u];
         // neighbours in the reference's edge order; the labels are fetched up front (distinct cells: an update of one does not
         // change another's), the updates then happen in order
         int nbr[8]; float dv[8];
+        if (BORDER_BLOCKED) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int ip = ui + di[k], jp = uj + dj[k];
-            const bool in = !(ip < 0 || jp < 0 || ip >= H || jp >= W);
-            const int v = in ? ip * W + jp : -1;
-            nbr[k] = (in && map[v]) ? v : -1;
-            dv[k] = nbr[k] >= 0 ? dist[nbr[k]] : 0.0f;
+            for (int k = 0; k < 8; k++) { nbr[k] = u + di[k] * W + dj[k]; dv[k] = dist[nbr[k]]; }
+        } else {
+            const int ui = u / W, uj = u - ui * W;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int ip = ui + di[k], jp = uj + dj[k];
+                const bool in = !(ip < 0 || jp < 0 || ip >= H || jp >= W);
+                nbr[k] = in ? ip * W + jp : -1;
+                dv[k] = in ? dist[nbr[k]] : -1.0f;
+            }
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -169,8 +177,10 @@ BP_DEV void spfa_serial_run(const uint8_t* map, int H, int W, int si, int sj, fl
     }
 }
 BP_DEV void spfa_serial_parents(const uint8_t* map, int H, int W, int si, int sj, float* dist, int* parents, int* ring, unsigned char* inq) {
-    spfa_serial_init(H * W, dist, parents, inq, 0, 1);
+    spfa_serial_init(map, H * W, dist, parents, inq, 0, 1);
     spfa_serial_run(map, H, W, si, sj, dist, parents, ring, inq);
+    const float inf = 2.0f * (float)(H * W);
+    for (int v = 0; v < H * W; v++) if (dist[v] < 0.0f) dist[v] = inf;      // blocked cells: unreachable, like the reference's labels
 }
 
 BP_DEV void spfa_block(SpfaShared& S, const uint8_t* map, int H, int W, int si, int sj, float* dist_out, int32_t* parents,

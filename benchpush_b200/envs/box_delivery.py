@@ -102,6 +102,7 @@ def bind(L):
     L.bp_boxdel_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
     L.bp_boxdel_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
     L.bp_boxdel_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs)]
+    L.bp_boxdel_step_host_obs_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
     L.bp_boxdel_get_bodies.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     L.bp_boxdel_get_step_debug.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bp_boxdel_launch_count.argtypes = [C.c_void_p]
@@ -478,9 +479,11 @@ class BoxDeliveryVecEnv:
                 "total_work": info[:, 5], "obs": b["box_verts"], "n_boxes_left": ii[:, 2], "box_completed_statuses": b["completed"],
                 "goal_positions": self.goal_points, "ministeps": info[:, 6], "inactivity": ii[:, 1], "status": ii[:, 3], "work": info[:, 7]}
 
-    def step_host(self, actions: np.ndarray, out: Optional["BoxDelOutputs"] = None):
+    def step_host(self, actions: np.ndarray, out: Optional["BoxDelOutputs"] = None, want_obs=False):
         """bp_boxdel_step_host: actions and results in HOST buffers (copies inside the call, synchronises).
-        Returns a dict of numpy arrays (reward, terminated, truncated, info, info_i); observations stay on the device."""
+        Returns a dict of numpy arrays (reward, terminated, truncated, info, info_i).  want_obs="device"
+        (bp_boxdel_step_host_obs_device): the observation kernel runs too and renders into ``self.obs`` on the device — the
+        call a GPU-resident policy makes; False: no observation is produced."""
         if not hasattr(self, "_hb"):
             E = self.num_envs
             self._hb = {"reward": np.zeros(E), "terminated": np.zeros(E, dtype=np.uint8), "truncated": np.zeros(E, dtype=np.uint8),
@@ -490,7 +493,10 @@ class BoxDeliveryVecEnv:
                 setattr(o, n, a.ctypes.data)
             self._ho = o
         a = np.ascontiguousarray(actions, dtype=np.float32)
-        self._check(self._L.bp_boxdel_step_host(self._h, a.ctypes.data, C.byref(self._ho)))
+        if want_obs == "device" and not self.low_dim_state:
+            self._check(self._L.bp_boxdel_step_host_obs_device(self._h, a.ctypes.data, C.byref(self._ho), self._ptr("obs")))
+        else:
+            self._check(self._L.bp_boxdel_step_host(self._h, a.ctypes.data, C.byref(self._ho)))
         return self._hb
 
     def set_profiling(self, on: bool):

@@ -381,6 +381,9 @@ int bp_boxdel_reset(bp_boxdel_t* h, const int32_t* layout_ids, const uint8_t* ma
 int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream);
 /* HOST buffers: copies in, steps, copies out, synchronises */
 int bp_boxdel_step_host(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host);
+/* same, with the observation rendered into the DEVICE buffer obs_dev (u8[E][LW][LW][4]) for a GPU-resident policy instead of being
+ * copied to the host (out_host->obs is ignored) */
+int bp_boxdel_step_host_obs_device(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host, uint8_t* obs_dev);
 /* HOST out[(1 + num_boxes)][7]: origin x, y, angle, vx, vy, w, alive; row 0 = robot */
 int bp_boxdel_get_bodies(bp_boxdel_t* h, int32_t env, double* out);
 int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double* dists, double* path);

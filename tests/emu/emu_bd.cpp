@@ -91,6 +91,7 @@ int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts
     h->envs.assign(K.env_bytes * h->cfg.n_envs, 0);
     K.envs = h->envs.data();
     h->scratch.assign(bd_scratch_ints(P), 0);
+    K.P.border_blocked = getenv("BP_EMU_CHECKED_BORDER") ? 0 : bd_border_blocked(cspace, R, H, W);
     int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
     pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
     int vis = 1;
@@ -169,6 +170,10 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
 }
 
 int bp_boxdel_step_host(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host) { return bp_boxdel_step(h, actions, nullptr, out_host, nullptr); }
+int bp_boxdel_step_host_obs_device(bp_boxdel_t* h, const float* actions, const bp_boxdel_outputs* out_host, uint8_t* obs_dev) {
+    bp_boxdel_outputs o = *out_host; o.obs = obs_dev;
+    return bp_boxdel_step(h, actions, nullptr, &o, nullptr);
+}
 
 int bp_boxdel_get_bodies(bp_boxdel_t* h, int32_t env, double* out) {
     const BdEnv* E = bd_env(h->HB.K, env);
