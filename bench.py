@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the secondary measurement of the fp32-state build (field fp32_state)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--env", default="ship-ice", choices=["ship-ice", "box-delivery", "area-clearing"],
+    ap.add_argument("--env", default="ship-ice", choices=["ship-ice", "box-delivery", "area-clearing", "maze"],
                     help="ship-ice (default, the BASELINE.json metric); box-delivery (BASELINE config 2: 4096 envs) and area-clearing (config 3: 16384 envs) print secondary lines")
     ap.add_argument("--obstacle-config", default="small_empty", choices=["small_empty", "small_columns", "large_columns", "large_divider"],
                     help="box-delivery room (cfg.env.obstacle_config); the column / divider rooms use a pool of --rooms layouts with their own maps")
@@ -552,10 +552,122 @@ def run_boxdel(a):
         "gpu_launches": launches}), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ maze-NAMO (secondary line, BASELINE config 4)
+def _maze_cpu_worker(args):
+    idx, budget, nsteps = args
+    from oracle.maze_oracle import MazeNamoOracleEnv
+    from benchpush_b200.layouts import generate_maze_layouts
+    env = MazeNamoOracleEnv(layouts=[generate_maze_layouts(64, seed=0)[idx % 64]], order_mode=1)
+    env.reset()
+    rng = np.random.default_rng(500 + idx)
+    n = 0
+    t0 = time.perf_counter()
+    while True:
+        obs, r, term, trunc, info = env.step(float(np.float32(rng.uniform(-1, 1))))
+        n += 1
+        if term or trunc:
+            env.reset()
+        if (nsteps is not None and n >= nsteps) or (nsteps is None and time.perf_counter() - t0 > budget):
+            break
+    return n, time.perf_counter() - t0
+
+
+def _maze_cpu(budget_s, nsteps=None):
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_maze_cpu_worker, [(i, budget_s, nsteps) for i in range(cores)])
+    steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return steps / wall, cores, steps, wall
+
+
+def run_maze(a):
+    """BASELINE config 4: maze-NAMO-v0 (maze v1, 5 movable obstacles), 16 384 envs, random actions, next-step auto reset.
+    One step = one step() of every env: 100 physics substeps, reward / info, 4x192x192 observation."""
+    n_envs = a.envs if a.envs != TOTAL_ENVS else 16384
+    metric = "env-steps/sec maze-NAMO-v0 @%d envs" % n_envs
+    wl = "maze-NAMO-v0 (BASELINE config 4): maze v1, 5 movable obstacles, 256 seeded layouts, U(-1,1) actions, next-step auto reset"
+    if a.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        _maze_cpu(0.0, max(a.warmup, 1))
+        v, cores, n, wall = _maze_cpu(0.0, a.steps)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": {"workload": wl + "; one env per host core",
+                                                           "note": "restated reference (oracle/ on the C++ Chipmunk restatement); the reference env cannot run here"},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d env steps per core on %d cores" % (a.steps, cores)},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    from benchpush_b200.envs import MazeNamoVecEnv
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    env = MazeNamoVecEnv(num_envs=n_envs, device=0, auto_reset=True, n_synthetic_layouts=256)
+    env.check_status = False
+    env.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    total = a.warmup + a.steps
+    actions = [(torch.rand(n_envs, generator=gen, device=dev) * 2 - 1).float() for _ in range(total)]
+    for k in range(a.warmup):
+        env.step_async_nocheck(actions[k])
+    torch.cuda.synchronize()
+    env.set_profiling(True); env.kernel_ms()
+    l0 = env.launch_count()
+    sampler = ClockSampler(0); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(a.warmup, total):
+        env.step_async_nocheck(actions[k])
+    e1.record(); torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    km = env.kernel_ms(); env.set_profiling(False)
+    launches = env.launch_count() - l0
+    h_act = [torch.empty(n_envs, dtype=torch.float32).pin_memory().copy_(actions[k].cpu()) for k in range(a.warmup, total)]
+    env.step_host(h_act[0].numpy(), want_obs="device")
+    torch.cuda.synchronize()
+    l1 = env.launch_count()
+    t0 = time.perf_counter()
+    for k in range(a.steps):
+        hb = env.step_host(h_act[k].numpy(), want_obs="device")
+    t_e2e = time.perf_counter() - t0
+    e2e_launches = env.launch_count() - l1
+    step_ms = km["step_ms"] / max(km["step_launches"], 1)
+    obs_ms = km["obs_ms"] / max(km["obs_launches"], 1)
+    alg = 4 + 4 * 192 * 192 + 2 * 6 * 6 * 8 + 64              # action + observation + poses of robot and 5 obstacles read and written + outputs
+    peak, peak_src = peaks()
+    achieved = alg * n_envs / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
+    cpu = None
+    if not a.no_cpu_baseline:
+        v, cores, n, wall = _maze_cpu(a.cpu_seconds, None)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "oracle (restated reference): one env per core on %d cores, %d env steps in %.1f s" % (cores, n, wall)}
+    d2h = sum(v.nbytes for k, v in hb.items() if isinstance(v, np.ndarray))
+    print(json.dumps({
+        "metric": metric, "value": n_envs * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl + ", %d envs, 4x192x192 u8 obs" % n_envs,
+                   "l2": "inputs_exceed_l2 (per-env state %.0f KB x %d envs)" % (env.env_bytes() / 1e3, n_envs),
+                   "env_status_bits": int(env._status.max())},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "k_shipice_step (maze handle)", "kernel_ms": step_ms, "obs_kernel_ms": obs_ms,
+                     "algorithmic_bytes_per_env_step": alg, "peak_source": peak_src,
+                     "note": "latency bound: 100 dependent physics substeps per env step on a handful of bodies"},
+        "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": {"value": n_envs * a.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": n_envs * 4, "d2h_bytes_per_step": int(d2h),
+                "launches_in_region": int(e2e_launches),
+                "what": "bp_maze_step_host_obs_device: actions from pinned host memory, step kernel + observation kernel every step, reward / flags / state read back every step; images stay in the env's device tensor"},
+        "gpu_launches": launches}), flush=True)
+
+
 def main():
     a = parse()
     if a.env in ("box-delivery", "area-clearing"):
         run_boxdel(a)
+    elif a.env == "maze":
+        run_maze(a)
     elif a.impl == "reference":
         run_reference(a)
     else:

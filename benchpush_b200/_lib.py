@@ -99,6 +99,7 @@ def lib(precision: str = "fp64"):
         L.bp_shipice_step_masked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
         L.bp_shipice_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs)]
         L.bp_shipice_step_host_obs_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ShipIceOutputs), C.c_void_p]
+        L.bp_maze_step_host_obs_device.argtypes = L.bp_shipice_step_host_obs_device.argtypes
         L.bp_shipice_get_obstacles.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.bp_shipice_low_dim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bp_maze_low_dim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -151,7 +152,7 @@ EXPORTS = [
     "bp_shipice_set_profiling", "bp_shipice_get_kernel_ms",
     "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host", "bp_spfa_batch_exact", "bp_spfa_batch_exact_host",
     "bp_maze_default_config", "bp_maze_create", "bp_maze_destroy", "bp_maze_load_layouts", "bp_maze_reset", "bp_maze_step",
-    "bp_maze_step_masked", "bp_maze_step_host", "bp_maze_get_obstacles", "bp_maze_get_bodies", "bp_maze_get_maps",
+    "bp_maze_step_masked", "bp_maze_step_host_obs_device", "bp_maze_step_host", "bp_maze_get_obstacles", "bp_maze_get_bodies", "bp_maze_get_maps",
     "bp_boxdel_default_config", "bp_boxdel_create", "bp_boxdel_destroy", "bp_boxdel_load", "bp_boxdel_load_rooms", "bp_boxdel_reset", "bp_boxdel_step", "bp_boxdel_step_host_obs_device",
     "bp_boxdel_step_host", "bp_boxdel_get_bodies", "bp_boxdel_get_step_debug", "bp_boxdel_launch_count", "bp_boxdel_env_bytes", "bp_boxdel_set_profiling", "bp_boxdel_get_kernel_ms",
 ]

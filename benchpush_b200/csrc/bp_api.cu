@@ -1039,6 +1039,9 @@ int bp_maze_step_masked(bp_maze_t* h, const float* actions, const uint8_t* mask,
     return bp_shipice_step_masked(h, actions, mask, out, stream);
 }
 int bp_maze_step_host(bp_maze_t* h, const float* actions, const bp_maze_outputs* out_host) { return bp_shipice_step_host(h, actions, out_host); }
+int bp_maze_step_host_obs_device(bp_maze_t* h, const float* actions, const bp_maze_outputs* out_host, uint8_t* obs_dev) {
+    return bp_shipice_step_host_obs_device(h, actions, out_host, obs_dev);
+}
 int bp_maze_low_dim(bp_maze_t* h, double* out, int32_t* counts, void* stream) {
     if (!h || !out) return fail(BP_ERR_INVALID, "null argument");
     if (h->kind != KIND_MAZE) return fail(BP_ERR_INVALID, "not a maze handle");

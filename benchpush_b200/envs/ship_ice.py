@@ -310,9 +310,7 @@ class ShipIceVecEnv:
         if want_obs is True:
             o.obs = hb["obs"].ctypes.data
         if want_obs == "device":
-            if self._prefix != "shipice":
-                raise NotImplementedError('want_obs="device" is a ship-ice entry point')
-            _lib.check(self._L.bp_shipice_step_host_obs_device(self._h, a.ctypes.data, C.byref(o), C.c_void_p(self.obs.data_ptr())))
+            _lib.check(self._fn("step_host_obs_device")(self._h, a.ctypes.data, C.byref(o), C.c_void_p(self.obs.data_ptr())))
         else:
             _lib.check(self._fn("step_host")(self._h, a.ctypes.data, C.byref(o)))
         return hb

@@ -251,6 +251,8 @@ int bp_maze_reset(bp_maze_t* h, const int32_t* layout_ids, const uint8_t* mask, 
 int bp_maze_step(bp_maze_t* h, const float* actions, const bp_maze_outputs* out, void* stream);
 int bp_maze_step_masked(bp_maze_t* h, const float* actions, const uint8_t* mask, const bp_maze_outputs* out, void* stream);
 int bp_maze_step_host(bp_maze_t* h, const float* actions, const bp_maze_outputs* out_host);
+/* observation (u8[E][4][192][192]) rendered into the DEVICE buffer obs_dev, everything else through host buffers */
+int bp_maze_step_host_obs_device(bp_maze_t* h, const float* actions, const bp_maze_outputs* out_host, uint8_t* obs_dev);
 
 /* Same as bp_shipice_set_start_poses, for the maze robot (chassis and wheels share the pose). */
 int bp_maze_set_start_poses(bp_maze_t* h, const double* poses);
