@@ -147,7 +147,7 @@ class ClearingMaps:
 
 class AreaClearingVecEnv(BoxDeliveryVecEnv):
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
-                 seed: int = 1, env_offset: int = 0, _backend=None, layout_pool_episodes: Optional[int] = None,
+                 seed: int = 1, env_offset: int = 0, layout_pool_episodes: Optional[int] = None,
                  exact_spfa_parents: bool = True):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
@@ -157,17 +157,7 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
             raise NotImplementedError("unknown action_type %r" % (c["agent"]["action_type"],))
         self.env_cfg = ENVS[c["env"]]
         self.num_envs = E = int(num_envs)
-        self._emu = _backend is not None
-        if self._emu:
-            self._L = bind(_backend)
-            self.device, self.device_index = None, 0
-        else:
-            import torch
-            if not torch.cuda.is_available():
-                raise _lib.BenchPushError("AreaClearingVecEnv needs a CUDA device (there is no CPU fallback)")
-            self._L = bind(_lib.lib())
-            self.device_index = torch.cuda.current_device() if device is None else int(device)
-            self.device = torch.device("cuda", self.device_index)
+        self._open(device)
         self.num_boxes = NB = int(c["num_obstacles"])
         self.num_channels = 4
         self.room = r = ClearingMaps(c, self.env_cfg)
@@ -222,17 +212,14 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
         self._finish_init(k, r, ch3_map=self.goal_point_global_map)
 
     def _spfa_many(self, cspace_u8, sources):
-        """One shortest-path field per source on the shared configuration space (GPU; the emulation uses its own host build)."""
+        """One shortest-path field per source on the shared configuration space (bp_spfa_batch_host of the bound library)."""
         n = len(sources)
         maps = np.ascontiguousarray(np.broadcast_to(cspace_u8, (n,) + cspace_u8.shape))
         src = np.ascontiguousarray(np.asarray(sources, dtype=np.int32))
         d = np.zeros((n,) + cspace_u8.shape, dtype=np.float32)
         p = np.zeros((n,) + cspace_u8.shape, dtype=np.int32)
-        if self._emu:
-            self._L.bp_spfa_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
-            self._check(self._L.bp_spfa_batch_host(maps.ctypes.data, src.ctypes.data, n, cspace_u8.shape[0], cspace_u8.shape[1], d.ctypes.data, p.ctypes.data))
-        else:
-            _lib.check(_lib.lib().bp_spfa_batch_host(maps.ctypes.data, src.ctypes.data, n, cspace_u8.shape[0], cspace_u8.shape[1], d.ctypes.data, p.ctypes.data))
+        self._L.bp_spfa_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        self._check(self._L.bp_spfa_batch_host(maps.ctypes.data, src.ctypes.data, n, cspace_u8.shape[0], cspace_u8.shape[1], d.ctypes.data, p.ctypes.data))
         return d
 
     def _goal_point_map(self):

@@ -232,7 +232,7 @@ class BoxDeliveryVecEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
-                 seed: Optional[int] = None, force_box_spfa: bool = False, env_offset: int = 0, _backend=None,
+                 seed: Optional[int] = None, force_box_spfa: bool = False, env_offset: int = 0,
                  layout_pool_episodes: Optional[int] = None, max_rooms: Optional[int] = 64,
                  exact_spfa_parents: bool = True):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
@@ -246,18 +246,7 @@ class BoxDeliveryVecEnv:
         if tuple(c["sim"]["gravity"]) != (0, 0):
             raise NotImplementedError("non-zero gravity is not supported")
         self.num_envs = E = int(num_envs)
-        self._emu = _backend is not None
-        if self._emu:
-            self._L = bind(_backend)                 # tests/emu only: the kernel sources compiled for the host
-            self.device = None
-            self.device_index = 0
-        else:
-            import torch
-            if not torch.cuda.is_available():
-                raise _lib.BenchPushError("BoxDeliveryVecEnv needs a CUDA device (there is no CPU fallback)")
-            self._L = bind(_lib.lib())
-            self.device_index = torch.cuda.current_device() if device is None else int(device)
-            self.device = torch.device("cuda", self.device_index)
+        self._open(device)
         small = c["env"]["obstacle_config"].split("_")[0] == "small"
         self.num_boxes = NB = int(c["boxes"]["num_boxes_small"] if small else c["boxes"]["num_boxes_large"])
         self.num_channels = 4
@@ -315,13 +304,22 @@ class BoxDeliveryVecEnv:
         k.bound_x = float(self.room.room_length); k.bound_y = float(self.room.room_width)     # D17: x clamps with map_height = room_length
         self._finish_init(k, self.rooms, ch3_map=None)
 
+    def _open(self, device):
+        """Bind the CUDA library and pick the device.  There is no CPU fallback: no device, no env."""
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.BenchPushError("%s needs a CUDA device (there is no CPU fallback)" % type(self).__name__)
+        self._L = bind(_lib.lib())
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+
     def _init_spaces(self):
         """The reference's spaces (box_delivery_env.py:157-173, area_clearing.py:200-221) as ``single_*``; ``action_space`` /
         ``observation_space`` carry a leading axis of num_envs.  Area-clearing declares its position action as int32 (1,)."""
         from .. import spaces
         at = self.cfg["agent"]["action_type"]
         LW = int(self.local_map_pixel_width)
-        area = type(self).__name__.startswith("AreaClearing")
+        area = any(k.__name__ == "AreaClearingVecEnv" for k in type(self).__mro__)
         if at == "velocity":
             a = spaces.box(-1, 1, (2,), np.float32)
         elif at == "heading":
@@ -393,31 +391,26 @@ class BoxDeliveryVecEnv:
     def _observation(self):
         return self.low_dim_observation() if self.low_dim_state else self._buf["obs"]
 
-    # ---- buffers: torch CUDA tensors (product) or numpy arrays (emulation)
+    # ---- buffers: torch CUDA tensors
     def _alloc(self, name, shape, dtype):
-        if self._emu:
-            self._buf[name] = np.zeros(shape, dtype=dtype)
-        else:
-            import torch
-            self._buf[name] = torch.zeros(shape, dtype=getattr(torch, dtype), device=self.device)
+        import torch
+        self._buf[name] = torch.zeros(shape, dtype=getattr(torch, dtype), device=self.device)
 
     def _ptr(self, name):
-        b = self._buf[name]
-        return b.ctypes.data if self._emu else b.data_ptr()
+        return self._buf[name].data_ptr()
 
     def _put(self, name, values):
-        if self._emu:
-            self._buf[name][...] = np.asarray(values, dtype=self._buf[name].dtype).reshape(self._buf[name].shape)
-        else:
-            import torch
-            t = values if isinstance(values, torch.Tensor) else torch.as_tensor(np.asarray(values))
-            self._buf[name].copy_(t.to(self.device).reshape(self._buf[name].shape).to(self._buf[name].dtype))
+        import torch
+        t = values if isinstance(values, torch.Tensor) else torch.as_tensor(np.asarray(values))
+        self._buf[name].copy_(t.to(self.device).reshape(self._buf[name].shape).to(self._buf[name].dtype))
 
     def _stream(self):
-        if self._emu:
-            return None
         import torch
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _as_bool(x):
+        return x.bool()
 
     def _check(self, rc):
         if rc < 0:
@@ -445,7 +438,7 @@ class BoxDeliveryVecEnv:
     def reset(self, seed=None, options=None, mask=None):
         """Every env (or those in ``mask``) starts its next episode: env e keeps its own episode counter k_e (advanced only
         when e is reset) and runs on layout (e + k_e * num_envs) % n_layouts."""
-        if mask is not None and not self._emu and hasattr(mask, "cpu"):
+        if mask is not None and hasattr(mask, "cpu"):
             mask = mask.to("cpu").numpy()
         if self.episode_idx is None:
             self.episode_idx = np.full(self.num_envs, -1, dtype=np.int64)
@@ -468,8 +461,7 @@ class BoxDeliveryVecEnv:
             mptr = self._ptr("mask")
         self._check(self._L.bp_boxdel_step(self._h, self._ptr("actions"), mptr, C.byref(self._out), self._stream()))
         b = self._buf
-        term = b["terminated"].astype(bool) if self._emu else b["terminated"].bool()
-        trunc = b["truncated"].astype(bool) if self._emu else b["truncated"].bool()
+        term, trunc = self._as_bool(b["terminated"]), self._as_bool(b["truncated"])
         return self._observation(), b["reward"], term, trunc, self._info()
 
     def _info(self):
@@ -515,16 +507,6 @@ class BoxDeliveryVecEnv:
         ``np.abs(poly_centroid(vertices))`` (x, y) in list order; zero padded to ``2 * num_boxes``.  Computed from ``info['obs']``."""
         v = self._buf["box_verts"]
         n = self._buf["info_i"][:, 2]
-        if self._emu:
-            x, y = v[..., 0], v[..., 1]
-            xp, yp = np.roll(x, 1, axis=2), np.roll(y, 1, axis=2)
-            A = 0.5 * np.abs((x * yp).sum(2) - (y * xp).sum(2))
-            u = x * yp - xp * y
-            with np.errstate(divide="ignore", invalid="ignore"):
-                cx = np.abs(((x + xp) * u).sum(2) / (6 * A)); cy = np.abs(((y + yp) * u).sum(2) / (6 * A))
-            valid = np.arange(self.num_boxes)[None, :] < n[:, None]
-            out = np.stack([np.where(valid, cx, 0.0), np.where(valid, cy, 0.0)], axis=2)
-            return out.reshape(self.num_envs, 2 * self.num_boxes)
         import torch
         x, y = v[..., 0], v[..., 1]
         xp, yp = torch.roll(x, 1, dims=2), torch.roll(y, 1, dims=2)

@@ -144,9 +144,13 @@ class BoxDeliveryEnvB200:
         x = property(lambda self: self[0])
         y = property(lambda self: self[1])
 
-    def __init__(self, cfg=None, **kw):
+    @staticmethod
+    def _vec_class():
         from .box_delivery import BoxDeliveryVecEnv
-        self._v = BoxDeliveryVecEnv(num_envs=1, cfg=cfg, **kw)
+        return BoxDeliveryVecEnv
+
+    def __init__(self, cfg=None, **kw):
+        self._v = self._vec_class()(num_envs=1, cfg=cfg, **kw)
         self.cfg = self._v.cfg
         self.num_channels = self._v.num_channels
         self.action_space, self.observation_space = self._v.single_action_space, self._v.single_observation_space
@@ -190,9 +194,13 @@ class AreaClearingEnvB200(BoxDeliveryEnvB200):
     ``state``, ``total_work``, ``collision reward``, ``diff_reward``, ``box_completed_reward``, ``obs``,
     ``box_completed_statuses``, ``box_count``, ``ministeps`` (+ ``goal_positions`` / ``boundary`` as at reset)."""
 
-    def __init__(self, cfg=None, **kw):
+    @staticmethod
+    def _vec_class():
         from .area_clearing import AreaClearingVecEnv
-        self._v = AreaClearingVecEnv(num_envs=1, cfg=cfg, **kw)
+        return AreaClearingVecEnv
+
+    def __init__(self, cfg=None, **kw):
+        self._v = self._vec_class()(num_envs=1, cfg=cfg, **kw)
         self.cfg = self._v.cfg
         self.num_channels = self._v.num_channels
         self.action_space, self.observation_space = self._v.single_action_space, self._v.single_observation_space

@@ -69,8 +69,8 @@ def _worker_rooms(rank, world, port, q):
     from benchpush_b200.metrics import TaskDrivenMetric
     from tests.emu import emu_bd
     lo, hi = shard_range(4, rank, world)
-    env = BoxDeliveryVecEnv(num_envs=hi - lo, cfg={"agent": {"action_type": "heading"}}, env_offset=lo, _backend=emu_bd.lib())
-    ac = AreaClearingVecEnv(num_envs=hi - lo, env_offset=lo, _backend=emu_bd.lib())
+    env = emu_bd.EmuBoxDeliveryVecEnv(num_envs=hi - lo, cfg={"agent": {"action_type": "heading"}}, env_offset=lo)
+    ac = emu_bd.EmuAreaClearingVecEnv(num_envs=hi - lo, env_offset=lo)
     m = TaskDrivenMetric("t", robot_mass=1)
     obs, info = env.reset()
     m.reset(info)
@@ -94,7 +94,7 @@ def test_room_envs_shard_by_global_env_id_world2_gloo():
     [p.start() for p in ps]
     res = sorted(q.get(timeout=300) for _ in ps)
     [p.join(timeout=60) for p in ps]
-    whole = BoxDeliveryVecEnv(num_envs=4, cfg={"agent": {"action_type": "heading"}}, _backend=emu_bd.lib())
+    whole = emu_bd.EmuBoxDeliveryVecEnv(num_envs=4, cfg={"agent": {"action_type": "heading"}})
     F = len(whole.layouts) // 4
     assert F == len(res[0][1]) == len(res[1][1]) and F > 1
     for f in range(F):       # same layouts as one rank with all envs, for every episode of the pool

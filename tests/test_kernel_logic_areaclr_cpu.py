@@ -24,7 +24,7 @@ def test_layout_sampler_and_intersection_predicate():
 
 def test_maps_reset_and_heading_episode_match_the_oracle(portable_trig):
     lay = [sample_layout(random.Random(1))]
-    env = AreaClearingVecEnv(num_envs=1, layouts=lay, _backend=emu_bd.lib())
+    env = emu_bd.EmuAreaClearingVecEnv(num_envs=1, layouts=lay)
     ora = AreaClearingOracleEnv(layouts=lay)
     obs, info = env.reset()
     oobs, oinfo = ora.reset()
@@ -44,7 +44,7 @@ def test_maps_reset_and_heading_episode_match_the_oracle(portable_trig):
 
 
 def test_clearing_a_box_resets_the_clock_and_marks_it_completed(portable_trig):
-    env = AreaClearingVecEnv(num_envs=1, cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT], _backend=emu_bd.lib())
+    env = emu_bd.EmuAreaClearingVecEnv(num_envs=1, cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT])
     ora = AreaClearingOracleEnv(cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT])
     env.reset(); ora.reset()
     counts, ts = [], []
@@ -61,7 +61,7 @@ def test_small_environment_matches_the_oracle(portable_trig):
     """clear_env_small: 12 m room, 8 m clearance square, 18.67 px / m, 542 x 542 grid."""
     cfg = {"env": "clear_env_small", "num_obstacles": 6, "min_obs_dist": 1.2}
     lay = [sample_layout(random.Random(4), cfg)]
-    env = AreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=lay, _backend=emu_bd.lib())
+    env = emu_bd.EmuAreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=lay)
     ora = AreaClearingOracleEnv(cfg=cfg, layouts=lay)
     obs, info = env.reset()
     oobs, oinfo = ora.reset()
@@ -84,7 +84,7 @@ def test_walled_environments_match_the_oracle(name, shape, portable_trig):
     configuration space; maps, reset and a heading episode against the oracle."""
     cfg = {"env": name, "num_obstacles": 6}
     lay = [sample_layout(random.Random(7), cfg)]
-    env = AreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=lay, _backend=emu_bd.lib())
+    env = emu_bd.EmuAreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=lay)
     ora = AreaClearingOracleEnv(cfg=cfg, layouts=lay)
     obs, info = env.reset()
     oobs, oinfo = ora.reset()
@@ -109,7 +109,7 @@ def test_velocity_actions_match_the_oracle(portable_trig):
     set once per step, then cfg.sim.steps substeps."""
     cfg = {"env": "walled_env", "num_obstacles": 5, "agent": {"action_type": "velocity"}}
     lay = [sample_layout(random.Random(11), cfg)]
-    env = AreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=lay, _backend=emu_bd.lib())
+    env = emu_bd.EmuAreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=lay)
     ora = AreaClearingOracleEnv(cfg=cfg, layouts=lay)
     env.reset(); ora.reset()
     assert env.single_action_space.shape == (2,)

@@ -13,7 +13,7 @@ from tests.emu import emu_bd
 
 
 def _pair(cfg, layouts, n=1, force_box_spfa=False):
-    env = BoxDeliveryVecEnv(num_envs=n, cfg=cfg, layouts=layouts, force_box_spfa=force_box_spfa, _backend=emu_bd.lib())
+    env = emu_bd.EmuBoxDeliveryVecEnv(num_envs=n, cfg=cfg, layouts=layouts, force_box_spfa=force_box_spfa)
     ora = BoxDeliveryOracleEnv(cfg=cfg, layouts=layouts)
     return env, ora
 
@@ -97,8 +97,8 @@ def test_delivery_removal_and_position_actions_match_the_oracle(portable_trig):
 def test_envs_of_a_batch_are_independent(portable_trig):
     lays = [sample_layout(np.random.RandomState(s)) for s in (1, 2)]
     cfg = {"agent": {"action_type": "heading"}}
-    both = BoxDeliveryVecEnv(num_envs=2, cfg=cfg, layouts=lays, _backend=emu_bd.lib())
-    one = BoxDeliveryVecEnv(num_envs=1, cfg=cfg, layouts=lays[1:], _backend=emu_bd.lib())
+    both = emu_bd.EmuBoxDeliveryVecEnv(num_envs=2, cfg=cfg, layouts=lays)
+    one = emu_bd.EmuBoxDeliveryVecEnv(num_envs=1, cfg=cfg, layouts=lays[1:])
     both.reset(); one.reset()
     for a in (0.3, -0.6):
         both.step(np.array([0.9, a], dtype=np.float32))
@@ -134,7 +134,7 @@ def test_masked_reset_advances_only_the_masked_envs_episode():
     default pool holds several (env, episode) layouts per env (the reference re-randomises at every reset)."""
     from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
     from tests.emu import emu_bd
-    env = BoxDeliveryVecEnv(num_envs=3, cfg={"agent": {"action_type": "heading"}}, _backend=emu_bd.lib())
+    env = emu_bd.EmuBoxDeliveryVecEnv(num_envs=3, cfg={"agent": {"action_type": "heading"}})
     assert len(env.layouts) == 3 * 4
     env.reset()
     s0 = [tuple(env.get_bodies(e)[0, :3]) for e in range(3)]
@@ -153,20 +153,20 @@ def test_room_env_spaces_follow_the_reference():
     from benchpush_b200.envs.area_clearing import AreaClearingVecEnv
     from benchpush_b200.envs.box_delivery import BoxDeliveryVecEnv
     from tests.emu import emu_bd
-    bd = BoxDeliveryVecEnv(num_envs=2, cfg={"agent": {"action_type": "heading"}}, _backend=emu_bd.lib())
+    bd = emu_bd.EmuBoxDeliveryVecEnv(num_envs=2, cfg={"agent": {"action_type": "heading"}})
     assert bd.single_action_space.shape == (1,) and bd.single_action_space.dtype == np.float32
     assert float(bd.single_action_space.low[0]) == -1 and float(bd.single_action_space.high[0]) == 1
     assert bd.single_observation_space.shape == (bd.local_map_pixel_width, bd.local_map_pixel_width, 4) and bd.single_observation_space.dtype == np.uint8
     assert bd.action_space.shape == (2, 1) and bd.observation_space.shape == (2,) + bd.single_observation_space.shape
     assert bd.single_action_space.sample() in bd.single_action_space
     bd.close()
-    bp = BoxDeliveryVecEnv(num_envs=1, cfg={"agent": {"action_type": "position"}}, _backend=emu_bd.lib())
+    bp = emu_bd.EmuBoxDeliveryVecEnv(num_envs=1, cfg={"agent": {"action_type": "position"}})
     assert bp.single_action_space.shape == () and float(bp.single_action_space.high) == bp.local_map_pixel_width ** 2
     bp.close()
-    bv = BoxDeliveryVecEnv(num_envs=1, cfg={"agent": {"action_type": "velocity"}}, _backend=emu_bd.lib())
+    bv = emu_bd.EmuBoxDeliveryVecEnv(num_envs=1, cfg={"agent": {"action_type": "velocity"}})
     assert bv.single_action_space.shape == (2,)
     bv.close()
-    ac = AreaClearingVecEnv(num_envs=1, cfg={"agent": {"action_type": "position"}}, _backend=emu_bd.lib())
+    ac = emu_bd.EmuAreaClearingVecEnv(num_envs=1, cfg={"agent": {"action_type": "position"}})
     assert ac.single_action_space.shape == (1,) and ac.single_action_space.dtype == np.int32
     ac.close()
 
@@ -180,8 +180,8 @@ def test_low_dim_state_observation_of_the_room_envs():
     from oracle.area_clearing_oracle import sample_layout as ac_layout
     from oracle.raster_oracle import poly_centroid
     from tests.emu import emu_bd
-    for mk in (lambda: BoxDeliveryVecEnv(num_envs=2, cfg={"low_dim_state": True, "agent": {"action_type": "heading"}}, _backend=emu_bd.lib()),
-               lambda: AreaClearingVecEnv(num_envs=2, cfg={"low_dim_state": True}, layouts=[ac_layout(random.Random(s)) for s in (1, 2)], _backend=emu_bd.lib())):
+    for mk in (lambda: emu_bd.EmuBoxDeliveryVecEnv(num_envs=2, cfg={"low_dim_state": True, "agent": {"action_type": "heading"}}),
+               lambda: emu_bd.EmuAreaClearingVecEnv(num_envs=2, cfg={"low_dim_state": True}, layouts=[ac_layout(random.Random(s)) for s in (1, 2)])):
         env = mk()
         obs, info = env.reset()
         NB = env.num_boxes
@@ -204,7 +204,7 @@ def test_column_and_divider_rooms_match_the_oracle(portable_trig, oc, seed, step
     cfg = {"agent": {"action_type": "heading"}, "env": {"obstacle_config": oc}}
     lay = [sample_layout(np.random.RandomState(seed), cfg)]
     assert lay[0]["columns"] or lay[0]["divider"]
-    env = BoxDeliveryVecEnv(num_envs=1, cfg=cfg, layouts=lay, _backend=emu_bd.lib(), exact_spfa_parents=True)
+    env = emu_bd.EmuBoxDeliveryVecEnv(num_envs=1, cfg=cfg, layouts=lay, exact_spfa_parents=True)
     ora = BoxDeliveryOracleEnv(cfg=cfg, layouts=lay)
     assert env._L.bp_boxdel_launch_count(env._h) == 0            # emulation: reports recept_visible
     obs, info = env.reset()
@@ -231,7 +231,7 @@ def test_rooms_are_indexed_by_layout_and_deterministic_parents_keep_the_physics(
     cfg = {"agent": {"action_type": "heading"}, "env": {"obstacle_config": "small_columns"}}
     lays = [sample_layout(np.random.RandomState(s), cfg) for s in (2, 0, 4)]
     assert [len(l["columns"]) for l in lays] == [0, 1, 2]
-    env = BoxDeliveryVecEnv(num_envs=3, cfg=cfg, layouts=lays, _backend=emu_bd.lib(), exact_spfa_parents=False)
+    env = emu_bd.EmuBoxDeliveryVecEnv(num_envs=3, cfg=cfg, layouts=lays, exact_spfa_parents=False)
     oras = [BoxDeliveryOracleEnv(cfg=cfg, layouts=[l]) for l in lays]
     obs, info = env.reset()
     for e, ora in enumerate(oras):

@@ -28,7 +28,7 @@ def test_mst_cost_is_pinned_to_networkx():
 
 
 def test_task_driven_metric_on_a_delivery_episode():
-    env = BoxDeliveryVecEnv(num_envs=1, cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT], _backend=emu_bd.lib())
+    env = emu_bd.EmuBoxDeliveryVecEnv(num_envs=1, cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT])
     m = TaskDrivenMetric("test", robot_mass=env.cfg.agent.mass)
     obs, info = env.reset()
     m.reset(info)
@@ -59,7 +59,7 @@ def test_task_driven_metric_on_a_delivery_episode():
 def test_single_env_views_return_the_reference_types():
     from benchpush_b200.envs.gym_single import AreaClearingEnvB200, BoxDeliveryEnvB200
     from tests.areaclr_common import CLEARING_CFG, CLEARING_LAYOUT
-    env = BoxDeliveryEnvB200(cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT], _backend=emu_bd.lib())
+    env = emu_bd.EmuBoxDeliveryEnvB200(cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT])
     obs, info = env.reset()
     assert obs.shape == (224, 224, 4) and obs.dtype == np.uint8 and isinstance(info["state"], tuple) and len(info["obs"]) == 4
     assert set(info) == {"state", "cumulative_distance", "cumulative_boxes", "cumulative_reward", "total_work", "obs",
@@ -69,7 +69,7 @@ def test_single_env_views_return_the_reference_types():
     assert isinstance(r, float) and isinstance(term, bool) and info["cumulative_boxes"] == 1 and len(info["obs"]) == 3
     assert info["goal_positions"][0].x == 4.25 and info["goal_positions"][0].y == 1.75
     env.close()
-    ac = AreaClearingEnvB200(cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT], _backend=emu_bd.lib())
+    ac = emu_bd.EmuAreaClearingEnvB200(cfg=CLEARING_CFG, layouts=[CLEARING_LAYOUT])
     obs, info = ac.reset()
     for _ in range(3):
         obs, r, term, trunc, info = ac.step(-1.0)
@@ -90,7 +90,7 @@ def test_low_dim_observation_and_batched_evaluate():
     from oracle.raster_oracle import poly_centroid
     from benchpush_b200.evaluate import evaluate
     from tests.areaclr_common import CLEARING_CFG, CLEARING_LAYOUT
-    env = BoxDeliveryVecEnv(num_envs=1, cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT], _backend=emu_bd.lib())
+    env = emu_bd.EmuBoxDeliveryVecEnv(num_envs=1, cfg=DELIVERY_CFG, layouts=[DELIVERY_LAYOUT])
     obs, info = env.reset()
     for _ in range(2):
         obs, r, te, tr, info = env.step(np.array([-1.0], dtype=np.float32))
@@ -102,7 +102,7 @@ def test_low_dim_observation_and_batched_evaluate():
     # batched evaluate(): two area-clearing envs, each episode ends by truncation after t_max = 2 steps
     from benchpush_b200.envs.area_clearing import AreaClearingVecEnv
     cfg = dict(CLEARING_CFG, sim={"t_max": 2})
-    ac = AreaClearingVecEnv(num_envs=2, cfg=cfg, layouts=[CLEARING_LAYOUT, CLEARING_LAYOUT], _backend=emu_bd.lib())
+    ac = emu_bd.EmuAreaClearingVecEnv(num_envs=2, cfg=cfg, layouts=[CLEARING_LAYOUT, CLEARING_LAYOUT])
     m = TaskDrivenMetric("t", robot_mass=1)
     res = evaluate(ac, lambda o: np.array([-1.0, -1.0], dtype=np.float32), m, num_episodes=4)
     assert len(res["rewards"]) == 4 and len(res["efficiency_scores"]) == 4 and res["success_rates"] == [0.0] * 4
