@@ -47,7 +47,8 @@ def parse():
                     help="ship-ice (default, the BASELINE.json metric); box-delivery (BASELINE config 2: 4096 envs) and area-clearing (config 3: 16384 envs) print secondary lines")
     ap.add_argument("--obstacle-config", default="small_empty", choices=["small_empty", "small_columns", "large_columns", "large_divider"],
                     help="box-delivery room (cfg.env.obstacle_config); the column / divider rooms use a pool of --rooms layouts with their own maps")
-    ap.add_argument("--rooms", type=int, default=64)
+    ap.add_argument("--rooms", type=int, default=64, help="with --host-rooms: size of the pool of host-built rooms")
+    ap.add_argument("--host-rooms", action="store_true", help="column / divider rooms: build the maps on the host (cv2 / scipy) per pool entry instead of on the device at reset")
     ap.add_argument("--fast-parents", dest="exact_parents", action="store_false",
                     help="box-delivery / area-clearing: deterministic spfa parents from the parallel relaxation instead of the reference-order ones (default)")
     ap.add_argument("--desync", type=int, default=34,
@@ -475,7 +476,7 @@ def run_boxdel(a):
     wl = ("area-clearing-v0 (BASELINE config 3): clear_env, 10 boxes of 1 m, heading actions U(-1,1)" if area
           else "box-delivery-v0 (BASELINE config 2): %s room, %d boxes, heading actions U(-1,1)%s" % (
               oc, 10 if oc.startswith("small") else 20,
-              "" if oc.endswith("_empty") else ", a pool of %d rooms" % a.rooms))
+              "" if oc.endswith("_empty") else (", room maps rebuilt on the device at every reset" if not a.host_rooms else ", a pool of %d host-built rooms" % a.rooms)))
     wl += ", %s spfa parents" % ("reference-order" if a.exact_parents else "deterministic (--fast-parents)")
     if a.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
@@ -493,7 +494,7 @@ def run_boxdel(a):
     from benchpush_b200.envs import AreaClearingVecEnv, BoxDeliveryVecEnv
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    env = AreaClearingVecEnv(num_envs=n_envs, device=0, exact_spfa_parents=a.exact_parents) if area else BoxDeliveryVecEnv(num_envs=n_envs, cfg=bd_cfg(oc), device=0, max_rooms=a.rooms,
+    env = AreaClearingVecEnv(num_envs=n_envs, device=0, exact_spfa_parents=a.exact_parents) if area else BoxDeliveryVecEnv(num_envs=n_envs, cfg=bd_cfg(oc), device=0, max_rooms=a.rooms, device_rooms=(False if a.host_rooms else None),
                                                                                          exact_spfa_parents=a.exact_parents)
     env.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(1234)

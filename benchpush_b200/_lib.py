@@ -153,7 +153,7 @@ EXPORTS = [
     "bp_shipice_launch_count", "bp_spfa_batch", "bp_spfa_batch_host", "bp_spfa_batch_exact", "bp_spfa_batch_exact_host",
     "bp_maze_default_config", "bp_maze_create", "bp_maze_destroy", "bp_maze_load_layouts", "bp_maze_reset", "bp_maze_step",
     "bp_maze_step_masked", "bp_maze_step_host_obs_device", "bp_maze_step_host", "bp_maze_get_obstacles", "bp_maze_get_bodies", "bp_maze_get_maps",
-    "bp_boxdel_default_config", "bp_boxdel_create", "bp_boxdel_destroy", "bp_boxdel_load", "bp_boxdel_load_rooms", "bp_boxdel_reset", "bp_boxdel_step", "bp_boxdel_step_host_obs_device",
+    "bp_boxdel_default_config", "bp_boxdel_create", "bp_boxdel_destroy", "bp_boxdel_load", "bp_boxdel_load_rooms", "bp_boxdel_load_rooms_device", "bp_boxdel_get_room_maps", "bp_boxdel_reset", "bp_boxdel_step", "bp_boxdel_step_host_obs_device",
     "bp_boxdel_step_host", "bp_boxdel_get_bodies", "bp_boxdel_get_step_debug", "bp_boxdel_launch_count", "bp_boxdel_env_bytes", "bp_boxdel_set_profiling", "bp_boxdel_get_kernel_ms",
 ]
 

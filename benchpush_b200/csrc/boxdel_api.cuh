@@ -2,6 +2,7 @@
 // Included at the end of bp_api.cu (one translation unit, one shared library).
 #pragma once
 #include "boxdel_obs.cuh"
+#include "boxdel_room.cuh"
 #include "boxdel_host.h"
 
 using namespace bp::bd;
@@ -20,6 +21,27 @@ __global__ void k_bd_init_statics(BdStatics* rooms, int n_static) {
 __global__ void k_bd_visibility(const BdConst* C, int* flag) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v < C->P.H * C->P.W && !bd_cell_visible(*C, blockIdx.y, v)) atomicAnd(flag, 0);
+}
+
+// block per env pulled from a counter: the env's room maps from its layout's static shapes (boxdel_room.cuh)
+__global__ void __launch_bounds__(256) k_bd_build_rooms(const BdConst* C, const int32_t* layout_ids, const uint8_t* mask, int* scratch, int* counter) {
+    __shared__ SpfaShared S;
+    __shared__ int s_env;
+    __shared__ int s_mm[2];
+    int* my = scratch + (size_t)blockIdx.x * bd_scratch_ints(C->P);
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int e;
+            for (;;) { e = atomicAdd(counter, 1); if (e >= C->n_envs || !(mask && !mask[e])) break; }
+            s_env = e;
+        }
+        __syncthreads();
+        int env = s_env;
+        __syncthreads();
+        if (env >= C->n_envs) break;
+        int layout = (layout_ids ? layout_ids[env] : env) % C->n_layouts;
+        bd_build_room_maps(S, *C, C->rooms[C->layouts[layout].room], env, my, s_mm);
+    }
 }
 
 // warp per env
@@ -172,6 +194,7 @@ struct bp_boxdel {
     uint8_t *d_cspace = nullptr, *d_thin = nullptr, *d_small = nullptr, *d_rchan = nullptr; int32_t* d_closest = nullptr; float* d_recept = nullptr;
     char* d_envs = nullptr; int* d_scratch = nullptr; int* d_counter = nullptr; int n_blocks = 0;
     bool loaded = false;
+    bool device_maps = false;         // rooms built on the device at reset (bp_boxdel_load_rooms_device)
     int64_t launches = 0;
     // optional kernel timing (CUDA events on the launching stream around k_bd_move / k_bd_obs of every step)
     bool profiling = false;
@@ -241,13 +264,45 @@ int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, cons
                                 H, W, cspace, cspace_thin, closest, small_free, robot_chan, ch3_map);
 }
 
+static int bd_load_impl(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                        int32_t n_rooms, const int32_t* layout_room,
+                        int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                        int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
+                        const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map,
+                        const int32_t* st_npx, const int32_t* st_pxy, bool device_maps);
+
 // As bp_boxdel_load with a leading room axis on every room-dependent array (include/benchpush_b200.h).
 int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
                          int32_t n_rooms, const int32_t* layout_room,
                          int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
                          int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
                          const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map) {
-    if (!h || !starts || !n_boxes || !boxes || !st_nv || !st_verts || !st_pose || !st_rad || !st_ctype || !cspace || !cspace_thin || !closest || !small_free || !robot_chan)
+    if (!cspace || !cspace_thin || !closest || !small_free) return fail(BP_ERR_INVALID, "null argument");
+    return bd_load_impl(h, n_layouts, starts, n_boxes, boxes, n_rooms, layout_room, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype,
+                        H, W, cspace, cspace_thin, closest, small_free, robot_chan, ch3_map, nullptr, nullptr, false);
+}
+
+// One room per layout, static shapes only; the maps of an env are built on the device whenever the env is reset
+// (k_bd_build_rooms, boxdel_room.cuh) into the env's own map slot.  st_npx[n_layouts][n_static], st_pxy[n_layouts][n_static][4][2]:
+// the pixel polygons of the collision_type-3 shapes as the reference passes them to cv2.fillPoly.
+int bp_boxdel_load_rooms_device(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                                int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                                const int32_t* st_npx, const int32_t* st_pxy, int32_t H, int32_t W, const uint8_t* robot_chan) {
+    if (!st_npx || !st_pxy) return fail(BP_ERR_INVALID, "null argument");
+    if (h && h->cfg.env_kind != 0) return fail(BP_ERR_INVALID, "device-built rooms are a box-delivery feature");
+    std::vector<int32_t> ident(n_layouts > 0 ? n_layouts : 0);
+    for (int i = 0; i < n_layouts; i++) ident[i] = i;
+    return bd_load_impl(h, n_layouts, starts, n_boxes, boxes, n_layouts, ident.data(), n_static, st_nv, st_verts, st_pose, st_rad, st_ctype,
+                        H, W, nullptr, nullptr, nullptr, nullptr, robot_chan, nullptr, st_npx, st_pxy, true);
+}
+
+static int bd_load_impl(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                        int32_t n_rooms, const int32_t* layout_room,
+                        int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                        int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
+                        const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map,
+                        const int32_t* st_npx, const int32_t* st_pxy, bool device_maps) {
+    if (!h || !starts || !n_boxes || !boxes || !st_nv || !st_verts || !st_pose || !st_rad || !st_ctype || !robot_chan)
         return fail(BP_ERR_INVALID, "null argument");
     if (h->loaded) return fail(BP_ERR_STATE, "already loaded");
     if (n_layouts <= 0 || n_static <= 0 || n_static > MAXSTAT || n_rooms <= 0) return fail(BP_ERR_INVALID, "n_layouts / n_static / n_rooms out of range");
@@ -255,7 +310,7 @@ int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts
     CUDA_TRY(cudaSetDevice(c.device));
     BdHost HB;
     {
-        std::string err = bd_host_build(HB, c, n_layouts, starts, n_boxes, boxes, n_rooms, layout_room, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype, H, W);
+        std::string err = bd_host_build(HB, c, n_layouts, starts, n_boxes, boxes, n_rooms, layout_room, n_static, st_nv, st_verts, st_pose, st_rad, st_ctype, H, W, st_npx, st_pxy);
         if (!err.empty()) return fail(BP_ERR_INVALID, err);
     }
     h->hC = HB.K;
@@ -263,22 +318,29 @@ int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts
     BdParams& P = K.P;
     std::vector<BdLayout>& LY = HB.LY;
     // ---- upload
-    const size_t nv = (size_t)H * W, R = (size_t)n_rooms;
+    // map slots: one per room (host-built maps), or one per env (built on the device at reset)
+    const size_t nv = (size_t)H * W, R = device_maps ? (size_t)c.n_envs : (size_t)n_rooms;
     std::vector<short>& pa = HB.pa; std::vector<short>& pb = HB.pb;
     CUDA_TRY(cudaMalloc((void**)&h->d_layouts, sizeof(BdLayout) * n_layouts));
     CUDA_TRY(cudaMemcpy(h->d_layouts, LY.data(), sizeof(BdLayout) * n_layouts, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void**)&h->d_pa, 2 * P.n_slots)); CUDA_TRY(cudaMalloc((void**)&h->d_pb, 2 * P.n_slots));
     CUDA_TRY(cudaMemcpy(h->d_pa, pa.data(), 2 * P.n_slots, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_pb, pb.data(), 2 * P.n_slots, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc((void**)&h->d_cspace, R * nv)); CUDA_TRY(cudaMemcpy(h->d_cspace, cspace, R * nv, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc((void**)&h->d_thin, R * nv)); CUDA_TRY(cudaMemcpy(h->d_thin, cspace_thin, R * nv, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc((void**)&h->d_closest, R * nv * 8)); CUDA_TRY(cudaMemcpy(h->d_closest, closest, R * nv * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc((void**)&h->d_small, R * P.SMALL * P.SMALL)); CUDA_TRY(cudaMemcpy(h->d_small, small_free, R * P.SMALL * P.SMALL, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_cspace, R * nv)); CUDA_TRY(cudaMalloc((void**)&h->d_thin, R * nv));
+    CUDA_TRY(cudaMalloc((void**)&h->d_closest, R * nv * 8)); CUDA_TRY(cudaMalloc((void**)&h->d_small, R * P.SMALL * P.SMALL));
+    if (!device_maps) {
+        CUDA_TRY(cudaMemcpy(h->d_cspace, cspace, R * nv, cudaMemcpyHostToDevice)); CUDA_TRY(cudaMemcpy(h->d_thin, cspace_thin, R * nv, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d_closest, closest, R * nv * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->d_small, small_free, R * P.SMALL * P.SMALL, cudaMemcpyHostToDevice));
+    } else {
+        CUDA_TRY(cudaMemset(h->d_cspace, 0, R * nv)); CUDA_TRY(cudaMemset(h->d_thin, 0, R * nv));
+        CUDA_TRY(cudaMemset(h->d_closest, 0, R * nv * 8)); CUDA_TRY(cudaMemset(h->d_small, 0, R * P.SMALL * P.SMALL));
+    }
     CUDA_TRY(cudaMalloc((void**)&h->d_rchan, (size_t)P.LW * P.LW)); CUDA_TRY(cudaMemcpy(h->d_rchan, robot_chan, (size_t)P.LW * P.LW, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void**)&h->d_recept, R * nv * 4));
-    P.border_blocked = bd_border_blocked(cspace, R, H, W);
+    P.border_blocked = device_maps ? 1 : bd_border_blocked(cspace, R, H, W);
     // receptacle cell of every room (closest valid cell of the receptacle position)
-    {
+    if (!device_maps) {
         int pi = (int)std::floor(H / 2.0 - P.recept_y * P.ppm), pj = (int)std::floor(W / 2.0 + P.recept_x * P.ppm);
         pi = pi < 0 ? 0 : (pi > H - 1 ? H - 1 : pi); pj = pj < 0 ? 0 : (pj > W - 1 ? W - 1 : pj);
         for (size_t r = 0; r < R; r++) {
@@ -286,10 +348,10 @@ int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts
             HB.RM[r].recept_ci = cl[(size_t)pi * W + pj]; HB.RM[r].recept_cj = cl[nv + (size_t)pi * W + pj];
         }
     }
-    CUDA_TRY(cudaMalloc((void**)&h->d_rooms, sizeof(BdStatics) * R));
-    CUDA_TRY(cudaMemcpy(h->d_rooms, HB.RM.data(), sizeof(BdStatics) * R, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&h->d_rooms, sizeof(BdStatics) * (size_t)n_rooms));
+    CUDA_TRY(cudaMemcpy(h->d_rooms, HB.RM.data(), sizeof(BdStatics) * (size_t)n_rooms, cudaMemcpyHostToDevice));
     K.layouts = h->d_layouts; K.n_layouts = n_layouts; K.n_envs = c.n_envs; K.pair_a = h->d_pa; K.pair_b = h->d_pb;
-    K.rooms = h->d_rooms; K.n_rooms = n_rooms;
+    K.rooms = h->d_rooms; K.n_rooms = n_rooms; K.maps_per_env = device_maps ? 1 : 0;
     K.cspace = h->d_cspace; K.cspace_thin = h->d_thin; K.closest = h->d_closest; K.small_free = h->d_small; K.robot_chan = h->d_rchan; K.ch3_map = h->d_recept;
     K.env_bytes = bd_env_bytes(P.n_slots);
     CUDA_TRY(cudaMalloc((void**)&h->d_envs, K.env_bytes * c.n_envs));
@@ -305,6 +367,14 @@ int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts
     CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdConst), cudaMemcpyHostToDevice));
     k_bd_init_statics<<<n_rooms, 32>>>(h->d_rooms, P.n_static);
     CUDA_TRY(cudaGetLastError());
+    if (device_maps) {
+        // maps, receptacle field: built per env at reset; the receptacle does not see every free cell of a room with obstacles
+        P.recept_visible = 0; P.border_blocked = 1;      // the padded room's margin is wider than the dilation disk: borders are blocked
+        CUDA_TRY(cudaMemcpy(h->dC, &K, sizeof(BdParams), cudaMemcpyHostToDevice));
+        h->device_maps = true;
+        h->loaded = true;
+        return BP_OK;
+    }
     // fourth observation channel, static per room: the caller's map (area-clearing goal-point map), or the scaled
     // receptacle-source distance field (the reference recomputes it every step, box_delivery_env.py:1115-1129)
     if (ch3_map) {
@@ -370,6 +440,13 @@ int bp_boxdel_reset(bp_boxdel_t* h, const int32_t* layout_ids, const uint8_t* ma
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     int E = h->cfg.n_envs;
+    if (h->device_maps) {
+        CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
+        int blocks = h->n_blocks < E ? h->n_blocks : E;
+        k_bd_build_rooms<<<blocks, 256, 0, st>>>(h->dC, layout_ids, mask, h->d_scratch, h->d_counter);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     k_bd_reset<<<(E * 32 + 127) / 128, 128, 0, st>>>(h->dC, layout_ids, mask, bd_out(out));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -481,6 +558,24 @@ static int bd_step_host_impl(bp_boxdel_t* h, const float* actions, const bp_boxd
     for (auto& it : items) if (*it.dev) cudaFree(*it.dev);
     cudaFree(d_act);
     return rc;
+}
+
+// HOST buffers (any may be NULL): the maps env `env` currently uses — cspace / cspace_thin u8[H][W], closest i32[2][H][W],
+// small_free u8[S][S], ch3 f32[H][W].  Parity / debugging aid (the device-built rooms are compared with the host build).  Synchronises.
+int bp_boxdel_get_room_maps(bp_boxdel_t* h, int32_t env, uint8_t* cspace, uint8_t* cspace_thin, int32_t* closest, uint8_t* small_free, float* ch3) {
+    if (!h || !h->loaded || env < 0 || env >= h->cfg.n_envs) return fail(BP_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    BdEnv hdr;
+    CUDA_TRY(cudaMemcpy(&hdr, h->d_envs + h->hC.env_bytes * env, sizeof(BdEnv), cudaMemcpyDeviceToHost));
+    const BdParams& P = h->hC.P;
+    const size_t nv = (size_t)P.H * P.W, s = (size_t)hdr.map_slot, nn = (size_t)P.SMALL * P.SMALL;
+    if (cspace) CUDA_TRY(cudaMemcpy(cspace, h->d_cspace + s * nv, nv, cudaMemcpyDeviceToHost));
+    if (cspace_thin) CUDA_TRY(cudaMemcpy(cspace_thin, h->d_thin + s * nv, nv, cudaMemcpyDeviceToHost));
+    if (closest) CUDA_TRY(cudaMemcpy(closest, h->d_closest + s * 2 * nv, nv * 8, cudaMemcpyDeviceToHost));
+    if (small_free) CUDA_TRY(cudaMemcpy(small_free, h->d_small + s * nn, nn, cudaMemcpyDeviceToHost));
+    if (ch3) CUDA_TRY(cudaMemcpy(ch3, h->d_recept + s * nv, nv * 4, cudaMemcpyDeviceToHost));
+    return BP_OK;
 }
 
 // HOST out[(1 + num_boxes)][7]: body origin x, y, angle, vx, vy, w, alive — row 0 = robot.  Synchronises.

@@ -51,7 +51,7 @@ struct BdParams {
     int H, W, LW, SMALL, CROP;    // padded room (430 x 542), local map (224), small map (244), crop (318)
     int small_i0, small_j0, px_off;
     double ppm;                   // local_map_pixels_per_meter
-    double local_map_width, step_size, room_length, room_width, robot_radius;
+    double local_map_width, step_size, room_length, room_width, robot_radius, robot_half_width;
     double recept_x, recept_y;
     // rewards / episode (box_delivery/config.yaml:135-147, :120-124)
     double partial_scale, goal_reward, collision_penalty, nonmove_penalty, correct_scale, ministep;
@@ -118,8 +118,12 @@ struct BdStatics {                // immutable per ROOM: static shapes (world) +
     BBox st_bb[MAXSTAT];
     double st_rad[MAXSTAT], st_e[MAXSTAT], st_u[MAXSTAT];
     int st_nv[MAXSTAT], st_ctype[MAXSTAT];           // st_nv == 0: slot not used in this room (fewer columns than the handle's maximum)
-    int recept_ci, recept_cj;                        // closest valid cell of the receptacle position
+    int recept_ci, recept_cj;                        // closest valid cell of the receptacle position (host-built maps)
     int pad[2];
+    // collision_type-3 shapes as the reference rasterises them into the small obstacle map (update_configuration_space,
+    // box_delivery_env.py:1151-1162): pixel vertices of the polygon as passed to cv2.fillPoly; st_npx 0 = not drawn.  Used by
+    // the on-device room build (boxdel_room.cuh).
+    int st_npx[MAXSTAT], st_px[MAXSTAT][SV], st_py[MAXSTAT][SV];
 };
 
 struct BdShapes {                 // immutable per handle: robot shapes (body-local), box material
@@ -143,7 +147,8 @@ struct BdEnvCold {                // per env, global memory only: touched once p
 };
 struct BdEnv {                    // mutable per env: the HOT header (6.6 KB) — k_bd_move keeps a copy in shared memory for the whole launch
     int layout, episode, t, status, stamp, n_order, robot_hit, inactivity, cum_boxes, done, truncated, n_prev;
-    int cleared_count, room;      // room = layouts[layout].room
+    int cleared_count, room;      // room = layouts[layout].room (static shapes)
+    int map_slot, pad_ms;         // slot of this env's maps: room, or the env's own slot when the maps are built on the device at reset
     int nc, fast;                 // this substep: candidate pairs; 1 = nothing overlaps and nothing is cached (phases B-D skipped)
     int n_path, move_sign, need_spfa, src_i, src_j, tgt_i, tgt_j, n_live;      // n_live: slots with state != SL_NONE
     long long stat_substeps, stat_cand, stat_arb;
@@ -167,7 +172,8 @@ struct BdConst {
     const short* pair_a; const short* pair_b;      // [n_slots] shape ids of the dense pair table (a < b)
     // rooms: static shapes and maps (box_delivery_env.py:1140-1175).  One room per handle in the obstacle-free configurations;
     // one per layout when the reference redraws columns / a divider at every reset (box_delivery_env.py:358-471).
-    const BdStatics* rooms; int n_rooms, pad_r;
+    const BdStatics* rooms; int n_rooms;
+    int maps_per_env;                                       // 0: map slot = room (host-built maps); 1: map slot = env, built on the device at reset
     const uint8_t* cspace; const uint8_t* cspace_thin;      // [n_rooms][H][W] 1 = free
     const int32_t* closest;                                 // [n_rooms][2][H][W] distance_transform_edt indices
     const uint8_t* small_free;                              // [n_rooms][SMALL][SMALL] 1 = free floor (small_obstacle_map)

@@ -105,7 +105,7 @@ BP_DEVNI void bd_reset_env(const BdConst& C, BdEnv* E, int layout, int episode) 
     #pragma unroll 1
     for (int p = lane; p < P.n_slots; p += BP_NL) { slots[p].state = SL_NONE; slots[p].cnt = 0; slots[p].stamp = 0; slots[p].gjk = 0; slots[p].ov = 0; slots[p].mvalid = 0; }
     if (lane == 0) {
-        E->layout = layout; E->room = L.room; E->episode = episode; E->t = 0; E->status = 0; E->stamp = 0; E->n_order = 0; E->robot_hit = 0;
+        E->layout = layout; E->room = L.room; E->map_slot = C.maps_per_env ? (int)(((char*)E - C.envs) / C.env_bytes) : L.room; E->episode = episode; E->t = 0; E->status = 0; E->stamp = 0; E->n_order = 0; E->robot_hit = 0;
         E->inactivity = 0; E->cum_boxes = 0; E->done = 0; E->truncated = 0; E->n_path = 0; E->need_spfa = 0; E->n_live = 0; E->cleared_count = 0;
         E->prev_dt = 0.0; E->cum_distance = 0.0; E->cum_reward = 0.0; E->total_work = 0.0; E->last_work = 0.0; E->reward = 0.0; E->ministeps = 0.0;
         E->stat_substeps = 0; E->stat_cand = 0; E->stat_arb = 0;
@@ -206,13 +206,13 @@ BP_DEV void bd_begin_step(const BdConst& C, BdEnv* E, double action, double acti
     // shortest_path(check_straight=True), first half
     int si, sj, ti, tj;
     pos_to_pixel(P, x0, y0, &si, &sj); pos_to_pixel(P, tx, ty, &ti, &tj);
-    if (line_free(bd_cspace_thin(C, E->room), P.W, si, sj, ti, tj)) {
+    if (line_free(bd_cspace_thin(C, E->map_slot), P.W, si, sj, ti, tj)) {
         E->need_spfa = 0; E->n_path = 2;
         E->cold->path[0][0] = x0; E->cold->path[0][1] = y0; E->cold->path[1][0] = tx; E->cold->path[1][1] = ty;
     } else {
         E->need_spfa = 1;
-        closest_valid(C, E->room, si, sj, &E->src_i, &E->src_j);
-        closest_valid(C, E->room, ti, tj, &E->tgt_i, &E->tgt_j);
+        closest_valid(C, E->map_slot, si, sj, &E->src_i, &E->src_j);
+        closest_valid(C, E->map_slot, ti, tj, &E->tgt_i, &E->tgt_j);
     }
     if (P.kind == 0 && P.recept_visible) bd_box_dists_visible(C, E, E->cold->init_dist);
 }
@@ -403,7 +403,7 @@ BP_DEVNI void mv_pre(const BdConst& C, BdEnv* E, MoveVars& V) {
             if (stuck) {
                 V2 o = bd_origin(B);
                 int pi, pj, ni, nj; pos_to_pixel(P, o.x, o.y, &pi, &pj);
-                closest_valid(C, E->room, pi, pj, &ni, &nj);
+                closest_valid(C, E->map_slot, pi, pj, &ni, &nj);
                 double nx, ny; pixel_to_pos(P, ni, nj, &nx, &ny);
                 bd_set_origin(B, mk(nx, ny));
                 B.vx = 0.0; B.vy = 0.0;

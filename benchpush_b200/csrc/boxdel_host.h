@@ -25,7 +25,7 @@ inline void bd_fill_prep(const bp_prep::BodyPrep& b, double (*lv)[2], double (*l
 inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
                                  int n_rooms, const int32_t* layout_room,
                                  int n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad,
-                                 const int32_t* st_ctype, int H, int W) {
+                                 const int32_t* st_ctype, int H, int W, const int32_t* st_npx = nullptr, const int32_t* st_pxy = nullptr) {
     memset(&HB.K, 0, sizeof(HB.K));
     BdConst& K = HB.K;
     BdParams& P = K.P;
@@ -45,6 +45,7 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
     P.px_off = (int)(c.local_map_width * P.ppm / 2) + 10;
     P.local_map_width = c.local_map_width; P.step_size = c.step_size; P.room_length = c.room_length; P.room_width = c.room_width;
     P.robot_radius = (std::pow(c.robot_length * c.robot_length + c.robot_width * c.robot_width, 0.5) / 2) * 1.2;
+    P.robot_half_width = (c.robot_length > c.robot_width ? c.robot_length : c.robot_width) / 2;
     P.recept_x = c.room_length / 2 - c.receptacle_width / 2; P.recept_y = c.room_width / 2 - c.receptacle_width / 2;
     P.partial_scale = c.partial_rewards_scale; P.goal_reward = c.goal_reward; P.collision_penalty = c.collision_penalty;
     P.nonmove_penalty = c.non_movement_penalty; P.correct_scale = c.correct_direction_reward_scale; P.ministep = c.ministep_size;
@@ -93,6 +94,13 @@ inline std::string bd_host_build(BdHost& HB, const bp_boxdel_config& c, int n_la
                 bd_fill_prep(b, T.st_lv[k], T.st_ln[k], &T.st_nv[k]);
                 T.st_pose[k][0] = st_pose[3 * q]; T.st_pose[k][1] = st_pose[3 * q + 1]; T.st_pose[k][2] = st_pose[3 * q + 2];
                 T.st_rad[k] = st_rad[q]; T.st_e[k] = c.static_e; T.st_u[k] = c.static_u;
+            }
+            // pixel polygons for the on-device room build: st_npx[n_rooms][n_static], st_pxy[n_rooms][n_static][4][2] (x, y)
+            for (int k = 0; k < n_static && st_npx && st_pxy; k++) {
+                const int q = r * n_static + k;
+                if (st_npx[q] < 0 || st_npx[q] > SV) return std::string("st_npx out of range");
+                T.st_npx[k] = st_npx[q];
+                for (int i = 0; i < st_npx[q]; i++) { T.st_px[k][i] = st_pxy[((size_t)q * SV + i) * 2]; T.st_py[k][i] = st_pxy[((size_t)q * SV + i) * 2 + 1]; }
             }
         }
         S.box_rad = 0.02; S.box_e = 0.01; S.box_u = 1.0;     // create_polygon ignores its radius argument (D7)

@@ -54,8 +54,8 @@ BP_DEV void bd_dist_item(SpfaShared& S, const BdConst& C, BdEnv* E, int k, int p
         V2 o = bd_origin(B);
         sx = o.x; sy = o.y; gx = P.recept_x; gy = P.recept_y;
         int pi, pj;
-        pos_to_pixel(P, sx, sy, &pi, &pj); closest_valid(C, E->room, pi, pj, &si, &sj);
-        pos_to_pixel(P, gx, gy, &pi, &pj); closest_valid(C, E->room, pi, pj, &ti, &tj);
+        pos_to_pixel(P, sx, sy, &pi, &pj); closest_valid(C, E->map_slot, pi, pj, &si, &sj);
+        pos_to_pixel(P, gx, gy, &pi, &pj); closest_valid(C, E->map_slot, pi, pj, &ti, &tj);
     } else {
         if (phase != 0 || !E->need_spfa) return;
         sx = E->init_pos[0]; sy = E->init_pos[1]; gx = E->tgt[0]; gy = E->tgt[1];
@@ -68,19 +68,19 @@ BP_DEV void bd_dist_item(SpfaShared& S, const BdConst& C, BdEnv* E, int k, int p
         parents = scratch + (size_t)4 * nv + (size_t)P.SMALL * P.SMALL / 4 + 64;
         // (labels in a shared-memory window of the room were measured slower: the solve is bound by the dependent instruction
         // chain of one thread, and the shared memory costs resident blocks)
-        spfa_serial_init(bd_cspace(C, E->room), nv, (float*)dist, parents, (unsigned char*)mark, BP_TID, BP_NT);
+        spfa_serial_init(bd_cspace(C, E->map_slot), nv, (float*)dist, parents, (unsigned char*)mark, BP_TID, BP_NT);
         BP_BSYNC();
         if (BP_TID == 0) {
-            if (P.border_blocked) spfa_serial_run<true>(bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, parents, q0, (unsigned char*)mark);
-            else spfa_serial_run<false>(bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, parents, q0, (unsigned char*)mark);
+            if (P.border_blocked) spfa_serial_run<true>(bd_cspace(C, E->map_slot), P.H, P.W, si, sj, (float*)dist, parents, q0, (unsigned char*)mark);
+            else spfa_serial_run<false>(bd_cspace(C, E->map_slot), P.H, P.W, si, sj, (float*)dist, parents, q0, (unsigned char*)mark);
         }
     } else {
-        spfa_relax(S, bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, q0, q1, mark);
+        spfa_relax(S, bd_cspace(C, E->map_slot), P.H, P.W, si, sj, (float*)dist, q0, q1, mark);
     }
     BP_BSYNC();
     if (BP_TID == 0) {
         double wp[MAXWP][3];
-        int n = bd_extract_path(C, bd_cspace(C, E->room), parents, dist, si, sj, ti, tj, sx, sy, gx, gy, q0, q1, mark, wp, MAXWP);
+        int n = bd_extract_path(C, bd_cspace(C, E->map_slot), parents, dist, si, sj, ti, tj, sx, sy, gx, gy, q0, q1, mark, wp, MAXWP);
         if (n == 0) { E->status |= BD_PATH_OVERFLOW; n = 2; wp[0][0] = sx; wp[0][1] = sy; wp[1][0] = gx; wp[1][1] = gy; }
         if (k < P.NB) {
             double d = 0.0;
@@ -172,12 +172,12 @@ BP_DEV void bd_obs_item(BdObsShared& S, const BdConst& C, const BdEnv* E, int* s
     // ---- robot-source distance field (create_global_shortest_path_map)
     {
         int pi, pj, si, sj;
-        pos_to_pixel(P, R.px, R.py, &pi, &pj); closest_valid(C, E->room, pi, pj, &si, &sj);
-        spfa_relax(S.sp, bd_cspace(C, E->room), P.H, P.W, si, sj, (float*)dist, q0, q1, mark);
+        pos_to_pixel(P, R.px, R.py, &pi, &pj); closest_valid(C, E->map_slot, pi, pj, &si, &sj);
+        spfa_relax(S.sp, bd_cspace(C, E->map_slot), P.H, P.W, si, sj, (float*)dist, q0, q1, mark);
         BP_BSYNC();
     }
     // ---- small overhead map: floor / obstacle, receptacle, boxes, robot chassis (update_global_overhead_map)
-    { const uint8_t* sf = bd_small_free(C, E->room); for (int i = tid; i < N * N; i += nt) small[i] = sf[i]; }        // static codes: 0 obstacle, 1 floor (3 goal area in area-clearing)
+    { const uint8_t* sf = bd_small_free(C, E->map_slot); for (int i = tid; i < N * N; i += nt) small[i] = sf[i]; }        // static codes: 0 obstacle, 1 floor (3 goal area in area-clearing)
     BP_BSYNC();
     auto to_px = [&](double wx, double wy, int* x, int* y) {
         int ix = (int)(wx * P.ppm), iy = (int)(wy * P.ppm);       // astype(np.int32): truncation toward zero
@@ -242,7 +242,7 @@ BP_DEV void bd_obs_item(BdObsShared& S, const BdConst& C, const BdEnv* E, int* s
         return gi * P.W + gj;
     };
     auto ch2 = [&](int g) -> float { if (g < 0) return 0.0f; float d = i2f(dist[g]); return bd_scale_sp(P, d < inf ? d : 0.0f); };
-    const float* ch3m = bd_ch3_map(C, E->room);
+    const float* ch3m = bd_ch3_map(C, E->map_slot);
     auto ch3 = [&](int g) -> float { if (g < 0) return 0.0f; return ch3m[g]; };
     // ---- pass 1: minima of the two distance channels over the window
     if (tid == 0) { S.minbits[0] = f2i(INFINITY); S.minbits[1] = f2i(INFINITY); }

@@ -20,12 +20,14 @@ namespace bp {
 
 #if defined(__CUDACC__) && !defined(BP_HOST_EMU)
 BP_DEV int spfa_atomic_min(int* p, int v) { return atomicMin(p, v); }
+BP_DEV int spfa_atomic_max(int* p, int v) { return atomicMax(p, v); }
 BP_DEV int spfa_atomic_exch(int* p, int v) { return atomicExch(p, v); }
 BP_DEV int spfa_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 BP_DEV int f2i(float f) { return __float_as_int(f); }
 BP_DEV float i2f(int i) { return __int_as_float(i); }
 #else
 BP_DEV int spfa_atomic_min(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+BP_DEV int spfa_atomic_max(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 BP_DEV int spfa_atomic_exch(int* p, int v) { int o = *p; *p = v; return o; }
 BP_DEV int spfa_atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
 BP_DEV int f2i(float f) { int i; memcpy(&i, &f, 4); return i; }

@@ -99,6 +99,9 @@ def bind(L):
                                 [C.c_int32, C.c_int32] + [C.c_void_p] * 6
     L.bp_boxdel_load_rooms.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + \
                                       [C.c_int32, C.c_int32] + [C.c_void_p] * 6
+    L.bp_boxdel_load_rooms_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 7 + \
+                                             [C.c_int32, C.c_int32, C.c_void_p]
+    L.bp_boxdel_get_room_maps.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
     L.bp_boxdel_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
     L.bp_boxdel_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs), C.c_void_p]
     L.bp_boxdel_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BoxDelOutputs)]
@@ -129,9 +132,9 @@ class RoomMaps:
     # fewer columns leaves slots empty): receptacle, 4 walls, [columns | divider], 3 room corners x 3 triangles, [2 divider corners x 3]
     MAX_COLUMNS = {"small_columns": 2, "large_columns": 7}      # randint(1, 3) / randint(1, 8): box_delivery_env.py:466-469
 
-    def __init__(self, cfg, layout=None):
-        import cv2
-        from scipy.ndimage import binary_dilation, distance_transform_edt
+    def __init__(self, cfg, layout=None, build_maps=True):
+        """build_maps=False: static shapes and their pixel polygons only (the maps are then built on the device at every reset,
+        csrc/boxdel_room.cuh)."""
         env = cfg["env"]
         small = env["obstacle_config"].split("_")[0] == "small"
         self.room_length = rl = env["room_length"]
@@ -189,10 +192,13 @@ class RoomMaps:
         # ---- maps
         shape = (int(2 * np.ceil((rw * ppm + LW * np.sqrt(2)) / 2)), int(2 * np.ceil((rl * ppm + LW * np.sqrt(2)) / 2)))
         self.shape = shape
-        obstacle_map = np.ones(shape, dtype=np.float32)
-        small_map = np.zeros((LW + 20, LW + 20), dtype=np.float32)
+        small_shape = (LW + 20, LW + 20)
         off = int(lmw * ppm / 2) + 10
-        for verts, pose, _, ctype in st:
+        # pixel polygon of every collision_type-3 shape as update_configuration_space passes it to cv2.fillPoly (:1151-1162)
+        self.st_npx = np.zeros(ns, dtype=np.int32)
+        self.st_pxy = np.zeros((ns, 4, 2), dtype=np.int32)
+        polys = []
+        for k, (verts, pose, _, ctype) in enumerate(st):
             if ctype != 3 or len(verts) == 0:
                 continue
             cs, sn = np.cos(pose[2]), np.sin(pose[2])
@@ -201,14 +207,10 @@ class RoomMaps:
             px = (world * ppm).astype(np.int32)
             px[:, 0] += off
             px[:, 1] += off
-            px[:, 1] = small_map.shape[0] - px[:, 1]
-            cv2.fillPoly(small_map, [px], color=1)
-        si, sj = int(shape[0] / 2 - small_map.shape[0] / 2), int(shape[1] / 2 - small_map.shape[1] / 2)
-        obstacle_map[si:si + small_map.shape[0], sj:sj + small_map.shape[1]] = small_map
-        self.configuration_space = 1 - binary_dilation(obstacle_map, disk(np.floor(self.robot_radius * ppm))).astype(np.float32)
-        self.configuration_space_thin = 1 - binary_dilation(obstacle_map, disk(np.floor(self.robot_half_width * ppm))).astype(np.float32)
-        self.closest_cspace_indices = distance_transform_edt(1 - self.configuration_space, return_distances=False, return_indices=True)
-        self.small_obstacle_map = 1 - small_map
+            px[:, 1] = small_shape[0] - px[:, 1]
+            polys.append(px)
+            self.st_npx[k] = len(px)
+            self.st_pxy[k, :len(px)] = px
         W = LW
         robot_pixel_width = int(2 * self.robot_radius * ppm)
         chan = np.zeros((W, W), dtype=np.float32)
@@ -218,6 +220,20 @@ class RoomMaps:
         inside = (((I + 0.5) - W / 2) ** 2 + ((J + 0.5) - W / 2) ** 2) ** 0.5 < robot_pixel_width / 2
         chan[I[inside], J[inside]] = 1
         self.robot_state_channel = chan
+        if not build_maps:
+            return
+        import cv2
+        from scipy.ndimage import binary_dilation, distance_transform_edt
+        obstacle_map = np.ones(shape, dtype=np.float32)
+        small_map = np.zeros(small_shape, dtype=np.float32)
+        for px in polys:
+            cv2.fillPoly(small_map, [px], color=1)
+        si, sj = int(shape[0] / 2 - small_map.shape[0] / 2), int(shape[1] / 2 - small_map.shape[1] / 2)
+        obstacle_map[si:si + small_map.shape[0], sj:sj + small_map.shape[1]] = small_map
+        self.configuration_space = 1 - binary_dilation(obstacle_map, disk(np.floor(self.robot_radius * ppm))).astype(np.float32)
+        self.configuration_space_thin = 1 - binary_dilation(obstacle_map, disk(np.floor(self.robot_half_width * ppm))).astype(np.float32)
+        self.closest_cspace_indices = distance_transform_edt(1 - self.configuration_space, return_distances=False, return_indices=True)
+        self.small_obstacle_map = 1 - small_map
 
 
 LAYOUT_EPISODE_STRIDE = 1000003
@@ -234,7 +250,7 @@ class BoxDeliveryVecEnv:
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
                  seed: Optional[int] = None, force_box_spfa: bool = False, env_offset: int = 0,
                  layout_pool_episodes: Optional[int] = None, max_rooms: Optional[int] = 64,
-                 exact_spfa_parents: bool = True):
+                 exact_spfa_parents: bool = True, device_rooms: Optional[bool] = None):
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"]["obstacle_config"] not in ("small_empty", "large_empty", "small_columns", "large_columns", "large_divider"):
@@ -251,7 +267,12 @@ class BoxDeliveryVecEnv:
         self.num_boxes = NB = int(c["boxes"]["num_boxes_small"] if small else c["boxes"]["num_boxes_large"])
         self.num_channels = 4
         per_layout_rooms = not c["env"]["obstacle_config"].endswith("_empty")
-        self.room = RoomMaps(c, {"columns": [], "divider": [0.0, 0.0]} if per_layout_rooms else None)      # sizes and constants only
+        # device_rooms (default in the column / divider configurations): every layout carries its static shapes only and the maps of
+        # an env are rebuilt ON THE DEVICE at each of its resets (csrc/boxdel_room.cuh), as the reference rebuilds them at every
+        # reset; False: the maps of every layout are built here with cv2 / scipy and uploaded (a pool of at most max_rooms)
+        self.device_rooms = per_layout_rooms if device_rooms is None else bool(device_rooms) and per_layout_rooms
+        self.room = RoomMaps(c, {"columns": [], "divider": [0.0, 0.0]} if per_layout_rooms else None,
+                             build_maps=not per_layout_rooms)      # sizes and constants (and the maps of an obstacle-free room)
         self.local_map_pixel_width = LW = self.room.LW
         self.goal_points = [self.room.receptacle_position]
         if layouts is None:
@@ -262,14 +283,14 @@ class BoxDeliveryVecEnv:
             # (env_offset = first env of this rank's shard) nor on when other envs finish; an env's episode k runs on entry k mod F.
             F = default_pool_episodes(E) if layout_pool_episodes is None else max(1, int(layout_pool_episodes))
             keys = [(f, e) for f in range(F) for e in range(E)]
-            if per_layout_rooms and max_rooms is not None:
+            if per_layout_rooms and not self.device_rooms and max_rooms is not None:
                 # every layout of a column / divider configuration carries its own room maps (3 - 4 MB each on the device,
                 # built on the host): the pool is capped; env e's episode k then runs on entry (e + k * E) mod len(pool)
                 keys = keys[:max(1, int(max_rooms))]
             layouts = [sample_box_delivery_layout(np.random.RandomState(base + int(env_offset) + e + f * LAYOUT_EPISODE_STRIDE), c)
                        for f, e in keys]
         self.layouts = list(layouts)
-        self.rooms = [RoomMaps(c, l) for l in self.layouts] if per_layout_rooms else [self.room]
+        self.rooms = [RoomMaps(c, l, build_maps=not self.device_rooms) for l in self.layouts] if per_layout_rooms else [self.room]
         # ---- native handle
         L = self._L
         k = BoxDelConfig()
@@ -350,6 +371,17 @@ class BoxDeliveryVecEnv:
         # rooms: one for the handle, or one per layout (column / divider configurations); every room array gains a leading axis
         rooms = list(r) if isinstance(r, (list, tuple)) else [r]
         r = rooms[0]
+        if getattr(self, "device_rooms", False):
+            stack = lambda f, dt: np.ascontiguousarray(np.stack([f(q) for q in rooms]).astype(dt))
+            st_nv = stack(lambda q: q.st_nv, np.int32); st_verts = stack(lambda q: q.st_verts, np.float64)
+            st_pose = stack(lambda q: q.st_pose, np.float64); st_rad = stack(lambda q: q.st_rad, np.float64); st_ctype = stack(lambda q: q.st_ctype, np.int32)
+            st_npx = stack(lambda q: q.st_npx, np.int32); st_pxy = stack(lambda q: q.st_pxy, np.int32)
+            rc = np.ascontiguousarray((r.robot_state_channel * 255).astype(np.uint8))
+            self._check(L.bp_boxdel_load_rooms_device(self._h, nl, starts.ctypes.data, nbx.ctypes.data, boxes.ctypes.data, len(r.statics),
+                                                      st_nv.ctypes.data, st_verts.ctypes.data, st_pose.ctypes.data, st_rad.ctypes.data, st_ctype.ctypes.data,
+                                                      st_npx.ctypes.data, st_pxy.ctypes.data, r.shape[0], r.shape[1], rc.ctypes.data))
+            self._alloc_buffers()
+            return
         if len(rooms) > 1:
             assert len(rooms) == nl, "one room per layout"
         layout_room = np.arange(nl, dtype=np.int32) if len(rooms) > 1 else np.zeros(nl, dtype=np.int32)
@@ -366,6 +398,10 @@ class BoxDeliveryVecEnv:
                                            len(r.statics), st_nv.ctypes.data, st_verts.ctypes.data, st_pose.ctypes.data, st_rad.ctypes.data, st_ctype.ctypes.data,
                                            r.shape[0], r.shape[1], cs.ctypes.data, th.ctypes.data, cl.ctypes.data, sm.ctypes.data, rc.ctypes.data,
                                            None if c3 is None else c3.ctypes.data))
+        self._alloc_buffers()
+
+    def _alloc_buffers(self):
+        L, E, NB, LW = self._L, self.num_envs, self.num_boxes, self.local_map_pixel_width
         # ---- buffers
         self._buf = {}
         self._alloc("obs", (E, LW, LW, 4), "uint8"); self._alloc("reward", (E,), "float64")
@@ -518,6 +554,16 @@ class BoxDeliveryVecEnv:
         return torch.stack([torch.where(valid, cx, zero), torch.where(valid, cy, zero)], dim=2).reshape(self.num_envs, 2 * self.num_boxes)
 
     # ---- parity / debugging aids
+    def get_room_maps(self, e: int) -> dict:
+        """The maps env ``e`` uses at the moment (bp_boxdel_get_room_maps): configuration_space, configuration_space_thin,
+        closest_cspace_indices, small_obstacle_map (1 = free floor), receptacle_map (fourth channel before the window shift)."""
+        H, W = self.room.shape
+        S = self.local_map_pixel_width + 20
+        cs = np.zeros((H, W), np.uint8); th = np.zeros((H, W), np.uint8); cl = np.zeros((2, H, W), np.int32)
+        sm = np.zeros((S, S), np.uint8); c3 = np.zeros((H, W), np.float32)
+        self._check(self._L.bp_boxdel_get_room_maps(self._h, int(e), cs.ctypes.data, th.ctypes.data, cl.ctypes.data, sm.ctypes.data, c3.ctypes.data))
+        return {"configuration_space": cs, "configuration_space_thin": th, "closest_cspace_indices": cl, "small_obstacle_map": sm, "receptacle_map": c3}
+
     def get_bodies(self, e: int) -> np.ndarray:
         out = np.zeros((1 + self.num_boxes, 7), dtype=np.float64)
         self._check(self._L.bp_boxdel_get_bodies(self._h, int(e), out.ctypes.data))

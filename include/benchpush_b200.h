@@ -378,6 +378,17 @@ int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts
                          int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
                          int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
                          const uint8_t* small_free, const uint8_t* robot_chan, const float* ch3_map);
+/* Rooms built ON THE DEVICE: one set of static shapes per layout (arrays [n_layouts][n_static]...), no maps.  At
+ * every reset of an env a thread block rebuilds that env's small obstacle map, both configuration spaces, the nearest-free-cell
+ * map (scipy's distance_transform_edt indices incl. its tie-breaks) and the receptacle distance field from the layout's shapes
+ * (csrc/boxdel_room.cuh), as the reference does in update_configuration_space at every reset (box_delivery_env.py:1140-1175).
+ * st_npx[n_layouts][n_static] / st_pxy[n_layouts][n_static][4][2]: the pixel polygon (x, y) of every collision_type-3 shape as the
+ * reference passes it to cv2.fillPoly ((world * ppm).astype(int32) + offset, y flipped); 0 vertices = not drawn. */
+int bp_boxdel_load_rooms_device(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                                int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                                const int32_t* st_npx, const int32_t* st_pxy, int32_t H, int32_t W, const uint8_t* robot_chan);
+/* HOST buffers (any may be NULL): the maps env `env` uses at the moment (parity aid; synchronises) */
+int bp_boxdel_get_room_maps(bp_boxdel_t* h, int32_t env, uint8_t* cspace, uint8_t* cspace_thin, int32_t* closest, uint8_t* small_free, float* ch3);
 /* DEVICE pointers, enqueued on `stream`, no host synchronisation */
 int bp_boxdel_reset(bp_boxdel_t* h, const int32_t* layout_ids, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream);
 int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, const bp_boxdel_outputs* out, void* stream);

@@ -16,6 +16,7 @@
 #include "../../benchpush_b200/csrc/shipice_env.cuh"
 #include "../../benchpush_b200/csrc/spfa.cuh"
 #include "../../benchpush_b200/csrc/boxdel_obs.cuh"
+#include "../../benchpush_b200/csrc/boxdel_room.cuh"
 #include "../../benchpush_b200/csrc/boxdel_host.h"
 
 using namespace bp;
@@ -28,6 +29,7 @@ struct bp_boxdel {
     std::vector<char> envs; std::vector<int> scratch;
     int64_t launches = 0;
     bool loaded = false;
+    bool device_maps = false;
 };
 
 static BdOut bd_out(const bp_boxdel_outputs* o) {
@@ -115,6 +117,45 @@ int bp_boxdel_load_rooms(bp_boxdel_t* h, int32_t n_layouts, const double* starts
     return 0;
 }
 
+int bp_boxdel_load_rooms_device(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
+                                int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
+                                const int32_t* st_npx, const int32_t* st_pxy, int32_t H, int32_t W, const uint8_t* robot_chan) {
+    std::vector<int32_t> ident(n_layouts);
+    for (int i = 0; i < n_layouts; i++) ident[i] = i;
+    std::string err = bd_host_build(h->HB, h->cfg, n_layouts, starts, n_boxes, boxes, n_layouts, ident.data(), n_static, st_nv, st_verts, st_pose, st_rad, st_ctype, H, W, st_npx, st_pxy);
+    if (!err.empty()) { fprintf(stderr, "emu_bd: %s\n", err.c_str()); return -1; }
+    BdConst& K = h->HB.K;
+    const BdParams& P = K.P;
+    const size_t nv = (size_t)H * W, R = (size_t)h->cfg.n_envs;
+    h->cspace.assign(R * nv, 0); h->thin.assign(R * nv, 0); h->closest.assign(2 * R * nv, 0);
+    h->small_free.assign(R * P.SMALL * P.SMALL, 0); h->rchan.assign(robot_chan, robot_chan + (size_t)P.LW * P.LW);
+    h->recept.assign(R * nv, 0.0f);
+    K.layouts = h->HB.LY.data(); K.pair_a = h->HB.pa.data(); K.pair_b = h->HB.pb.data();
+    K.rooms = h->HB.RM.data(); K.n_rooms = n_layouts; K.maps_per_env = 1;
+    K.cspace = h->cspace.data(); K.cspace_thin = h->thin.data(); K.closest = h->closest.data(); K.small_free = h->small_free.data();
+    K.robot_chan = h->rchan.data(); K.ch3_map = h->recept.data();
+    h->envs.assign(K.env_bytes * h->cfg.n_envs, 0);
+    K.envs = h->envs.data();
+    h->scratch.assign(bd_scratch_ints(P), 0);
+    for (int r = 0; r < n_layouts; r++) for (int k = 0; k < P.n_static; k++) bd_init_static(h->HB.RM[r], k);
+    K.P.recept_visible = 0; K.P.border_blocked = 1;
+    h->device_maps = true;
+    h->loaded = true;
+    return 0;
+}
+
+int bp_boxdel_get_room_maps(bp_boxdel_t* h, int32_t env, uint8_t* cspace, uint8_t* cspace_thin, int32_t* closest, uint8_t* small_free, float* ch3) {
+    const BdConst& K = h->HB.K;
+    const BdParams& P = K.P;
+    const size_t nv = (size_t)P.H * P.W, s = (size_t)bd_env(K, env)->map_slot, nn = (size_t)P.SMALL * P.SMALL;
+    if (cspace) memcpy(cspace, K.cspace + s * nv, nv);
+    if (cspace_thin) memcpy(cspace_thin, K.cspace_thin + s * nv, nv);
+    if (closest) memcpy(closest, K.closest + s * 2 * nv, nv * 8);
+    if (small_free) memcpy(small_free, K.small_free + s * nn, nn);
+    if (ch3) memcpy(ch3, K.ch3_map + s * nv, nv * 4);
+    return 0;
+}
+
 int bp_boxdel_load(bp_boxdel_t* h, int32_t n_layouts, const double* starts, const int32_t* n_boxes, const double* boxes,
                    int32_t n_static, const int32_t* st_nv, const double* st_verts, const double* st_pose, const double* st_rad, const int32_t* st_ctype,
                    int32_t H, int32_t W, const uint8_t* cspace, const uint8_t* cspace_thin, const int32_t* closest,
@@ -137,6 +178,11 @@ int bp_boxdel_reset(bp_boxdel_t* h, const int32_t* layout_ids, const uint8_t* ma
     for (int e = 0; e < h->cfg.n_envs; e++) {
         if (mask && !mask[e]) continue;
         BdEnv* E = bd_env(K, e);
+        if (h->device_maps) {
+            SpfaShared S; int mm[2];
+            int layout = (layout_ids ? layout_ids[e] : e) % K.n_layouts;
+            bd_build_room_maps(S, K, K.rooms[K.layouts[layout].room], e, h->scratch.data(), mm);
+        }
         bd_reset_env(K, E, (layout_ids ? layout_ids[e] : e) % K.n_layouts, 0);
         bd_reset_out(K, E, e, o);
     }

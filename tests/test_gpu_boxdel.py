@@ -195,16 +195,23 @@ def test_column_and_divider_rooms_match_the_oracle_gpu(portable_trig, oc, seeds,
     cfg = {"agent": {"action_type": "heading"}, "env": {"obstacle_config": oc}}
     lays = [sample_layout(np.random.RandomState(s), cfg) for s in seeds]
     n = len(lays)
-    env = BoxDeliveryVecEnv(num_envs=n, cfg=cfg, layouts=lays, device=0, exact_spfa_parents=True)
-    fast = BoxDeliveryVecEnv(num_envs=n, cfg=cfg, layouts=lays, device=0, exact_spfa_parents=False)
+    from benchpush_b200.envs.box_delivery import RoomMaps
+    env = BoxDeliveryVecEnv(num_envs=n, cfg=cfg, layouts=lays, device=0, exact_spfa_parents=True)            # rooms built on the device at reset
+    fast = BoxDeliveryVecEnv(num_envs=n, cfg=cfg, layouts=lays, device=0, exact_spfa_parents=False, device_rooms=False)   # host-built maps uploaded
+    assert env.device_rooms and not fast.device_rooms
     oras = [BoxDeliveryOracleEnv(cfg=cfg, layouts=[l]) for l in lays]
     obs, info = env.reset()
     fobs, _ = fast.reset()
     assert np.array_equal(obs.cpu().numpy(), fobs.cpu().numpy())
     for e, ora in enumerate(oras):
         oobs, _ = ora.reset()
-        assert np.array_equal(env.rooms[e].configuration_space, ora.configuration_space)
-        assert np.array_equal(env.rooms[e].closest_cspace_indices, ora.closest_cspace_indices)
+        m, host = env.get_room_maps(e), RoomMaps(env.cfg, lays[e])
+        for key in ("configuration_space", "configuration_space_thin", "closest_cspace_indices", "small_obstacle_map"):
+            assert np.array_equal(m[key], np.asarray(getattr(host, key)).astype(m[key].dtype)), (e, key)      # device build == cv2 / scipy
+            assert np.array_equal(m[key], np.asarray(getattr(ora, key)).astype(m[key].dtype)), (e, key)
+            assert np.array_equal(fast.get_room_maps(e)[key], m[key]), (e, key)
+        assert np.array_equal(m["receptacle_map"], ora.create_global_shortest_path_to_receptacle_map().astype(np.float32))
+        assert np.array_equal(fast.get_room_maps(e)["receptacle_map"], m["receptacle_map"])
         assert np.array_equal(obs[e].cpu().numpy(), oobs), e
         assert np.array_equal(env.get_bodies(e)[:, :6], ora.space.state()[:1 + env.num_boxes])
     rng = np.random.default_rng(0)
