@@ -39,6 +39,55 @@ BP_DEV bool bd_dilated(const int* gcol, int H, int W, int i, int j, int r, int r
     return false;
 }
 
+// scipy.ndimage.distance_transform_edt(1 - free, return_distances=False, return_indices=True) for a 2-D map: for every cell the
+// (row, column) of the nearest free cell, a free cell mapping to itself; among equally near free cells the one in the smallest
+// column, then the smallest row (scipy's own outcome; tests/test_kernel_logic_boxdel_cpu.py holds this against scipy on random
+// maps).  Block-cooperative; gcol / grow: H * W ints of scratch each; sh_minmax: 2 ints shared by the block.
+// out[0][H][W] = rows, out[1][H][W] = columns.
+BP_DEV void bd_feature_transform(const uint8_t* cs, int H, int W, int32_t* closest, int* gcol, int* grow, int* sh_minmax) {
+    const int tid = BP_TID, nt = BP_NT;
+    const size_t nv = (size_t)H * W;
+    const int BIG = 1 << 20;
+    if (tid == 0) { sh_minmax[0] = W; sh_minmax[1] = -1; }
+    BP_BSYNC();
+    for (int j = tid; j < W; j += nt) {
+        int last = -BIG; bool any = false;
+        for (int i = 0; i < H; i++) {
+            if (cs[(size_t)i * W + j]) { last = i; any = true; }
+            gcol[(size_t)i * W + j] = i - last; grow[(size_t)i * W + j] = last;          // nearest free cell above (or far away)
+        }
+        last = BIG;
+        for (int i = H - 1; i >= 0; i--) {
+            if (cs[(size_t)i * W + j]) last = i;
+            if (last - i < gcol[(size_t)i * W + j]) { gcol[(size_t)i * W + j] = last - i; grow[(size_t)i * W + j] = last; }   // strictly nearer: ties keep the upper one
+        }
+        if (any) { spfa_atomic_min(&sh_minmax[0], j); spfa_atomic_max(&sh_minmax[1], j); }
+    }
+    BP_BSYNC();
+    {
+        const int c0 = sh_minmax[0], c1 = sh_minmax[1];
+        for (size_t v = tid; v < nv; v += nt) {
+            const int i = (int)(v / W), j = (int)(v - (size_t)i * W);
+            int bj = j, bi = i;
+            if (!cs[v] && c1 >= c0) {
+                const int g = gcol[v];
+                const int R = g < BIG / 2 ? g : W;                         // a better column is at most g away
+                int lo = j - R < c0 ? c0 : j - R, hi = j + R > c1 ? c1 : j + R;
+                long long best = -1;
+                for (int jj = lo; jj <= hi; jj++) {
+                    const int gg = gcol[(size_t)i * W + jj];
+                    if (gg >= BIG / 2) continue;
+                    const long long cost = (long long)gg * gg + (long long)(j - jj) * (j - jj);
+                    if (best < 0 || cost < best) { best = cost; bj = jj; }
+                }
+                bi = grow[(size_t)i * W + bj];
+            }
+            closest[v] = bi; closest[nv + v] = bj;
+        }
+    }
+    BP_BSYNC();
+}
+
 // Block-cooperative.  scratch: >= 4 * H * W ints (the per-block scratch of k_bd_dist / k_bd_obs).  Writes the maps of `slot`.
 BP_DEV void bd_build_room_maps(SpfaShared& S, const BdConst& C, const BdStatics& T, int slot, int* scratch, int* sh_minmax) {
     const BdParams& P = C.P;
@@ -92,45 +141,7 @@ BP_DEV void bd_build_room_maps(SpfaShared& S, const BdConst& C, const BdStatics&
     }
     BP_BSYNC();
     // ---- 4. feature transform of the configuration space: nearest free cell, ties -> smallest column, then smallest row
-    const int BIG = 1 << 20;
-    if (tid == 0) { sh_minmax[0] = W; sh_minmax[1] = -1; }
-    BP_BSYNC();
-    for (int j = tid; j < W; j += nt) {
-        int last = -BIG; bool any = false;
-        for (int i = 0; i < H; i++) {
-            if (cs[(size_t)i * W + j]) { last = i; any = true; }
-            gcol[(size_t)i * W + j] = i - last; grow[(size_t)i * W + j] = last;          // nearest free cell above (or far away)
-        }
-        last = BIG;
-        for (int i = H - 1; i >= 0; i--) {
-            if (cs[(size_t)i * W + j]) last = i;
-            if (last - i < gcol[(size_t)i * W + j]) { gcol[(size_t)i * W + j] = last - i; grow[(size_t)i * W + j] = last; }   // strictly nearer: ties keep the upper one
-        }
-        if (any) { spfa_atomic_min(&sh_minmax[0], j); spfa_atomic_max(&sh_minmax[1], j); }
-    }
-    BP_BSYNC();
-    {
-        const int c0 = sh_minmax[0], c1 = sh_minmax[1];
-        for (size_t v = tid; v < nv; v += nt) {
-            const int i = (int)(v / W), j = (int)(v - (size_t)i * W);
-            int bj = j, bi = i;
-            if (!cs[v] && c1 >= c0) {
-                const int g = gcol[v];
-                const int R = g < BIG / 2 ? g : W;                         // a better column is at most g away
-                int lo = j - R < c0 ? c0 : j - R, hi = j + R > c1 ? c1 : j + R;
-                long long best = -1;
-                for (int jj = lo; jj <= hi; jj++) {
-                    const int gg = gcol[(size_t)i * W + jj];
-                    if (gg >= BIG / 2) continue;
-                    const long long cost = (long long)gg * gg + (long long)(j - jj) * (j - jj);
-                    if (best < 0 || cost < best) { best = cost; bj = jj; }
-                }
-                bi = grow[(size_t)i * W + bj];
-            }
-            closest[v] = bi; closest[nv + v] = bj;
-        }
-    }
-    BP_BSYNC();
+    bd_feature_transform(cs, H, W, closest, gcol, grow, sh_minmax);
     // ---- 5. small_free = 1 - small obstacle map
     for (int i = tid; i < N * N; i += nt) sm[i] = sm[i] ? 0 : 1;
     BP_BSYNC();

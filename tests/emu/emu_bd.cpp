@@ -243,6 +243,12 @@ int bp_boxdel_get_step_debug(bp_boxdel_t* h, int32_t env, double* out16, double*
     if (path) memcpy(path, E->cold->path, sizeof(E->cold->path));
     return 0;
 }
+// bd_feature_transform (csrc/boxdel_room.cuh) on an arbitrary map: free u8[H][W] -> indices i32[2][H][W]
+void emu_feature_transform(const uint8_t* free_map, int H, int W, int32_t* out) {
+    std::vector<int> g((size_t)H * W), r((size_t)H * W);
+    int mm[2];
+    bd_feature_transform(free_map, H, W, out, g.data(), r.data(), mm);
+}
 // host twin of bp_spfa_batch_host (same kernel source, one lane)
 int bp_spfa_batch_host(const uint8_t* maps, const int32_t* sources, int32_t batch, int32_t H, int32_t W, float* dists, int32_t* parents) {
     size_t nv = (size_t)H * W;

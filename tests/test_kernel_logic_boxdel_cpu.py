@@ -259,3 +259,34 @@ def test_rooms_are_indexed_by_layout_and_deterministic_parents_keep_the_physics(
             assert np.abs(gb[0, :3] - ora.space.state()[0, :3]).max() <= 1e-9
             assert np.abs(gb[1:][alive][:, :3] - ora.space.state()[list(ora.box_bodies)][:, :3]).max() <= 1e-9
     env.close()
+
+
+def test_device_feature_transform_reproduces_scipy_including_ties():
+    """bd_feature_transform (csrc/boxdel_room.cuh: the nearest-free-cell map of the on-device room build) against
+    scipy.ndimage.distance_transform_edt(..., return_indices=True) itself: random maps of several densities, block-structured
+    maps (many equidistant candidates), a single free cell, a fully free map."""
+    import ctypes as C
+    from scipy.ndimage import distance_transform_edt
+    L = emu_bd.lib()
+    rng = np.random.default_rng(0)
+    cases = []
+    for t in range(40):
+        H, W = int(rng.integers(6, 70)), int(rng.integers(6, 70))
+        blocked = (rng.random((H, W)) < rng.choice([0.3, 0.8, 0.97])).astype(np.uint8)
+        if t % 3 == 0:
+            blocked[:] = 1
+            for _ in range(int(rng.integers(1, 6))):
+                a, b = int(rng.integers(0, H - 2)), int(rng.integers(0, W - 2))
+                blocked[a:a + int(rng.integers(1, 9)), b:b + int(rng.integers(1, 9))] = 0
+        if (blocked == 0).sum() == 0:
+            blocked[H // 2, W // 2] = 0
+        cases.append(blocked)
+    one = np.ones((31, 47), np.uint8); one[13, 20] = 0
+    cases += [one, np.zeros((9, 12), np.uint8)]
+    for blocked in cases:
+        H, W = blocked.shape
+        ref = distance_transform_edt(blocked, return_distances=False, return_indices=True)
+        free = np.ascontiguousarray(1 - blocked)
+        out = np.zeros((2, H, W), dtype=np.int32)
+        L.emu_feature_transform(free.ctypes.data_as(C.c_void_p), C.c_int(H), C.c_int(W), out.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(out, ref.astype(np.int32)), (H, W)
