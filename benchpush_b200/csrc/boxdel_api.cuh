@@ -193,6 +193,7 @@ struct bp_boxdel {
     BdLayout* d_layouts = nullptr; BdStatics* d_rooms = nullptr; short* d_pa = nullptr; short* d_pb = nullptr;
     uint8_t *d_cspace = nullptr, *d_thin = nullptr, *d_small = nullptr, *d_rchan = nullptr; int32_t* d_closest = nullptr; float* d_recept = nullptr;
     char* d_envs = nullptr; int* d_scratch = nullptr; int* d_counter = nullptr; int n_blocks = 0;
+    int dist_blocks = 0, dist_threads = 256;      // k_bd_dist launch shape (reference-order parents: many small blocks, one serial solve each)
     bool loaded = false;
     bool device_maps = false;         // rooms built on the device at reset (bp_boxdel_load_rooms_device)
     int64_t launches = 0;
@@ -359,7 +360,13 @@ static int bd_load_impl(bp_boxdel_t* h, int32_t n_layouts, const double* starts,
     K.envs = h->d_envs;
     int sms = 0; CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
     h->n_blocks = sms * 4;
-    CUDA_TRY(cudaMalloc((void**)&h->d_scratch, (size_t)h->n_blocks * bd_scratch_ints(P) * sizeof(int)));
+    // Reference-order parents: a solve is one thread's sequential queue (the rest of the block only initialises), so k_bd_dist
+    // runs as many 64-thread blocks as fit an SM (80 registers: 12) instead of 3 blocks of 256 threads — 4x the concurrent solves.
+    h->dist_threads = P.exact_parents ? 64 : 256;
+    h->dist_blocks = P.exact_parents ? sms * 12 : h->n_blocks;
+    if (const char* e = getenv("BP_BD_DIST_WIDE")) { if (atoi(e) != 0) { h->dist_threads = 256; h->dist_blocks = h->n_blocks; } }      // A/B measurements
+    const int max_blocks = h->dist_blocks > h->n_blocks ? h->dist_blocks : h->n_blocks;
+    CUDA_TRY(cudaMalloc((void**)&h->d_scratch, (size_t)max_blocks * bd_scratch_ints(P) * sizeof(int)));
     CUDA_TRY(cudaMalloc((void**)&h->d_counter, 64));
     CUDA_TRY(cudaMalloc((void**)&h->d_mv, sizeof(MoveVars) * (size_t)c.n_envs));
     CUDA_TRY(cudaMallocHost((void**)&h->h_flag, 64));
@@ -460,10 +467,10 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
     cudaStream_t st = (cudaStream_t)stream;
     int E = h->cfg.n_envs;
     int items = E * (h->cfg.num_boxes + 1);
-    int blocks = h->n_blocks < items ? h->n_blocks : items;
+    int blocks = h->dist_blocks < items ? h->dist_blocks : items;
     k_bd_begin<<<(E + 127) / 128, 128, 0, st>>>(h->dC, actions, mask);
     CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
-    k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 0, h->d_scratch, h->d_counter);
+    k_bd_dist<<<blocks, h->dist_threads, 0, st>>>(h->dC, mask, 0, h->d_scratch, h->d_counter);
     cudaEvent_t e4[4] = {nullptr, nullptr, nullptr, nullptr};
     if (h->profiling) { for (auto& e : e4) { CUDA_TRY(cudaEventCreate(&e)); h->ev.push_back(e); } CUDA_TRY(cudaEventRecord(e4[0], st)); }
     if (h->cfg.phase_kernels) {
@@ -493,7 +500,7 @@ int bp_boxdel_step(bp_boxdel_t* h, const float* actions, const uint8_t* mask, co
     if (h->profiling) CUDA_TRY(cudaEventRecord(e4[1], st));
     if (!h->hC.P.recept_visible) {
         CUDA_TRY(cudaMemsetAsync(h->d_counter, 0, 4, st));
-        k_bd_dist<<<blocks, 256, 0, st>>>(h->dC, mask, 1, h->d_scratch, h->d_counter);
+        k_bd_dist<<<blocks, h->dist_threads, 0, st>>>(h->dC, mask, 1, h->d_scratch, h->d_counter);
         h->launches++;
     }
     k_bd_finish<<<(E + 127) / 128, 128, 0, st>>>(h->dC, mask, bd_out(out));

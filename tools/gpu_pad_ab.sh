@@ -14,5 +14,3 @@ for oc in small_columns large_columns; do
   timeout 900 python bench.py --env box-delivery --obstacle-config $oc --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_bench_boxdel_$oc.json 2> gpurun_out/r02b_bench_boxdel_$oc.err
   tail -n 1 gpurun_out/r02b_bench_boxdel_$oc.json | cut -c1-230; tail -2 gpurun_out/r02b_bench_boxdel_$oc.err
 done
-timeout 900 python bench.py --env box-delivery --obstacle-config small_columns --exact-parents --envs 1024 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r02b_bench_boxdel_small_columns_exact.json 2>&1
-tail -n 1 gpurun_out/r02b_bench_boxdel_small_columns_exact.json | cut -c1-230
