@@ -145,7 +145,11 @@ __global__ void __launch_bounds__(1024) k_schedule(const char* mem, size_t env_b
     __syncthreads();
     for (int e = threadIdx.x; e < n_envs; e += blockDim.x) {
         int p = atomicAdd(&start[key_of(e)], 1);
-        int idx = balanced ? (p % n_batches) * bk + p / n_batches : p;
+        // balanced: deal the sorted envs over the batches like cards; balanced == 2 reverses every other round (snake order), so that
+        // the batch that got the heaviest env of one round gets the lightest of the next
+        int round = p / n_batches, q = p % n_batches;
+        if (balanced == 2 && (round & 1)) q = n_batches - 1 - q;
+        int idx = balanced ? q * bk + round : p;
         perm[idx] = e;
     }
 }
@@ -344,6 +348,7 @@ struct bp_shipice {
     bool warp_impl = false;        // BP_STEP_IMPL=warp: one env per warp (A/B measurements)
     int* perm = nullptr; int perm_cap = 0;   // step schedule (k_schedule); BP_NO_SCHEDULE=1 keeps the identity order
     bool use_schedule = true;
+    bool snake = true;                 // BP_NO_SNAKE=1: plain round-robin dealing (A/B measurements)
     bool pad_batches = true;           // BP_NO_PAD=1 turns the partly-filled-batch schedule off (A/B measurements)
     bool res_impl = false;         // resident step (sim_res.cuh): the default for ship-ice; BP_STEP_IMPL=batch selects sim_batch.cuh
     int res_blocks_per_sm = 1;
@@ -519,6 +524,7 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
     if (const char* e = getenv("BP_STEP_IMPL")) h->warp_impl = (strcmp(e, "warp") == 0);
     if (const char* e = getenv("BP_NO_SCHEDULE")) h->use_schedule = !(atoi(e) != 0);
     if (const char* e = getenv("BP_NO_PAD")) h->pad_batches = !(atoi(e) != 0);
+    if (const char* e = getenv("BP_NO_SNAKE")) h->snake = !(atoi(e) != 0);
     // resident step (sim_res.cuh), ship-ice only (the per-substep checks of the maze run on the env block).  Selected with
     // BP_STEP_IMPL=res: in fp64 only three pools fit an SM, and three warps per SM issue too slowly to beat the batched
     // kernel (profiles/r02a_*), so the batched kernel stays the default.
@@ -681,7 +687,7 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
             CUDA_TRY(cudaMalloc((void**)&h->perm, (size_t)n_batches * bk * 4));
             h->perm_cap = n_batches * bk;
         }
-        k_schedule<<<1, 1024, 0, st>>>(h->mem, h->env_bytes, h->d.n_envs, mask, h->cfg.auto_reset, h->perm, bk, n_batches, n_batches < 2 * warp_slots ? 1 : 0);
+        k_schedule<<<1, 1024, 0, st>>>(h->mem, h->env_bytes, h->d.n_envs, mask, h->cfg.auto_reset, h->perm, bk, n_batches, n_batches < 2 * warp_slots ? (h->snake ? 2 : 1) : 0);
         a.perm = h->perm; a.n_sched = n_batches * bk;
     }
     if (h->res_impl) {
