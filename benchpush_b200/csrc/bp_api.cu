@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepAr
 //     round-robin over the batches, so that every batch gets the same mix and the launch does not wait for one heavy batch.
 // Results do not depend on the schedule (envs never interact; tests run the same envs under different schedules).
 __global__ void __launch_bounds__(1024) k_schedule(const char* mem, size_t env_bytes, int n_envs, const uint8_t* mask, int auto_reset,
-                                                    int* perm, int bk, int n_batches, int balanced) {
+                                                    int* perm, int bk, int n_batches, int balanced, long long* prev, int* keybuf) {
     __shared__ int hist[256];
     __shared__ int start[256];
     const int n_sched = n_batches * bk;
@@ -135,16 +135,27 @@ __global__ void __launch_bounds__(1024) k_schedule(const char* mem, size_t env_b
         if (mask && !mask[e]) return 255;                                   // not stepping: last
         const EnvScal* sc = (const EnvScal*)(mem + env_bytes * (size_t)e);
         if (auto_reset && sc->done) return 254;                             // reset = copy of a snapshot: light
+        if (prev && balanced) {
+            // balanced dealing wants the env's COST: arbiters and awake bodies averaged over its previous step (the counters the
+            // substep loop keeps), not the state it happens to be in at the end of it
+            long long ds = sc->stat_substeps - prev[3 * (size_t)e + 2];
+            long long dl = sc->stat_live_sum - prev[3 * (size_t)e], da = sc->stat_awake_sum - prev[3 * (size_t)e + 1];
+            prev[3 * (size_t)e] = sc->stat_live_sum; prev[3 * (size_t)e + 1] = sc->stat_awake_sum; prev[3 * (size_t)e + 2] = sc->stat_substeps;
+            if (ds > 0 && dl >= 0 && da >= 0) {
+                long long cost = (2 * dl + da) / ds;
+                return 253 - (int)(cost > 252 ? 252 : cost);
+            }
+        }
         int nc = sc->n_colours < 15 ? sc->n_colours : 15;
         int na = sc->n_awake / 4; if (na > 14) na = 14;
         return 253 - (nc * 15 + na);                                        // descending cost
     };
-    for (int e = threadIdx.x; e < n_envs; e += blockDim.x) atomicAdd(&hist[key_of(e)], 1);
+    for (int e = threadIdx.x; e < n_envs; e += blockDim.x) { int k = key_of(e); keybuf[e] = k; atomicAdd(&hist[k], 1); }
     __syncthreads();
     if (threadIdx.x == 0) { int acc = 0; for (int i = 0; i < 256; i++) { start[i] = acc; acc += hist[i]; } }
     __syncthreads();
     for (int e = threadIdx.x; e < n_envs; e += blockDim.x) {
-        int p = atomicAdd(&start[key_of(e)], 1);
+        int p = atomicAdd(&start[keybuf[e]], 1);
         // balanced: deal the sorted envs over the batches like cards; balanced == 2 reverses every other round (snake order), so that
         // the batch that got the heaviest env of one round gets the lightest of the next
         int round = p / n_batches, q = p % n_batches;
@@ -348,6 +359,8 @@ struct bp_shipice {
     bool warp_impl = false;        // BP_STEP_IMPL=warp: one env per warp (A/B measurements)
     int* perm = nullptr; int perm_cap = 0;   // step schedule (k_schedule); BP_NO_SCHEDULE=1 keeps the identity order
     bool use_schedule = true;
+    bool sched_history = true;         // balanced dealing by the previous step's average arbiters / awake bodies (BP_SCHED_HISTORY=0: by the current colours / awake count)
+    long long* sched_prev = nullptr; int* sched_keys = nullptr;
     bool snake = true;                 // BP_NO_SNAKE=1: plain round-robin dealing (A/B measurements)
     bool pad_batches = true;           // BP_NO_PAD=1 turns the partly-filled-batch schedule off (A/B measurements)
     bool res_impl = false;         // resident step (sim_res.cuh): the default for ship-ice; BP_STEP_IMPL=batch selects sim_batch.cuh
@@ -456,6 +469,8 @@ int bp_shipice_destroy(bp_shipice_t* h) {
     if (h->mem) cudaFree(h->mem);
     if (h->counter) cudaFree(h->counter);
     if (h->perm) cudaFree(h->perm);
+    if (h->sched_keys) cudaFree(h->sched_keys);
+    if (h->sched_prev) cudaFree(h->sched_prev);
     if (h->d_actions) cudaFree(h->d_actions);
     if (h->d_obs) cudaFree(h->d_obs);
     if (h->h_actions) cudaFreeHost(h->h_actions);
@@ -525,6 +540,7 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
     if (const char* e = getenv("BP_NO_SCHEDULE")) h->use_schedule = !(atoi(e) != 0);
     if (const char* e = getenv("BP_NO_PAD")) h->pad_batches = !(atoi(e) != 0);
     if (const char* e = getenv("BP_NO_SNAKE")) h->snake = !(atoi(e) != 0);
+    if (const char* e = getenv("BP_SCHED_HISTORY")) h->sched_history = atoi(e) != 0;
     // resident step (sim_res.cuh), ship-ice only (the per-substep checks of the maze run on the env block).  Selected with
     // BP_STEP_IMPL=res: in fp64 only three pools fit an SM, and three warps per SM issue too slowly to beat the batched
     // kernel (profiles/r02a_*), so the batched kernel stays the default.
@@ -682,12 +698,17 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
         // partly filled batches (perm entries -1) instead of leaving slots idle — the step is latency bound, extra warps are free.
         if (h->pad_batches && n_batches < warp_slots) n_batches = warp_slots < h->d.n_envs ? warp_slots : h->d.n_envs;
         sched_batches = n_batches;
+        if (!h->sched_keys) {
+            CUDA_TRY(cudaMalloc((void**)&h->sched_keys, (size_t)h->d.n_envs * 4));
+            CUDA_TRY(cudaMalloc((void**)&h->sched_prev, (size_t)h->d.n_envs * 24));
+            CUDA_TRY(cudaMemsetAsync(h->sched_prev, 0, (size_t)h->d.n_envs * 24, st));
+        }
         if (!h->perm || h->perm_cap < n_batches * bk) {
             if (h->perm) cudaFree(h->perm);
             CUDA_TRY(cudaMalloc((void**)&h->perm, (size_t)n_batches * bk * 4));
             h->perm_cap = n_batches * bk;
         }
-        k_schedule<<<1, 1024, 0, st>>>(h->mem, h->env_bytes, h->d.n_envs, mask, h->cfg.auto_reset, h->perm, bk, n_batches, n_batches < 2 * warp_slots ? (h->snake ? 2 : 1) : 0);
+        k_schedule<<<1, 1024, 0, st>>>(h->mem, h->env_bytes, h->d.n_envs, mask, h->cfg.auto_reset, h->perm, bk, n_batches, n_batches < 2 * warp_slots ? (h->snake ? 2 : 1) : 0, h->sched_history ? h->sched_prev : nullptr, h->sched_keys);
         a.perm = h->perm; a.n_sched = n_batches * bk;
     }
     if (h->res_impl) {
