@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128, BP_MIN_BLOCKS) k_shipice_step_warp(StepAr
 //     round-robin over the batches, so that every batch gets the same mix and the launch does not wait for one heavy batch.
 // Results do not depend on the schedule (envs never interact; tests run the same envs under different schedules).
 __global__ void __launch_bounds__(1024) k_schedule(const char* mem, size_t env_bytes, int n_envs, const uint8_t* mask, int auto_reset,
-                                                    int* perm, int bk, int n_batches, int balanced, long long* prev, int* keybuf) {
+                                                    int* perm, int bk, int n_batches, int balanced, long long* prev, int* keybuf, int hist_all) {
     __shared__ int hist[256];
     __shared__ int start[256];
     const int n_sched = n_batches * bk;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(1024) k_schedule(const char* mem, size_t env_b
         if (mask && !mask[e]) return 255;                                   // not stepping: last
         const EnvScal* sc = (const EnvScal*)(mem + env_bytes * (size_t)e);
         if (auto_reset && sc->done) return 254;                             // reset = copy of a snapshot: light
-        if (prev && balanced) {
+        if (prev && (balanced || hist_all)) {
             // balanced dealing wants the env's COST: arbiters and awake bodies averaged over its previous step (the counters the
             // substep loop keeps), not the state it happens to be in at the end of it
             long long ds = sc->stat_substeps - prev[3 * (size_t)e + 2];
@@ -361,6 +361,7 @@ struct bp_shipice {
     bool use_schedule = true;
     bool sched_history = true;         // balanced dealing by the previous step's average arbiters / awake bodies (BP_SCHED_HISTORY=0: by the current colours / awake count)
     long long* sched_prev = nullptr; int* sched_keys = nullptr;
+    bool sched_hist_all = false;       // BP_SCHED_HISTORY=2: the history key also orders the grouped (many batches per warp) mode
     bool snake = true;                 // BP_NO_SNAKE=1: plain round-robin dealing (A/B measurements)
     bool pad_batches = true;           // BP_NO_PAD=1 turns the partly-filled-batch schedule off (A/B measurements)
     bool res_impl = false;         // resident step (sim_res.cuh): the default for ship-ice; BP_STEP_IMPL=batch selects sim_batch.cuh
@@ -540,7 +541,7 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
     if (const char* e = getenv("BP_NO_SCHEDULE")) h->use_schedule = !(atoi(e) != 0);
     if (const char* e = getenv("BP_NO_PAD")) h->pad_batches = !(atoi(e) != 0);
     if (const char* e = getenv("BP_NO_SNAKE")) h->snake = !(atoi(e) != 0);
-    if (const char* e = getenv("BP_SCHED_HISTORY")) h->sched_history = atoi(e) != 0;
+    if (const char* e = getenv("BP_SCHED_HISTORY")) { h->sched_history = atoi(e) != 0; h->sched_hist_all = atoi(e) == 2; }
     // resident step (sim_res.cuh), ship-ice only (the per-substep checks of the maze run on the env block).  Selected with
     // BP_STEP_IMPL=res: in fp64 only three pools fit an SM, and three warps per SM issue too slowly to beat the batched
     // kernel (profiles/r02a_*), so the batched kernel stays the default.
@@ -708,7 +709,7 @@ int bp_shipice_step_masked(bp_shipice_t* h, const float* actions, const uint8_t*
             CUDA_TRY(cudaMalloc((void**)&h->perm, (size_t)n_batches * bk * 4));
             h->perm_cap = n_batches * bk;
         }
-        k_schedule<<<1, 1024, 0, st>>>(h->mem, h->env_bytes, h->d.n_envs, mask, h->cfg.auto_reset, h->perm, bk, n_batches, n_batches < 2 * warp_slots ? (h->snake ? 2 : 1) : 0, h->sched_history ? h->sched_prev : nullptr, h->sched_keys);
+        k_schedule<<<1, 1024, 0, st>>>(h->mem, h->env_bytes, h->d.n_envs, mask, h->cfg.auto_reset, h->perm, bk, n_batches, n_batches < 2 * warp_slots ? (h->snake ? 2 : 1) : 0, h->sched_history ? h->sched_prev : nullptr, h->sched_keys, h->sched_hist_all ? 1 : 0);
         a.perm = h->perm; a.n_sched = n_batches * bk;
     }
     if (h->res_impl) {
