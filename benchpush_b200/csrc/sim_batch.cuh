@@ -45,6 +45,7 @@ struct BatchShared {             // one per warp, in shared memory
     int n_col, wl_valid;
     int skip_res;                // resident step (sim_res.cuh): gate == -2 marks a touching pair that is evaluated from shared memory
     unsigned char flags[BK];     // bit0 yaw violated, bit1 boundary violated (ship_ice_env.py:284-290)
+    int st_sub[BK], st_live[BK], st_awake[BK];   // per-step sums of the schedule's cost counters (EnvScal::stat_*), flushed once per env step
     unsigned wl[BWL];            // (e << 16) | slot, grouped by colour
     unsigned q0[BQ], q1[BQ];     // (e << 24) | index into apairs
     unsigned q2[BQE], q2hint[BQE];
@@ -482,7 +483,7 @@ BP_DEVNI void batch_substep(const DevConst* C, BatchShared& S, real dt, real pre
         view_s(S.base[ent >> 16]).slot[ent & 0xFFFF].first = 0;
     }
     for (int e = lane; e < BK; e += BP_NL)
-        if (S.base[e]) { EnvScal* sc = (EnvScal*)S.base[e]; sc->stat_substeps++; sc->stat_live_sum += sc->n_order; sc->stat_awake_sum += sc->n_awake; }
+        if (S.base[e]) { const EnvScal* sc = (const EnvScal*)S.base[e]; S.st_sub[e]++; S.st_live[e] += sc->n_order; S.st_awake[e] += sc->n_awake; }
     bp_wsync();
 }
 
@@ -516,7 +517,7 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
                 shipice_step_begin(ev, L, P, d, (real)actions[env]);
             }
         }
-        if (lane == 0) { S.base[e] = base; S.env_id[e] = env; S.flags[e] = 0; }
+        if (lane == 0) { S.base[e] = base; S.env_id[e] = env; S.flags[e] = 0; S.st_sub[e] = 0; S.st_live[e] = 0; S.st_awake[e] = 0; }
         bp_wsync();
     }
     if (lane == 0) { S.wl_valid = 0; S.skip_res = 0; }
@@ -540,7 +541,11 @@ BP_DEVNI void shipice_step_batch(const DevConst* C, BatchShared& S, char* mem, s
         EnvView ev = view_s(base);
         int env = S.env_id[e];
         env_step_finish(ev, S.L[e], P, d, env, out, (int)S.flags[e]);
-        if (lane == 0) { ev.sc->done = out.terminated[env]; ev.sc->obs_raw = 0; }
+        if (lane == 0) {
+            EnvScal* sc = ev.sc;
+            sc->done = out.terminated[env]; sc->obs_raw = 0;
+            sc->stat_substeps += S.st_sub[e]; sc->stat_live_sum += S.st_live[e]; sc->stat_awake_sum += S.st_awake[e];
+        }
         bp_wsync();
     }
 }
