@@ -542,6 +542,8 @@ static int finish_load_layouts(bp_shipice* h, int32_t n_layouts) {
     if (const char* e = getenv("BP_NO_PAD")) h->pad_batches = !(atoi(e) != 0);
     if (const char* e = getenv("BP_NO_SNAKE")) h->snake = !(atoi(e) != 0);
     if (const char* e = getenv("BP_SCHED_HISTORY")) { h->sched_history = atoi(e) != 0; h->sched_hist_all = atoi(e) == 2; }
+    // tuning experiments only: DRAM -> L2 fetch granularity hint (32 / 64 / 128 bytes); the env state is accessed sector by sector
+    if (const char* e = getenv("BP_L2_FETCH")) { int g = atoi(e); if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g); }
     // resident step (sim_res.cuh), ship-ice only (the per-substep checks of the maze run on the env block).  Selected with
     // BP_STEP_IMPL=res: in fp64 only three pools fit an SM, and three warps per SM issue too slowly to beat the batched
     // kernel (profiles/r02a_*), so the batched kernel stays the default.

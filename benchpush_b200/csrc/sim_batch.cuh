@@ -27,9 +27,19 @@ namespace bp {
 namespace BP_BATCH_NS {
 
 constexpr int BK = BP_BK;        // envs per warp batch
-constexpr int BQ = 256;          // per-warp narrowphase queue (entries)
-constexpr int BQE = 96;          // per-warp EPA queue
-constexpr int BWL = 512;         // merged solver work list (arbiters of the whole batch)
+#ifndef BP_BQ
+#define BP_BQ 256
+#endif
+#ifndef BP_BQE
+#define BP_BQE 96
+#endif
+#ifndef BP_BWL
+#define BP_BWL 512
+#endif
+constexpr int BQ = BP_BQ;        // per-warp narrowphase queue (entries)
+constexpr int BQE = BP_BQE;      // per-warp EPA queue
+constexpr int BWL = BP_BWL;      // merged solver work list (arbiters of the whole batch; a longer list is solved env by env)
+static_assert(BQ >= 2 * BP_NL && BQE >= 2 * BP_NL && BQ % BP_NL == 0 && BQE % BP_NL == 0, "queues are filled a warp at a time");
 constexpr int BCOL = 16;         // colours the merged solve handles (more -> per-env fallback)
 
 struct BatchShared {             // one per warp, in shared memory
@@ -38,8 +48,8 @@ struct BatchShared {             // one per warp, in shared memory
     int env_id[BK];
     int off_awake[BK + 1], off_ap[BK + 1], off_ord[BK + 1];
     unsigned long long dmax_bits[BK];
-    int ccnt[BK][BCOL];          // arbiters of env e with colour c
-    int cpre[BK][BCOL];          // start of env e's segment inside the merged colour-c segment
+    unsigned short ccnt[BK][BCOL];   // arbiters of env e with colour c
+    unsigned short cpre[BK][BCOL];          // start of env e's segment inside the merged colour-c segment
     int off_col[BCOL + 1];
     int n_items;                 // merged list length, -1 = does not fit (per-env fallback)
     int n_col, wl_valid;
@@ -203,7 +213,7 @@ BP_DEVNI void batch_build_worklist(const DevConst* C, BatchShared& S) {
             EnvView ev = view_s(S.base[e]);
             if (c < ev.sc->n_colours) v = ev.col_start[c + 1] - ev.col_start[c];
         }
-        S.ccnt[e][c] = v;
+        S.ccnt[e][c] = (unsigned short)v;
     }
     bp_wsync();
     if (lane == 0) {
@@ -223,7 +233,7 @@ BP_DEVNI void batch_build_worklist(const DevConst* C, BatchShared& S) {
         if (ncol > BCOL) ncol = BCOL;
         for (int c = 0; c < ncol; c++) {
             S.off_col[c] = acc;
-            for (int e = 0; e < BK; e++) { S.cpre[e][c] = acc; acc += S.ccnt[e][c]; }
+            for (int e = 0; e < BK; e++) { S.cpre[e][c] = (unsigned short)acc; acc += S.ccnt[e][c]; }
         }
         S.off_col[ncol] = acc;
         S.n_col = ncol;

@@ -62,8 +62,13 @@ def test_portable_trig_accuracy():
     assert cpo.sincos(0.5) == (math.sin(0.5), math.cos(0.5))      # default mode is libm
 
 
-def test_batched_path_equals_one_env_per_warp_path():
-    """sim_batch.cuh (a warp advances 8 envs together) against sim_step.cuh (one env per warp): bit-identical."""
+@pytest.mark.parametrize("flags", ["", "-DBP_BWL=128 -DBP_BQ=64 -DBP_BQE=64", "-DBP_BWL=24 -DBP_BQ=64 -DBP_BQE=64 -DBP_RES_PA=24 -DBP_RES_PV=300 -DBP_RES_PS=20"])
+def test_batched_path_equals_one_env_per_warp_path(flags, monkeypatch):
+    """sim_batch.cuh (a warp advances 8 envs together) against sim_step.cuh (one env per warp): bit-identical, whatever the
+    capacities of the per-warp queues (BP_BQ / BP_BQE: narrowphase queues flushed in rounds; BP_BWL: merged solver list — 24
+    entries do not hold the arbiters of 8 envs, so those substeps are solved env by env)."""
+    if flags:
+        monkeypatch.setenv("BP_EMU_FLAGS", flags)
     nl = 3
     packed = pack_trials(generate_experiment(nl, 0.5, seed=11))
     E = 10

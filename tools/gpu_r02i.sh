@@ -1,0 +1,51 @@
+#!/bin/bash
+# Last GPU call of round 2.
+#  1. A/B of k_shipice_step launch variants at the headline workload (65 536 envs, concentration 0.5, steady-state phases):
+#     per-warp queue capacities (BP_BWL / BP_BQ / BP_BQE: 26.6 KB -> 13.3 KB of shared memory per block = 132 KB -> 64 KB
+#     carve-out, i.e. 124 KB -> 192 KB of L1 per SM), 5 / 6 blocks per SM on top of the small queues, and the DRAM -> L2 fetch
+#     granularity hint (BP_L2_FETCH).  The final-state hashes must agree.
+#  2. GPU suite, smoke() and bench.py with the fastest bit-identical variant (the default when nothing beats it by 2 %).
+mkdir -p gpurun_out
+AB=gpurun_out/r02i_step_variants_ab.txt; : > $AB
+V=$PWD/benchpush_b200/csrc/variants
+ab() {   # label, library ("" = default), L2 fetch ("" = unset)
+  echo "variant $1" >> $AB
+  ( [ -n "$2" ] && export BENCHPUSH_B200_LIB=$2; [ -n "$3" ] && export BP_L2_FETCH=$3; timeout 240 python tools/bench_variant.py 65536 0.5 3 4 10 ) 2>&1 | tail -1 >> $AB
+}
+ab default "" ""
+ab tinyq $V/lib_tinyq.so ""
+ab tinyq_b5 $V/lib_tinyq_b5.so ""
+ab tinyq_b6 $V/lib_tinyq_b6.so ""
+ab default_l2fetch32 "" 32
+ab tinyq_l2fetch32 $V/lib_tinyq.so 32
+python - >> $AB <<'E'
+import re
+rows, lab = [], None
+for ln in open("gpurun_out/r02i_step_variants_ab.txt"):
+    if ln.startswith("variant "): lab = ln.split()[1]; continue
+    m = re.search(r"-> (\d+) env-steps/s .* sha (\w+)", ln)
+    if m and lab: rows.append((lab, int(m.group(1)), m.group(2)))
+base = dict((r[0], r) for r in rows).get("default")
+best = base
+for r in rows:
+    if base and r[2] == base[2] and best and r[1] > best[1]: best = r
+if base and best and best[1] < 1.02 * base[1]: best = base
+print("winner", best[0] if best else "default")
+open("gpurun_out/r02i_winner.txt", "w").write(best[0] if best else "default")
+E
+W=$(cat gpurun_out/r02i_winner.txt 2>/dev/null || echo default)
+case "$W" in
+  tinyq) export BENCHPUSH_B200_LIB=$V/lib_tinyq.so ;;
+  tinyq_b5) export BENCHPUSH_B200_LIB=$V/lib_tinyq_b5.so ;;
+  tinyq_b6) export BENCHPUSH_B200_LIB=$V/lib_tinyq_b6.so ;;
+  default_l2fetch32) export BP_L2_FETCH=32 ;;
+  tinyq_l2fetch32) export BENCHPUSH_B200_LIB=$V/lib_tinyq.so; export BP_L2_FETCH=32 ;;
+esac
+cat $AB
+echo "suite / smoke / bench run with: LIB=${BENCHPUSH_B200_LIB:-default} L2_FETCH=${BP_L2_FETCH:-unset}" | tee gpurun_out/r02i_gputest.log
+python -c "from oracle import cpo; cpo.lib()" 2>&1 | tail -1      # one build check before the parallel workers start
+timeout 420 python -m pytest tests -m gpu -q -n 4 2>&1 | tail -6 >> gpurun_out/r02i_gputest.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 >> gpurun_out/r02i_gputest.log
+cat gpurun_out/r02i_gputest.log
+timeout 300 python bench.py > gpurun_out/r02i_bench.json 2> gpurun_out/r02i_bench.err
+tail -c 1500 gpurun_out/r02i_bench.json
