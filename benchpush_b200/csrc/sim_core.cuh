@@ -219,6 +219,7 @@ static inline EnvOff env_offsets(const Dims& d) {
 }
 BP_DEV EnvView view_at(char* base, const EnvOff& O) {
     EnvView v;
+    BP_ASSUME_GLOBAL_PTR(base);      // accesses through the view compile to LDG / STG instead of generic LD / ST: +2 % (profiles/r02l_assume_global_ab.txt)
 #define X(i, member, type) v.member = (type*)(base + O.o[i]);
     BP_ENV_FIELD_LIST(X)
 #undef X

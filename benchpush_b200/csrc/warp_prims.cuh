@@ -26,6 +26,18 @@ typedef double real;
 #if defined(__CUDACC__) && !defined(BP_HOST_EMU)
 #define BP_DEV __device__ __forceinline__
 #define BP_DEVNI __device__ __noinline__
+// An address-space fact the compiler cannot see through pointers that travel in structs / shared memory / out-of-line calls:
+// env blocks live in device global memory.  With the assumption (made where an EnvView is formed, view_at) those accesses
+// compile to LDG / STG instead of generic LD / ST: +2 % on the batched step (profiles/r02l_assume_global_ab.txt).  Extending
+// it to the layout tables, the handle constants and the polygon scans (one loop per address space) was measured slower
+// (profiles/r02m_address_space_ab.txt) and is not done.  -DBP_NO_ASSUME_SPACE builds the generic code.
+#if defined(__CUDA_ARCH__) && !defined(BP_NO_ASSUME_SPACE)
+#define BP_ASSUME_GLOBAL_PTR(p) __builtin_assume(__isGlobal((const void*)(p)))
+#define BP_ASSUME_SHARED_PTR(p) __builtin_assume(__isShared((const void*)(p)))
+#else
+#define BP_ASSUME_GLOBAL_PTR(p) ((void)0)
+#define BP_ASSUME_SHARED_PTR(p) ((void)0)
+#endif
 // One environment is simulated by a GROUP of BP_NL consecutive lanes of a warp (BP_NL = 32, 16, 8 or
 // 4; 32 / BP_NL environments share a warp).  Groups of one warp start every substep together and run
 // the same instruction stream, so SIMT divergence/reconvergence keeps them in lockstep through the
@@ -83,6 +95,8 @@ BP_DEV void bp_prefetch(const void* p, int n_lines) {
 #include <math.h>
 #define BP_DEV static inline
 #define BP_DEVNI static
+#define BP_ASSUME_GLOBAL_PTR(p) ((void)0)
+#define BP_ASSUME_SHARED_PTR(p) ((void)0)
 #define BP_NL 1
 BP_DEV int bp_lane() { return 0; }
 BP_DEV void bp_wsync() {}
