@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit for box-delivery-v0: parity tests, timing at BASELINE config 2 (4096 envs), ncu launch list and
-# full captures of the two heaviest kernels.   gpurun --timeout 1500 -- 'bash tools/gpu_boxdel.sh'
+# full captures of the two heaviest kernels.   gpurun --timeout 1500 -- 'bash tools/gpu_runs/gpu_boxdel.sh'
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.csv 2>&1

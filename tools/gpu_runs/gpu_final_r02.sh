@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 final measurement set on one B200: GPU test suite, smoke, headline bench + reference arm, secondary env benches,
-# ncu launch list of the headline command.   gpurun --timeout 3000 -- 'bash tools/gpu_final_r02.sh'
+# ncu launch list of the headline command.   gpurun --timeout 3000 -- 'bash tools/gpu_runs/gpu_final_r02.sh'
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r02f_gpu.txt
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee gpurun_out/r02f_gputest.log

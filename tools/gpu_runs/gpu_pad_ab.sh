@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of the partly-filled-batch schedule (BP_NO_PAD) at the per-GPU shares of the N = 8 / 4 strong-scaling points; box-delivery
-# benches with the box-distance cache.   gpurun --timeout 2400 -- 'bash tools/gpu_pad_ab.sh'
+# benches with the box-distance cache.   gpurun --timeout 2400 -- 'bash tools/gpu_runs/gpu_pad_ab.sh'
 mkdir -p gpurun_out; : > gpurun_out/r02_pad_ab.log
 timeout 900 python -m pytest tests/test_gpu_shipice.py tests/test_gpu_boxdel.py -m gpu -x -q 2>&1 | tail -3 >> gpurun_out/r02_pad_ab.log
 for E in 8192 16384 4096; do

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Follow-up of tools/gpu_r02i.sh: which per-warp queue capacity made the small-queue variants 19 % slower?  One capacity changed
+# Follow-up of tools/gpu_runs/gpu_r02i.sh: which per-warp queue capacity made the small-queue variants 19 % slower?  One capacity changed
 # at a time (same workload and arguments as r02i; default there: 61 724 env-steps/s), plus two larger capacities.
 mkdir -p gpurun_out
 AB=gpurun_out/r02j_step_queue_capacity_ab.txt; : > $AB

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Scaling points of the headline bench on one box: gpurun --gpus N --timeout 1500 -- 'bash tools/gpu_scale_r02.sh N [N2 ...]'
+# Scaling points of the headline bench on one box: gpurun --gpus N --timeout 1500 -- 'bash tools/gpu_runs/gpu_scale_r02.sh N [N2 ...]'
 mkdir -p gpurun_out
 for N in "$@"; do
   if [ "$N" = 1 ]; then
