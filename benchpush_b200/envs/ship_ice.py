@@ -5,6 +5,12 @@ Keeps the reference's gym-style API (``ShipIceEnv``, ship_ice_env.py:37-355): ``
 the same one-level merge, and the same ``info`` keys — but every return value carries a leading
 batch dimension and lives on the GPU as a torch tensor.  All simulation work happens in
 ``libbenchpush_b200.so`` (CUDA, sm_100a); torch only owns the buffers and the stream.
+
+Ownership differs from the reference in one way: the reference allocates fresh numpy arrays per call, whereas the tensors
+returned by ``reset()`` / ``step()`` (``obs``, ``reward``, ``terminated``, ``truncated`` and the tensors inside ``info``) are
+the env's persistent device buffers, overwritten in place by the next ``step()`` / ``reset()`` (zero-copy hand-off to a
+policy on the GPU).  A caller that keeps a value across steps — a replay buffer, a per-episode trace — must ``.clone()`` it.
+The same holds for ``MazeNamoVecEnv`` and the room envs.
 """
 from __future__ import annotations
 
