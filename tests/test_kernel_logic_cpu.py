@@ -86,6 +86,10 @@ def test_batched_path_equals_one_env_per_warp_path(flags, monkeypatch):
         for e in range(E):
             assert np.array_equal(A.bodies(e, e % nl), B.bodies(e, e % nl))
             assert A.out(e) == B.out(e)
+            # the schedule's cost counters (summed in shared memory by the batched path, flushed once per env step) agree with
+            # the one-env path, which bumps them in the env block every substep
+            sa, sb = A.scal(e), B.scal(e)
+            assert (sa["substeps"], sa["live_sum"], sa["awake_sum"]) == (sb["substeps"], sb["live_sum"], sb["awake_sum"]), (k, e)
 
 
 def test_awake_set_is_small_and_exact(golden_layouts):
