@@ -148,7 +148,14 @@ class ClearingMaps:
 class AreaClearingVecEnv(BoxDeliveryVecEnv):
     def __init__(self, num_envs: int = 1, cfg=None, device: Optional[int] = None, layouts: Optional[Sequence[dict]] = None,
                  seed: int = 1, env_offset: int = 0, layout_pool_episodes: Optional[int] = None,
-                 exact_spfa_parents: bool = True):
+                 exact_spfa_parents: bool = True, sam: bool = False):
+        # ``sam``: the observation of the spatial-action-map baselines — ``sam_local_map_pixel_width`` (96) instead of
+        # ``local_map_pixel_width`` (224) pixels for the same local map (what ``configure_env_for_SAM`` switches to,
+        # area_clearing.py:221-223)
+        self._ctor = dict(num_envs=num_envs, cfg=cfg, device=device, layouts=layouts, seed=seed, env_offset=env_offset,
+                          layout_pool_episodes=layout_pool_episodes, exact_spfa_parents=exact_spfa_parents)
+        self.sam = bool(sam)
+        self.path = None
         self.cfg = merge_cfg(DotDict(DEFAULT_CFG), cfg)
         c = self.cfg
         if c["env"] not in ENVS:
@@ -156,6 +163,8 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
         if c["agent"]["action_type"] not in ("heading", "position", "velocity"):
             raise NotImplementedError("unknown action_type %r" % (c["agent"]["action_type"],))
         self.env_cfg = ENVS[c["env"]]
+        if self.sam:
+            self.env_cfg = dict(self.env_cfg, local_map_pixel_width=self.env_cfg["sam_local_map_pixel_width"])
         self.num_envs = E = int(num_envs)
         self._open(device)
         self.num_boxes = NB = int(c["num_obstacles"])
@@ -210,6 +219,21 @@ class AreaClearingVecEnv(BoxDeliveryVecEnv):
         self.goal_point_global_map = self._goal_point_map()
         k.exact_spfa_parents = 1 if exact_spfa_parents else 0      # see BoxDeliveryVecEnv
         self._finish_init(k, r, ch3_map=self.goal_point_global_map)
+
+    def configure_env_for_SAM(self):
+        """``AreaClearingEnv.configure_env_for_SAM`` (area_clearing.py:221-223): observations, maps and the position-action
+        space switch to ``sam_local_map_pixel_width``.  The reference calls it right after construction; here the native handle,
+        whose rasters and room maps are sized at creation, is rebuilt with the same arguments (episode state is discarded, call
+        ``reset()`` next)."""
+        if self.sam:
+            return
+        kw = self._ctor
+        self.close()
+        type(self).__init__(self, sam=True, **kw)
+
+    def update_path(self, new_path):
+        """area_clearing.py:922-925: remembers the path for a renderer (no renderer here)."""
+        self.path = new_path
 
     def _spfa_many(self, cspace_u8, sources):
         """One shortest-path field per source on the shared configuration space (bp_spfa_batch_host of the bound library)."""

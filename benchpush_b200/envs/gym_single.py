@@ -207,6 +207,17 @@ class AreaClearingEnvB200(BoxDeliveryEnvB200):
         self.local_map_pixel_width = self._v.local_map_pixel_width
         self.episode_idx = None
 
+    def configure_env_for_SAM(self):
+        """area_clearing.py:221-223: switch to the 96-pixel observation of the spatial-action-map baselines (call before reset)."""
+        self._v.configure_env_for_SAM()
+        self.action_space, self.observation_space = self._v.single_action_space, self._v.single_observation_space
+        self.local_map_pixel_width = self._v.local_map_pixel_width
+
+    def update_path(self, new_path):
+        """area_clearing.py:922-925."""
+        self._v.update_path(new_path)
+        self.path = new_path
+
     def _info(self, info):
         n = int(_np(info["n_boxes_left"])[0])
         st = _np(info["state"])[0]

@@ -125,18 +125,7 @@ class AreaClearingOracleEnv(BoxDeliveryOracleEnv):
         self.path = None
         self.dp = None
         self.local_map_pixel_width = self.env_cfg["local_map_pixel_width"]
-        self.local_map_width = self.env_cfg["local_map_width"]
-        self.local_map_pixels_per_meter = self.local_map_pixel_width / self.local_map_width
-        ag = c["agent"]
-        self.robot_radius = ((ag["length"] ** 2 + ag["width"] ** 2) ** 0.5 / 2) * 1.2
-        W = self.local_map_pixel_width
-        rpw = int(2 * self.robot_radius * self.local_map_pixels_per_meter)
-        self.robot_state_channel = np.zeros((W, W), dtype=np.float32)
-        start = int(np.floor(W / 2 - rpw / 2))
-        for i in range(start, start + rpw):
-            for j in range(start, start + rpw):
-                if (((i + 0.5) - W / 2) ** 2 + ((j + 0.5) - W / 2) ** 2) ** 0.5 < rpw / 2:
-                    self.robot_state_channel[i, j] = 1
+        self._configure_state_and_observation_channels()
         self.target_speed = c["controller"]["target_speed"]
         self.outer = self.env_cfg["outer_boundary"]
         self.boundary_vertices = self.env_cfg["boundary"]
@@ -162,6 +151,29 @@ class AreaClearingOracleEnv(BoxDeliveryOracleEnv):
                 self.goal_points.append(tuple(p0 + (d / length) * (p1 - p0)))
         self.goal_point_global_map = None
         self.configuration_space = None
+
+    def _configure_state_and_observation_channels(self):
+        """area_clearing.py:168-190: everything that depends on ``local_map_pixel_width``."""
+        c = self.cfg
+        self.local_map_width = self.env_cfg["local_map_width"]
+        self.local_map_pixels_per_meter = self.local_map_pixel_width / self.local_map_width
+        ag = c["agent"]
+        self.robot_radius = ((ag["length"] ** 2 + ag["width"] ** 2) ** 0.5 / 2) * 1.2
+        W = self.local_map_pixel_width
+        rpw = int(2 * self.robot_radius * self.local_map_pixels_per_meter)
+        self.robot_state_channel = np.zeros((W, W), dtype=np.float32)
+        start = int(np.floor(W / 2 - rpw / 2))
+        for i in range(start, start + rpw):
+            for j in range(start, start + rpw):
+                if (((i + 0.5) - W / 2) ** 2 + ((j + 0.5) - W / 2) ** 2) ** 0.5 < rpw / 2:
+                    self.robot_state_channel[i, j] = 1
+        self.goal_point_global_map = None
+        self.configuration_space = None
+
+    def configure_env_for_SAM(self):
+        """area_clearing.py:221-223."""
+        self.local_map_pixel_width = self.env_cfg["sam_local_map_pixel_width"]
+        self._configure_state_and_observation_channels()
 
     def _build_space(self, layout):
         c = self.cfg

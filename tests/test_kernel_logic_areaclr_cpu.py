@@ -57,6 +57,38 @@ def test_clearing_a_box_resets_the_clock_and_marks_it_completed(portable_trig):
     env.close()
 
 
+def test_configure_env_for_sam_matches_the_oracle(portable_trig):
+    """``configure_env_for_SAM`` (area_clearing.py:221-223): the 96-pixel observation of the spatial-action-map baselines —
+    room maps, goal-point map, rasters and position actions at 4 pixels per metre, heading and position actions."""
+    lay = [sample_layout(random.Random(1))]
+    env = emu_bd.EmuAreaClearingVecEnv(num_envs=1, layouts=lay)
+    ora = AreaClearingOracleEnv(layouts=lay)
+    assert env.local_map_pixel_width == 224
+    env.configure_env_for_SAM(); ora.configure_env_for_SAM()
+    env.configure_env_for_SAM()                                                   # idempotent
+    assert env.sam and env.local_map_pixel_width == 96 == ora.local_map_pixel_width and env.observation_shape == (96, 96, 4)
+    obs, info = env.reset()
+    oobs, oinfo = ora.reset()
+    assert np.array_equal(env.room.configuration_space, ora.configuration_space)
+    assert np.array_equal(env.room.closest_cspace_indices, ora.closest_cspace_indices)
+    assert np.array_equal(env.goal_point_global_map, ora.goal_point_global_map)
+    assert obs.shape[1:] == (96, 96, 4) and np.array_equal(obs[0], oobs)
+    rng = np.random.default_rng(2)
+    for k in range(6):
+        a = float(np.float32(rng.uniform(-1, 1)))
+        compare_step(env, ora, 0, a, env.step(np.array([a], dtype=np.float32)), state_tol=1e-9)
+    env.update_path([(0.0, 0.0), (1.0, 1.0)])
+    assert env.path == [(0.0, 0.0), (1.0, 1.0)]
+    env.close()
+    cfg = dict(CLEARING_CFG, agent={"action_type": "position"})
+    env = emu_bd.EmuAreaClearingVecEnv(num_envs=1, cfg=cfg, layouts=[CLEARING_LAYOUT], sam=True)
+    ora = AreaClearingOracleEnv(cfg=cfg, layouts=[CLEARING_LAYOUT]); ora.configure_env_for_SAM()
+    env.reset(); ora.reset()
+    for pix in (20 * 96 + 48, 48 * 96 + 12, 85 * 96 + 85):
+        compare_step(env, ora, 0, float(pix), env.step(np.array([float(pix)], dtype=np.float32)), state_tol=1e-9)
+    env.close()
+
+
 def test_small_environment_matches_the_oracle(portable_trig):
     """clear_env_small: 12 m room, 8 m clearance square, 18.67 px / m, 542 x 542 grid."""
     cfg = {"env": "clear_env_small", "num_obstacles": 6, "min_obs_dist": 1.2}

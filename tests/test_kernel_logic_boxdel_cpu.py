@@ -94,6 +94,28 @@ def test_delivery_removal_and_position_actions_match_the_oracle(portable_trig):
     env.close()
 
 
+def test_sam_job_type_matches_the_oracle(portable_trig):
+    """``train.job_type: sam`` (box_delivery_env.py:118-147, config.yaml): 96 x 96 observation (``local_map_pixel_width_sam``),
+    the ``rewards_sam`` table and ``inactivity_cutoff_sam``; heading and position actions against the oracle."""
+    lay = [sample_layout(np.random.RandomState(42))]
+    cfg = {"agent": {"action_type": "heading"}, "train": {"job_type": "sam"}}
+    env, ora = _pair(cfg, lay)
+    assert env.local_map_pixel_width == 96 and env.observation_shape == (96, 96, 4) and ora.local_map_pixel_width == 96
+    obs, _ = env.reset(); oobs, _ = ora.reset()
+    assert obs.shape[1:] == (96, 96, 4) and np.array_equal(obs[0], oobs)
+    rng = np.random.default_rng(1)
+    for k in range(6):
+        a = float(np.float32(rng.uniform(-1, 1)))
+        compare_step(env, ora, 0, a, a, state_tol=1e-9)
+    env.close()
+    cfg = dict(DELIVERY_CFG, agent={"action_type": "position"}, train={"job_type": "sam"})
+    env, ora = _pair(cfg, [DELIVERY_LAYOUT])
+    env.reset(); ora.reset()
+    for pix in (20 * 96 + 48, 48 * 96 + 12, 85 * 96 + 85):
+        compare_step(env, ora, 0, float(pix), pix, state_tol=1e-9)
+    env.close()
+
+
 def test_envs_of_a_batch_are_independent(portable_trig):
     lays = [sample_layout(np.random.RandomState(s)) for s in (1, 2)]
     cfg = {"agent": {"action_type": "heading"}}
