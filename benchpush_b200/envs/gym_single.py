@@ -68,6 +68,11 @@ class ShipIceEnvB200:
     def render(self):
         raise NotImplementedError("rendering is out of scope for the batched simulator")
 
+    def update_path(self, new_path):
+        """ship_ice_env.py:373-375 (the lattice-planner baseline calls it every step)."""
+        self._v.update_path(new_path)
+        self.path = new_path
+
     def close(self):
         self._v.close()
 
@@ -217,6 +222,10 @@ class AreaClearingEnvB200(BoxDeliveryEnvB200):
         """area_clearing.py:922-925."""
         self._v.update_path(new_path)
         self.path = new_path
+
+    def activate_demo_mode(self):
+        """area_clearing.py:266-272 prepares keyboard tele-operation of the rendered env: interactive, out of scope."""
+        raise NotImplementedError("demo / tele-operation mode needs the interactive renderer, which the batched simulator does not have")
 
     def _info(self, info):
         n = int(_np(info["n_boxes_left"])[0])

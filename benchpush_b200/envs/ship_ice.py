@@ -321,6 +321,11 @@ class ShipIceVecEnv:
             _lib.check(self._fn("step_host")(self._h, a.ctypes.data, C.byref(o)))
         return hb
 
+    def update_path(self, new_path):
+        """ship_ice_env.py:373-375: a planner hands its current path to the env for the renderer; kept in ``self.path``
+        (there is no renderer here)."""
+        self.path = new_path
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._fn("destroy")(self._h)
