@@ -243,3 +243,45 @@ def test_fp32_build_of_the_kernel_sources_stays_within_tolerance(golden_layouts,
         for e in (A, B, C_):
             np.testing.assert_allclose(-e.out(0)["collision_reward"], w, rtol=1e-7, atol=1e-12)
         prev = cur
+
+
+def test_open_water_and_ragged_batches_match_the_oracle(portable_trig):
+    """Edge cases of the layout input: a trial with NO floes (open water: the ship alone, no pairs, no arbiters) next to a dense
+    field in the same packed batch (ragged floe counts, padded to the largest), stepped together in one warp batch; and a whole
+    open-water episode up to ``terminated`` at the goal line."""
+    dense = generate_experiment(1, 0.5, seed=11)[0]
+    water = {"obstacles": [], "ship_state": dense["ship_state"]}
+    packed = pack_trials([water, dense, water])
+    assert packed.n_floes.tolist()[0] == 0 and packed.n_floes.tolist()[2] == 0 and packed.n_floes[1] > 100
+    E = 3
+    emu = Emu(E, packed, SHIP_VERTS, pmax=8 * (packed.max_floes + 1), lmax=2 * (packed.max_floes + 1))
+    oras = [ShipIceOracleEnv({"concentration": 0.5}, experiment=unpack_trials(packed)[l:l + 1], order_mode=1) for l in range(E)]
+    for e in range(E):
+        emu.reset(e, e)
+        obs, _ = oras[e].reset()
+        assert np.array_equal(oras[e].space.state(), emu.bodies(e, e))
+        assert np.array_equal(obs, emu.render_obs(e, True))
+    assert emu.scal(0)["n_pairs"] == 0 and emu.scal(0)["n_order"] == 0
+    rng = np.random.default_rng(5)
+    for k in range(3):
+        acts = rng.uniform(-1, 1, E).astype(np.float32)
+        emu.step_batch(0, acts)
+        for e in range(E):
+            obs, r, term, _, info = oras[e].step(float(acts[e]))
+            assert np.array_equal(oras[e].space.state(), emu.bodies(e, e)), (k, e)
+            out = emu.out(e)
+            assert out["status"] == 0 and bool(out["terminated"]) == bool(term)
+            np.testing.assert_allclose(out["reward"], r, rtol=1e-9, atol=1e-7)
+            assert np.array_equal(obs, emu.render_obs(e, False)), (k, e)
+    # open water to the goal: straight ahead, terminates when the ship crosses goal_y, work stays exactly 0
+    steps = 0
+    while True:
+        obs, r, term, _, info = oras[0].step(0.0)
+        emu.step(0, 0.0)
+        steps += 1
+        out = emu.out(0)
+        assert np.array_equal(oras[0].space.state(), emu.bodies(0, 0))
+        assert bool(out["terminated"]) == bool(term) and out["total_work"] == 0.0 == info["total_work"]
+        if term or steps > 400:
+            break
+    assert term and steps < 400
