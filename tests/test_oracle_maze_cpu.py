@@ -199,3 +199,27 @@ def test_maze_metric_matches_reference_formulas():
     np.testing.assert_allclose(met.efficiency_scores, ora.efficiency_scores, rtol=1e-12)
     np.testing.assert_allclose(met.effort_scores, ora.effort_scores, rtol=1e-12)
     np.testing.assert_allclose(met.rewards, ora.rewards, rtol=1e-12)
+
+
+def test_emulated_maze_without_obstacles_and_with_ragged_counts(portable_trig):
+    """Edge cases of the layout input: a maze with NO movable obstacle and one with two, in the same handle (ragged counts,
+    padded to the largest): reset image, per-step state triple, status and images against the oracle."""
+    from tests.emu.emu import MazeEmu
+    layouts = [[], [[11.3, 5.2], [11.0, 7.5]]]
+    emu = MazeEmu(2, layouts)
+    for ep in (0, 1):
+        env = MazeNamoOracleEnv(layouts=layouts[ep:ep + 1], order_mode=1)
+        obs, info = env.reset()
+        emu.reset(ep, ep)
+        assert len(info["obs"]) == len(layouts[ep])
+        assert np.array_equal(obs, emu.render_obs(ep, True))
+        rng = np.random.default_rng(ep)
+        for k in range(5):
+            a = float(np.float32(rng.uniform(-0.3, 0.3)))
+            obs, r, term, _, info = env.step(a)
+            emu.step(ep, a)
+            o = emu.out(ep)
+            assert o["status"] == 0 and bool(o["terminated"]) == term
+            assert (o["sx"], o["sy"], o["sa"]) == tuple(float(x) for x in info["state"])
+            np.testing.assert_allclose(o["reward"], r, rtol=1e-9, atol=1e-9)
+            assert np.array_equal(obs, emu.render_obs(ep, False)), (ep, k)
