@@ -78,3 +78,46 @@ def test_pack_unpack_roundtrip_and_generator_statistics():
     # determinism
     p2 = pack_trials(generate_experiment(2, 0.5, seed=11))
     assert np.array_equal(p.verts, p2.verts)
+
+
+def test_create_rejects_bad_arguments_before_touching_cuda():
+    """Error behaviour of the C ABI (include/benchpush_b200.h: negative status + bp_last_error(), nothing thrown, nothing
+    allocated): argument checks come first, so they are observable on a machine without a GPU.  The reference's counterpart is a
+    Python exception from the env constructor; the ctypes mirror turns the status into BenchPushError."""
+    L = _lib.lib()
+    L.bp_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p()
+    INVALID = -1
+    # ship-ice
+    cfg = _lib.ShipIceConfig(); L.bp_shipice_default_config(ctypes.byref(cfg))
+    assert L.bp_shipice_create(None, ctypes.byref(h)) == INVALID and b"null" in L.bp_last_error()
+    assert L.bp_shipice_create(ctypes.byref(cfg), None) == INVALID
+    for field, bad in (("n_envs", 0), ("n_envs", -3), ("max_floes", 0), ("max_floes", 60001), ("n_ship_verts", 2), ("n_ship_verts", 33),
+                       ("steps", 0), ("iterations", 0), ("dt", 0.0)):
+        c = _lib.ShipIceConfig(); L.bp_shipice_default_config(ctypes.byref(c))
+        if c.n_envs <= 0: c.n_envs = 4
+        if c.max_floes <= 0: c.max_floes = 100
+        setattr(c, field, bad)
+        assert L.bp_shipice_create(ctypes.byref(c), ctypes.byref(h)) == INVALID, field
+        assert L.bp_last_error(), field
+        with pytest.raises(_lib.BenchPushError):
+            _lib.check(INVALID)
+    # maze-NAMO
+    m = _lib.MazeConfig(); L.bp_maze_default_config(ctypes.byref(m), 1)
+    assert L.bp_maze_create(None, ctypes.byref(h)) == INVALID
+    for field, bad in (("n_envs", 0), ("max_boxes", -1), ("max_boxes", 4097), ("n_walls", -1), ("n_robot_verts", 2), ("steps", 0), ("m_to_pix_scale", 0)):
+        c = _lib.MazeConfig(); L.bp_maze_default_config(ctypes.byref(c), 1)
+        if c.n_envs <= 0: c.n_envs = 4
+        setattr(c, field, bad)
+        assert L.bp_maze_create(ctypes.byref(c), ctypes.byref(h)) == INVALID, field
+    # room envs
+    from benchpush_b200.envs.box_delivery import BoxDelConfig, bind
+    bind(L)
+    for field, bad in (("n_envs", 0), ("num_boxes", 0), ("num_boxes", 10 ** 6), ("action_type", 3), ("action_type", -1)):
+        c = BoxDelConfig(); L.bp_boxdel_default_config(ctypes.byref(c))
+        if c.n_envs <= 0: c.n_envs = 4
+        if c.num_boxes <= 0: c.num_boxes = 10
+        setattr(c, field, bad)
+        assert L.bp_boxdel_create(ctypes.byref(c), ctypes.byref(h)) == INVALID, field
+    assert L.bp_boxdel_create(None, ctypes.byref(h)) == INVALID
+    assert not h.value                                             # no handle was ever produced
