@@ -1,6 +1,6 @@
 """SURVEY.md appendix D, the parity checklist of reference quirks, item by item — the ones that have no dedicated test elsewhere.
 Each test names the quirk (D<n>), the reference lines, and checks the oracle and the kernel sources (CPU emulation, tests/emu)
-for exactly that behaviour.  (D2, D4, D7, D8, D10, D11, D13, D17, D20 are asserted in the env / metric / pin tests next to the
+for exactly that behaviour.  (D4, D7, D8, D10, D11, D13, D17, D20 are asserted in the env / metric / pin tests next to the
 code they concern; D3, D5, D6, D19 by the pins of tests/test_ref_pins_cpu.py, which compare with the reference's own modules.
 D15 needs nothing: the ``move_sign`` expression of box_delivery_env.py:932-935 only feeds ``robot_new_position`` /
 ``robot_new_heading`` (:919-938), which the reference never reads again — the robot is driven by the DP controller.)"""
@@ -130,3 +130,44 @@ def test_d21_d22_registry_limits_are_data_and_reset_ignores_the_seed(portable_tr
     o2, i2 = env.reset(seed=7)
     assert np.array_equal(o1, np.array(o2)) and np.array_equal(s1, np.array(i2["state"]))
     env.close()
+
+
+# ------------------------------------------------------------------ D1 / D2: velocity direction frozen per env step, yaw limit zeroes w only
+def test_d1_d2_velocity_direction_is_frozen_and_the_yaw_limit_only_zeroes_omega(portable_trig):
+    """ship_ice_env.py:270-274 sets the ship's velocity VECTOR once per env step from the heading at step start, while the heading
+    keeps integrating through the 400 substeps: in open water the ship moves on a straight segment along its initial heading and
+    ends the step turned by omega * dt.  :284-286: past the yaw limits (theta <= 0 or >= pi) the angular velocity is zeroed, theta
+    itself is never clamped, and the next env step sets omega again."""
+    from benchpush_b200.layouts import generate_experiment, pack_trials, unpack_trials
+    from oracle.ship_ice_oracle import ShipIceOracleEnv
+    from tests.conftest import SHIP_VERTS
+    from tests.emu.emu import Emu
+    t = generate_experiment(1, 0.1, seed=3)[0]
+    packed = pack_trials([{"obstacles": [], "ship_state": t["ship_state"]}])
+    emu = Emu(1, packed, SHIP_VERTS)
+    ora = ShipIceOracleEnv({"concentration": 0.1}, experiment=unpack_trials(packed), order_mode=1)
+    ora.reset(); emu.reset(0, 0)
+    ship = ora.space.state().shape[0] - 1
+    row = lambda: emu.bodies(0, 0)[ship]
+    assert np.array_equal(ora.space.state(), emu.bodies(0, 0))
+    x0, y0, th0 = row()[:3]
+    ora.step(1.0); emu.step(0, 1.0)
+    assert np.array_equal(ora.space.state(), emu.bodies(0, 0))
+    x1, y1, th1 = row()[:3]
+    dt, speed = float(ora.cfg["dt"]), float(ora.cfg["target_speed"])
+    # straight segment along the heading at step start, although the heading itself has turned by max_yaw_rate_step * dt
+    assert abs(np.arctan2(y1 - y0, x1 - x0) - th0) < 1e-12
+    assert abs(np.hypot(x1 - x0, y1 - y0) - speed * dt) < 1e-9
+    assert abs((th1 - th0) - ora.max_yaw_rate_step * dt) < 1e-9 and th1 - th0 > 0.05
+    # drive the heading across pi: omega is zeroed in that substep (theta stops a little PAST the limit, unclamped) ...
+    for k in range(40):
+        ora.step(1.0); emu.step(0, 1.0)
+        assert np.array_equal(ora.space.state(), emu.bodies(0, 0)), k
+        if row()[2] >= np.pi:
+            break
+    th_lim = row()[2]
+    assert th_lim >= np.pi and th_lim - np.pi < ora.max_yaw_rate_step * dt / 400 * 1.0001 and row()[5] == 0.0
+    # ... and the next env step sets omega again: one more substep of turning before it is zeroed again, theta keeps growing
+    ora.step(1.0); emu.step(0, 1.0)
+    assert np.array_equal(ora.space.state(), emu.bodies(0, 0))
+    assert row()[2] > th_lim and row()[5] == 0.0
