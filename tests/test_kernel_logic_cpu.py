@@ -285,3 +285,33 @@ def test_open_water_and_ragged_batches_match_the_oracle(portable_trig):
         if term or steps > 400:
             break
     assert term and steps < 400
+
+
+def test_emulated_spfa_on_degenerate_and_random_shapes(golden_layouts):
+    """Edge cases of the map input: single cell, single row / column, nothing free, everything free, a walled-off source — and 40
+    random maps of random shapes: distances of both kernels bit-identical to the port of main.cpp, parents of the
+    reference-order kernel too, parents of the frontier kernel valid (a neighbour that attains the minimum)."""
+    emu = Emu(1, golden_layouts["c10_t0"], SHIP_VERTS)
+    rng = np.random.default_rng(123)
+    cases = [(np.ones((1, 1), bool), (0, 0)), (np.ones((1, 17), bool), (0, 5)), (np.ones((23, 1), bool), (22, 0)),
+             (np.zeros((4, 6), bool), (1, 1)), (np.ones((9, 13), bool), (8, 12))]
+    walled = np.ones((7, 7), bool); walled[2, 2:5] = walled[4, 2:5] = walled[2:5, 2] = walled[2:5, 4] = False
+    cases.append((walled, (3, 3)))
+    for _ in range(40):
+        H, W = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        m = rng.random((H, W)) > rng.uniform(0.1, 0.6)
+        cases.append((m, (int(rng.integers(0, H)), int(rng.integers(0, W)))))
+    s2 = np.float32(np.sqrt(np.float32(2.0)))
+    for m, src in cases:
+        rd, rp = cpo.spfa(m, src)
+        d1, p1 = emu.spfa(m, src)
+        d2, p2 = emu.spfa_serial(m, src)
+        assert np.array_equal(rd, d1) and np.array_equal(rd, d2), (m.shape, src)
+        assert np.array_equal(rp, p2), (m.shape, src)
+        H, W = m.shape
+        for i, j in zip(*np.nonzero(d1 > 0)):                      # frontier kernel: any minimising neighbour is a valid parent
+            pi, pj = divmod(int(p1[i, j]), W)
+            assert m[pi, pj] and max(abs(pi - i), abs(pj - j)) == 1
+            w = s2 if (pi != i and pj != j) else np.float32(1.0)
+            assert np.float32(d1[pi, pj] + w) == d1[i, j]
+    assert cpo.spfa(walled, (3, 3))[0].sum() == 0                   # the walled-off source reaches nothing: all zeros (D18)
